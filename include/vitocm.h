@@ -1,0 +1,187 @@
+/* vitocm.h -- C ABI of libvitocm.so, the B200 (sm_100a) implementation of the ViT-OCM
+ * attention-map / sliding-window segmentation hot path.
+ *
+ * The reference (linum-uqam/ViT-OCM-WMSegmentation) has NO FFI, plugin or operator interface:
+ * its boundary for this path is the Python nn.Module surface of
+ * Self-supervised_segmentation/dino/vision_transformer.py (abbrev. vit.py) plus a handful of
+ * post-processing functions.  Each entry point below therefore cites
+ * the reference Python function(s) whose arithmetic it replaces; the Python mirror of that
+ * surface (same class / function names and arguments) lives in vit-ocm-wmsegmentation_b200/
+ * and binds these symbols with ctypes.
+ *
+ * Conventions: every function returns 0 on success or a negative vitocm_status; the message of
+ * the last failure on the calling thread is vitocm_last_error().  No exception crosses the
+ * ABI.  All data pointers are DEVICE pointers unless the parameter is named host_*; tensors
+ * are dense row-major.  `stream` is a cudaStream_t passed as void*.  No hidden device
+ * allocation on the forward paths: the caller passes a workspace sized by
+ * vitocm_workspace_bytes().  A handle is thread-compatible (one thread at a time).
+ */
+#ifndef VITOCM_H_
+#define VITOCM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITOCM_VERSION 100
+
+typedef enum vitocm_status {
+  VITOCM_OK = 0,
+  VITOCM_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  VITOCM_ERR_CUDA = -2,      /* CUDA runtime or driver error */
+  VITOCM_ERR_STATE = -3,     /* weights missing / not finalized */
+  VITOCM_ERR_WORKSPACE = -4  /* workspace too small */
+} vitocm_status;
+
+typedef enum vitocm_precision {
+  VITOCM_BF16 = 0, /* bf16 tensor-core operands, fp32 accumulate / residual / LN / softmax statistics */
+  VITOCM_FP32 = 1  /* fp32-parity mode: every operand a bf16 (hi, lo) pair, products hi*hi+hi*lo+lo*hi */
+} vitocm_precision;
+
+/* Constructor constants of VisionTransformer (vit.py:137-139) and of the factories
+ * vit_tiny/small/base (vit.py:259-279).  head_dim must be 64. */
+typedef struct vitocm_config {
+  int embed_dim;
+  int depth;
+  int num_heads;
+  int mlp_hidden;
+  int patch_size;
+  int in_chans;
+  float ln_eps;
+  float qk_scale; /* head_dim ** -0.5 unless qk_scale was given (vit.py:70-71) */
+  int precision;  /* vitocm_precision */
+} vitocm_config;
+
+typedef struct vitocm_engine vitocm_engine;
+
+int vitocm_version(void);
+const char* vitocm_last_error(void);
+
+int vitocm_create(const vitocm_config* cfg, vitocm_engine** out);
+int vitocm_destroy(vitocm_engine* e);
+
+/* Replaces nn.Module.load_state_dict for the hot path (SSS/eval.py:67-77): `name` is a
+ * state-dict key (cls_token, pos_embed, mask_token, patch_embed.proj.{weight,bias},
+ * blocks.{i}.{norm1,norm2}.{weight,bias}, blocks.{i}.attn.{qkv,proj}.{weight,bias},
+ * blocks.{i}.mlp.{fc1,fc2}.{weight,bias}, norm.{weight,bias}); host_data is fp32, `numel`
+ * elements.  vitocm_finalize_weights repacks them into the kernels' layouts (bf16 hi/lo,
+ * transposed patch filter) and must be called after the last load and before any forward. */
+int vitocm_load_weight(vitocm_engine* e, const char* name, const float* host_data, int64_t numel);
+int vitocm_finalize_weights(vitocm_engine* e);
+
+/* Bytes of workspace needed by the forward entry points for chunks of `chunk_tiles` images of
+ * n_tokens tokens each. */
+size_t vitocm_workspace_bytes(const vitocm_engine* e, int chunk_tiles, int n_tokens);
+
+/* HOT PATH.  VisionTransformer.get_last_selfattention(x)[:, :, 0, :] (vit.py:239-246), i.e. the
+ * CLS query row per head that SSS/utils.py:232 (query = 0) slices out of
+ * get_intermediate_feat(x, n=1) (vit.py:225-237; callers SSS/eval.py:136, SSS/sw_processing.py:239).
+ * x [B][C][H][W] fp32; pos [1 + (H/p)(W/p)][D] fp32 = (interpolated) position table (vit.py:176-196);
+ * out_rows [B][heads][N] fp32.  Internally: patch embedding, depth-1 full blocks, and for the last
+ * block only LN1 -> K projection -> softmax(q_cls K^T).  Processes the batch in chunks that fit ws. */
+int vitocm_forward_cls_attn(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, float* out_rows,
+                            void* ws, size_t ws_bytes, int chunk_tiles, void* stream);
+
+/* prepare_tokens (vit.py:198-209): patch embedding + CLS + position add -> X [B][N][D] fp32.
+ * mask [B][n] fp32 in {0,1} or NULL: SimMIM mask-token mixing (SSS/model.py:31-33). */
+int vitocm_prepare_tokens(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const float* mask,
+                          float* X, void* stream);
+
+/* Block.forward (vit.py:106-114) in place on X [B][N][D] fp32 for block index `layer`. */
+int vitocm_block_forward(vitocm_engine* e, int layer, float* X, int B, int n_tokens, void* ws, size_t ws_bytes,
+                         void* stream);
+
+/* Attention probabilities of block `layer` for input X (vit.py:78-84, the `attn` that
+ * Block.forward(return_attention=True) returns): attn [B][heads][N][N] fp32; qkv_out
+ * [B*N][3D] fp32 (the pre-permute qkv activation, vit.py:80) -- required scratch/output. */
+int vitocm_block_attn_probs(vitocm_engine* e, int layer, const float* X, int B, int n_tokens, float* attn,
+                            float* qkv_out, void* ws, size_t ws_bytes, void* stream);
+
+/* self.norm (vit.py:215, :234): out [M][D] fp32 = LayerNorm(X [M][D]). */
+int vitocm_final_norm(vitocm_engine* e, const float* X, float* out, int M, void* stream);
+
+/* ---- post-processing (SSS/utils.py, SSS/eval.py, SSS/sw_processing.py) ---- */
+
+/* rows [T][heads][N] -> lowres [T][N-1]: head mean of the CLS row without its CLS column
+ * (SSS/utils.py:232-233 + np.mean at SSS/eval.py:142).  mode 1 also applies the per-tile
+ * (a-min)/(max-min)*255 of SSS/sw_processing.py:253-254. */
+int vitocm_head_mean(const float* rows, float* lowres, int T, int heads, int n_tokens, int mode, void* stream);
+
+/* SSS/eval.py:169-173 + utils.threshold (SSS/utils.py:62-115) for T images: lowres [T][lh][lw],
+ * x [T][C][S][S] fp32 in [0,1]; masks [T][3][S][S] u8 = (th "ours", th2 "otsu", th3 "heatmap_threshold");
+ * thresholds [T][3] int32; att_out [T][S][S] fp32 or NULL (the bilinearly upsampled map).
+ * att_in [T][S][S] fp32 (optional): a caller-supplied full-resolution attention map, used instead of
+ * upsampling lowres -- this is the exact signature of utils.threshold(img, attention).
+ * img_in [T][S][S] u8 (optional): the PIL "L" image, used instead of deriving it from x. */
+int vitocm_tile_threshold(const float* lowres, const float* x, int T, int C, int S, int lh, int lw, uint8_t* masks,
+                          int* thresholds, float* att_out, const float* att_in, const uint8_t* img_in, void* stream);
+
+/* sliding_window (SSS/sw_processing.py:151-163) + ToTensor for tiles t0..t0+T-1 of an n x n grid:
+ * mosaic u8 gray [mos_h][pitch] -> x [T][C][W][W] fp32. */
+int vitocm_extract_tiles(const uint8_t* mosaic, int mos_h, int mos_w, int64_t pitch, int n, int W, int S, int t0, int T,
+                         int C, float* x, void* stream);
+
+/* concat_crops on the uint8 image crops (SSS/sw_processing.py:113-149 at :225) for output rows
+ * [y_begin, y_end): out [E][E] u8 (full-size buffer, E = (n-1) S + W).  wtab = host-computed
+ * numpy.linspace(1, 0, W - S) copied to the device (double[W - S]). */
+int vitocm_stitch_gray(const uint8_t* mosaic, int mos_h, int mos_w, int64_t pitch, int n, int W, int S,
+                       const double* wtab, int y_begin, int y_end, uint8_t* out, void* stream);
+
+/* Stitched attention map = resize pair (SSS/sw_processing.py:255-257) + concat_crops (:259) of the
+ * per-tile maps lowres [n*n][lh][lw]; pass 1 of sw_processing.threshold (:43): global min / max over
+ * rows [y_begin, y_end) accumulated into minmax_ord[2] (order-preserving int keys; initialise with
+ * vitocm_minmax_init).  map_out [E][E] fp32 or NULL.  map_in [E][E] fp32 (optional, also on the two
+ * passes below): a caller-supplied stitched map used instead of stitching lowres -- the exact
+ * signature of sw_processing.threshold(img, attention). */
+int vitocm_minmax_init(int* minmax_ord, void* stream);
+int vitocm_stitch_minmax(const float* lowres, int n, int W, int S, int lh, int lw, const double* wtab, int y_begin,
+                         int y_end, int* minmax_ord, float* map_out, const float* map_in, void* stream);
+
+/* pass 2 (SSS/sw_processing.py:44-48): 256-bin histograms of result = u8(img*att), of the stitched
+ * gray image and of att_u8, accumulated into hists[3][256] (uint64; caller zeroes). */
+int vitocm_stitch_hist(const float* lowres, int n, int W, int S, int lh, int lw, const double* wtab,
+                       const uint8_t* gray, const int* minmax_ord, int y_begin, int y_end, uint64_t* hists,
+                       const float* map_in, void* stream);
+
+/* cv2.threshold(..., THRESH_OTSU) threshold selection for nhist histograms [nhist][256] uint64. */
+int vitocm_otsu(const uint64_t* hists, int nhist, int* thresholds, void* stream);
+
+/* pass 3 (SSS/sw_processing.py:54-61): masks for rows [y_begin, y_end), each [(y_end-y_begin)][E] u8
+ * (any may be NULL): th = result > thr[0], th2 = gray > thr[1], th3 = att_u8 > thr[2]. */
+int vitocm_stitch_mask(const float* lowres, int n, int W, int S, int lh, int lw, const double* wtab,
+                       const uint8_t* gray, const int* minmax_ord, const int* thr, int y_begin, int y_end, uint8_t* th,
+                       uint8_t* th2, uint8_t* th3, const float* map_in, void* stream);
+
+/* concat_crops(crops, stride, window_size) (SSS/sw_processing.py:113-149) on full-resolution crops:
+ * float32 [n*n][W][W] -> out [E][E]; uint8 HWC [n*n][W][W][C] -> out [E][E][C]. */
+int vitocm_concat_crops_f32(const float* crops, int n, int W, int S, const double* wtab, float* out, void* stream);
+int vitocm_concat_crops_u8(const uint8_t* crops, int n, int W, int S, int C, const double* wtab, uint8_t* out,
+                           void* stream);
+/* sliding_window(image, stride, window_size) (SSS/sw_processing.py:151-163) on a uint8 HWC image:
+ * ny x nx windows at stride S -> crops [ny*nx][W][W][C], zero padded outside the image. */
+int vitocm_crop_u8(const uint8_t* img, int img_h, int img_w, int C, int ny, int nx, int W, int S, uint8_t* crops,
+                   void* stream);
+
+/* ---- kernel-level entry points used by the tests / the bench roofline leg ---- */
+
+/* C = epilogue(A[M][K] . B[N][K]^T): A, B bf16 device (split: [rows][2K] = hi|lo); epilogue enum:
+ * 0 bias->bf16, 1 bias+gelu->bf16, 2 bias + in-place fp32 residual add, 3 bias->fp32. */
+int vitocm_gemm(vitocm_engine* e, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
+                int split_in, int epilogue, const float* bias, void* out, int64_t ldo, int split_out, int lo_off,
+                void* stream);
+/* ctx = MHSA(qkv) for B images of n_tokens tokens: qkv bf16 [B*N][ld], ctx bf16 [B*N][ldo]. */
+int vitocm_attention(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo,
+                     void* stream);
+/* LayerNorm rows of X [M][D] fp32 with affine (gamma, beta) -> out bf16 [M][ldo] (hi | lo if split). */
+int vitocm_layernorm(vitocm_engine* e, const float* X, const float* gamma, const float* beta, void* out_bf16,
+                     int64_t ldo, int split, int lo_off, int M, void* stream);
+/* number of kernels launched by this library on the calling process since load (gpu_launches) */
+int64_t vitocm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITOCM_H_ */

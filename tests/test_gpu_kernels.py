@@ -1,0 +1,135 @@
+"""GPU (B200): each hand-written kernel against a plain fp32 torch statement of the same op,
+called through the C ABI."""
+import math
+
+import pytest
+import torch
+
+import vitocm_b200 as vob
+from gpu_util import attention, attention_reference, gemm, make_engine, split_bf16
+from vitocm_b200._lib import check, cur_stream, ptr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+@pytest.fixture(scope="module")
+def engine():
+    return make_engine()
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(shape, generator=g, device="cuda") * scale
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 256, 128), (785, 1152, 384), (1570, 1536, 384),
+                                   (785, 384, 1536), (200, 192, 192), (77, 64, 64), (2355, 320, 384)])
+def test_gemm_bias_bf16(engine, M, N, K):
+    A = _rand((M, K), 1).to(torch.bfloat16)
+    B = _rand((N, K), 2, 0.05).to(torch.bfloat16)
+    bias = _rand((N,), 3, 0.1)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    gemm(engine, A, B, M, N, K, 0, 0, bias, out, N)
+    ref = A.float() @ B.float().T + bias
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item() + 1e-3, err
+    assert torch.isfinite(out.float()).all()
+
+
+def test_gemm_gelu_epilogue(engine):
+    M, N, K = 785, 1536, 384
+    A = _rand((M, K), 4).to(torch.bfloat16)
+    B = _rand((N, K), 5, 0.08).to(torch.bfloat16)
+    bias = _rand((N,), 6, 0.2)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    gemm(engine, A, B, M, N, K, 0, 1, bias, out, N)
+    ref = torch.nn.functional.gelu(A.float() @ B.float().T + bias)
+    assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
+
+
+def test_gemm_residual_and_f32_epilogues(engine):
+    M, N, K = 1000, 384, 1536
+    A = _rand((M, K), 7).to(torch.bfloat16)
+    B = _rand((N, K), 8, 0.03).to(torch.bfloat16)
+    bias = _rand((N,), 9, 0.1)
+    resid = _rand((M, N), 10)
+    ref = resid + A.float() @ B.float().T + bias
+    x = resid.clone()
+    gemm(engine, A, B, M, N, K, 0, 2, bias, x, N)
+    assert (x - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+    y = torch.empty(M, N, device="cuda")
+    gemm(engine, A, B, M, N, K, 0, 3, bias, y, N)
+    assert (y - (ref - resid)).abs().max().item() <= 2e-4 * ref.abs().max().item()
+
+
+def test_gemm_split_precision_is_fp32_grade(engine):
+    M, N, K = 785, 384, 384
+    A32, B32 = _rand((M, K), 11), _rand((N, K), 12, 0.05)
+    bias = _rand((N,), 13, 0.1)
+    A, B = split_bf16(A32), split_bf16(B32)
+    y = torch.empty(M, N, device="cuda")
+    gemm(engine, A, B, M, N, K, 1, 3, bias, y, N)
+    ref = (A32.double() @ B32.double().T + bias.double()).float()
+    rel = ((y - ref).abs().max() / ref.abs().max()).item()
+    assert rel < 2e-5, rel
+    # split output: hi | lo reconstructs the fp32 value
+    out = torch.empty(M, 2 * N, device="cuda", dtype=torch.bfloat16)
+    gemm(engine, A, B, M, N, K, 1, 0, bias, out, 2 * N, 1, N)
+    rec = out[:, :N].float() + out[:, N:].float()
+    assert ((rec - ref).abs().max() / ref.abs().max()).item() < 5e-5
+
+
+def test_layernorm(engine):
+    lib = vob._lib.load_library()
+    M, D = 1000, 128
+    x = _rand((M, D), 14, 3.0) + 0.5
+    g, b = _rand((D,), 15) * 0.1 + 1, _rand((D,), 16) * 0.1
+    out = torch.empty(M, 2 * D, device="cuda", dtype=torch.bfloat16)
+    check(lib.vitocm_layernorm(engine, ptr(x), ptr(g), ptr(b), ptr(out), 2 * D, 1, D, M, cur_stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (D,), g, b, 1e-6)
+    assert (out[:, :D].float() - ref).abs().max().item() < 2e-2
+    assert ((out[:, :D].float() + out[:, D:].float()) - ref).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("B,H,N", [(1, 2, 17), (2, 2, 65), (1, 2, 128), (1, 2, 129), (2, 2, 300), (1, 6, 785), (3, 2, 37)])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_attention(B, H, N, precision):
+    eng = make_engine(embed_dim=64 * H, heads=H, precision=precision)
+    D = 64 * H
+    q, k, v = (_rand((B, H, N, 64), s, sc) for s, sc in ((20, 1.0), (21, 1.0), (22, 1.0)))
+    parts = 2 if precision else 1
+    # [B*N, 3D] layout with columns [3][H][64]
+    qkv32 = torch.stack([q, k, v], 0).permute(1, 3, 0, 2, 4).reshape(B * N, 3 * D).contiguous()
+    if precision:
+        qkv = split_bf16(qkv32)
+        qr = kr = vr = None
+        src = qkv[:, :3 * D].float() + qkv[:, 3 * D:].float()
+    else:
+        qkv = qkv32.to(torch.bfloat16).contiguous()
+        src = qkv.float()
+    s5 = src.reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = attention_reference(s5[0], s5[1], s5[2], 0.125).reshape(B * N, D)
+    ctx = torch.full((B * N, D * parts), float("nan"), device="cuda", dtype=torch.bfloat16)
+    attention(eng, qkv, B, N, ctx)
+    got = ctx[:, :D].float() + (ctx[:, D:].float() if precision else 0)
+    err = (got - ref).abs().max().item()
+    tol = 3e-5 if precision else 2e-2
+    assert err <= tol * max(1.0, ref.abs().max().item()), (err, ref.abs().max().item())
+    vob._lib.load_library().vitocm_destroy(eng)
+
+
+def test_launch_counter_counts():
+    before = vob._lib.launch_count()
+    eng = make_engine()
+    A = torch.zeros(128, 64, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(128, 64, device="cuda", dtype=torch.bfloat16)
+    gemm(eng, A, A[:64].contiguous(), 128, 64, 64, 0, 0, None, out, 64)
+    assert vob._lib.launch_count() == before + 1

@@ -1,0 +1,139 @@
+"""GPU (B200): post-processing / stitching kernels against the golden vectors and the oracle.
+Integer and byte outputs must be bit-exact; float32 stitched maps must be bit-exact too."""
+import numpy as np
+import pytest
+import torch
+
+import vitocm_b200 as vob
+from conftest import load_golden
+from gpu_util import build_model
+from oracle import post_oracle as PO
+from oracle import vit_oracle as VO
+from vitocm_b200 import sw_processing as sw
+from vitocm_b200 import utils as vu
+from vitocm_b200._lib import check, cur_stream, ptr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_otsu_kernel_matches_cv2_goldens():
+    g = load_golden("cv2_ops.npz")
+    hists = np.stack([np.bincount(img.ravel(), minlength=256) for img in g["otsu_imgs"]]).astype(np.int64)
+    d = torch.from_numpy(hists).cuda()
+    thr = torch.empty(len(hists), dtype=torch.int32, device="cuda")
+    check(vob._lib.load_library().vitocm_otsu(ptr(d), len(hists), ptr(thr), cur_stream()))
+    assert np.array_equal(thr.cpu().numpy(), g["otsu_t"])
+    # degenerate histograms
+    deg = torch.zeros(3, 256, dtype=torch.int64, device="cuda")
+    deg[1, 17] = 100
+    deg[2, 0] = 5
+    deg[2, 255] = 5
+    t = torch.empty(3, dtype=torch.int32, device="cuda")
+    check(vob._lib.load_library().vitocm_otsu(ptr(deg), 3, ptr(t), cur_stream()))
+    exp = [PO.otsu_from_hist(h) for h in deg.cpu().numpy()]
+    assert t.cpu().tolist() == exp
+
+
+def test_threshold_flavours_bit_exact():
+    g = load_golden("threshold.npz")
+    th, th2, th3 = sw.threshold(g["img"], g["att"], save=False)
+    assert np.array_equal(th, g["sw_th"]) and np.array_equal(th2, g["sw_th2"]) and np.array_equal(th3, g["sw_th3"])
+    th, th2, th3 = vu.threshold(g["img"], g["att"], save=False)
+    assert np.array_equal(th, g["ut_th"]) and np.array_equal(th2, g["ut_th2"]) and np.array_equal(th3, g["ut_th3"])
+    # flat attention: min_max_normalize returns its input
+    flat = np.full((16, 16), 0.5, np.float32)
+    img = np.random.RandomState(0).randint(0, 256, (16, 16)).astype(np.uint8)
+    for fn, orc in ((sw.threshold, PO.threshold_sw), (vu.threshold, PO.threshold_utils)):
+        got = fn(img, flat, save=False)
+        exp = orc(img, flat)
+        assert all(np.array_equal(a, b) for a, b in zip(got, exp[:3]))
+
+
+@pytest.mark.parametrize("name,W,S,n", [("w32s16n4", 32, 16, 4), ("w48s16n3", 48, 16, 3), ("w24s8n5", 24, 8, 5), ("w32s16n1", 32, 16, 1)])
+def test_concat_crops_and_sliding_window_bit_exact(name, W, S, n):
+    g = load_golden("stitch.npz")
+    out = sw.concat_crops(list(g[name + "/tiles"]), S, W)
+    assert out.dtype == np.float32 and np.array_equal(out, g[name + "/out"])
+    if name + "/img" in g:
+        img = g[name + "/img"]
+        rgb = np.stack([img] * 3, -1)
+        crops = sw.sliding_window(rgb, S, W)
+        ocrops = PO.sliding_window(rgb, S, W)
+        assert len(crops) == len(ocrops) == n * n and all(np.array_equal(a, b) for a, b in zip(crops, ocrops))
+        st = sw.concat_crops(crops, S, W)
+        assert np.array_equal(st[..., 0], g[name + "/gray_stitched"])
+        # device-resident variant used by MosaicSegmenter
+        d = torch.from_numpy(img).cuda()
+        E = (n - 1) * S + W
+        gray = torch.zeros(E, E, dtype=torch.uint8, device="cuda")
+        wtab = sw._wtab(W, S, d.device)
+        check(vob._lib.load_library().vitocm_stitch_gray(ptr(d), img.shape[0], img.shape[1], d.stride(0), n, W, S, ptr(wtab), 0, E,
+                                                         ptr(gray), cur_stream()))
+        assert np.array_equal(gray.cpu().numpy(), g[name + "/gray_stitched"])
+
+
+def test_sliding_window_ragged_image_zero_pads():
+    rng = np.random.RandomState(1)
+    img = rng.randint(0, 256, (100, 100, 3)).astype(np.uint8)       # 100 is not a multiple of the stride
+    got = sw.sliding_window(img, 16, 48)
+    exp = PO.sliding_window(img, 16, 48)
+    assert len(got) == len(exp) and all(np.array_equal(a, b) for a, b in zip(got, exp))
+    assert sw.sliding_window(np.zeros((20, 20), np.uint8), 16, 48) == []
+
+
+def test_head_mean_and_tile_threshold_vs_oracle():
+    rng = np.random.RandomState(2)
+    T, H, S, p = 5, 6, 64, 8
+    n = (S // p) ** 2
+    rows = rng.rand(T, H, n + 1).astype(np.float32)
+    rows /= rows.sum(-1, keepdims=True)
+    x = VO.synthetic_tile(S, seed=11, batch=T)
+    d_rows = torch.from_numpy(rows).cuda()
+    low = vob.head_mean_maps(d_rows).cpu().numpy()
+    for t in range(T):
+        a, _ = PO.compute_attention_from_rows(rows[t], S // p, S // p, p)
+        assert np.array_equal(low[t].reshape(S // p, S // p), np.mean(a, axis=0)[::p, ::p])
+    low255 = vob.head_mean_maps(d_rows, per_tile_minmax255=True).cpu().numpy()
+    for t in range(T):
+        assert np.array_equal(PO.resize_linear(low255[t].reshape(8, 8), (S, S)), PO.sw_tile_map(rows[t], S, p))
+    masks = torch.empty(T, 3, S, S, dtype=torch.uint8, device="cuda")
+    thr = torch.empty(T, 3, dtype=torch.int32, device="cuda")
+    att = torch.empty(T, S, S, device="cuda")
+    lowd = torch.from_numpy(low).cuda()
+    check(vob._lib.load_library().vitocm_tile_threshold(ptr(lowd), ptr(x.cuda()), T, 3, S, S // p, S // p, ptr(masks), ptr(thr),
+                                                        ptr(att), None, None, cur_stream()))
+    for t in range(T):
+        assert np.array_equal(att[t].cpu().numpy(), PO.tile_attention_map(rows[t], S, p))
+        th, th2, th3, _, _ = PO.eval_tile(rows[t], x[t, 0].numpy(), p)
+        got = masks[t].cpu().numpy()
+        assert np.array_equal(got[0], th) and np.array_equal(got[1], th2) and np.array_equal(got[2], th3)
+
+
+@pytest.mark.parametrize("W,S,size", [(32, 16, 112), (48, 16, 128), (32, 16, 100)])
+def test_mosaic_pipeline_vs_oracle(W, S, size):
+    """Whole sliding-window pipeline on a small mosaic with a tiny ViT: the ViT stage is compared
+    within tolerance, everything after it (fed with the GPU's own CLS rows) bit-exactly."""
+    tiny = VO.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=8, img_size=W)
+    sd = VO.randomize_affine(VO.init_state_dict(tiny, seed=21), seed=22)
+    m = build_model(tiny, sd, "fp32", chunk_tiles=5)
+    mosaic = VO.synthetic_mosaic_u8(size, seed=77)
+    seg = vob.MosaicSegmenter(m, window=W, stride=S, tile_batch=7)
+    out = seg.segment(torch.from_numpy(mosaic).cuda(), want=("th", "th2", "th3"))
+    n = vob.grid_size(size, S)
+    assert out["grid"] == n and out["extent"] == (n - 1) * S + W
+    # ViT stage vs oracle
+    crops = PO.sliding_window(mosaic, S, W)
+    xs = torch.from_numpy(np.stack(crops)).float().div(255.0).unsqueeze(1).expand(-1, 3, -1, -1).contiguous()
+    rows_ref = VO.cls_attention_rows(sd, tiny, xs).numpy()
+    rows_gpu = m.cls_attention_rows(xs.cuda()).cpu().numpy()
+    assert float((np.abs(rows_gpu - rows_ref) / rows_ref).max()) <= 1e-3
+    # post stage, exact, from the GPU's rows
+    stitched, (th, th2, th3, _, _), gray = PO.mosaic_segment(rows_gpu, mosaic, S, W, 8)
+    assert np.array_equal(seg.stitched_map(out["lowres"]).cpu().numpy(), stitched)
+    assert np.array_equal(out["th"].cpu().numpy(), th)
+    assert np.array_equal(out["th2"].cpu().numpy(), th2)
+    assert np.array_equal(out["th3"].cpu().numpy(), th3)
+    # and end to end against the pure oracle
+    _, (th_o, _, th3_o, _, _), _ = PO.mosaic_segment(rows_ref, mosaic, S, W, 8)
+    assert float((out["th"].cpu().numpy() == th_o).mean()) >= 0.999
+    assert float((out["th3"].cpu().numpy() == th3_o).mean()) >= 0.999

@@ -1,0 +1,119 @@
+"""CPU: the oracle restatement against the golden vectors produced by the reference's own code
+(oracle/make_golden.py) and against the installed OpenCV."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import check_weight_sums, load_golden
+from oracle import post_oracle as PO
+from oracle import vit_oracle as VO
+
+TINY = VO.ViTConfig(embed_dim=128, depth=3, num_heads=2, patch_size=8, img_size=32)
+
+
+def tiny_sd():
+    return VO.randomize_affine(VO.init_state_dict(TINY, seed=7), seed=8)
+
+
+def test_param_count_known_answers():
+    # SSS/output/log_rank0.txt:5570 and :9746
+    assert VO.param_count(VO.init_state_dict(VO.ViTConfig(**VO.VIT_SMALL))) == 21670272
+    mim = VO.param_count(VO.init_state_dict(VO.ViTConfig(**VO.VIT_SMALL), mim=True)) + 384 * 192 + 192
+    assert mim == 21744576
+
+
+def test_tiny_vit_matches_reference_outputs():
+    g = load_golden("tiny_vit.npz")
+    sd = tiny_sd()
+    check_weight_sums(sd, g)
+    for name in ("a", "b", "c"):
+        x = torch.from_numpy(g[f"{name}/x"])
+        attn = VO.get_last_selfattention(sd, TINY, x)
+        feat, attns, qkvs = VO.get_intermediate_feat(sd, TINY, x)
+        assert np.abs(attn.numpy() - g[f"{name}/attn"]).max() < 1e-5
+        assert np.abs(attns[0].numpy() - g[f"{name}/attn"]).max() < 1e-5
+        assert np.abs(feat[0].numpy() - g[f"{name}/feat"]).max() < 1e-4
+        assert np.abs(qkvs[0].numpy() - g[f"{name}/qkv"]).max() < 1e-4
+        assert np.abs(VO.forward_feats(sd, TINY, x)[:, 0].numpy() - g[f"{name}/cls"]).max() < 1e-4
+        rows = VO.cls_attention_rows(sd, TINY, x)
+        assert np.allclose(rows.sum(-1).numpy(), 1.0, atol=1e-5)
+
+
+def test_synthetic_inputs_are_reproducible():
+    g = load_golden("tiny_vit.npz")
+    for name, (B, S) in {"a": (2, 32), "b": (1, 48), "c": (3, 64)}.items():
+        x = VO.synthetic_tile(S, seed=100 + S, batch=B)
+        assert np.array_equal(x.numpy(), g[f"{name}/x"])
+
+
+def test_otsu_and_resize_match_cv2_goldens():
+    g = load_golden("cv2_ops.npz")
+    for img, t in zip(g["otsu_imgs"], g["otsu_t"]):
+        to, mask = PO.otsu_threshold(img)
+        assert to == int(t)
+        assert np.array_equal(mask, np.where(img > t, 255, 0).astype(np.uint8))
+    for s, u in zip(g["resize_in"], g["resize_out"]):
+        assert np.abs(PO.resize_linear(s, (56, 56)) - u).max() < 1e-6
+        nearest = np.repeat(np.repeat(s, 8, 0), 8, 1)
+        assert np.abs(PO.resize_linear(nearest, (7, 7)) - s).max() < 1e-6   # the down-resize is an identity
+
+
+def test_otsu_and_resize_match_installed_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(3)
+    for _ in range(20):
+        img = np.clip(rng.normal(rng.randint(20, 200), rng.randint(5, 60), (33, 47)), 0, 255).astype(np.uint8)
+        t, m = cv2.threshold(img, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)
+        to, mo = PO.otsu_threshold(img)
+        assert int(t) == to and np.array_equal(m, mo)
+    s = rng.rand(28, 28).astype(np.float32)
+    assert np.abs(cv2.resize(s, (224, 224), interpolation=cv2.INTER_LINEAR) - PO.resize_linear(s, (224, 224))).max() < 1e-6
+
+
+def test_stitching_matches_reference_loops():
+    g = load_golden("stitch.npz")
+    for name, (W, S, n) in {"w32s16n4": (32, 16, 4), "w48s16n3": (48, 16, 3), "w24s8n5": (24, 8, 5), "w32s16n1": (32, 16, 1)}.items():
+        tiles = list(g[name + "/tiles"])
+        out = PO.concat_crops_blend(tiles, S, W)
+        assert out.dtype == np.float32 and np.array_equal(out, g[name + "/out"])
+        if name + "/img" in g:
+            img = g[name + "/img"]
+            crops = PO.sliding_window(img, S, W)
+            assert len(crops) == n * n
+            assert np.array_equal(PO.concat_crops_blend(crops, S, W), g[name + "/gray_stitched"])
+        # separable-weights property (size independent): every output pixel is a convex combination
+        P = PO.blend_profiles(n, S, W)
+        assert np.allclose(P.sum(0), 1.0, atol=1e-12)
+
+
+def test_threshold_flavours_match_reference():
+    g = load_golden("threshold.npz")
+    o = PO.threshold_sw(g["img"], g["att"])
+    assert np.array_equal(o[0], g["sw_th"]) and np.array_equal(o[1], g["sw_th2"]) and np.array_equal(o[2], g["sw_th3"])
+    u = PO.threshold_utils(g["img"], g["att"])
+    assert np.array_equal(u[0], g["ut_th"]) and np.array_equal(u[1], g["ut_th2"]) and np.array_equal(u[2], g["ut_th3"])
+
+
+def test_vits8_tile_post_chain_matches_reference():
+    g = load_golden("vits8_tile.npz")
+    x = VO.synthetic_tile(224, seed=int(g["x_seed"]), batch=1)
+    rows = g["cls_rows"][0]
+    att = PO.tile_attention_map(rows, 224, 8)
+    assert np.abs(att - g["att_map"]).max() <= 1e-6 * np.abs(g["att_map"]).max()
+    th, th2, th3, _, _ = PO.eval_tile(rows, x[0, 0].numpy(), 8)
+    for a, b in ((th, g["th"]), (th2, g["th2"]), (th3, g["th3"])):
+        assert (a == b).mean() >= 0.9999
+
+
+def test_mask_generator_and_mim_loss():
+    g = load_golden("mim_tiny.npz")
+    m = VO.mask_generator(np.random.RandomState(0), 224, 16, 8, 0.5)
+    assert np.array_equal(m, g["mask224_seed0"]) and m.sum() == 392
+    cfg_init = VO.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=8, img_size=224)
+    cfg = VO.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=8, img_size=32)
+    sd = VO.randomize_affine(VO.init_state_dict(cfg_init, seed=11, mim=True), seed=12)
+    check_weight_sums(sd, g)
+    loss, x_rec, _ = VO.mim_forward(sd, cfg, torch.from_numpy(g["dec_w"]), torch.from_numpy(g["dec_b"]),
+                                    torch.from_numpy(g["x"]), torch.from_numpy(g["mask"]))
+    assert abs(loss.item() - float(g["loss"])) < 1e-6
+    assert np.abs(x_rec.detach().numpy() - g["x_rec"]).max() < 1e-5

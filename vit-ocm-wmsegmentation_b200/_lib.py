@@ -1,0 +1,106 @@
+"""ctypes binding of libvitocm.so (include/vitocm.h).  There is no CPU or eager-PyTorch fallback:
+if the CUDA library is missing or a call fails, this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libvitocm.so")
+
+c_void_p, c_int, c_int64, c_size_t, c_float, c_char_p = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_char_p
+
+
+class VitocmConfig(C.Structure):
+    _fields_ = [("embed_dim", c_int), ("depth", c_int), ("num_heads", c_int), ("mlp_hidden", c_int),
+                ("patch_size", c_int), ("in_chans", c_int), ("ln_eps", c_float), ("qk_scale", c_float),
+                ("precision", c_int)]
+
+
+# name -> (restype, argtypes); mirrors include/vitocm.h one to one
+SIGNATURES = {
+    "vitocm_version": (c_int, []),
+    "vitocm_last_error": (c_char_p, []),
+    "vitocm_create": (c_int, [C.POINTER(VitocmConfig), C.POINTER(c_void_p)]),
+    "vitocm_destroy": (c_int, [c_void_p]),
+    "vitocm_load_weight": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "vitocm_finalize_weights": (c_int, [c_void_p]),
+    "vitocm_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "vitocm_forward_cls_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                        c_int, c_void_p]),
+    "vitocm_prepare_tokens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vitocm_block_forward": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "vitocm_block_attn_probs": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                        c_void_p]),
+    "vitocm_final_norm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "vitocm_head_mean": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "vitocm_tile_threshold": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
+    "vitocm_extract_tiles": (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                     c_void_p]),
+    "vitocm_stitch_gray": (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
+                                   c_void_p]),
+    "vitocm_minmax_init": (c_int, [c_void_p, c_void_p]),
+    "vitocm_stitch_minmax": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
+                                     c_void_p, c_void_p, c_void_p]),
+    "vitocm_stitch_hist": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p]),
+    "vitocm_otsu": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "vitocm_stitch_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vitocm_concat_crops_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "vitocm_concat_crops_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "vitocm_crop_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vitocm_gemm": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                            c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "vitocm_attention": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p]),
+    "vitocm_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "vitocm_launch_count": (c_int64, []),
+}
+
+_lib = None
+
+
+class VitocmError(RuntimeError):
+    pass
+
+
+def load_library() -> C.CDLL:
+    """dlopen libvitocm.so and declare every exported symbol.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VitocmError(f"{LIB_PATH} not found: build it with `python {os.path.join(PKG_DIR, 'build.py')}` "
+                          "(nvcc, sm_100a).  There is no CPU / PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load_library().vitocm_last_error()
+        raise VitocmError(f"libvitocm error {rc}: {msg.decode() if msg else ''}")
+
+
+def ptr(t) -> int | None:
+    """Device (or host) address of a tensor; None passes NULL."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "vitocm expects dense row-major tensors"
+    return t.data_ptr()
+
+
+def cur_stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(load_library().vitocm_launch_count())

@@ -1,0 +1,339 @@
+// Bandwidth-bound ViT kernels (vectorised, coalesced, fp32 statistics):
+//   patch_embed_kernel   SSS/dino/vision_transformer.py:129-132 + :203-207 (+ model.py:31-33 mask-token mix)
+//   layernorm_kernel     vit.py:107,111 (norm1/norm2) and :215/:234 (final norm), eps = 1e-6
+//   cls_attn_row_kernel  vit.py:80-84 restricted to the CLS query of the last block
+//   attn_probs_kernel    vit.py:83-84 full softmax(QK^T) (API-complete get_last_selfattention)
+#pragma once
+#include "ptx.cuh"
+
+namespace vitocm {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// Patch embedding, im2col-free: reads NCHW pixels directly, writes the fp32 token stream
+//   X[b, 1 + py*Wp + px, :] = W[:, c, yi, xi] . x[b, c, py*p+yi, px*p+xi] + bias + pos[1 + ...]
+//   X[b, 0, :]              = cls_token + pos[0]
+// One block = one row of patches (Wp patches) of one image; thread d-loop over D with the
+// transposed weight Wt[K][D] so that weight loads are coalesced; pixels staged in smem.
+// Optional SimMIM mask-token mixing (mask[b, n] in {0,1}) before the position add.
+// ---------------------------------------------------------------------------------------
+constexpr int PE_MAX_PATCHES = 32;   // patches per block iteration
+
+__global__ void __launch_bounds__(128)
+patch_embed_kernel(const float* __restrict__ x, const float* __restrict__ wt /*[K][D]*/, const float* __restrict__ bias,
+                   const float* __restrict__ pos /*[1+n][D]*/, const float* __restrict__ cls_token,
+                   const float* __restrict__ mask /*[B][n] or null*/, const float* __restrict__ mask_token,
+                   float* __restrict__ out /*[B][1+n][D]*/, int C, int H, int W, int p, int D) {
+  extern __shared__ float pe_smem[];  // [PE_MAX_PATCHES][K]
+  const int Wp = W / p, Hp = H / p;
+  const int K = C * p * p;
+  const int py = blockIdx.x, b = blockIdx.y;
+  const int n = Hp * Wp;
+  const float* xb = x + static_cast<long long>(b) * C * H * W;
+  float* ob = out + static_cast<long long>(b) * (n + 1) * D;
+
+  if (py == 0) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) ob[d] = cls_token[d] + pos[d];
+  }
+  for (int px0 = 0; px0 < Wp; px0 += PE_MAX_PATCHES) {
+    const int np = min(PE_MAX_PATCHES, Wp - px0);
+    __syncthreads();
+    // stage np patches: iterate over (c, yi) rows; each row segment is np*p contiguous pixels
+    const int seg = np * p;
+    for (int idx = threadIdx.x; idx < C * p * seg; idx += blockDim.x) {
+      const int cy = idx / seg;       // c*p + yi
+      const int xx = idx - cy * seg;  // pixel inside the segment
+      const int c = cy / p, yi = cy - c * p;
+      const int pl = xx / p, xi = xx - pl * p;
+      pe_smem[pl * K + c * p * p + yi * p + xi] = xb[(static_cast<long long>(c) * H + py * p + yi) * W + px0 * p + xx];
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float acc[PE_MAX_PATCHES];
+#pragma unroll
+      for (int i = 0; i < PE_MAX_PATCHES; ++i) acc[i] = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const float w = __ldg(wt + static_cast<long long>(k) * D + d);
+#pragma unroll
+        for (int i = 0; i < PE_MAX_PATCHES; ++i)
+          if (i < np) acc[i] = fmaf(w, pe_smem[i * K + k], acc[i]);
+      }
+      const float bd = bias[d];
+#pragma unroll
+      for (int i = 0; i < PE_MAX_PATCHES; ++i) {
+        if (i < np) {
+          const int tok = py * Wp + px0 + i;
+          float v = acc[i] + bd;
+          if (mask != nullptr) {
+            const float m = mask[static_cast<long long>(b) * n + tok];
+            v = v * (1.f - m) + mask_token[d] * m;
+          }
+          ob[static_cast<long long>(1 + tok) * D + d] = v + pos[static_cast<long long>(1 + tok) * D + d];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm over the last dim of the fp32 token stream, one warp per row, float4 loads.
+// Outputs: bf16 (hi) and, in split mode, lo = bf16(y - hi) at column offset lo_off of the same
+// row (the A operand of the following GEMM); optionally the fp32 result (final norm -> feat).
+// ---------------------------------------------------------------------------------------
+constexpr int LN_MAX_VEC = 8;  // up to D = 8*32*4 = 1024
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ out_bf16, long long ldo, int split, int lo_off,
+                 float* __restrict__ out_f32, long long ldf, int M, int D, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * D);
+  const int nvec = D >> 2;
+  float4 v[LN_MAX_VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      v[i] = xr[idx];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(D) + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float4 g = reinterpret_cast<const float4*>(gamma)[idx];
+      const float4 bb = reinterpret_cast<const float4*>(beta)[idx];
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x + bb.x;
+      y.y = (v[i].y - mean) * rstd * g.y + bb.y;
+      y.z = (v[i].z - mean) * rstd * g.z + bb.z;
+      y.w = (v[i].w - mean) * rstd * g.w + bb.w;
+      if (out_bf16 != nullptr) {
+        __nv_bfloat16* o = out_bf16 + static_cast<long long>(row) * ldo + idx * 4;
+        *reinterpret_cast<uint2*>(o) = make_uint2(ptx::pack_bf16x2(y.x, y.y), ptx::pack_bf16x2(y.z, y.w));
+        if (split) {
+          *reinterpret_cast<uint2*>(o + lo_off) =
+              make_uint2(ptx::pack_bf16x2(y.x - ptx::bf16_round(y.x), y.y - ptx::bf16_round(y.y)),
+                         ptx::pack_bf16x2(y.z - ptx::bf16_round(y.z), y.w - ptx::bf16_round(y.w)));
+        }
+      }
+      if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * ldf)[idx] = y;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Last block, CLS query only (the slice every hot-path caller reads, SSS/utils.py:232 with
+// query = 0): one block per (head, image):
+//   xn  = LayerNorm(X[b, 0, :])                       (fp32)
+//   q_h = Wq[h*64:(h+1)*64, :] . xn + bq              (fp32 weights, fp32 math)
+//   out[b, h, j] = softmax_j( scale * q_h . K[b, j, h*64:(h+1)*64] )   for j in [0, N)
+// K comes from the (split-precision) K-projection GEMM as fp32 [B*N, D].
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cls_attn_row_kernel(const float* __restrict__ X, const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps,
+                    const float* __restrict__ Wq /*[D][D] rows = q outputs*/, const float* __restrict__ bq,
+                    const float* __restrict__ Kmat /*[B*N][D] fp32*/, float* __restrict__ out /*[B][H][N]*/, int N, int D,
+                    int heads, float scale) {
+  extern __shared__ float cls_smem[];  // xn[D] | q[64] | logits[N] | red[32]
+  float* xn = cls_smem;
+  float* qv = xn + D;
+  float* logits = qv + 64;
+  float* red = logits + N;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const float* xr = X + static_cast<long long>(b) * N * D;  // CLS token row
+
+  // LayerNorm of the CLS row (block-wide two-pass)
+  float s = 0.f;
+  for (int d = tid; d < D; d += blockDim.x) s += xr[d];
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < nwarps; ++w) tot += red[w];
+  const float mean = tot / static_cast<float>(D);
+  __syncthreads();
+  float ss = 0.f;
+  for (int d = tid; d < D; d += blockDim.x) {
+    const float c = xr[d] - mean;
+    ss += c * c;
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  tot = 0.f;
+  for (int w = 0; w < nwarps; ++w) tot += red[w];
+  const float rstd = rsqrtf(tot / static_cast<float>(D) + eps);
+  for (int d = tid; d < D; d += blockDim.x) xn[d] = (xr[d] - mean) * rstd * ln_w[d] + ln_b[d];
+  __syncthreads();
+
+  // q_h: 64 outputs, one warp per output (coalesced weight rows)
+  for (int o = warp; o < 64; o += nwarps) {
+    const float* wr = Wq + static_cast<long long>(h * 64 + o) * D;
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) acc = fmaf(wr[d], xn[d], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) qv[o] = acc + bq[h * 64 + o];
+  }
+  __syncthreads();
+
+  // logits: one warp per key, two channels per lane
+  const float q0 = qv[2 * lane], q1 = qv[2 * lane + 1];
+  float lmax = -INFINITY;
+  for (int j = warp; j < N; j += nwarps) {
+    const float2 kk = *reinterpret_cast<const float2*>(Kmat + (static_cast<long long>(b) * N + j) * D + h * 64 + 2 * lane);
+    float acc = warp_sum(fmaf(q0, kk.x, q1 * kk.y)) * scale;
+    if (lane == 0) logits[j] = acc;
+    lmax = fmaxf(lmax, acc);
+  }
+  if (lane == 0) red[warp] = lmax;
+  __syncthreads();
+  float gmax = -INFINITY;
+  for (int w = 0; w < nwarps; ++w) gmax = fmaxf(gmax, red[w]);
+  __syncthreads();
+  float lsum = 0.f;
+  for (int j = tid; j < N; j += blockDim.x) {
+    const float e = expf(logits[j] - gmax);
+    logits[j] = e;
+    lsum += e;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) red[warp] = lsum;
+  __syncthreads();
+  float gsum = 0.f;
+  for (int w = 0; w < nwarps; ++w) gsum += red[w];
+  const float inv = 1.0f / gsum;
+  float* o = out + (static_cast<long long>(b) * heads + h) * N;
+  for (int j = tid; j < N; j += blockDim.x) o[j] = logits[j] * inv;
+}
+
+// ---------------------------------------------------------------------------------------
+// Full attention probabilities of one block, fp32 math on CUDA cores (API-complete path for
+// get_last_selfattention / get_intermediate_feat; the hot path never materialises N x N).
+// Reads q and k from an fp32 [B*N, 3D] activation.  One block = (qrows-query group, head, image);
+// K_h is staged once per block in smem as fp32 with a padded row (65 floats) so that the
+// lane-per-key dot products are bank-conflict free.
+// ---------------------------------------------------------------------------------------
+constexpr int AP_QROWS = 16;
+
+__global__ void __launch_bounds__(256)
+attn_probs_kernel(const float* __restrict__ qkv /*[B*N][3D]*/, float* __restrict__ attn /*[B][H][N][N]*/, int N, int D,
+                  int heads, float scale, int kchunk /*keys staged per pass*/, int qrows) {
+  extern __shared__ float ap_smem[];  // K chunk [kchunk][65] | q [qrows][64] | logits [qrows][N]
+  float* ks = ap_smem;
+  float* qs = ks + kchunk * 65;
+  float* lg = qs + qrows * 64;
+  const int q0 = blockIdx.x * qrows, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const long long ld = 3LL * D;
+  const float* base = qkv + static_cast<long long>(b) * N * ld;
+  for (int i = tid; i < qrows * 64; i += blockDim.x) {
+    const int r = i >> 6, c = i & 63;
+    qs[i] = (q0 + r < N) ? base[(q0 + r) * ld + h * 64 + c] : 0.f;
+  }
+  for (int k0 = 0; k0 < N; k0 += kchunk) {
+    const int kn = min(kchunk, N - k0);
+    __syncthreads();
+    for (int i = tid; i < kn * 64; i += blockDim.x) {
+      const int r = i >> 6, c = i & 63;
+      ks[r * 65 + c] = base[(k0 + r) * ld + D + h * 64 + c];
+    }
+    __syncthreads();
+    // each warp: 2 query rows; lane-per-key
+    for (int r = warp; r < qrows; r += nwarps) {
+      const float* qr = qs + r * 64;
+      for (int j = lane; j < kn; j += 32) {
+        const float* kr = ks + j * 65;
+        float acc = 0.f;
+#pragma unroll 16
+        for (int c = 0; c < 64; ++c) acc = fmaf(qr[c], kr[c], acc);
+        lg[r * N + k0 + j] = acc * scale;
+      }
+    }
+  }
+  __syncthreads();
+  for (int r = warp; r < qrows; r += nwarps) {
+    if (q0 + r >= N) continue;
+    float* lr = lg + r * N;
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, lr[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) {
+      const float e = expf(lr[j] - mx);
+      lr[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    float* o = attn + ((static_cast<long long>(b) * heads + h) * N + (q0 + r)) * N;
+    for (int j = lane; j < N; j += 32) o[j] = lr[j] * inv;
+  }
+}
+
+// bf16 (hi [+ lo]) activation -> fp32 (qkv / ctx export for the API-complete path)
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, long long ldi, int split, int lo_off,
+                                   float* __restrict__ out, long long ldo, int M, int ncols) {
+  const long long total = static_cast<long long>(M) * ncols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / ncols;
+    const int c = static_cast<int>(i - r * ncols);
+    float v = __bfloat162float(in[r * ldi + c]);
+    if (split) v += __bfloat162float(in[r * ldi + lo_off + c]);
+    out[r * ldo + c] = v;
+  }
+}
+
+// fp32 [R, C] weight -> bf16 hi (and lo) [R, ldo]  (weight repack at load time)
+__global__ void split_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, long long ldo, int split,
+                                    int lo_off, int R, int C) {
+  const long long total = static_cast<long long>(R) * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C;
+    const int c = static_cast<int>(i - r * C);
+    const float v = w[i];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[r * ldo + c] = hi;
+    if (split) out[r * ldo + lo_off + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+// [R][C] -> [C][R] fp32 (patch-embed weight transpose at load time)
+__global__ void transpose_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+  const long long total = static_cast<long long>(R) * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / C), c = static_cast<int>(i - static_cast<long long>(r) * C);
+    out[static_cast<long long>(c) * R + r] = in[i];
+  }
+}
+
+}  // namespace vitocm

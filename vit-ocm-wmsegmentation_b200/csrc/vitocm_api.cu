@@ -1,0 +1,643 @@
+// C ABI of libvitocm.so (see include/vitocm.h).  Host-side engine: weight store + repack,
+// TMA tensor-map construction, kernel launches.  No torch types; plain pointers and sizes.
+#include "../../include/vitocm.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "attention_sm100.cuh"
+#include "gemm_sm100.cuh"
+#include "post_kernels.cuh"
+#include "vit_kernels.cuh"
+
+using namespace vitocm;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                      \
+  do {                                                                                                      \
+    cudaError_t err__ = (expr);                                                                             \
+    if (err__ != cudaSuccess) return fail(VITOCM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+#define TRY(expr)                \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != 0) return rc__;  \
+  } while (0)
+#define LAUNCH_CHECK()                                                                                            \
+  do {                                                                                                            \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                                           \
+    cudaError_t err__ = cudaGetLastError();                                                                       \
+    if (err__ != cudaSuccess) return fail(VITOCM_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows][ld] matrix, box = [box_rows][64 cols], SWIZZLE_128B
+int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return fail(VITOCM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0)
+    return fail(VITOCM_ERR_INVALID, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VITOCM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return 0;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t n) {
+    if (p) { cudaFree(p); p = nullptr; }
+    bytes = n;
+    cudaError_t e = cudaMalloc(&p, n ? n : 1);
+    if (e != cudaSuccess) { p = nullptr; return fail(VITOCM_ERR_CUDA, "cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e)); }
+    return 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct LayerW {
+  DevBuf wqkv, wproj, w1, w2;      // bf16 [rows][K * parts]  (hi | lo)
+  DevBuf wk_split;                 // last layer: K rows of qkv, always split [D][2D]
+  const float *bqkv = nullptr, *bproj = nullptr, *b1 = nullptr, *b2 = nullptr;
+  const float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
+  const float* wqkv_f32 = nullptr;  // master copy (q rows used by the CLS kernel)
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct vitocm_engine {
+  vitocm_config cfg{};
+  int split = 0;
+  int parts = 1;
+  int num_sms = 148;
+  bool finalized = false;
+  std::map<std::string, DevBuf*> master;  // fp32 weights as loaded
+  std::vector<LayerW> layers;
+  DevBuf patch_wt;  // [K][D] fp32
+  ~vitocm_engine() { for (auto& kv : master) delete kv.second; }
+  const float* w(const std::string& name) const {
+    auto it = master.find(name);
+    return it == master.end() ? nullptr : it->second->as<float>();
+  }
+  long long numel(const std::string& name) const {
+    auto it = master.find(name);
+    return it == master.end() ? -1 : static_cast<long long>(it->second->bytes / 4);
+  }
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------- GEMM launch
+template <int BN, int EPI>
+int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_sms, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI>;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * (a.N / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+int launch_gemm_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_sms, cudaStream_t st) {
+  switch (epi) {
+    case EPI_BIAS_BF16: return launch_gemm_inst<BN, EPI_BIAS_BF16>(ta, tb, a, num_sms, st);
+    case EPI_BIAS_GELU_BF16: return launch_gemm_inst<BN, EPI_BIAS_GELU_BF16>(ta, tb, a, num_sms, st);
+    case EPI_BIAS_RESID_F32: return launch_gemm_inst<BN, EPI_BIAS_RESID_F32>(ta, tb, a, num_sms, st);
+    case EPI_BIAS_F32: return launch_gemm_inst<BN, EPI_BIAS_F32>(ta, tb, a, num_sms, st);
+  }
+  return fail(VITOCM_ERR_INVALID, "unknown GEMM epilogue %d", epi);
+}
+
+int pick_bn(int N) {
+  if (N % 256 == 0) return 256;
+  if (N % 192 == 0) return 192;
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  return 0;
+}
+
+// A [M][lda] (split: hi at col 0, lo at col K), B [N][ldb] likewise.
+int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+             int split_in, int epi, const float* bias, void* out, long long ldo, int split_out, int lo_off, cudaStream_t st) {
+  if (M <= 0) return 0;
+  if (K % GEMM_BK != 0) return fail(VITOCM_ERR_INVALID, "GEMM K=%d must be a multiple of %d", K, GEMM_BK);
+  const int bn = pick_bn(N);
+  if (bn == 0) return fail(VITOCM_ERR_INVALID, "GEMM N=%d must be a multiple of 64", N);
+  const long long kext = static_cast<long long>(K) * (split_in ? 2 : 1);
+  CUtensorMap ta, tb;
+  TRY(make_tmap_bf16(&ta, A, M, kext, lda, GEMM_BM));
+  TRY(make_tmap_bf16(&tb, B, N, kext, ldb, bn));
+  GemmArgs a{};
+  a.M = M; a.N = N; a.kblocks = K / GEMM_BK; a.nterms = split_in ? 3 : 1;
+  a.a_koff[0] = 0; a.b_koff[0] = 0;   // hi * hi
+  a.a_koff[1] = 0; a.b_koff[1] = K;   // hi * lo
+  a.a_koff[2] = K; a.b_koff[2] = 0;   // lo * hi
+  a.bias = bias; a.out = out; a.ldo = ldo; a.split_out = split_out; a.lo_off = lo_off;
+  switch (bn) {
+    case 256: return launch_gemm_bn<256>(epi, ta, tb, a, e->num_sms, st);
+    case 192: return launch_gemm_bn<192>(epi, ta, tb, a, e->num_sms, st);
+    case 128: return launch_gemm_bn<128>(epi, ta, tb, a, e->num_sms, st);
+    default: return launch_gemm_bn<64>(epi, ta, tb, a, e->num_sms, st);
+  }
+}
+
+// ---------------------------------------------------------------------------------- attention launch
+int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, int N, void* ctx, long long ldo, cudaStream_t st) {
+  const int D = e->cfg.embed_dim, H = e->cfg.num_heads;
+  const long long M = static_cast<long long>(B) * N;
+  CUtensorMap tq;
+  TRY(make_tmap_bf16(&tq, qkv, M, 3LL * D * e->parts, ld, 128));
+  AttnArgs a{};
+  a.n_tokens = N; a.embed_dim = D; a.lo_col_off = 3 * D;
+  a.scale_log2 = e->cfg.qk_scale * 1.44269504088896340736f;
+  a.out = reinterpret_cast<__nv_bfloat16*>(ctx); a.ldo = ldo; a.out_lo_off = D;
+  dim3 grid((N + ATT_BQ - 1) / ATT_BQ, H, B);
+  if (e->split) {
+    static bool attr = false;
+    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<true>::SMEM_BYTES)); attr = true; }
+    attn_fwd_tcgen05_kernel<true><<<grid, ATT_THREADS, AttnCfg<true>::SMEM_BYTES, st>>>(tq, a);
+  } else {
+    static bool attr = false;
+    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<false>::SMEM_BYTES)); attr = true; }
+    attn_fwd_tcgen05_kernel<false><<<grid, ATT_THREADS, AttnCfg<false>::SMEM_BYTES, st>>>(tq, a);
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int run_layernorm(const float* X, const float* g, const float* b, void* out_bf16, long long ldo, int split, int lo_off,
+                  float* out_f32, long long ldf, int M, int D, float eps, cudaStream_t st) {
+  if (M <= 0) return 0;
+  if (D % 4 != 0 || D > LN_MAX_VEC * 128) return fail(VITOCM_ERR_INVALID, "LayerNorm D=%d unsupported", D);
+  const int rows_per_block = 8;
+  layernorm_kernel<<<(M + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, st>>>(
+      X, g, b, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, split, lo_off, out_f32, ldf, M, D, eps);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int run_patch_embed(const vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const float* mask,
+                    float* X, cudaStream_t st) {
+  const int p = e->cfg.patch_size, C = e->cfg.in_chans, D = e->cfg.embed_dim;
+  if (H % p != 0 || W % p != 0) return fail(VITOCM_ERR_INVALID, "image %dx%d not a multiple of patch %d", H, W, p);
+  const int K = C * p * p;
+  const size_t smem = static_cast<size_t>(PE_MAX_PATCHES) * K * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    CUDA_TRY(cudaFuncSetAttribute(patch_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    smem_set = smem;
+  }
+  const float* mask_token = e->w("mask_token");
+  if (mask != nullptr && mask_token == nullptr) return fail(VITOCM_ERR_STATE, "mask given but mask_token was never loaded");
+  dim3 grid(H / p, B);
+  patch_embed_kernel<<<grid, 128, smem, st>>>(x, e->patch_wt.as<float>(), e->w("patch_embed.proj.bias"), pos, e->w("cls_token"),
+                                              mask, mask_token, X, C, H, W, p, D);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// workspace carve-up for a chunk of `tiles` images
+struct Workspace {
+  float* X;            // [M][D] fp32 token stream
+  __nv_bfloat16* XN;   // [M][2D]  (always room for hi|lo: the last block's K projection is split)
+  __nv_bfloat16* QKV;  // [M][3D*parts]
+  __nv_bfloat16* CTX;  // [M][D*parts]
+  __nv_bfloat16* HID;  // [M][4D*parts]  (aliased by KF fp32 [M][D] in the last block)
+  size_t total;
+};
+Workspace carve(const vitocm_engine* e, void* base, int tiles, int N) {
+  const size_t M = static_cast<size_t>(tiles) * N;
+  const size_t D = e->cfg.embed_dim, Hd = e->cfg.mlp_hidden, P = e->parts;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  Workspace w{};
+  auto take = [&](size_t bytes) { uint8_t* r = p + off; off += align_up(bytes, 1024); return r; };
+  w.X = reinterpret_cast<float*>(take(M * D * 4));
+  w.XN = reinterpret_cast<__nv_bfloat16*>(take(M * 2 * D * 2));
+  w.QKV = reinterpret_cast<__nv_bfloat16*>(take(M * 3 * D * P * 2));
+  w.CTX = reinterpret_cast<__nv_bfloat16*>(take(M * D * P * 2));
+  size_t hid = M * Hd * P * 2;
+  if (hid < M * D * 4) hid = M * D * 4;
+  w.HID = reinterpret_cast<__nv_bfloat16*>(take(hid));
+  w.total = off;
+  return w;
+}
+
+// one full transformer block in place on ws.X (vit.py:106-114)
+int block_forward(const vitocm_engine* e, int l, const Workspace& ws, int B, int N, cudaStream_t st) {
+  const LayerW& L = e->layers[l];
+  const int D = e->cfg.embed_dim, Hd = e->cfg.mlp_hidden, P = e->parts, S = e->split;
+  const int M = B * N;
+  TRY(run_layernorm(ws.X, L.ln1w, L.ln1b, ws.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
+  TRY(run_gemm(e, ws.XN, 2LL * D, L.wqkv.p, static_cast<long long>(D) * P, M, 3 * D, D, S, EPI_BIAS_BF16, L.bqkv, ws.QKV,
+               3LL * D * P, S, 3 * D, st));
+  TRY(run_attention(e, ws.QKV, 3LL * D * P, B, N, ws.CTX, static_cast<long long>(D) * P, st));
+  TRY(run_gemm(e, ws.CTX, static_cast<long long>(D) * P, L.wproj.p, static_cast<long long>(D) * P, M, D, D, S,
+               EPI_BIAS_RESID_F32, L.bproj, ws.X, D, 0, 0, st));
+  TRY(run_layernorm(ws.X, L.ln2w, L.ln2b, ws.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
+  TRY(run_gemm(e, ws.XN, 2LL * D, L.w1.p, static_cast<long long>(D) * P, M, Hd, D, S, EPI_BIAS_GELU_BF16, L.b1, ws.HID,
+               static_cast<long long>(Hd) * P, S, Hd, st));
+  TRY(run_gemm(e, ws.HID, static_cast<long long>(Hd) * P, L.w2.p, static_cast<long long>(Hd) * P, M, D, Hd, S,
+               EPI_BIAS_RESID_F32, L.b2, ws.X, D, 0, 0, st));
+  return 0;
+}
+
+int check_engine(const vitocm_engine* e) {
+  if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
+  if (!e->finalized) return fail(VITOCM_ERR_STATE, "weights not finalized (call vitocm_finalize_weights)");
+  return 0;
+}
+
+}  // namespace
+
+// ====================================================================================== C ABI
+extern "C" {
+
+int vitocm_version(void) { return VITOCM_VERSION; }
+const char* vitocm_last_error(void) { return g_err; }
+int64_t vitocm_launch_count(void) { return g_launches.load(); }
+
+int vitocm_create(const vitocm_config* cfg, vitocm_engine** out) {
+  if (cfg == nullptr || out == nullptr) return fail(VITOCM_ERR_INVALID, "null argument");
+  if (cfg->num_heads <= 0 || cfg->embed_dim != cfg->num_heads * 64)
+    return fail(VITOCM_ERR_INVALID, "head_dim must be 64 (embed_dim %d, heads %d)", cfg->embed_dim, cfg->num_heads);
+  if (cfg->mlp_hidden % 64 != 0 || cfg->depth < 1) return fail(VITOCM_ERR_INVALID, "bad mlp_hidden/depth");
+  if (cfg->precision != VITOCM_BF16 && cfg->precision != VITOCM_FP32) return fail(VITOCM_ERR_INVALID, "bad precision");
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(VITOCM_ERR_CUDA, "libvitocm is built for sm_100a only (device is sm_%d%d)", prop.major, prop.minor);
+  vitocm_engine* e = new vitocm_engine();
+  e->cfg = *cfg;
+  e->split = cfg->precision == VITOCM_FP32 ? 1 : 0;
+  e->parts = e->split ? 2 : 1;
+  e->num_sms = prop.multiProcessorCount;
+  e->layers.resize(cfg->depth);
+  *out = e;
+  return 0;
+}
+
+int vitocm_destroy(vitocm_engine* e) {
+  delete e;
+  return 0;
+}
+
+int vitocm_load_weight(vitocm_engine* e, const char* name, const float* host_data, int64_t numel) {
+  if (e == nullptr || name == nullptr || host_data == nullptr || numel <= 0) return fail(VITOCM_ERR_INVALID, "bad argument");
+  DevBuf* b = new DevBuf();
+  int rc = b->alloc(static_cast<size_t>(numel) * 4);
+  if (rc != 0) { delete b; return rc; }
+  cudaError_t ce = cudaMemcpy(b->p, host_data, static_cast<size_t>(numel) * 4, cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { delete b; return fail(VITOCM_ERR_CUDA, "cudaMemcpy failed: %s", cudaGetErrorString(ce)); }
+  auto it = e->master.find(name);
+  if (it != e->master.end()) { delete it->second; it->second = b; } else { e->master[name] = b; }
+  e->finalized = false;
+  return 0;
+}
+
+int vitocm_finalize_weights(vitocm_engine* e) {
+  if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
+  const int D = e->cfg.embed_dim, Hd = e->cfg.mlp_hidden, P = e->parts, S = e->split;
+  const int K = e->cfg.in_chans * e->cfg.patch_size * e->cfg.patch_size;
+  auto need = [&](const std::string& n, long long cnt) -> int {
+    if (e->numel(n) != cnt) return fail(VITOCM_ERR_STATE, "weight '%s' missing or wrong size (have %lld, need %lld)", n.c_str(), e->numel(n), cnt);
+    return 0;
+  };
+  TRY(need("cls_token", D));
+  TRY(need("patch_embed.proj.weight", static_cast<long long>(D) * K));
+  TRY(need("patch_embed.proj.bias", D));
+  TRY(need("norm.weight", D));
+  TRY(need("norm.bias", D));
+  TRY(e->patch_wt.alloc(static_cast<size_t>(D) * K * 4));
+  transpose_f32_kernel<<<256, 256>>>(e->w("patch_embed.proj.weight"), e->patch_wt.as<float>(), D, K);
+  LAUNCH_CHECK();
+  auto pack = [&](DevBuf& dst, const float* src, int R, int C, int split) -> int {
+    const int parts = split ? 2 : 1;
+    TRY(dst.alloc(static_cast<size_t>(R) * C * parts * 2));
+    split_weight_kernel<<<512, 256>>>(src, dst.as<__nv_bfloat16>(), static_cast<long long>(C) * parts, split, C, R, C);
+    LAUNCH_CHECK();
+    return 0;
+  };
+  for (int l = 0; l < e->cfg.depth; ++l) {
+    const std::string pre = "blocks." + std::to_string(l) + ".";
+    LayerW& L = e->layers[l];
+    TRY(need(pre + "norm1.weight", D)); TRY(need(pre + "norm1.bias", D));
+    TRY(need(pre + "norm2.weight", D)); TRY(need(pre + "norm2.bias", D));
+    TRY(need(pre + "attn.qkv.weight", 3LL * D * D)); TRY(need(pre + "attn.qkv.bias", 3LL * D));
+    TRY(need(pre + "attn.proj.weight", static_cast<long long>(D) * D)); TRY(need(pre + "attn.proj.bias", D));
+    TRY(need(pre + "mlp.fc1.weight", static_cast<long long>(Hd) * D)); TRY(need(pre + "mlp.fc1.bias", Hd));
+    TRY(need(pre + "mlp.fc2.weight", static_cast<long long>(D) * Hd)); TRY(need(pre + "mlp.fc2.bias", D));
+    L.ln1w = e->w(pre + "norm1.weight"); L.ln1b = e->w(pre + "norm1.bias");
+    L.ln2w = e->w(pre + "norm2.weight"); L.ln2b = e->w(pre + "norm2.bias");
+    L.bqkv = e->w(pre + "attn.qkv.bias"); L.bproj = e->w(pre + "attn.proj.bias");
+    L.b1 = e->w(pre + "mlp.fc1.bias"); L.b2 = e->w(pre + "mlp.fc2.bias");
+    L.wqkv_f32 = e->w(pre + "attn.qkv.weight");
+    TRY(pack(L.wqkv, e->w(pre + "attn.qkv.weight"), 3 * D, D, S));
+    TRY(pack(L.wproj, e->w(pre + "attn.proj.weight"), D, D, S));
+    TRY(pack(L.w1, e->w(pre + "mlp.fc1.weight"), Hd, D, S));
+    TRY(pack(L.w2, e->w(pre + "mlp.fc2.weight"), D, Hd, S));
+    if (l == e->cfg.depth - 1) TRY(pack(L.wk_split, L.wqkv_f32 + static_cast<long long>(D) * D, D, D, 1));
+  }
+  (void)P;
+  CUDA_TRY(cudaDeviceSynchronize());
+  e->finalized = true;
+  return 0;
+}
+
+size_t vitocm_workspace_bytes(const vitocm_engine* e, int chunk_tiles, int n_tokens) {
+  if (e == nullptr || chunk_tiles <= 0 || n_tokens <= 0) return 0;
+  return carve(e, nullptr, chunk_tiles, n_tokens).total + 1024;
+}
+
+int vitocm_prepare_tokens(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const float* mask,
+                          float* X, void* stream) {
+  TRY(check_engine(e));
+  return run_patch_embed(e, x, B, H, W, pos, mask, X, static_cast<cudaStream_t>(stream));
+}
+
+int vitocm_forward_cls_attn(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, float* out_rows,
+                            void* ws, size_t ws_bytes, int chunk_tiles, void* stream) {
+  TRY(check_engine(e));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int p = e->cfg.patch_size, D = e->cfg.embed_dim, heads = e->cfg.num_heads, C = e->cfg.in_chans;
+  if (B <= 0) return 0;
+  if (H % p || W % p) return fail(VITOCM_ERR_INVALID, "image %dx%d not a multiple of patch %d", H, W, p);
+  const int N = (H / p) * (W / p) + 1;
+  if (chunk_tiles <= 0) return fail(VITOCM_ERR_INVALID, "chunk_tiles must be positive");
+  if (chunk_tiles > B) chunk_tiles = B;
+  void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  const size_t avail = ws_bytes - (reinterpret_cast<uintptr_t>(base) - reinterpret_cast<uintptr_t>(ws));
+  const Workspace wsp = carve(e, base, chunk_tiles, N);
+  if (ws == nullptr || wsp.total > avail) return fail(VITOCM_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", wsp.total + 1024, ws_bytes);
+  const LayerW& last = e->layers[e->cfg.depth - 1];
+  const size_t cls_smem = static_cast<size_t>(D + 64 + N + 32) * sizeof(float);
+  static size_t cls_smem_set = 0;
+  if (cls_smem > 48 * 1024 && cls_smem > cls_smem_set) {
+    CUDA_TRY(cudaFuncSetAttribute(cls_attn_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cls_smem)));
+    cls_smem_set = cls_smem;
+  }
+  for (int b0 = 0; b0 < B; b0 += chunk_tiles) {
+    const int bc = (B - b0 < chunk_tiles) ? (B - b0) : chunk_tiles;
+    const int M = bc * N;
+    TRY(run_patch_embed(e, x + static_cast<long long>(b0) * C * H * W, bc, H, W, pos, nullptr, wsp.X, st));
+    for (int l = 0; l + 1 < e->cfg.depth; ++l) TRY(block_forward(e, l, wsp, bc, N, st));
+    // last block: LN1 (split) -> K projection in split precision -> fp32 K -> CLS-row softmax
+    float* KF = reinterpret_cast<float*>(wsp.HID);
+    TRY(run_layernorm(wsp.X, last.ln1w, last.ln1b, wsp.XN, 2LL * D, 1, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
+    TRY(run_gemm(e, wsp.XN, 2LL * D, last.wk_split.p, 2LL * D, M, D, D, 1, EPI_BIAS_F32, last.bqkv + D, KF, D, 0, 0, st));
+    dim3 grid(heads, bc);
+    cls_attn_row_kernel<<<grid, 256, cls_smem, st>>>(wsp.X, last.ln1w, last.ln1b, e->cfg.ln_eps, last.wqkv_f32, last.bqkv, KF,
+                                                     out_rows + static_cast<long long>(b0) * heads * N, N, D, heads, e->cfg.qk_scale);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int vitocm_block_forward(vitocm_engine* e, int layer, float* X, int B, int n_tokens, void* ws, size_t ws_bytes, void* stream) {
+  TRY(check_engine(e));
+  if (layer < 0 || layer >= e->cfg.depth) return fail(VITOCM_ERR_INVALID, "layer %d out of range", layer);
+  void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  const size_t avail = ws_bytes - (reinterpret_cast<uintptr_t>(base) - reinterpret_cast<uintptr_t>(ws));
+  Workspace wsp = carve(e, base, B, n_tokens);
+  if (ws == nullptr || wsp.total > avail) return fail(VITOCM_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", wsp.total + 1024, ws_bytes);
+  wsp.X = X;  // operate in place on the caller's token stream
+  return block_forward(e, layer, wsp, B, n_tokens, static_cast<cudaStream_t>(stream));
+}
+
+int vitocm_block_attn_probs(vitocm_engine* e, int layer, const float* X, int B, int n_tokens, float* attn, float* qkv_out,
+                            void* ws, size_t ws_bytes, void* stream) {
+  TRY(check_engine(e));
+  if (layer < 0 || layer >= e->cfg.depth) return fail(VITOCM_ERR_INVALID, "layer %d out of range", layer);
+  if (qkv_out == nullptr || attn == nullptr) return fail(VITOCM_ERR_INVALID, "attn and qkv_out are required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = e->cfg.embed_dim, P = e->parts, S = e->split, heads = e->cfg.num_heads, N = n_tokens;
+  void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  const size_t avail = ws_bytes - (reinterpret_cast<uintptr_t>(base) - reinterpret_cast<uintptr_t>(ws));
+  const Workspace wsp = carve(e, base, B, N);
+  if (ws == nullptr || wsp.total > avail) return fail(VITOCM_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", wsp.total + 1024, ws_bytes);
+  const LayerW& L = e->layers[layer];
+  const int M = B * N;
+  TRY(run_layernorm(X, L.ln1w, L.ln1b, wsp.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
+  TRY(run_gemm(e, wsp.XN, 2LL * D, L.wqkv.p, static_cast<long long>(D) * P, M, 3 * D, D, S, EPI_BIAS_F32, L.bqkv, qkv_out, 3LL * D, 0, 0, st));
+  const int kchunk = 256;
+  int qrows = AP_QROWS;
+  auto smem_for = [&](int qr) { return static_cast<size_t>(kchunk * 65 + qr * 64 + static_cast<size_t>(qr) * N) * sizeof(float); };
+  while (qrows > 1 && smem_for(qrows) > 200 * 1024) qrows >>= 1;
+  const size_t smem = smem_for(qrows);
+  if (smem > 220 * 1024) return fail(VITOCM_ERR_INVALID, "n_tokens=%d too large for attn_probs", N);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    CUDA_TRY(cudaFuncSetAttribute(attn_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    smem_set = smem;
+  }
+  dim3 grid((N + qrows - 1) / qrows, heads, B);
+  attn_probs_kernel<<<grid, 256, smem, st>>>(qkv_out, attn, N, D, heads, e->cfg.qk_scale, kchunk, qrows);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int vitocm_final_norm(vitocm_engine* e, const float* X, float* out, int M, void* stream) {
+  TRY(check_engine(e));
+  const int D = e->cfg.embed_dim;
+  return run_layernorm(X, e->w("norm.weight"), e->w("norm.bias"), nullptr, 0, 0, 0, out, D, M, D, e->cfg.ln_eps,
+                       static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------ post-processing
+int vitocm_head_mean(const float* rows, float* lowres, int T, int heads, int n_tokens, int mode, void* stream) {
+  if (T <= 0) return 0;
+  head_mean_kernel<<<T, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, lowres, heads, n_tokens, mode);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int vitocm_tile_threshold(const float* lowres, const float* x, int T, int C, int S, int lh, int lw, uint8_t* masks,
+                          int* thresholds, float* att_out, const float* att_in, const uint8_t* img_in, void* stream) {
+  if (T <= 0) return 0;
+  if (lowres == nullptr && att_in == nullptr) return fail(VITOCM_ERR_INVALID, "tile_threshold needs lowres or att_in");
+  if (x == nullptr && img_in == nullptr) return fail(VITOCM_ERR_INVALID, "tile_threshold needs x or img_in");
+  tile_threshold_kernel<<<T, 512, 0, static_cast<cudaStream_t>(stream)>>>(lowres, x, C, S, lh, lw, masks, thresholds, att_out, att_in, img_in);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int vitocm_extract_tiles(const uint8_t* mosaic, int mos_h, int mos_w, int64_t pitch, int n, int W, int S, int t0, int T, int C,
+                         float* x, void* stream) {
+  if (T <= 0) return 0;
+  const long long total = static_cast<long long>(T) * W * W;
+  extract_tiles_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(mosaic, mos_h, mos_w, pitch, n, W, S, t0, T, C, x);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static StitchGeom make_geom(int n, int W, int S, int lh, int lw) {
+  StitchGeom g;
+  g.n = n; g.W = W; g.S = S; g.step = W - S; g.E = (n - 1) * S + W; g.lh = lh; g.lw = lw;
+  g.scale = static_cast<double>(lw) / static_cast<double>(W);
+  return g;
+}
+static int check_geom(int n, int W, int S, int y_begin, int y_end) {
+  if (n < 1 || S < 1 || W <= S) return fail(VITOCM_ERR_INVALID, "bad sliding-window geometry n=%d W=%d S=%d", n, W, S);
+  const int E = (n - 1) * S + W;
+  if (y_begin < 0 || y_end > E || y_begin > y_end) return fail(VITOCM_ERR_INVALID, "bad row band [%d,%d) for extent %d", y_begin, y_end, E);
+  return 0;
+}
+
+int vitocm_stitch_gray(const uint8_t* mosaic, int mos_h, int mos_w, int64_t pitch, int n, int W, int S, const double* wtab,
+                       int y_begin, int y_end, uint8_t* out, void* stream) {
+  TRY(check_geom(n, W, S, y_begin, y_end));
+  if (y_end == y_begin) return 0;
+  const StitchGeom g = make_geom(n, W, S, 1, 1);
+  stitch_gray_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mosaic, mos_h, mos_w, pitch, g, wtab, y_begin, y_end, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int vitocm_minmax_init(int* minmax_ord, void* stream) {
+  const int init[2] = {0x7fffffff, static_cast<int>(0x80000000u)};
+  CUDA_TRY(cudaMemcpyAsync(minmax_ord, init, sizeof(init), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int vitocm_stitch_minmax(const float* lowres, int n, int W, int S, int lh, int lw, const double* wtab, int y_begin, int y_end,
+                         int* minmax_ord, float* map_out, const float* map_in, void* stream) {
+  TRY(check_geom(n, W, S, y_begin, y_end));
+  if (y_end == y_begin) return 0;
+  const StitchGeom g = make_geom(n, W, S, lh, lw);
+  stitch_minmax_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      lowres, g, wtab, y_begin, y_end, minmax_ord, map_out, map_in);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int vitocm_stitch_hist(const float* lowres, int n, int W, int S, int lh, int lw, const double* wtab, const uint8_t* gray,
+                       const int* minmax_ord, int y_begin, int y_end, uint64_t* hists, const float* map_in, void* stream) {
+  TRY(check_geom(n, W, S, y_begin, y_end));
+  if (y_end == y_begin) return 0;
+  const StitchGeom g = make_geom(n, W, S, lh, lw);
+  stitch_hist_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      lowres, g, wtab, gray, minmax_ord, y_begin, y_end, reinterpret_cast<unsigned long long*>(hists), map_in);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int vitocm_otsu(const uint64_t* hists, int nhist, int* thresholds, void* stream) {
+  if (nhist <= 0) return 0;
+  otsu_kernel<<<(nhist + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const unsigned long long*>(hists), nhist, thresholds);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int vitocm_stitch_mask(const float* lowres, int n, int W, int S, int lh, int lw, const double* wtab, const uint8_t* gray,
+                       const int* minmax_ord, const int* thr, int y_begin, int y_end, uint8_t* th, uint8_t* th2, uint8_t* th3,
+                       const float* map_in, void* stream) {
+  TRY(check_geom(n, W, S, y_begin, y_end));
+  if (y_end == y_begin) return 0;
+  const StitchGeom g = make_geom(n, W, S, lh, lw);
+  stitch_mask_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      lowres, g, wtab, gray, minmax_ord, thr, y_begin, y_end, th, th2, th3, map_in);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int vitocm_concat_crops_f32(const float* crops, int n, int W, int S, const double* wtab, float* out, void* stream) {
+  TRY(check_geom(n, W, S, 0, 0));
+  const StitchGeom g = make_geom(n, W, S, 1, 1);
+  concat_crops_f32_kernel<<<grid_for(static_cast<long long>(g.E) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(crops, g, wtab, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int vitocm_concat_crops_u8(const uint8_t* crops, int n, int W, int S, int C, const double* wtab, uint8_t* out, void* stream) {
+  TRY(check_geom(n, W, S, 0, 0));
+  const StitchGeom g = make_geom(n, W, S, 1, 1);
+  concat_crops_u8_kernel<<<grid_for(static_cast<long long>(g.E) * g.E * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(crops, g, C, wtab, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int vitocm_crop_u8(const uint8_t* img, int img_h, int img_w, int C, int ny, int nx, int W, int S, uint8_t* crops, void* stream) {
+  if (ny <= 0 || nx <= 0) return 0;
+  crop_u8_kernel<<<grid_for(static_cast<long long>(ny) * nx * W * W * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, img_h, img_w, C, ny, nx, W, S, crops);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ kernel-level entry points
+int vitocm_gemm(vitocm_engine* e, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int split_in,
+                int epilogue, const float* bias, void* out, int64_t ldo, int split_out, int lo_off, void* stream) {
+  if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
+  return run_gemm(e, A, lda, B, ldb, M, N, K, split_in, epilogue, bias, out, ldo, split_out, lo_off, static_cast<cudaStream_t>(stream));
+}
+
+int vitocm_attention(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo, void* stream) {
+  if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
+  return run_attention(e, qkv, ld, B, n_tokens, ctx, ldo, static_cast<cudaStream_t>(stream));
+}
+
+int vitocm_layernorm(vitocm_engine* e, const float* X, const float* gamma, const float* beta, void* out_bf16, int64_t ldo,
+                     int split, int lo_off, int M, void* stream) {
+  if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
+  return run_layernorm(X, gamma, beta, out_bf16, ldo, split, lo_off, nullptr, 0, M, e->cfg.embed_dim, e->cfg.ln_eps,
+                       static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,284 @@
+"""Drop-in for the reference's mosaic script ``sw_processing.py`` on B200.
+
+Function-level mirrors (same names / arguments as the reference, host arrays in and out):
+  ``sliding_window`` (SSS/sw_processing.py:151-163), ``concat_crops`` + blends (:113-149),
+  ``threshold`` (:37-81).
+Device pipeline: ``MosaicSegmenter`` = the ``__main__`` body (:223-262) -- sliding window, per-crop
+ViT CLS attention, head mean, per-tile min-max, resize pair, ramp-blended stitching, global
+min-max, img*att, Otsu -- with the mosaic, every tile and the masks resident in HBM, tiles
+batched through the engine, and (optionally) sharded over ranks of a torch.distributed group:
+each rank runs the ViT on a contiguous slice of the tiles, the low-res maps are all-gathered,
+each rank thresholds a band of output rows, {min, max, histograms} are all-reduced, and the mask
+bands are gathered on rank 0 ("only a final mask gather").
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, cur_stream, ptr
+from .utils import _dev, _save_gray, head_mean_maps
+
+
+def _wtab(window_size: int, stride: int, device) -> torch.Tensor:
+    """numpy.linspace(1, 0, window - stride) -- the blend ramp of :138/:145, bit-identical."""
+    return torch.from_numpy(np.linspace(1, 0, window_size - stride)).to(device)
+
+
+def grid_size(size: int, stride: int) -> int:
+    """Number of window origins per axis: len(range(0, size - 2*stride, stride)) (:156-157)."""
+    return len(range(0, size - stride * 2, stride))
+
+
+# ----------------------------------------------------------------------------- function mirrors
+def sliding_window(image, stride=128, window_size=384):
+    """SSS/sw_processing.py:151-163.  image: PIL image or uint8 array [H, W(, C)].
+    Returns the list of uint8 crops (row-major; zero padded beyond the image like PIL's crop)."""
+    dev = _dev()
+    arr = np.ascontiguousarray(np.array(image), dtype=np.uint8)
+    squeeze = arr.ndim == 2
+    if squeeze:
+        arr = arr[:, :, None]
+    H, W, C = arr.shape
+    # the reference unpacks PIL's (width, height) as `height, width`: y iterates over the width
+    ny, nx = grid_size(W, stride), grid_size(H, stride)
+    if ny <= 0 or nx <= 0:
+        return []
+    d_img = torch.from_numpy(arr).to(dev)
+    crops = torch.empty(ny * nx, window_size, window_size, C, dtype=torch.uint8, device=dev)
+    check(_lib.load_library().vitocm_crop_u8(ptr(d_img), H, W, C, ny, nx, window_size, stride, ptr(crops), cur_stream()))
+    out = crops.cpu().numpy()
+    if squeeze:
+        out = out[..., 0]
+    return [out[i] for i in range(out.shape[0])]
+
+
+def concat_crops(crops, stride, window_size):
+    """SSS/sw_processing.py:113-134: row-major n x n grid of crops, overlapping by window - stride,
+    seams blended with a linear ramp, first along x inside each strip then along y.  float32 crops
+    accumulate in float32, uint8 crops truncate at every seam -- as the reference's dtypes do."""
+    dev = _dev()
+    n = int(np.sqrt(len(crops)))
+    first = np.asarray(crops[0])
+    lib = _lib.load_library()
+    wtab = _wtab(window_size, stride, dev)
+    E = (n - 1) * stride + window_size
+    if first.dtype == np.uint8:
+        stack = np.ascontiguousarray(np.stack([np.asarray(c) for c in crops[:n * n]]), dtype=np.uint8)
+        squeeze = stack.ndim == 3
+        if squeeze:
+            stack = stack[..., None]
+        C = stack.shape[-1]
+        d = torch.from_numpy(stack).to(dev)
+        out = torch.empty(E, E, C, dtype=torch.uint8, device=dev)
+        check(lib.vitocm_concat_crops_u8(ptr(d), n, window_size, stride, C, ptr(wtab), ptr(out), cur_stream()))
+        res = out.cpu().numpy()
+        return res[..., 0] if squeeze else res
+    stack = np.ascontiguousarray(np.stack([np.asarray(c, dtype=np.float32) for c in crops[:n * n]]))
+    d = torch.from_numpy(stack).to(dev)
+    out = torch.empty(E, E, dtype=torch.float32, device=dev)
+    check(lib.vitocm_concat_crops_f32(ptr(d), n, window_size, stride, ptr(wtab), ptr(out), cur_stream()))
+    return out.cpu().numpy()
+
+
+def _threshold_device(lib, lowres, geom, wtab, gray, map_in, y0, y1, group=None, want=("th", "th3")):
+    """Three passes over output rows [y0, y1): min/max -> histograms -> Otsu -> masks."""
+    n, W, S, lh, lw = geom
+    E = (n - 1) * S + W
+    dev = gray.device
+    st = cur_stream()
+    minmax = torch.empty(2, dtype=torch.int32, device=dev)
+    check(lib.vitocm_minmax_init(ptr(minmax), st))
+    check(lib.vitocm_stitch_minmax(ptr(lowres), n, W, S, lh, lw, ptr(wtab), y0, y1, ptr(minmax), None, ptr(map_in), st))
+    if group is not None:
+        allreduce_minmax(minmax, group)
+    hists = torch.zeros(3, 256, dtype=torch.int64, device=dev)
+    check(lib.vitocm_stitch_hist(ptr(lowres), n, W, S, lh, lw, ptr(wtab), ptr(gray), ptr(minmax), y0, y1, ptr(hists),
+                                 ptr(map_in), st))
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(hists, op=dist.ReduceOp.SUM, group=group)
+    thr = torch.empty(3, dtype=torch.int32, device=dev)
+    check(lib.vitocm_otsu(ptr(hists), 3, ptr(thr), st))
+    rows = y1 - y0
+    masks = {k: torch.empty(rows, E, dtype=torch.uint8, device=dev) for k in want}
+    check(lib.vitocm_stitch_mask(ptr(lowres), n, W, S, lh, lw, ptr(wtab), ptr(gray), ptr(minmax), ptr(thr), y0, y1,
+                                 ptr(masks.get("th")), ptr(masks.get("th2")), ptr(masks.get("th3")), ptr(map_in), st))
+    return masks, thr, minmax, hists
+
+
+def threshold(img, attention, output_directory="", save=True, name=None):
+    """SSS/sw_processing.py:37-81.  img: PIL "L" image or uint8 array [E, E]; attention: float array
+    [E, E] (the stitched map).  Returns (th, th2, th3): Otsu of img * normalised attention, Otsu of
+    the image (the reference uses skimage's Otsu for this off-path output; OpenCV's rule here), Otsu
+    of the attention heat-map."""
+    dev = _dev()
+    img_np = np.ascontiguousarray(np.array(img), dtype=np.uint8)
+    att_np = np.ascontiguousarray(np.asarray(attention), dtype=np.float32)
+    if img_np.shape != att_np.shape or img_np.ndim != 2 or img_np.shape[0] != img_np.shape[1]:
+        raise ValueError("threshold expects a square gray image and an attention map of the same size")
+    E = img_np.shape[0]
+    gray = torch.from_numpy(img_np).to(dev)
+    amap = torch.from_numpy(att_np).to(dev)
+    # geometry with a single "tile" covering the whole extent: n=1, W=E (S only has to be < W)
+    geom = (1, E, E - 1 if E > 1 else 1, 1, 1)
+    wtab = torch.zeros(max(E - geom[2], 1), dtype=torch.float64, device=dev)
+    masks, thr, _, _ = _threshold_device(_lib.load_library(), None, geom, wtab, gray, amap, 0, E, want=("th", "th2", "th3"))
+    th, th2, th3 = (masks[k].cpu().numpy() for k in ("th", "th2", "th3"))
+    if save:
+        import os
+        sub = (name + "/") if name is not None else ""
+        os.makedirs(os.path.join(output_directory, sub) or ".", exist_ok=True)
+        _save_gray(os.path.join(output_directory, sub, "OTSU_th_average.png"), th)
+        _save_gray(os.path.join(output_directory, "OTSU_th_original.png"), th2)
+        _save_gray(os.path.join(output_directory, "heatmap_otsu_attention.png"), th3)
+    return th, th2, th3
+
+
+# ----------------------------------------------------------------------------- device pipeline
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced [begin, end) slice of `total` items for `rank` of `world`."""
+    base, rem = divmod(total, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def allgather_shards(local: torch.Tensor, total: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """Every rank holds items shard_range(total, rank, world) along dim 0; returns all `total`
+    items on every rank (one padded all_gather; works for NCCL on CUDA and gloo on CPU tensors)."""
+    if world == 1:
+        return local.contiguous()
+    import torch.distributed as dist
+    per = (total + world - 1) // world
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    out = []
+    for r in range(world):
+        a, b = shard_range(total, r, world)
+        out.append(parts[r][: b - a])
+    return torch.cat(out).contiguous()
+
+
+def gather_bands(band: torch.Tensor, total_rows: int, rank: int, world: int, group=None, dst: int = 0):
+    """Row bands shard_range(total_rows, r, world) -> the full [total_rows, ...] tensor on group rank
+    `dst` (None elsewhere): the final mask gather."""
+    if world == 1:
+        return band
+    import torch.distributed as dist
+    per = (total_rows + world - 1) // world
+    pad = torch.zeros((per,) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
+    pad[: band.shape[0]] = band
+    buf = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    gdst = dist.get_global_rank(group, dst) if group is not None else dst
+    dist.gather(pad, buf, dst=gdst, group=group)
+    if rank != dst:
+        return None
+    out = []
+    for r in range(world):
+        a, b = shard_range(total_rows, r, world)
+        out.append(buf[r][: b - a])
+    return torch.cat(out)
+
+
+def allreduce_minmax(minmax_ord: torch.Tensor, group=None) -> None:
+    """minmax_ord int32 [2] (order-preserving keys): element 0 reduces with MIN, element 1 with MAX."""
+    import torch.distributed as dist
+    dist.all_reduce(minmax_ord[0:1], op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(minmax_ord[1:2], op=dist.ReduceOp.MAX, group=group)
+
+
+class MosaicSegmenter:
+    """Sliding-window white-matter segmentation of a gray mosaic (SSS/sw_processing.py:223-262).
+
+    model: vitocm VisionTransformer (patch 8); window/stride: crop geometry (reference default
+    384/128; BASELINE configs use 224/112); tile_batch: tiles per engine call; group: optional
+    torch.distributed process group (NCCL) to shard over -- None = single GPU."""
+
+    def __init__(self, model, window=384, stride=128, tile_batch=64, group=None):
+        self.model = model
+        self.window, self.stride, self.tile_batch = int(window), int(stride), int(tile_batch)
+        self.group = group
+        if group is not None:
+            import torch.distributed as dist
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self.patch = model.patch_embed.patch_size
+        if self.window % self.patch:
+            raise ValueError("window must be a multiple of the patch size")
+
+    @torch.no_grad()
+    def lowres_maps(self, mosaic: torch.Tensor, t0: int, t1: int) -> torch.Tensor:
+        """Per-tile normalised low-res maps [t1-t0, h, w] for tiles t0..t1-1 of the n x n grid."""
+        lib = _lib.load_library()
+        W, S, C = self.window, self.stride, self.model.in_chans
+        n = grid_size(mosaic.shape[0], S)
+        lh = W // self.patch
+        out = torch.empty(max(t1 - t0, 0), lh * lh, dtype=torch.float32, device=mosaic.device)
+        xbuf = torch.empty(self.tile_batch, C, W, W, dtype=torch.float32, device=mosaic.device)
+        for a in range(t0, t1, self.tile_batch):
+            b = min(a + self.tile_batch, t1)
+            x = xbuf[: b - a]
+            check(lib.vitocm_extract_tiles(ptr(mosaic), mosaic.shape[0], mosaic.shape[1], mosaic.stride(0), n, W, S, a,
+                                           b - a, C, ptr(x), cur_stream()))
+            rows = self.model.cls_attention_rows(x)
+            out[a - t0:b - t0] = head_mean_maps(rows, per_tile_minmax255=True)
+        return out.view(-1, lh, lh)
+
+    @torch.no_grad()
+    def segment(self, mosaic: torch.Tensor, want=("th", "th3"), gather: bool = True):
+        """mosaic: uint8 gray [E0, E0] CUDA tensor.  Returns dict with the masks of this rank's row
+        band (and, on rank 0 with gather=True, the full [E, E] masks), thresholds, min/max, lowres."""
+        if mosaic.dtype != torch.uint8 or mosaic.dim() != 2 or not mosaic.is_cuda or mosaic.shape[0] != mosaic.shape[1]:
+            raise ValueError("mosaic must be a square uint8 gray CUDA tensor")
+        lib = _lib.load_library()
+        W, S = self.window, self.stride
+        n = grid_size(mosaic.shape[0], S)
+        if n < 1:
+            raise ValueError("mosaic smaller than one window")
+        T = n * n
+        lh = W // self.patch
+        E = (n - 1) * S + W
+        dev = mosaic.device
+        wtab = _wtab(W, S, dev)
+        # 1. ViT on this rank's tiles
+        t0, t1 = shard_range(T, self.rank, self.world)
+        mine = self.lowres_maps(mosaic, t0, t1)
+        lowres = allgather_shards(mine, T, self.rank, self.world, self.group)
+        # 2. this rank's band of output rows
+        y0, y1 = shard_range(E, self.rank, self.world)
+        gray = torch.empty(E, E, dtype=torch.uint8, device=dev)
+        check(lib.vitocm_stitch_gray(ptr(mosaic), mosaic.shape[0], mosaic.shape[1], mosaic.stride(0), n, W, S, ptr(wtab),
+                                     y0, y1, ptr(gray), cur_stream()))
+        masks, thr, minmax, hists = _threshold_device(lib, lowres, (n, W, S, lh, lh), wtab, gray, None, y0, y1,
+                                                      group=self.group if self.world > 1 else None, want=want)
+        out = dict(band=(y0, y1), thresholds=thr, minmax_ord=minmax, hists=hists, lowres=lowres, extent=E, grid=n)
+        out.update({k + "_band": v for k, v in masks.items()})
+        # 3. final mask gather on rank 0
+        if self.world > 1 and gather:
+            for k, v in masks.items():
+                full = gather_bands(v, E, self.rank, self.world, self.group, dst=0)
+                if full is not None:
+                    out[k] = full
+        elif self.world == 1:
+            out.update(masks)
+        return out
+
+    @torch.no_grad()
+    def stitched_map(self, lowres: torch.Tensor) -> torch.Tensor:
+        """The full stitched attention map [E, E] fp32 (:259) from low-res maps (for inspection / tests)."""
+        lib = _lib.load_library()
+        W, S = self.window, self.stride
+        n = int(round(lowres.shape[0] ** 0.5))
+        E = (n - 1) * S + W
+        lh = lowres.shape[-1]
+        wtab = _wtab(W, S, lowres.device)
+        minmax = torch.empty(2, dtype=torch.int32, device=lowres.device)
+        out = torch.empty(E, E, dtype=torch.float32, device=lowres.device)
+        check(lib.vitocm_minmax_init(ptr(minmax), cur_stream()))
+        check(lib.vitocm_stitch_minmax(ptr(lowres.contiguous()), n, W, S, lh, lh, ptr(wtab), 0, E, ptr(minmax), ptr(out),
+                                       None, cur_stream()))
+        return out

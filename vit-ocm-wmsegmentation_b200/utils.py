@@ -1,0 +1,114 @@
+"""Drop-in for the hot-path half of the reference's ``utils.py`` (eval / PGT flavour):
+``compute_attention`` (SSS/utils.py:229-235), ``min_max_normalize`` (:55-60), ``threshold``
+(:62-115) and the plain-tiling ``concat_crops`` (:304-317), plus ``attention_masks`` -- the
+batched, device-resident version of the per-image loop body at SSS/eval.py:136-173.
+
+All arithmetic runs in libvitocm.so kernels; torch is used for device buffers only.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, cur_stream, ptr
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise _lib.VitocmError("vitocm needs a CUDA device (B200, sm_100a); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def head_mean_maps(cls_rows: torch.Tensor, per_tile_minmax255: bool = False) -> torch.Tensor:
+    """[T, heads, N] CLS rows -> [T, N-1] low-res maps (head mean; optionally the per-tile
+    min-max * 255 of SSS/sw_processing.py:253-254)."""
+    cls_rows = cls_rows.contiguous()
+    T, H, N = cls_rows.shape
+    out = torch.empty(T, N - 1, dtype=torch.float32, device=cls_rows.device)
+    check(_lib.load_library().vitocm_head_mean(ptr(cls_rows), ptr(out), T, H, N, int(per_tile_minmax255), cur_stream()))
+    return out
+
+
+def compute_attention(attentions, query, w_featmap, h_featmap, patch_size):
+    """SSS/utils.py:229-235: attention of `query` for batch element 0, per head, nearest-upsampled
+    by the patch size, as a host numpy array [nh, w*p, h*p]; returns (array, nh)."""
+    a0 = attentions[0]
+    nh = a0.shape[1]
+    row = a0[0, :, query, 1:]                       # LazyAttention serves query == 0 from the CLS rows
+    row = row.reshape(nh, w_featmap, h_featmap)
+    up = row.repeat_interleave(patch_size, dim=1).repeat_interleave(patch_size, dim=2)   # nearest: a copy, no arithmetic
+    return up.cpu().numpy(), nh
+
+
+def min_max_normalize(image):
+    """SSS/utils.py:55-60 (host helper kept for callers; `threshold` does this on the device)."""
+    mn, mx = np.min(image), np.max(image)
+    if mx == mn:
+        return image
+    return (image - mn) / (mx - mn)
+
+
+def _save_gray(path, arr):
+    from PIL import Image
+    Image.fromarray(np.asarray(arr, dtype=np.uint8)).save(path)
+
+
+def threshold(img, attention, output_directory="", save=True, name=None):
+    """SSS/utils.py:62-115.  img: PIL "L" image or uint8 array [S, S]; attention: float array [S, S].
+    Returns (th, th2, th3) uint8 {0,255} host arrays: Otsu of the 0.6/0.4 image/attention blend
+    ("ours"), Otsu of the image, Otsu of the attention heat-map ("heatmap_threshold")."""
+    dev = _dev()
+    img_np = np.ascontiguousarray(np.array(img), dtype=np.uint8)
+    att_np = np.ascontiguousarray(np.asarray(attention), dtype=np.float32)
+    if img_np.ndim != 2 or img_np.shape != att_np.shape or img_np.shape[0] != img_np.shape[1]:
+        raise ValueError("threshold expects a square gray image and an attention map of the same size")
+    S = img_np.shape[0]
+    d_img = torch.from_numpy(img_np).to(dev)
+    d_att = torch.from_numpy(att_np).to(dev)
+    masks = torch.empty(1, 3, S, S, dtype=torch.uint8, device=dev)
+    thr = torch.empty(1, 3, dtype=torch.int32, device=dev)
+    check(_lib.load_library().vitocm_tile_threshold(None, None, 1, 1, S, 1, 1, ptr(masks), ptr(thr), None, ptr(d_att),
+                                                    ptr(d_img), cur_stream()))
+    th, th2, th3 = (m.cpu().numpy() for m in masks[0])
+    if save:
+        sub = (name + "/") if name is not None else ""
+        os.makedirs(os.path.join(output_directory, sub) or ".", exist_ok=True)
+        _save_gray(os.path.join(output_directory, sub, "OTSU_th_average.png"), th)
+        _save_gray(os.path.join(output_directory, "OTSU_th_original.png"), th2)
+        _save_gray(os.path.join(output_directory, "heatmap_otsu_attention.png"), th3)
+    return th, th2, th3
+
+
+def concat_crops(crops):
+    """SSS/utils.py:304-317: non-overlapping row-major tiling of n*n crops (pure data movement)."""
+    n = int(np.sqrt(len(crops)))
+    rows = [np.concatenate(list(crops[i * n:(i + 1) * n]), axis=1) for i in range(n)]
+    return np.concatenate(rows, axis=0)
+
+
+@torch.no_grad()
+def attention_masks(model, x: torch.Tensor, return_attention: bool = False):
+    """Device-resident, batched SSS/eval.py:136-173 (`--crop 1`): for every image of x [B, C, S, S]
+    the last-layer CLS attention -> head mean -> bilinear x p -> utils.threshold.
+    Returns dict(masks [B, 3, S, S] u8 (ours, otsu, heatmap), thresholds [B, 3] int32, lowres [B, h, w]
+    [, attention [B, S, S]])."""
+    rows = model.cls_attention_rows(x)
+    B, _, S, S2 = x.shape
+    if S != S2:
+        raise ValueError("attention_masks expects square tiles")
+    p = model.patch_embed.patch_size
+    low = head_mean_maps(rows, per_tile_minmax255=False)
+    lh = lw = S // p
+    masks = torch.empty(B, 3, S, S, dtype=torch.uint8, device=x.device)
+    thr = torch.empty(B, 3, dtype=torch.int32, device=x.device)
+    att = torch.empty(B, S, S, dtype=torch.float32, device=x.device) if return_attention else None
+    xx = x.detach().to(torch.float32).contiguous()
+    check(_lib.load_library().vitocm_tile_threshold(ptr(low), ptr(xx), B, x.shape[1], S, lh, lw, ptr(masks), ptr(thr),
+                                                    ptr(att), None, None, cur_stream()))
+    out = dict(masks=masks, thresholds=thr, lowres=low.view(B, lh, lw), cls_rows=rows)
+    if return_attention:
+        out["attention"] = att
+    return out

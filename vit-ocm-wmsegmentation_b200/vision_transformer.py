@@ -1,0 +1,441 @@
+"""Drop-in for the reference's ``dino.vision_transformer`` on B200.
+
+Same constructor arguments, parameter names (state-dict keys) and methods as
+Self-supervised_segmentation/dino/vision_transformer.py:135-279 of the reference
+(``VisionTransformer``, ``vit_tiny`` / ``vit_small`` / ``vit_base``), but every forward runs in
+libvitocm.so (hand-written sm_100a kernels behind a C ABI).  The torch modules below only own
+the parameters -- they carry no arithmetic; there is no eager fallback.
+
+Hot path: ``get_intermediate_feat(x, n=1)`` -> (feat, attns, qkvs) computes the last-layer CLS
+attention rows eagerly with ``vitocm_forward_cls_attn`` and hands back *lazy* views for the
+three lists; ``attns[0][0, :, 0, 1:]`` (the only slice the reference's callers read,
+SSS/utils.py:232) is served from those rows, anything else materialises the full tensors
+through the block-by-block entry points.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import VitocmConfig, check, cur_stream, ptr
+
+PRECISIONS = {"bf16": 0, "fp32": 1}
+
+
+def _trunc_normal_(t: torch.Tensor, std: float = 0.02, a: float = -2.0, b: float = 2.0) -> torch.Tensor:
+    """Truncated-normal init with the reference's recipe (SSS/dino/utils.py:482-520)."""
+    cdf = lambda v: (1.0 + math.erf(v / math.sqrt(2.0))) / 2.0   # noqa: E731
+    lo, hi = cdf(a / std), cdf(b / std)
+    with torch.no_grad():
+        t.uniform_(2 * lo - 1, 2 * hi - 1).erfinv_().mul_(std * math.sqrt(2.0)).clamp_(min=a, max=b)
+    return t
+
+
+# --------------------------------------------------------------------------- parameter containers
+class _Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim, num_heads, qkv_bias):
+        super().__init__()
+        self.num_heads = num_heads
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, num_heads, mlp_ratio, qkv_bias, norm_layer):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = _Attention(dim, num_heads, qkv_bias)
+        self.norm2 = norm_layer(dim)
+        self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, img_size, patch_size, in_chans, embed_dim):
+        super().__init__()
+        self.img_size = img_size
+        self.patch_size = patch_size
+        self.num_patches = (img_size // patch_size) ** 2
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+
+# --------------------------------------------------------------------------- lazy results
+class LazyTensor:
+    """A tensor computed on first use.  Quacks like the tensor it stands for."""
+
+    def __init__(self, shape, producer):
+        self._shape = torch.Size(shape)
+        self._producer = producer
+        self._value = None
+
+    def materialize(self) -> torch.Tensor:
+        if self._value is None:
+            self._value = self._producer()
+            assert tuple(self._value.shape) == tuple(self._shape), (self._value.shape, self._shape)
+        return self._value
+
+    @property
+    def shape(self):
+        return self._shape
+
+    def size(self, dim=None):
+        return self._shape if dim is None else self._shape[dim]
+
+    def dim(self):
+        return len(self._shape)
+
+    def __len__(self):
+        return self._shape[0]
+
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
+
+    def __getattr__(self, name):          # anything else: behave as the real tensor
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        unwrap = lambda a: a.materialize() if isinstance(a, LazyTensor) else a   # noqa: E731
+        return func(*[unwrap(a) for a in args], **{k: unwrap(v) for k, v in kwargs.items()})
+
+
+class LazyAttention(LazyTensor):
+    """``attn`` of a block, [B, heads, N, N].  ``attn[b, :, 0, c]`` (CLS query, any column index)
+    is answered from the eagerly computed CLS rows; everything else materialises N x N."""
+
+    def __init__(self, shape, producer, cls_rows: torch.Tensor):
+        super().__init__(shape, producer)
+        self.cls_rows = cls_rows                    # [B, heads, N] fp32, device
+
+    def __getitem__(self, idx):
+        if self._value is None and isinstance(idx, tuple) and len(idx) >= 3:
+            q = idx[2]
+            if isinstance(q, int) and q == 0:
+                return self.cls_rows[(idx[0], idx[1]) + tuple(idx[3:])]
+        return self.materialize()[idx]
+
+
+# --------------------------------------------------------------------------- the model
+class VisionTransformer(nn.Module):
+    """Vision Transformer whose forward passes run in libvitocm (B200 / sm_100a).
+
+    Constructor signature follows the reference (vit.py:137-139); ``precision`` ("bf16" |
+    "fp32") and ``chunk_tiles`` are additions.  Dropout / stochastic depth must be 0 (the
+    reference's inference and MIM configurations all use 0)."""
+
+    def __init__(self, img_size=[224], patch_size=16, in_chans=3, num_classes=0, embed_dim=768, depth=12,
+                 num_heads=12, mlp_ratio=4., qkv_bias=False, qk_scale=None, drop_rate=0., attn_drop_rate=0.,
+                 drop_path_rate=0., norm_layer=nn.LayerNorm, precision="bf16", chunk_tiles=16, **kwargs):
+        super().__init__()
+        if drop_rate or attn_drop_rate or drop_path_rate:
+            raise NotImplementedError("vitocm: dropout / drop-path rates must be 0 on this path")
+        if embed_dim % num_heads or embed_dim // num_heads != 64:
+            raise NotImplementedError("vitocm kernels are specialised for head_dim 64")
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        self.num_features = self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.depth = depth
+        self.mlp_ratio = mlp_ratio
+        self.in_chans = in_chans
+        self.precision = precision
+        self.chunk_tiles = chunk_tiles
+        self.qk_scale = qk_scale or (embed_dim // num_heads) ** -0.5
+
+        self.patch_embed = _PatchEmbed(img_size[0], patch_size, in_chans, embed_dim)
+        n = self.patch_embed.num_patches
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, n + 1, embed_dim))
+        self.blocks = nn.ModuleList([_Block(embed_dim, num_heads, mlp_ratio, qkv_bias, norm_layer) for _ in range(depth)])
+        self.norm = norm_layer(embed_dim)
+        self.head = nn.Linear(embed_dim, num_classes) if num_classes > 0 else nn.Identity()
+        self.ln_eps = float(self.norm.eps)
+
+        _trunc_normal_(self.pos_embed, std=.02)
+        _trunc_normal_(self.cls_token, std=.02)
+        for m in self.modules():                   # vit.py:166-174
+            if isinstance(m, nn.Linear):
+                _trunc_normal_(m.weight, std=.02)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+
+        self._engine = None
+        self._engine_key = None
+        self._pos_cache = {}
+        self._ws = None
+        self._zero_qkv_bias = torch.zeros(3 * embed_dim)
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _engine_params(self):
+        """(state-dict key, tensor) for everything the C engine needs."""
+        out = [("cls_token", self.cls_token), ("patch_embed.proj.weight", self.patch_embed.proj.weight),
+               ("patch_embed.proj.bias", self.patch_embed.proj.bias), ("norm.weight", self.norm.weight),
+               ("norm.bias", self.norm.bias)]
+        if hasattr(self, "mask_token"):
+            out.append(("mask_token", self.mask_token))
+        for i, blk in enumerate(self.blocks):
+            pre = f"blocks.{i}."
+            qkv_b = blk.attn.qkv.bias if blk.attn.qkv.bias is not None else self._zero_qkv_bias
+            out += [(pre + "norm1.weight", blk.norm1.weight), (pre + "norm1.bias", blk.norm1.bias),
+                    (pre + "attn.qkv.weight", blk.attn.qkv.weight), (pre + "attn.qkv.bias", qkv_b),
+                    (pre + "attn.proj.weight", blk.attn.proj.weight), (pre + "attn.proj.bias", blk.attn.proj.bias),
+                    (pre + "norm2.weight", blk.norm2.weight), (pre + "norm2.bias", blk.norm2.bias),
+                    (pre + "mlp.fc1.weight", blk.mlp.fc1.weight), (pre + "mlp.fc1.bias", blk.mlp.fc1.bias),
+                    (pre + "mlp.fc2.weight", blk.mlp.fc2.weight), (pre + "mlp.fc2.bias", blk.mlp.fc2.bias)]
+        return out
+
+    def _weights_key(self):
+        return (self.precision, torch.cuda.current_device(),
+                tuple((p.data_ptr(), p._version) for _, p in self._engine_params()), self.pos_embed._version)
+
+    def refresh_engine(self):
+        """(Re)load the parameters into the C engine: repack to bf16 hi/lo etc."""
+        lib = _lib.load_library()
+        if not torch.cuda.is_available():
+            raise _lib.VitocmError("vitocm needs a CUDA device (B200, sm_100a); there is no CPU path")
+        if self._engine is None:
+            cfg = VitocmConfig(self.embed_dim, self.depth, self.num_heads, int(self.embed_dim * self.mlp_ratio),
+                               self.patch_embed.patch_size, self.in_chans, self.ln_eps, float(self.qk_scale),
+                               PRECISIONS[self.precision])
+            handle = C.c_void_p()
+            check(lib.vitocm_create(C.byref(cfg), C.byref(handle)))
+            self._engine = handle
+        for name, p in self._engine_params():
+            host = p.detach().to(device="cpu", dtype=torch.float32).contiguous()
+            check(lib.vitocm_load_weight(self._engine, name.encode(), host.data_ptr(), host.numel()))
+        check(lib.vitocm_finalize_weights(self._engine))
+        self._engine_key = self._weights_key()
+        self._pos_cache = {}
+
+    def _ensure_engine(self):
+        if self._engine is None or self._engine_key != self._weights_key():
+            self.refresh_engine()
+        return self._engine
+
+    def __del__(self):
+        eng = getattr(self, "_engine", None)
+        if eng is not None and _lib._lib is not None:
+            try:
+                _lib._lib.vitocm_destroy(eng)
+            except Exception:
+                pass
+
+    def set_precision(self, precision: str):
+        if precision not in PRECISIONS:
+            raise ValueError(precision)
+        if precision != self.precision:
+            self.precision = precision
+            if self._engine is not None:
+                _lib.load_library().vitocm_destroy(self._engine)
+                self._engine = None
+        return self
+
+    def _workspace(self, tiles: int, n_tokens: int, device) -> torch.Tensor:
+        need = int(_lib.load_library().vitocm_workspace_bytes(self._engine, tiles, n_tokens))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
+
+    # ------------------------------------------------------------------ position table
+    def interpolate_pos_encoding(self, x, w, h):
+        """vit.py:176-196.  `x` only supplies the token count, as in the reference."""
+        npatch = x.shape[1] - 1
+        return self._pos_table(npatch, w, h).unsqueeze(0)
+
+    def _pos_table(self, npatch: int, w: int, h: int) -> torch.Tensor:
+        """[1 + npatch, D] fp32 on the current device; bicubic resize of the stored table when the
+        input is not the constructor size (frozen weights -> computed once per shape and cached)."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        key = (npatch, w, h, dev)
+        hit = self._pos_cache.get(key)
+        if hit is not None:
+            return hit
+        pos = self.pos_embed.detach().to(device=dev, dtype=torch.float32)
+        N = pos.shape[1] - 1
+        if not (npatch == N and w == h):
+            p = self.patch_embed.patch_size
+            dim = pos.shape[-1]
+            w0, h0 = w // p + 0.1, h // p + 0.1
+            s = int(math.sqrt(N))
+            grid = nn.functional.interpolate(pos[:, 1:].reshape(1, s, s, dim).permute(0, 3, 1, 2),
+                                             scale_factor=(w0 / math.sqrt(N), h0 / math.sqrt(N)), mode="bicubic")
+            assert int(w0) == grid.shape[-2] and int(h0) == grid.shape[-1]
+            pos = torch.cat((pos[:, :1], grid.permute(0, 2, 3, 1).reshape(1, -1, dim)), dim=1)
+        table = pos[0].contiguous()
+        self._pos_cache[key] = table
+        return table
+
+    # ------------------------------------------------------------------ C-ABI calls
+    def _check_input(self, x):
+        if x.dim() != 4 or x.shape[1] != self.in_chans:
+            raise ValueError(f"expected [B,{self.in_chans},H,W], got {tuple(x.shape)}")
+        p = self.patch_embed.patch_size
+        if x.shape[2] % p or x.shape[3] % p:
+            raise ValueError("H and W must be multiples of the patch size")
+        if not x.is_cuda:
+            raise _lib.VitocmError("vitocm: input must be a CUDA tensor (no CPU path)")
+        return x.detach().to(torch.float32).contiguous()
+
+    def _tokens(self, x):
+        p = self.patch_embed.patch_size
+        return (x.shape[2] // p) * (x.shape[3] // p) + 1
+
+    @torch.no_grad()
+    def cls_attention_rows(self, x: torch.Tensor) -> torch.Tensor:
+        """get_last_selfattention(x)[:, :, 0, :] -> [B, heads, N] fp32, without forming N x N."""
+        x = self._check_input(x)
+        eng = self._ensure_engine()
+        B, _, H, W = x.shape
+        N = self._tokens(x)
+        pos = self._pos_table(N - 1, H, W)
+        chunk = max(1, min(self.chunk_tiles, B))
+        ws = self._workspace(chunk, N, x.device)
+        out = torch.empty(B, self.num_heads, N, dtype=torch.float32, device=x.device)
+        check(_lib.load_library().vitocm_forward_cls_attn(eng, ptr(x), B, H, W, ptr(pos), ptr(out), ptr(ws), ws.numel(),
+                                                          chunk, cur_stream()))
+        return out
+
+    @torch.no_grad()
+    def prepare_tokens(self, x, mask=None):
+        """vit.py:198-209 -> [B, N, D] fp32."""
+        x = self._check_input(x)
+        eng = self._ensure_engine()
+        B, _, H, W = x.shape
+        N = self._tokens(x)
+        pos = self._pos_table(N - 1, H, W)
+        X = torch.empty(B, N, self.embed_dim, dtype=torch.float32, device=x.device)
+        m = None if mask is None else mask.detach().reshape(B, -1).to(device=x.device, dtype=torch.float32).contiguous()
+        check(_lib.load_library().vitocm_prepare_tokens(eng, ptr(x), B, H, W, ptr(pos), ptr(m), ptr(X), cur_stream()))
+        return X
+
+    def _run_blocks(self, X, first, last):
+        """Blocks [first, last) in place on X [B, N, D], chunked over the batch."""
+        lib = _lib.load_library()
+        B, N, _ = X.shape
+        chunk = max(1, min(self.chunk_tiles, B))
+        ws = self._workspace(chunk, N, X.device)
+        for b0 in range(0, B, chunk):
+            xb = X[b0:b0 + chunk]
+            for layer in range(first, last):
+                check(lib.vitocm_block_forward(self._engine, layer, ptr(xb), xb.shape[0], N, ptr(ws), ws.numel(), cur_stream()))
+        return X
+
+    def _attn_probs(self, X, layer):
+        lib = _lib.load_library()
+        B, N, D = X.shape
+        attn = torch.empty(B, self.num_heads, N, N, dtype=torch.float32, device=X.device)
+        qkv = torch.empty(B * N, 3 * D, dtype=torch.float32, device=X.device)
+        chunk = max(1, min(self.chunk_tiles, B))
+        ws = self._workspace(chunk, N, X.device)
+        for b0 in range(0, B, chunk):
+            xb, ab, qb = X[b0:b0 + chunk], attn[b0:b0 + chunk], qkv[b0 * N:(b0 + chunk) * N]
+            check(lib.vitocm_block_attn_probs(self._engine, layer, ptr(xb), xb.shape[0], N, ptr(ab), ptr(qb), ptr(ws),
+                                              ws.numel(), cur_stream()))
+        # [B*N, 3D] -> [3, B, heads, N, dh]  (vit.py:80 reshape/permute; a view, no arithmetic)
+        qkv = qkv.reshape(B, N, 3, self.num_heads, D // self.num_heads).permute(2, 0, 3, 1, 4)
+        return attn, qkv
+
+    def _final_norm(self, X):
+        B, N, D = X.shape
+        out = torch.empty_like(X)
+        check(_lib.load_library().vitocm_final_norm(self._engine, ptr(X), ptr(out), B * N, cur_stream()))
+        return out
+
+    # ------------------------------------------------------------------ reference methods
+    @torch.no_grad()
+    def forward_feats(self, x):
+        """vit.py:218-223 -> norm(x) [B, N, D]."""
+        X = self.prepare_tokens(x)
+        self._run_blocks(X, 0, self.depth)
+        return self._final_norm(X)
+
+    def forward(self, x):
+        """vit.py:211-216 -> CLS embedding [B, D]."""
+        return self.forward_feats(x)[:, 0]
+
+    @torch.no_grad()
+    def get_last_selfattention(self, x):
+        """vit.py:239-246 -> attention of the last block, [B, heads, N, N] fp32."""
+        X = self.prepare_tokens(x)
+        self._run_blocks(X, 0, self.depth - 1)
+        return self._attn_probs(X, self.depth - 1)[0]
+
+    @torch.no_grad()
+    def get_intermediate_layers(self, x, n=1):
+        """vit.py:248-256 -> [norm(x_i)] for the n last blocks."""
+        X = self.prepare_tokens(x)
+        outs = []
+        for i in range(self.depth):
+            self._run_blocks(X, i, i + 1)
+            if self.depth - i <= n:
+                outs.append(self._final_norm(X))
+        return outs
+
+    @torch.no_grad()
+    def _intermediate_full(self, x, n):
+        X = self.prepare_tokens(x)
+        feat, attns, qkvs = [], [], []
+        for i in range(self.depth):
+            if self.depth - i <= n:
+                a, q = self._attn_probs(X, i)
+                attns.append(a)
+                qkvs.append(q)
+            self._run_blocks(X, i, i + 1)
+            if self.depth - i <= n:
+                feat.append(self._final_norm(X))
+        return feat, attns, qkvs
+
+    @torch.no_grad()
+    def get_intermediate_feat(self, x, n=1, lazy=True):
+        """vit.py:225-237 -> (feat list, attn list, qkv list) for the n last blocks.
+
+        With ``lazy`` (default) and n == 1 only the CLS attention rows are computed now; the
+        returned objects materialise the full tensors on demand (see module docstring)."""
+        if not lazy or n != 1:
+            return self._intermediate_full(x, n)
+        rows = self.cls_attention_rows(x)
+        B, H, N = rows.shape
+        D = self.embed_dim
+        cache = {}
+
+        def full():
+            if "v" not in cache:
+                cache["v"] = self._intermediate_full(x, 1)
+            return cache["v"]
+
+        feat = LazyTensor((B, N, D), lambda: full()[0][0])
+        attn = LazyAttention((B, H, N, N), lambda: full()[1][0], rows)
+        qkv = LazyTensor((3, B, H, N, D // H), lambda: full()[2][0])
+        return [feat], [attn], [qkv]
+
+
+def vit_tiny(patch_size=16, **kwargs):
+    return VisionTransformer(patch_size=patch_size, embed_dim=192, depth=12, num_heads=3, mlp_ratio=4, qkv_bias=True,
+                             norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+
+
+def vit_small(patch_size=16, **kwargs):
+    return VisionTransformer(patch_size=patch_size, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4, qkv_bias=True,
+                             norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+
+
+def vit_base(patch_size=16, **kwargs):
+    return VisionTransformer(patch_size=patch_size, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, qkv_bias=True,
+                             norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)

@@ -1,0 +1,12 @@
+"""Import shim: exposes the package in ``vit-ocm-wmsegmentation_b200/`` (a directory name that
+is not a valid Python identifier) as the module ``vitocm_b200``."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vit-ocm-wmsegmentation_b200")
+_spec = importlib.util.spec_from_file_location("vitocm_b200", os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["vitocm_b200"] = _mod
+_spec.loader.exec_module(_mod)
