@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- sliding-window segmentation throughput of the ViT-OCM hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --steps K --warmup W    (CPU arm: the reference algorithm on host cores)
+
+One "step" = one pass of the whole hot path over one synthetic gray mosaic: sliding window ->
+ViT-S/8 CLS attention rows per 224x224 tile -> head mean / per-tile min-max / bilinear / ramp-blended
+stitch -> global min-max -> img*att -> Otsu -> masks.  N=1 is BASELINE.json configs[1] (4096x4096,
+window 224, stride 112 -> 35x35 = 1225 tiles, stitched extent 4032^2 = 16.257 MP, bf16).  For N>1 the
+mosaic grows so that tiles per GPU stay ~1225 (weak scaling); tiles shard over ranks, low-res maps are
+all-gathered, {min,max,histograms} all-reduced and the mask bands gathered on rank 0.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WINDOW, STRIDE, PATCH = 224, 112, 8
+ARCHS = {"vit_small": dict(embed_dim=384, depth=12, num_heads=6), "vit_base": dict(embed_dim=768, depth=12, num_heads=12)}
+METRIC = "sliding_window_seg_megapixels_per_s"
+
+
+def flops_per_tile(D, depth, heads, N):
+    """Algorithmic FLOPs of the CLS-row path per tile: patch-embed, depth-1 full
+    blocks, last block K projection + q_cls.K^T; 2*M*N*K per contraction, softmax/LN/GELU excluded."""
+    n = N - 1
+    pe = 2 * n * (3 * PATCH * PATCH) * D
+    blk = 2 * N * D * 3 * D + 4 * N * N * D + 2 * N * D * D + 16 * N * D * D
+    last = 2 * N * D * D + 2 * D * D + 2 * N * D
+    return pe + (depth - 1) * blk + last
+
+
+def class_flops(cls, D, N, tiles, depth):
+    """Algorithmic FLOPs of all launches of one kernel class in a step."""
+    M = tiles * N
+    L = depth - 1
+    return {"gemm_qkv": 2 * M * D * 3 * D * L, "gemm_proj": 2 * M * D * D * L, "gemm_fc1_gelu": 2 * M * D * 4 * D * L,
+            "gemm_fc2": 2 * M * 4 * D * D * L, "attention": 4 * tiles * N * N * D * L, "gemm_k_last": 2 * M * D * D,
+            "patch_embed": 2 * tiles * (N - 1) * 192 * D}.get(cls, 0)
+
+
+def mosaic_geometry(n_gpus):
+    n = int(round(35 * math.sqrt(n_gpus)))
+    size = (n + 1) * STRIDE + 64          # range(0, size - 2*STRIDE, STRIDE) has exactly n origins; 4096 for n = 35
+    extent = (n - 1) * STRIDE + WINDOW
+    return n, size, extent
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 7 for i in range(4) if s[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_sample(arch, threads, n_s=3, repeats=1):
+    """The reference algorithm (oracle port, torch-CPU fp32 + numpy) on a bounded sample: n_s x n_s tiles
+    through get_intermediate_feat -> compute_attention -> mean -> per-tile min-max -> resize pair, then
+    concat_crops + threshold.  Returns (tiles_per_s, post_s_per_MP, sample description)."""
+    from oracle import post_oracle as PO
+    from oracle import vit_oracle as VO
+    torch.set_num_threads(threads)
+    cfg = VO.ViTConfig(**ARCHS[arch])
+    sd = VO.init_state_dict(cfg, seed=0)
+    size = (n_s + 1) * STRIDE + 64
+    mosaic = VO.synthetic_mosaic_u8(size, seed=4321)
+    crops = PO.sliding_window(mosaic, STRIDE, WINDOW)
+    t_tiles = t_post = 0.0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        rows = []
+        for c in crops:                                           # serial, batch 1, like the reference loop
+            x = torch.from_numpy(c).float().div(255.0)[None, None].expand(1, 3, -1, -1).contiguous()
+            feat, attns, qkvs = VO.get_intermediate_feat(sd, cfg, x, n=1)
+            rows.append(attns[0][0, :, 0, :].numpy())
+        t1 = time.perf_counter()
+        stitched, masks, gray = PO.mosaic_segment(np.stack(rows), mosaic, STRIDE, WINDOW, PATCH)
+        t2 = time.perf_counter()
+        t_tiles += t1 - t0
+        t_post += t2 - t1
+    ntiles = len(crops) * repeats
+    ext = (n_s - 1) * STRIDE + WINDOW
+    return ntiles / t_tiles, t_post / (repeats * ext * ext / 1e6), f"{n_s}x{n_s} tiles of {arch}/8 ({WINDOW}^2, stride {STRIDE}) + stitch/threshold of the {ext}^2 extent, x{repeats}"
+
+
+def cpu_value(tiles_per_s, post_s_per_mp, n_tiles, extent):
+    mp = extent * extent / 1e6
+    return mp / (n_tiles / tiles_per_s + post_s_per_mp * mp)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n, size, extent = mosaic_geometry(1)
+    vals = []
+    t_start = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        tps, ppm, sample = cpu_reference_sample(args.arch, threads, n_s=4 if args.arch == "vit_small" else 3)
+        if i >= args.warmup:
+            vals.append(cpu_value(tps, ppm, n * n, extent))
+    v = statistics.mean(vals)
+    mp = extent * extent / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * mp / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.arch}/8 sliding-window segmentation, {size}x{size} gray mosaic, window {WINDOW}, stride {STRIDE}, "
+                                   f"{n * n} tiles, extent {extent}^2", "note": "each step times a bounded sample and extrapolates linearly in tiles and pixels"},
+            "cpu_baseline": {"value": v, "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t_start}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arch", default="vit_small", choices=sorted(ARCHS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--chunk-tiles", type=int, default=32)
+    ap.add_argument("--tile-batch", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    import vitocm_b200 as vob
+    from oracle import vit_oracle as VO   # synthetic-input recipe only (shared with the tests)
+
+    a = ARCHS[args.arch]
+    torch.manual_seed(0)
+    model = getattr(vob, args.arch)(patch_size=PATCH, num_classes=0, precision=args.precision, chunk_tiles=args.chunk_tiles)
+    model = model.cuda().eval()
+    n, size, extent = mosaic_geometry(world)
+    T = n * n
+    N = (WINDOW // PATCH) ** 2 + 1
+    mosaic_host = torch.from_numpy(VO.synthetic_mosaic_u8(size, seed=4321)).pin_memory()
+    mosaic = mosaic_host.to(dev)
+    seg = vob.MosaicSegmenter(model, window=WINDOW, stride=STRIDE, tile_batch=args.tile_batch, group=group)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return seg.segment(mosaic, want=("th", "th3"), gather=True)
+
+    for _ in range(args.warmup):
+        out = step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = vob._lib.launch_count()
+    step_ms = []
+    barrier()
+    for _ in range(args.steps):
+        flush.fill_(1)                                   # evict L2 between timed steps (not timed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        out = step_device()
+        e1.record()
+        barrier()
+        step_ms.append(e0.elapsed_time(e1))
+    launches = vob._lib.launch_count() - launches0
+    sampler.stop_flag.set()
+    sampler.join(timeout=3)
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    mp = extent * extent / 1e6
+    value = mp / (ms_per_step / 1e3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    host_masks = {k: torch.empty(extent, extent, dtype=torch.uint8).pin_memory() for k in ("th", "th3")} if rank == 0 else {}
+    e2e_ms = []
+    for i in range(2 + args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        d_mosaic = mosaic_host.to(dev, non_blocking=True)
+        res = seg.segment(d_mosaic, want=("th", "th3"), gather=True)
+        if rank == 0:
+            for k in host_masks:
+                host_masks[k].copy_(res[k], non_blocking=True)
+        e1.record()
+        barrier()
+        if i >= 2:
+            e2e_ms.append(e0.elapsed_time(e1))
+    e2e_t = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(e2e_t, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = mp / (float(e2e_t.item()) / 1e3)
+
+    # ---- per-kernel-class device times (CUDA events on the launching stream) for the roofline
+    vob._lib.profile_enable(True)
+    step_device()
+    torch.cuda.synchronize()
+    prof = vob._lib.profile_read()
+    vob._lib.profile_enable(False)
+    t0, t1 = vob.shard_range(T, rank, world)
+    my_tiles = t1 - t0
+    classes = {k: {"ms": v[0], "launches": v[1], "gflop": class_flops(k, a["embed_dim"], N, my_tiles, a["depth"]) / 1e9}
+               for k, v in prof.items() if v[1] > 0}
+    for k, c in classes.items():
+        c["tflops"] = (c["gflop"] / c["ms"]) if c["ms"] > 0 and c["gflop"] > 0 else None
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peaks = json.load(open(peaks_path))
+        peak, peak_src = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))), "measured (sustained cuBLAS bf16, MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+    tensor_classes = {k: c for k, c in classes.items() if c["gflop"] > 0}
+    dom = max(tensor_classes, key=lambda k: tensor_classes[k]["ms"]) if tensor_classes else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if dom and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)
+    roofline = None
+    if dom:
+        c = tensor_classes[dom]
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": c["tflops"], "peak": peak, "unit": "TFLOP/s",
+                    "frac": c["tflops"] / peak, "traffic": traffic, "peak_source": peak_src,
+                    "launches_per_step": c["launches"], "avg_launch_ms": c["ms"] / c["launches"]}
+    step_tflops = flops_per_tile(a["embed_dim"], a["depth"], a["num_heads"], N) * my_tiles / 1e12 / (ms_per_step / 1e3)
+
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": f"{args.arch}/8 sliding-window segmentation, {size}x{size} gray mosaic, window {WINDOW}, stride {STRIDE}, "
+                                       f"{T} tiles, extent {extent}^2", "tiles": T, "tiles_per_gpu": my_tiles, "weights": "random init (seed 0)",
+                           "chunk_tiles": args.chunk_tiles, "l2": "flushed between timed steps (256 MiB write, untimed); per-step working set >> L2",
+                           "parallelism": f"tiles sharded over {world} rank(s)"},
+                "tiles_per_s": T / (ms_per_step / 1e3),
+                "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": int(mosaic_host.numel()),
+                        "d2h_bytes_per_step": int(2 * extent * extent), "ms_per_step": float(e2e_t.item())},
+                "gpu_launches": int(launches),
+                "clocks": sampler.summary(),
+                "roofline": roofline,
+                "step_tensor": {"tflops_per_gpu": step_tflops, "frac_of_peak": step_tflops / peak, "gflop_per_tile": flops_per_tile(a["embed_dim"], a["depth"], a["num_heads"], N) / 1e9},
+                "kernel_classes": classes}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            tps, ppm, sample = cpu_reference_sample(args.arch, threads, n_s=3)
+            line["cpu_baseline"] = {"value": cpu_value(tps, ppm, T, extent), "unit": "MP/s", "cores": threads, "kind": "port",
+                                    "sample": sample, "tiles_per_s": tps}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -178,6 +178,13 @@ int vitocm_attention(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n
 /* LayerNorm rows of X [M][D] fp32 with affine (gamma, beta) -> out bf16 [M][ldo] (hi | lo if split). */
 int vitocm_layernorm(vitocm_engine* e, const float* X, const float* gamma, const float* beta, void* out_bf16,
                      int64_t ldo, int split, int lo_off, int M, void* stream);
+/* Optional per-kernel-class device timing: when enabled every launch is bracketed by CUDA events on
+ * its own stream; vitocm_profile_read synchronises, sums milliseconds and launch counts per class
+ * (vitocm_profile_classes() slots, names from vitocm_profile_class_name) and clears the log. */
+int vitocm_profile_enable(int on);
+int vitocm_profile_classes(void);
+const char* vitocm_profile_class_name(int cls);
+int vitocm_profile_read(double* ms, int64_t* counts, int nclasses);
 /* number of kernels launched by this library on the calling process since load (gpu_launches) */
 int64_t vitocm_launch_count(void);
 

@@ -58,6 +58,10 @@ SIGNATURES = {
     "vitocm_attention": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "vitocm_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "vitocm_launch_count": (c_int64, []),
+    "vitocm_profile_enable": (c_int, [c_int]),
+    "vitocm_profile_classes": (c_int, []),
+    "vitocm_profile_class_name": (c_char_p, [c_int]),
+    "vitocm_profile_read": (c_int, [c_void_p, c_void_p, c_int]),
 }
 
 _lib = None
@@ -100,6 +104,20 @@ def ptr(t) -> int | None:
 
 def cur_stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def profile_enable(on: bool) -> None:
+    load_library().vitocm_profile_enable(int(on))
+
+
+def profile_read() -> dict:
+    """{class name: (total ms, launches)} since the last read."""
+    lib = load_library()
+    n = lib.vitocm_profile_classes()
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    check(lib.vitocm_profile_read(ms, cnt, n))
+    return {lib.vitocm_profile_class_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
 
 
 def launch_count() -> int:

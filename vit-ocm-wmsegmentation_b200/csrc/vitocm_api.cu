@@ -49,6 +49,22 @@ int fail(int code, const char* fmt, ...) {
     if (err__ != cudaSuccess) return fail(VITOCM_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(err__), __FILE__, __LINE__); \
   } while (0)
 
+// ---- optional per-kernel-class device timing (CUDA events on the launching stream) ----
+enum ProfClass { PC_PATCH = 0, PC_LN, PC_GEMM_QKV, PC_ATTN, PC_GEMM_PROJ, PC_GEMM_FC1, PC_GEMM_FC2, PC_GEMM_KLAST, PC_CLSROW,
+                 PC_POST, PC_OTHER, PC_COUNT };
+const char* const kProfNames[PC_COUNT] = {"patch_embed", "layernorm", "gemm_qkv", "attention", "gemm_proj", "gemm_fc1_gelu",
+                                          "gemm_fc2", "gemm_k_last", "cls_attn_row", "post", "other"};
+struct ProfRec { int cls; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+struct ProfScope {
+  cudaStream_t st; bool on; ProfRec r;
+  ProfScope(int cls, cudaStream_t s) : st(s), on(g_prof_on) {
+    if (on) { r.cls = cls; cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, st); }
+  }
+  ~ProfScope() { if (on) { cudaEventRecord(r.b, st); g_prof.push_back(r); } }
+};
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -168,8 +184,10 @@ int pick_bn(int N) {
 
 // A [M][lda] (split: hi at col 0, lo at col K), B [N][ldb] likewise.
 int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
-             int split_in, int epi, const float* bias, void* out, long long ldo, int split_out, int lo_off, cudaStream_t st) {
+             int split_in, int epi, const float* bias, void* out, long long ldo, int split_out, int lo_off, cudaStream_t st,
+             int pcls = PC_OTHER) {
   if (M <= 0) return 0;
+  ProfScope prof(pcls, st);
   if (K % GEMM_BK != 0) return fail(VITOCM_ERR_INVALID, "GEMM K=%d must be a multiple of %d", K, GEMM_BK);
   const int bn = pick_bn(N);
   if (bn == 0) return fail(VITOCM_ERR_INVALID, "GEMM N=%d must be a multiple of 64", N);
@@ -195,6 +213,7 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
 int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, int N, void* ctx, long long ldo, cudaStream_t st) {
   const int D = e->cfg.embed_dim, H = e->cfg.num_heads;
   const long long M = static_cast<long long>(B) * N;
+  ProfScope prof(PC_ATTN, st);
   CUtensorMap tq;
   TRY(make_tmap_bf16(&tq, qkv, M, 3LL * D * e->parts, ld, 128));
   AttnArgs a{};
@@ -219,6 +238,7 @@ int run_layernorm(const float* X, const float* g, const float* b, void* out_bf16
                   float* out_f32, long long ldf, int M, int D, float eps, cudaStream_t st) {
   if (M <= 0) return 0;
   if (D % 4 != 0 || D > LN_MAX_VEC * 128) return fail(VITOCM_ERR_INVALID, "LayerNorm D=%d unsupported", D);
+  ProfScope prof(PC_LN, st);
   const int rows_per_block = 8;
   layernorm_kernel<<<(M + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, st>>>(
       X, g, b, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, split, lo_off, out_f32, ldf, M, D, eps);
@@ -239,6 +259,7 @@ int run_patch_embed(const vitocm_engine* e, const float* x, int B, int H, int W,
   }
   const float* mask_token = e->w("mask_token");
   if (mask != nullptr && mask_token == nullptr) return fail(VITOCM_ERR_STATE, "mask given but mask_token was never loaded");
+  ProfScope prof(PC_PATCH, st);
   dim3 grid(H / p, B);
   patch_embed_kernel<<<grid, 128, smem, st>>>(x, e->patch_wt.as<float>(), e->w("patch_embed.proj.bias"), pos, e->w("cls_token"),
                                               mask, mask_token, X, C, H, W, p, D);
@@ -280,15 +301,15 @@ int block_forward(const vitocm_engine* e, int l, const Workspace& ws, int B, int
   const int M = B * N;
   TRY(run_layernorm(ws.X, L.ln1w, L.ln1b, ws.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
   TRY(run_gemm(e, ws.XN, 2LL * D, L.wqkv.p, static_cast<long long>(D) * P, M, 3 * D, D, S, EPI_BIAS_BF16, L.bqkv, ws.QKV,
-               3LL * D * P, S, 3 * D, st));
+               3LL * D * P, S, 3 * D, st, PC_GEMM_QKV));
   TRY(run_attention(e, ws.QKV, 3LL * D * P, B, N, ws.CTX, static_cast<long long>(D) * P, st));
   TRY(run_gemm(e, ws.CTX, static_cast<long long>(D) * P, L.wproj.p, static_cast<long long>(D) * P, M, D, D, S,
-               EPI_BIAS_RESID_F32, L.bproj, ws.X, D, 0, 0, st));
+               EPI_BIAS_RESID_F32, L.bproj, ws.X, D, 0, 0, st, PC_GEMM_PROJ));
   TRY(run_layernorm(ws.X, L.ln2w, L.ln2b, ws.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
   TRY(run_gemm(e, ws.XN, 2LL * D, L.w1.p, static_cast<long long>(D) * P, M, Hd, D, S, EPI_BIAS_GELU_BF16, L.b1, ws.HID,
-               static_cast<long long>(Hd) * P, S, Hd, st));
+               static_cast<long long>(Hd) * P, S, Hd, st, PC_GEMM_FC1));
   TRY(run_gemm(e, ws.HID, static_cast<long long>(Hd) * P, L.w2.p, static_cast<long long>(Hd) * P, M, D, Hd, S,
-               EPI_BIAS_RESID_F32, L.b2, ws.X, D, 0, 0, st));
+               EPI_BIAS_RESID_F32, L.b2, ws.X, D, 0, 0, st, PC_GEMM_FC2));
   return 0;
 }
 
@@ -306,6 +327,28 @@ extern "C" {
 int vitocm_version(void) { return VITOCM_VERSION; }
 const char* vitocm_last_error(void) { return g_err; }
 int64_t vitocm_launch_count(void) { return g_launches.load(); }
+
+int vitocm_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return 0;
+}
+int vitocm_profile_classes(void) { return PC_COUNT; }
+const char* vitocm_profile_class_name(int cls) { return (cls >= 0 && cls < PC_COUNT) ? kProfNames[cls] : ""; }
+int vitocm_profile_read(double* ms, int64_t* counts, int nclasses) {
+  if (ms == nullptr || counts == nullptr || nclasses < PC_COUNT) return fail(VITOCM_ERR_INVALID, "profile_read needs %d slots", PC_COUNT);
+  for (int i = 0; i < nclasses; ++i) { ms[i] = 0.0; counts[i] = 0; }
+  for (ProfRec& r : g_prof) {
+    float t = 0.f;
+    cudaEventSynchronize(r.b);
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms[r.cls] += t;
+    counts[r.cls] += 1;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return 0;
+}
 
 int vitocm_create(const vitocm_config* cfg, vitocm_engine** out) {
   if (cfg == nullptr || out == nullptr) return fail(VITOCM_ERR_INVALID, "null argument");
@@ -435,7 +478,8 @@ int vitocm_forward_cls_attn(vitocm_engine* e, const float* x, int B, int H, int 
     // last block: LN1 (split) -> K projection in split precision -> fp32 K -> CLS-row softmax
     float* KF = reinterpret_cast<float*>(wsp.HID);
     TRY(run_layernorm(wsp.X, last.ln1w, last.ln1b, wsp.XN, 2LL * D, 1, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
-    TRY(run_gemm(e, wsp.XN, 2LL * D, last.wk_split.p, 2LL * D, M, D, D, 1, EPI_BIAS_F32, last.bqkv + D, KF, D, 0, 0, st));
+    TRY(run_gemm(e, wsp.XN, 2LL * D, last.wk_split.p, 2LL * D, M, D, D, 1, EPI_BIAS_F32, last.bqkv + D, KF, D, 0, 0, st, PC_GEMM_KLAST));
+    ProfScope prof(PC_CLSROW, st);
     dim3 grid(heads, bc);
     cls_attn_row_kernel<<<grid, 256, cls_smem, st>>>(wsp.X, last.ln1w, last.ln1b, e->cfg.ln_eps, last.wqkv_f32, last.bqkv, KF,
                                                      out_rows + static_cast<long long>(b0) * heads * N, N, D, heads, e->cfg.qk_scale);
@@ -497,6 +541,7 @@ int vitocm_final_norm(vitocm_engine* e, const float* X, float* out, int M, void*
 // ------------------------------------------------------------------------------ post-processing
 int vitocm_head_mean(const float* rows, float* lowres, int T, int heads, int n_tokens, int mode, void* stream) {
   if (T <= 0) return 0;
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
   head_mean_kernel<<<T, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows, lowres, heads, n_tokens, mode);
   LAUNCH_CHECK();
   return 0;
@@ -507,6 +552,7 @@ int vitocm_tile_threshold(const float* lowres, const float* x, int T, int C, int
   if (T <= 0) return 0;
   if (lowres == nullptr && att_in == nullptr) return fail(VITOCM_ERR_INVALID, "tile_threshold needs lowres or att_in");
   if (x == nullptr && img_in == nullptr) return fail(VITOCM_ERR_INVALID, "tile_threshold needs x or img_in");
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
   tile_threshold_kernel<<<T, 512, 0, static_cast<cudaStream_t>(stream)>>>(lowres, x, C, S, lh, lw, masks, thresholds, att_out, att_in, img_in);
   LAUNCH_CHECK();
   return 0;
@@ -522,6 +568,7 @@ int vitocm_extract_tiles(const uint8_t* mosaic, int mos_h, int mos_w, int64_t pi
                          float* x, void* stream) {
   if (T <= 0) return 0;
   const long long total = static_cast<long long>(T) * W * W;
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
   extract_tiles_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(mosaic, mos_h, mos_w, pitch, n, W, S, t0, T, C, x);
   LAUNCH_CHECK();
   return 0;
@@ -545,6 +592,7 @@ int vitocm_stitch_gray(const uint8_t* mosaic, int mos_h, int mos_w, int64_t pitc
   TRY(check_geom(n, W, S, y_begin, y_end));
   if (y_end == y_begin) return 0;
   const StitchGeom g = make_geom(n, W, S, 1, 1);
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
   stitch_gray_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       mosaic, mos_h, mos_w, pitch, g, wtab, y_begin, y_end, out);
   LAUNCH_CHECK();
@@ -562,6 +610,7 @@ int vitocm_stitch_minmax(const float* lowres, int n, int W, int S, int lh, int l
   TRY(check_geom(n, W, S, y_begin, y_end));
   if (y_end == y_begin) return 0;
   const StitchGeom g = make_geom(n, W, S, lh, lw);
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
   stitch_minmax_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       lowres, g, wtab, y_begin, y_end, minmax_ord, map_out, map_in);
   LAUNCH_CHECK();
@@ -573,6 +622,7 @@ int vitocm_stitch_hist(const float* lowres, int n, int W, int S, int lh, int lw,
   TRY(check_geom(n, W, S, y_begin, y_end));
   if (y_end == y_begin) return 0;
   const StitchGeom g = make_geom(n, W, S, lh, lw);
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
   stitch_hist_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       lowres, g, wtab, gray, minmax_ord, y_begin, y_end, reinterpret_cast<unsigned long long*>(hists), map_in);
   LAUNCH_CHECK();
@@ -581,6 +631,7 @@ int vitocm_stitch_hist(const float* lowres, int n, int W, int S, int lh, int lw,
 
 int vitocm_otsu(const uint64_t* hists, int nhist, int* thresholds, void* stream) {
   if (nhist <= 0) return 0;
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
   otsu_kernel<<<(nhist + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const unsigned long long*>(hists), nhist, thresholds);
   LAUNCH_CHECK();
   return 0;
@@ -592,6 +643,7 @@ int vitocm_stitch_mask(const float* lowres, int n, int W, int S, int lh, int lw,
   TRY(check_geom(n, W, S, y_begin, y_end));
   if (y_end == y_begin) return 0;
   const StitchGeom g = make_geom(n, W, S, lh, lw);
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
   stitch_mask_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       lowres, g, wtab, gray, minmax_ord, thr, y_begin, y_end, th, th2, th3, map_in);
   LAUNCH_CHECK();
@@ -601,6 +653,7 @@ int vitocm_stitch_mask(const float* lowres, int n, int W, int S, int lh, int lw,
 int vitocm_concat_crops_f32(const float* crops, int n, int W, int S, const double* wtab, float* out, void* stream) {
   TRY(check_geom(n, W, S, 0, 0));
   const StitchGeom g = make_geom(n, W, S, 1, 1);
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
   concat_crops_f32_kernel<<<grid_for(static_cast<long long>(g.E) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(crops, g, wtab, out);
   LAUNCH_CHECK();
   return 0;
@@ -609,6 +662,7 @@ int vitocm_concat_crops_f32(const float* crops, int n, int W, int S, const doubl
 int vitocm_concat_crops_u8(const uint8_t* crops, int n, int W, int S, int C, const double* wtab, uint8_t* out, void* stream) {
   TRY(check_geom(n, W, S, 0, 0));
   const StitchGeom g = make_geom(n, W, S, 1, 1);
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
   concat_crops_u8_kernel<<<grid_for(static_cast<long long>(g.E) * g.E * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(crops, g, C, wtab, out);
   LAUNCH_CHECK();
   return 0;
@@ -616,6 +670,7 @@ int vitocm_concat_crops_u8(const uint8_t* crops, int n, int W, int S, int C, con
 
 int vitocm_crop_u8(const uint8_t* img, int img_h, int img_w, int C, int ny, int nx, int W, int S, uint8_t* crops, void* stream) {
   if (ny <= 0 || nx <= 0) return 0;
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
   crop_u8_kernel<<<grid_for(static_cast<long long>(ny) * nx * W * W * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, img_h, img_w, C, ny, nx, W, S, crops);
   LAUNCH_CHECK();
   return 0;
