@@ -5,13 +5,19 @@
 //
 // One CTA = one (image b, head h, 128-query tile).  q/k/v are read straight out of the fused
 // QKV activation [B*N, ld] (bf16, columns [3][H][64]) by one 2-D TMA tensor map (box 64 x 128,
-// SWIZZLE_128B).  Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM
-// allocator, warps 2..5 = softmax (one thread per query row; TMEM lane quadrant = warp % 4).
+// SWIZZLE_128B).  Warp roles (256 threads): warps 0..3 = softmax (one thread per query row; TMEM lane
+// quadrant = warp % 4), warp 4 = TMA producer, warp 5 = MMA issuer + TMEM allocator, warps 6..7 idle.
+// setmaxnreg moves registers from warpgroup 1 to the softmax warpgroup (208 vs 48 per thread).
 //   S = Q K_j^T      : tcgen05.mma  M128 x N(<=128) x K64, both operands K-major, into TMEM
-//   softmax          : tcgen05.ld S (pass 1 row max, pass 2 exp2), P -> smem (bf16, swizzled)
-//   O_j = P V_j      : tcgen05.mma  M128 x N64 x K(<=128), A = P (K-major), B = V (MN-major)
-//   running output   : registers (fp32), rescaled by exp2(m_old - m_new) per KV block
-// Two CTAs are co-resident per SM (96 KB smem, 256 TMEM columns each) so one CTA's MMAs overlap
+//   softmax          : one tcgen05.ld pass of S into registers, exp2 with a lazily updated row max,
+//                      P -> smem (bf16, 128B-swizzled, the A operand of the next two MMAs)
+//   O += P V_j       : tcgen05.mma  M128 x N64 x K(<=128), B = V (MN-major), accumulating in TMEM
+//   L += P 1         : tcgen05.mma  M128 x N16 against a tile of ones -> the softmax row sums, so the
+//                      normaliser is built from exactly the bf16 P that multiplies V
+// The running maximum is only raised when a row exceeds it by more than 2^8 ("lazy rescale"): softmax
+// is shift invariant, so a stale maximum changes nothing but keeps O/L in TMEM untouched in the
+// common case; when it is raised the softmax warps rescale their O/L rows in TMEM.
+// Two CTAs are co-resident per SM (98 KB smem, 256 TMEM columns each) so one CTA's MMAs overlap
 // the other's exponentials.  SPLIT = true is the fp32-parity mode: every operand is a bf16
 // (hi, lo) pair and each product is hi*hi + hi*lo + lo*hi (fp32 accumulate in TMEM).
 #pragma once
@@ -32,12 +38,17 @@ struct AttnArgs {
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 128;
 constexpr int ATT_DH = 64;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 256;   // warpgroup 0 = softmax (warps 0..3), warpgroup 1 = TMA (warp 4) + MMA (warp 5)
+constexpr int ATT_REGS_SOFTMAX = 208;
+constexpr int ATT_REGS_OTHER = 48;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: one [128 x 64] bf16 tile
 constexpr int ATT_RING = 3;
-constexpr int ATT_TMEM_COLS = 256;  // S: 128 cols, O: 64 cols
-constexpr int ATT_S_COL = 0;
-constexpr int ATT_O_COL = 128;
+constexpr int ATT_TMEM_COLS = 256;
+constexpr int ATT_S_COL = 0;      // S: 128 columns
+constexpr int ATT_O_COL = 128;    // O: 64 columns
+constexpr int ATT_L_COL = 192;    // L: 16 columns (all equal: row sums of P)
+constexpr int ATT_ONES_BYTES = 2048;
+constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 template <bool SPLIT>
 struct AttnCfg {
@@ -45,7 +56,7 @@ struct AttnCfg {
   static constexpr int SLOT_BYTES = ATT_TILE_BYTES * NPART;       // one K or V block
   static constexpr int Q_BYTES = ATT_TILE_BYTES * NPART;
   static constexpr int P_BYTES = 2 * ATT_TILE_BYTES * NPART;      // [128 x 128] bf16 (two 64-key halves)
-  static constexpr int SMEM_BYTES = Q_BYTES + ATT_RING * SLOT_BYTES + P_BYTES + 1024 + 128;
+  static constexpr int SMEM_BYTES = Q_BYTES + ATT_RING * SLOT_BYTES + P_BYTES + ATT_ONES_BYTES + 1024 + 128;
 };
 
 template <bool SPLIT>
@@ -58,7 +69,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
   uint8_t* smem_q = smem;
   uint8_t* smem_ring = smem_q + Cfg::Q_BYTES;
   uint8_t* smem_p = smem_ring + ATT_RING * Cfg::SLOT_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + Cfg::P_BYTES);
+  uint8_t* smem_ones = smem_p + Cfg::P_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ones + ATT_ONES_BYTES);
   uint64_t* q_full = bars;            // [1]
   uint64_t* kv_full = bars + 1;       // [3]
   uint64_t* kv_empty = bars + 4;      // [3]
@@ -76,7 +88,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
   const int n_kv = (N + ATT_BKV - 1) / ATT_BKV;
   const int row_base = b * N;  // first row of this image in the [B*N, ld] activation
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     ptx::prefetch_tmap(&tmap_qkv);
     ptx::mbar_init(q_full, 1);
     for (int i = 0; i < ATT_RING; ++i) {
@@ -89,16 +101,24 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == 5) {
     ptx::tmem_alloc(tmem_ptr_smem, ATT_TMEM_COLS);
     ptx::tmem_relinquish();
+  }
+  if (warp < 4) {  // tile of bf16 ones (layout-agnostic B operand of the row-sum MMA)
+    uint4* o = reinterpret_cast<uint4*>(smem_ones);
+    const uint32_t one2 = 0x3F803F80u;
+    for (int i = threadIdx.x; i < ATT_ONES_BYTES / 16; i += 128) o[i] = make_uint4(one2, one2, one2, one2);
+    ptx::fence_proxy_async_smem();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 0) {
+  if (warp >= 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT_REGS_OTHER));
+   if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       ptx::mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
@@ -123,13 +143,15 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
         load(2, j);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t q_addr = ptx::smem_u32(smem_q);
       const uint32_t p_addr = ptx::smem_u32(smem_p);
       const uint32_t s_tmem = tmem_base + ATT_S_COL;
       const uint32_t o_tmem = tmem_base + ATT_O_COL;
+      const uint32_t l_tmem = tmem_base + ATT_L_COL;
+      const uint64_t ones_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_ones), 1024, 0);
       int item = 0;
       auto kv_len_mma = [&](int j) {  // keys of block j rounded up to the MMA granularity (16)
         int len = N - j * ATT_BKV;
@@ -144,6 +166,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
         const uint32_t idesc = ptx::make_idesc(ATT_BQ, kv_len_mma(j), false, false);
         uint32_t acc = 0;
         // terms: (Qhi,Khi) [, (Qhi,Klo), (Qlo,Khi)]
+#pragma unroll 1
         for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
           const uint32_t qa = q_addr + (t == 2 ? ATT_TILE_BYTES : 0);
           const uint32_t ka = k_addr + (t == 1 ? ATT_TILE_BYTES : 0);
@@ -164,19 +187,35 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
         ptx::tc_fence_after();
         const uint32_t v_addr = ptx::smem_u32(smem_ring + slot * Cfg::SLOT_BYTES);
         constexpr uint32_t idesc = ptx::make_idesc(ATT_BQ, ATT_DH, false, /*B = V is MN-major*/ true);
+        constexpr uint32_t idesc_l = ptx::make_idesc(ATT_BQ, 16, false, false);
         const int ksteps = kv_len_mma(j) / 16;
-        uint32_t acc = 0;
+        // O and L accumulate across KV blocks in TMEM.  Loops are kept rolled: this warp runs on a
+        // 48-register budget and the operands live in uniform registers.
+        // A = P: K-major, 64-key halves of 16 KB, 32 B per 16-key step inside the 128 B swizzle row
+        // B = V: MN-major [keys x 64]; 16 keys = two 8-row groups of 1024 B
+        uint32_t acc = j > 0 ? 1u : 0u;
         // terms: (Phi,Vhi) [, (Phi,Vlo), (Plo,Vhi)]
+#pragma unroll 1
         for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
           const uint32_t pa = p_addr + (t == 2 ? 2 * ATT_TILE_BYTES : 0);
           const uint32_t va = v_addr + (t == 1 ? ATT_TILE_BYTES : 0);
+#pragma unroll 1
           for (int k = 0; k < ksteps; ++k) {
-            // A = P: K-major, 64-key halves of 16 KB, 32 B per 16-key step inside the 128 B swizzle row
-            const uint64_t adesc = ptx::make_smem_desc_sw128(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 1024, 0);
-            // B = V: MN-major [keys x 64]; 16 keys = two 8-row groups of 1024 B
-            const uint64_t bdesc = ptx::make_smem_desc_sw128(va + k * 2048, 1024, 1024);
-            ptx::umma_bf16_ss(o_tmem, adesc, bdesc, idesc, acc);
+            ptx::umma_bf16_ss(o_tmem, ptx::make_smem_desc_sw128(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 1024, 0),
+                              ptx::make_smem_desc_sw128(va + k * 2048, 1024, 1024), idesc, acc);
             acc = 1;
+          }
+        }
+        // row sums: (Phi [+ Plo]) . 1
+        uint32_t acc_l = j > 0 ? 1u : 0u;
+#pragma unroll 1
+        for (int t = 0; t < (SPLIT ? 2 : 1); ++t) {
+          const uint32_t pa = p_addr + (t == 1 ? 2 * ATT_TILE_BYTES : 0);
+#pragma unroll 1
+          for (int k = 0; k < ksteps; ++k) {
+            ptx::umma_bf16_ss(l_tmem, ptx::make_smem_desc_sw128(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 1024, 0),
+                              ones_desc, idesc_l, acc_l);
+            acc_l = 1;
           }
         }
         ptx::umma_commit(&kv_empty[slot]);
@@ -192,124 +231,159 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
           ptx::tc_fence_after();
           issue_s(j + 1);
         }
-        ptx::mbar_wait(p_full, j & 1, 15);     // P_j in smem, O_{j-1} consumed
+        ptx::mbar_wait(p_full, j & 1, 15);     // P_j in smem, O/L rescaled if needed
         ptx::tc_fence_after();
         issue_pv(j);
       }
     }
+   }
   } else {
-    // ===================== softmax / output (warps 2..5) =====================
+    // ===================== softmax / output (warps 0..3) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ATT_REGS_SOFTMAX));
     const int q = warp & 3;
     const int r = q * 32 + lane;  // query row inside the tile == TMEM lane
-    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float sl2 = args.scale_log2;
-    float o_acc[ATT_DH];
-#pragma unroll
-    for (int d = 0; d < ATT_DH; ++d) o_acc[d] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
-
-    auto fetch_o = [&](int j) {  // o_acc += O_j  (PV of block j, in units of the current m_run)
-      ptx::mbar_wait(o_full, j & 1, 20);
-      ptx::tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < ATT_DH; c += 32) {
-        uint32_t t[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + ATT_O_COL + c, t);
-        ptx::tmem_ld_wait(t);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c + i] += __uint_as_float(t[i]);
-      }
-    };
+    float m_used = -INFINITY;     // the row maximum the exponentials are taken against
 
     for (int j = 0; j < n_kv; ++j) {
       int kv_len = N - j * ATT_BKV;
       kv_len = kv_len > ATT_BKV ? ATT_BKV : kv_len;
-      const int ncols = (kv_len + 15) & ~15;       // columns the MMA produced
-      const int nchunks = (ncols + 31) >> 5;
+      const bool full = kv_len == ATT_BKV;
+      const int nchunks = (((kv_len + 15) & ~15) + 31) >> 5;   // 32-column chunks the MMA produced
       ptx::mbar_wait(s_full, j & 1, 21);
       ptx::tc_fence_after();
-      // ---- pass 1: row maximum
-      float mx = m_run;
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t t[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + ATT_S_COL + c * 32, t);
-        ptx::tmem_ld_wait(t);
+      // ---- S_j -> registers (one pass), then hand the TMEM columns back to the MMA warp
+      uint32_t s[4][32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < kv_len) mx = fmaxf(mx, __uint_as_float(t[i]));
+      for (int c = 0; c < 4; ++c)
+        if (c < nchunks) ptx::tmem_ld_32x32b_x32(lane_addr + ATT_S_COL + c * 32, s[c]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < nchunks) ptx::tmem_ld_wait(s[c]);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(s_empty);
+      // ---- row maximum (masked only in the ragged last block)
+      float mx = -INFINITY;
+      if (full) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c < nchunks && c * 32 + i < kv_len) mx = fmaxf(mx, __uint_as_float(s[c][i]));
       }
-      const float alpha = exp2f((m_run - mx) * sl2);
-      // ---- previous block's PV result (also: P buffer is free again)
-      if (j > 0) fetch_o(j - 1);
+      // ---- lazy rescale decision
+      float alpha = 1.0f;
+      if (j == 0) {
+        m_used = mx;
+      } else if ((mx - m_used) * sl2 > ATT_RESCALE_THRESHOLD) {
+        alpha = ptx::ex2_approx((m_used - mx) * sl2);
+        m_used = mx;
+      }
+      const float m_sl2 = m_used * sl2;
+      // ---- p = exp2(s*sl2 - m*sl2) -> bf16 pairs -> swizzled smem (A operand of the PV / row-sum MMAs).
+      // 32 keys = 64 B = four 16-byte chunks of this row; the chunk index inside the 128 B row is
+      // XOR-swizzled with (row % 8) (SWIZZLE_128B, tile base 1024-aligned).
+      auto exp_chunk = [&](int c, uint32_t (&ph)[16], uint32_t (&pl)[16]) {
 #pragma unroll
-      for (int d = 0; d < ATT_DH; ++d) o_acc[d] *= alpha;
-      l_run *= alpha;
-      m_run = mx;
-      const float m_sl2 = mx * sl2;
-      // ---- pass 2: p = exp2(s*sl2 - m*sl2) -> bf16 -> swizzled smem (A operand of the PV MMA)
-      float psum = 0.f;
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t t[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + lane_addr + ATT_S_COL + c * 32, t);
-        ptx::tmem_ld_wait(t);
-        float p[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = exp2f(fmaf(__uint_as_float(t[i]), sl2, -m_sl2));
-          p[i] = (c * 32 + i < kv_len) ? e : 0.f;
-          psum += p[i];
+        for (int i = 0; i < 16; ++i) {
+          float e0 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][2 * i]), sl2, -m_sl2));
+          float e1 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][2 * i + 1]), sl2, -m_sl2));
+          if (!full) {
+            if (c * 32 + 2 * i >= kv_len) e0 = 0.f;
+            if (c * 32 + 2 * i + 1 >= kv_len) e1 = 0.f;
+          }
+          ph[i] = ptx::pack_bf16x2(e0, e1);
+          if (SPLIT) pl[i] = ptx::pack_bf16x2(e0 - ptx::bf16_round(e0), e1 - ptx::bf16_round(e1));
         }
-        // 32 keys = 64 B = four 16-byte chunks of this row; chunk index inside the 128 B row is
-        // XOR-swizzled with (row % 8) (SWIZZLE_128B, tile base 1024-aligned)
+      };
+      auto store_chunk = [&](int c, const uint32_t (&ph)[16], const uint32_t (&pl)[16]) {
         uint8_t* half_base = smem_p + (c >> 1) * ATT_TILE_BYTES + r * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int chunk16 = ((c & 1) * 4 + g) ^ (r & 7);
-          uint4 hi;
-          hi.x = ptx::pack_bf16x2(p[8 * g + 0], p[8 * g + 1]);
-          hi.y = ptx::pack_bf16x2(p[8 * g + 2], p[8 * g + 3]);
-          hi.z = ptx::pack_bf16x2(p[8 * g + 4], p[8 * g + 5]);
-          hi.w = ptx::pack_bf16x2(p[8 * g + 6], p[8 * g + 7]);
-          *reinterpret_cast<uint4*>(half_base + chunk16 * 16) = hi;
-          if (SPLIT) {
-            uint4 lo;
-            lo.x = ptx::pack_bf16x2(p[8 * g + 0] - ptx::bf16_round(p[8 * g + 0]), p[8 * g + 1] - ptx::bf16_round(p[8 * g + 1]));
-            lo.y = ptx::pack_bf16x2(p[8 * g + 2] - ptx::bf16_round(p[8 * g + 2]), p[8 * g + 3] - ptx::bf16_round(p[8 * g + 3]));
-            lo.z = ptx::pack_bf16x2(p[8 * g + 4] - ptx::bf16_round(p[8 * g + 4]), p[8 * g + 5] - ptx::bf16_round(p[8 * g + 5]));
-            lo.w = ptx::pack_bf16x2(p[8 * g + 6] - ptx::bf16_round(p[8 * g + 6]), p[8 * g + 7] - ptx::bf16_round(p[8 * g + 7]));
-            *reinterpret_cast<uint4*>(half_base + 2 * ATT_TILE_BYTES + chunk16 * 16) = lo;
+          *reinterpret_cast<uint4*>(half_base + chunk16 * 16) = make_uint4(ph[4 * g], ph[4 * g + 1], ph[4 * g + 2], ph[4 * g + 3]);
+          if (SPLIT)
+            *reinterpret_cast<uint4*>(half_base + 2 * ATT_TILE_BYTES + chunk16 * 16) =
+                make_uint4(pl[4 * g], pl[4 * g + 1], pl[4 * g + 2], pl[4 * g + 3]);
+        }
+      };
+      // the first two chunks are exponentiated while the previous PV MMA may still be running
+      uint32_t ph0[16], ph1[16], pl0[16], pl1[16];
+      exp_chunk(0, ph0, pl0);
+      if (nchunks > 1) exp_chunk(1, ph1, pl1);
+      // ---- previous PV done: P buffer free, O/L valid -> rescale them if this warp raised a maximum
+      if (j > 0) {
+        ptx::mbar_wait(o_full, (j - 1) & 1, 20);
+        ptx::tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+          for (int c = 0; c < ATT_DH; c += 32) {
+            uint32_t t[32];
+            ptx::tmem_ld_32x32b_x32(lane_addr + ATT_O_COL + c, t);
+            ptx::tmem_ld_wait(t);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            ptx::tmem_st_32x32b_x32(lane_addr + ATT_O_COL + c, t);
           }
+          uint32_t l0;
+          ptx::tmem_ld_32x32b_x1(lane_addr + ATT_L_COL, l0);
+          ptx::tmem_ld_wait1(l0);
+          ptx::tmem_st_32x32b_x1(lane_addr + ATT_L_COL, __float_as_uint(__uint_as_float(l0) * alpha));
+          ptx::tmem_st_wait();
         }
       }
-      l_run += psum;
-      // S_j fully read: the MMA warp may overwrite it with S_{j+1}
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(s_empty);
-      // P_j visible to the async proxy (tcgen05.mma reads smem through it)
-      ptx::fence_proxy_async_smem();
+      store_chunk(0, ph0, pl0);
+      if (nchunks > 1) store_chunk(1, ph1, pl1);
+#pragma unroll
+      for (int c = 2; c < 4; ++c) {
+        if (c < nchunks) {
+          uint32_t ph[16], pl[16];
+          exp_chunk(c, ph, pl);
+          store_chunk(c, ph, pl);
+        }
+      }
+      ptx::fence_proxy_async_smem();   // generic-proxy smem writes -> visible to tcgen05.mma
+      ptx::tc_fence_before();          // orders the TMEM rescale before the MMA that accumulates on it
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_full);
     }
-    fetch_o(n_kv - 1);
+    // ---- epilogue: ctx = O / L
+    ptx::mbar_wait(o_full, (n_kv - 1) & 1, 22);
+    ptx::tc_fence_after();
+    uint32_t l0;
+    ptx::tmem_ld_32x32b_x1(lane_addr + ATT_L_COL, l0);
+    ptx::tmem_ld_wait1(l0);
+    const float inv = 1.0f / __uint_as_float(l0);
     const int qrow = qt * ATT_BQ + r;
-    if (qrow < N) {
-      const float inv = 1.0f / l_run;
-      __nv_bfloat16* o = args.out + static_cast<long long>(row_base + qrow) * args.ldo + h * ATT_DH;
+    __nv_bfloat16* o = args.out + static_cast<long long>(row_base + qrow) * args.ldo + h * ATT_DH;
 #pragma unroll
-      for (int g = 0; g < ATT_DH / 8; ++g) {
-        float v[8];
+    for (int c = 0; c < ATT_DH; c += 32) {
+      uint32_t t[32];
+      ptx::tmem_ld_32x32b_x32(lane_addr + ATT_O_COL + c, t);
+      ptx::tmem_ld_wait(t);
+      if (qrow < N) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = o_acc[8 * g + i] * inv;
-        reinterpret_cast<uint4*>(o)[g] = make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]),
-                                                    ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
-        if (SPLIT) {
-          float w[8];
+        for (int g = 0; g < 4; ++g) {
+          float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) w[i] = v[i] - ptx::bf16_round(v[i]);
-          reinterpret_cast<uint4*>(o + args.out_lo_off)[g] =
-              make_uint4(ptx::pack_bf16x2(w[0], w[1]), ptx::pack_bf16x2(w[2], w[3]), ptx::pack_bf16x2(w[4], w[5]),
-                         ptx::pack_bf16x2(w[6], w[7]));
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(t[8 * g + i]) * inv;
+          reinterpret_cast<uint4*>(o + c)[g] = make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]),
+                                                          ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+          if (SPLIT) {
+            float w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = v[i] - ptx::bf16_round(v[i]);
+            reinterpret_cast<uint4*>(o + args.out_lo_off + c)[g] =
+                make_uint4(ptx::pack_bf16x2(w[0], w[1]), ptx::pack_bf16x2(w[2], w[3]), ptx::pack_bf16x2(w[4], w[5]),
+                           ptx::pack_bf16x2(w[6], w[7]));
+          }
         }
       }
     }
@@ -317,7 +391,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 5) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, ATT_TMEM_COLS);
   }

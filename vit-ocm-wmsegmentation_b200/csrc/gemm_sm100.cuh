@@ -25,9 +25,8 @@ enum GemmEpilogue : int {
 struct GemmArgs {
   int M, N;
   int kblocks;        // K / 64 per term
-  int nterms;         // 1 (bf16 mode) or 3 (split mode)
-  int a_koff[3];      // element offset along K into A for each term
-  int b_koff[3];      // element offset along K into B for each term
+  int nterms;         // 1 (bf16 mode) or 3 (split mode: hi*hi + hi*lo + lo*hi)
+  int lo_k;           // split mode: column where the lo halves of A and B start (= K)
   const float* bias;  // [N] or nullptr
   void* out;          // bf16 or f32, row-major, leading dimension ldo
   long long ldo;
@@ -40,14 +39,27 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARP0 = 4;
 
-template <int BN>
+constexpr int GEMM_NUM_EPI_WARPS = 8;
+constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
+
+template <int BN, int EPI>
 struct GemmCfg {
+  static constexpr bool OUT_BF16 = (EPI == 0 || EPI == 1);
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;       // 16 KB
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+  // epilogue staging: one [32 rows][32 cols] chunk per warp, rows padded by 16 B (conflict-free 128-bit stores)
+  static constexpr int STG_PITCH = (OUT_BF16 ? 64 : 128) + 16;
+  static constexpr int STG_WARP_BYTES = 32 * STG_PITCH;
+  static constexpr int STG_BYTES = GEMM_NUM_EPI_WARPS * STG_WARP_BYTES;
+  static constexpr int BIAS_WARP_FLOATS = 128;                 // >= BN / 2
+  static constexpr int BIAS_BYTES = GEMM_NUM_EPI_WARPS * BIAS_WARP_FLOATS * 4;
+  static constexpr int FIXED_BYTES = STG_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGES_FIT = (GEMM_SMEM_LIMIT - FIXED_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
+  static_assert(STAGES >= 3, "not enough shared memory for a 3-stage pipeline");
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -59,14 +71,16 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmArgs args) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_stg = smem + STAGES * Cfg::STAGE_BYTES;
+  float* smem_bias = reinterpret_cast<float*>(smem_stg + Cfg::STG_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + Cfg::STG_BYTES + Cfg::BIAS_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;           // [STAGES]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;       // [2]       MMA -> epilogue
@@ -117,8 +131,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const int kb = it - term * args.kblocks;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          ptx::tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], args.a_koff[term] + kb * GEMM_BK, m0);
-          ptx::tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage], args.b_koff[term] + kb * GEMM_BK, n0);
+          // split mode terms: (hi,hi) (hi,lo) (lo,hi); lo halves start at column K of each operand
+          const int a_off = (term == 2 ? args.lo_k : 0) + kb * GEMM_BK;
+          const int b_off = (term == 1 ? args.lo_k : 0) + kb * GEMM_BK;
+          ptx::tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], a_off, m0);
+          ptx::tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage], b_off, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -155,63 +172,93 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp >= GEMM_EPI_WARP0) {
     // ===================== epilogue =====================
+    // TMEM -> registers (lane = row) -> +bias/GELU -> per-warp smem transpose -> global stores in which
+    // consecutive lanes cover consecutive 16-byte pieces of a row (full 32-byte sectors, no partial writes).
     const int q = warp & 3;                         // TMEM lane quadrant this warp may access
-    const int half = (warp - GEMM_EPI_WARP0) >> 2;  // which half of the BN columns
+    const int ew = warp - GEMM_EPI_WARP0;           // 0..7
+    const int half = ew >> 2;                       // which half of the BN columns
     constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int PITCH = Cfg::STG_PITCH;
+    uint8_t* stg = smem_stg + ew * Cfg::STG_WARP_BYTES;
+    float* bias_s = smem_bias + ew * Cfg::BIAS_WARP_FLOATS;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * GEMM_BM;
       const int n0 = (tile % tiles_n) * BN;
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < args.M;
+      const int row_base = m0 + q * 32;
+      const int col_base = n0 + half * COLS_PER_WARP;
+      // this warp's slice of the bias, fetched before waiting on the accumulator
+      for (int j = lane; j < COLS_PER_WARP; j += 32) bias_s[j] = (args.bias != nullptr) ? __ldg(args.bias + col_base + j) : 0.f;
+      __syncwarp();
       ptx::mbar_wait(&tfull_bar[as], aphase, 4);
       ptx::tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP; c += 32) {
-        const int col_t = half * COLS_PER_WARP + c;  // column inside the tile
-        const int col = n0 + col_t;
+        // residual epilogue: the 8 row-pieces of x this lane will update are fetched first, so their
+        // latency hides behind the TMEM load and the smem transpose (lane -> row it*4 + lane/8, piece lane%8)
+        float4 xres[8];
+        if (EPI == EPI_BIAS_RESID_F32) {
+          const float* xbase = reinterpret_cast<const float*>(args.out) + col_base + c + (lane & 7) * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = row_base + it * 4 + (lane >> 3);
+            xres[it] = (row < args.M) ? *reinterpret_cast<const float4*>(xbase + static_cast<long long>(row) * args.ldo)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN + col_t), r);
+        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN + half * COLS_PER_WARP + c), r);
         ptx::tmem_ld_wait(r);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          v[j] = __uint_as_float(r[j]);
-          if (args.bias != nullptr) v[j] += __ldg(args.bias + col + j);
+          v[j] = __uint_as_float(r[j]) + bias_s[c + j];
           if (EPI == EPI_BIAS_GELU_BF16) v[j] = gelu_erf(v[j]);
         }
-        if (row_ok) {
-          if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + static_cast<long long>(row) * args.ldo + col;
-            uint32_t hi[16];
+        const int col = col_base + c;
+        if (Cfg::OUT_BF16) {
+          const int npass = args.split_out ? 2 : 1;
+          for (int pass = 0; pass < npass; ++pass) {
+            uint32_t w[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) hi[j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < 16; ++j)
+              w[j] = pass == 0 ? ptx::pack_bf16x2(v[2 * j], v[2 * j + 1])
+                               : ptx::pack_bf16x2(v[2 * j] - ptx::bf16_round(v[2 * j]), v[2 * j + 1] - ptx::bf16_round(v[2 * j + 1]));
+            uint4* srow = reinterpret_cast<uint4*>(stg + lane * PITCH);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              reinterpret_cast<uint4*>(o)[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-            if (args.split_out) {
-              uint32_t lo[16];
+            for (int j = 0; j < 4; ++j) srow[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            __syncwarp();
+            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(args.out) + col + (pass ? args.lo_off : 0);
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                lo[j] = ptx::pack_bf16x2(v[2 * j] - ptx::bf16_round(v[2 * j]), v[2 * j + 1] - ptx::bf16_round(v[2 * j + 1]));
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                reinterpret_cast<uint4*>(o + args.lo_off)[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + (lane >> 2), piece = lane & 3;
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * PITCH + piece * 16);
+              const int row = row_base + rr;
+              if (row < args.M) *reinterpret_cast<uint4*>(obase + static_cast<long long>(row) * args.ldo + piece * 8) = val;
             }
-          } else if (EPI == EPI_BIAS_RESID_F32) {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + static_cast<long long>(row) * args.ldo + col);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 x = o[j];
-              x.x += v[4 * j]; x.y += v[4 * j + 1]; x.z += v[4 * j + 2]; x.w += v[4 * j + 3];
-              o[j] = x;
-            }
-          } else {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.out) + static_cast<long long>(row) * args.ldo + col);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
           }
+        } else {
+          float4* srow = reinterpret_cast<float4*>(stg + lane * PITCH);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          float* obase = reinterpret_cast<float*>(args.out) + col;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3), piece = lane & 7;
+            float4 val = *reinterpret_cast<const float4*>(stg + rr * PITCH + piece * 16);
+            const int row = row_base + rr;
+            if (row < args.M) {
+              float4* o = reinterpret_cast<float4*>(obase + static_cast<long long>(row) * args.ldo + piece * 4);
+              if (EPI == EPI_BIAS_RESID_F32) {
+                val.x += xres[it].x; val.y += xres[it].y; val.z += xres[it].z; val.w += xres[it].w;
+              }
+              *o = val;
+            }
+          }
+          __syncwarp();
         }
       }
       ptx::tc_fence_before();

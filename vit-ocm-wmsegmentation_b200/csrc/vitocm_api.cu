@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -149,7 +150,7 @@ namespace {
 // ---------------------------------------------------------------------------------- GEMM launch
 template <int BN, int EPI>
 int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_sms, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI>;
   static bool attr_set = false;
   auto kern = gemm_bf16_tcgen05_kernel<BN, EPI>;
   if (!attr_set) {
@@ -197,9 +198,7 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
   TRY(make_tmap_bf16(&tb, B, N, kext, ldb, bn));
   GemmArgs a{};
   a.M = M; a.N = N; a.kblocks = K / GEMM_BK; a.nterms = split_in ? 3 : 1;
-  a.a_koff[0] = 0; a.b_koff[0] = 0;   // hi * hi
-  a.a_koff[1] = 0; a.b_koff[1] = K;   // hi * lo
-  a.a_koff[2] = K; a.b_koff[2] = 0;   // lo * hi
+  a.lo_k = K;
   a.bias = bias; a.out = out; a.ldo = ldo; a.split_out = split_out; a.lo_off = lo_off;
   switch (bn) {
     case 256: return launch_gemm_bn<256>(epi, ta, tb, a, e->num_sms, st);
