@@ -2,7 +2,8 @@
 # GPU box: correctness (each group in its own process), smoke, short bench, ncu launch list + full captures
 mkdir -p gpurun_out
 : > gpurun_out/t.log
-run() { echo "=== $*" >> gpurun_out/t.log; timeout 600 python -m pytest "$@" -m gpu -q --no-header --maxfail=20 2>&1 | tail -25 >> gpurun_out/t.log; }
+i=0
+run() { i=$((i+1)); echo "=== $*" >> gpurun_out/t.log; timeout 600 python -m pytest "$@" -m gpu -q --no-header --maxfail=20 > gpurun_out/pytest_$i.log 2>&1; grep -E "vitocm: mbarrier|^E  |passed|failed" gpurun_out/pytest_$i.log | head -40 >> gpurun_out/t.log; }
 run tests/test_gpu_kernels.py -k "gemm or layernorm or launch"
 run tests/test_gpu_kernels.py -k "attention"
 run tests/test_gpu_post.py

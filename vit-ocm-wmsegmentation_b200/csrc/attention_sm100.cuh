@@ -7,17 +7,15 @@
 // QKV activation [B*N, ld] (bf16, columns [3][H][64]) by one 2-D TMA tensor map (box 64 x 128,
 // SWIZZLE_128B).  Warp roles (256 threads): warps 0..3 = softmax (one thread per query row; TMEM lane
 // quadrant = warp % 4), warp 4 = TMA producer, warp 5 = MMA issuer + TMEM allocator, warps 6..7 idle.
-// setmaxnreg moves registers from warpgroup 1 to the softmax warpgroup (208 vs 48 per thread).
+// setmaxnreg moves registers from warpgroup 1 to the softmax warpgroup (208 vs 48 per thread in bf16 mode).
 //   S = Q K_j^T      : tcgen05.mma  M128 x N(<=128) x K64, both operands K-major, into TMEM
-//   softmax          : one tcgen05.ld pass of S into registers, exp2 with a lazily updated row max,
-//                      P -> smem (bf16, 128B-swizzled, the A operand of the next two MMAs)
+//   softmax          : one tcgen05.ld pass of S into registers; scale/shift on the packed f32x2 pipe
+//                      (FFMA2), MUFU.EX2, row sums on FADD2, P -> smem (bf16, 128B-swizzled)
 //   O += P V_j       : tcgen05.mma  M128 x N64 x K(<=128), B = V (MN-major), accumulating in TMEM
-//   L += P 1         : tcgen05.mma  M128 x N16 against a tile of ones -> the softmax row sums, so the
-//                      normaliser is built from exactly the bf16 P that multiplies V
 // The running maximum is only raised when a row exceeds it by more than 2^8 ("lazy rescale"): softmax
-// is shift invariant, so a stale maximum changes nothing but keeps O/L in TMEM untouched in the
-// common case; when it is raised the softmax warps rescale their O/L rows in TMEM.
-// Two CTAs are co-resident per SM (98 KB smem, 256 TMEM columns each) so one CTA's MMAs overlap
+// is shift invariant, so a stale maximum changes nothing but keeps O in TMEM untouched in the
+// common case; when it is raised the softmax warps rescale their O rows in TMEM.
+// Two CTAs are co-resident per SM (96 KB smem, 256 TMEM columns each) so one CTA's MMAs overlap
 // the other's exponentials.  SPLIT = true is the fp32-parity mode: every operand is a bf16
 // (hi, lo) pair and each product is hi*hi + hi*lo + lo*hi (fp32 accumulate in TMEM).
 #pragma once
@@ -39,15 +37,11 @@ constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 128;
 constexpr int ATT_DH = 64;
 constexpr int ATT_THREADS = 256;   // warpgroup 0 = softmax (warps 0..3), warpgroup 1 = TMA (warp 4) + MMA (warp 5)
-constexpr int ATT_REGS_SOFTMAX = 208;
-constexpr int ATT_REGS_OTHER = 48;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: one [128 x 64] bf16 tile
 constexpr int ATT_RING = 3;
 constexpr int ATT_TMEM_COLS = 256;
 constexpr int ATT_S_COL = 0;      // S: 128 columns
 constexpr int ATT_O_COL = 128;    // O: 64 columns
-constexpr int ATT_L_COL = 192;    // L: 16 columns (all equal: row sums of P)
-constexpr int ATT_ONES_BYTES = 2048;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 template <bool SPLIT>
@@ -56,7 +50,10 @@ struct AttnCfg {
   static constexpr int SLOT_BYTES = ATT_TILE_BYTES * NPART;       // one K or V block
   static constexpr int Q_BYTES = ATT_TILE_BYTES * NPART;
   static constexpr int P_BYTES = 2 * ATT_TILE_BYTES * NPART;      // [128 x 128] bf16 (two 64-key halves)
-  static constexpr int SMEM_BYTES = Q_BYTES + ATT_RING * SLOT_BYTES + P_BYTES + ATT_ONES_BYTES + 1024 + 128;
+  static constexpr int SMEM_BYTES = Q_BYTES + ATT_RING * SLOT_BYTES + P_BYTES + 1024 + 128;
+  // setmaxnreg budgets: 2 CTAs/SM x 128 x (208 + 48) = 64 K registers (bf16); one CTA/SM in split mode
+  static constexpr int REGS_SOFTMAX = SPLIT ? 240 : 208;
+  static constexpr int REGS_OTHER = SPLIT ? 64 : 48;
 };
 
 template <bool SPLIT>
@@ -64,21 +61,20 @@ __global__ void __launch_bounds__(ATT_THREADS, SPLIT ? 1 : 2)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs args) {
   using Cfg = AttnCfg<SPLIT>;
   constexpr int NPART = Cfg::NPART;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;
-  uint8_t* smem_ring = smem_q + Cfg::Q_BYTES;
-  uint8_t* smem_p = smem_ring + ATT_RING * Cfg::SLOT_BYTES;
-  uint8_t* smem_ones = smem_p + Cfg::P_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ones + ATT_ONES_BYTES);
-  uint64_t* q_full = bars;            // [1]
-  uint64_t* kv_full = bars + 1;       // [3]
-  uint64_t* kv_empty = bars + 4;      // [3]
-  uint64_t* s_full = bars + 7;        // MMA -> softmax
-  uint64_t* s_empty = bars + 8;       // softmax -> MMA   (4 warps)
-  uint64_t* p_full = bars + 9;        // softmax -> MMA   (4 warps)
-  uint64_t* o_full = bars + 10;       // MMA -> softmax
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 11);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_q = smem;
+  const uint32_t smem_ring = smem_q + Cfg::Q_BYTES;
+  const uint32_t smem_p = smem_ring + ATT_RING * Cfg::SLOT_BYTES;
+  const uint32_t bars = smem_p + Cfg::P_BYTES;
+  const uint32_t q_full = bars;             // [1]
+  const uint32_t kv_full = bars + 8;        // [3]
+  const uint32_t kv_empty = bars + 32;      // [3]
+  const uint32_t s_full = bars + 56;        // MMA -> softmax
+  const uint32_t s_empty = bars + 64;       // softmax -> MMA   (4 warps)
+  const uint32_t p_full = bars + 72;        // softmax -> MMA   (4 warps)
+  const uint32_t o_full = bars + 80;        // MMA -> softmax
+  const uint32_t tmem_ptr_smem = bars + 88;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,8 +88,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     ptx::prefetch_tmap(&tmap_qkv);
     ptx::mbar_init(q_full, 1);
     for (int i = 0; i < ATT_RING; ++i) {
-      ptx::mbar_init(&kv_full[i], 1);
-      ptx::mbar_init(&kv_empty[i], 1);
+      ptx::mbar_init(kv_full + 8 * i, 1);
+      ptx::mbar_init(kv_empty + 8 * i, 1);
     }
     ptx::mbar_init(s_full, 1);
     ptx::mbar_init(s_empty, 4);
@@ -105,19 +101,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     ptx::tmem_alloc(tmem_ptr_smem, ATT_TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  if (warp < 4) {  // tile of bf16 ones (layout-agnostic B operand of the row-sum MMA)
-    uint4* o = reinterpret_cast<uint4*>(smem_ones);
-    const uint32_t one2 = 0x3F803F80u;
-    for (int i = threadIdx.x; i < ATT_ONES_BYTES / 16; i += 128) o[i] = make_uint4(one2, one2, one2, one2);
-    ptx::fence_proxy_async_smem();
-  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = ptx::lds_u32(tmem_ptr_smem);
 
   if (warp >= 4) {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT_REGS_OTHER));
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_OTHER));
    if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -130,10 +120,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
       auto load = [&](int which /*1 = K, 2 = V*/, int j) {
         const int slot = item % ATT_RING;
         const uint32_t parity = ((item / ATT_RING) & 1) ^ 1;
-        ptx::mbar_wait(&kv_empty[slot], parity, 10);
-        ptx::mbar_arrive_expect_tx(&kv_full[slot], Cfg::SLOT_BYTES);
+        ptx::mbar_wait(kv_empty + 8 * slot, parity, 10);
+        ptx::mbar_arrive_expect_tx(kv_full + 8 * slot, Cfg::SLOT_BYTES);
         for (int part = 0; part < NPART; ++part)
-          ptx::tma_load_2d(smem_ring + slot * Cfg::SLOT_BYTES + part * ATT_TILE_BYTES, &tmap_qkv, &kv_full[slot],
+          ptx::tma_load_2d(smem_ring + slot * Cfg::SLOT_BYTES + part * ATT_TILE_BYTES, &tmap_qkv, kv_full + 8 * slot,
                            part * args.lo_col_off + which * D + h * ATT_DH, row_base + j * ATT_BKV);
         ++item;
       };
@@ -146,12 +136,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t q_addr = ptx::smem_u32(smem_q);
-      const uint32_t p_addr = ptx::smem_u32(smem_p);
       const uint32_t s_tmem = tmem_base + ATT_S_COL;
       const uint32_t o_tmem = tmem_base + ATT_O_COL;
-      const uint32_t l_tmem = tmem_base + ATT_L_COL;
-      const uint64_t ones_desc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_ones), 1024, 0);
       int item = 0;
       auto kv_len_mma = [&](int j) {  // keys of block j rounded up to the MMA granularity (16)
         int len = N - j * ATT_BKV;
@@ -160,15 +146,15 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
       };
       auto issue_s = [&](int j) {
         const int slot = item % ATT_RING;
-        ptx::mbar_wait(&kv_full[slot], (item / ATT_RING) & 1, 11);
+        ptx::mbar_wait(kv_full + 8 * slot, (item / ATT_RING) & 1, 11);
         ptx::tc_fence_after();
-        const uint32_t k_addr = ptx::smem_u32(smem_ring + slot * Cfg::SLOT_BYTES);
+        const uint32_t k_addr = smem_ring + slot * Cfg::SLOT_BYTES;
         const uint32_t idesc = ptx::make_idesc(ATT_BQ, kv_len_mma(j), false, false);
         uint32_t acc = 0;
         // terms: (Qhi,Khi) [, (Qhi,Klo), (Qlo,Khi)]
 #pragma unroll 1
         for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
-          const uint32_t qa = q_addr + (t == 2 ? ATT_TILE_BYTES : 0);
+          const uint32_t qa = smem_q + (t == 2 ? ATT_TILE_BYTES : 0);
           const uint32_t ka = k_addr + (t == 1 ? ATT_TILE_BYTES : 0);
 #pragma unroll
           for (int k = 0; k < ATT_DH / 16; ++k) {
@@ -177,27 +163,26 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
             acc = 1;
           }
         }
-        ptx::umma_commit(&kv_empty[slot]);
+        ptx::umma_commit(kv_empty + 8 * slot);
         ptx::umma_commit(s_full);
         ++item;
       };
       auto issue_pv = [&](int j) {
         const int slot = item % ATT_RING;
-        ptx::mbar_wait(&kv_full[slot], (item / ATT_RING) & 1, 12);
+        ptx::mbar_wait(kv_full + 8 * slot, (item / ATT_RING) & 1, 12);
         ptx::tc_fence_after();
-        const uint32_t v_addr = ptx::smem_u32(smem_ring + slot * Cfg::SLOT_BYTES);
+        const uint32_t v_addr = smem_ring + slot * Cfg::SLOT_BYTES;
         constexpr uint32_t idesc = ptx::make_idesc(ATT_BQ, ATT_DH, false, /*B = V is MN-major*/ true);
-        constexpr uint32_t idesc_l = ptx::make_idesc(ATT_BQ, 16, false, false);
         const int ksteps = kv_len_mma(j) / 16;
-        // O and L accumulate across KV blocks in TMEM.  Loops are kept rolled: this warp runs on a
-        // 48-register budget and the operands live in uniform registers.
+        // O accumulates across KV blocks in TMEM.  Loops are kept rolled: this warp runs on a
+        // 48-register budget.
         // A = P: K-major, 64-key halves of 16 KB, 32 B per 16-key step inside the 128 B swizzle row
         // B = V: MN-major [keys x 64]; 16 keys = two 8-row groups of 1024 B
         uint32_t acc = j > 0 ? 1u : 0u;
         // terms: (Phi,Vhi) [, (Phi,Vlo), (Plo,Vhi)]
 #pragma unroll 1
         for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
-          const uint32_t pa = p_addr + (t == 2 ? 2 * ATT_TILE_BYTES : 0);
+          const uint32_t pa = smem_p + (t == 2 ? 2 * ATT_TILE_BYTES : 0);
           const uint32_t va = v_addr + (t == 1 ? ATT_TILE_BYTES : 0);
 #pragma unroll 1
           for (int k = 0; k < ksteps; ++k) {
@@ -206,19 +191,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
             acc = 1;
           }
         }
-        // row sums: (Phi [+ Plo]) . 1
-        uint32_t acc_l = j > 0 ? 1u : 0u;
-#pragma unroll 1
-        for (int t = 0; t < (SPLIT ? 2 : 1); ++t) {
-          const uint32_t pa = p_addr + (t == 1 ? 2 * ATT_TILE_BYTES : 0);
-#pragma unroll 1
-          for (int k = 0; k < ksteps; ++k) {
-            ptx::umma_bf16_ss(l_tmem, ptx::make_smem_desc_sw128(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 1024, 0),
-                              ones_desc, idesc_l, acc_l);
-            acc_l = 1;
-          }
-        }
-        ptx::umma_commit(&kv_empty[slot]);
+        ptx::umma_commit(kv_empty + 8 * slot);
         ptx::umma_commit(o_full);
         ++item;
       };
@@ -231,7 +204,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
           ptx::tc_fence_after();
           issue_s(j + 1);
         }
-        ptx::mbar_wait(p_full, j & 1, 15);     // P_j in smem, O/L rescaled if needed
+        ptx::mbar_wait(p_full, j & 1, 15);     // P_j in smem, O rescaled if needed
         ptx::tc_fence_after();
         issue_pv(j);
       }
@@ -239,17 +212,20 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
    }
   } else {
     // ===================== softmax / output (warps 0..3) =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ATT_REGS_SOFTMAX));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_SOFTMAX));
     const int q = warp & 3;
     const int r = q * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float sl2 = args.scale_log2;
+    const uint64_t sl2_2 = ptx::dup_f32x2(sl2);
+    const uint32_t p_row = smem_p + r * 128;
+    const int rsw = r & 7;
     float m_used = -INFINITY;     // the row maximum the exponentials are taken against
+    float l_run = 0.f;            // running row sum (same units as O in TMEM)
 
     for (int j = 0; j < n_kv; ++j) {
       int kv_len = N - j * ATT_BKV;
       kv_len = kv_len > ATT_BKV ? ATT_BKV : kv_len;
-      const bool full = kv_len == ATT_BKV;
       const int nchunks = (((kv_len + 15) & ~15) + 31) >> 5;   // 32-column chunks the MMA produced
       ptx::mbar_wait(s_full, j & 1, 21);
       ptx::tc_fence_after();
@@ -264,20 +240,25 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(s_empty);
-      // ---- row maximum (masked only in the ragged last block)
-      float mx = -INFINITY;
-      if (full) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
-      } else {
+      // ---- ragged last block only: columns beyond the sequence (and chunks the MMA never wrote) -> -inf,
+      //      so the common path below carries no masks (exp2(-inf) = 0)
+      if (kv_len < ATT_BKV) {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c < nchunks && c * 32 + i < kv_len) mx = fmaxf(mx, __uint_as_float(s[c][i]));
+            if (c * 32 + i >= kv_len) s[c][i] = 0xff800000u;
       }
+      // ---- row maximum: four independent 3-input chains
+      float mx4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
+#pragma unroll
+        for (int i = 2; i < 32; i += 2) m0 = fmaxf(fmaxf(m0, __uint_as_float(s[c][i])), __uint_as_float(s[c][i + 1]));
+        mx4[c] = m0;
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       // ---- lazy rescale decision
       float alpha = 1.0f;
       if (j == 0) {
@@ -285,40 +266,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
       } else if ((mx - m_used) * sl2 > ATT_RESCALE_THRESHOLD) {
         alpha = ptx::ex2_approx((m_used - mx) * sl2);
         m_used = mx;
+        l_run *= alpha;
       }
-      const float m_sl2 = m_used * sl2;
-      // ---- p = exp2(s*sl2 - m*sl2) -> bf16 pairs -> swizzled smem (A operand of the PV / row-sum MMAs).
-      // 32 keys = 64 B = four 16-byte chunks of this row; the chunk index inside the 128 B row is
-      // XOR-swizzled with (row % 8) (SWIZZLE_128B, tile base 1024-aligned).
-      auto exp_chunk = [&](int c, uint32_t (&ph)[16], uint32_t (&pl)[16]) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float e0 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][2 * i]), sl2, -m_sl2));
-          float e1 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][2 * i + 1]), sl2, -m_sl2));
-          if (!full) {
-            if (c * 32 + 2 * i >= kv_len) e0 = 0.f;
-            if (c * 32 + 2 * i + 1 >= kv_len) e1 = 0.f;
-          }
-          ph[i] = ptx::pack_bf16x2(e0, e1);
-          if (SPLIT) pl[i] = ptx::pack_bf16x2(e0 - ptx::bf16_round(e0), e1 - ptx::bf16_round(e1));
-        }
-      };
-      auto store_chunk = [&](int c, const uint32_t (&ph)[16], const uint32_t (&pl)[16]) {
-        uint8_t* half_base = smem_p + (c >> 1) * ATT_TILE_BYTES + r * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk16 = ((c & 1) * 4 + g) ^ (r & 7);
-          *reinterpret_cast<uint4*>(half_base + chunk16 * 16) = make_uint4(ph[4 * g], ph[4 * g + 1], ph[4 * g + 2], ph[4 * g + 3]);
-          if (SPLIT)
-            *reinterpret_cast<uint4*>(half_base + 2 * ATT_TILE_BYTES + chunk16 * 16) =
-                make_uint4(pl[4 * g], pl[4 * g + 1], pl[4 * g + 2], pl[4 * g + 3]);
-        }
-      };
-      // the first two chunks are exponentiated while the previous PV MMA may still be running
-      uint32_t ph0[16], ph1[16], pl0[16], pl1[16];
-      exp_chunk(0, ph0, pl0);
-      if (nchunks > 1) exp_chunk(1, ph1, pl1);
-      // ---- previous PV done: P buffer free, O/L valid -> rescale them if this warp raised a maximum
+      const uint64_t nm2 = ptx::dup_f32x2(-m_used * sl2);
+      // ---- previous PV done: P buffer free, O valid -> rescale it if this warp raised a maximum
       if (j > 0) {
         ptx::mbar_wait(o_full, (j - 1) & 1, 20);
         ptx::tc_fence_after();
@@ -332,35 +283,51 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
             for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
             ptx::tmem_st_32x32b_x32(lane_addr + ATT_O_COL + c, t);
           }
-          uint32_t l0;
-          ptx::tmem_ld_32x32b_x1(lane_addr + ATT_L_COL, l0);
-          ptx::tmem_ld_wait1(l0);
-          ptx::tmem_st_32x32b_x1(lane_addr + ATT_L_COL, __float_as_uint(__uint_as_float(l0) * alpha));
           ptx::tmem_st_wait();
         }
       }
-      store_chunk(0, ph0, pl0);
-      if (nchunks > 1) store_chunk(1, ph1, pl1);
+      // ---- p = exp2(s*sl2 - m*sl2) -> bf16 pairs -> swizzled smem (A operand of the PV MMA).
+      // 32 keys = 64 B = four 16-byte chunks of this row; the chunk index inside the 128 B row is
+      // XOR-swizzled with (row % 8) (SWIZZLE_128B, tile base 1024-aligned).
+      uint64_t sum2[2] = {0ull, 0ull};
 #pragma unroll
-      for (int c = 2; c < 4; ++c) {
+      for (int c = 0; c < 4; ++c) {
         if (c < nchunks) {
           uint32_t ph[16], pl[16];
-          exp_chunk(c, ph, pl);
-          store_chunk(c, ph, pl);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t a2 = ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sl2_2, nm2);
+            float a0, a1;
+            ptx::unpack_f32x2(a2, a0, a1);
+            const float e0 = ptx::ex2_approx(a0), e1 = ptx::ex2_approx(a1);
+            sum2[i & 1] = ptx::add_f32x2(sum2[i & 1], ptx::pack_f32x2(e0, e1));
+            ph[i] = ptx::pack_bf16x2(e0, e1);
+            if (SPLIT) pl[i] = ptx::pack_bf16x2(e0 - ptx::bf16_round(e0), e1 - ptx::bf16_round(e1));
+          }
+          const uint32_t half_base = p_row + (c >> 1) * ATT_TILE_BYTES;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t off = static_cast<uint32_t>((((c & 1) * 4 + g) ^ rsw) << 4);
+            ptx::sts_v4(half_base + off, ph[4 * g], ph[4 * g + 1], ph[4 * g + 2], ph[4 * g + 3]);
+            if (SPLIT) ptx::sts_v4(half_base + 2 * ATT_TILE_BYTES + off, pl[4 * g], pl[4 * g + 1], pl[4 * g + 2], pl[4 * g + 3]);
+          }
         }
+      }
+      {
+        float a0, a1, b0, b1;
+        ptx::unpack_f32x2(sum2[0], a0, a1);
+        ptx::unpack_f32x2(sum2[1], b0, b1);
+        l_run += (a0 + a1) + (b0 + b1);
       }
       ptx::fence_proxy_async_smem();   // generic-proxy smem writes -> visible to tcgen05.mma
       ptx::tc_fence_before();          // orders the TMEM rescale before the MMA that accumulates on it
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_full);
     }
-    // ---- epilogue: ctx = O / L
+    // ---- epilogue: ctx = O / l
     ptx::mbar_wait(o_full, (n_kv - 1) & 1, 22);
     ptx::tc_fence_after();
-    uint32_t l0;
-    ptx::tmem_ld_32x32b_x1(lane_addr + ATT_L_COL, l0);
-    ptx::tmem_ld_wait1(l0);
-    const float inv = 1.0f / __uint_as_float(l0);
+    const float inv = 1.0f / l_run;
     const int qrow = qt * ATT_BQ + r;
     __nv_bfloat16* o = args.out + static_cast<long long>(row_base + qrow) * args.ldo + h * ATT_DH;
 #pragma unroll

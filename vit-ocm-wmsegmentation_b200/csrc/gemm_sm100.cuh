@@ -6,10 +6,19 @@
 // split-bf16 ("fp32 mode") product  hi*hi + hi*lo + lo*hi  in the same kernel.
 //
 // Replaces, on the reference path, nn.Linear at SSS/dino/vision_transformer.py:58,61 (fc1/fc2),
-// :80 (qkv), :88 (proj) with their bias / GELU (:59) / residual (:110-111) fused as epilogues.
+// :80 (qkv), :88 (proj) with their bias / GELU (:59) / residual (:110-111) fused as epilogues, and
+// (A_PATCH) the patch-embedding Conv2d at :127-131 + prepare_tokens :203-207 as an im2col-free GEMM:
+// the producer warps read NCHW fp32 pixels and write the bf16 K-major A tile straight into the
+// swizzled smem layout the MMA reads; nothing is materialised in HBM.
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warp 3 = idle, warps 4..11 = epilogue (lane quadrant = warp % 4, column half = (warp - 4) / 4).
+// Epilogue: TMEM -> registers (lane = row) -> bias / GELU -> per-warp swizzled smem box -> one TMA
+// store per 32x32 chunk (cp.async.bulk.tensor, rows beyond M clipped by the tensor map).  The fp32
+// residual epilogue uses the TMA reduce-add (cp.reduce.async.bulk.tensor .add): x += acc + bias is
+// performed by the L2, so the residual stream is never read back into the SM.
+//
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator
+// (+ A producer with warp 3 in A_PATCH mode), warps 4..11 = epilogue (lane quadrant = warp % 4,
+// column half = (warp - 4) / 4).
 #pragma once
 #include "ptx.cuh"
 
@@ -20,6 +29,7 @@ enum GemmEpilogue : int {
   EPI_BIAS_GELU_BF16 = 1,  // out_bf16 = gelu_erf(acc + bias)      (fc1)
   EPI_BIAS_RESID_F32 = 2,  // resid_f32 += acc + bias              (proj, fc2)
   EPI_BIAS_F32 = 3,        // out_f32 = acc + bias                 (generic / decoder)
+  EPI_PATCH_F32 = 4,       // X[b, 1+i, :] = mix(acc + bias, mask_token) + pos[1+i]   (patch embedding)
 };
 
 struct GemmArgs {
@@ -28,33 +38,34 @@ struct GemmArgs {
   int nterms;         // 1 (bf16 mode) or 3 (split mode: hi*hi + hi*lo + lo*hi)
   int lo_k;           // split mode: column where the lo halves of A and B start (= K)
   const float* bias;  // [N] or nullptr
-  void* out;          // bf16 or f32, row-major, leading dimension ldo
-  long long ldo;
   int split_out;      // bf16 outputs only: also write lo = bf16(v - hi) at column offset lo_off
   int lo_off;
+  // A_PATCH / EPI_PATCH_F32 only
+  const float* img;         // [B][C][H][W] fp32 pixels
+  int img_h, img_w, patch;  // pixels; patch size p (multiple of 8)
+  int n_patches;            // (H/p)*(W/p) per image
+  const float* pos;         // [1 + n_patches][N] position table
+  const float* mask;        // [B][n_patches] in {0,1} or nullptr (SimMIM mask-token mixing, SSS/model.py:31-33)
+  const float* mask_token;  // [N]
+  float* out_f32;           // X [B][1 + n_patches][N] token stream
 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARP0 = 4;
-
 constexpr int GEMM_NUM_EPI_WARPS = 8;
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
+constexpr int GEMM_STG_WARP_BYTES = 4096;   // one 32 x 32 fp32 box, or hi + lo 32 x 32 bf16 boxes
 
 template <int BN, int EPI>
 struct GemmCfg {
-  static constexpr bool OUT_BF16 = (EPI == 0 || EPI == 1);
+  static constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16);
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;       // 16 KB
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // epilogue staging: one [32 rows][32 cols] chunk per warp, rows padded by 16 B (conflict-free 128-bit stores)
-  static constexpr int STG_PITCH = (OUT_BF16 ? 64 : 128) + 16;
-  static constexpr int STG_WARP_BYTES = 32 * STG_PITCH;
-  static constexpr int STG_BYTES = GEMM_NUM_EPI_WARPS * STG_WARP_BYTES;
-  static constexpr int BIAS_WARP_FLOATS = 128;                 // >= BN / 2
-  static constexpr int BIAS_BYTES = GEMM_NUM_EPI_WARPS * BIAS_WARP_FLOATS * 4;
-  static constexpr int FIXED_BYTES = STG_BYTES + BIAS_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STG_BYTES = GEMM_NUM_EPI_WARPS * GEMM_STG_WARP_BYTES;
+  static constexpr int FIXED_BYTES = STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int STAGES_FIT = (GEMM_SMEM_LIMIT - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -67,25 +78,51 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-template <int BN, int EPI>
+// Exact-erf GELU for two values at once on the packed-f32x2 pipe (FFMA2/FMUL2), Abramowitz-Stegun
+// 7.1.26: erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + p z), z >= 0,
+// |error| <= 1.5e-7 (fp32 grade).  With z = |x| / sqrt(2) and q = x * erfc(z) / 2:
+//     gelu(x) = max(x, 0) - |q|
+__device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
+  const uint64_t x2 = ptx::pack_f32x2(x0, x1);
+  const uint64_t ax2 = x2 & 0x7fffffff7fffffffULL;
+  const uint64_t den = ptx::fma_f32x2(ax2, ptx::dup_f32x2(0.3275911f * 0.70710678118654752440f), ptx::dup_f32x2(1.0f));
+  float d0, d1;
+  ptx::unpack_f32x2(den, d0, d1);
+  const uint64_t t = ptx::pack_f32x2(ptx::rcp_approx(d0), ptx::rcp_approx(d1));
+  const uint64_t arg = ptx::mul_f32x2(ptx::mul_f32x2(x2, x2), ptx::dup_f32x2(-0.5f * 1.44269504088896340736f));
+  float g0, g1;
+  ptx::unpack_f32x2(arg, g0, g1);
+  const uint64_t e = ptx::pack_f32x2(ptx::ex2_approx(g0), ptx::ex2_approx(g1));
+  // coefficients pre-multiplied by 1/2
+  uint64_t h = ptx::fma_f32x2(t, ptx::dup_f32x2(0.5f * 1.061405429f), ptx::dup_f32x2(0.5f * -1.453152027f));
+  h = ptx::fma_f32x2(h, t, ptx::dup_f32x2(0.5f * 1.421413741f));
+  h = ptx::fma_f32x2(h, t, ptx::dup_f32x2(0.5f * -0.284496736f));
+  h = ptx::fma_f32x2(h, t, ptx::dup_f32x2(0.5f * 0.254829592f));
+  const uint64_t q = ptx::mul_f32x2(ptx::mul_f32x2(ptx::mul_f32x2(h, t), e), x2);
+  float q0, q1;
+  ptx::unpack_f32x2(q, q0, q1);
+  x0 = fmaxf(x0, 0.f) - fabsf(q0);
+  x1 = fmaxf(x1, 0.f) - fabsf(q1);
+}
+
+template <int BN, int EPI, bool A_PATCH>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const GemmArgs args) {
+                         const __grid_constant__ CUtensorMap tmap_c, const GemmArgs args) {
   using Cfg = GemmCfg<BN, EPI>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint8_t* smem_stg = smem + STAGES * Cfg::STAGE_BYTES;
-  float* smem_bias = reinterpret_cast<float*>(smem_stg + Cfg::STG_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + Cfg::STG_BYTES + Cfg::BIAS_BYTES);
-  uint64_t* full_bar = bars;                     // [STAGES]  TMA -> MMA
-  uint64_t* empty_bar = bars + STAGES;           // [STAGES]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * STAGES;       // [2]       MMA -> epilogue
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]       epilogue -> MMA
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment; all later accesses use 32-bit shared-window addresses
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + STAGES * Cfg::A_BYTES;
+  const uint32_t smem_stg = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bars = smem_stg + Cfg::STG_BYTES;
+  const uint32_t full_bar = bars;                         // [STAGES]  producers -> MMA
+  const uint32_t empty_bar = bars + 8 * STAGES;           // [STAGES]  MMA -> producers
+  const uint32_t tfull_bar = bars + 16 * STAGES;          // [2]       MMA -> epilogue
+  const uint32_t tempty_bar = bars + 16 * STAGES + 16;    // [2]       epilogue -> MMA
+  const uint32_t tmem_ptr_smem = bars + 16 * STAGES + 32;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -95,17 +132,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int k_iters = args.kblocks * args.nterms;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmap_a);
+    if (!A_PATCH) ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
+    if (EPI != EPI_PATCH_F32) ptx::prefetch_tmap(&tmap_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(full_bar + 8 * s, A_PATCH ? 3 : 1);   // TMA thread (+ one arrive per A-producer warp)
+      ptx::mbar_init(empty_bar + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&tfull_bar[s], 1);
-      ptx::mbar_init(&tempty_bar[s], 8);  // one arrive per epilogue warp
+      ptx::mbar_init(tfull_bar + 8 * s, 1);
+      ptx::mbar_init(tempty_bar + 8 * s, GEMM_NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -116,7 +154,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = ptx::lds_u32(tmem_ptr_smem);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -129,13 +167,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int it = 0; it < k_iters; ++it) {
           const int term = it / args.kblocks;
           const int kb = it - term * args.kblocks;
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1, 1);
+          ptx::mbar_arrive_expect_tx(full_bar + 8 * stage, A_PATCH ? Cfg::B_BYTES : Cfg::STAGE_BYTES);
           // split mode terms: (hi,hi) (hi,lo) (lo,hi); lo halves start at column K of each operand
           const int a_off = (term == 2 ? args.lo_k : 0) + kb * GEMM_BK;
           const int b_off = (term == 1 ? args.lo_k : 0) + kb * GEMM_BK;
-          ptx::tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], a_off, m0);
-          ptx::tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage], b_off, n0);
+          if (!A_PATCH) ptx::tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, full_bar + 8 * stage, a_off, m0);
+          ptx::tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, full_bar + 8 * stage, b_off, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -149,38 +187,87 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       int as = 0;
       uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, 2);
+        ptx::mbar_wait(tempty_bar + 8 * as, aphase ^ 1, 2);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
         for (int it = 0; it < k_iters; ++it) {
-          ptx::mbar_wait(&full_bar[stage], phase, 3);
+          ptx::mbar_wait(full_bar + 8 * stage, phase, 3);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem_a + stage * Cfg::A_BYTES);
-          const uint32_t b_addr = ptx::smem_u32(smem_b + stage * Cfg::B_BYTES);
+          const uint32_t a_addr = smem_a + stage * Cfg::A_BYTES;
+          const uint32_t b_addr = smem_b + stage * Cfg::B_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr + k * 32, 1024, 0);
             const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * 32, 1024, 0);
             ptx::umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          ptx::umma_commit(empty_bar + 8 * stage);  // smem slot reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tfull_bar[as]);  // accumulator complete
+        ptx::umma_commit(tfull_bar + 8 * as);  // accumulator complete
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else if (warp >= GEMM_EPI_WARP0) {
+  } else if (warp < GEMM_EPI_WARP0) {
+    // ===================== A producer (patch embedding only) =====================
+    // A[m, k] = bf16(x[b, c, py*p + yi, px*p + xi]),  m = b*n + py*Wp + px,  k = c*p*p + yi*p + xi.
+    // One item = (row, 16-byte chunk): 8 consecutive pixels of one patch row -> 8 bf16 at the
+    // SWIZZLE_128B position  row*128 + ((chunk ^ (row & 7)) << 4)  of the stage's A tile.
+    if (A_PATCH) {
+      const int t = threadIdx.x - 64;  // 0..63
+      const int p = args.patch, pp = p * p;
+      const int Wp = args.img_w / p;
+      const long long plane = static_cast<long long>(args.img_h) * args.img_w;
+      const int chans = (args.kblocks * GEMM_BK) / pp;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * GEMM_BM;
+        for (int it = 0; it < k_iters; ++it) {
+          const int term = it / args.kblocks;
+          const int kb = it - term * args.kblocks;
+          const bool want_lo = term == 2;
+          ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1, 5);
+          const uint32_t a_tile = smem_a + stage * Cfg::A_BYTES;
+#pragma unroll 4
+          for (int item = t; item < GEMM_BM * 8; item += 64) {
+            const int chunk = item >> 7;        // 0..7: consecutive threads -> consecutive rows (coalesced pixel reads)
+            const int row = item & 127;
+            const int m = m0 + row;
+            float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+            if (m < args.M) {
+              const int b = m / args.n_patches, i = m - b * args.n_patches;
+              const int py = i / Wp, px = i - py * Wp;
+              const int k = kb * GEMM_BK + chunk * 8;
+              const int c = k / pp, rem = k - c * pp;
+              const int yi = rem / p, xi = rem - yi * p;
+              const float* src = args.img + (static_cast<long long>(b) * chans + c) * plane +
+                                 static_cast<long long>(py * p + yi) * args.img_w + px * p + xi;
+              f0 = __ldg(reinterpret_cast<const float4*>(src));
+              f1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            }
+            float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+            if (want_lo) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] -= ptx::bf16_round(v[j]);
+            }
+            ptx::sts_v4(a_tile + row * 128 + ((chunk ^ (row & 7)) << 4), ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]),
+                        ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(full_bar + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
     // ===================== epilogue =====================
-    // TMEM -> registers (lane = row) -> +bias/GELU -> per-warp smem transpose -> global stores in which
-    // consecutive lanes cover consecutive 16-byte pieces of a row (full 32-byte sectors, no partial writes).
     const int q = warp & 3;                         // TMEM lane quadrant this warp may access
     const int ew = warp - GEMM_EPI_WARP0;           // 0..7
     const int half = ew >> 2;                       // which half of the BN columns
     constexpr int COLS_PER_WARP = BN / 2;
-    constexpr int PITCH = Cfg::STG_PITCH;
-    uint8_t* stg = smem_stg + ew * Cfg::STG_WARP_BYTES;
-    float* bias_s = smem_bias + ew * Cfg::BIAS_WARP_FLOATS;
+    const uint32_t stg = smem_stg + ew * GEMM_STG_WARP_BYTES;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -188,84 +275,105 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int n0 = (tile % tiles_n) * BN;
       const int row_base = m0 + q * 32;
       const int col_base = n0 + half * COLS_PER_WARP;
-      // this warp's slice of the bias, fetched before waiting on the accumulator
-      for (int j = lane; j < COLS_PER_WARP; j += 32) bias_s[j] = (args.bias != nullptr) ? __ldg(args.bias + col_base + j) : 0.f;
-      __syncwarp();
-      ptx::mbar_wait(&tfull_bar[as], aphase, 4);
+      ptx::mbar_wait(tfull_bar + 8 * as, aphase, 4);
       ptx::tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP; c += 32) {
-        // residual epilogue: the 8 row-pieces of x this lane will update are fetched first, so their
-        // latency hides behind the TMEM load and the smem transpose (lane -> row it*4 + lane/8, piece lane%8)
-        float4 xres[8];
-        if (EPI == EPI_BIAS_RESID_F32) {
-          const float* xbase = reinterpret_cast<const float*>(args.out) + col_base + c + (lane & 7) * 4;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int row = row_base + it * 4 + (lane >> 3);
-            xres[it] = (row < args.M) ? *reinterpret_cast<const float4*>(xbase + static_cast<long long>(row) * args.ldo)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
+        const int col = col_base + c;
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN + half * COLS_PER_WARP + c), r);
+        float bv[32];
+        if (args.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + col) + j);   // same address in every lane
+            bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bv[j] = 0.f;
+        }
         ptx::tmem_ld_wait(r);
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = __uint_as_float(r[j]) + bias_s[c + j];
-          if (EPI == EPI_BIAS_GELU_BF16) v[j] = gelu_erf(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bv[j];
+        if (EPI == EPI_BIAS_GELU_BF16) {
+          if (args.nterms == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) gelu_erf_x2(v[j], v[j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
         }
-        const int col = col_base + c;
-        if (Cfg::OUT_BF16) {
-          const int npass = args.split_out ? 2 : 1;
-          for (int pass = 0; pass < npass; ++pass) {
-            uint32_t w[16];
+        if (EPI == EPI_PATCH_F32) {
+          // token row of patch m = b*n + i is b*(n+1) + 1 + i: the row remap (and the +1 jump at image
+          // boundaries inside a chunk) rules out a box store; each lane writes its own 128 contiguous bytes
+          const int m = row_base + lane;
+          if (m < args.M) {
+            const int b = m / args.n_patches, i = m - b * args.n_patches;
+            if (args.mask != nullptr) {
+              const float mk = __ldg(args.mask + m);
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              w[j] = pass == 0 ? ptx::pack_bf16x2(v[2 * j], v[2 * j + 1])
-                               : ptx::pack_bf16x2(v[2 * j] - ptx::bf16_round(v[2 * j]), v[2 * j + 1] - ptx::bf16_round(v[2 * j + 1]));
-            uint4* srow = reinterpret_cast<uint4*>(stg + lane * PITCH);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) srow[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-            __syncwarp();
-            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(args.out) + col + (pass ? args.lo_off : 0);
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int rr = it * 8 + (lane >> 2), piece = lane & 3;
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * PITCH + piece * 16);
-              const int row = row_base + rr;
-              if (row < args.M) *reinterpret_cast<uint4*>(obase + static_cast<long long>(row) * args.ldo + piece * 8) = val;
+              for (int j = 0; j < 32; ++j) v[j] = v[j] * (1.f - mk) + __ldg(args.mask_token + col + j) * mk;
             }
-            __syncwarp();
+            const float4* pr = reinterpret_cast<const float4*>(args.pos + static_cast<long long>(1 + i) * args.N + col);
+            float4* orow = reinterpret_cast<float4*>(args.out_f32 + (static_cast<long long>(b) * (args.n_patches + 1) + 1 + i) * args.N + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 p4 = __ldg(pr + j);
+              orow[j] = make_float4(v[4 * j] + p4.x, v[4 * j + 1] + p4.y, v[4 * j + 2] + p4.z, v[4 * j + 3] + p4.w);
+            }
+          }
+          continue;
+        }
+        // the previous TMA store of this warp must have finished reading the staging box
+        if (lane == 0) ptx::bulk_wait_read0();
+        __syncwarp();
+        if (Cfg::OUT_BF16) {
+          // 32 rows x 64 B, SWIZZLE_64B: 16-byte chunk j of row r sits at r*64 + ((j ^ ((r >> 1) & 3)) << 4)
+          const uint32_t rowaddr = stg + lane * 64;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            ptx::sts_v4(rowaddr + ((j ^ sw) << 4), ptx::pack_bf16x2(v[8 * j], v[8 * j + 1]), ptx::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                        ptx::pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), ptx::pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          if (args.split_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] -= ptx::bf16_round(v[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              ptx::sts_v4(rowaddr + 2048 + ((j ^ sw) << 4), ptx::pack_bf16x2(v[8 * j], v[8 * j + 1]), ptx::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                          ptx::pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), ptx::pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
           }
         } else {
-          float4* srow = reinterpret_cast<float4*>(stg + lane * PITCH);
+          // 32 rows x 128 B, SWIZZLE_128B: chunk j of row r sits at r*128 + ((j ^ (r & 7)) << 4)
+          const uint32_t rowaddr = stg + lane * 128;
+          const int sw = lane & 7;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          __syncwarp();
-          float* obase = reinterpret_cast<float*>(args.out) + col;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + (lane >> 3), piece = lane & 7;
-            float4 val = *reinterpret_cast<const float4*>(stg + rr * PITCH + piece * 16);
-            const int row = row_base + rr;
-            if (row < args.M) {
-              float4* o = reinterpret_cast<float4*>(obase + static_cast<long long>(row) * args.ldo + piece * 4);
-              if (EPI == EPI_BIAS_RESID_F32) {
-                val.x += xres[it].x; val.y += xres[it].y; val.z += xres[it].z; val.w += xres[it].w;
-              }
-              *o = val;
-            }
+          for (int j = 0; j < 8; ++j)
+            ptx::sts_v4(rowaddr + ((j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                        __float_as_uint(v[4 * j + 3]));
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (EPI == EPI_BIAS_RESID_F32) {
+            ptx::tma_reduce_add_2d(&tmap_c, stg, col, row_base);
+          } else {
+            ptx::tma_store_2d(&tmap_c, stg, col, row_base);
+            if (Cfg::OUT_BF16 && args.split_out) ptx::tma_store_2d(&tmap_c, stg + 2048, col + args.lo_off, row_base);
           }
-          __syncwarp();
+          ptx::bulk_commit();
         }
       }
+      // accumulator stage fully read into registers -> hand it back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * as);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (lane == 0) ptx::bulk_wait_all0();   // global writes complete before the CTA exits
   }
 
   ptx::tc_fence_before();

@@ -1,5 +1,5 @@
 // Bandwidth-bound ViT kernels (vectorised, coalesced, fp32 statistics):
-//   patch_embed_kernel   SSS/dino/vision_transformer.py:129-132 + :203-207 (+ model.py:31-33 mask-token mix)
+//   cls_rows_kernel      SSS/dino/vision_transformer.py:203-207, CLS row (patch rows: gemm_sm100.cuh A_PATCH)
 //   layernorm_kernel     vit.py:107,111 (norm1/norm2) and :215/:234 (final norm), eps = 1e-6
 //   cls_attn_row_kernel  vit.py:80-84 restricted to the CLS query of the last block
 //   attn_probs_kernel    vit.py:83-84 full softmax(QK^T) (API-complete get_last_selfattention)
@@ -20,69 +20,15 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Patch embedding, im2col-free: reads NCHW pixels directly, writes the fp32 token stream
-//   X[b, 1 + py*Wp + px, :] = W[:, c, yi, xi] . x[b, c, py*p+yi, px*p+xi] + bias + pos[1 + ...]
-//   X[b, 0, :]              = cls_token + pos[0]
-// One block = one row of patches (Wp patches) of one image; thread d-loop over D with the
-// transposed weight Wt[K][D] so that weight loads are coalesced; pixels staged in smem.
-// Optional SimMIM mask-token mixing (mask[b, n] in {0,1}) before the position add.
+// prepare_tokens, CLS part (vit.py:203-207): X[b, 0, :] = cls_token + pos[0].  The patch rows are
+// written by the patch-embedding GEMM (gemm_sm100.cuh, A_PATCH / EPI_PATCH_F32).
 // ---------------------------------------------------------------------------------------
-constexpr int PE_MAX_PATCHES = 32;   // patches per block iteration
-
-__global__ void __launch_bounds__(128)
-patch_embed_kernel(const float* __restrict__ x, const float* __restrict__ wt /*[K][D]*/, const float* __restrict__ bias,
-                   const float* __restrict__ pos /*[1+n][D]*/, const float* __restrict__ cls_token,
-                   const float* __restrict__ mask /*[B][n] or null*/, const float* __restrict__ mask_token,
-                   float* __restrict__ out /*[B][1+n][D]*/, int C, int H, int W, int p, int D) {
-  extern __shared__ float pe_smem[];  // [PE_MAX_PATCHES][K]
-  const int Wp = W / p, Hp = H / p;
-  const int K = C * p * p;
-  const int py = blockIdx.x, b = blockIdx.y;
-  const int n = Hp * Wp;
-  const float* xb = x + static_cast<long long>(b) * C * H * W;
-  float* ob = out + static_cast<long long>(b) * (n + 1) * D;
-
-  if (py == 0) {
-    for (int d = threadIdx.x; d < D; d += blockDim.x) ob[d] = cls_token[d] + pos[d];
-  }
-  for (int px0 = 0; px0 < Wp; px0 += PE_MAX_PATCHES) {
-    const int np = min(PE_MAX_PATCHES, Wp - px0);
-    __syncthreads();
-    // stage np patches: iterate over (c, yi) rows; each row segment is np*p contiguous pixels
-    const int seg = np * p;
-    for (int idx = threadIdx.x; idx < C * p * seg; idx += blockDim.x) {
-      const int cy = idx / seg;       // c*p + yi
-      const int xx = idx - cy * seg;  // pixel inside the segment
-      const int c = cy / p, yi = cy - c * p;
-      const int pl = xx / p, xi = xx - pl * p;
-      pe_smem[pl * K + c * p * p + yi * p + xi] = xb[(static_cast<long long>(c) * H + py * p + yi) * W + px0 * p + xx];
-    }
-    __syncthreads();
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-      float acc[PE_MAX_PATCHES];
-#pragma unroll
-      for (int i = 0; i < PE_MAX_PATCHES; ++i) acc[i] = 0.f;
-      for (int k = 0; k < K; ++k) {
-        const float w = __ldg(wt + static_cast<long long>(k) * D + d);
-#pragma unroll
-        for (int i = 0; i < PE_MAX_PATCHES; ++i)
-          if (i < np) acc[i] = fmaf(w, pe_smem[i * K + k], acc[i]);
-      }
-      const float bd = bias[d];
-#pragma unroll
-      for (int i = 0; i < PE_MAX_PATCHES; ++i) {
-        if (i < np) {
-          const int tok = py * Wp + px0 + i;
-          float v = acc[i] + bd;
-          if (mask != nullptr) {
-            const float m = mask[static_cast<long long>(b) * n + tok];
-            v = v * (1.f - m) + mask_token[d] * m;
-          }
-          ob[static_cast<long long>(1 + tok) * D + d] = v + pos[static_cast<long long>(1 + tok) * D + d];
-        }
-      }
-    }
-  }
+__global__ void cls_rows_kernel(const float* __restrict__ cls_token, const float* __restrict__ pos, float* __restrict__ X, int B,
+                                long long image_stride, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int b = i / D, d = i - b * D;
+  X[static_cast<long long>(b) * image_stride + d] = cls_token[d] + pos[d];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -323,16 +269,6 @@ __global__ void split_weight_kernel(const float* __restrict__ w, __nv_bfloat16* 
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     out[r * ldo + c] = hi;
     if (split) out[r * ldo + lo_off + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
-  }
-}
-
-// [R][C] -> [C][R] fp32 (patch-embed weight transpose at load time)
-__global__ void transpose_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
-  const long long total = static_cast<long long>(R) * C;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / C), c = static_cast<int>(i - static_cast<long long>(r) * C);
-    out[static_cast<long long>(c) * R + r] = in[i];
   }
 }
 

@@ -82,21 +82,29 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map over a row-major [rows][ld] matrix, box = [box_rows][64 cols], SWIZZLE_128B
-int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+// Tensor map over a dense row-major matrix (rank 2: [rows][ld]; rank 3: [outer][rows][ld] with `outer_stride`
+// elements between slabs).  Operand loads: bf16, box [box_rows][64], SWIZZLE_128B.  Epilogue stores: box
+// [32][32], SWIZZLE_64B (bf16) or SWIZZLE_128B (fp32).
+int make_tmap(CUtensorMap* tm, const void* ptr, bool f32, long long cols, long long rows, long long ld, int box_cols,
+              int box_rows, CUtensorMapSwizzle swz, long long outer = 0, long long outer_stride = 0) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return fail(VITOCM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0)
+  const int es = f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * es) % 16 != 0 || (outer_stride * es) % 16 != 0)
     return fail(VITOCM_ERR_INVALID, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const cuuint32_t rank = outer > 0 ? 3 : 2;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * es, static_cast<cuuint64_t>(outer_stride) * es};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(VITOCM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
   return 0;
+}
+int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  return make_tmap(tm, ptr, false, cols, rows, ld, 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 struct DevBuf {
@@ -133,7 +141,7 @@ struct vitocm_engine {
   bool finalized = false;
   std::map<std::string, DevBuf*> master;  // fp32 weights as loaded
   std::vector<LayerW> layers;
-  DevBuf patch_wt;  // [K][D] fp32
+  DevBuf patch_w;   // bf16 [D][2K]  (hi | lo): the conv filter as a K-major GEMM operand
   ~vitocm_engine() { for (auto& kv : master) delete kv.second; }
   const float* w(const std::string& name) const {
     auto it = master.find(name);
@@ -148,29 +156,31 @@ struct vitocm_engine {
 namespace {
 
 // ---------------------------------------------------------------------------------- GEMM launch
-template <int BN, int EPI>
-int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_sms, cudaStream_t st) {
+template <int BN, int EPI, bool A_PATCH>
+int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& a, int num_sms,
+                     cudaStream_t st) {
   using Cfg = GemmCfg<BN, EPI>;
   static bool attr_set = false;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, A_PATCH>;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * (a.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, a);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, a);
   LAUNCH_CHECK();
   return 0;
 }
 
 template <int BN>
-int launch_gemm_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, int num_sms, cudaStream_t st) {
+int launch_gemm_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& a, int num_sms,
+                   cudaStream_t st) {
   switch (epi) {
-    case EPI_BIAS_BF16: return launch_gemm_inst<BN, EPI_BIAS_BF16>(ta, tb, a, num_sms, st);
-    case EPI_BIAS_GELU_BF16: return launch_gemm_inst<BN, EPI_BIAS_GELU_BF16>(ta, tb, a, num_sms, st);
-    case EPI_BIAS_RESID_F32: return launch_gemm_inst<BN, EPI_BIAS_RESID_F32>(ta, tb, a, num_sms, st);
-    case EPI_BIAS_F32: return launch_gemm_inst<BN, EPI_BIAS_F32>(ta, tb, a, num_sms, st);
+    case EPI_BIAS_BF16: return launch_gemm_inst<BN, EPI_BIAS_BF16, false>(ta, tb, tc, a, num_sms, st);
+    case EPI_BIAS_GELU_BF16: return launch_gemm_inst<BN, EPI_BIAS_GELU_BF16, false>(ta, tb, tc, a, num_sms, st);
+    case EPI_BIAS_RESID_F32: return launch_gemm_inst<BN, EPI_BIAS_RESID_F32, false>(ta, tb, tc, a, num_sms, st);
+    case EPI_BIAS_F32: return launch_gemm_inst<BN, EPI_BIAS_F32, false>(ta, tb, tc, a, num_sms, st);
   }
   return fail(VITOCM_ERR_INVALID, "unknown GEMM epilogue %d", epi);
 }
@@ -192,19 +202,22 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
   if (K % GEMM_BK != 0) return fail(VITOCM_ERR_INVALID, "GEMM K=%d must be a multiple of %d", K, GEMM_BK);
   const int bn = pick_bn(N);
   if (bn == 0) return fail(VITOCM_ERR_INVALID, "GEMM N=%d must be a multiple of 64", N);
+  if (bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15) != 0) return fail(VITOCM_ERR_INVALID, "GEMM bias must be 16-byte aligned");
   const long long kext = static_cast<long long>(K) * (split_in ? 2 : 1);
-  CUtensorMap ta, tb;
+  const bool out_f32 = (epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_F32);
+  CUtensorMap ta, tb, tc;
   TRY(make_tmap_bf16(&ta, A, M, kext, lda, GEMM_BM));
   TRY(make_tmap_bf16(&tb, B, N, kext, ldb, bn));
+  TRY(make_tmap(&tc, out, out_f32, ldo, M, ldo, 32, 32, out_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
   GemmArgs a{};
   a.M = M; a.N = N; a.kblocks = K / GEMM_BK; a.nterms = split_in ? 3 : 1;
   a.lo_k = K;
-  a.bias = bias; a.out = out; a.ldo = ldo; a.split_out = split_out; a.lo_off = lo_off;
+  a.bias = bias; a.split_out = split_out; a.lo_off = lo_off;
   switch (bn) {
-    case 256: return launch_gemm_bn<256>(epi, ta, tb, a, e->num_sms, st);
-    case 192: return launch_gemm_bn<192>(epi, ta, tb, a, e->num_sms, st);
-    case 128: return launch_gemm_bn<128>(epi, ta, tb, a, e->num_sms, st);
-    default: return launch_gemm_bn<64>(epi, ta, tb, a, e->num_sms, st);
+    case 256: return launch_gemm_bn<256>(epi, ta, tb, tc, a, e->num_sms, st);
+    case 192: return launch_gemm_bn<192>(epi, ta, tb, tc, a, e->num_sms, st);
+    case 128: return launch_gemm_bn<128>(epi, ta, tb, tc, a, e->num_sms, st);
+    default: return launch_gemm_bn<64>(epi, ta, tb, tc, a, e->num_sms, st);
   }
 }
 
@@ -245,25 +258,34 @@ int run_layernorm(const float* X, const float* g, const float* b, void* out_bf16
   return 0;
 }
 
+// prepare_tokens (vit.py:198-209) as an im2col-free tcgen05 GEMM: M = B * n patches, K = C p^2, N = D.
 int run_patch_embed(const vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const float* mask,
                     float* X, cudaStream_t st) {
   const int p = e->cfg.patch_size, C = e->cfg.in_chans, D = e->cfg.embed_dim;
   if (H % p != 0 || W % p != 0) return fail(VITOCM_ERR_INVALID, "image %dx%d not a multiple of patch %d", H, W, p);
   const int K = C * p * p;
-  const size_t smem = static_cast<size_t>(PE_MAX_PATCHES) * K * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    CUDA_TRY(cudaFuncSetAttribute(patch_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    smem_set = smem;
-  }
+  if (p % 8 != 0 || K % GEMM_BK != 0) return fail(VITOCM_ERR_INVALID, "patch embedding needs patch %% 8 == 0 and C*p*p %% 64 == 0 (patch %d, chans %d)", p, C);
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(pos) & 15) != 0)
+    return fail(VITOCM_ERR_INVALID, "patch embedding inputs must be 16-byte aligned");
   const float* mask_token = e->w("mask_token");
   if (mask != nullptr && mask_token == nullptr) return fail(VITOCM_ERR_STATE, "mask given but mask_token was never loaded");
+  const int n = (H / p) * (W / p);
+  const int M = B * n;
   ProfScope prof(PC_PATCH, st);
-  dim3 grid(H / p, B);
-  patch_embed_kernel<<<grid, 128, smem, st>>>(x, e->patch_wt.as<float>(), e->w("patch_embed.proj.bias"), pos, e->w("cls_token"),
-                                              mask, mask_token, X, C, H, W, p, D);
+  cls_rows_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(e->w("cls_token"), pos, X, B, static_cast<long long>(n + 1) * D, D);
   LAUNCH_CHECK();
-  return 0;
+  const int bn = (D % 192 == 0) ? 192 : (D % 128 == 0 ? 128 : 64);
+  CUtensorMap tb;
+  TRY(make_tmap_bf16(&tb, e->patch_w.p, D, 2LL * K, 2LL * K, bn));
+  GemmArgs a{};
+  a.M = M; a.N = D; a.kblocks = K / GEMM_BK; a.nterms = 3; a.lo_k = K;   // split precision in both modes
+  a.bias = e->w("patch_embed.proj.bias");
+  a.img = x; a.img_h = H; a.img_w = W; a.patch = p; a.n_patches = n; a.pos = pos; a.mask = mask; a.mask_token = mask_token; a.out_f32 = X;
+  switch (bn) {
+    case 192: return launch_gemm_inst<192, EPI_PATCH_F32, true>(tb, tb, tb, a, e->num_sms, st);
+    case 128: return launch_gemm_inst<128, EPI_PATCH_F32, true>(tb, tb, tb, a, e->num_sms, st);
+    default: return launch_gemm_inst<64, EPI_PATCH_F32, true>(tb, tb, tb, a, e->num_sms, st);
+  }
 }
 
 // workspace carve-up for a chunk of `tiles` images
@@ -401,9 +423,6 @@ int vitocm_finalize_weights(vitocm_engine* e) {
   TRY(need("patch_embed.proj.bias", D));
   TRY(need("norm.weight", D));
   TRY(need("norm.bias", D));
-  TRY(e->patch_wt.alloc(static_cast<size_t>(D) * K * 4));
-  transpose_f32_kernel<<<256, 256>>>(e->w("patch_embed.proj.weight"), e->patch_wt.as<float>(), D, K);
-  LAUNCH_CHECK();
   auto pack = [&](DevBuf& dst, const float* src, int R, int C, int split) -> int {
     const int parts = split ? 2 : 1;
     TRY(dst.alloc(static_cast<size_t>(R) * C * parts * 2));
@@ -411,6 +430,7 @@ int vitocm_finalize_weights(vitocm_engine* e) {
     LAUNCH_CHECK();
     return 0;
   };
+  TRY(pack(e->patch_w, e->w("patch_embed.proj.weight"), D, K, 1));   // always hi | lo: K is tiny, keep the tokens fp32-grade
   for (int l = 0; l < e->cfg.depth; ++l) {
     const std::string pre = "blocks." + std::to_string(l) + ".";
     LayerW& L = e->layers[l];
