@@ -10,12 +10,14 @@
 // setmaxnreg moves registers from warpgroup 1 to the softmax warpgroup (208 vs 48 per thread in bf16 mode).
 //   S = Q K_j^T      : tcgen05.mma  M128 x N(<=128) x K64, both operands K-major, into TMEM
 //   softmax          : one tcgen05.ld pass of S into registers; scale/shift on the packed f32x2 pipe
-//                      (FFMA2), MUFU.EX2, row sums on FADD2, P -> smem (bf16, 128B-swizzled)
-//   O += P V_j       : tcgen05.mma  M128 x N64 x K(<=128), B = V (MN-major), accumulating in TMEM
+//                      (FFMA2), MUFU.EX2, row sums on FADD2, P -> TMEM (tcgen05.st, packed bf16x2 columns):
+//                      no shared-memory round trip, no generic->async proxy fence
+//   O += P V_j       : tcgen05.mma  M128 x N64 x K(<=128), A = P from TMEM, B = V (smem, MN-major),
+//                      accumulating in TMEM
 // The running maximum is only raised when a row exceeds it by more than 2^8 ("lazy rescale"): softmax
 // is shift invariant, so a stale maximum changes nothing but keeps O in TMEM untouched in the
 // common case; when it is raised the softmax warps rescale their O rows in TMEM.
-// Two CTAs are co-resident per SM (96 KB smem, 256 TMEM columns each) so one CTA's MMAs overlap
+// Two CTAs are co-resident per SM (64 KB smem, 256 TMEM columns each: S 128 | O 64 | P 64) so one CTA's MMAs overlap
 // the other's exponentials.  SPLIT = true is the fp32-parity mode: every operand is a bf16
 // (hi, lo) pair and each product is hi*hi + hi*lo + lo*hi (fp32 accumulate in TMEM).
 #pragma once
@@ -39,9 +41,9 @@ constexpr int ATT_DH = 64;
 constexpr int ATT_THREADS = 256;   // warpgroup 0 = softmax (warps 0..3), warpgroup 1 = TMA (warp 4) + MMA (warp 5)
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: one [128 x 64] bf16 tile
 constexpr int ATT_RING = 3;
-constexpr int ATT_TMEM_COLS = 256;
-constexpr int ATT_S_COL = 0;      // S: 128 columns
-constexpr int ATT_O_COL = 128;    // O: 64 columns
+constexpr int ATT_S_COL = 0;      // S: 128 columns (fp32)
+constexpr int ATT_O_COL = 128;    // O: 64 columns (fp32)
+constexpr int ATT_P_COL = 192;    // P: 64 columns of packed bf16x2 (128 keys); split mode: lo part in the next 64
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 template <bool SPLIT>
@@ -49,8 +51,8 @@ struct AttnCfg {
   static constexpr int NPART = SPLIT ? 2 : 1;                     // hi (+ lo)
   static constexpr int SLOT_BYTES = ATT_TILE_BYTES * NPART;       // one K or V block
   static constexpr int Q_BYTES = ATT_TILE_BYTES * NPART;
-  static constexpr int P_BYTES = 2 * ATT_TILE_BYTES * NPART;      // [128 x 128] bf16 (two 64-key halves)
-  static constexpr int SMEM_BYTES = Q_BYTES + ATT_RING * SLOT_BYTES + P_BYTES + 1024 + 128;
+  static constexpr int SMEM_BYTES = Q_BYTES + ATT_RING * SLOT_BYTES + 1024 + 128;
+  static constexpr int TMEM_COLS = SPLIT ? 512 : 256;
   // setmaxnreg budgets: 2 CTAs/SM x 128 x (208 + 48) = 64 K registers (bf16); one CTA/SM in split mode
   static constexpr int REGS_SOFTMAX = SPLIT ? 240 : 208;
   static constexpr int REGS_OTHER = SPLIT ? 64 : 48;
@@ -65,8 +67,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
   const uint32_t smem = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_q = smem;
   const uint32_t smem_ring = smem_q + Cfg::Q_BYTES;
-  const uint32_t smem_p = smem_ring + ATT_RING * Cfg::SLOT_BYTES;
-  const uint32_t bars = smem_p + Cfg::P_BYTES;
+  const uint32_t bars = smem_ring + ATT_RING * Cfg::SLOT_BYTES;
   const uint32_t q_full = bars;             // [1]
   const uint32_t kv_full = bars + 8;        // [3]
   const uint32_t kv_empty = bars + 32;      // [3]
@@ -98,7 +99,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     ptx::fence_barrier_init();
   }
   if (warp == 5) {
-    ptx::tmem_alloc(tmem_ptr_smem, ATT_TMEM_COLS);
+    ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -174,20 +175,19 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
         const uint32_t v_addr = smem_ring + slot * Cfg::SLOT_BYTES;
         constexpr uint32_t idesc = ptx::make_idesc(ATT_BQ, ATT_DH, false, /*B = V is MN-major*/ true);
         const int ksteps = kv_len_mma(j) / 16;
-        // O accumulates across KV blocks in TMEM.  Loops are kept rolled: this warp runs on a
-        // 48-register budget.
-        // A = P: K-major, 64-key halves of 16 KB, 32 B per 16-key step inside the 128 B swizzle row
+        // O accumulates across KV blocks in TMEM.  Loops are kept rolled: this warp runs on a small
+        // register budget.
+        // A = P in TMEM: 16 keys = 8 packed columns per step
         // B = V: MN-major [keys x 64]; 16 keys = two 8-row groups of 1024 B
         uint32_t acc = j > 0 ? 1u : 0u;
         // terms: (Phi,Vhi) [, (Phi,Vlo), (Plo,Vhi)]
 #pragma unroll 1
         for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
-          const uint32_t pa = smem_p + (t == 2 ? 2 * ATT_TILE_BYTES : 0);
+          const uint32_t pa = tmem_base + ATT_P_COL + (t == 2 ? 64 : 0);
           const uint32_t va = v_addr + (t == 1 ? ATT_TILE_BYTES : 0);
 #pragma unroll 1
           for (int k = 0; k < ksteps; ++k) {
-            ptx::umma_bf16_ss(o_tmem, ptx::make_smem_desc_sw128(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 1024, 0),
-                              ptx::make_smem_desc_sw128(va + k * 2048, 1024, 1024), idesc, acc);
+            ptx::umma_bf16_ts(o_tmem, pa + k * 8, ptx::make_smem_desc_sw128(va + k * 2048, 1024, 1024), idesc, acc);
             acc = 1;
           }
         }
@@ -218,8 +218,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float sl2 = args.scale_log2;
     const uint64_t sl2_2 = ptx::dup_f32x2(sl2);
-    const uint32_t p_row = smem_p + r * 128;
-    const int rsw = r & 7;
     float m_used = -INFINITY;     // the row maximum the exponentials are taken against
     float l_run = 0.f;            // running row sum (same units as O in TMEM)
 
@@ -283,12 +281,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
             for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
             ptx::tmem_st_32x32b_x32(lane_addr + ATT_O_COL + c, t);
           }
-          ptx::tmem_st_wait();
         }
       }
-      // ---- p = exp2(s*sl2 - m*sl2) -> bf16 pairs -> swizzled smem (A operand of the PV MMA).
-      // 32 keys = 64 B = four 16-byte chunks of this row; the chunk index inside the 128 B row is
-      // XOR-swizzled with (row % 8) (SWIZZLE_128B, tile base 1024-aligned).
+      // ---- p = exp2(s*sl2 - m*sl2) -> bf16 pairs -> TMEM columns P_COL + key/2 of this thread's lane
+      // (the A operand of the PV MMA)
       uint64_t sum2[2] = {0ull, 0ull};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -304,13 +300,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
             ph[i] = ptx::pack_bf16x2(e0, e1);
             if (SPLIT) pl[i] = ptx::pack_bf16x2(e0 - ptx::bf16_round(e0), e1 - ptx::bf16_round(e1));
           }
-          const uint32_t half_base = p_row + (c >> 1) * ATT_TILE_BYTES;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t off = static_cast<uint32_t>((((c & 1) * 4 + g) ^ rsw) << 4);
-            ptx::sts_v4(half_base + off, ph[4 * g], ph[4 * g + 1], ph[4 * g + 2], ph[4 * g + 3]);
-            if (SPLIT) ptx::sts_v4(half_base + 2 * ATT_TILE_BYTES + off, pl[4 * g], pl[4 * g + 1], pl[4 * g + 2], pl[4 * g + 3]);
-          }
+          ptx::tmem_st_32x32b_x16(lane_addr + ATT_P_COL + c * 16, ph);
+          if (SPLIT) ptx::tmem_st_32x32b_x16(lane_addr + ATT_P_COL + 64 + c * 16, pl);
         }
       }
       {
@@ -319,8 +310,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
         ptx::unpack_f32x2(sum2[1], b0, b1);
         l_run += (a0 + a1) + (b0 + b1);
       }
-      ptx::fence_proxy_async_smem();   // generic-proxy smem writes -> visible to tcgen05.mma
-      ptx::tc_fence_before();          // orders the TMEM rescale before the MMA that accumulates on it
+      ptx::tmem_st_wait();             // P (and a rescaled O) are in TMEM
+      ptx::tc_fence_before();          // ... and ordered before the MMA that reads / accumulates on them
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_full);
     }
@@ -360,7 +351,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
   __syncthreads();
   if (warp == 5) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

@@ -56,7 +56,6 @@ constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARP0 = 4;
 constexpr int GEMM_NUM_EPI_WARPS = 8;
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
-constexpr int GEMM_STG_WARP_BYTES = 4096;   // one 32 x 32 fp32 box, or hi + lo 32 x 32 bf16 boxes
 
 template <int BN, int EPI>
 struct GemmCfg {
@@ -64,7 +63,11 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;       // 16 KB
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STG_BYTES = GEMM_NUM_EPI_WARPS * GEMM_STG_WARP_BYTES;
+  // per-warp epilogue staging, double buffered: 2 x (32 x 32 fp32 box) or 2 x (32 x 32 bf16 box); with a split
+  // bf16 output the two bf16 boxes hold hi and lo instead (single buffered -- the parity mode is not the fast path)
+  static constexpr int STG_BOX_BYTES = OUT_BF16 ? 2048 : 4096;
+  static constexpr int STG_WARP_BYTES = 2 * STG_BOX_BYTES;
+  static constexpr int STG_BYTES = GEMM_NUM_EPI_WARPS * STG_WARP_BYTES;
   static constexpr int FIXED_BYTES = STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int STAGES_FIT = (GEMM_SMEM_LIMIT - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
@@ -165,8 +168,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int m0 = (tile / tiles_n) * GEMM_BM;
         const int n0 = (tile % tiles_n) * BN;
         for (int it = 0; it < k_iters; ++it) {
-          const int term = it / args.kblocks;
-          const int kb = it - term * args.kblocks;
+          // operand order: term-major for TMA-fed A; k-block-major in patch mode so that the three terms of
+          // one k-block re-read the same pixels out of L1
+          const int term = A_PATCH ? it % args.nterms : it / args.kblocks;
+          const int kb = A_PATCH ? it / args.nterms : it - term * args.kblocks;
           ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1, 1);
           ptx::mbar_arrive_expect_tx(full_bar + 8 * stage, A_PATCH ? Cfg::B_BYTES : Cfg::STAGE_BYTES);
           // split mode terms: (hi,hi) (hi,lo) (lo,hi); lo halves start at column K of each operand
@@ -224,35 +229,49 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / tiles_n) * GEMM_BM;
         for (int it = 0; it < k_iters; ++it) {
-          const int term = it / args.kblocks;
-          const int kb = it - term * args.kblocks;
+          const int term = it % args.nterms;
+          const int kb = it / args.nterms;
           const bool want_lo = term == 2;
           ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1, 5);
           const uint32_t a_tile = smem_a + stage * Cfg::A_BYTES;
-#pragma unroll 4
-          for (int item = t; item < GEMM_BM * 8; item += 64) {
-            const int chunk = item >> 7;        // 0..7: consecutive threads -> consecutive rows (coalesced pixel reads)
-            const int row = item & 127;
-            const int m = m0 + row;
-            float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
-            if (m < args.M) {
-              const int b = m / args.n_patches, i = m - b * args.n_patches;
-              const int py = i / Wp, px = i - py * Wp;
-              const int k = kb * GEMM_BK + chunk * 8;
-              const int c = k / pp, rem = k - c * pp;
-              const int yi = rem / p, xi = rem - yi * p;
-              const float* src = args.img + (static_cast<long long>(b) * chans + c) * plane +
-                                 static_cast<long long>(py * p + yi) * args.img_w + px * p + xi;
-              f0 = __ldg(reinterpret_cast<const float4*>(src));
-              f1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-            }
-            float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-            if (want_lo) {
+          // 16 items per thread in two batches of 8: all 16 loads of a batch are issued before the first
+          // conversion so that their latencies overlap
+#pragma unroll 1
+          for (int batch = 0; batch < 2; ++batch) {
+            float4 f[8][2];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] -= ptx::bf16_round(v[j]);
+            for (int u = 0; u < 8; ++u) {
+              const int item = t + 64 * (batch * 8 + u);
+              const int chunk = item >> 7;        // 0..7: consecutive threads -> consecutive rows (coalesced pixel reads)
+              const int row = item & 127;
+              const int m = m0 + row;
+              f[u][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+              f[u][1] = f[u][0];
+              if (m < args.M) {
+                const int b = m / args.n_patches, i = m - b * args.n_patches;
+                const int py = i / Wp, px = i - py * Wp;
+                const int k = kb * GEMM_BK + chunk * 8;
+                const int c = k / pp, rem = k - c * pp;
+                const int yi = rem / p, xi = rem - yi * p;
+                const float* src = args.img + (static_cast<long long>(b) * chans + c) * plane +
+                                   static_cast<long long>(py * p + yi) * args.img_w + px * p + xi;
+                f[u][0] = __ldg(reinterpret_cast<const float4*>(src));
+                f[u][1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+              }
             }
-            ptx::sts_v4(a_tile + row * 128 + ((chunk ^ (row & 7)) << 4), ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]),
-                        ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int item = t + 64 * (batch * 8 + u);
+              const int chunk = item >> 7;
+              const int row = item & 127;
+              float v[8] = {f[u][0].x, f[u][0].y, f[u][0].z, f[u][0].w, f[u][1].x, f[u][1].y, f[u][1].z, f[u][1].w};
+              if (want_lo) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] -= ptx::bf16_round(v[j]);
+              }
+              ptx::sts_v4(a_tile + row * 128 + ((chunk ^ (row & 7)) << 4), ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]),
+                          ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+            }
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
@@ -267,7 +286,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int ew = warp - GEMM_EPI_WARP0;           // 0..7
     const int half = ew >> 2;                       // which half of the BN columns
     constexpr int COLS_PER_WARP = BN / 2;
-    const uint32_t stg = smem_stg + ew * GEMM_STG_WARP_BYTES;
+    const uint32_t stg_warp = smem_stg + ew * Cfg::STG_WARP_BYTES;
+    const bool stg_single = Cfg::OUT_BF16 && args.split_out;   // both boxes used by one chunk (hi, lo)
+    uint32_t stg_sel = 0;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -327,8 +348,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           continue;
         }
-        // the previous TMA store of this warp must have finished reading the staging box
-        if (lane == 0) ptx::bulk_wait_read0();
+        // the TMA store that last used this staging box must have finished reading it
+        const uint32_t stg = stg_warp + (stg_single ? 0u : stg_sel * Cfg::STG_BOX_BYTES);
+        stg_sel ^= 1u;
+        if (lane == 0) {
+          if (stg_single) ptx::bulk_wait_read0(); else ptx::bulk_wait_read1();
+        }
         __syncwarp();
         if (Cfg::OUT_BF16) {
           // 32 rows x 64 B, SWIZZLE_64B: 16-byte chunk j of row r sits at r*64 + ((j ^ ((r >> 1) & 3)) << 4)
@@ -343,7 +368,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             for (int j = 0; j < 32; ++j) v[j] -= ptx::bf16_round(v[j]);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              ptx::sts_v4(rowaddr + 2048 + ((j ^ sw) << 4), ptx::pack_bf16x2(v[8 * j], v[8 * j + 1]), ptx::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+              ptx::sts_v4(rowaddr + Cfg::STG_BOX_BYTES + ((j ^ sw) << 4), ptx::pack_bf16x2(v[8 * j], v[8 * j + 1]), ptx::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                           ptx::pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), ptx::pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
           }
         } else {
@@ -362,7 +387,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             ptx::tma_reduce_add_2d(&tmap_c, stg, col, row_base);
           } else {
             ptx::tma_store_2d(&tmap_c, stg, col, row_base);
-            if (Cfg::OUT_BF16 && args.split_out) ptx::tma_store_2d(&tmap_c, stg + 2048, col + args.lo_off, row_base);
+            if (Cfg::OUT_BF16 && args.split_out) ptx::tma_store_2d(&tmap_c, stg + Cfg::STG_BOX_BYTES, col + args.lo_off, row_base);
           }
           ptx::bulk_commit();
         }

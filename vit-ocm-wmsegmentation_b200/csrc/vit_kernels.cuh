@@ -38,42 +38,46 @@ __global__ void cls_rows_kernel(const float* __restrict__ cls_token, const float
 // ---------------------------------------------------------------------------------------
 constexpr int LN_MAX_VEC = 8;  // up to D = 8*32*4 = 1024
 
+// NV > 0: D == NV * 128 exactly (no predicates: 3 float4 per lane for ViT-S, 6 for ViT-B); NV == 0: any D % 4 == 0.
+template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ out_bf16, long long ldo, int split, int lo_off,
                  float* __restrict__ out_f32, long long ldf, int M, int D, float eps) {
+  constexpr int CNT = NV > 0 ? NV : LN_MAX_VEC;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * D);
   const int nvec = D >> 2;
-  float4 v[LN_MAX_VEC];
+  float4 v[CNT];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < CNT; ++i) {
     const int idx = lane + 32 * i;
-    if (idx < nvec) {
+    if (NV > 0 || idx < nvec) {
       v[i] = xr[idx];
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
-  const float mean = warp_sum(s) / static_cast<float>(D);
+  const float inv_d = 1.0f / static_cast<float>(D);
+  const float mean = warp_sum(s) * inv_d;
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < CNT; ++i) {
     const int idx = lane + 32 * i;
-    if (idx < nvec) {
+    if (NV > 0 || idx < nvec) {
       const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
       ss += (a * a + b * b) + (c * c + d * d);
     }
   }
-  const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(D) + eps);
+  const float rstd = rsqrtf(warp_sum(ss) * inv_d + eps);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < CNT; ++i) {
     const int idx = lane + 32 * i;
-    if (idx < nvec) {
-      const float4 g = reinterpret_cast<const float4*>(gamma)[idx];
-      const float4 bb = reinterpret_cast<const float4*>(beta)[idx];
+    if (NV > 0 || idx < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(beta) + idx);
       float4 y;
       y.x = (v[i].x - mean) * rstd * g.x + bb.x;
       y.y = (v[i].y - mean) * rstd * g.y + bb.y;

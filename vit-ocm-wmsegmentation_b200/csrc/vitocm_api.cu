@@ -185,12 +185,22 @@ int launch_gemm_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const 
   return fail(VITOCM_ERR_INVALID, "unknown GEMM epilogue %d", epi);
 }
 
-int pick_bn(int N) {
-  if (N % 256 == 0) return 256;
-  if (N % 192 == 0) return 192;
-  if (N % 128 == 0) return 128;
-  if (N % 64 == 0) return 64;
-  return 0;
+// Tile width: among the instantiated BN that divide N, minimise (waves of the persistent grid) x (per-tile
+// cost ~ BN + fixed overhead) -- e.g. N = 384, M = 25120 on 148 SMs: BN = 192 needs 3 waves of 394 tiles,
+// BN = 128 needs 4 waves of 591 smaller tiles and wins.
+int pick_bn(int M, int N, int num_sms) {
+  const int cand[4] = {256, 192, 128, 64};
+  const long long tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+  int best = 0;
+  long long best_cost = 0;
+  for (int bn : cand) {
+    if (N % bn != 0) continue;
+    const long long tiles = tiles_m * (N / bn);
+    const long long waves = (tiles + num_sms - 1) / num_sms;
+    const long long cost = waves * (bn + 48);
+    if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
 }
 
 // A [M][lda] (split: hi at col 0, lo at col K), B [N][ldb] likewise.
@@ -200,7 +210,7 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
   if (M <= 0) return 0;
   ProfScope prof(pcls, st);
   if (K % GEMM_BK != 0) return fail(VITOCM_ERR_INVALID, "GEMM K=%d must be a multiple of %d", K, GEMM_BK);
-  const int bn = pick_bn(N);
+  const int bn = pick_bn(M, N, e->num_sms);
   if (bn == 0) return fail(VITOCM_ERR_INVALID, "GEMM N=%d must be a multiple of 64", N);
   if (bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15) != 0) return fail(VITOCM_ERR_INVALID, "GEMM bias must be 16-byte aligned");
   const long long kext = static_cast<long long>(K) * (split_in ? 2 : 1);
@@ -252,8 +262,12 @@ int run_layernorm(const float* X, const float* g, const float* b, void* out_bf16
   if (D % 4 != 0 || D > LN_MAX_VEC * 128) return fail(VITOCM_ERR_INVALID, "LayerNorm D=%d unsupported", D);
   ProfScope prof(PC_LN, st);
   const int rows_per_block = 8;
-  layernorm_kernel<<<(M + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, st>>>(
-      X, g, b, reinterpret_cast<__nv_bfloat16*>(out_bf16), ldo, split, lo_off, out_f32, ldf, M, D, eps);
+  const dim3 grid((M + rows_per_block - 1) / rows_per_block), block(rows_per_block * 32);
+  __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  if (D == 384) layernorm_kernel<3><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps);
+  else if (D == 768) layernorm_kernel<6><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps);
+  else if (D == 128) layernorm_kernel<1><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps);
+  else layernorm_kernel<0><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps);
   LAUNCH_CHECK();
   return 0;
 }
