@@ -175,6 +175,10 @@ int vitocm_gemm(vitocm_engine* e, const void* A, int64_t lda, const void* B, int
 /* ctx = MHSA(qkv) for B images of n_tokens tokens: qkv bf16 [B*N][ld], ctx bf16 [B*N][ldo]. */
 int vitocm_attention(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo,
                      void* stream);
+/* Diagnostics: vitocm_attention that also records SM-clock stamps of the CTAs of query tiles 0 and 1 of
+ * (image 0, head 0): stamps int64 [2 cta][2 role: softmax warp 0, MMA thread][16 kv blocks][8 events]. */
+int vitocm_attention_timeline(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo,
+                              int64_t* stamps, void* stream);
 /* LayerNorm rows of X [M][D] fp32 with affine (gamma, beta) -> out bf16 [M][ldo] (hi | lo if split). */
 int vitocm_layernorm(vitocm_engine* e, const float* X, const float* gamma, const float* beta, void* out_bf16,
                      int64_t ldo, int split, int lo_off, int M, void* stream);

@@ -21,6 +21,8 @@
 // the other's exponentials.  SPLIT = true is the fp32-parity mode: every operand is a bf16
 // (hi, lo) pair and each product is hi*hi + hi*lo + lo*hi (fp32 accumulate in TMEM).
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace vitocm {
@@ -33,7 +35,15 @@ struct AttnArgs {
   __nv_bfloat16* out;  // ctx [B*N, ldo]
   long long ldo;
   int out_lo_off;    // SPLIT: column offset of the lo half of ctx
+  long long* timeline;  // diagnostics (vitocm_attention_timeline) or nullptr: clock64 stamps of CTAs (0,0,0) and (1,0,0)
 };
+
+// timeline layout: [cta 0..1][role 0 = softmax warp 0, 1 = MMA thread][kv block j < 16][event < 8]
+constexpr int ATT_TL_EVENTS = 8;
+constexpr int ATT_TL_BLOCKS = 16;
+__device__ __forceinline__ void att_stamp(const AttnArgs& args, bool on, int role, int j, int ev) {
+  if (on && j < ATT_TL_BLOCKS) args.timeline[((blockIdx.x * 2 + role) * ATT_TL_BLOCKS + j) * ATT_TL_EVENTS + ev] = clock64();
+}
 
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 128;
@@ -45,6 +55,7 @@ constexpr int ATT_S_COL = 0;      // S: 128 columns (fp32)
 constexpr int ATT_O_COL = 128;    // O: 64 columns (fp32)
 constexpr int ATT_P_COL = 192;    // P: 64 columns of packed bf16x2 (128 keys); split mode: lo part in the next 64
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
+constexpr int ATT_POLY_DEFAULT = 0;            // see run_attention (0: all MUFU, 1: 4/16 polynomial, 2: 7/16)
 
 template <bool SPLIT>
 struct AttnCfg {
@@ -58,7 +69,8 @@ struct AttnCfg {
   static constexpr int REGS_OTHER = SPLIT ? 64 : 48;
 };
 
-template <bool SPLIT>
+// POLY_MASK: bit i set = pair i of every 16 pairs of a 32-key chunk takes the FMA-pipe exp2 polynomial
+template <bool SPLIT, uint32_t POLY_MASK>
 __global__ void __launch_bounds__(ATT_THREADS, SPLIT ? 1 : 2)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs args) {
   using Cfg = AttnCfg<SPLIT>;
@@ -84,6 +96,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
   const int D = args.embed_dim;
   const int n_kv = (N + ATT_BKV - 1) / ATT_BKV;
   const int row_base = b * N;  // first row of this image in the [B*N, ld] activation
+  const bool tl = args.timeline != nullptr && blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0;
 
   if (warp == 4 && lane == 0) {
     ptx::prefetch_tmap(&tmap_qkv);
@@ -111,7 +124,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_OTHER));
    if (warp == 4) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
       for (int part = 0; part < NPART; ++part)
         ptx::tma_load_2d(smem_q + part * ATT_TILE_BYTES, &tmap_qkv, q_full, part * args.lo_col_off + h * ATT_DH,
@@ -136,9 +149,12 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // One elected thread issues (elect.sync lets ptxas emit the tcgen05 instructions without a per-instruction
+    // leader-election loop); descriptors are advanced by compile-time constants in fully unrolled loops.
+    if (ptx::elect_one()) {
       const uint32_t s_tmem = tmem_base + ATT_S_COL;
       const uint32_t o_tmem = tmem_base + ATT_O_COL;
+      const uint64_t q_desc = ptx::make_smem_desc_sw128(smem_q, 1024, 0);
       int item = 0;
       auto kv_len_mma = [&](int j) {  // keys of block j rounded up to the MMA granularity (16)
         int len = N - j * ATT_BKV;
@@ -149,50 +165,51 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
         const int slot = item % ATT_RING;
         ptx::mbar_wait(kv_full + 8 * slot, (item / ATT_RING) & 1, 11);
         ptx::tc_fence_after();
-        const uint32_t k_addr = smem_ring + slot * Cfg::SLOT_BYTES;
+        const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_ring + slot * Cfg::SLOT_BYTES, 1024, 0);
         const uint32_t idesc = ptx::make_idesc(ATT_BQ, kv_len_mma(j), false, false);
-        uint32_t acc = 0;
-        // terms: (Qhi,Khi) [, (Qhi,Klo), (Qlo,Khi)]
-#pragma unroll 1
-        for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
-          const uint32_t qa = smem_q + (t == 2 ? ATT_TILE_BYTES : 0);
-          const uint32_t ka = k_addr + (t == 1 ? ATT_TILE_BYTES : 0);
+        // terms: (Qhi,Khi) [, (Qhi,Klo), (Qlo,Khi)]; K-major operands advance 32 B per 16-wide k step
 #pragma unroll
-          for (int k = 0; k < ATT_DH / 16; ++k) {
-            ptx::umma_bf16_ss(s_tmem, ptx::make_smem_desc_sw128(qa + k * 32, 1024, 0),
-                              ptx::make_smem_desc_sw128(ka + k * 32, 1024, 0), idesc, acc);
-            acc = 1;
-          }
+        for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
+          const uint64_t qa = ptx::desc_advance(q_desc, t == 2 ? ATT_TILE_BYTES : 0);
+          const uint64_t ka = ptx::desc_advance(k_desc, t == 1 ? ATT_TILE_BYTES : 0);
+#pragma unroll
+          for (int k = 0; k < ATT_DH / 16; ++k)
+            ptx::umma_bf16_ss(s_tmem, ptx::desc_advance(qa, k * 32), ptx::desc_advance(ka, k * 32), idesc, (t | k) ? 1u : 0u);
         }
         ptx::umma_commit(kv_empty + 8 * slot);
         ptx::umma_commit(s_full);
+        att_stamp(args, tl, 1, j, 0);   // S_j issued
         ++item;
       };
       auto issue_pv = [&](int j) {
         const int slot = item % ATT_RING;
         ptx::mbar_wait(kv_full + 8 * slot, (item / ATT_RING) & 1, 12);
         ptx::tc_fence_after();
-        const uint32_t v_addr = smem_ring + slot * Cfg::SLOT_BYTES;
-        constexpr uint32_t idesc = ptx::make_idesc(ATT_BQ, ATT_DH, false, /*B = V is MN-major*/ true);
-        const int ksteps = kv_len_mma(j) / 16;
-        // O accumulates across KV blocks in TMEM.  Loops are kept rolled: this warp runs on a small
-        // register budget.
+        // O accumulates across KV blocks in TMEM.
         // A = P in TMEM: 16 keys = 8 packed columns per step
         // B = V: MN-major [keys x 64]; 16 keys = two 8-row groups of 1024 B
-        uint32_t acc = j > 0 ? 1u : 0u;
+        const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_ring + slot * Cfg::SLOT_BYTES, 1024, 1024);
+        constexpr uint32_t idesc = ptx::make_idesc(ATT_BQ, ATT_DH, false, /*B = V is MN-major*/ true);
+        const int ksteps = kv_len_mma(j) / 16;
+        const uint32_t acc0 = j > 0 ? 1u : 0u;
         // terms: (Phi,Vhi) [, (Phi,Vlo), (Plo,Vhi)]
-#pragma unroll 1
+#pragma unroll
         for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
           const uint32_t pa = tmem_base + ATT_P_COL + (t == 2 ? 64 : 0);
-          const uint32_t va = v_addr + (t == 1 ? ATT_TILE_BYTES : 0);
+          const uint64_t va = ptx::desc_advance(v_desc, t == 1 ? ATT_TILE_BYTES : 0);
+          if (ksteps == ATT_BKV / 16) {
+#pragma unroll
+            for (int k = 0; k < ATT_BKV / 16; ++k)
+              ptx::umma_bf16_ts(o_tmem, pa + k * 8, ptx::desc_advance(va, k * 2048), idesc, (t | k) ? 1u : acc0);
+          } else {
 #pragma unroll 1
-          for (int k = 0; k < ksteps; ++k) {
-            ptx::umma_bf16_ts(o_tmem, pa + k * 8, ptx::make_smem_desc_sw128(va + k * 2048, 1024, 1024), idesc, acc);
-            acc = 1;
+            for (int k = 0; k < ksteps; ++k)
+              ptx::umma_bf16_ts(o_tmem, pa + k * 8, ptx::desc_advance(va, k * 2048), idesc, (t | k) ? 1u : acc0);
           }
         }
         ptx::umma_commit(kv_empty + 8 * slot);
         ptx::umma_commit(o_full);
+        att_stamp(args, tl, 1, j, 1);   // PV_j issued
         ++item;
       };
       ptx::mbar_wait(q_full, 0, 13);
@@ -204,7 +221,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
           ptx::tc_fence_after();
           issue_s(j + 1);
         }
-        ptx::mbar_wait(p_full, j & 1, 15);     // P_j in smem, O rescaled if needed
+        ptx::mbar_wait(p_full, j & 1, 15);     // P_j in TMEM, O rescaled if needed
         ptx::tc_fence_after();
         issue_pv(j);
       }
@@ -225,8 +242,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
       int kv_len = N - j * ATT_BKV;
       kv_len = kv_len > ATT_BKV ? ATT_BKV : kv_len;
       const int nchunks = (((kv_len + 15) & ~15) + 31) >> 5;   // 32-column chunks the MMA produced
+      att_stamp(args, tl && warp == 0, 0, j, 0);   // waiting for S_j
       ptx::mbar_wait(s_full, j & 1, 21);
       ptx::tc_fence_after();
+      att_stamp(args, tl && warp == 0, 0, j, 1);   // S_j complete
       // ---- S_j -> registers (one pass), then hand the TMEM columns back to the MMA warp
       uint32_t s[4][32];
 #pragma unroll
@@ -238,6 +257,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(s_empty);
+      att_stamp(args, tl && warp == 0, 0, j, 2);   // S_j in registers
       // ---- ragged last block only: columns beyond the sequence (and chunks the MMA never wrote) -> -inf,
       //      so the common path below carries no masks (exp2(-inf) = 0)
       if (kv_len < ATT_BKV) {
@@ -268,9 +288,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
       }
       const uint64_t nm2 = ptx::dup_f32x2(-m_used * sl2);
       // ---- previous PV done: P buffer free, O valid -> rescale it if this warp raised a maximum
+      att_stamp(args, tl && warp == 0, 0, j, 3);   // row max done
       if (j > 0) {
         ptx::mbar_wait(o_full, (j - 1) & 1, 20);
         ptx::tc_fence_after();
+        att_stamp(args, tl && warp == 0, 0, j, 4); // PV_{j-1} complete
         if (__any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll
           for (int c = 0; c < ATT_DH; c += 32) {
@@ -284,36 +306,49 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
         }
       }
       // ---- p = exp2(s*sl2 - m*sl2) -> bf16 pairs -> TMEM columns P_COL + key/2 of this thread's lane
-      // (the A operand of the PV MMA)
+      // (the A operand of the PV MMA).  In bf16 mode 7 of every 16 pairs take the FMA-pipe polynomial instead
+      // of MUFU.EX2 so that the two pipes finish together (full blocks only: the ragged block carries -inf).
       uint64_t sum2[2] = {0ull, 0ull};
+      auto exp_chunks = [&](auto poly_tag) {
+        constexpr bool POLY = decltype(poly_tag)::value;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < nchunks) {
-          uint32_t ph[16], pl[16];
+        for (int c = 0; c < 4; ++c) {
+          if (c < nchunks) {
+            uint32_t ph[16], pl[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const uint64_t a2 = ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sl2_2, nm2);
-            float a0, a1;
-            ptx::unpack_f32x2(a2, a0, a1);
-            const float e0 = ptx::ex2_approx(a0), e1 = ptx::ex2_approx(a1);
-            sum2[i & 1] = ptx::add_f32x2(sum2[i & 1], ptx::pack_f32x2(e0, e1));
-            ph[i] = ptx::pack_bf16x2(e0, e1);
-            if (SPLIT) pl[i] = ptx::pack_bf16x2(e0 - ptx::bf16_round(e0), e1 - ptx::bf16_round(e1));
+            for (int i = 0; i < 16; ++i) {
+              const uint64_t a2 = ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sl2_2, nm2);
+              float e0, e1;
+              if (POLY && ((POLY_MASK >> i) & 1u)) {
+                ptx::ex2_poly_x2(a2, e0, e1);
+              } else {
+                float a0, a1;
+                ptx::unpack_f32x2(a2, a0, a1);
+                e0 = ptx::ex2_approx(a0);
+                e1 = ptx::ex2_approx(a1);
+              }
+              sum2[i & 1] = ptx::add_f32x2(sum2[i & 1], ptx::pack_f32x2(e0, e1));
+              ph[i] = ptx::pack_bf16x2(e0, e1);
+              if (SPLIT) pl[i] = ptx::pack_bf16x2(e0 - ptx::bf16_round(e0), e1 - ptx::bf16_round(e1));
+            }
+            ptx::tmem_st_32x32b_x16(lane_addr + ATT_P_COL + c * 16, ph);
+            if (SPLIT) ptx::tmem_st_32x32b_x16(lane_addr + ATT_P_COL + 64 + c * 16, pl);
           }
-          ptx::tmem_st_32x32b_x16(lane_addr + ATT_P_COL + c * 16, ph);
-          if (SPLIT) ptx::tmem_st_32x32b_x16(lane_addr + ATT_P_COL + 64 + c * 16, pl);
         }
-      }
+      };
+      if (!SPLIT && POLY_MASK != 0 && kv_len == ATT_BKV) exp_chunks(std::true_type{}); else exp_chunks(std::false_type{});
       {
         float a0, a1, b0, b1;
         ptx::unpack_f32x2(sum2[0], a0, a1);
         ptx::unpack_f32x2(sum2[1], b0, b1);
         l_run += (a0 + a1) + (b0 + b1);
       }
+      att_stamp(args, tl && warp == 0, 0, j, 5);   // exponentials issued
       ptx::tmem_st_wait();             // P (and a rescaled O) are in TMEM
       ptx::tc_fence_before();          // ... and ordered before the MMA that reads / accumulates on them
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_full);
+      att_stamp(args, tl && warp == 0, 0, j, 6);   // P_j handed to the MMA warp
     }
     // ---- epilogue: ctx = O / l
     ptx::mbar_wait(o_full, (n_kv - 1) & 1, 22);

@@ -185,8 +185,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // One elected thread issues (elect.sync lets ptxas emit the tcgen05 instructions without a per-instruction
+    // leader-election loop); descriptors are advanced by compile-time constants in fully unrolled loops.
+    if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc(GEMM_BM, BN, false, false);
+      const uint64_t a_desc0 = ptx::make_smem_desc_sw128(smem_a, 1024, 0);
+      const uint64_t b_desc0 = ptx::make_smem_desc_sw128(smem_b, 1024, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -198,14 +202,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int it = 0; it < k_iters; ++it) {
           ptx::mbar_wait(full_bar + 8 * stage, phase, 3);
           ptx::tc_fence_after();
-          const uint32_t a_addr = smem_a + stage * Cfg::A_BYTES;
-          const uint32_t b_addr = smem_b + stage * Cfg::B_BYTES;
+          const uint64_t adesc = ptx::desc_advance(a_desc0, stage * Cfg::A_BYTES);
+          const uint64_t bdesc = ptx::desc_advance(b_desc0, stage * Cfg::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr + k * 32, 1024, 0);
-            const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * 32, 1024, 0);
-            ptx::umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            ptx::umma_bf16_ss(d_tmem, ptx::desc_advance(adesc, k * 32), ptx::desc_advance(bdesc, k * 32), idesc,
+                              (it > 0 || k > 0) ? 1u : 0u);
           ptx::umma_commit(empty_bar + 8 * stage);  // smem slot reusable once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }

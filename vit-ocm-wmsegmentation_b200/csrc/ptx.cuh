@@ -126,7 +126,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate; one thread issues.
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate; issued by ONE thread (call inside an
+// `if (lane == 0)` region).  Keep the per-instruction scalar work minimal (desc_advance with constants, unrolled):
+// that thread's dependent-issue latency is what paces short MMA sequences.
 __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -137,7 +139,8 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t adesc, ui
       : "memory");
 }
 // A operand from tensor memory (M x K bf16, lane = row, two K-elements per 32-bit column), B from shared memory
-__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -145,20 +148,9 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// fp32 (tf32) inputs from shared memory
-__device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // mbarrier arrives (count 1) once all previously issued tcgen05.mma of this thread completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 // TMEM -> registers: each thread of the warp reads 32 consecutive fp32 columns of its own lane
@@ -238,6 +230,9 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   d |= static_cast<uint64_t>(2) << 61;   // SWIZZLE_128B
   return d;
 }
+// Same descriptor with its start address advanced by `bytes` (multiple of 16; the 14-bit address field cannot carry
+// out for shared-window addresses below 256 KB)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.  fmt: 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major, bool b_mn_major, uint32_t fmt = 1) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
@@ -255,6 +250,12 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// 2^x for two values on the FMA/ALU pipes instead of MUFU (the SFU retires only 16 ex2 per clock per SM, which
+// paces the softmax at head_dim 64): x = n + f, n = round(x) via the 1.5 * 2^23 magic add, 2^f by a degree-3
+// minimax polynomial on [-0.5, 0.5] (max relative error 7.5e-5 -- below the bf16 rounding of P), and n added
+// into the exponent field (the magic constant's high bits shift out with << 23).  x is clamped at -120.
+__device__ __forceinline__ void ex2_poly_x2(uint64_t x2, float& e0, float& e1);
 
 // ------------------------------------------------------------------ packed f32x2 arithmetic (FFMA2 / FMUL2 / FADD2)
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
@@ -280,6 +281,23 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
+}
+
+__device__ __forceinline__ void ex2_poly_x2(uint64_t x2, float& e0, float& e1) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  const uint64_t xc = pack_f32x2(fmaxf(x0, -120.f), fmaxf(x1, -120.f));
+  const uint64_t t = add_f32x2(xc, dup_f32x2(12582912.f));
+  const uint64_t n = add_f32x2(t, dup_f32x2(-12582912.f));
+  const uint64_t f = fma_f32x2(n, dup_f32x2(-1.f), xc);
+  uint64_t p = fma_f32x2(f, dup_f32x2(0.05517132207751274f), dup_f32x2(0.24261054396629333f));
+  p = fma_f32x2(p, f, dup_f32x2(0.6932609677314758f));
+  p = fma_f32x2(p, f, dup_f32x2(0.9999281167984009f));
+  float t0, t1, p0, p1;
+  unpack_f32x2(t, t0, t1);
+  unpack_f32x2(p, p0, p1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
 }
 
 }  // namespace ptx

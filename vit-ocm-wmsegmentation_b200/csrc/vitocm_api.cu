@@ -232,7 +232,8 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
 }
 
 // ---------------------------------------------------------------------------------- attention launch
-int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, int N, void* ctx, long long ldo, cudaStream_t st) {
+int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, int N, void* ctx, long long ldo, cudaStream_t st,
+                  long long* timeline = nullptr) {
   const int D = e->cfg.embed_dim, H = e->cfg.num_heads;
   const long long M = static_cast<long long>(B) * N;
   ProfScope prof(PC_ATTN, st);
@@ -241,17 +242,20 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
   AttnArgs a{};
   a.n_tokens = N; a.embed_dim = D; a.lo_col_off = 3 * D;
   a.scale_log2 = e->cfg.qk_scale * 1.44269504088896340736f;
-  a.out = reinterpret_cast<__nv_bfloat16*>(ctx); a.ldo = ldo; a.out_lo_off = D;
+  a.out = reinterpret_cast<__nv_bfloat16*>(ctx); a.ldo = ldo; a.out_lo_off = D; a.timeline = timeline;
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, H, B);
-  if (e->split) {
-    static bool attr = false;
-    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<true>::SMEM_BYTES)); attr = true; }
-    attn_fwd_tcgen05_kernel<true><<<grid, ATT_THREADS, AttnCfg<true>::SMEM_BYTES, st>>>(tq, a);
-  } else {
-    static bool attr = false;
-    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<false>::SMEM_BYTES)); attr = true; }
-    attn_fwd_tcgen05_kernel<false><<<grid, ATT_THREADS, AttnCfg<false>::SMEM_BYTES, st>>>(tq, a);
-  }
+  auto launch = [&](auto kern, int smem_bytes, bool& attr) -> int {
+    if (!attr) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); attr = true; }
+    kern<<<grid, ATT_THREADS, smem_bytes, st>>>(tq, a);
+    return 0;
+  };
+  // fraction of the exponentials moved from MUFU to the FMA pipe (bf16 mode): tuning knob, default from measurement
+  static const int poly = [] { const char* v = getenv("VITOCM_ATTN_POLY"); return v ? atoi(v) : ATT_POLY_DEFAULT; }();
+  static bool attr[4] = {false, false, false, false};
+  if (e->split) TRY(launch(attn_fwd_tcgen05_kernel<true, 0u>, AttnCfg<true>::SMEM_BYTES, attr[3]));
+  else if (poly == 1) TRY(launch(attn_fwd_tcgen05_kernel<false, 0x1248u>, AttnCfg<false>::SMEM_BYTES, attr[1]));   // 4 of 16 pairs
+  else if (poly == 2) TRY(launch(attn_fwd_tcgen05_kernel<false, 0x5529u>, AttnCfg<false>::SMEM_BYTES, attr[2]));   // 7 of 16 pairs
+  else TRY(launch(attn_fwd_tcgen05_kernel<false, 0u>, AttnCfg<false>::SMEM_BYTES, attr[0]));
   LAUNCH_CHECK();
   return 0;
 }
@@ -719,6 +723,12 @@ int vitocm_gemm(vitocm_engine* e, const void* A, int64_t lda, const void* B, int
 int vitocm_attention(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo, void* stream) {
   if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
   return run_attention(e, qkv, ld, B, n_tokens, ctx, ldo, static_cast<cudaStream_t>(stream));
+}
+
+int vitocm_attention_timeline(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo,
+                              int64_t* stamps, void* stream) {
+  if (e == nullptr || stamps == nullptr) return fail(VITOCM_ERR_INVALID, "null argument");
+  return run_attention(e, qkv, ld, B, n_tokens, ctx, ldo, static_cast<cudaStream_t>(stream), reinterpret_cast<long long*>(stamps));
 }
 
 int vitocm_layernorm(vitocm_engine* e, const float* X, const float* gamma, const float* beta, void* out_bf16, int64_t ldo,
