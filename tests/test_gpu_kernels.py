@@ -69,6 +69,27 @@ def test_gemm_residual_and_f32_epilogues(engine):
     assert (y - (ref - resid)).abs().max().item() <= 2e-4 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 384, 384), (3000, 768, 256), (25120, 384, 384), (130, 128, 64)])
+def test_gemm_weight_panel_resident_epilogues(engine, M, N, K):
+    """K <= 384 with single-bf16 operands takes the weight-panel-resident kernel (n-major contiguous tile ranges,
+    panel reloads when a CTA crosses into the next column of tiles)."""
+    A = _rand((M, K), 30).to(torch.bfloat16)
+    B = _rand((N, K), 31, 0.05).to(torch.bfloat16)
+    bias = _rand((N,), 32, 0.1)
+    resid = _rand((M, N), 33)
+    prod = A.float() @ B.float().T + bias
+    x = resid.clone()
+    gemm(engine, A, B, M, N, K, 0, 2, bias, x, N)
+    assert (x - (resid + prod)).abs().max().item() <= 2e-4 * prod.abs().max().item() + 1e-5
+    y = torch.full((M, N), float("nan"), device="cuda")
+    gemm(engine, A, B, M, N, K, 0, 3, bias, y, N)
+    assert (y - prod).abs().max().item() <= 2e-4 * prod.abs().max().item() + 1e-5
+    z = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    gemm(engine, A, B, M, N, K, 0, 1, bias, z, N)
+    ref = torch.nn.functional.gelu(prod)
+    assert (z.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
+
+
 def test_gemm_split_precision_is_fp32_grade(engine):
     M, N, K = 785, 384, 384
     A32, B32 = _rand((M, K), 11), _rand((N, K), 12, 0.05)

@@ -18,7 +18,7 @@
 //
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator
 // (+ A producer with warp 3 in A_PATCH mode), warps 4..11 = epilogue (lane quadrant = warp % 4,
-// column half = (warp - 4) / 4).
+// column group = (warp - 4) / 4).
 #pragma once
 #include "ptx.cuh"
 
@@ -40,6 +40,9 @@ struct GemmArgs {
   const float* bias;  // [N] or nullptr
   int split_out;      // bf16 outputs only: also write lo = bf16(v - hi) at column offset lo_off
   int lo_off;
+  int debug;          // diagnostics only (VITOCM_GEMM_DEBUG): 1 = epilogue drains TMEM but skips math + stores, 2 = epilogue
+                      // signals only (no TMEM load either)
+  int stages;         // B_RES only: number of A stages that fit next to the resident B panel (host-computed)
   // A_PATCH / EPI_PATCH_F32 only
   const float* img;         // [B][C][H][W] fp32 pixels
   int img_h, img_w, patch;  // pixels; patch size p (multiple of 8)
@@ -52,28 +55,46 @@ struct GemmArgs {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARP0 = 4;
-constexpr int GEMM_NUM_EPI_WARPS = 8;
+// epilogue warps: 8 (two column halves per TMEM lane quadrant), or 12 with BN = 192 (three 64-column groups): the
+// GELU epilogue is issue / latency bound, a third warp per scheduler hides its MUFU + FMA chains
+__host__ __device__ constexpr int gemm_epi_warps(int BN, int EPI) { return (EPI == 1 && BN == 192) ? 12 : 8; }
+__host__ __device__ constexpr int gemm_threads(int BN, int EPI) { return (4 + gemm_epi_warps(BN, EPI)) * 32; }
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 
-template <int BN, int EPI>
+constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_RES_MAX_KBLOCKS = 6;     // B_RES: K <= 384
+
+// B_RES ("weight panel resident"): for K <= 384 the whole [BN x K] weight panel stays in shared memory while the
+// CTA walks down M (tiles are assigned n-major in contiguous ranges), so only A streams from L2.  The plain kernel
+// re-fetches A and B for every tile: (128 + BN) * 128 B per 2*BN tensor clocks = 96-128 B/clk/SM, i.e. 14-19 KB/clk
+// chip-wide against a measured L2->SM ceiling of ~9 KB/clk -- the GEMMs of this model were L2-bandwidth bound at
+// 45-55 % of tensor peak.  With the panel resident the demand drops to 128*128 B per 2*BN clocks (43 B/clk at BN 192).
+template <int BN, int EPI, bool B_RES = false>
 struct GemmCfg {
   static constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16);
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;       // 16 KB
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // per-warp epilogue staging, double buffered: 2 x (32 x 32 fp32 box) or 2 x (32 x 32 bf16 box); with a split
-  // bf16 output the two bf16 boxes hold hi and lo instead (single buffered -- the parity mode is not the fast path)
+  static constexpr int STAGE_BYTES = A_BYTES + (B_RES ? 0 : B_BYTES);
+  // per-warp epilogue staging: 2 x (32 x 32 fp32 box) or 2 x (32 x 32 bf16 box), double buffered; with a split
+  // bf16 output the two bf16 boxes hold hi and lo instead (single buffered -- the parity mode is not the fast
+  // path).  B_RES keeps one box per warp (single buffered) to leave room for the panel.
   static constexpr int STG_BOX_BYTES = OUT_BF16 ? 2048 : 4096;
-  static constexpr int STG_WARP_BYTES = 2 * STG_BOX_BYTES;
-  static constexpr int STG_BYTES = GEMM_NUM_EPI_WARPS * STG_WARP_BYTES;
+  static constexpr int STG_WARP_BYTES = (B_RES ? 1 : 2) * STG_BOX_BYTES;
+  static constexpr int EPI_WARPS = gemm_epi_warps(BN, EPI);
+  static constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
   static constexpr int FIXED_BYTES = STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int STAGES_FIT = (GEMM_SMEM_LIMIT - FIXED_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;   // plain kernel (compile time)
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
-  static_assert(STAGES >= 3, "not enough shared memory for a 3-stage pipeline");
+  static_assert(B_RES || STAGES >= 3, "not enough shared memory for a 3-stage pipeline");
+  // B_RES: stages next to a kblocks-deep panel
+  static constexpr int res_stages(int kblocks) {
+    const int fit = (GEMM_SMEM_LIMIT - FIXED_BYTES - kblocks * B_BYTES) / A_BYTES;
+    return fit > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : fit;
+  }
+  static constexpr int res_smem_bytes(int kblocks) { return res_stages(kblocks) * A_BYTES + kblocks * B_BYTES + FIXED_BYTES; }
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -81,51 +102,53 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-// Exact-erf GELU for two values at once on the packed-f32x2 pipe (FFMA2/FMUL2), Abramowitz-Stegun
-// 7.1.26: erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + p z), z >= 0,
-// |error| <= 1.5e-7 (fp32 grade).  With z = |x| / sqrt(2) and q = x * erfc(z) / 2:
-//     gelu(x) = max(x, 0) - |q|
-__device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
+// erf-GELU for two values at once on the packed-f32x2 pipe (bf16 mode; the output is rounded to bf16, 2^-9 relative):
+//     gelu(x) = x * Phi(x),   Phi(x) ~= sigmoid(x * (a + b x^2 + c x^4))
+// with (a, b, c) fitted to the exact Phi (erf form) over [-7, 7]: max |error| of gelu = 2.5e-5 (the familiar
+// "tanh GELU" is the two-coefficient member of this family, 2.7e-4).  x^2 is clamped at 100 so the quintic stays
+// monotone; sigmoid = rcp(1 + ex2(.)): 6 packed FMA-pipe instructions + 4 MUFU per pair, against 37 instructions per
+// element for erff() -- the fc1 epilogue is issue bound, not tensor bound (K = 384 gives the tensor core only
+// 0.09 clk of work per output element).  The fp32-parity mode keeps erff().
+__device__ __forceinline__ void gelu_sigmoid_x2(float& x0, float& x1) {
   const uint64_t x2 = ptx::pack_f32x2(x0, x1);
-  const uint64_t ax2 = x2 & 0x7fffffff7fffffffULL;
-  const uint64_t den = ptx::fma_f32x2(ax2, ptx::dup_f32x2(0.3275911f * 0.70710678118654752440f), ptx::dup_f32x2(1.0f));
+  const uint64_t sq = ptx::mul_f32x2(x2, x2);
+  float u0, u1;
+  ptx::unpack_f32x2(sq, u0, u1);
+  const uint64_t u = ptx::pack_f32x2(fminf(u0, 100.f), fminf(u1, 100.f));
+  // coefficients pre-multiplied by -log2(e):  ex2(x * w) = exp(-x (a + b u + c u^2))
+  uint64_t w = ptx::fma_f32x2(u, ptx::dup_f32x2(0.0010142630596f), ptx::dup_f32x2(-0.1067757240f));
+  w = ptx::fma_f32x2(w, u, ptx::dup_f32x2(-2.3011213394f));
+  const uint64_t arg = ptx::mul_f32x2(x2, w);
+  float a0, a1;
+  ptx::unpack_f32x2(arg, a0, a1);
+  const uint64_t den = ptx::add_f32x2(ptx::pack_f32x2(ptx::ex2_approx(a0), ptx::ex2_approx(a1)), ptx::dup_f32x2(1.0f));
   float d0, d1;
   ptx::unpack_f32x2(den, d0, d1);
-  const uint64_t t = ptx::pack_f32x2(ptx::rcp_approx(d0), ptx::rcp_approx(d1));
-  const uint64_t arg = ptx::mul_f32x2(ptx::mul_f32x2(x2, x2), ptx::dup_f32x2(-0.5f * 1.44269504088896340736f));
-  float g0, g1;
-  ptx::unpack_f32x2(arg, g0, g1);
-  const uint64_t e = ptx::pack_f32x2(ptx::ex2_approx(g0), ptx::ex2_approx(g1));
-  // coefficients pre-multiplied by 1/2
-  uint64_t h = ptx::fma_f32x2(t, ptx::dup_f32x2(0.5f * 1.061405429f), ptx::dup_f32x2(0.5f * -1.453152027f));
-  h = ptx::fma_f32x2(h, t, ptx::dup_f32x2(0.5f * 1.421413741f));
-  h = ptx::fma_f32x2(h, t, ptx::dup_f32x2(0.5f * -0.284496736f));
-  h = ptx::fma_f32x2(h, t, ptx::dup_f32x2(0.5f * 0.254829592f));
-  const uint64_t q = ptx::mul_f32x2(ptx::mul_f32x2(ptx::mul_f32x2(h, t), e), x2);
-  float q0, q1;
-  ptx::unpack_f32x2(q, q0, q1);
-  x0 = fmaxf(x0, 0.f) - fabsf(q0);
-  x1 = fmaxf(x1, 0.f) - fabsf(q1);
+  const uint64_t r = ptx::mul_f32x2(x2, ptx::pack_f32x2(ptx::rcp_approx(d0), ptx::rcp_approx(d1)));
+  ptx::unpack_f32x2(r, x0, x1);
 }
 
-template <int BN, int EPI, bool A_PATCH>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int EPI, bool A_PATCH, bool B_RES = false>
+__global__ void __launch_bounds__(gemm_threads(BN, EPI), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, const GemmArgs args) {
-  using Cfg = GemmCfg<BN, EPI>;
-  constexpr int STAGES = Cfg::STAGES;
+  using Cfg = GemmCfg<BN, EPI, B_RES>;
+  static_assert(!(A_PATCH && B_RES), "patch embedding uses the plain pipeline");
+  const int STAGES = B_RES ? args.stages : Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment; all later accesses use 32-bit shared-window addresses
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
-  const uint32_t smem_b = smem_base + STAGES * Cfg::A_BYTES;
-  const uint32_t smem_stg = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t smem_b = smem_base + STAGES * Cfg::A_BYTES;     // plain: [STAGES] B tiles; B_RES: the [kblocks] panel
+  const uint32_t smem_stg = smem_b + (B_RES ? args.kblocks : STAGES) * Cfg::B_BYTES;
   const uint32_t bars = smem_stg + Cfg::STG_BYTES;
-  const uint32_t full_bar = bars;                         // [STAGES]  producers -> MMA
-  const uint32_t empty_bar = bars + 8 * STAGES;           // [STAGES]  MMA -> producers
-  const uint32_t tfull_bar = bars + 16 * STAGES;          // [2]       MMA -> epilogue
-  const uint32_t tempty_bar = bars + 16 * STAGES + 16;    // [2]       epilogue -> MMA
-  const uint32_t tmem_ptr_smem = bars + 16 * STAGES + 32;
+  const uint32_t full_bar = bars;                                   // [STAGES]  producers -> MMA
+  const uint32_t empty_bar = bars + 8 * GEMM_MAX_STAGES;            // [STAGES]  MMA -> producers
+  const uint32_t tfull_bar = bars + 16 * GEMM_MAX_STAGES;           // [2]       MMA -> epilogue
+  const uint32_t tempty_bar = bars + 16 * GEMM_MAX_STAGES + 16;     // [2]       epilogue -> MMA
+  const uint32_t bfull_bar = bars + 16 * GEMM_MAX_STAGES + 32;      // B_RES: panel loaded
+  const uint32_t bempty_bar = bars + 16 * GEMM_MAX_STAGES + 40;     // B_RES: panel no longer read
+  const uint32_t tmem_ptr_smem = bars + 16 * GEMM_MAX_STAGES + 48;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -133,6 +156,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int tiles_n = args.N / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int k_iters = args.kblocks * args.nterms;
+  // tile schedule.  plain: m-major, strided over the persistent grid.  B_RES: n-major, one contiguous range per CTA
+  // (so that a CTA changes weight panel at most a couple of times).
+  const int tile_begin = B_RES ? static_cast<int>(static_cast<long long>(blockIdx.x) * num_tiles / gridDim.x) : static_cast<int>(blockIdx.x);
+  const int tile_end = B_RES ? static_cast<int>(static_cast<long long>(blockIdx.x + 1) * num_tiles / gridDim.x) : num_tiles;
+  const int tile_step = B_RES ? 1 : static_cast<int>(gridDim.x);
+  auto tile_m = [&](int t) { return B_RES ? t % tiles_m : t / tiles_n; };
+  auto tile_n = [&](int t) { return B_RES ? t / tiles_m : t % tiles_n; };
 
   if (warp == 0 && lane == 0) {
     if (!A_PATCH) ptx::prefetch_tmap(&tmap_a);
@@ -146,8 +176,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar + 8 * s, 1);
-      ptx::mbar_init(tempty_bar + 8 * s, GEMM_NUM_EPI_WARPS);  // one arrive per epilogue warp
+      ptx::mbar_init(tempty_bar + 8 * s, Cfg::EPI_WARPS);  // one arrive per epilogue warp
     }
+    ptx::mbar_init(bfull_bar, 1);
+    ptx::mbar_init(bempty_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -164,9 +196,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * GEMM_BM;
-        const int n0 = (tile % tiles_n) * BN;
+      int cur_n = -1, panels = 0;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+        const int m0 = tile_m(tile) * GEMM_BM;
+        const int n0 = tile_n(tile) * BN;
+        if (B_RES && tile_n(tile) != cur_n) {
+          // (re)load the weight panel: kblocks boxes [BN x 64] -> smem_b, once the MMAs on the old panel retired
+          if (panels > 0) ptx::mbar_wait(bempty_bar, (panels - 1) & 1, 6);
+          ptx::mbar_arrive_expect_tx(bfull_bar, args.kblocks * Cfg::B_BYTES);
+          for (int kb = 0; kb < args.kblocks; ++kb)
+            ptx::tma_load_2d(smem_b + kb * Cfg::B_BYTES, &tmap_b, bfull_bar, kb * GEMM_BK, n0);
+          cur_n = tile_n(tile);
+          ++panels;
+        }
         for (int it = 0; it < k_iters; ++it) {
           // operand order: term-major for TMA-fed A; k-block-major in patch mode so that the three terms of
           // one k-block re-read the same pixels out of L1
@@ -178,7 +220,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const int a_off = (term == 2 ? args.lo_k : 0) + kb * GEMM_BK;
           const int b_off = (term == 1 ? args.lo_k : 0) + kb * GEMM_BK;
           if (!A_PATCH) ptx::tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, full_bar + 8 * stage, a_off, m0);
-          ptx::tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, full_bar + 8 * stage, b_off, n0);
+          if (!B_RES) ptx::tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, full_bar + 8 * stage, b_off, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -195,7 +237,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int cur_n = -1, panels = 0;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+        if (B_RES && tile_n(tile) != cur_n) {
+          ptx::mbar_wait(bfull_bar, panels & 1, 7);
+          cur_n = tile_n(tile);
+          ++panels;
+        }
         ptx::mbar_wait(tempty_bar + 8 * as, aphase ^ 1, 2);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
@@ -203,7 +251,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           ptx::mbar_wait(full_bar + 8 * stage, phase, 3);
           ptx::tc_fence_after();
           const uint64_t adesc = ptx::desc_advance(a_desc0, stage * Cfg::A_BYTES);
-          const uint64_t bdesc = ptx::desc_advance(b_desc0, stage * Cfg::B_BYTES);
+          const uint64_t bdesc = ptx::desc_advance(b_desc0, (B_RES ? it : stage) * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
             ptx::umma_bf16_ss(d_tmem, ptx::desc_advance(adesc, k * 32), ptx::desc_advance(bdesc, k * 32), idesc,
@@ -212,6 +260,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit(tfull_bar + 8 * as);  // accumulator complete
+        if (B_RES && (tile + 1 >= tile_end || tile_n(tile + 1) != cur_n)) ptx::umma_commit(bempty_bar);  // panel free
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -228,8 +277,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int chans = (args.kblocks * GEMM_BK) / pp;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * GEMM_BM;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+        const int m0 = tile_m(tile) * GEMM_BM;
         for (int it = 0; it < k_iters; ++it) {
           const int term = it % args.nterms;
           const int kb = it / args.nterms;
@@ -286,23 +335,39 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ===================== epilogue =====================
     const int q = warp & 3;                         // TMEM lane quadrant this warp may access
     const int ew = warp - GEMM_EPI_WARP0;           // 0..7
-    const int half = ew >> 2;                       // which half of the BN columns
-    constexpr int COLS_PER_WARP = BN / 2;
+    const int half = ew >> 2;                       // which column group of the BN columns
+    constexpr int COLS_PER_WARP = BN / (Cfg::EPI_WARPS / 4);
     const uint32_t stg_warp = smem_stg + ew * Cfg::STG_WARP_BYTES;
-    const bool stg_single = Cfg::OUT_BF16 && args.split_out;   // both boxes used by one chunk (hi, lo)
+    const bool stg_single = B_RES || (Cfg::OUT_BF16 && args.split_out);   // one box, or both boxes used by one chunk (hi, lo)
     uint32_t stg_sel = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * GEMM_BM;
-      const int n0 = (tile % tiles_n) * BN;
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      const int m0 = tile_m(tile) * GEMM_BM;
+      const int n0 = tile_n(tile) * BN;
       const int row_base = m0 + q * 32;
       const int col_base = n0 + half * COLS_PER_WARP;
       ptx::mbar_wait(tfull_bar + 8 * as, aphase, 4);
       ptx::tc_fence_after();
+      if (args.debug == 3) {   // diagnostics: drain the warp's slice with back-to-back loads and one wait
+        constexpr int NCH = COLS_PER_WARP / 32;
+        uint32_t rr[NCH][32];
+#pragma unroll
+        for (int g = 0; g < NCH; ++g)
+          ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN + half * COLS_PER_WARP + g * 32), rr[g]);
+#pragma unroll
+        for (int g = 0; g < NCH; ++g) ptx::tmem_ld_wait(rr[g]);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int g = 0; g < NCH; ++g)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc ^= rr[g][j];
+        if (acc == 0x7fc12345u) args.out_f32[0] = 1.f;
+      }
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP; c += 32) {
         const int col = col_base + c;
+        if (args.debug >= 2) continue;
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN + half * COLS_PER_WARP + c), r);
         float bv[32];
@@ -317,13 +382,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int j = 0; j < 32; ++j) bv[j] = 0.f;
         }
         ptx::tmem_ld_wait(r);
+        if (args.debug == 1) {
+          uint32_t acc = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc ^= r[j];
+          if (acc == 0x7fc12345u) args.out_f32[0] = 1.f;   // keep the load alive
+          continue;
+        }
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bv[j];
         if (EPI == EPI_BIAS_GELU_BF16) {
           if (args.nterms == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) gelu_erf_x2(v[j], v[j + 1]);
+            for (int j = 0; j < 32; j += 2) gelu_sigmoid_x2(v[j], v[j + 1]);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);

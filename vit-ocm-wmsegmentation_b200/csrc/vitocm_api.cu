@@ -161,21 +161,50 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
                      cudaStream_t st) {
   using Cfg = GemmCfg<BN, EPI>;
   static bool attr_set = false;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, A_PATCH>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, A_PATCH, false>;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * (a.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tc, a);
+  kern<<<grid, gemm_threads(BN, EPI), Cfg::SMEM_BYTES, st>>>(ta, tb, tc, a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// weight-panel-resident variant (K <= 384, single-bf16 operands): see GemmCfg
+template <int BN, int EPI>
+int launch_gemm_res(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, GemmArgs a, int num_sms, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, EPI, true>;
+  static int attr_bytes = 0;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, false, true>;
+  const int smem = Cfg::res_smem_bytes(a.kblocks);
+  if (smem > attr_bytes) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_bytes = smem;
+  }
+  a.stages = Cfg::res_stages(a.kblocks);
+  const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * (a.N / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, gemm_threads(BN, EPI), smem, st>>>(ta, tb, tc, a);
   LAUNCH_CHECK();
   return 0;
 }
 
 template <int BN>
-int launch_gemm_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& a, int num_sms,
-                   cudaStream_t st) {
+int launch_gemm_bn(int epi, bool res, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& a,
+                   int num_sms, cudaStream_t st) {
+  if constexpr (BN == 192 || BN == 128) {
+    if (res) {
+      switch (epi) {
+        case EPI_BIAS_BF16: return launch_gemm_res<BN, EPI_BIAS_BF16>(ta, tb, tc, a, num_sms, st);
+        case EPI_BIAS_GELU_BF16: return launch_gemm_res<BN, EPI_BIAS_GELU_BF16>(ta, tb, tc, a, num_sms, st);
+        case EPI_BIAS_RESID_F32: return launch_gemm_res<BN, EPI_BIAS_RESID_F32>(ta, tb, tc, a, num_sms, st);
+        case EPI_BIAS_F32: return launch_gemm_res<BN, EPI_BIAS_F32>(ta, tb, tc, a, num_sms, st);
+      }
+    }
+  }
   switch (epi) {
     case EPI_BIAS_BF16: return launch_gemm_inst<BN, EPI_BIAS_BF16, false>(ta, tb, tc, a, num_sms, st);
     case EPI_BIAS_GELU_BF16: return launch_gemm_inst<BN, EPI_BIAS_GELU_BF16, false>(ta, tb, tc, a, num_sms, st);
@@ -185,16 +214,16 @@ int launch_gemm_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const 
   return fail(VITOCM_ERR_INVALID, "unknown GEMM epilogue %d", epi);
 }
 
-// Tile width: among the instantiated BN that divide N, minimise (waves of the persistent grid) x (per-tile
-// cost ~ BN + fixed overhead) -- e.g. N = 384, M = 25120 on 148 SMs: BN = 192 needs 3 waves of 394 tiles,
-// BN = 128 needs 4 waves of 591 smaller tiles and wins.
-int pick_bn(int M, int N, int num_sms) {
+// Tile width: among the instantiated BN that divide N, minimise (tiles per CTA of the persistent grid) x (per-tile
+// cost ~ BN + fixed overhead) -- e.g. N = 384, M = 25120 on 148 SMs: BN = 192 needs 3 rounds of 394 tiles,
+// BN = 128 needs 4 rounds of 591 smaller tiles and wins.
+int pick_bn(int M, int N, int num_sms, int max_bn) {
   const int cand[4] = {256, 192, 128, 64};
   const long long tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
   int best = 0;
   long long best_cost = 0;
   for (int bn : cand) {
-    if (N % bn != 0) continue;
+    if (bn > max_bn || N % bn != 0) continue;
     const long long tiles = tiles_m * (N / bn);
     const long long waves = (tiles + num_sms - 1) / num_sms;
     const long long cost = waves * (bn + 48);
@@ -210,9 +239,13 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
   if (M <= 0) return 0;
   ProfScope prof(pcls, st);
   if (K % GEMM_BK != 0) return fail(VITOCM_ERR_INVALID, "GEMM K=%d must be a multiple of %d", K, GEMM_BK);
-  const int bn = pick_bn(M, N, e->num_sms);
-  if (bn == 0) return fail(VITOCM_ERR_INVALID, "GEMM N=%d must be a multiple of 64", N);
+  if (N % 64 != 0) return fail(VITOCM_ERR_INVALID, "GEMM N=%d must be a multiple of 64", N);
   if (bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15) != 0) return fail(VITOCM_ERR_INVALID, "GEMM bias must be 16-byte aligned");
+  static const bool allow_res = [] { const char* v = getenv("VITOCM_GEMM_RESIDENT"); return v == nullptr || atoi(v) != 0; }();
+  // weight panel resident in smem: single-bf16 operands, K <= 384, tile width 192 or 128
+  bool res = allow_res && !split_in && !split_out && K / GEMM_BK <= GEMM_RES_MAX_KBLOCKS && (N % 128 == 0 || N % 192 == 0);
+  const int bn = pick_bn(M, N, e->num_sms, res ? 192 : 256);
+  if (res && bn < 128) res = false;
   const long long kext = static_cast<long long>(K) * (split_in ? 2 : 1);
   const bool out_f32 = (epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_F32);
   CUtensorMap ta, tb, tc;
@@ -223,11 +256,13 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
   a.M = M; a.N = N; a.kblocks = K / GEMM_BK; a.nterms = split_in ? 3 : 1;
   a.lo_k = K;
   a.bias = bias; a.split_out = split_out; a.lo_off = lo_off;
+  static const int dbg = [] { const char* v = getenv("VITOCM_GEMM_DEBUG"); return v ? atoi(v) : 0; }();
+  a.debug = dbg; a.out_f32 = reinterpret_cast<float*>(out);
   switch (bn) {
-    case 256: return launch_gemm_bn<256>(epi, ta, tb, tc, a, e->num_sms, st);
-    case 192: return launch_gemm_bn<192>(epi, ta, tb, tc, a, e->num_sms, st);
-    case 128: return launch_gemm_bn<128>(epi, ta, tb, tc, a, e->num_sms, st);
-    default: return launch_gemm_bn<64>(epi, ta, tb, tc, a, e->num_sms, st);
+    case 256: return launch_gemm_bn<256>(epi, res, ta, tb, tc, a, e->num_sms, st);
+    case 192: return launch_gemm_bn<192>(epi, res, ta, tb, tc, a, e->num_sms, st);
+    case 128: return launch_gemm_bn<128>(epi, res, ta, tb, tc, a, e->num_sms, st);
+    default: return launch_gemm_bn<64>(epi, res, ta, tb, tc, a, e->num_sms, st);
   }
 }
 
