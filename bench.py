@@ -160,8 +160,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arch", default="vit_small", choices=sorted(ARCHS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--chunk-tiles", type=int, default=32)
-    ap.add_argument("--tile-batch", type=int, default=128)
+    ap.add_argument("--chunk-tiles", type=int, default=175)
+    ap.add_argument("--tile-batch", type=int, default=175)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -16,8 +16,8 @@
 // residual epilogue uses the TMA reduce-add (cp.reduce.async.bulk.tensor .add): x += acc + bias is
 // performed by the L2, so the residual stream is never read back into the SM.
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator
-// (+ A producer with warp 3 in A_PATCH mode), warps 4..11 = epilogue (lane quadrant = warp % 4,
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..11(15) = epilogue
+// (A_PATCH: warps 2, 3 and six more warps after the epilogue warps are the A producers) (lane quadrant = warp % 4,
 // column group = (warp - 4) / 4).
 #pragma once
 #include "ptx.cuh"
@@ -59,7 +59,11 @@ constexpr int GEMM_EPI_WARP0 = 4;
 // epilogue warps: 8 (two column halves per TMEM lane quadrant), or 12 with BN = 192 (three 64-column groups): the
 // GELU epilogue is issue / latency bound, a third warp per scheduler hides its MUFU + FMA chains
 __host__ __device__ constexpr int gemm_epi_warps(int BN, int EPI) { return (EPI == 1 && BN == 192) ? 12 : 8; }
-__host__ __device__ constexpr int gemm_threads(int BN, int EPI) { return (4 + gemm_epi_warps(BN, EPI)) * 32; }
+// patch embedding: 6 extra warps after the epilogue warps join warps 2-3 as A producers (8 producer warps)
+constexpr int GEMM_PATCH_PRODUCER_WARPS = 8;
+__host__ __device__ constexpr int gemm_threads(int BN, int EPI) {
+  return (4 + gemm_epi_warps(BN, EPI) + (EPI == 4 ? GEMM_PATCH_PRODUCER_WARPS - 2 : 0)) * 32;
+}
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 
 constexpr int GEMM_MAX_STAGES = 8;
@@ -171,7 +175,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(full_bar + 8 * s, A_PATCH ? 3 : 1);   // TMA thread (+ one arrive per A-producer warp)
+      ptx::mbar_init(full_bar + 8 * s, A_PATCH ? 1 + GEMM_PATCH_PRODUCER_WARPS : 1);   // TMA thread (+ one arrive per A-producer warp)
       ptx::mbar_init(empty_bar + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -264,13 +268,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else if (warp < GEMM_EPI_WARP0) {
+  } else if (warp < GEMM_EPI_WARP0 || warp >= GEMM_EPI_WARP0 + Cfg::EPI_WARPS) {
     // ===================== A producer (patch embedding only) =====================
     // A[m, k] = bf16(x[b, c, py*p + yi, px*p + xi]),  m = b*n + py*Wp + px,  k = c*p*p + yi*p + xi.
     // One item = (row, 16-byte chunk): 8 consecutive pixels of one patch row -> 8 bf16 at the
     // SWIZZLE_128B position  row*128 + ((chunk ^ (row & 7)) << 4)  of the stage's A tile.
     if (A_PATCH) {
-      const int t = threadIdx.x - 64;  // 0..63
+      // producer thread index 0..255: warps 2, 3 and the six warps after the epilogue warps
+      const int t = (warp < GEMM_EPI_WARP0 ? warp - 2 : warp - (GEMM_EPI_WARP0 + Cfg::EPI_WARPS) + 2) * 32 + lane;
       const int p = args.patch, pp = p * p;
       const int Wp = args.img_w / p;
       const long long plane = static_cast<long long>(args.img_h) * args.img_w;
@@ -285,14 +290,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const bool want_lo = term == 2;
           ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1, 5);
           const uint32_t a_tile = smem_a + stage * Cfg::A_BYTES;
-          // 16 items per thread in two batches of 8: all 16 loads of a batch are issued before the first
-          // conversion so that their latencies overlap
-#pragma unroll 1
-          for (int batch = 0; batch < 2; ++batch) {
-            float4 f[8][2];
+          // 4 items per thread: all 8 loads are issued before the first conversion so that their latencies overlap
+          {
+            float4 f[4][2];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int item = t + 64 * (batch * 8 + u);
+            for (int u = 0; u < 4; ++u) {
+              const int item = t + 256 * u;
               const int chunk = item >> 7;        // 0..7: consecutive threads -> consecutive rows (coalesced pixel reads)
               const int row = item & 127;
               const int m = m0 + row;
@@ -311,8 +314,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               }
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int item = t + 64 * (batch * 8 + u);
+            for (int u = 0; u < 4; ++u) {
+              const int item = t + 256 * u;
               const int chunk = item >> 7;
               const int row = item & 127;
               float v[8] = {f[u][0].x, f[u][0].y, f[u][0].z, f[u][0].w, f[u][1].x, f[u][1].y, f[u][1].z, f[u][1].w};
