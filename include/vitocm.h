@@ -64,7 +64,7 @@ int vitocm_create(const vitocm_config* cfg, vitocm_engine** out);
 int vitocm_destroy(vitocm_engine* e);
 
 /* Replaces nn.Module.load_state_dict for the hot path (SSS/eval.py:67-77): `name` is a
- * state-dict key (cls_token, pos_embed, mask_token, patch_embed.proj.{weight,bias},
+ * state-dict key (cls_token, pos_embed, mask_token, decoder.0.{weight,bias} (MIM), patch_embed.proj.{weight,bias},
  * blocks.{i}.{norm1,norm2}.{weight,bias}, blocks.{i}.attn.{qkv,proj}.{weight,bias},
  * blocks.{i}.mlp.{fc1,fc2}.{weight,bias}, norm.{weight,bias}); host_data is fp32, `numel`
  * elements.  vitocm_finalize_weights repacks them into the kernels' layouts (bf16 hi/lo,
@@ -99,6 +99,14 @@ int vitocm_block_forward(vitocm_engine* e, int layer, float* X, int B, int n_tok
  * [B*N][3D] fp32 (the pre-permute qkv activation, vit.py:80) -- required scratch/output. */
 int vitocm_block_attn_probs(vitocm_engine* e, int layer, const float* X, int B, int n_tokens, float* attn,
                             float* qkv_out, void* ws, size_t ws_bytes, void* stream);
+
+/* MIM.forward (SSS/model.py:71-77) without autograd: VisionTransformerForSimMIM.forward (model.py:25-53: patch embed,
+ * mask-token mixing, cls, pos, all blocks, norm) -> 1x1-conv decoder + PixelShuffle(patch) (model.py:61-66) -> masked L1.
+ * Needs the weights "mask_token", "decoder.0.weight" [C p^2][D] and "decoder.0.bias".  x [B][C][H][W]; mask [B][n] fp32
+ * in {0,1} (MaskGenerator, SSS/data.py:163-186); x_rec [B][C][H][W] fp32; loss_sums double[2] = {sum |x - x_rec| * mask,
+ * sum mask}: loss = loss_sums[0] / (loss_sums[1] + 1e-5) / C (model.py:75-76). */
+int vitocm_mim_forward(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const float* mask, float* x_rec,
+                       double* loss_sums, void* ws, size_t ws_bytes, int chunk_tiles, void* stream);
 
 /* self.norm (vit.py:215, :234): out [M][D] fp32 = LayerNorm(X [M][D]). */
 int vitocm_final_norm(vitocm_engine* e, const float* X, float* out, int M, void* stream);

@@ -157,3 +157,34 @@ def test_fp32_and_bf16_modes_agree_loosely(vits_sd):
     a = build_model(cfg, vits_sd, "fp32").cls_attention_rows(x)
     b = build_model(cfg, vits_sd, "bf16").cls_attention_rows(x)
     assert ((a - b).abs() / a.abs()).max().item() <= 2e-2
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_mim_forward_matches_reference_golden(precision):
+    """MIM.forward (SSS/model.py:71-77) on the reference's own outputs (tests/golden/mim_tiny.npz): masked-L1 loss and
+    the PixelShuffle reconstruction; also the SimMIM encoder output against the oracle."""
+    from functools import partial
+    g = load_golden("mim_tiny.npz")
+    cfg_init = VO.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=8, img_size=224)
+    cfg = VO.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=8, img_size=32)
+    sd = VO.randomize_affine(VO.init_state_dict(cfg_init, seed=11, mim=True), seed=12)
+    check_weight_sums(sd, g)
+    enc = vob.VisionTransformerForSimMIM(patch_size=8, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4, img_size=[32],
+                                         qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), precision=precision)
+    enc.load_state_dict(sd, strict=True)
+    mim = vob.MIM(encoder=enc, encoder_stride=8)
+    mim.decoder[0].weight.data.copy_(torch.from_numpy(g["dec_w"]))
+    mim.decoder[0].bias.data.copy_(torch.from_numpy(g["dec_b"]))
+    mim = mim.cuda().eval()
+    x, mask = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["mask"]).cuda()
+    loss, x_rec, mask_up = mim(x, mask)
+    tol = 2e-5 if precision == "fp32" else 2e-2
+    assert abs(loss.item() - float(g["loss"])) <= tol * max(1.0, abs(float(g["loss"]))), (loss.item(), float(g["loss"]))
+    assert np.abs(x_rec.cpu().numpy() - g["x_rec"]).max() <= (1e-4 if precision == "fp32" else 5e-2)
+    assert mask_up.shape == (4, 1, 32, 32) and int(mask_up.sum()) == int(g["mask"].sum()) * 64
+    z = enc(x, mask).cpu()
+    z_ref = VO.simmim_encoder(sd, cfg, torch.from_numpy(g["x"]), torch.from_numpy(g["mask"]))
+    assert z.shape == z_ref.shape and (z - z_ref).abs().max().item() <= (1e-4 if precision == "fp32" else 6e-2)
+    # MaskGenerator mirror (SSS/data.py:163-186) draws from numpy's global RNG exactly like the reference
+    np.random.seed(0)
+    assert np.array_equal(vob.MaskGenerator(224, 16, 8, 0.5)(), g["mask224_seed0"])

@@ -3,6 +3,7 @@
 //   layernorm_kernel     vit.py:107,111 (norm1/norm2) and :215/:234 (final norm), eps = 1e-6
 //   cls_attn_row_kernel  vit.py:80-84 restricted to the CLS query of the last block
 //   attn_probs_kernel    vit.py:83-84 full softmax(QK^T) (API-complete get_last_selfattention)
+//   mim_shuffle_loss_kernel  SSS/model.py:61-66,73-76 (PixelShuffle + masked L1 of MIM.forward)
 #pragma once
 #include "ptx.cuh"
 
@@ -244,6 +245,49 @@ attn_probs_kernel(const float* __restrict__ qkv /*[B*N][3D]*/, float* __restrict
     const float inv = 1.0f / sum;
     float* o = attn + ((static_cast<long long>(b) * heads + h) * N + (q0 + r)) * N;
     for (int j = lane; j < N; j += 32) o[j] = lr[j] * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// MIM.forward tail (SSS/model.py:61-66, :73-76): PixelShuffle(p) of the 1x1-conv decoder output and the
+// masked L1 reconstruction loss.  Y [B][1 + n][C*p*p] fp32 is the decoder GEMM over the normed tokens
+// (row 0 of each image = CLS, ignored); x [B][C][H][W]; mask [B][n] in {0,1}.
+//   x_rec[b, c, py*p + i, px*p + j] = Y[b, 1 + py*Wp + px, c*p*p + i*p + j]
+//   sums[0] += sum |x - x_rec| * mask(py, px)   (over all channels),   sums[1] += sum mask (per pixel)
+// loss = sums[0] / (sums[1] + 1e-5) / C is formed by the caller (two doubles, accumulated with atomics).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mim_shuffle_loss_kernel(const float* __restrict__ Y, const float* __restrict__ x, const float* __restrict__ mask,
+                        float* __restrict__ x_rec, double* __restrict__ sums, int B, int C, int H, int W, int p) {
+  __shared__ double red[2][8];
+  const int Wp = W / p, n = (H / p) * Wp, ldy = C * p * p;
+  const long long total = static_cast<long long>(B) * C * H * W;
+  double s_abs = 0.0, s_msk = 0.0;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xx = static_cast<int>(idx % W);
+    const int yy = static_cast<int>((idx / W) % H);
+    const int c = static_cast<int>((idx / (static_cast<long long>(W) * H)) % C);
+    const int b = static_cast<int>(idx / (static_cast<long long>(W) * H * C));
+    const int py = yy / p, i = yy - py * p, px = xx / p, j = xx - px * p;
+    const int tok = py * Wp + px;
+    const float r = Y[(static_cast<long long>(b) * (n + 1) + 1 + tok) * ldy + c * p * p + i * p + j];
+    x_rec[idx] = r;
+    const float m = mask[static_cast<long long>(b) * n + tok];
+    s_abs += static_cast<double>(fabsf(x[idx] - r) * m);
+    if (c == 0) s_msk += static_cast<double>(m);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s_abs += __shfl_xor_sync(0xffffffffu, s_abs, o);
+    s_msk += __shfl_xor_sync(0xffffffffu, s_msk, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s_abs; red[1][threadIdx.x >> 5] = s_msk; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, m = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { a += red[0][w]; m += red[1][w]; }
+    atomicAdd(sums, a);
+    atomicAdd(sums + 1, m);
   }
 }
 

@@ -142,6 +142,7 @@ struct vitocm_engine {
   std::map<std::string, DevBuf*> master;  // fp32 weights as loaded
   std::vector<LayerW> layers;
   DevBuf patch_w;   // bf16 [D][2K]  (hi | lo): the conv filter as a K-major GEMM operand
+  DevBuf dec_w;     // MIM decoder 1x1 conv weight, bf16 [C p^2][D * parts] (present iff "decoder.0.weight" was loaded)
   ~vitocm_engine() { for (auto& kv : master) delete kv.second; }
   const float* w(const std::string& name) const {
     auto it = master.find(name);
@@ -505,6 +506,12 @@ int vitocm_finalize_weights(vitocm_engine* e) {
     if (l == e->cfg.depth - 1) TRY(pack(L.wk_split, L.wqkv_f32 + static_cast<long long>(D) * D, D, D, 1));
   }
   (void)P;
+  const long long dec_rows = static_cast<long long>(e->cfg.in_chans) * e->cfg.patch_size * e->cfg.patch_size;
+  if (e->numel("decoder.0.weight") > 0) {   // MIM decoder (SSS/model.py:61-64), optional
+    TRY(need("decoder.0.weight", dec_rows * D));
+    TRY(need("decoder.0.bias", dec_rows));
+    TRY(pack(e->dec_w, e->w("decoder.0.weight"), static_cast<int>(dec_rows), D, S));
+  }
   CUDA_TRY(cudaDeviceSynchronize());
   e->finalized = true;
   return 0;
@@ -600,6 +607,47 @@ int vitocm_block_attn_probs(vitocm_engine* e, int layer, const float* X, int B, 
   dim3 grid((N + qrows - 1) / qrows, heads, B);
   attn_probs_kernel<<<grid, 256, smem, st>>>(qkv_out, attn, N, D, heads, e->cfg.qk_scale, kchunk, qrows);
   LAUNCH_CHECK();
+  return 0;
+}
+
+int vitocm_mim_forward(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const float* mask, float* x_rec,
+                       double* loss_sums, void* ws, size_t ws_bytes, int chunk_tiles, void* stream) {
+  TRY(check_engine(e));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int p = e->cfg.patch_size, D = e->cfg.embed_dim, C = e->cfg.in_chans, P = e->parts, S = e->split;
+  if (B <= 0) return 0;
+  if (e->dec_w.p == nullptr) return fail(VITOCM_ERR_STATE, "MIM decoder weights (decoder.0.weight / decoder.0.bias) were never loaded");
+  if (mask == nullptr || x_rec == nullptr || loss_sums == nullptr) return fail(VITOCM_ERR_INVALID, "mim_forward needs mask, x_rec and loss_sums");
+  if (H % p || W % p) return fail(VITOCM_ERR_INVALID, "image %dx%d not a multiple of patch %d", H, W, p);
+  const int n = (H / p) * (W / p), N = n + 1, ldy = C * p * p;
+  if (ldy % 64 != 0) return fail(VITOCM_ERR_INVALID, "decoder width C*p*p=%d must be a multiple of 64", ldy);
+  if (chunk_tiles <= 0) return fail(VITOCM_ERR_INVALID, "chunk_tiles must be positive");
+  if (chunk_tiles > B) chunk_tiles = B;
+  void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  const size_t avail = ws_bytes - (reinterpret_cast<uintptr_t>(base) - reinterpret_cast<uintptr_t>(ws));
+  const Workspace wsp = carve(e, base, chunk_tiles, N);
+  if (ws == nullptr || wsp.total > avail) return fail(VITOCM_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", wsp.total + 1024, ws_bytes);
+  CUDA_TRY(cudaMemsetAsync(loss_sums, 0, 2 * sizeof(double), st));
+  float* Y = reinterpret_cast<float*>(wsp.QKV);   // [M][C p^2] fp32 fits in the QKV slab (3D*parts bf16 per row)
+  for (int b0 = 0; b0 < B; b0 += chunk_tiles) {
+    const int bc = (B - b0 < chunk_tiles) ? (B - b0) : chunk_tiles;
+    const int M = bc * N;
+    const float* xc = x + static_cast<long long>(b0) * C * H * W;
+    const float* mc = mask + static_cast<long long>(b0) * n;
+    // VisionTransformerForSimMIM.forward (SSS/model.py:25-53): patch embed + mask-token mix + cls + pos, all blocks, norm
+    TRY(run_patch_embed(e, xc, bc, H, W, pos, mc, wsp.X, st));
+    for (int l = 0; l < e->cfg.depth; ++l) TRY(block_forward(e, l, wsp, bc, N, st));
+    TRY(run_layernorm(wsp.X, e->w("norm.weight"), e->w("norm.bias"), wsp.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
+    // decoder: 1x1 conv D -> C p^2 == per-token linear (model.py:61-64); CLS rows are computed and ignored
+    TRY(run_gemm(e, wsp.XN, 2LL * D, e->dec_w.p, static_cast<long long>(D) * P, M, ldy, D, S, EPI_BIAS_F32, e->w("decoder.0.bias"), Y,
+                 ldy, 0, 0, st));
+    const long long total = static_cast<long long>(bc) * C * H * W;
+    long long grid = (total + 255) / 256;
+    if (grid > 148LL * 16) grid = 148LL * 16;
+    mim_shuffle_loss_kernel<<<static_cast<int>(grid), 256, 0, st>>>(Y, xc, mc, x_rec + static_cast<long long>(b0) * C * H * W, loss_sums, bc, C, H,
+                                                                     W, p);
+    LAUNCH_CHECK();
+  }
   return 0;
 }
 

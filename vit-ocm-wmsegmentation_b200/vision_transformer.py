@@ -190,6 +190,9 @@ class VisionTransformer(nn.Module):
                ("norm.bias", self.norm.bias)]
         if hasattr(self, "mask_token"):
             out.append(("mask_token", self.mask_token))
+        extra = getattr(self, "_extra_engine_params", None)     # e.g. the MIM decoder (model.py)
+        if extra is not None:
+            out += list(extra())
         for i, blk in enumerate(self.blocks):
             pre = f"blocks.{i}."
             qkv_b = blk.attn.qkv.bias if blk.attn.qkv.bias is not None else self._zero_qkv_bias
