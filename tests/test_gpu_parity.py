@@ -188,3 +188,19 @@ def test_mim_forward_matches_reference_golden(precision):
     # MaskGenerator mirror (SSS/data.py:163-186) draws from numpy's global RNG exactly like the reference
     np.random.seed(0)
     assert np.array_equal(vob.MaskGenerator(224, 16, 8, 0.5)(), g["mask224_seed0"])
+
+
+def test_larger_tile_448_interpolated_pos_matches_oracle(vits_sd):
+    """BASELINE config 5 shape: a 448x448 tile (N = 3137) goes through the bicubic position-table resize
+    (vit.py:176-196) and the multi-block attention path; fp32-parity mode against the CPU oracle."""
+    cfg = VO.ViTConfig(**VO.VIT_SMALL)
+    cfg4 = VO.ViTConfig(embed_dim=cfg.embed_dim, depth=4, num_heads=cfg.num_heads, patch_size=8, img_size=224)
+    sd = {k: v for k, v in vits_sd.items() if not k.startswith("blocks.") or int(k.split(".")[1]) < 4}
+    m = build_model(cfg4, sd, "fp32", chunk_tiles=1)
+    x = VO.synthetic_tile(448, seed=44, batch=1)
+    ref = VO.cls_attention_rows(sd, cfg4, x).numpy()
+    rows = m.cls_attention_rows(x.cuda()).cpu().numpy()
+    assert rows.shape == (1, 6, 3137)
+    assert rel_err(rows, ref) <= 1e-3, rel_err(rows, ref)
+    m16 = build_model(cfg4, sd, "bf16", chunk_tiles=1)
+    assert rel_err(m16.cls_attention_rows(x.cuda()).cpu().numpy(), ref) <= 2e-2
