@@ -274,7 +274,10 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if dom and os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom)
+        rec = json.load(open(tpath)).get(dom)
+        if rec:   # DRAM bytes per launch = ncu's per-tile figure x tiles per launch of this run
+            tiles_per_launch = my_tiles * (a["depth"] - 1) / max(classes[dom]["launches"], 1)
+            traffic = rec["dram_bytes_per_tile"] * tiles_per_launch
     roofline = None
     if dom:
         c = tensor_classes[dom]
