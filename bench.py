@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--chunk-tiles", type=int, default=175)
     ap.add_argument("--tile-batch", type=int, default=175)
+    ap.add_argument("--lanes", type=int, default=1, help="chunks in flight on concurrent streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -185,7 +186,7 @@ def main():
 
     a = ARCHS[args.arch]
     torch.manual_seed(0)
-    model = getattr(vob, args.arch)(patch_size=PATCH, num_classes=0, precision=args.precision, chunk_tiles=args.chunk_tiles)
+    model = getattr(vob, args.arch)(patch_size=PATCH, num_classes=0, precision=args.precision, chunk_tiles=args.chunk_tiles, lanes=args.lanes)
     model = model.cuda().eval()
     n, size, extent = mosaic_geometry(world)
     T = n * n
@@ -293,7 +294,7 @@ def main():
                 "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": f"{args.arch}/8 sliding-window segmentation, {size}x{size} gray mosaic, window {WINDOW}, stride {STRIDE}, "
                                        f"{T} tiles, extent {extent}^2", "tiles": T, "tiles_per_gpu": my_tiles, "weights": "random init (seed 0)",
-                           "chunk_tiles": args.chunk_tiles, "l2": "flushed between timed steps (256 MiB write, untimed); per-step working set >> L2",
+                           "chunk_tiles": args.chunk_tiles, "lanes": args.lanes, "l2": "flushed between timed steps (256 MiB write, untimed); per-step working set >> L2",
                            "parallelism": f"tiles sharded over {world} rank(s)"},
                 "tiles_per_s": T / (ms_per_step / 1e3),
                 "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": int(mosaic_host.numel()),

@@ -76,6 +76,11 @@ int vitocm_finalize_weights(vitocm_engine* e);
  * n_tokens tokens each. */
 size_t vitocm_workspace_bytes(const vitocm_engine* e, int chunk_tiles, int n_tokens);
 
+/* Chunk-level concurrency of vitocm_forward_cls_attn: `lanes` (1..4) independent chunks of tiles are processed
+ * concurrently, lane 0 on the caller's stream, the others on streams owned by the engine (forked from / joined back
+ * into the caller's stream with events).  vitocm_workspace_bytes accounts for the configured number of lanes. */
+int vitocm_set_concurrency(vitocm_engine* e, int lanes);
+
 /* HOT PATH.  VisionTransformer.get_last_selfattention(x)[:, :, 0, :] (vit.py:239-246), i.e. the
  * CLS query row per head that SSS/utils.py:232 (query = 0) slices out of
  * get_intermediate_feat(x, n=1) (vit.py:225-237; callers SSS/eval.py:136, SSS/sw_processing.py:239).
@@ -180,6 +185,11 @@ int vitocm_crop_u8(const uint8_t* img, int img_h, int img_w, int C, int ny, int 
 int vitocm_gemm(vitocm_engine* e, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K,
                 int split_in, int epilogue, const float* bias, void* out, int64_t ldo, int split_out, int lo_off,
                 void* stream);
+/* X[M][N] (fp32, in place) += A . B^T + bias, then XN[M][ld_xn] (bf16) = LayerNorm(X) * gamma + beta with the engine's
+ * eps: Block.forward's residual add (vit.py:110-111) fused with the LayerNorm that reads it next (:107 / :111).
+ * bf16 engines only; N / 128 must be 1, 2, 3, 4 or 6 (one thread-block cluster spans a row). */
+int vitocm_gemm_ln(vitocm_engine* e, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, const float* bias,
+                   float* X, const float* gamma, const float* beta, void* XN, int64_t ld_xn, void* stream);
 /* ctx = MHSA(qkv) for B images of n_tokens tokens: qkv bf16 [B*N][ld], ctx bf16 [B*N][ldo]. */
 int vitocm_attention(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo,
                      void* stream);

@@ -90,6 +90,28 @@ def test_gemm_weight_panel_resident_epilogues(engine, M, N, K):
     assert (z.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 384, 384), (25120, 384, 1536), (300, 128, 128), (777, 768, 384), (500, 512, 64), (900, 256, 128)])
+def test_gemm_fused_residual_layernorm(engine, M, N, K):
+    """proj / fc2 epilogue with the next LayerNorm fused: a row spans N / BN CTAs of one cluster which exchange
+    (mean, M2) partials through distributed shared memory."""
+    lib = vob._lib.load_library()
+    A = _rand((M, K), 40).to(torch.bfloat16)
+    B = _rand((N, K), 41, 0.05).to(torch.bfloat16)
+    bias = _rand((N,), 42, 0.1)
+    resid = _rand((M, N), 43) + 0.3
+    gamma, beta = _rand((N,), 44) * 0.1 + 1, _rand((N,), 45) * 0.1
+    x = resid.clone()
+    xn = torch.full((M, 2 * N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    check(lib.vitocm_gemm_ln(engine, ptr(A), A.stride(0), ptr(B), B.stride(0), M, N, K, ptr(bias), ptr(x), ptr(gamma), ptr(beta),
+                             ptr(xn), xn.stride(0), cur_stream()))
+    torch.cuda.synchronize()
+    ref_x = resid + A.float() @ B.float().T + bias
+    assert (x - ref_x).abs().max().item() <= 2e-4 * ref_x.abs().max().item() + 1e-5
+    ref_n = torch.nn.functional.layer_norm(x, (N,), gamma, beta, 1e-6)          # LN of the kernel's own updated rows
+    assert (xn[:, :N].float() - ref_n).abs().max().item() <= 2e-2
+    assert torch.isnan(xn[:, N:].float()).all()                                   # lo half untouched
+
+
 def test_gemm_split_precision_is_fp32_grade(engine):
     M, N, K = 785, 384, 384
     A32, B32 = _rand((M, K), 11), _rand((N, K), 12, 0.05)

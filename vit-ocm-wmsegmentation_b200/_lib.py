@@ -28,6 +28,7 @@ SIGNATURES = {
     "vitocm_load_weight": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
     "vitocm_finalize_weights": (c_int, [c_void_p]),
     "vitocm_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "vitocm_set_concurrency": (c_int, [c_void_p, c_int]),
     "vitocm_forward_cls_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                         c_int, c_void_p]),
     "vitocm_prepare_tokens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -57,6 +58,8 @@ SIGNATURES = {
     "vitocm_crop_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vitocm_gemm": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p,
                             c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "vitocm_gemm_ln": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_int64, c_void_p]),
     "vitocm_attention": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "vitocm_attention_timeline": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "vitocm_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),

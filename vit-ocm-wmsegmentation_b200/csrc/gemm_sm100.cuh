@@ -30,6 +30,7 @@ enum GemmEpilogue : int {
   EPI_BIAS_RESID_F32 = 2,  // resid_f32 += acc + bias              (proj, fc2)
   EPI_BIAS_F32 = 3,        // out_f32 = acc + bias                 (generic / decoder)
   EPI_PATCH_F32 = 4,       // X[b, 1+i, :] = mix(acc + bias, mask_token) + pos[1+i]   (patch embedding)
+  EPI_RESID_LN = 5,        // resid_f32 += acc + bias;  xn_bf16 = LayerNorm(resid_f32) * gamma + beta   (proj / fc2 + next LN)
 };
 
 struct GemmArgs {
@@ -40,6 +41,13 @@ struct GemmArgs {
   const float* bias;  // [N] or nullptr
   int split_out;      // bf16 outputs only: also write lo = bf16(v - hi) at column offset lo_off
   int lo_off;
+  // EPI_RESID_LN only: the LayerNorm that consumes the updated residual stream (vit.py:107/111), fused here
+  const float* ln_gamma;
+  const float* ln_beta;
+  float ln_eps;
+  __nv_bfloat16* xn;   // [M][ld_xn] bf16 normalised rows (A operand of the next GEMM)
+  long long ld_xn;
+  int num_clusters;    // persistent grid = num_clusters clusters of N / BN CTAs (one CTA per column block of a row tile)
   int debug;          // diagnostics only (VITOCM_GEMM_DEBUG): 1 = epilogue drains TMEM but skips math + stores, 2 = epilogue
                       // signals only (no TMEM load either)
   int stages;         // B_RES only: number of A stages that fit next to the resident B panel (host-computed)
@@ -74,7 +82,13 @@ constexpr int GEMM_RES_MAX_KBLOCKS = 6;     // B_RES: K <= 384
 // re-fetches A and B for every tile: (128 + BN) * 128 B per 2*BN tensor clocks = 96-128 B/clk/SM, i.e. 14-19 KB/clk
 // chip-wide against a measured L2->SM ceiling of ~9 KB/clk -- the GEMMs of this model were L2-bandwidth bound at
 // 45-55 % of tensor peak.  With the panel resident the demand drops to 128*128 B per 2*BN clocks (43 B/clk at BN 192).
-template <int BN, int EPI, bool B_RES = false>
+// EPI_RESID_LN ("fused LayerNorm"): a row of the residual stream spans CS = N / BN column tiles, owned by the CS CTAs
+// of one thread-block cluster.  Every epilogue thread owns one row x 64 columns in registers, computes (mean, M2) of
+// its 64 values exactly, writes the pair into the stats slab of every CTA of the cluster through distributed shared
+// memory, and after a cluster-scope mbarrier round combines the (EPI_WARPS/4 * CS) partials with Chan's formula --
+// full-row statistics without ever re-reading the row.  The separate LayerNorm kernel (one HBM pass over the fp32
+// residual stream per LayerNorm) disappears.
+template <int BN, int EPI, bool B_RES = false, int CS = 1>
 struct GemmCfg {
   static constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16);
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;       // 16 KB
@@ -84,10 +98,14 @@ struct GemmCfg {
   // bf16 output the two bf16 boxes hold hi and lo instead (single buffered -- the parity mode is not the fast
   // path).  B_RES keeps one box per warp (single buffered) to leave room for the panel.
   static constexpr int STG_BOX_BYTES = OUT_BF16 ? 2048 : 4096;
-  static constexpr int STG_WARP_BYTES = (B_RES ? 1 : 2) * STG_BOX_BYTES;
+  // LN: per warp two fp32 boxes (the residual rows come in and go out through them) + one bf16 box (normalised rows)
+  static constexpr int STG_WARP_BYTES = EPI == EPI_RESID_LN ? 2 * 4096 + 2048 : (B_RES ? 1 : 2) * STG_BOX_BYTES;
   static constexpr int EPI_WARPS = gemm_epi_warps(BN, EPI);
   static constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
-  static constexpr int FIXED_BYTES = STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // EPI_RESID_LN: [2 slots][LN_SRC partial sources][128 rows] x (mean, M2)
+  static constexpr int LN_SRC = (EPI_WARPS / 4) * CS;
+  static constexpr int STATS_BYTES = EPI == EPI_RESID_LN ? 2 * LN_SRC * GEMM_BM * 8 : 0;
+  static constexpr int FIXED_BYTES = STG_BYTES + STATS_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
   static constexpr int STAGES_FIT = (GEMM_SMEM_LIMIT - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;   // plain kernel (compile time)
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -132,11 +150,14 @@ __device__ __forceinline__ void gelu_sigmoid_x2(float& x0, float& x1) {
   ptx::unpack_f32x2(r, x0, x1);
 }
 
-template <int BN, int EPI, bool A_PATCH, bool B_RES = false>
+template <int BN, int EPI, bool A_PATCH, bool B_RES = false, int CS = 1>
 __global__ void __launch_bounds__(gemm_threads(BN, EPI), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_c, const GemmArgs args) {
-  using Cfg = GemmCfg<BN, EPI, B_RES>;
+                         const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_d, const GemmArgs args) {
+  using Cfg = GemmCfg<BN, EPI, B_RES, CS>;
+  constexpr bool LN = EPI == EPI_RESID_LN;
+  static_assert(LN || CS == 1, "clusters are only used by the fused-LayerNorm epilogue");
+  static_assert(!(LN && (A_PATCH || B_RES)), "fused LayerNorm uses the plain pipeline");
   static_assert(!(A_PATCH && B_RES), "patch embedding uses the plain pipeline");
   const int STAGES = B_RES ? args.stages : Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -145,14 +166,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + STAGES * Cfg::A_BYTES;     // plain: [STAGES] B tiles; B_RES: the [kblocks] panel
   const uint32_t smem_stg = smem_b + (B_RES ? args.kblocks : STAGES) * Cfg::B_BYTES;
-  const uint32_t bars = smem_stg + Cfg::STG_BYTES;
+  const uint32_t smem_stats = smem_stg + Cfg::STG_BYTES;
+  const uint32_t bars = smem_stats + Cfg::STATS_BYTES;
   const uint32_t full_bar = bars;                                   // [STAGES]  producers -> MMA
   const uint32_t empty_bar = bars + 8 * GEMM_MAX_STAGES;            // [STAGES]  MMA -> producers
   const uint32_t tfull_bar = bars + 16 * GEMM_MAX_STAGES;           // [2]       MMA -> epilogue
   const uint32_t tempty_bar = bars + 16 * GEMM_MAX_STAGES + 16;     // [2]       epilogue -> MMA
   const uint32_t bfull_bar = bars + 16 * GEMM_MAX_STAGES + 32;      // B_RES: panel loaded
   const uint32_t bempty_bar = bars + 16 * GEMM_MAX_STAGES + 40;     // B_RES: panel no longer read
-  const uint32_t tmem_ptr_smem = bars + 16 * GEMM_MAX_STAGES + 48;
+  const uint32_t stat_bar = bars + 16 * GEMM_MAX_STAGES + 48;       // [2]  LN: partial statistics of a row tile arrived
+  const uint32_t xin_bar = bars + 16 * GEMM_MAX_STAGES + 64;        // [8]  LN: per epilogue warp, residual boxes landed
+  const uint32_t tmem_ptr_smem = bars + 16 * GEMM_MAX_STAGES + 128;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -162,16 +186,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int k_iters = args.kblocks * args.nterms;
   // tile schedule.  plain: m-major, strided over the persistent grid.  B_RES: n-major, one contiguous range per CTA
   // (so that a CTA changes weight panel at most a couple of times).
-  const int tile_begin = B_RES ? static_cast<int>(static_cast<long long>(blockIdx.x) * num_tiles / gridDim.x) : static_cast<int>(blockIdx.x);
-  const int tile_end = B_RES ? static_cast<int>(static_cast<long long>(blockIdx.x + 1) * num_tiles / gridDim.x) : num_tiles;
-  const int tile_step = B_RES ? 1 : static_cast<int>(gridDim.x);
-  auto tile_m = [&](int t) { return B_RES ? t % tiles_m : t / tiles_n; };
-  auto tile_n = [&](int t) { return B_RES ? t / tiles_m : t % tiles_n; };
+  // LN: cluster c walks row tiles c, c + num_clusters, ...; the CTA of rank r owns column tile r of each.
+  const int cta_rank = LN ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int tile_begin = LN ? static_cast<int>(blockIdx.x) / CS
+                            : (B_RES ? static_cast<int>(static_cast<long long>(blockIdx.x) * num_tiles / gridDim.x) : static_cast<int>(blockIdx.x));
+  const int tile_end = LN ? tiles_m : (B_RES ? static_cast<int>(static_cast<long long>(blockIdx.x + 1) * num_tiles / gridDim.x) : num_tiles);
+  const int tile_step = LN ? args.num_clusters : (B_RES ? 1 : static_cast<int>(gridDim.x));
+  auto tile_m = [&](int t) { return LN ? t : (B_RES ? t % tiles_m : t / tiles_n); };
+  auto tile_n = [&](int t) { return LN ? cta_rank : (B_RES ? t / tiles_m : t % tiles_n); };
 
   if (warp == 0 && lane == 0) {
     if (!A_PATCH) ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
     if (EPI != EPI_PATCH_F32) ptx::prefetch_tmap(&tmap_c);
+    if (LN) ptx::prefetch_tmap(&tmap_d);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -184,6 +212,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     ptx::mbar_init(bfull_bar, 1);
     ptx::mbar_init(bempty_bar, 1);
+    ptx::mbar_init(stat_bar, 1);        // LN: one expect_tx arrive per row tile; the partials arrive as st.async complete_tx bytes
+    ptx::mbar_init(stat_bar + 8, 1);
+    for (int w = 0; w < 8; ++w) ptx::mbar_init(xin_bar + 8 * w, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -192,6 +223,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (LN && CS > 1) ptx::cluster_sync_all();   // peers' barriers are initialised before anyone arrives on them remotely
   ptx::tc_fence_after();
   const uint32_t tmem_base = ptx::lds_u32(tmem_ptr_smem);
 
@@ -345,11 +377,136 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint32_t stg_sel = 0;
     int as = 0;
     uint32_t aphase = 0;
+    int ln_tiles = 0;
     for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
       const int m0 = tile_m(tile) * GEMM_BM;
       const int n0 = tile_n(tile) * BN;
       const int row_base = m0 + q * 32;
       const int col_base = n0 + half * COLS_PER_WARP;
+      if constexpr (LN) {
+        static_assert(!LN || COLS_PER_WARP == 64, "fused LayerNorm: 64 columns per epilogue warp");
+        constexpr int SRC = Cfg::LN_SRC;
+        // staging of this warp: [box 0: cols 0..31 fp32][box 1: cols 32..63 fp32][bf16 box]
+        const uint32_t xbox = stg_warp, nbox = stg_warp + 8192;
+        const uint32_t my_xin = xin_bar + 8 * ew;
+        // residual rows of this warp's 32 x 64 patch: two TMA boxes, fetched while the tile's MMAs are still running
+        // (the boxes were last read by the previous tile's TMA stores)
+        if (lane == 0) {
+          ptx::bulk_wait_read0();
+          ptx::mbar_arrive_expect_tx(my_xin, 8192);
+          ptx::tma_load_2d(xbox, &tmap_c, my_xin, col_base, row_base);
+          ptx::tma_load_2d(xbox + 4096, &tmap_c, my_xin, col_base + 32, row_base);
+        }
+        __syncwarp();
+        ptx::mbar_wait(tfull_bar + 8 * as, aphase, 4);
+        ptx::tc_fence_after();
+        float y[2][32];
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN + half * COLS_PER_WARP), r0);
+        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN + half * COLS_PER_WARP + 32), r1);
+        ptx::mbar_wait(my_xin, ln_tiles & 1, 9);
+        ptx::tmem_ld_wait(r0);
+        ptx::tmem_ld_wait(r1);
+        // accumulator stage is in registers -> hand it back to the MMA warp right away
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * as);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        float sum = 0.f;
+        const int sw = lane & 7;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 xo = ptx::lds_v4f(xbox + g * 4096 + lane * 128 + ((j ^ sw) << 4));   // SWIZZLE_128B box row
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + col_base + g * 32) + j);
+            const uint32_t* rr = g == 0 ? r0 : r1;
+            y[g][4 * j] = __uint_as_float(rr[4 * j]) + b4.x + xo.x;
+            y[g][4 * j + 1] = __uint_as_float(rr[4 * j + 1]) + b4.y + xo.y;
+            y[g][4 * j + 2] = __uint_as_float(rr[4 * j + 2]) + b4.z + xo.z;
+            y[g][4 * j + 3] = __uint_as_float(rr[4 * j + 3]) + b4.w + xo.w;
+            sum += (y[g][4 * j] + y[g][4 * j + 1]) + (y[g][4 * j + 2] + y[g][4 * j + 3]);
+          }
+        }
+        // exact local statistics of the 64 values, published to every CTA of the cluster
+        const float mean_i = sum * (1.0f / 64.0f);
+        float m2_i = 0.f;
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = y[g][j] - mean_i;
+            m2_i = fmaf(d, d, m2_i);
+          }
+        const int slot = ln_tiles & 1;
+        const uint32_t row_off = static_cast<uint32_t>((q * 32 + lane) * 8);
+        const uint32_t mine = smem_stats + static_cast<uint32_t>(((slot * SRC + cta_rank * (Cfg::EPI_WARPS / 4) + half) * GEMM_BM) * 8) + row_off;
+        // the first epilogue thread of the CTA announces how many bytes of partials this row tile will receive
+        if (ew == 0 && lane == 0) ptx::mbar_arrive_expect_tx(stat_bar + 8 * slot, SRC * GEMM_BM * 8);
+#pragma unroll
+        for (int r = 0; r < CS; ++r) ptx::st_async_v2(ptx::mapa(mine, r), mean_i, m2_i, ptx::mapa(stat_bar + 8 * slot, r));
+        // meanwhile: the updated residual rows go back out through the same boxes
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ptx::sts_v4(xbox + g * 4096 + lane * 128 + ((j ^ sw) << 4), __float_as_uint(y[g][4 * j]), __float_as_uint(y[g][4 * j + 1]),
+                        __float_as_uint(y[g][4 * j + 2]), __float_as_uint(y[g][4 * j + 3]));
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(&tmap_c, xbox, col_base, row_base);
+          ptx::tma_store_2d(&tmap_c, xbox + 4096, col_base + 32, row_base);
+          ptx::bulk_commit();
+        }
+        ptx::mbar_wait(stat_bar + 8 * slot, (ln_tiles >> 1) & 1, 8);
+        ++ln_tiles;
+        // Chan's combination of SRC groups of 64 values
+        float mp[SRC];
+        float mean = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int p = 0; p < SRC; ++p) {
+          const float2 v = ptx::lds_v2f(smem_stats + static_cast<uint32_t>(((slot * SRC + p) * GEMM_BM) * 8) + row_off);
+          mp[p] = v.x;
+          mean += v.x;
+          m2 += v.y;
+        }
+        mean *= 1.0f / static_cast<float>(SRC);
+#pragma unroll
+        for (int p = 0; p < SRC; ++p) {
+          const float d = mp[p] - mean;
+          m2 = fmaf(64.0f * d, d, m2);
+        }
+        const float rstd = rsqrtf(m2 / static_cast<float>(args.N) + args.ln_eps);
+        // normalised rows: bf16 box (32 x 32, SWIZZLE_64B) -> TMA store, one chunk at a time
+        const int sw2 = (lane >> 1) & 3;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int col = col_base + g * 32;
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(args.ln_gamma + col) + j);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.ln_beta + col) + j);
+            pk[2 * j] = ptx::pack_bf16x2((y[g][4 * j] - mean) * rstd * g4.x + b4.x, (y[g][4 * j + 1] - mean) * rstd * g4.y + b4.y);
+            pk[2 * j + 1] = ptx::pack_bf16x2((y[g][4 * j + 2] - mean) * rstd * g4.z + b4.z, (y[g][4 * j + 3] - mean) * rstd * g4.w + b4.w);
+          }
+          if (g == 1) {   // the bf16 box is still being read by the first chunk's store
+            if (lane == 0) ptx::bulk_wait_read0();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            ptx::sts_v4(nbox + lane * 64 + ((j ^ sw2) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmap_d, nbox, col, row_base);
+            ptx::bulk_commit();
+          }
+        }
+        continue;
+      }
       ptx::mbar_wait(tfull_bar + 8 * as, aphase, 4);
       ptx::tc_fence_after();
       if (args.debug == 3) {   // diagnostics: drain the warp's slice with back-to-back loads and one wait
@@ -480,6 +637,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (LN && CS > 1) ptx::cluster_sync_all();   // no CTA leaves while a peer could still address its shared memory
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

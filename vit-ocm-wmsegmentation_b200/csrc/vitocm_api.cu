@@ -143,7 +143,20 @@ struct vitocm_engine {
   std::vector<LayerW> layers;
   DevBuf patch_w;   // bf16 [D][2K]  (hi | lo): the conv filter as a K-major GEMM operand
   DevBuf dec_w;     // MIM decoder 1x1 conv weight, bf16 [C p^2][D * parts] (present iff "decoder.0.weight" was loaded)
-  ~vitocm_engine() { for (auto& kv : master) delete kv.second; }
+  // chunk-level concurrency: independent chunks of tiles run on `lanes` streams (lane 0 = the caller's stream) so that
+  // one chunk's kernel tails and bandwidth-bound kernels overlap the other chunk's tensor-bound kernels
+  static constexpr int MAX_LANES = 4;
+  int lanes = 1;
+  cudaStream_t aux[MAX_LANES - 1] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES - 1] = {nullptr, nullptr, nullptr};
+  ~vitocm_engine() {
+    for (auto& kv : master) delete kv.second;
+    for (int i = 0; i < MAX_LANES - 1; ++i) {
+      if (aux[i]) cudaStreamDestroy(aux[i]);
+      if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+    }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+  }
   const float* w(const std::string& name) const {
     auto it = master.find(name);
     return it == master.end() ? nullptr : it->second->as<float>();
@@ -169,7 +182,7 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   }
   const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * (a.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, gemm_threads(BN, EPI), Cfg::SMEM_BYTES, st>>>(ta, tb, tc, a);
+  kern<<<grid, gemm_threads(BN, EPI), Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tc, a);
   LAUNCH_CHECK();
   return 0;
 }
@@ -188,7 +201,38 @@ int launch_gemm_res(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
   a.stages = Cfg::res_stages(a.kblocks);
   const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * (a.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, gemm_threads(BN, EPI), smem, st>>>(ta, tb, tc, a);
+  kern<<<grid, gemm_threads(BN, EPI), smem, st>>>(ta, tb, tc, tc, a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// proj / fc2 with the following LayerNorm fused (EPI_RESID_LN): clusters of CS = N / BN CTAs, one per column tile
+template <int BN, int CS>
+int launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td, GemmArgs a, int num_sms,
+                   cudaStream_t st) {
+  using Cfg = GemmCfg<BN, EPI_RESID_LN, false, CS>;
+  static int max_clusters = -1;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI_RESID_LN, false, false, CS>;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(gemm_threads(BN, EPI_RESID_LN));
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (max_clusters < 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    cfg.gridDim = dim3(CS * (num_sms / CS));
+    int n = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    if (n < 1) return fail(VITOCM_ERR_CUDA, "no %d-CTA cluster of the fused-LayerNorm GEMM fits on this device", CS);
+    max_clusters = n < num_sms / CS ? n : num_sms / CS;
+  }
+  const int tiles_m = (a.M + GEMM_BM - 1) / GEMM_BM;
+  a.num_clusters = tiles_m < max_clusters ? tiles_m : max_clusters;
+  cfg.gridDim = dim3(CS * a.num_clusters);
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, td, a));
   LAUNCH_CHECK();
   return 0;
 }
@@ -264,6 +308,40 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
     case 192: return launch_gemm_bn<192>(epi, res, ta, tb, tc, a, e->num_sms, st);
     case 128: return launch_gemm_bn<128>(epi, res, ta, tb, tc, a, e->num_sms, st);
     default: return launch_gemm_bn<64>(epi, res, ta, tb, tc, a, e->num_sms, st);
+  }
+}
+
+// X[M][N] += A . B^T + bias;  XN = bf16(LayerNorm(X) * gamma + beta)   (single-bf16 operands only).
+// Returns 1 when the shape has no fused instantiation (the caller then runs the two kernels separately).
+int run_gemm_ln(const vitocm_engine* e, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                const float* bias, float* X, const float* gamma, const float* beta, float eps, void* XN, long long ld_xn,
+                cudaStream_t st, int pcls) {
+  // VITOCM_FUSE_LN: 0 = never, 1 = short-K GEMMs only (proj; default -- measured: the long-K fc2 is L2-bandwidth bound and
+  // loses more to the extra residual traffic and the per-tile cluster lockstep than the LayerNorm kernel costs), 2 = always
+  static const int mode = [] { const char* v = getenv("VITOCM_FUSE_LN"); return v == nullptr ? 1 : atoi(v); }();
+  if (mode == 0 || (mode == 1 && K > 512 && pcls != PC_OTHER)) return 1;
+  if (e->split || M <= 0 || K % GEMM_BK != 0 || bias == nullptr) return 1;
+  // one cluster of CS = N / 128 CTAs spans a row (cluster sizes 1, 2, 3, 4, 6: N = 128 ... 768)
+  if (N % 128 != 0) return 1;
+  const int cs = N / 128;
+  if (cs != 1 && cs != 2 && cs != 3 && cs != 4 && cs != 6) return 1;
+  ProfScope prof(pcls, st);
+  CUtensorMap ta, tb, tc, td;
+  TRY(make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM));
+  TRY(make_tmap_bf16(&tb, B, N, K, ldb, 128));
+  TRY(make_tmap(&tc, X, true, N, M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  TRY(make_tmap(&td, XN, false, ld_xn, M, ld_xn, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+  GemmArgs a{};
+  a.M = M; a.N = N; a.kblocks = K / GEMM_BK; a.nterms = 1; a.lo_k = K;
+  a.bias = bias; a.out_f32 = X;
+  a.ln_gamma = gamma; a.ln_beta = beta; a.ln_eps = eps;
+  a.xn = reinterpret_cast<__nv_bfloat16*>(XN); a.ld_xn = ld_xn;
+  switch (cs) {
+    case 1: return launch_gemm_ln<128, 1>(ta, tb, tc, td, a, e->num_sms, st);
+    case 2: return launch_gemm_ln<128, 2>(ta, tb, tc, td, a, e->num_sms, st);
+    case 3: return launch_gemm_ln<128, 3>(ta, tb, tc, td, a, e->num_sms, st);
+    case 4: return launch_gemm_ln<128, 4>(ta, tb, tc, td, a, e->num_sms, st);
+    default: return launch_gemm_ln<128, 6>(ta, tb, tc, td, a, e->num_sms, st);
   }
 }
 
@@ -369,22 +447,43 @@ Workspace carve(const vitocm_engine* e, void* base, int tiles, int N) {
   return w;
 }
 
-// one full transformer block in place on ws.X (vit.py:106-114)
-int block_forward(const vitocm_engine* e, int l, const Workspace& ws, int B, int N, cudaStream_t st) {
+// one full transformer block in place on ws.X (vit.py:106-114).
+// xn_ready: ws.XN already holds norm1(X) of this block (produced by the previous block's fused fc2 epilogue).
+// next_ln (or null): LayerNorm parameters of the NEXT consumer of X; when the fused epilogue is available, fc2 also
+// leaves that norm's output in ws.XN and *xn_done is set.
+int block_forward(const vitocm_engine* e, int l, const Workspace& ws, int B, int N, cudaStream_t st, bool xn_ready = false,
+                  const float* next_ln_w = nullptr, const float* next_ln_b = nullptr, bool* xn_done = nullptr) {
   const LayerW& L = e->layers[l];
   const int D = e->cfg.embed_dim, Hd = e->cfg.mlp_hidden, P = e->parts, S = e->split;
   const int M = B * N;
-  TRY(run_layernorm(ws.X, L.ln1w, L.ln1b, ws.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
+  if (xn_done != nullptr) *xn_done = false;
+  if (!xn_ready) TRY(run_layernorm(ws.X, L.ln1w, L.ln1b, ws.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
   TRY(run_gemm(e, ws.XN, 2LL * D, L.wqkv.p, static_cast<long long>(D) * P, M, 3 * D, D, S, EPI_BIAS_BF16, L.bqkv, ws.QKV,
                3LL * D * P, S, 3 * D, st, PC_GEMM_QKV));
   TRY(run_attention(e, ws.QKV, 3LL * D * P, B, N, ws.CTX, static_cast<long long>(D) * P, st));
-  TRY(run_gemm(e, ws.CTX, static_cast<long long>(D) * P, L.wproj.p, static_cast<long long>(D) * P, M, D, D, S,
-               EPI_BIAS_RESID_F32, L.bproj, ws.X, D, 0, 0, st, PC_GEMM_PROJ));
-  TRY(run_layernorm(ws.X, L.ln2w, L.ln2b, ws.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
+  // proj + residual (+ norm2 fused when possible)
+  int rc = run_gemm_ln(e, ws.CTX, static_cast<long long>(D) * P, L.wproj.p, static_cast<long long>(D) * P, M, D, D, L.bproj, ws.X,
+                       L.ln2w, L.ln2b, e->cfg.ln_eps, ws.XN, 2LL * D, st, PC_GEMM_PROJ);
+  if (rc < 0) return rc;
+  if (rc == 1) {
+    TRY(run_gemm(e, ws.CTX, static_cast<long long>(D) * P, L.wproj.p, static_cast<long long>(D) * P, M, D, D, S,
+                 EPI_BIAS_RESID_F32, L.bproj, ws.X, D, 0, 0, st, PC_GEMM_PROJ));
+    TRY(run_layernorm(ws.X, L.ln2w, L.ln2b, ws.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
+  }
   TRY(run_gemm(e, ws.XN, 2LL * D, L.w1.p, static_cast<long long>(D) * P, M, Hd, D, S, EPI_BIAS_GELU_BF16, L.b1, ws.HID,
                static_cast<long long>(Hd) * P, S, Hd, st, PC_GEMM_FC1));
-  TRY(run_gemm(e, ws.HID, static_cast<long long>(Hd) * P, L.w2.p, static_cast<long long>(Hd) * P, M, D, Hd, S,
-               EPI_BIAS_RESID_F32, L.b2, ws.X, D, 0, 0, st, PC_GEMM_FC2));
+  // fc2 + residual (+ the next block's norm1 fused when possible)
+  rc = 1;
+  if (next_ln_w != nullptr)
+    rc = run_gemm_ln(e, ws.HID, static_cast<long long>(Hd) * P, L.w2.p, static_cast<long long>(Hd) * P, M, D, Hd, L.b2, ws.X, next_ln_w,
+                     next_ln_b, e->cfg.ln_eps, ws.XN, 2LL * D, st, PC_GEMM_FC2);
+  if (rc < 0) return rc;
+  if (rc == 1) {
+    TRY(run_gemm(e, ws.HID, static_cast<long long>(Hd) * P, L.w2.p, static_cast<long long>(Hd) * P, M, D, Hd, S,
+                 EPI_BIAS_RESID_F32, L.b2, ws.X, D, 0, 0, st, PC_GEMM_FC2));
+  } else if (xn_done != nullptr) {
+    *xn_done = true;
+  }
   return 0;
 }
 
@@ -519,7 +618,19 @@ int vitocm_finalize_weights(vitocm_engine* e) {
 
 size_t vitocm_workspace_bytes(const vitocm_engine* e, int chunk_tiles, int n_tokens) {
   if (e == nullptr || chunk_tiles <= 0 || n_tokens <= 0) return 0;
-  return carve(e, nullptr, chunk_tiles, n_tokens).total + 1024;
+  return carve(e, nullptr, chunk_tiles, n_tokens).total * e->lanes + 1024;
+}
+
+int vitocm_set_concurrency(vitocm_engine* e, int lanes) {
+  if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
+  if (lanes < 1 || lanes > vitocm_engine::MAX_LANES) return fail(VITOCM_ERR_INVALID, "lanes must be in [1, %d]", vitocm_engine::MAX_LANES);
+  if (e->ev_fork == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < lanes - 1; ++i) {
+    if (e->aux[i] == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&e->aux[i], cudaStreamNonBlocking));
+    if (e->ev_join[i] == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
+  }
+  e->lanes = lanes;
+  return 0;
 }
 
 int vitocm_prepare_tokens(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const float* mask,
@@ -538,10 +649,15 @@ int vitocm_forward_cls_attn(vitocm_engine* e, const float* x, int B, int H, int 
   const int N = (H / p) * (W / p) + 1;
   if (chunk_tiles <= 0) return fail(VITOCM_ERR_INVALID, "chunk_tiles must be positive");
   if (chunk_tiles > B) chunk_tiles = B;
-  void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
   const size_t avail = ws_bytes - (reinterpret_cast<uintptr_t>(base) - reinterpret_cast<uintptr_t>(ws));
-  const Workspace wsp = carve(e, base, chunk_tiles, N);
-  if (ws == nullptr || wsp.total > avail) return fail(VITOCM_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", wsp.total + 1024, ws_bytes);
+  const size_t lane_bytes = carve(e, base, chunk_tiles, N).total;
+  if (ws == nullptr || lane_bytes > avail) return fail(VITOCM_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", lane_bytes + 1024, ws_bytes);
+  // as many concurrent lanes as configured, as the workspace holds, and as there are chunks
+  int lanes = e->lanes;
+  if (static_cast<size_t>(lanes) * lane_bytes > avail) lanes = static_cast<int>(avail / lane_bytes);
+  const int n_chunks = (B + chunk_tiles - 1) / chunk_tiles;
+  if (lanes > n_chunks) lanes = n_chunks;
   const LayerW& last = e->layers[e->cfg.depth - 1];
   const size_t cls_smem = static_cast<size_t>(D + 64 + N + 32) * sizeof(float);
   static size_t cls_smem_set = 0;
@@ -549,20 +665,57 @@ int vitocm_forward_cls_attn(vitocm_engine* e, const float* x, int B, int H, int 
     CUDA_TRY(cudaFuncSetAttribute(cls_attn_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cls_smem)));
     cls_smem_set = cls_smem;
   }
-  for (int b0 = 0; b0 < B; b0 += chunk_tiles) {
-    const int bc = (B - b0 < chunk_tiles) ? (B - b0) : chunk_tiles;
-    const int M = bc * N;
-    TRY(run_patch_embed(e, x + static_cast<long long>(b0) * C * H * W, bc, H, W, pos, nullptr, wsp.X, st));
-    for (int l = 0; l + 1 < e->cfg.depth; ++l) TRY(block_forward(e, l, wsp, bc, N, st));
-    // last block: LN1 (split) -> K projection in split precision -> fp32 K -> CLS-row softmax
-    float* KF = reinterpret_cast<float*>(wsp.HID);
-    TRY(run_layernorm(wsp.X, last.ln1w, last.ln1b, wsp.XN, 2LL * D, 1, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
-    TRY(run_gemm(e, wsp.XN, 2LL * D, last.wk_split.p, 2LL * D, M, D, D, 1, EPI_BIAS_F32, last.bqkv + D, KF, D, 0, 0, st, PC_GEMM_KLAST));
-    ProfScope prof(PC_CLSROW, st);
-    dim3 grid(heads, bc);
-    cls_attn_row_kernel<<<grid, 256, cls_smem, st>>>(wsp.X, last.ln1w, last.ln1b, e->cfg.ln_eps, last.wqkv_f32, last.bqkv, KF,
-                                                     out_rows + static_cast<long long>(b0) * heads * N, N, D, heads, e->cfg.qk_scale);
-    LAUNCH_CHECK();
+  cudaStream_t lane_st[vitocm_engine::MAX_LANES];
+  Workspace lane_ws[vitocm_engine::MAX_LANES];
+  for (int k = 0; k < lanes; ++k) {
+    lane_st[k] = k == 0 ? st : e->aux[k - 1];
+    lane_ws[k] = carve(e, base + static_cast<size_t>(k) * lane_bytes, chunk_tiles, N);
+  }
+  if (lanes > 1) {   // fork: the auxiliary streams start after everything already queued on the caller's stream
+    CUDA_TRY(cudaEventRecord(e->ev_fork, st));
+    for (int k = 1; k < lanes; ++k) CUDA_TRY(cudaStreamWaitEvent(lane_st[k], e->ev_fork, 0));
+  }
+  // groups of `lanes` chunks; launches are interleaved layer by layer so that the lanes advance together
+  for (int g0 = 0; g0 < B; g0 += lanes * chunk_tiles) {
+    int b0s[vitocm_engine::MAX_LANES], bcs[vitocm_engine::MAX_LANES], active = 0;
+    for (int k = 0; k < lanes; ++k) {
+      const int b0 = g0 + k * chunk_tiles;
+      if (b0 >= B) break;
+      b0s[k] = b0;
+      bcs[k] = (B - b0 < chunk_tiles) ? (B - b0) : chunk_tiles;
+      ++active;
+    }
+    for (int k = 0; k < active; ++k)
+      TRY(run_patch_embed(e, x + static_cast<long long>(b0s[k]) * C * H * W, bcs[k], H, W, pos, nullptr, lane_ws[k].X, lane_st[k]));
+    bool xn_ready[vitocm_engine::MAX_LANES] = {false, false, false, false};
+    for (int l = 0; l + 1 < e->cfg.depth; ++l) {
+      // the next block's norm1 rides on this block's fc2 epilogue -- except into the last block, whose K projection
+      // wants the split-precision (hi | lo) normalised rows
+      const bool chain = l + 2 < e->cfg.depth;
+      for (int k = 0; k < active; ++k) {
+        bool done = false;
+        TRY(block_forward(e, l, lane_ws[k], bcs[k], N, lane_st[k], xn_ready[k], chain ? e->layers[l + 1].ln1w : nullptr,
+                          chain ? e->layers[l + 1].ln1b : nullptr, &done));
+        xn_ready[k] = done;
+      }
+    }
+    for (int k = 0; k < active; ++k) {
+      // last block: LN1 (split) -> K projection in split precision -> fp32 K -> CLS-row softmax
+      const Workspace& wsp = lane_ws[k];
+      const int M = bcs[k] * N;
+      float* KF = reinterpret_cast<float*>(wsp.HID);
+      TRY(run_layernorm(wsp.X, last.ln1w, last.ln1b, wsp.XN, 2LL * D, 1, D, nullptr, 0, M, D, e->cfg.ln_eps, lane_st[k]));
+      TRY(run_gemm(e, wsp.XN, 2LL * D, last.wk_split.p, 2LL * D, M, D, D, 1, EPI_BIAS_F32, last.bqkv + D, KF, D, 0, 0, lane_st[k], PC_GEMM_KLAST));
+      ProfScope prof(PC_CLSROW, lane_st[k]);
+      dim3 grid(heads, bcs[k]);
+      cls_attn_row_kernel<<<grid, 256, cls_smem, lane_st[k]>>>(wsp.X, last.ln1w, last.ln1b, e->cfg.ln_eps, last.wqkv_f32, last.bqkv, KF,
+                                                               out_rows + static_cast<long long>(b0s[k]) * heads * N, N, D, heads, e->cfg.qk_scale);
+      LAUNCH_CHECK();
+    }
+  }
+  for (int k = 1; k < lanes; ++k) {   // join
+    CUDA_TRY(cudaEventRecord(e->ev_join[k - 1], lane_st[k]));
+    CUDA_TRY(cudaStreamWaitEvent(st, e->ev_join[k - 1], 0));
   }
   return 0;
 }
@@ -801,6 +954,14 @@ int vitocm_gemm(vitocm_engine* e, const void* A, int64_t lda, const void* B, int
                 int epilogue, const float* bias, void* out, int64_t ldo, int split_out, int lo_off, void* stream) {
   if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
   return run_gemm(e, A, lda, B, ldb, M, N, K, split_in, epilogue, bias, out, ldo, split_out, lo_off, static_cast<cudaStream_t>(stream));
+}
+
+int vitocm_gemm_ln(vitocm_engine* e, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, const float* bias,
+                   float* X, const float* gamma, const float* beta, void* XN, int64_t ld_xn, void* stream) {
+  if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
+  const int rc = run_gemm_ln(e, A, lda, B, ldb, M, N, K, bias, X, gamma, beta, e->cfg.ln_eps, XN, ld_xn, static_cast<cudaStream_t>(stream), PC_OTHER);
+  if (rc == 1) return fail(VITOCM_ERR_INVALID, "no fused GEMM+LayerNorm instantiation for N=%d (needs N/128 in {1,2,3,4,6}, bf16 engine)", N);
+  return rc;
 }
 
 int vitocm_attention(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo, void* stream) {

@@ -134,12 +134,12 @@ class VisionTransformer(nn.Module):
     """Vision Transformer whose forward passes run in libvitocm (B200 / sm_100a).
 
     Constructor signature follows the reference (vit.py:137-139); ``precision`` ("bf16" |
-    "fp32") and ``chunk_tiles`` are additions.  Dropout / stochastic depth must be 0 (the
+    "fp32"), ``chunk_tiles`` (tiles per kernel launch) and ``lanes`` (chunks in flight on concurrent streams) are additions.  Dropout / stochastic depth must be 0 (the
     reference's inference and MIM configurations all use 0)."""
 
     def __init__(self, img_size=[224], patch_size=16, in_chans=3, num_classes=0, embed_dim=768, depth=12,
                  num_heads=12, mlp_ratio=4., qkv_bias=False, qk_scale=None, drop_rate=0., attn_drop_rate=0.,
-                 drop_path_rate=0., norm_layer=nn.LayerNorm, precision="bf16", chunk_tiles=64, **kwargs):
+                 drop_path_rate=0., norm_layer=nn.LayerNorm, precision="bf16", chunk_tiles=64, lanes=1, **kwargs):
         super().__init__()
         if drop_rate or attn_drop_rate or drop_path_rate:
             raise NotImplementedError("vitocm: dropout / drop-path rates must be 0 on this path")
@@ -154,6 +154,7 @@ class VisionTransformer(nn.Module):
         self.in_chans = in_chans
         self.precision = precision
         self.chunk_tiles = chunk_tiles
+        self.lanes = int(lanes)          # chunks processed concurrently by cls_attention_rows (vitocm_set_concurrency)
         self.qk_scale = qk_scale or (embed_dim // num_heads) ** -0.5
 
         self.patch_embed = _PatchEmbed(img_size[0], patch_size, in_chans, embed_dim)
@@ -220,6 +221,7 @@ class VisionTransformer(nn.Module):
             handle = C.c_void_p()
             check(lib.vitocm_create(C.byref(cfg), C.byref(handle)))
             self._engine = handle
+            check(lib.vitocm_set_concurrency(handle, self.lanes))
         for name, p in self._engine_params():
             host = p.detach().to(device="cpu", dtype=torch.float32).contiguous()
             check(lib.vitocm_load_weight(self._engine, name.encode(), host.data_ptr(), host.numel()))
