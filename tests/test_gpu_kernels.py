@@ -112,6 +112,27 @@ def test_gemm_fused_residual_layernorm(engine, M, N, K):
     assert torch.isnan(xn[:, N:].float()).all()                                   # lo half untouched
 
 
+@pytest.mark.parametrize("M,N,K,epi", [(70000, 1152, 384, 0), (66000, 1536, 384, 1), (5000, 384, 1536, 2), (4100, 256, 1024, 3),
+                                       (65537, 128, 64, 0)])
+def test_gemm_cta_pair_mode(engine, M, N, K, epi):
+    """Shapes that take the cta_group::2 kernel (CTA pairs on 256-row tiles, each CTA staging half of the B tile)."""
+    A = _rand((M, K), 50).to(torch.bfloat16)
+    B = _rand((N, K), 51, 0.05).to(torch.bfloat16)
+    bias = _rand((N,), 52, 0.1)
+    prod = A.float() @ B.float().T + bias
+    if epi <= 1:
+        out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        gemm(engine, A, B, M, N, K, 0, epi, bias, out, N)
+        ref = torch.nn.functional.gelu(prod) if epi == 1 else prod
+        assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
+    else:
+        resid = _rand((M, N), 53)
+        out = resid.clone() if epi == 2 else torch.full((M, N), float("nan"), device="cuda")
+        gemm(engine, A, B, M, N, K, 0, epi, bias, out, N)
+        ref = resid + prod if epi == 2 else prod
+        assert (out - ref).abs().max().item() <= 2e-4 * ref.abs().max().item() + 1e-5
+
+
 def test_gemm_split_precision_is_fp32_grade(engine):
     M, N, K = 785, 384, 384
     A32, B32 = _rand((M, K), 11), _rand((N, K), 12, 0.05)

@@ -75,6 +75,7 @@ __host__ __device__ constexpr int gemm_threads(int BN, int EPI) {
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 
 constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_PAIR_DEFAULT = 1;        // cta_group::2 for eligible shapes (VITOCM_GEMM_PAIR overrides)
 constexpr int GEMM_RES_MAX_KBLOCKS = 6;     // B_RES: K <= 384
 
 // B_RES ("weight panel resident"): for K <= 384 the whole [BN x K] weight panel stays in shared memory while the
@@ -88,11 +89,14 @@ constexpr int GEMM_RES_MAX_KBLOCKS = 6;     // B_RES: K <= 384
 // memory, and after a cluster-scope mbarrier round combines the (EPI_WARPS/4 * CS) partials with Chan's formula --
 // full-row statistics without ever re-reading the row.  The separate LayerNorm kernel (one HBM pass over the fp32
 // residual stream per LayerNorm) disappears.
-template <int BN, int EPI, bool B_RES = false, int CS = 1>
+// PAIR (cta_group::2): two CTAs of a cluster share one 256 x BN tile -- each stages its own 128 rows of A and only
+// BN/2 rows of B per k-block, so the per-SM operand traffic drops from (128 + BN) to (128 + BN/2) rows per 2*BN
+// tensor clocks (96 -> 64 B/clk/SM at BN = 256): the plain kernel is L2->SM bandwidth bound.
+template <int BN, int EPI, bool B_RES = false, int CS = 1, bool PAIR = false>
 struct GemmCfg {
   static constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16);
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;       // 16 KB
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + (B_RES ? 0 : B_BYTES);
   // per-warp epilogue staging: 2 x (32 x 32 fp32 box) or 2 x (32 x 32 bf16 box), double buffered; with a split
   // bf16 output the two bf16 boxes hold hi and lo instead (single buffered -- the parity mode is not the fast
@@ -150,12 +154,14 @@ __device__ __forceinline__ void gelu_sigmoid_x2(float& x0, float& x1) {
   ptx::unpack_f32x2(r, x0, x1);
 }
 
-template <int BN, int EPI, bool A_PATCH, bool B_RES = false, int CS = 1>
+template <int BN, int EPI, bool A_PATCH, bool B_RES = false, int CS = 1, bool PAIR = false>
 __global__ void __launch_bounds__(gemm_threads(BN, EPI), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_d, const GemmArgs args) {
-  using Cfg = GemmCfg<BN, EPI, B_RES, CS>;
+  using Cfg = GemmCfg<BN, EPI, B_RES, CS, PAIR>;
   constexpr bool LN = EPI == EPI_RESID_LN;
+  static_assert(!(PAIR && (LN || A_PATCH || B_RES)), "cta_group::2 uses the plain pipeline and epilogues");
+  constexpr int TILE_M = PAIR ? 2 * GEMM_BM : GEMM_BM;   // rows per tile (per CTA pair in PAIR mode)
   static_assert(LN || CS == 1, "clusters are only used by the fused-LayerNorm epilogue");
   static_assert(!(LN && (A_PATCH || B_RES)), "fused LayerNorm uses the plain pipeline");
   static_assert(!(A_PATCH && B_RES), "patch embedding uses the plain pipeline");
@@ -180,18 +186,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tiles_m = (args.M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_m = (args.M + TILE_M - 1) / TILE_M;
   const int tiles_n = args.N / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int k_iters = args.kblocks * args.nterms;
   // tile schedule.  plain: m-major, strided over the persistent grid.  B_RES: n-major, one contiguous range per CTA
   // (so that a CTA changes weight panel at most a couple of times).
   // LN: cluster c walks row tiles c, c + num_clusters, ...; the CTA of rank r owns column tile r of each.
-  const int cta_rank = LN ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int cta_rank = (LN || PAIR) ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   const int tile_begin = LN ? static_cast<int>(blockIdx.x) / CS
+                            : PAIR ? static_cast<int>(blockIdx.x) / 2
                             : (B_RES ? static_cast<int>(static_cast<long long>(blockIdx.x) * num_tiles / gridDim.x) : static_cast<int>(blockIdx.x));
   const int tile_end = LN ? tiles_m : (B_RES ? static_cast<int>(static_cast<long long>(blockIdx.x + 1) * num_tiles / gridDim.x) : num_tiles);
-  const int tile_step = LN ? args.num_clusters : (B_RES ? 1 : static_cast<int>(gridDim.x));
+  const int tile_step = LN ? args.num_clusters : PAIR ? static_cast<int>(gridDim.x) / 2 : (B_RES ? 1 : static_cast<int>(gridDim.x));
+  const int pair_row = PAIR ? cta_rank * GEMM_BM : 0;   // this CTA's rows inside the 256-row pair tile
   auto tile_m = [&](int t) { return LN ? t : (B_RES ? t % tiles_m : t / tiles_n); };
   auto tile_n = [&](int t) { return LN ? cta_rank : (B_RES ? t / tiles_m : t % tiles_n); };
 
@@ -208,7 +216,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar + 8 * s, 1);
-      ptx::mbar_init(tempty_bar + 8 * s, Cfg::EPI_WARPS);  // one arrive per epilogue warp
+      ptx::mbar_init(tempty_bar + 8 * s, Cfg::EPI_WARPS * (PAIR ? 2 : 1));  // one arrive per epilogue warp (of both CTAs)
     }
     ptx::mbar_init(bfull_bar, 1);
     ptx::mbar_init(bempty_bar, 1);
@@ -218,12 +226,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (PAIR) {
+      ptx::tmem_alloc_2cta(tmem_ptr_smem, Cfg::TMEM_COLS);
+      ptx::tmem_relinquish_2cta();
+    } else {
+      ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (LN && CS > 1) ptx::cluster_sync_all();   // peers' barriers are initialised before anyone arrives on them remotely
+  if ((LN && CS > 1) || PAIR) ptx::cluster_sync_all();   // peers' barriers are initialised before anyone arrives on them remotely
   ptx::tc_fence_after();
   const uint32_t tmem_base = ptx::lds_u32(tmem_ptr_smem);
 
@@ -234,8 +247,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       int cur_n = -1, panels = 0;
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-        const int m0 = tile_m(tile) * GEMM_BM;
-        const int n0 = tile_n(tile) * BN;
+        const int m0 = tile_m(tile) * TILE_M + pair_row;
+        const int n0 = tile_n(tile) * BN + (PAIR ? cta_rank * (BN / 2) : 0);   // PAIR: this CTA stages its half of the B tile
         if (B_RES && tile_n(tile) != cur_n) {
           // (re)load the weight panel: kblocks boxes [BN x 64] -> smem_b, once the MMAs on the old panel retired
           if (panels > 0) ptx::mbar_wait(bempty_bar, (panels - 1) & 1, 6);
@@ -251,12 +264,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const int term = A_PATCH ? it % args.nterms : it / args.kblocks;
           const int kb = A_PATCH ? it / args.nterms : it - term * args.kblocks;
           ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1, 1);
-          ptx::mbar_arrive_expect_tx(full_bar + 8 * stage, A_PATCH ? Cfg::B_BYTES : Cfg::STAGE_BYTES);
           // split mode terms: (hi,hi) (hi,lo) (lo,hi); lo halves start at column K of each operand
           const int a_off = (term == 2 ? args.lo_k : 0) + kb * GEMM_BK;
           const int b_off = (term == 1 ? args.lo_k : 0) + kb * GEMM_BK;
-          if (!A_PATCH) ptx::tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, full_bar + 8 * stage, a_off, m0);
-          if (!B_RES) ptx::tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, full_bar + 8 * stage, b_off, n0);
+          if (PAIR) {
+            // both CTAs load into their own stage; all bytes complete on the leader's full barrier
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * Cfg::STAGE_BYTES);
+            ptx::tma_load_2d_2cta(smem_a + stage * Cfg::A_BYTES, &tmap_a, full_bar + 8 * stage, a_off, m0);
+            ptx::tma_load_2d_2cta(smem_b + stage * Cfg::B_BYTES, &tmap_b, full_bar + 8 * stage, b_off, n0);
+          } else {
+            ptx::mbar_arrive_expect_tx(full_bar + 8 * stage, A_PATCH ? Cfg::B_BYTES : Cfg::STAGE_BYTES);
+            if (!A_PATCH) ptx::tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, full_bar + 8 * stage, a_off, m0);
+            if (!B_RES) ptx::tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, full_bar + 8 * stage, b_off, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -265,8 +285,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ===================== MMA issuer =====================
     // One elected thread issues (elect.sync lets ptxas emit the tcgen05 instructions without a per-instruction
     // leader-election loop); descriptors are advanced by compile-time constants in fully unrolled loops.
-    if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc(GEMM_BM, BN, false, false);
+    if ((!PAIR || cta_rank == 0) && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc(TILE_M, BN, false, false);
       const uint64_t a_desc0 = ptx::make_smem_desc_sw128(smem_a, 1024, 0);
       const uint64_t b_desc0 = ptx::make_smem_desc_sw128(smem_b, 1024, 0);
       int stage = 0;
@@ -289,13 +309,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint64_t adesc = ptx::desc_advance(a_desc0, stage * Cfg::A_BYTES);
           const uint64_t bdesc = ptx::desc_advance(b_desc0, (B_RES ? it : stage) * Cfg::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            ptx::umma_bf16_ss(d_tmem, ptx::desc_advance(adesc, k * 32), ptx::desc_advance(bdesc, k * 32), idesc,
-                              (it > 0 || k > 0) ? 1u : 0u);
-          ptx::umma_commit(empty_bar + 8 * stage);  // smem slot reusable once these MMAs retire
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            if (PAIR) ptx::umma_bf16_ss_2cta(d_tmem, ptx::desc_advance(adesc, k * 32), ptx::desc_advance(bdesc, k * 32), idesc, (it > 0 || k > 0) ? 1u : 0u);
+            else ptx::umma_bf16_ss(d_tmem, ptx::desc_advance(adesc, k * 32), ptx::desc_advance(bdesc, k * 32), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          // smem slot reusable once these MMAs retire (PAIR: in both CTAs)
+          if (PAIR) ptx::umma_commit_2cta(empty_bar + 8 * stage); else ptx::umma_commit(empty_bar + 8 * stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(tfull_bar + 8 * as);  // accumulator complete
+        // accumulator complete (PAIR: each CTA's epilogue waits on its own copy of the barrier)
+        if (PAIR) ptx::umma_commit_2cta(tfull_bar + 8 * as); else ptx::umma_commit(tfull_bar + 8 * as);
         if (B_RES && (tile + 1 >= tile_end || tile_n(tile + 1) != cur_n)) ptx::umma_commit(bempty_bar);  // panel free
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
@@ -379,7 +402,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint32_t aphase = 0;
     int ln_tiles = 0;
     for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-      const int m0 = tile_m(tile) * GEMM_BM;
+      const int m0 = tile_m(tile) * TILE_M + pair_row;
       const int n0 = tile_n(tile) * BN;
       const int row_base = m0 + q * 32;
       const int col_base = n0 + half * COLS_PER_WARP;
@@ -626,10 +649,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           ptx::bulk_commit();
         }
       }
-      // accumulator stage fully read into registers -> hand it back to the MMA warp
+      // accumulator stage fully read into registers -> hand it back to the MMA warp (PAIR: the leader CTA's)
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar + 8 * as);
+      if (lane == 0) {
+        if (PAIR) ptx::mbar_arrive_leader(tempty_bar + 8 * as); else ptx::mbar_arrive(tempty_bar + 8 * as);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (lane == 0) ptx::bulk_wait_all0();   // global writes complete before the CTA exits
@@ -637,10 +662,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (LN && CS > 1) ptx::cluster_sync_all();   // no CTA leaves while a peer could still address its shared memory
+  if ((LN && CS > 1) || PAIR) ptx::cluster_sync_all();   // no CTA leaves while a peer could still address its shared memory / TMEM
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (PAIR) ptx::tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS); else ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

@@ -207,6 +207,45 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- cta_group::2: the tensor cores of a CTA pair (cluster ranks 2i, 2i+1) compute one 256 x N tile; each CTA holds
+// its own 128 rows of A and HALF of the B tile (N/2 rows), the accumulator rows of each CTA live in its own TMEM.
+// Issued by one thread of the even ("leader") CTA; smem descriptors carry the same offsets in both CTAs.
+__device__ __forceinline__ void umma_bf16_ss_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (count 1) on the barrier at this offset in BOTH CTAs of the pair once all prior MMAs completed
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address -> same offset in the even CTA of the pair
+// TMA load into this CTA's smem whose transaction bytes complete on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the leader CTA's barrier at this offset (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t smem_dst, uint32_t ncols) {  // one full warp in each CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 // mbarrier arrives (count 1) once all previously issued tcgen05.mma of this thread completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -237,6 +237,47 @@ int launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   return 0;
 }
 
+// cta_group::2 variant: clusters of two CTAs share 256 x BN tiles (see GemmCfg)
+template <int BN, int EPI>
+int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& a, int num_sms, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, EPI, false, 1, true>;
+  static int max_pairs = -1;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, false, false, 1, true>;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(gemm_threads(BN, EPI));
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (max_pairs < 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    cfg.gridDim = dim3(2 * (num_sms / 2));
+    int n = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    if (n < 1) return fail(VITOCM_ERR_CUDA, "no CTA pair of the cta_group::2 GEMM fits on this device");
+    max_pairs = n < num_sms / 2 ? n : num_sms / 2;
+  }
+  const int tiles = ((a.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * (a.N / BN);
+  cfg.gridDim = dim3(2 * (tiles < max_pairs ? tiles : max_pairs));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tc, a));
+  LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+int launch_gemm_pair_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& a, int num_sms,
+                        cudaStream_t st) {
+  switch (epi) {
+    case EPI_BIAS_BF16: return launch_gemm_pair<BN, EPI_BIAS_BF16>(ta, tb, tc, a, num_sms, st);
+    case EPI_BIAS_GELU_BF16: return launch_gemm_pair<BN, EPI_BIAS_GELU_BF16>(ta, tb, tc, a, num_sms, st);
+    case EPI_BIAS_RESID_F32: return launch_gemm_pair<BN, EPI_BIAS_RESID_F32>(ta, tb, tc, a, num_sms, st);
+    case EPI_BIAS_F32: return launch_gemm_pair<BN, EPI_BIAS_F32>(ta, tb, tc, a, num_sms, st);
+  }
+  return fail(VITOCM_ERR_INVALID, "unknown GEMM epilogue %d", epi);
+}
+
 template <int BN>
 int launch_gemm_bn(int epi, bool res, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& a,
                    int num_sms, cudaStream_t st) {
@@ -286,6 +327,25 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
   if (K % GEMM_BK != 0) return fail(VITOCM_ERR_INVALID, "GEMM K=%d must be a multiple of %d", K, GEMM_BK);
   if (N % 64 != 0) return fail(VITOCM_ERR_INVALID, "GEMM N=%d must be a multiple of 64", N);
   if (bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15) != 0) return fail(VITOCM_ERR_INVALID, "GEMM bias must be 16-byte aligned");
+  // cta_group::2 (CTA pairs on 256-row tiles): single-bf16 operands, enough rows to fill the pairs
+  static const int pair_mode = [] { const char* v = getenv("VITOCM_GEMM_PAIR"); return v ? atoi(v) : GEMM_PAIR_DEFAULT; }();
+  // measured (profiles/r01_gemm_pair.txt): pairs win once the launch is long enough to amortise the cluster lockstep
+  // (M = 137k: qkv +21 %, fc2 +6 %, fc1 +3 %) and for long K at any size; mode 2 forces pairs wherever legal
+  const bool pair_pays = pair_mode == 2 || M >= 65536 || (K >= 1024 && M >= 4096);
+  if (pair_mode != 0 && pair_pays && !split_in && !split_out && M >= 4 * GEMM_BM && (N % 256 == 0 || N % 192 == 0 || N % 128 == 0)) {
+    const int pbn = N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 128);
+    const bool of32 = (epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_F32);
+    CUtensorMap pa, pb, pc;
+    TRY(make_tmap_bf16(&pa, A, M, K, lda, GEMM_BM));
+    TRY(make_tmap_bf16(&pb, B, N, K, ldb, pbn / 2));
+    TRY(make_tmap(&pc, out, of32, ldo, M, ldo, 32, 32, of32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
+    GemmArgs pg{};
+    pg.M = M; pg.N = N; pg.kblocks = K / GEMM_BK; pg.nterms = 1; pg.lo_k = K; pg.bias = bias; pg.out_f32 = reinterpret_cast<float*>(out);
+    { static const int dbgp = [] { const char* v = getenv("VITOCM_GEMM_DEBUG"); return v ? atoi(v) : 0; }(); pg.debug = dbgp; }
+    if (pbn == 256) return launch_gemm_pair_bn<256>(epi, pa, pb, pc, pg, e->num_sms, st);
+    if (pbn == 192) return launch_gemm_pair_bn<192>(epi, pa, pb, pc, pg, e->num_sms, st);
+    return launch_gemm_pair_bn<128>(epi, pa, pb, pc, pg, e->num_sms, st);
+  }
   static const bool allow_res = [] { const char* v = getenv("VITOCM_GEMM_RESIDENT"); return v == nullptr || atoi(v) != 0; }();
   // weight panel resident in smem: single-bf16 operands, K <= 384, tile width 192 or 128
   bool res = allow_res && !split_in && !split_out && K / GEMM_BK <= GEMM_RES_MAX_KBLOCKS && (N % 128 == 0 || N % 192 == 0);
