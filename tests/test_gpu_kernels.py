@@ -190,6 +190,27 @@ def test_attention(B, H, N, precision):
     vob._lib.load_library().vitocm_destroy(eng)
 
 
+@pytest.mark.parametrize("gain", [6.0, 60.0])
+def test_attention_rising_logits_rescale_and_redo(gain):
+    """Logits that grow along the key axis: later KV blocks exceed the running row maximum by 2^8 (lazy rescale of
+    O / l before the next block) and, at the larger gain, by more than 2^60 inside one block (the block is redone
+    against the raised maximum instead of overflowing exp2)."""
+    B, H, N, precision = 1, 2, 600, 0
+    eng = make_engine(embed_dim=64 * H, heads=H, precision=precision)
+    D = 64 * H
+    q, k, v = (_rand((B, H, N, 64), s) for s in (60, 61, 62))
+    ramp = torch.linspace(0.2, 1.0, N, device="cuda").view(1, 1, N, 1)
+    k = k * ramp * gain                                  # |logit| grows with the key index
+    qkv = torch.stack([q, k, v], 0).permute(1, 3, 0, 2, 4).reshape(B * N, 3 * D).to(torch.bfloat16).contiguous()
+    s5 = qkv.float().reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = attention_reference(s5[0], s5[1], s5[2], 0.125).reshape(B * N, D)
+    ctx = torch.full((B * N, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    attention(eng, qkv, B, N, ctx)
+    assert torch.isfinite(ctx.float()).all()
+    assert (ctx.float() - ref).abs().max().item() <= 3e-2 * max(1.0, ref.abs().max().item())
+    vob._lib.load_library().vitocm_destroy(eng)
+
+
 def test_launch_counter_counts():
     before = vob._lib.launch_count()
     eng = make_engine()

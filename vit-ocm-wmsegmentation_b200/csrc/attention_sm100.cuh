@@ -54,7 +54,8 @@ constexpr int ATT_RING = 3;
 constexpr int ATT_S_COL = 0;      // S: 128 columns (fp32)
 constexpr int ATT_O_COL = 128;    // O: 64 columns (fp32)
 constexpr int ATT_P_COL = 192;    // P: 64 columns of packed bf16x2 (128 keys); split mode: lo part in the next 64
-constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
+constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units: raise the running maximum (rescale O, l) before the next block
+constexpr float ATT_REDO_THRESHOLD = 60.0f;    // log2 units: exp2 of the current block may overflow -> redo it now
 constexpr int ATT_POLY_DEFAULT = 0;            // see run_attention (0: all MUFU, 1: 4/16 polynomial, 2: 7/16)
 
 template <bool SPLIT>
@@ -236,6 +237,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     const float sl2 = args.scale_log2;
     const uint64_t sl2_2 = ptx::dup_f32x2(sl2);
     float m_used = -INFINITY;     // the row maximum the exponentials are taken against
+    float m_next = -INFINITY;     // a larger maximum seen in the previous block (lazy rescale pending)
     float l_run = 0.f;            // running row sum (same units as O in TMEM)
 
     for (int j = 0; j < n_kv; ++j) {
@@ -267,50 +269,57 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
           for (int i = 0; i < 32; ++i)
             if (c * 32 + i >= kv_len) s[c][i] = 0xff800000u;
       }
-      // ---- row maximum: four independent 3-input chains
-      float mx4[4];
+      // ---- row maximum.  Block 0 needs it before any exponential (it sets the scale).  For the later blocks the
+      // exponentials are taken against the maximum already in use and this block's maximum is computed inside the
+      // same instruction stream (off the critical path): softmax is shift invariant and O / l live in fp32, so a
+      // stale maximum costs nothing until a row exceeds it by 2^ATT_RESCALE_THRESHOLD -- then O and l are rescaled
+      // before the NEXT block -- or by 2^ATT_REDO_THRESHOLD inside one block -- then this block is redone.
+      auto row_max = [&]() {
+        float mx4[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
+        for (int c = 0; c < 4; ++c) {
+          float m0 = fmaxf(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]));
 #pragma unroll
-        for (int i = 2; i < 32; i += 2) m0 = fmaxf(fmaxf(m0, __uint_as_float(s[c][i])), __uint_as_float(s[c][i + 1]));
-        mx4[c] = m0;
-      }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      // ---- lazy rescale decision
+          for (int i = 2; i < 32; i += 2) m0 = fmaxf(fmaxf(m0, __uint_as_float(s[c][i])), __uint_as_float(s[c][i + 1]));
+          mx4[c] = m0;
+        }
+        return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      };
+      if (j == 0) m_used = row_max();
+      // ---- a maximum raised by the previous block: rescale l now, O once PV_{j-1} has completed
       float alpha = 1.0f;
-      if (j == 0) {
-        m_used = mx;
-      } else if ((mx - m_used) * sl2 > ATT_RESCALE_THRESHOLD) {
-        alpha = ptx::ex2_approx((m_used - mx) * sl2);
-        m_used = mx;
+      if (m_next > m_used) {
+        alpha = ptx::ex2_approx((m_used - m_next) * sl2);
+        m_used = m_next;
         l_run *= alpha;
       }
-      const uint64_t nm2 = ptx::dup_f32x2(-m_used * sl2);
-      // ---- previous PV done: P buffer free, O valid -> rescale it if this warp raised a maximum
-      att_stamp(args, tl && warp == 0, 0, j, 3);   // row max done
+      att_stamp(args, tl && warp == 0, 0, j, 3);   // scale known
+      auto rescale_o = [&](float a) {
+#pragma unroll
+        for (int c = 0; c < ATT_DH; c += 32) {
+          uint32_t t[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + ATT_O_COL + c, t);
+          ptx::tmem_ld_wait(t);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * a);
+          ptx::tmem_st_32x32b_x32(lane_addr + ATT_O_COL + c, t);
+        }
+      };
       if (j > 0) {
-        ptx::mbar_wait(o_full, (j - 1) & 1, 20);
+        ptx::mbar_wait(o_full, (j - 1) & 1, 20);   // PV_{j-1} done: the P columns are free, O is complete up to j-1
         ptx::tc_fence_after();
         att_stamp(args, tl && warp == 0, 0, j, 4); // PV_{j-1} complete
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll
-          for (int c = 0; c < ATT_DH; c += 32) {
-            uint32_t t[32];
-            ptx::tmem_ld_32x32b_x32(lane_addr + ATT_O_COL + c, t);
-            ptx::tmem_ld_wait(t);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
-            ptx::tmem_st_32x32b_x32(lane_addr + ATT_O_COL + c, t);
-          }
-        }
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) rescale_o(alpha);
       }
       // ---- p = exp2(s*sl2 - m*sl2) -> bf16 pairs -> TMEM columns P_COL + key/2 of this thread's lane
-      // (the A operand of the PV MMA).  In bf16 mode 7 of every 16 pairs take the FMA-pipe polynomial instead
-      // of MUFU.EX2 so that the two pipes finish together (full blocks only: the ragged block carries -inf).
-      uint64_t sum2[2] = {0ull, 0ull};
+      // (the A operand of the PV MMA).  Optionally some pairs take the FMA-pipe polynomial instead of MUFU.EX2
+      // (full blocks only: the ragged block carries -inf).
+      uint64_t sum2[2];
       auto exp_chunks = [&](auto poly_tag) {
         constexpr bool POLY = decltype(poly_tag)::value;
+        const uint64_t nm2 = ptx::dup_f32x2(-m_used * sl2);
+        sum2[0] = 0ull;
+        sum2[1] = 0ull;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c < nchunks) {
@@ -336,7 +345,25 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
           }
         }
       };
-      if (!SPLIT && POLY_MASK != 0 && kv_len == ATT_BKV) exp_chunks(std::true_type{}); else exp_chunks(std::false_type{});
+      auto run_exps = [&]() {
+        if (!SPLIT && POLY_MASK != 0 && kv_len == ATT_BKV) exp_chunks(std::true_type{}); else exp_chunks(std::false_type{});
+      };
+      run_exps();
+      if (j > 0) {
+        const float excess = (row_max() - m_used) * sl2;       // independent of the exponentials above: overlaps them
+        if (__any_sync(0xffffffffu, excess > ATT_REDO_THRESHOLD)) {
+          // rare: a row jumped so far above the running maximum that exp2 may have overflowed -> raise the maximum
+          // now (O is complete up to block j-1 and may be rescaled here) and redo this block's exponentials
+          const float m_new = excess > ATT_REDO_THRESHOLD ? m_used + excess / sl2 : m_used;
+          const float a = ptx::ex2_approx((m_used - m_new) * sl2);
+          m_used = m_new;
+          l_run *= a;
+          rescale_o(a);
+          run_exps();
+        } else if (excess > ATT_RESCALE_THRESHOLD) {
+          m_next = m_used + excess / sl2;                        // applied before the next block
+        }
+      }
       {
         float a0, a1, b0, b1;
         ptx::unpack_f32x2(sum2[0], a0, a1);
