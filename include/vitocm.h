@@ -200,6 +200,49 @@ int vitocm_attention_timeline(vitocm_engine* e, const void* qkv, int64_t ld, int
 /* LayerNorm rows of X [M][D] fp32 with affine (gamma, beta) -> out bf16 [M][ldo] (hi | lo if split). */
 int vitocm_layernorm(vitocm_engine* e, const float* X, const float* gamma, const float* beta, void* out_bf16,
                      int64_t ldo, int split, int lo_off, int M, void* stream);
+/* ---- MIM training step (SSS/mim.py:153-182; model.py:71-77 under autograd).  bf16 engines only. ---- */
+
+/* Master weights owned by the caller (training): `name` as in vitocm_load_weight, dev_data = DEVICE fp32, 16-byte aligned,
+ * used in place (no copy) -- an optimizer updates it and vitocm_refresh_weights repacks the bf16 operand copies on
+ * `stream` without synchronising.  The first use still needs one vitocm_finalize_weights. */
+int vitocm_bind_weight(vitocm_engine* e, const char* name, float* dev_data, int64_t numel);
+int vitocm_refresh_weights(vitocm_engine* e, void* stream);
+/* Where vitocm_mim_backward ACCUMULATES dL/d(name) (fp32, same shape as the parameter; the caller zeroes it, like
+ * optimizer.zero_grad(), mim.py:173).  NULL unbinds. */
+int vitocm_bind_grad(vitocm_engine* e, const char* name, float* dev_grad);
+
+size_t vitocm_mim_train_workspace_bytes(const vitocm_engine* e, int B, int n_tokens);
+/* MIM.forward (model.py:71-77) for one batch, keeping the activations the backward needs in ws (same arguments as
+ * vitocm_mim_forward; the whole batch is one chunk). */
+int vitocm_mim_train_forward(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const float* mask,
+                             float* x_rec, double* loss_sums, void* ws, size_t ws_bytes, void* stream);
+/* loss.backward() (mim.py:174) for the batch vitocm_mim_train_forward just ran on the same ws: gradients of
+ * grad_scale * loss are accumulated into the buffers bound with vitocm_bind_grad (all parameters except pos_embed);
+ * dpos [N][D] fp32 is WRITTEN with the gradient of the (interpolated) position table passed to the forward. */
+int vitocm_mim_backward(vitocm_engine* e, const float* x, int B, int H, int W, const float* mask, const float* x_rec,
+                        const double* loss_sums, float grad_scale, float* dpos, void* ws, size_t ws_bytes, void* stream);
+
+/* torch.nn.utils.clip_grad_norm_ (mim.py:176), first half: out[0] = sum g^2 over a flat fp32 gradient buffer (fp64). */
+int vitocm_grad_sumsq(const float* g, int64_t n, double* out, void* stream);
+/* Second half fused with torch.optim.AdamW.step (optimizer.py:73-75) over flat fp32 buffers of n elements:
+ * g <- g * grad_scale * min(1, max_norm / (sqrt(*sumsq) * grad_scale + 1e-6)) (max_norm <= 0 or sumsq NULL: no clipping),
+ * then the decoupled-weight-decay Adam update with bias correction for step number `step` (1-based); decay[i] != 0
+ * selects weight decay per element (none for 1-D parameters and biases, optimizer.py:14-33). */
+int vitocm_adamw_step(float* p, float* g, float* m, float* v, const uint8_t* decay, int64_t n, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, int step, float max_norm, float grad_scale, const double* sumsq, void* stream);
+
+/* kernel-level: dW[R][C] (fp32) += G[M][R]^T . A[M][C], bf16 row-major activations (the weight gradient of nn.Linear) */
+int vitocm_wgrad(vitocm_engine* e, const void* G, int64_t ldg, const void* A, int64_t lda, int M, int R, int C, float* dW,
+                 void* stream);
+/* vitocm_attention that also returns lse2 [B][heads][N] = log2 sum_k exp(scale q.k) */
+int vitocm_attention_fwd_lse(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo,
+                             float* lse2, void* stream);
+/* backward of vitocm_attention: dqkv bf16 [B*N][ldq] (columns [3][H][64]) from dctx; scratch: delta [B][heads][N] fp32,
+ * dqacc [B*N][D] fp32 (zero on entry, zero again on return) */
+int vitocm_attention_bwd(vitocm_engine* e, const void* qkv, int64_t ld, const void* ctx, const void* dctx, int64_t ldc,
+                         const float* lse2, float* delta, float* dqacc, void* dqkv, int64_t ldq, int B, int n_tokens,
+                         void* stream);
+
 /* Optional per-kernel-class device timing: when enabled every launch is bracketed by CUDA events on
  * its own stream; vitocm_profile_read synchronises, sums milliseconds and launch counts per class
  * (vitocm_profile_classes() slots, names from vitocm_profile_class_name) and clears the log. */

@@ -63,6 +63,21 @@ SIGNATURES = {
     "vitocm_attention": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "vitocm_attention_timeline": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "vitocm_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "vitocm_bind_weight": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "vitocm_refresh_weights": (c_int, [c_void_p, c_void_p]),
+    "vitocm_bind_grad": (c_int, [c_void_p, c_char_p, c_void_p]),
+    "vitocm_mim_train_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "vitocm_mim_train_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_size_t, c_void_p]),
+    "vitocm_mim_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]),
+    "vitocm_grad_sumsq": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "vitocm_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_float,
+                                  c_int, c_float, c_float, c_void_p, c_void_p]),
+    "vitocm_wgrad": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vitocm_attention_fwd_lse": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "vitocm_attention_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int64, c_int, c_int, c_void_p]),
     "vitocm_launch_count": (c_int64, []),
     "vitocm_profile_enable": (c_int, [c_int]),
     "vitocm_profile_classes": (c_int, []),

@@ -1,0 +1,287 @@
+// Flash-attention backward for sm_100a (head_dim 64), tcgen05 + TMEM + TMA -- the `loss.backward()` half of
+// SSS/dino/vision_transformer.py:83-87 (q@k^T*scale, softmax, attn@v) inside the MIM training step (SSS/mim.py:153-182).
+// Nothing N x N is ever written to HBM: P is recomputed from the saved log-sum-exp of the forward pass.
+//
+//   given  dO = dL/dctx,  LSE2[q] = log2 sum_k exp(scale * q.k)  (forward),  Delta[q] = sum_d dO[q,d] * O[q,d]:
+//     P   = exp2(scale*log2e * Q K^T - LSE2)                 dV = P^T dO
+//     dP  = dO V^T                                           dK = dS^T Q
+//     dS  = scale * P o (dP - Delta)                         dQ = dS K
+//
+// One CTA = one (image b, head h, 128-key block j); it keeps K_j, V_j in shared memory, accumulates dK_j, dV_j in
+// TMEM and walks over the 128-query tiles i.  Per (i, j):
+//   MMA   S  = Q_i K_j^T, dP = dO_i V_j^T                    (K-major operands)            -> TMEM S | dP
+//   warps 0..3 (thread = query row): tcgen05.ld S, dP -> P, dS (bf16) -> shared memory, row-major [q][k]
+//   MMA   dV += P^T dO_i, dK += dS^T Q_i                     (A = P / dS read MN-major: the contraction runs over the
+//                                                             rows q; B = dO_i / Q_i MN-major)  -> TMEM dV | dK
+//   MMA   dQ_i = dS K_j                                      (A = dS K-major, B = K_j MN-major) -> TMEM dQ
+//   warps 0..3: dQ tile -> shared memory -> TMA reduce-add (fp32, done by the L2) into dQacc[b, i*128.., h*64..];
+//               a 3-D tensor map [B][N][D] clips the rows beyond the image.
+// The same shared-memory image of P / dS serves as MN-major A (dV, dK) and as K-major A (dQ): no transposes.
+// dK_j, dV_j leave through registers as bf16 into the dQKV activation; dQacc is converted by dq_convert_kernel.
+// Warp roles: warps 0..3 softmax/drain, warp 4 = TMA producer, warp 5 = MMA issuer + TMEM allocator.
+#pragma once
+#include "ptx.cuh"
+
+namespace vitocm {
+
+struct AttnBwdArgs {
+  int n_tokens;       // N
+  int embed_dim;      // D = H * 64
+  int heads;
+  float scale;        // qk scale
+  float scale_log2;   // scale * log2(e)
+  const float* lse2;  // [B][H][N]
+  const float* delta; // [B][H][N]
+  __nv_bfloat16* dqkv;  // [B*N][ld]: dK at column D + h*64, dV at 2D + h*64 (dQ comes from dq_convert_kernel)
+  long long ld;
+};
+
+constexpr int ABW_THREADS = 192;   // warps 0..3 softmax / drain, warp 4 TMA, warp 5 MMA
+constexpr int ABW_TILE = 128 * 64 * 2;          // 16 KB: [128 rows][64 bf16]
+constexpr int ABW_S_COL = 0, ABW_DP_COL = 128, ABW_DV_COL = 256, ABW_DK_COL = 320, ABW_DQ_COL = 384;
+constexpr int ABW_TMEM_COLS = 512;
+// shared memory: K | V | (Q, dO) x 2 | P (2 atoms) | dS (2 atoms) | dQ staging (4 warps x 2 boxes x 4 KB) | barriers
+constexpr int ABW_SMEM_BYTES = 2 * ABW_TILE + 4 * ABW_TILE + 2 * ABW_TILE + 2 * ABW_TILE + 32768 + 1024 + 256;
+
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tmap, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(ABW_THREADS, 1)
+attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                        const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_k = smem;
+  const uint32_t smem_v = smem_k + ABW_TILE;
+  const uint32_t smem_qdo = smem_v + ABW_TILE;            // [2 slots][Q | dO]
+  const uint32_t smem_p = smem_qdo + 4 * ABW_TILE;        // [2 atoms of 64 keys][128 q][128 B]
+  const uint32_t smem_ds = smem_p + 2 * ABW_TILE;
+  const uint32_t smem_dq = smem_ds + 2 * ABW_TILE;        // fp32 staging
+  const uint32_t bars = smem_dq + 32768;
+  const uint32_t kv_full = bars;            // K_j, V_j landed
+  const uint32_t qdo_full = bars + 8;       // [2]
+  const uint32_t qdo_empty = bars + 24;     // [2]
+  const uint32_t sdp_full = bars + 40;      // MMA -> softmax: S, dP complete
+  const uint32_t pds_full = bars + 48;      // softmax -> MMA: P, dS in shared memory (4 warps)
+  const uint32_t dq_full = bars + 56;       // MMA -> softmax: dQ_i complete (also: P / dS / dV / dK MMAs retired)
+  const uint32_t dq_empty = bars + 64;      // softmax -> MMA: dQ columns drained (4 warps)
+  const uint32_t tmem_ptr_smem = bars + 72;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int N = args.n_tokens, D = args.embed_dim;
+  const int n_q = (N + 127) / 128;
+  const int row_base = b * N;
+  int kv_len = N - j * 128;
+  kv_len = kv_len > 128 ? 128 : kv_len;
+
+  if (warp == 4 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_qkv);
+    ptx::prefetch_tmap(&tmap_do);
+    ptx::prefetch_tmap(&tmap_dq);
+    ptx::mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(qdo_full + 8 * s, 1);
+      ptx::mbar_init(qdo_empty + 8 * s, 1);
+    }
+    ptx::mbar_init(sdp_full, 1);
+    ptx::mbar_init(pds_full, 4);
+    ptx::mbar_init(dq_full, 1);
+    ptx::mbar_init(dq_empty, 4);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 5) {
+    ptx::tmem_alloc(tmem_ptr_smem, ABW_TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ptx::lds_u32(tmem_ptr_smem);
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(kv_full, 2 * ABW_TILE);
+      ptx::tma_load_2d(smem_k, &tmap_qkv, kv_full, D + h * 64, row_base + j * 128);
+      ptx::tma_load_2d(smem_v, &tmap_qkv, kv_full, 2 * D + h * 64, row_base + j * 128);
+      for (int i = 0; i < n_q; ++i) {
+        const int slot = i & 1;
+        ptx::mbar_wait(qdo_empty + 8 * slot, ((i >> 1) & 1) ^ 1, 40);
+        ptx::mbar_arrive_expect_tx(qdo_full + 8 * slot, 2 * ABW_TILE);
+        ptx::tma_load_2d(smem_qdo + slot * 2 * ABW_TILE, &tmap_qkv, qdo_full + 8 * slot, h * 64, row_base + i * 128);
+        ptx::tma_load_2d(smem_qdo + slot * 2 * ABW_TILE + ABW_TILE, &tmap_do, qdo_full + 8 * slot, h * 64, row_base + i * 128);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc_s = ptx::make_idesc(128, 128, false, false);   // S, dP: both operands K-major
+      constexpr uint32_t idesc_t = ptx::make_idesc(128, 64, true, true);      // dV, dK: A (P / dS) and B (dO / Q) MN-major
+      constexpr uint32_t idesc_q = ptx::make_idesc(128, 64, false, true);     // dQ: A = dS K-major, B = K_j MN-major
+      const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_k, 1024, 0);
+      const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_v, 1024, 0);
+      const uint64_t k_desc_mn = ptx::make_smem_desc_sw128(smem_k, 1024, 1024);
+      const uint64_t p_desc_mn = ptx::make_smem_desc_sw128(smem_p, 1024, ABW_TILE);    // 64-key atoms 16 KB apart
+      const uint64_t ds_desc_mn = ptx::make_smem_desc_sw128(smem_ds, 1024, ABW_TILE);
+      const uint64_t ds_desc_k = ptx::make_smem_desc_sw128(smem_ds, 1024, 0);
+      auto issue_sdp = [&](int i) {
+        const int slot = i & 1;
+        ptx::mbar_wait(qdo_full + 8 * slot, (i >> 1) & 1, 41);
+        ptx::tc_fence_after();
+        const uint64_t q_desc = ptx::make_smem_desc_sw128(smem_qdo + slot * 2 * ABW_TILE, 1024, 0);
+        const uint64_t do_desc = ptx::desc_advance(q_desc, ABW_TILE);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          ptx::umma_bf16_ss(tmem_base + ABW_S_COL, ptx::desc_advance(q_desc, k * 32), ptx::desc_advance(k_desc, k * 32), idesc_s, k ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          ptx::umma_bf16_ss(tmem_base + ABW_DP_COL, ptx::desc_advance(do_desc, k * 32), ptx::desc_advance(v_desc, k * 32), idesc_s, k ? 1u : 0u);
+        ptx::umma_commit(sdp_full);
+      };
+      ptx::mbar_wait(kv_full, 0, 42);
+      issue_sdp(0);
+      for (int i = 0; i < n_q; ++i) {
+        const int slot = i & 1;
+        ptx::mbar_wait(pds_full, i & 1, 43);     // P_i, dS_i in shared memory; S / dP columns read
+        ptx::tc_fence_after();
+        const uint64_t q_desc_mn = ptx::make_smem_desc_sw128(smem_qdo + slot * 2 * ABW_TILE, 1024, 1024);
+        const uint64_t do_desc_mn = ptx::desc_advance(q_desc_mn, ABW_TILE);
+        const uint32_t acc0 = i > 0 ? 1u : 0u;
+        // dV += P^T dO_i,  dK += dS^T Q_i: 16 query rows (2048 B of every atom) per MMA
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          ptx::umma_bf16_ss(tmem_base + ABW_DV_COL, ptx::desc_advance(p_desc_mn, k * 2048), ptx::desc_advance(do_desc_mn, k * 2048), idesc_t, k ? 1u : acc0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          ptx::umma_bf16_ss(tmem_base + ABW_DK_COL, ptx::desc_advance(ds_desc_mn, k * 2048), ptx::desc_advance(q_desc_mn, k * 2048), idesc_t, k ? 1u : acc0);
+        ptx::umma_commit(qdo_empty + 8 * slot);   // Q_i / dO_i no longer needed
+        // dQ_i = dS K_j: 16 keys per MMA (32 B inside a 64-key atom of dS; 2048 B of K_j)
+        if (i > 0) {
+          ptx::mbar_wait(dq_empty, (i - 1) & 1, 44);
+          ptx::tc_fence_after();
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          ptx::umma_bf16_ss(tmem_base + ABW_DQ_COL, ptx::desc_advance(ds_desc_k, (k >> 2) * ABW_TILE + (k & 3) * 32),
+                            ptx::desc_advance(k_desc_mn, k * 2048), idesc_q, k ? 1u : 0u);
+        ptx::umma_commit(dq_full);
+        if (i + 1 < n_q) issue_sdp(i + 1);        // overlaps the dQ drain of tile i
+      }
+    }
+  } else if (warp < 4) {
+    // ===================== softmax / drain warps =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;   // query row inside the tile (S, dP, dQ phases) or key row (final dK / dV drain)
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float sl2 = args.scale_log2;
+    const float* lse_bh = args.lse2 + (static_cast<long long>(b) * args.heads + h) * N;
+    const float* delta_bh = args.delta + (static_cast<long long>(b) * args.heads + h) * N;
+    const uint32_t stg = smem_dq + q * 8192;
+    for (int i = 0; i < n_q; ++i) {
+      const int qrow = i * 128 + r;
+      const bool qvalid = qrow < N;
+      const float lse = qvalid ? __ldg(lse_bh + qrow) : INFINITY;     // invalid query rows: P = 0
+      const float dlt = qvalid ? __ldg(delta_bh + qrow) : 0.f;
+      ptx::mbar_wait(sdp_full, i & 1, 45);
+      ptx::tc_fence_after();
+      // P / dS of the previous tile have been consumed: the MMA warp committed dq_full(i-1) after those MMAs and
+      // this warp waited for it before draining dQ_{i-1}
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32], dp[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + ABW_S_COL + c * 32, s);
+        ptx::tmem_ld_32x32b_x32(lane_addr + ABW_DP_COL + c * 32, dp);
+        ptx::tmem_ld_wait(s);
+        ptx::tmem_ld_wait(dp);
+        uint32_t pp[16], dd[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          float p0 = ptx::ex2_approx(fmaf(__uint_as_float(s[2 * t]), sl2, -lse));
+          float p1 = ptx::ex2_approx(fmaf(__uint_as_float(s[2 * t + 1]), sl2, -lse));
+          if (c * 32 + 2 * t >= kv_len) p0 = 0.f;
+          if (c * 32 + 2 * t + 1 >= kv_len) p1 = 0.f;
+          const float d0 = p0 * (__uint_as_float(dp[2 * t]) - dlt) * args.scale;
+          const float d1 = p1 * (__uint_as_float(dp[2 * t + 1]) - dlt) * args.scale;
+          pp[t] = ptx::pack_bf16x2(p0, p1);
+          dd[t] = ptx::pack_bf16x2(qvalid ? d0 : 0.f, qvalid ? d1 : 0.f);
+        }
+        // 32 keys = 4 chunks of 16 B in row r of atom c / 2 (SWIZZLE_128B: chunk ^ (r & 7))
+        const uint32_t off = (c >> 1) * ABW_TILE + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t ch = static_cast<uint32_t>((((c & 1) * 4 + g) ^ (r & 7)) << 4);
+          ptx::sts_v4(smem_p + off + ch, pp[4 * g], pp[4 * g + 1], pp[4 * g + 2], pp[4 * g + 3]);
+          ptx::sts_v4(smem_ds + off + ch, dd[4 * g], dd[4 * g + 1], dd[4 * g + 2], dd[4 * g + 3]);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(pds_full);
+      // ---- dQ_i: TMEM -> fp32 boxes -> reduce-add into dQacc[b, i*128 + q*32 .., h*64 ..]
+      ptx::mbar_wait(dq_full, i & 1, 46);
+      ptx::tc_fence_after();
+      uint32_t t0[32], t1[32];
+      ptx::tmem_ld_32x32b_x32(lane_addr + ABW_DQ_COL, t0);
+      ptx::tmem_ld_32x32b_x32(lane_addr + ABW_DQ_COL + 32, t1);
+      if (lane == 0) ptx::bulk_wait_read0();   // the previous tile's reduce has finished reading the boxes
+      __syncwarp();
+      ptx::tmem_ld_wait(t0);
+      ptx::tmem_ld_wait(t1);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(dq_empty);
+      const int sw = lane & 7;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        ptx::sts_v4(stg + lane * 128 + ((g ^ sw) << 4), t0[4 * g], t0[4 * g + 1], t0[4 * g + 2], t0[4 * g + 3]);
+        ptx::sts_v4(stg + 4096 + lane * 128 + ((g ^ sw) << 4), t1[4 * g], t1[4 * g + 1], t1[4 * g + 2], t1[4 * g + 3]);
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_3d(&tmap_dq, stg, h * 64, i * 128 + q * 32, b);
+        tma_reduce_add_3d(&tmap_dq, stg + 4096, h * 64 + 32, i * 128 + q * 32, b);
+        ptx::bulk_commit();
+      }
+    }
+    // ---- dK_j, dV_j: complete once dq_full of the last tile fired (the commit covers all earlier MMAs)
+    {
+      __nv_bfloat16* orow = args.dqkv + static_cast<long long>(row_base + j * 128 + r) * args.ld + h * 64;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {   // 0: dK -> column block D, 1: dV -> column block 2D
+        __nv_bfloat16* o = orow + (which == 0 ? D : 2 * D);
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t t[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + (which == 0 ? ABW_DK_COL : ABW_DV_COL) + c, t);   // warp-collective
+          ptx::tmem_ld_wait(t);
+          if (r < kv_len) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              reinterpret_cast<uint4*>(o + c)[g] =
+                  make_uint4(ptx::pack_bf16x2(__uint_as_float(t[8 * g]), __uint_as_float(t[8 * g + 1])),
+                             ptx::pack_bf16x2(__uint_as_float(t[8 * g + 2]), __uint_as_float(t[8 * g + 3])),
+                             ptx::pack_bf16x2(__uint_as_float(t[8 * g + 4]), __uint_as_float(t[8 * g + 5])),
+                             ptx::pack_bf16x2(__uint_as_float(t[8 * g + 6]), __uint_as_float(t[8 * g + 7])));
+          }
+        }
+      }
+    }
+    if (lane == 0) ptx::bulk_wait_all0();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, ABW_TMEM_COLS);
+  }
+}
+
+}  // namespace vitocm

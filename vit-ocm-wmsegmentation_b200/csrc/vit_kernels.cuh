@@ -44,7 +44,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ out_bf16, long long ldo, int split, int lo_off,
-                 float* __restrict__ out_f32, long long ldf, int M, int D, float eps) {
+                 float* __restrict__ out_f32, long long ldf, int M, int D, float eps, float* __restrict__ x_copy = nullptr) {
   constexpr int CNT = NV > 0 ? NV : LN_MAX_VEC;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -59,6 +59,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
     if (NV > 0 || idx < nvec) {
       v[i] = xr[idx];
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      // training: snapshot of the row this LayerNorm saw (its backward needs x, the residual stream moves on in place)
+      if (x_copy != nullptr) reinterpret_cast<float4*>(x_copy + static_cast<long long>(row) * D)[idx] = v[i];
     }
   }
   const float inv_d = 1.0f / static_cast<float>(D);

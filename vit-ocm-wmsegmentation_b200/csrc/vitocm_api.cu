@@ -14,10 +14,13 @@
 #include <string>
 #include <vector>
 
+#include "attention_bwd_sm100.cuh"
 #include "attention_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "post_kernels.cuh"
+#include "train_kernels.cuh"
 #include "vit_kernels.cuh"
+#include "wgrad_sm100.cuh"
 
 using namespace vitocm;
 
@@ -52,9 +55,10 @@ int fail(int code, const char* fmt, ...) {
 
 // ---- optional per-kernel-class device timing (CUDA events on the launching stream) ----
 enum ProfClass { PC_PATCH = 0, PC_LN, PC_GEMM_QKV, PC_ATTN, PC_GEMM_PROJ, PC_GEMM_FC1, PC_GEMM_FC2, PC_GEMM_KLAST, PC_CLSROW,
-                 PC_POST, PC_OTHER, PC_COUNT };
+                 PC_POST, PC_OTHER, PC_WGRAD, PC_DGRAD, PC_ATTN_BWD, PC_TRAIN_ELEM, PC_OPTIM, PC_COUNT };
 const char* const kProfNames[PC_COUNT] = {"patch_embed", "layernorm", "gemm_qkv", "attention", "gemm_proj", "gemm_fc1_gelu",
-                                          "gemm_fc2", "gemm_k_last", "cls_attn_row", "post", "other"};
+                                          "gemm_fc2", "gemm_k_last", "cls_attn_row", "post", "other", "gemm_wgrad", "gemm_dgrad",
+                                          "attention_bwd", "train_elementwise", "optimizer"};
 struct ProfRec { int cls; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
@@ -110,9 +114,16 @@ int make_tmap_bf16(CUtensorMap* tm, const void* ptr, long long rows, long long c
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
+  bool owned = true;   // false: caller-owned device memory (vitocm_bind_weight)
+  ~DevBuf() { if (p && owned) cudaFree(p); }
+  void bind(void* ptr, size_t n) {
+    if (p && owned) cudaFree(p);
+    p = ptr; bytes = n; owned = false;
+  }
   int alloc(size_t n) {
-    if (p) { cudaFree(p); p = nullptr; }
+    if (p && owned && bytes == n) return 0;   // repack in place (vitocm_refresh_weights)
+    if (p && owned) cudaFree(p);
+    p = nullptr; owned = true;
     bytes = n;
     cudaError_t e = cudaMalloc(&p, n ? n : 1);
     if (e != cudaSuccess) { p = nullptr; return fail(VITOCM_ERR_CUDA, "cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e)); }
@@ -124,6 +135,7 @@ struct DevBuf {
 struct LayerW {
   DevBuf wqkv, wproj, w1, w2;      // bf16 [rows][K * parts]  (hi | lo)
   DevBuf wk_split;                 // last layer: K rows of qkv, always split [D][2D]
+  DevBuf wqkv_t, wproj_t, w1_t, w2_t;   // bf16 [K][rows]: transposed copies, the B operand of the input-gradient GEMMs (bf16 engines)
   const float *bqkv = nullptr, *bproj = nullptr, *b1 = nullptr, *b2 = nullptr;
   const float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
   const float* wqkv_f32 = nullptr;  // master copy (q rows used by the CLS kernel)
@@ -143,6 +155,8 @@ struct vitocm_engine {
   std::vector<LayerW> layers;
   DevBuf patch_w;   // bf16 [D][2K]  (hi | lo): the conv filter as a K-major GEMM operand
   DevBuf dec_w;     // MIM decoder 1x1 conv weight, bf16 [C p^2][D * parts] (present iff "decoder.0.weight" was loaded)
+  DevBuf dec_w_t;   // bf16 [D][C p^2] (training)
+  std::map<std::string, float*> grads;   // vitocm_bind_grad: where vitocm_mim_backward accumulates dL/d(parameter)
   // chunk-level concurrency: independent chunks of tiles run on `lanes` streams (lane 0 = the caller's stream) so that
   // one chunk's kernel tails and bandwidth-bound kernels overlap the other chunk's tensor-bound kernels
   static constexpr int MAX_LANES = 4;
@@ -409,7 +423,7 @@ int run_gemm_ln(const vitocm_engine* e, const void* A, long long lda, const void
 
 // ---------------------------------------------------------------------------------- attention launch
 int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, int N, void* ctx, long long ldo, cudaStream_t st,
-                  long long* timeline = nullptr) {
+                  long long* timeline = nullptr, float* lse2 = nullptr) {
   const int D = e->cfg.embed_dim, H = e->cfg.num_heads;
   const long long M = static_cast<long long>(B) * N;
   ProfScope prof(PC_ATTN, st);
@@ -418,7 +432,7 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
   AttnArgs a{};
   a.n_tokens = N; a.embed_dim = D; a.lo_col_off = 3 * D;
   a.scale_log2 = e->cfg.qk_scale * 1.44269504088896340736f;
-  a.out = reinterpret_cast<__nv_bfloat16*>(ctx); a.ldo = ldo; a.out_lo_off = D; a.timeline = timeline;
+  a.out = reinterpret_cast<__nv_bfloat16*>(ctx); a.ldo = ldo; a.out_lo_off = D; a.timeline = timeline; a.lse2 = lse2;
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, H, B);
   auto launch = [&](auto kern, int smem_bytes, bool& attr) -> int {
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); attr = true; }
@@ -437,17 +451,17 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
 }
 
 int run_layernorm(const float* X, const float* g, const float* b, void* out_bf16, long long ldo, int split, int lo_off,
-                  float* out_f32, long long ldf, int M, int D, float eps, cudaStream_t st) {
+                  float* out_f32, long long ldf, int M, int D, float eps, cudaStream_t st, float* x_copy = nullptr) {
   if (M <= 0) return 0;
   if (D % 4 != 0 || D > LN_MAX_VEC * 128) return fail(VITOCM_ERR_INVALID, "LayerNorm D=%d unsupported", D);
   ProfScope prof(PC_LN, st);
   const int rows_per_block = 8;
   const dim3 grid((M + rows_per_block - 1) / rows_per_block), block(rows_per_block * 32);
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  if (D == 384) layernorm_kernel<3><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps);
-  else if (D == 768) layernorm_kernel<6><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps);
-  else if (D == 128) layernorm_kernel<1><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps);
-  else layernorm_kernel<0><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps);
+  if (D == 384) layernorm_kernel<3><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps, x_copy);
+  else if (D == 768) layernorm_kernel<6><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps, x_copy);
+  else if (D == 128) layernorm_kernel<1><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps, x_copy);
+  else layernorm_kernel<0><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps, x_copy);
   LAUNCH_CHECK();
   return 0;
 }
@@ -625,8 +639,7 @@ int vitocm_load_weight(vitocm_engine* e, const char* name, const float* host_dat
   return 0;
 }
 
-int vitocm_finalize_weights(vitocm_engine* e) {
-  if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
+static int repack_weights(vitocm_engine* e, cudaStream_t st) {
   const int D = e->cfg.embed_dim, Hd = e->cfg.mlp_hidden, P = e->parts, S = e->split;
   const int K = e->cfg.in_chans * e->cfg.patch_size * e->cfg.patch_size;
   auto need = [&](const std::string& n, long long cnt) -> int {
@@ -641,7 +654,13 @@ int vitocm_finalize_weights(vitocm_engine* e) {
   auto pack = [&](DevBuf& dst, const float* src, int R, int C, int split) -> int {
     const int parts = split ? 2 : 1;
     TRY(dst.alloc(static_cast<size_t>(R) * C * parts * 2));
-    split_weight_kernel<<<512, 256>>>(src, dst.as<__nv_bfloat16>(), static_cast<long long>(C) * parts, split, C, R, C);
+    split_weight_kernel<<<512, 256, 0, st>>>(src, dst.as<__nv_bfloat16>(), static_cast<long long>(C) * parts, split, C, R, C);
+    LAUNCH_CHECK();
+    return 0;
+  };
+  auto pack_t = [&](DevBuf& dst, const float* src, int R, int C) -> int {   // fp32 [R][C] -> bf16 [C][R]
+    TRY(dst.alloc(static_cast<size_t>(R) * C * 2));
+    transpose_weight_kernel<<<dim3((C + 31) / 32, (R + 31) / 32), 256, 0, st>>>(src, dst.as<__nv_bfloat16>(), R, C);
     LAUNCH_CHECK();
     return 0;
   };
@@ -665,6 +684,12 @@ int vitocm_finalize_weights(vitocm_engine* e) {
     TRY(pack(L.w1, e->w(pre + "mlp.fc1.weight"), Hd, D, S));
     TRY(pack(L.w2, e->w(pre + "mlp.fc2.weight"), D, Hd, S));
     if (l == e->cfg.depth - 1) TRY(pack(L.wk_split, L.wqkv_f32 + static_cast<long long>(D) * D, D, D, 1));
+    if (!S) {
+      TRY(pack_t(L.wqkv_t, e->w(pre + "attn.qkv.weight"), 3 * D, D));
+      TRY(pack_t(L.wproj_t, e->w(pre + "attn.proj.weight"), D, D));
+      TRY(pack_t(L.w1_t, e->w(pre + "mlp.fc1.weight"), Hd, D));
+      TRY(pack_t(L.w2_t, e->w(pre + "mlp.fc2.weight"), D, Hd));
+    }
   }
   (void)P;
   const long long dec_rows = static_cast<long long>(e->cfg.in_chans) * e->cfg.patch_size * e->cfg.patch_size;
@@ -672,11 +697,41 @@ int vitocm_finalize_weights(vitocm_engine* e) {
     TRY(need("decoder.0.weight", dec_rows * D));
     TRY(need("decoder.0.bias", dec_rows));
     TRY(pack(e->dec_w, e->w("decoder.0.weight"), static_cast<int>(dec_rows), D, S));
+    if (!S) TRY(pack_t(e->dec_w_t, e->w("decoder.0.weight"), static_cast<int>(dec_rows), D));
   }
+  return 0;
+}
+
+int vitocm_finalize_weights(vitocm_engine* e) {
+  if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
+  TRY(repack_weights(e, nullptr));
   CUDA_TRY(cudaDeviceSynchronize());
   e->finalized = true;
   return 0;
 }
+
+int vitocm_refresh_weights(vitocm_engine* e, void* stream) {
+  TRY(check_engine(e));
+  return repack_weights(e, static_cast<cudaStream_t>(stream));
+}
+
+int vitocm_bind_weight(vitocm_engine* e, const char* name, float* dev_data, int64_t numel) {
+  if (e == nullptr || name == nullptr || dev_data == nullptr || numel <= 0) return fail(VITOCM_ERR_INVALID, "bad argument");
+  if ((reinterpret_cast<uintptr_t>(dev_data) & 15) != 0) return fail(VITOCM_ERR_INVALID, "bound weight '%s' must be 16-byte aligned", name);
+  auto it = e->master.find(name);
+  DevBuf* b = it != e->master.end() ? it->second : (e->master[name] = new DevBuf());
+  b->bind(dev_data, static_cast<size_t>(numel) * 4);
+  e->finalized = false;
+  return 0;
+}
+
+int vitocm_bind_grad(vitocm_engine* e, const char* name, float* dev_grad) {
+  if (e == nullptr || name == nullptr) return fail(VITOCM_ERR_INVALID, "bad argument");
+  if ((reinterpret_cast<uintptr_t>(dev_grad) & 15) != 0) return fail(VITOCM_ERR_INVALID, "bound gradient '%s' must be 16-byte aligned", name);
+  if (dev_grad == nullptr) e->grads.erase(name); else e->grads[name] = dev_grad;
+  return 0;
+}
+
 
 size_t vitocm_workspace_bytes(const vitocm_engine* e, int chunk_tiles, int n_tokens) {
   if (e == nullptr || chunk_tiles <= 0 || n_tokens <= 0) return 0;
@@ -1045,3 +1100,5 @@ int vitocm_layernorm(vitocm_engine* e, const float* X, const float* gamma, const
 }
 
 }  // extern "C"
+
+#include "train_api.inc"
