@@ -151,6 +151,201 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------- MIM pre-training step (configs[3])
+def mim_flops_per_image(D, depth, heads, N, ldy=192):
+    """2*M*N*K of every contraction, forward + input-gradient + weight-gradient (3 x (fwd 44.811 + decoder))."""
+    K0 = 3 * PATCH * PATCH
+    block = 2.0 * N * D * 3 * D + 4.0 * N * N * D + 2.0 * N * D * D + 4.0 * N * D * 4 * D
+    fwd = 2.0 * (N - 1) * D * K0 + depth * block + 2.0 * N * D * ldy
+    return 3.0 * fwd
+
+
+def mim_cpu_sample(threads, batch=2, steps=1):
+    """The reference training step (oracle port: torch-CPU autograd + restated clip / AdamW) on a bounded batch."""
+    from oracle import train_oracle as TO
+    from oracle import vit_oracle as VO
+    torch.set_num_threads(threads)
+    cfg = VO.ViTConfig(**ARCHS["vit_small"])
+    sd = VO.init_state_dict(cfg, seed=0, mim=True)
+    gd = torch.Generator().manual_seed(5)
+    params = dict(sd)
+    params["decoder.0.weight"], params["decoder.0.bias"] = torch.randn(192, cfg.embed_dim, 1, 1, generator=gd) * 0.02, torch.zeros(192)
+    state = TO.TrainState(params)
+    x = VO.synthetic_tile(WINDOW, seed=9, batch=batch)
+    rs = np.random.RandomState(0)
+    mask = torch.from_numpy(np.stack([VO.mask_generator(rs, WINDOW, 16, PATCH, 0.5) for _ in range(batch)]))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        TO.train_step(state, cfg, x, mask)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, f"{steps} training step(s) of ViT-S/8 MIM at batch {batch} (224^2): torch-CPU fwd+bwd, clip 5.0, AdamW"
+
+
+def main_mim(args):
+    """BASELINE.json configs[3]: MIM (SimMIM-style) pre-training step, ViT-S/8, 224^2 synthetic tiles, bf16 fwd+bwd with fp32
+    master weights / AdamW, batch 32 per GPU (256 on 8), NCCL all-reduce of the flat gradient.  One step = zero_grad,
+    forward, loss.sum().backward(), all-reduce, clip_grad_norm_(5.0), AdamW, bf16 weight repack."""
+    metric = "mim_pretrain_images_per_s"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        vals = []
+        for i in range(args.warmup + args.steps):
+            ips, sample = mim_cpu_sample(threads, batch=2, steps=1)
+            if i >= args.warmup:
+                vals.append(ips)
+        v = statistics.mean(vals)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch_per_gpu * args.gpus / v, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"MIM pre-training step, vit_small/8, 224^2, global batch {args.batch_per_gpu * args.gpus}",
+                                     "note": "each step times a bounded batch-2 sample and extrapolates linearly in images"},
+                          "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    import vitocm_b200 as vob
+    from oracle import vit_oracle as VO   # synthetic-input recipe only
+    from functools import partial
+    from types import SimpleNamespace as NS
+    a = ARCHS["vit_small"]
+    torch.manual_seed(0)
+    enc = vob.VisionTransformerForSimMIM(patch_size=PATCH, embed_dim=a["embed_dim"], depth=a["depth"], num_heads=a["num_heads"], mlp_ratio=4,
+                                         img_size=[WINDOW], qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), precision="bf16")
+    mim = vob.MIM(encoder=enc, encoder_stride=PATCH).cuda().train()
+    cfg = NS(TRAIN=NS(BASE_LR=5e-4, WEIGHT_DECAY=0.05, CLIP_GRAD=5.0, OPTIMIZER=NS(NAME="adamw", EPS=1e-8, BETAS=(0.9, 0.999))))
+    opt = vob.optimizer.build_pretrain_optimizer(cfg, mim, None)
+    Bg = args.batch_per_gpu
+    N = (WINDOW // PATCH) ** 2 + 1
+    # a few distinct synthetic batches in pinned host memory (rank-dependent seeds), cycled through
+    n_host = 4
+    rs = np.random.RandomState(1000 + rank)
+    base = VO.synthetic_tile(WINDOW, seed=500 + rank, batch=min(Bg, 8))
+    xs_host = [base[torch.randint(0, base.shape[0], (Bg,), generator=torch.Generator().manual_seed(i))].contiguous().pin_memory() for i in range(n_host)]
+    ms_host = [torch.from_numpy(np.stack([VO.mask_generator(rs, WINDOW, 16, PATCH, 0.5) for _ in range(Bg)])).pin_memory() for _ in range(n_host)]
+    xs_dev = [x.to(dev) for x in xs_host]
+    ms_dev = [m.to(dev) for m in ms_host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def train_step(x, m):
+        opt.zero_grad()
+        loss, _, _ = mim(x, m)
+        loss.sum().backward()
+        mim.all_reduce_grads()
+        vob.optimizer.clip_grad_norm_(mim, cfg.TRAIN.CLIP_GRAD)
+        opt.step()
+        return loss
+
+    for i in range(args.warmup):
+        train_step(xs_dev[i % n_host], ms_dev[i % n_host])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = vob._lib.launch_count()
+    step_ms = []
+    for i in range(args.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        loss = train_step(xs_dev[i % n_host], ms_dev[i % n_host])
+        e1.record()
+        barrier()
+        step_ms.append(e0.elapsed_time(e1))
+    launches = vob._lib.launch_count() - launches0
+    sampler.stop_flag.set()
+    sampler.join(timeout=3)
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    value = Bg * world / (ms_per_step / 1e3)
+    # ---- end to end: pinned host batch -> device inside the timed region, loss read back every step
+    e2e_ms = []
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    for i in range(2 + args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        x = xs_host[i % n_host].to(dev, non_blocking=True)
+        m = ms_host[i % n_host].to(dev, non_blocking=True)
+        loss = train_step(x, m)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        e1.record()
+        barrier()
+        if i >= 2:
+            e2e_ms.append(e0.elapsed_time(e1))
+    e2e_t = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(e2e_t, op=torch.distributed.ReduceOp.MAX)
+    final_loss = float(loss_host.item())
+    # ---- per-kernel-class device times
+    vob._lib.profile_enable(True)
+    train_step(xs_dev[0], ms_dev[0])
+    torch.cuda.synchronize()
+    prof = vob._lib.profile_read()
+    vob._lib.profile_enable(False)
+    classes = {k: {"ms": v[0], "launches": v[1]} for k, v in prof.items() if v[1] > 0}
+    D, depth = a["embed_dim"], a["depth"]
+    M = Bg * N
+    gemm_fwd = 2.0 * M * D * (3 * D + D + 8 * D) * depth
+    attn_fwd = 4.0 * N * N * D * Bg * depth
+    cls_gflop = {"gemm_wgrad": gemm_fwd + 2.0 * M * D * 192 * 2, "gemm_dgrad": gemm_fwd + 2.0 * M * D * 192, "attention": attn_fwd, "attention_bwd": 2.5 * attn_fwd,
+                 "gemm_qkv": 2.0 * M * D * 3 * D * depth, "gemm_proj": 2.0 * M * D * D * depth, "gemm_fc1_gelu": 2.0 * M * D * 4 * D * depth,
+                 "gemm_fc2": 2.0 * M * D * 4 * D * depth}
+    for k, c in classes.items():
+        c["gflop"] = cls_gflop.get(k, 0.0) / 1e9
+        c["tflops"] = c["gflop"] / c["ms"] if c["ms"] > 0 and c["gflop"] > 0 else None
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peaks = json.load(open(peaks_path))
+        peak, peak_src = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))), "measured (sustained cuBLAS bf16, MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+    tensor_classes = {k: c for k, c in classes.items() if c["gflop"] > 0}
+    dom = max(tensor_classes, key=lambda k: tensor_classes[k]["ms"])
+    c = tensor_classes[dom]
+    roofline = {"kernel": dom, "bound": "tensor", "achieved": c["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": c["tflops"] / peak,
+                "traffic": None, "peak_source": peak_src, "launches_per_step": c["launches"], "avg_launch_ms": c["ms"] / c["launches"]}
+    step_tflops = mim_flops_per_image(D, depth, a["num_heads"], N) * Bg / 1e12 / (ms_per_step / 1e3)
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"MIM pre-training step (SimMIM masked patches), vit_small/8, 224^2 synthetic tiles, batch {Bg} per GPU = {Bg * world} global, "
+                                       "bf16 fwd+bwd, fp32 master weights + fused clip/AdamW, NCCL all-reduce(SUM) of the flat gradient",
+                           "batch_per_gpu": Bg, "global_batch": Bg * world, "weights": "random init (seed 0)",
+                           "l2": "flushed between timed steps (256 MiB write, untimed); per-step working set >> L2",
+                           "parallelism": f"data parallel over {world} rank(s)", "final_loss": final_loss},
+                "e2e": {"value": Bg * world / (float(e2e_t.item()) / 1e3), "unit": "images/s",
+                        "h2d_bytes_per_step": int(xs_host[0].numel() * 4 + ms_host[0].numel() * 8), "d2h_bytes_per_step": 4, "ms_per_step": float(e2e_t.item())},
+                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
+                "step_tensor": {"tflops_per_gpu": step_tflops, "frac_of_peak": step_tflops / peak, "gflop_per_image": mim_flops_per_image(D, depth, a["num_heads"], N) / 1e9},
+                "kernel_classes": classes}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            ips, sample = mim_cpu_sample(threads)
+            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -164,7 +359,12 @@ def main():
     ap.add_argument("--tile-batch", type=int, default=175)
     ap.add_argument("--lanes", type=int, default=1, help="chunks in flight on concurrent streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="segmentation", choices=["segmentation", "mim_train"],
+                    help="segmentation = BASELINE.json configs[1] (the headline); mim_train = configs[3] (MIM pre-training step)")
+    ap.add_argument("--batch-per-gpu", type=int, default=32, help="mim_train: images per GPU per step (256 over 8 GPUs)")
     args = ap.parse_args()
+    if args.workload == "mim_train":
+        return main_mim(args)
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.warmup < 3:

@@ -217,10 +217,10 @@ size_t vitocm_mim_train_workspace_bytes(const vitocm_engine* e, int B, int n_tok
 int vitocm_mim_train_forward(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const float* mask,
                              float* x_rec, double* loss_sums, void* ws, size_t ws_bytes, void* stream);
 /* loss.backward() (mim.py:174) for the batch vitocm_mim_train_forward just ran on the same ws: gradients of
- * grad_scale * loss are accumulated into the buffers bound with vitocm_bind_grad (all parameters except pos_embed);
+ * (*grad_scale) * loss (grad_scale = DEVICE pointer to the upstream gradient of the scalar loss, NULL = 1) are accumulated into the buffers bound with vitocm_bind_grad (all parameters except pos_embed);
  * dpos [N][D] fp32 is WRITTEN with the gradient of the (interpolated) position table passed to the forward. */
 int vitocm_mim_backward(vitocm_engine* e, const float* x, int B, int H, int W, const float* mask, const float* x_rec,
-                        const double* loss_sums, float grad_scale, float* dpos, void* ws, size_t ws_bytes, void* stream);
+                        const double* loss_sums, const float* grad_scale, float* dpos, void* ws, size_t ws_bytes, void* stream);
 
 /* torch.nn.utils.clip_grad_norm_ (mim.py:176), first half: out[0] = sum g^2 over a flat fp32 gradient buffer (fp64). */
 int vitocm_grad_sumsq(const float* g, int64_t n, double* out, void* stream);

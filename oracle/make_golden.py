@@ -277,6 +277,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "mim_tiny.npz"), **g)
     report.append("mim_tiny.npz: MaskGenerator + MIM forward oracle == reference")
 
+    report += make_train_golden(ref_model)
+
     with open(os.path.join(OUT, "README.md"), "w") as f:
         f.write("# Golden fixtures\n\nGenerated by `python -m oracle.make_golden` in the build container from the\n"
                 "reference's own code at /root/reference (outputs only; no reference source is stored).\n\n")
@@ -285,5 +287,80 @@ def main():
     print("\n".join(report))
 
 
+def sample(t: torch.Tensor) -> np.ndarray:
+    """fixture-size control: 1-D tensors whole, larger ones every 7th element (+ their sums, stored separately)"""
+    f = t.detach().reshape(-1)
+    return (f if t.dim() <= 1 or f.numel() <= 4096 else f[::7]).numpy().copy()
+
+
+def make_train_golden(ref_model):
+    """Two iterations of the reference training step (SSS/mim.py:172-179) on the tiny MIM: the reference's MIM module,
+    its optimizer grouping (SSS/optimizer.py:14-33, exec'd: the module imports nothing exotic), torch's
+    clip_grad_norm_ and AdamW -- checked against oracle/train_oracle.py and stored."""
+    from oracle import train_oracle as TO
+    from oracle import vit_oracle as VO
+    tiny_m = VO.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=8, img_size=32)
+    tiny_m_init = VO.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=8, img_size=224)
+    sd_m = VO.randomize_affine(VO.init_state_dict(tiny_m_init, seed=11, mim=True), seed=12)
+    enc = ref_model.VisionTransformerForSimMIM(patch_size=8, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4, img_size=[32],
+                                               qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    mim = ref_model.MIM(encoder=enc, encoder_stride=8)
+    enc.load_state_dict(sd_m, strict=True)
+    gd = torch.Generator().manual_seed(5)
+    dec_w = torch.randn(192, 128, 1, 1, generator=gd) * 0.05
+    dec_b = torch.randn(192, generator=gd) * 0.05
+    mim.decoder[0].weight.data.copy_(dec_w)
+    mim.decoder[0].bias.data.copy_(dec_b)
+    ns = _exec_lines(os.path.join(REF, "optimizer.py"), [(1, 33)], {})
+    class _Log:
+        def info(self, *a, **k):
+            pass
+    groups = ns["get_pretrain_param_groups"](mim, _Log(), mim.no_weight_decay(), mim.no_weight_decay_keywords())
+    opt = torch.optim.AdamW(groups, eps=1e-8, betas=(0.9, 0.999), lr=5e-4, weight_decay=0.05)   # SSS/optimizer.py:73-75, config.py:98-130
+    params = dict(sd_m)
+    params["decoder.0.weight"], params["decoder.0.bias"] = dec_w, dec_b
+    state = TO.TrainState(params)
+    decay_names = {n for n, p in mim.named_parameters() if any(p is q for q in groups[0]["params"])}
+    for k, v in params.items():
+        assert TO.has_weight_decay(k, v.shape) == (TO.full_name(k) in decay_names), k
+    g = {}
+    rs = np.random.RandomState(9)
+    mim.train()
+    for it in range(2):
+        xm = VO.synthetic_tile(32, seed=200 + it, batch=4)
+        masks = torch.from_numpy(np.stack([VO.mask_generator(rs, 32, 16, 8, 0.5) for _ in range(4)]))
+        opt.zero_grad()
+        loss, _, _ = mim(xm, masks)
+        loss.sum().backward()
+        raw = {n: p.grad.detach().clone() for n, p in mim.named_parameters()}
+        total = torch.nn.utils.clip_grad_norm_(mim.parameters(), 5.0 if it == 0 else 0.05)   # second step: the clip is active
+        opt.step()
+        o_loss, o_total, o_grads = TO.train_step(state, tiny_m, xm, masks, clip_grad=5.0 if it == 0 else 0.05)
+        assert abs(loss.item() - o_loss.item()) < 1e-6, (loss.item(), o_loss.item())
+        assert abs(total.item() - o_total.item()) < 1e-5 * max(1.0, total.item())
+        g[f"step{it}/x"], g[f"step{it}/mask"] = xm.numpy(), masks.numpy()
+        g[f"step{it}/loss"], g[f"step{it}/grad_norm"] = np.array(loss.item()), np.array(total.item())
+        for n, p in mim.named_parameters():
+            key = n[len("encoder."):] if n.startswith("encoder.") else n
+            assert (p.grad - o_grads[key]).abs().max().item() <= 1e-5 * max(1e-3, p.grad.abs().max().item()), n
+            assert (p.detach() - state.params[key]).abs().max().item() <= 2e-6, n
+            g[f"step{it}/grad/{key}"] = sample(raw[n])
+            g[f"step{it}/gradsum/{key}"] = np.array([float(raw[n].double().sum()), float(raw[n].double().abs().sum())])
+            g[f"step{it}/param/{key}"] = sample(p)
+    g["dec_w"], g["dec_b"] = dec_w.numpy(), dec_b.numpy()
+    for k, v in checksum(sd_m).items():
+        g["wsum/" + k] = v
+    np.savez_compressed(os.path.join(OUT, "mim_train_tiny.npz"), **g)
+    return ["mim_train_tiny.npz: two reference training steps (MIM fwd/bwd, optimizer.py grouping, torch clip_grad_norm_ + AdamW); "
+            "oracle/train_oracle.py == reference on loss, grad norm, every gradient and every updated parameter"]
+
+
 if __name__ == "__main__":
-    main()
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "train":
+        lines = make_train_golden(_import_reference()[1])
+        with open(os.path.join(OUT, "README.md"), "a") as f:
+            for r in lines:
+                f.write(f"* {r}\n")
+        print("\n".join(lines))
+    else:
+        main()

@@ -1,0 +1,150 @@
+"""GPU (B200): the MIM training step (SSS/mim.py:153-182) through the reference-shaped API -- MIM.forward under autograd,
+loss.sum().backward(), clip_grad_norm_, AdamW -- against the reference's golden vectors and the CPU oracle."""
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+
+import vitocm_b200 as vob
+from conftest import check_weight_sums, load_golden
+from oracle import train_oracle as TO
+from oracle import vit_oracle as VO
+
+pytestmark = pytest.mark.gpu
+
+# bf16 tensor-core operands with fp32 accumulation.  The masked-L1 loss has a discontinuous gradient (sign(x_rec - x),
+# model.py:75): a bf16-sized change of x_rec flips a few signs, each moving a decoder-bias gradient entry by 2 / (3 * sum(mask))
+# -- with the tiny fixture's 32 masked tokens per column that is ~10 % of the entry, so the bars are: global relative L2
+# error over all gradients, and a looser per-tensor bound (relative to the tensor's largest entry).
+GRAD_TOL_GLOBAL = 3e-2
+GRAD_TOL_TENSOR = 2e-1
+
+
+def _sample(t):
+    f = t.detach().reshape(-1)
+    return (f if t.dim() <= 1 or f.numel() <= 4096 else f[::7]).cpu().numpy()
+
+
+def _tiny_mim(g):
+    cfg_init = VO.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=8, img_size=224)
+    sd = VO.randomize_affine(VO.init_state_dict(cfg_init, seed=11, mim=True), seed=12)
+    check_weight_sums(sd, g)
+    enc = vob.VisionTransformerForSimMIM(patch_size=8, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4, img_size=[32], qkv_bias=True,
+                                         norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), precision="bf16")
+    enc.load_state_dict(sd, strict=True)
+    mim = vob.MIM(encoder=enc, encoder_stride=8)
+    mim.decoder[0].weight.data.copy_(torch.from_numpy(g["dec_w"]))
+    mim.decoder[0].bias.data.copy_(torch.from_numpy(g["dec_b"]))
+    return mim.cuda().train(), sd
+
+
+def _key(n):
+    return n[len("encoder."):] if n.startswith("encoder.") else n
+
+
+def test_backward_matches_reference_golden_with_stock_torch_optimizer():
+    """The reference loop verbatim: zero_grad, forward, loss.sum().backward(), torch clip_grad_norm_, torch.optim.AdamW."""
+    g = load_golden("mim_train_tiny.npz")
+    mim, _ = _tiny_mim(g)
+    groups = vob.optimizer.get_pretrain_param_groups(mim, None, mim.no_weight_decay(), mim.no_weight_decay_keywords())
+    opt = torch.optim.AdamW(groups, eps=1e-8, betas=(0.9, 0.999), lr=5e-4, weight_decay=0.05)
+    for it, clip in ((0, 5.0), (1, 0.05)):
+        x, mask = torch.from_numpy(g[f"step{it}/x"]).cuda(), torch.from_numpy(g[f"step{it}/mask"]).cuda()
+        opt.zero_grad()
+        loss, x_rec, mask_up = mim(x, mask)
+        assert loss.requires_grad and not x_rec.requires_grad
+        loss.sum().backward()
+        assert abs(loss.item() - float(g[f"step{it}/loss"])) <= 2e-2 * abs(float(g[f"step{it}/loss"]))
+        errs, num, den = [], 0.0, 0.0
+        for n, p in mim.named_parameters():
+            ref = g[f"step{it}/grad/{_key(n)}"]
+            assert p.grad is not None, n
+            d = _sample(p.grad) - ref
+            errs.append((float(np.abs(d).max() / max(np.abs(ref).max(), 1e-6)), n))
+            num += float((d.astype(np.float64) ** 2).sum())
+            den += float((ref.astype(np.float64) ** 2).sum())
+        errs.sort(reverse=True)
+        print(f"step {it}: global relative L2 gradient error {(num / den) ** 0.5:.3e}; worst tensors {errs[:4]}")
+        # step 1 starts from parameters that already differ from the reference's: Adam's first update is ~lr * sign(g), so
+        # elements with near-zero gradients moved the other way -- the second step is checked at a looser bar
+        assert (num / den) ** 0.5 <= (GRAD_TOL_GLOBAL if it == 0 else 1.5e-1)
+        assert errs[0][0] <= (GRAD_TOL_TENSOR if it == 0 else 6e-1), errs[0]
+        total = torch.nn.utils.clip_grad_norm_(mim.parameters(), clip)
+        assert abs(total.item() - float(g[f"step{it}/grad_norm"])) <= 2e-2 * float(g[f"step{it}/grad_norm"])
+        opt.step()
+        # Adam's normalised update moves every element by at most ~lr per step whatever the gradient's size
+        for n, p in mim.named_parameters():
+            assert np.abs(_sample(p) - g[f"step{it}/param/{_key(n)}"]).max() <= 2.5 * 5e-4 * (it + 1), n
+
+
+def test_fused_optimizer_path_tracks_oracle():
+    """build_pretrain_optimizer -> FusedAdamW (flat buffers, clip folded into the update) for two steps."""
+    from types import SimpleNamespace as NS
+    g = load_golden("mim_train_tiny.npz")
+    mim, sd = _tiny_mim(g)
+    args = NS(TRAIN=NS(BASE_LR=5e-4, WEIGHT_DECAY=0.05, OPTIMIZER=NS(NAME="adamw", EPS=1e-8, BETAS=(0.9, 0.999))))
+    opt = vob.optimizer.build_pretrain_optimizer(args, mim, None)
+    assert isinstance(opt, vob.optimizer.FusedAdamW) and len(opt.param_groups) == 2
+    for it, clip in ((0, 5.0), (1, 0.05)):
+        x, mask = torch.from_numpy(g[f"step{it}/x"]).cuda(), torch.from_numpy(g[f"step{it}/mask"]).cuda()
+        opt.zero_grad()
+        loss, _, _ = mim(x, mask)
+        loss.sum().backward()
+        total = vob.optimizer.clip_grad_norm_(mim.parameters() if False else mim, clip)
+        opt.step()
+        assert abs(loss.item() - float(g[f"step{it}/loss"])) <= 2e-2 * abs(float(g[f"step{it}/loss"]))
+        assert abs(total.item() - float(g[f"step{it}/grad_norm"])) <= 2e-2 * float(g[f"step{it}/grad_norm"])
+        for n, p in mim.named_parameters():
+            assert np.abs(_sample(p) - g[f"step{it}/param/{_key(n)}"]).max() <= 2.5 * 5e-4 * (it + 1), n
+        if it == 1:   # the clipped gradient is written back by the fused step: its norm is max_norm
+            assert abs(mim._gflat.double().norm().item() - clip) <= 1e-3 * clip
+    # the loss goes down when the same batch is revisited a few times
+    x, mask = torch.from_numpy(g["step0/x"]).cuda(), torch.from_numpy(g["step0/mask"]).cuda()
+    first = None
+    for _ in range(8):
+        opt.zero_grad()
+        loss, _, _ = mim(x, mask)
+        loss.sum().backward()
+        opt.step()
+        first = loss.item() if first is None else first
+    assert loss.item() < first
+
+
+def test_vit_small_224_gradients_match_oracle():
+    """BASELINE config 4 shapes (ViT-S/8, 224^2, N = 785) at batch 2 against CPU autograd of the oracle."""
+    cfg = VO.ViTConfig(**VO.VIT_SMALL)
+    sd = VO.randomize_affine(VO.init_state_dict(cfg, seed=0, mim=True), seed=1)
+    gd = torch.Generator().manual_seed(5)
+    dec_w, dec_b = torch.randn(192, 384, 1, 1, generator=gd) * 0.05, torch.randn(192, generator=gd) * 0.05
+    enc = vob.VisionTransformerForSimMIM(patch_size=8, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4, img_size=[224], qkv_bias=True,
+                                         norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), precision="bf16")
+    enc.load_state_dict(sd, strict=True)
+    mim = vob.MIM(encoder=enc, encoder_stride=8)
+    mim.decoder[0].weight.data.copy_(dec_w)
+    mim.decoder[0].bias.data.copy_(dec_b)
+    mim = mim.cuda().train()
+    x = VO.synthetic_tile(224, seed=9, batch=2)
+    rs = np.random.RandomState(4)
+    mask = torch.from_numpy(np.stack([VO.mask_generator(rs, 224, 16, 8, 0.5) for _ in range(2)]))
+    params = dict(sd)
+    params["decoder.0.weight"], params["decoder.0.bias"] = dec_w, dec_b
+    torch.set_num_threads(8)
+    ref_loss, ref = TO.mim_loss_and_grads(params, cfg, x, mask)
+    loss, _, _ = mim(x.cuda(), mask.cuda())
+    loss.sum().backward()
+    assert abs(loss.item() - ref_loss.item()) <= 2e-2 * abs(ref_loss.item())
+    worst = ("", 0.0)
+    num = den = 0.0
+    for n, p in mim.named_parameters():
+        r = ref[_key(n)]
+        d = (p.grad.cpu() - r)
+        err = d.abs().max().item() / max(r.abs().max().item(), 1e-8)
+        num += d.double().pow(2).sum().item()
+        den += r.double().pow(2).sum().item()
+        if err > worst[1]:
+            worst = (n, err)
+    print(f"ViT-S/8 224: loss {loss.item():.6f} vs {ref_loss.item():.6f}; worst per-tensor gradient error {worst[1]:.3e} ({worst[0]}); "
+          f"global relative L2 error {(num / den) ** 0.5:.3e}")
+    assert (num / den) ** 0.5 <= 2e-2
+    assert worst[1] <= 6e-2, worst

@@ -117,3 +117,77 @@ def test_mask_generator_and_mim_loss():
                                     torch.from_numpy(g["x"]), torch.from_numpy(g["mask"]))
     assert abs(loss.item() - float(g["loss"])) < 1e-6
     assert np.abs(x_rec.detach().numpy() - g["x_rec"]).max() < 1e-5
+
+
+def _sample(t):
+    f = t.detach().reshape(-1)
+    return (f if t.dim() <= 1 or f.numel() <= 4096 else f[::7]).numpy()
+
+
+def test_train_step_oracle_matches_reference_golden():
+    """oracle/train_oracle.py (autograd over the functional forward + restated clip_grad_norm_ / AdamW / param grouping)
+    against two iterations of the reference's own training step (tests/golden/mim_train_tiny.npz)."""
+    from oracle import train_oracle as TO
+    g = load_golden("mim_train_tiny.npz")
+    cfg_init = VO.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=8, img_size=224)
+    cfg = VO.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=8, img_size=32)
+    sd = VO.randomize_affine(VO.init_state_dict(cfg_init, seed=11, mim=True), seed=12)
+    check_weight_sums(sd, g)
+    params = dict(sd)
+    params["decoder.0.weight"], params["decoder.0.bias"] = torch.from_numpy(g["dec_w"]), torch.from_numpy(g["dec_b"])
+    state = TO.TrainState(params)
+    for it, clip in ((0, 5.0), (1, 0.05)):
+        x, mask = torch.from_numpy(g[f"step{it}/x"]), torch.from_numpy(g[f"step{it}/mask"])
+        loss, raw = TO.mim_loss_and_grads(state.params, cfg, x, mask)
+        for k, gr in raw.items():
+            ref = g[f"step{it}/grad/{k}"]
+            assert np.abs(_sample(gr) - ref).max() <= 1e-5 * max(1e-3, np.abs(ref).max()), k
+            assert np.allclose([float(gr.double().sum()), float(gr.double().abs().sum())], g[f"step{it}/gradsum/{k}"], rtol=1e-4, atol=1e-6), k
+        loss2, total, _ = TO.train_step(state, cfg, x, mask, clip_grad=clip)
+        assert abs(loss.item() - float(g[f"step{it}/loss"])) < 1e-6 and abs(loss2.item() - loss.item()) < 1e-7
+        assert abs(total.item() - float(g[f"step{it}/grad_norm"])) <= 1e-5 * max(1.0, float(g[f"step{it}/grad_norm"]))
+        for k, p in state.params.items():
+            assert np.abs(_sample(p) - g[f"step{it}/param/{k}"]).max() <= 2e-6, k
+    assert float(g["step1/grad_norm"]) > 0.05      # the second step's clip (max_norm 0.05) was active
+
+
+def test_adamw_restatement_matches_torch_optim():
+    from oracle import train_oracle as TO
+    gen = torch.Generator().manual_seed(0)
+    p0 = torch.randn(1000, generator=gen)
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([p_ref], lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    p, m, v = p0.clone(), torch.zeros(1000), torch.zeros(1000)
+    for step in range(1, 6):
+        gr = torch.randn(1000, generator=gen) * 0.1
+        p_ref.grad = gr.clone()
+        opt.step()
+        p, m, v = TO.adamw_update(p, gr, m, v, step, 5e-4, 0.9, 0.999, 1e-8, 0.05)
+        assert (p - p_ref.detach()).abs().max().item() < 1e-6
+
+
+def test_lr_scheduler_and_param_groups_mirror():
+    """Host logic of the mirrors (no GPU): cosine schedule == the oracle's timm formula; parameter grouping of
+    optimizer.get_pretrain_param_groups == SSS/optimizer.py:14-33 on the MIM module."""
+    from functools import partial
+    from types import SimpleNamespace as NS
+    import vitocm_b200 as vob
+    from oracle import train_oracle as TO
+    enc = vob.VisionTransformerForSimMIM(patch_size=8, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4, img_size=[32], qkv_bias=True,
+                                         norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    mim = vob.MIM(encoder=enc, encoder_stride=8)
+    assert mim.no_weight_decay() == set() or mim.no_weight_decay() == {}
+    groups = vob.optimizer.get_pretrain_param_groups(mim, None, mim.no_weight_decay(), mim.no_weight_decay_keywords())
+    decay_ids = {id(p) for p in groups[0]["params"]}
+    for n, p in mim.named_parameters():
+        key = n[len("encoder."):] if n.startswith("encoder.") else n
+        assert (id(p) in decay_ids) == TO.has_weight_decay(key, p.shape), n
+    assert groups[1]["weight_decay"] == 0.0
+    opt = torch.optim.SGD([{"params": groups[0]["params"]}, {"params": groups[1]["params"]}], lr=5e-4)
+    cfg = NS(TRAIN=NS(EPOCHS=10, WARMUP_EPOCHS=2, MIN_LR=5e-6, WARMUP_LR=5e-7, LR_SCHEDULER=NS(NAME="cosine", DECAY_EPOCHS=30, MULTISTEPS=[])))
+    sched = vob.lr_scheduler.build_scheduler(cfg, opt, n_iter_per_epoch=7)
+    assert abs(opt.param_groups[0]["lr"] - 5e-7) < 1e-12          # timm initialises the groups to warmup_lr_init
+    for t in (0, 1, 13, 14, 15, 40, 69, 70, 100):
+        sched.step_update(t)
+        want = TO.cosine_lr(t, 5e-4, 70, 5e-6, 14, 5e-7)
+        assert all(abs(gp["lr"] - want) < 1e-12 for gp in opt.param_groups), t

@@ -221,13 +221,14 @@ dq_convert_kernel(float4* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, lo
 
 // ------------------------------------------------------------------------------------------------ loss backward
 // loss = sum |x - x_rec| * mask / (sum mask + 1e-5) / C  (model.py:75-76), x_rec = PixelShuffle(Y) (model.py:61-66):
-//   dY[b*(n+1) + 1 + tok][c p^2 + i p + j] = gscale * mask[b, tok] * sign(x_rec - x) / ((sums[1] + 1e-5) * C)
+//   dY[b*(n+1) + 1 + tok][c p^2 + i p + j] = *gscale * mask[b, tok] * sign(x_rec - x) / ((sums[1] + 1e-5) * C)
 // CLS rows of dY are zero.  One thread per 8 consecutive columns (one patch row of one channel when p == 8).
 __global__ void __launch_bounds__(256)
 mim_loss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ x_rec, const float* __restrict__ mask,
-                    const double* __restrict__ sums, float gscale, __nv_bfloat16* __restrict__ dY, int B, int C, int H, int W, int p) {
+                    const double* __restrict__ sums, const float* __restrict__ gscale, __nv_bfloat16* __restrict__ dY, int B, int C, int H,
+                    int W, int p) {
   const int Wp = W / p, n = (H / p) * Wp, ldy = C * p * p, groups = ldy / 8;
-  const float coef = gscale / (static_cast<float>(sums[1] + 1e-5) * static_cast<float>(C));
+  const float coef = (gscale != nullptr ? *gscale : 1.0f) / (static_cast<float>(sums[1] + 1e-5) * static_cast<float>(C));
   const long long total = static_cast<long long>(B) * (n + 1) * groups;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {

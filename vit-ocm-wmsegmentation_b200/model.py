@@ -4,8 +4,13 @@ Mirrors ``VisionTransformerForSimMIM`` (SSS/model.py:11-53), ``MIM`` (:55-89) an
 (:91-108): same constructor arguments, parameter names (``mask_token``, ``decoder.0.{weight,bias}``) and
 return values.  The arithmetic runs in libvitocm.so (``vitocm_mim_forward``): patch-embedding GEMM with the
 mask-token mix fused in its epilogue, the transformer blocks, final norm, the 1x1-conv decoder as a
-per-token tcgen05 GEMM, PixelShuffle + masked L1 in one pass.  There is no autograd here: the backward
-kernels of the training step (SSS/mim.py:153-180) are not built yet, so ``loss`` carries no graph.
+per-token tcgen05 GEMM, PixelShuffle + masked L1 in one pass.
+
+Training (SSS/mim.py:153-182): when gradients are enabled and a parameter requires them, ``MIM.forward`` runs
+``vitocm_mim_train_forward`` inside a ``torch.autograd.Function`` whose backward is ``vitocm_mim_backward`` --
+``loss.sum().backward()``, ``clip_grad_norm_`` and ``optimizer.step()`` of the reference loop work unchanged.  All
+parameters then live in one flat fp32 buffer and their ``.grad`` in another (``MIM.flatten_parameters``), which is what
+the fused clip + AdamW kernel (``optimizer.FusedAdamW``) and the NCCL gradient all-reduce operate on.
 ``MaskGenerator`` (SSS/data.py:163-186) is host-side numpy in the reference and stays so.
 """
 from __future__ import annotations
@@ -84,8 +89,64 @@ class VisionTransformerForSimMIM(VisionTransformer):
         h = w = int((N - 1) ** 0.5)
         return z.permute(0, 2, 1).reshape(B, self.embed_dim, h, w)     # a view change, no arithmetic
 
-    def no_weight_decay(self):
-        return {"pos_embed", "cls_token", "mask_token"}
+    # NB: like the reference's encoder (SSS/model.py:11-53, vit.py:135-258) this class has no ``no_weight_decay``: the
+    # skip list of build_pretrain_optimizer is empty and cls_token / pos_embed / mask_token (3-D) do get weight decay.
+
+    def _mim_pos_graph(self, x):
+        """The position table as a differentiable function of ``pos_embed`` (training): [N, D] on x's device."""
+        size = self.img_size[0] if isinstance(self.img_size, (list, tuple)) else self.img_size
+        pos = self.pos_embed
+        if size == 224:
+            return pos[0]
+        p = self.patch_embed.patch_size
+        N = pos.shape[1] - 1
+        dim = pos.shape[-1]
+        w0 = h0 = size // p + 0.1
+        s_ = int(math.sqrt(N))
+        grid = nn.functional.interpolate(pos[:, 1:].reshape(1, s_, s_, dim).permute(0, 3, 1, 2),
+                                         scale_factor=(w0 / math.sqrt(N), h0 / math.sqrt(N)), mode="bicubic")
+        return torch.cat((pos[:, :1], grid.permute(0, 2, 3, 1).reshape(1, -1, dim)), dim=1)[0]
+
+
+class _MIMStep(torch.autograd.Function):
+    """loss = MIM(x, mask) with the backward of SSS/mim.py:174 in libvitocm.  Parameter gradients do not travel through
+    autograd: vitocm_mim_backward accumulates them straight into the flat ``.grad`` buffer of ``MIM`` (the parameters are
+    passed as inputs only so that autograd schedules this node); the position table's gradient is returned."""
+
+    @staticmethod
+    def forward(ctx, mim, xx, maskf, pos, *params):
+        enc = mim.encoder
+        eng = enc._ensure_engine()
+        lib = _lib.load_library()
+        B, C, H, W = xx.shape
+        N = enc._tokens(xx)
+        x_rec = torch.empty_like(xx)
+        sums = torch.empty(2, dtype=torch.float64, device=xx.device)
+        need = int(lib.vitocm_mim_train_workspace_bytes(eng, B, N))
+        if mim._train_ws is None or mim._train_ws.numel() < need or mim._train_ws.device != xx.device:
+            mim._train_ws = None
+            mim._train_ws = torch.empty(need, dtype=torch.uint8, device=xx.device)
+        posc = pos.detach().to(torch.float32).contiguous()
+        check(lib.vitocm_mim_train_forward(eng, ptr(xx), B, H, W, ptr(posc), ptr(maskf), ptr(x_rec), ptr(sums), ptr(mim._train_ws),
+                                           mim._train_ws.numel(), cur_stream()))
+        ctx.mim = mim
+        ctx.save_for_backward(xx, maskf, x_rec, sums)
+        ctx.pos_shape = tuple(pos.shape)
+        ctx.mark_non_differentiable(x_rec)
+        loss = (sums[0] / (sums[1] + 1e-5) / mim.in_chans).to(torch.float32)
+        return loss, x_rec
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_xrec):
+        mim = ctx.mim
+        xx, maskf, x_rec, sums = ctx.saved_tensors
+        B, C, H, W = xx.shape
+        mim._prepare_grads()
+        dpos = torch.empty(ctx.pos_shape, dtype=torch.float32, device=xx.device)
+        gs = grad_loss.detach().to(torch.float32).reshape(1).contiguous()      # stays on the device: no host sync
+        check(_lib.load_library().vitocm_mim_backward(mim.encoder._engine, ptr(xx), B, H, W, ptr(maskf), ptr(x_rec), ptr(sums), ptr(gs),
+                                                      ptr(dpos), ptr(mim._train_ws), mim._train_ws.numel(), cur_stream()))
+        return (None, None, None, dpos) + (None,) * len(mim._param_list)
 
 
 class MIM(nn.Module):
@@ -105,10 +166,118 @@ class MIM(nn.Module):
             raise NotImplementedError("vitocm MIM: encoder_stride must equal the patch size")
         # the decoder's parameters are loaded into the encoder's engine under their state-dict names
         self.encoder._extra_engine_params = lambda: [("decoder.0.weight", self.decoder[0].weight), ("decoder.0.bias", self.decoder[0].bias)]
+        self._train_ws = None
+        self._param_list = None      # [(engine name, parameter)] in flat-buffer order
+        self._pflat = self._gflat = None
+        self._grad_views = None
+        self._grads_bound_to = None
+        self._flat_ptrs = None
+
+    # ------------------------------------------------------------------ training plumbing
+    def _engine_name(self, pname: str) -> str:
+        return pname[len("encoder."):] if pname.startswith("encoder.") else pname
+
+    def flatten_parameters(self):
+        """Move every parameter into one flat fp32 device buffer (``self._pflat``) and give it a ``.grad`` view into a
+        second one (``self._gflat``): the engine aliases the weights (vitocm_bind_weight), the backward kernels accumulate
+        straight into the gradients (vitocm_bind_grad), and clip / AdamW / the NCCL all-reduce are single flat operations.
+        Offsets are 16-byte aligned.  Idempotent; call after ``.cuda()``."""
+        named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+        dev = named[0][1].device
+        if dev.type != "cuda":
+            raise _lib.VitocmError("vitocm MIM training needs the parameters on a CUDA device (no CPU path)")
+        ptrs = tuple(p.data_ptr() for _, p in named)
+        if self._pflat is not None and ptrs == self._flat_ptrs:
+            return self
+        offs, total = [], 0
+        for _, p in named:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        pflat = torch.zeros(total, dtype=torch.float32, device=dev)
+        gflat = torch.zeros(total, dtype=torch.float32, device=dev)
+        views = []
+        with torch.no_grad():
+            for (n, p), o in zip(named, offs):
+                pflat[o:o + p.numel()].copy_(p.detach().reshape(-1).to(torch.float32))
+                p.data = pflat[o:o + p.numel()].view(p.shape)
+                g = gflat[o:o + p.numel()].view(p.shape)
+                if p.grad is not None:
+                    g.copy_(p.grad)
+                p.grad = g
+                views.append(g)
+        self._pflat, self._gflat, self._grad_views, self._flat_offsets = pflat, gflat, views, offs
+        self._param_list = [(self._engine_name(n), p) for n, p in named]
+        self._flat_ptrs = tuple(p.data_ptr() for _, p in named)
+        self._grads_bound_to = None
+        self.encoder._bind_weights = True
+        return self
+
+    def decay_flags(self, skip_list=(), skip_keywords=()):
+        """uint8 [numel of the flat buffer]: 1 where AdamW applies weight decay -- the has_decay / no_decay split of
+        get_pretrain_param_groups (SSS/optimizer.py:14-33): none for 1-D parameters, biases, and the skip list."""
+        self.flatten_parameters()
+        flags = torch.zeros(self._pflat.numel(), dtype=torch.uint8, device=self._pflat.device)
+        for (n, p), o in zip([(n, p) for n, p in self.named_parameters() if p.requires_grad], self._flat_offsets):
+            no_decay = len(p.shape) == 1 or n.endswith(".bias") or n in skip_list or any(k in n for k in skip_keywords)
+            if not no_decay:
+                flags[o:o + p.numel()] = 1
+        return flags
+
+    def _prepare_grads(self):
+        """Before a backward: every parameter's ``.grad`` must be its view into the flat buffer.  After
+        ``optimizer.zero_grad()`` (set_to_none) the views are re-attached and the buffer is zeroed (one memset)."""
+        self.flatten_parameters()
+        none = [p.grad is None for _, p in self._param_list]
+        if all(none):
+            self._gflat.zero_()
+            for (_, p), g in zip(self._param_list, self._grad_views):
+                p.grad = g
+        elif any(none) or any(p.grad is not g for (_, p), g in zip(self._param_list, self._grad_views)):
+            for (_, p), g in zip(self._param_list, self._grad_views):     # mixed state: keep what is there, re-home it
+                if p.grad is None:
+                    g.zero_()
+                elif p.grad is not g:
+                    g.copy_(p.grad)
+                p.grad = g
+        eng = self.encoder._engine
+        key = (eng.value, self._gflat.data_ptr())
+        if self._grads_bound_to != key:
+            lib = _lib.load_library()
+            for (name, p), g in zip(self._param_list, self._grad_views):
+                if name != "pos_embed":
+                    check(lib.vitocm_bind_grad(eng, name.encode(), g.data_ptr()))
+            self._grads_bound_to = key
+
+    def all_reduce_grads(self, group=None):
+        """Data parallelism over one process per GPU: sum the flat gradient buffer across ranks (NCCL over NVLink).
+        The reference trains under nn.DataParallel with ``loss.sum().backward()`` (SSS/mim.py:102,174): the gradient is
+        the SUM over replicas of each replica's mean loss, which is exactly all_reduce(SUM) of the per-rank gradients."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self._gflat, op=dist.ReduceOp.SUM, group=group)
+
+    def _forward_train(self, x, mask):
+        enc = self.encoder
+        self.flatten_parameters()
+        xx = enc._check_input(x)
+        B = xx.shape[0]
+        N = enc._tokens(xx)
+        pos = enc._mim_pos_graph(xx)
+        assert pos.shape[0] == N, "position table does not match the token count (img_size vs input size)"
+        m = mask.detach().reshape(B, -1).to(device=xx.device, dtype=torch.float32).contiguous()
+        loss, x_rec = _MIMStep.apply(self, xx, m, pos, *[p for _, p in self._param_list])
+        mask_up = mask.repeat_interleave(self.patch_size, 1).repeat_interleave(self.patch_size, 2).unsqueeze(1).contiguous()
+        return loss, x_rec, mask_up
+
+    def forward(self, x, mask):
+        """-> (loss, x_rec, mask upsampled to pixels) (model.py:71-77).  With gradients enabled the loss carries the
+        backward of the training step; under ``torch.no_grad()`` this is a plain evaluation."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_train(x, mask)
+        return self._forward_eval(x, mask)
 
     @torch.no_grad()
-    def forward(self, x, mask):
-        """-> (loss, x_rec, mask upsampled to pixels) (model.py:71-77)."""
+    def _forward_eval(self, x, mask):
         enc = self.encoder
         xx = enc._check_input(x)
         eng = enc._ensure_engine()

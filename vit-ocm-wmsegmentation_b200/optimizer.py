@@ -1,0 +1,130 @@
+"""Drop-in for the reference's ``optimizer.py`` (SSS/optimizer.py) on B200: parameter grouping + AdamW for MIM
+pre-training, with the update itself in libvitocm (one fused kernel over the flat parameter / gradient / moment
+buffers of ``model.MIM``: gradient clipping coefficient, decoupled weight decay, Adam moments, bias correction).
+
+    optimizer = build_pretrain_optimizer(config, model, logger)        # SSS/mim.py:106
+    ...
+    loss.sum().backward()
+    grad_norm = clip_grad_norm_(model.parameters(), config.TRAIN.CLIP_GRAD)   # this module's, or torch's
+    optimizer.step()
+
+``clip_grad_norm_`` here only measures the norm (fp64 sum of squares on the device, no host sync) and leaves the scaling
+to the next ``optimizer.step()``, which folds min(1, max_norm / (norm + 1e-6)) into the update and writes the clipped
+gradient back -- the values ``torch.nn.utils.clip_grad_norm_`` + ``torch.optim.AdamW`` would produce.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, cur_stream, ptr
+
+
+def check_keywords_in_name(name, keywords=()):
+    return any(k in name for k in keywords)
+
+
+def get_pretrain_param_groups(model, logger=None, skip_list=(), skip_keywords=()):
+    """SSS/optimizer.py:14-33: no weight decay for 1-D parameters, biases, and the skip list / keywords."""
+    has_decay, no_decay, has_decay_name, no_decay_name = [], [], [], []
+    for name, param in model.named_parameters():
+        if not param.requires_grad:
+            continue
+        if len(param.shape) == 1 or name.endswith(".bias") or (name in skip_list) or check_keywords_in_name(name, skip_keywords):
+            no_decay.append(param)
+            no_decay_name.append(name)
+        else:
+            has_decay.append(param)
+            has_decay_name.append(name)
+    if logger is not None:
+        logger.info(f'No decay params: {no_decay_name}')
+        logger.info(f'Has decay params: {has_decay_name}')
+    return [{'params': has_decay}, {'params': no_decay, 'weight_decay': 0.}]
+
+
+def _unwrap(model):
+    return model.module if hasattr(model, "module") else model
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW semantics (decoupled weight decay, bias correction, eps outside the square root) executed by
+    ``vitocm_adamw_step`` on the flat buffers of a ``model.MIM``.  ``param_groups`` keeps the reference's two groups so
+    that LR schedulers that write ``group['lr']`` work unchanged (both groups must carry the same lr)."""
+
+    def __init__(self, model, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05, skip_list=(), skip_keywords=()):
+        mim = _unwrap(model)
+        mim.flatten_parameters()
+        groups = get_pretrain_param_groups(mim, None, skip_list, skip_keywords)
+        super().__init__(groups, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.mim = mim
+        self.decay = mim.decay_flags(skip_list, skip_keywords)
+        self.exp_avg = torch.zeros_like(mim._pflat)
+        self.exp_avg_sq = torch.zeros_like(mim._pflat)
+        self.steps = 0
+        self._sumsq = torch.zeros(1, dtype=torch.float64, device=mim._pflat.device)
+        self._pending_max_norm = 0.0
+
+    def measure_grad_norm(self, max_norm: float = 0.0) -> torch.Tensor:
+        """Global L2 norm of the flat gradient (device tensor); max_norm > 0 arms the clip of the next step()."""
+        g = self.mim._gflat
+        check(_lib.load_library().vitocm_grad_sumsq(ptr(g), g.numel(), ptr(self._sumsq), cur_stream()))
+        self._pending_max_norm = float(max_norm)
+        return self._sumsq.sqrt().to(torch.float32)[0]
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        mim = self.mim
+        if mim._pflat is None or any(p.grad is None for _, p in mim._param_list):
+            raise _lib.VitocmError("FusedAdamW.step: no gradients (call loss.backward() first)")
+        g0, g1 = self.param_groups[0], self.param_groups[1]
+        if g0["lr"] != g1["lr"]:
+            raise _lib.VitocmError("FusedAdamW: both parameter groups must carry the same learning rate")
+        self.steps += 1
+        b1, b2 = g0["betas"]
+        n = mim._pflat.numel()
+        check(_lib.load_library().vitocm_adamw_step(ptr(mim._pflat), ptr(mim._gflat), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.decay), n,
+                                                    float(g0["lr"]), float(b1), float(b2), float(g0["eps"]), float(g0["weight_decay"]),
+                                                    self.steps, float(self._pending_max_norm), float(grad_scale),
+                                                    ptr(self._sumsq) if self._pending_max_norm > 0 else None, cur_stream()))
+        self._pending_max_norm = 0.0
+        mim.encoder.refresh_engine()      # asynchronous bf16 repack of the updated masters (vitocm_refresh_weights)
+        return None
+
+    def zero_grad(self, set_to_none: bool = False):
+        """One memset of the flat gradient buffer; the ``.grad`` views stay attached."""
+        mim = self.mim
+        if mim._gflat is not None:
+            mim._gflat.zero_()
+            for (_, p), g in zip(mim._param_list, mim._grad_views):
+                p.grad = g
+
+
+def clip_grad_norm_(parameters, max_norm, optimizer: FusedAdamW | None = None):
+    """``torch.nn.utils.clip_grad_norm_`` for the fused path: returns the total norm (device tensor, no sync) and arms
+    the clip coefficient of the next ``optimizer.step()``.  ``parameters`` may be the model, its ``.parameters()`` or a
+    FusedAdamW; the optimizer is found through the model it was built for."""
+    opt = optimizer
+    if opt is None and isinstance(parameters, FusedAdamW):
+        opt = parameters
+    if opt is None:
+        mim = _unwrap(parameters) if hasattr(parameters, "parameters") else None
+        opt = getattr(mim, "_fused_optimizer", None) if mim is not None else None
+    if opt is None:
+        raise _lib.VitocmError("clip_grad_norm_: pass the FusedAdamW optimizer (or the model it was built for)")
+    return opt.measure_grad_norm(max_norm)
+
+
+def build_pretrain_optimizer(args, model, logger=None):
+    """SSS/optimizer.py:47-78 (AdamW branch; lr / betas / eps / weight decay from args.TRAIN)."""
+    mim = _unwrap(model)
+    skip = mim.no_weight_decay() if hasattr(mim, 'no_weight_decay') else {}
+    skip_keywords = mim.no_weight_decay_keywords() if hasattr(mim, 'no_weight_decay_keywords') else {}
+    name = args.TRAIN.OPTIMIZER.NAME.lower()
+    if name != 'adamw':
+        raise NotImplementedError("vitocm: only the AdamW branch of build_pretrain_optimizer (the reference's default) is fused")
+    opt = FusedAdamW(mim, lr=args.TRAIN.BASE_LR, betas=tuple(args.TRAIN.OPTIMIZER.BETAS), eps=args.TRAIN.OPTIMIZER.EPS,
+                     weight_decay=args.TRAIN.WEIGHT_DECAY, skip_list=skip, skip_keywords=skip_keywords)
+    mim._fused_optimizer = opt
+    if logger is not None:
+        logger.info(opt)
+    return opt

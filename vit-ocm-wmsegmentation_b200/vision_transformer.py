@@ -209,8 +209,17 @@ class VisionTransformer(nn.Module):
         return (self.precision, torch.cuda.current_device(),
                 tuple((p.data_ptr(), p._version) for _, p in self._engine_params()), self.pos_embed._version)
 
+    def _bindable(self):
+        """Training mode: every engine parameter is fp32, contiguous, 16-byte aligned and already on the current
+        device, so the engine can use the storage in place (vitocm_bind_weight) instead of a host round trip."""
+        dev = torch.cuda.current_device()
+        return all(p.is_cuda and p.device.index == dev and p.dtype == torch.float32 and p.is_contiguous() and p.data_ptr() % 16 == 0
+                   for _, p in self._engine_params())
+
     def refresh_engine(self):
-        """(Re)load the parameters into the C engine: repack to bf16 hi/lo etc."""
+        """(Re)load the parameters into the C engine: repack to bf16 hi/lo etc.  With ``self._bind_weights`` set (the
+        training path) the engine aliases the parameters' device storage and a change of their values only costs an
+        asynchronous repack (vitocm_refresh_weights)."""
         lib = _lib.load_library()
         if not torch.cuda.is_available():
             raise _lib.VitocmError("vitocm needs a CUDA device (B200, sm_100a); there is no CPU path")
@@ -221,11 +230,23 @@ class VisionTransformer(nn.Module):
             handle = C.c_void_p()
             check(lib.vitocm_create(C.byref(cfg), C.byref(handle)))
             self._engine = handle
+            self._bound_ptrs = None
             check(lib.vitocm_set_concurrency(handle, self.lanes))
-        for name, p in self._engine_params():
-            host = p.detach().to(device="cpu", dtype=torch.float32).contiguous()
-            check(lib.vitocm_load_weight(self._engine, name.encode(), host.data_ptr(), host.numel()))
-        check(lib.vitocm_finalize_weights(self._engine))
+        if getattr(self, "_bind_weights", False) and self._bindable():
+            ptrs = tuple(p.data_ptr() for _, p in self._engine_params())
+            if ptrs != self._bound_ptrs:
+                for name, p in self._engine_params():
+                    check(lib.vitocm_bind_weight(self._engine, name.encode(), p.data_ptr(), p.numel()))
+                check(lib.vitocm_finalize_weights(self._engine))
+                self._bound_ptrs = ptrs
+            else:
+                check(lib.vitocm_refresh_weights(self._engine, cur_stream()))
+        else:
+            for name, p in self._engine_params():
+                host = p.detach().to(device="cpu", dtype=torch.float32).contiguous()
+                check(lib.vitocm_load_weight(self._engine, name.encode(), host.data_ptr(), host.numel()))
+            check(lib.vitocm_finalize_weights(self._engine))
+            self._bound_ptrs = None
         self._engine_key = self._weights_key()
         self._pos_cache = {}
 
