@@ -18,7 +18,10 @@
 //               a 3-D tensor map [B][N][D] clips the rows beyond the image.
 // The same shared-memory image of P / dS serves as MN-major A (dV, dK) and as K-major A (dQ): no transposes.
 // dK_j, dV_j leave through registers as bf16 into the dQKV activation; dQacc is converted by dq_convert_kernel.
-// Warp roles: warps 0..3 softmax/drain, warp 4 = TMA producer, warp 5 = MMA issuer + TMEM allocator.
+// Warp roles: warps 0..7 softmax/drain (quadrant = warp % 4, key-column half = warp / 4: two warps per scheduler hide each
+// other's MUFU / TMEM latencies -- the backward needs no row reductions, so a row splits freely), warp 8 = TMA producer,
+// warp 9 = MMA issuer + TMEM allocator.  Ragged tails are trimmed: a short key block runs S / dP at N = 32 per 32 keys and
+// only the dQ k-steps that hold keys; a short query tile only the dV / dK k-steps that hold queries.
 #pragma once
 #include "ptx.cuh"
 
@@ -36,7 +39,8 @@ struct AttnBwdArgs {
   long long ld;
 };
 
-constexpr int ABW_THREADS = 192;   // warps 0..3 softmax / drain, warp 4 TMA, warp 5 MMA
+constexpr int ABW_SM_WARPS = 8;    // softmax / drain warps: two per TMEM lane quadrant, each takes half of the key columns
+constexpr int ABW_THREADS = (ABW_SM_WARPS + 2) * 32;   // + warp 8 = TMA producer, warp 9 = MMA issuer
 constexpr int ABW_TILE = 128 * 64 * 2;          // 16 KB: [128 rows][64 bf16]
 constexpr int ABW_S_COL = 0, ABW_DP_COL = 128, ABW_DV_COL = 256, ABW_DK_COL = 320, ABW_DQ_COL = 384;
 constexpr int ABW_TMEM_COLS = 512;
@@ -79,7 +83,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   int kv_len = N - j * 128;
   kv_len = kv_len > 128 ? 128 : kv_len;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == ABW_SM_WARPS && lane == 0) {
     ptx::prefetch_tmap(&tmap_qkv);
     ptx::prefetch_tmap(&tmap_do);
     ptx::prefetch_tmap(&tmap_dq);
@@ -89,12 +93,12 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       ptx::mbar_init(qdo_empty + 8 * s, 1);
     }
     ptx::mbar_init(sdp_full, 1);
-    ptx::mbar_init(pds_full, 4);
+    ptx::mbar_init(pds_full, ABW_SM_WARPS);
     ptx::mbar_init(dq_full, 1);
-    ptx::mbar_init(dq_empty, 4);
+    ptx::mbar_init(dq_empty, ABW_SM_WARPS);
     ptx::fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == ABW_SM_WARPS + 1) {
     ptx::tmem_alloc(tmem_ptr_smem, ABW_TMEM_COLS);
     ptx::tmem_relinquish();
   }
@@ -103,7 +107,8 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   ptx::tc_fence_after();
   const uint32_t tmem_base = ptx::lds_u32(tmem_ptr_smem);
 
-  if (warp == 4) {
+  const int nch = (kv_len + 31) >> 5;          // 32-key chunks of this key block that hold keys
+  if (warp == ABW_SM_WARPS) {
     // ===================== TMA producer =====================
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(kv_full, 2 * ABW_TILE);
@@ -117,10 +122,10 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         ptx::tma_load_2d(smem_qdo + slot * 2 * ABW_TILE + ABW_TILE, &tmap_do, qdo_full + 8 * slot, h * 64, row_base + i * 128);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == ABW_SM_WARPS + 1) {
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc_s = ptx::make_idesc(128, 128, false, false);   // S, dP: both operands K-major
+      const uint32_t idesc_s = ptx::make_idesc(128, nch * 32, false, false);  // S, dP: both operands K-major; only the chunks with keys
       constexpr uint32_t idesc_t = ptx::make_idesc(128, 64, true, true);      // dV, dK: A (P / dS) and B (dO / Q) MN-major
       constexpr uint32_t idesc_q = ptx::make_idesc(128, 64, false, true);     // dQ: A = dS K-major, B = K_j MN-major
       const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_k, 1024, 0);
@@ -152,36 +157,57 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         const uint64_t q_desc_mn = ptx::make_smem_desc_sw128(smem_qdo + slot * 2 * ABW_TILE, 1024, 1024);
         const uint64_t do_desc_mn = ptx::desc_advance(q_desc_mn, ABW_TILE);
         const uint32_t acc0 = i > 0 ? 1u : 0u;
+        int q_len = N - i * 128;
+        q_len = q_len > 128 ? 128 : q_len;
+        const int qsteps = (q_len + 15) >> 4;      // 16-row steps that hold queries (P = dS = 0 beyond q_len inside them)
         // dV += P^T dO_i,  dK += dS^T Q_i: 16 query rows (2048 B of every atom) per MMA
+        if (qsteps == 8) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          ptx::umma_bf16_ss(tmem_base + ABW_DV_COL, ptx::desc_advance(p_desc_mn, k * 2048), ptx::desc_advance(do_desc_mn, k * 2048), idesc_t, k ? 1u : acc0);
+          for (int k = 0; k < 8; ++k)
+            ptx::umma_bf16_ss(tmem_base + ABW_DV_COL, ptx::desc_advance(p_desc_mn, k * 2048), ptx::desc_advance(do_desc_mn, k * 2048), idesc_t, k ? 1u : acc0);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          ptx::umma_bf16_ss(tmem_base + ABW_DK_COL, ptx::desc_advance(ds_desc_mn, k * 2048), ptx::desc_advance(q_desc_mn, k * 2048), idesc_t, k ? 1u : acc0);
+          for (int k = 0; k < 8; ++k)
+            ptx::umma_bf16_ss(tmem_base + ABW_DK_COL, ptx::desc_advance(ds_desc_mn, k * 2048), ptx::desc_advance(q_desc_mn, k * 2048), idesc_t, k ? 1u : acc0);
+        } else {
+#pragma unroll 1
+          for (int k = 0; k < qsteps; ++k)
+            ptx::umma_bf16_ss(tmem_base + ABW_DV_COL, ptx::desc_advance(p_desc_mn, k * 2048), ptx::desc_advance(do_desc_mn, k * 2048), idesc_t, k ? 1u : acc0);
+#pragma unroll 1
+          for (int k = 0; k < qsteps; ++k)
+            ptx::umma_bf16_ss(tmem_base + ABW_DK_COL, ptx::desc_advance(ds_desc_mn, k * 2048), ptx::desc_advance(q_desc_mn, k * 2048), idesc_t, k ? 1u : acc0);
+        }
         ptx::umma_commit(qdo_empty + 8 * slot);   // Q_i / dO_i no longer needed
         // dQ_i = dS K_j: 16 keys per MMA (32 B inside a 64-key atom of dS; 2048 B of K_j)
         if (i > 0) {
           ptx::mbar_wait(dq_empty, (i - 1) & 1, 44);
           ptx::tc_fence_after();
         }
+        if (kv_len == 128) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          ptx::umma_bf16_ss(tmem_base + ABW_DQ_COL, ptx::desc_advance(ds_desc_k, (k >> 2) * ABW_TILE + (k & 3) * 32),
-                            ptx::desc_advance(k_desc_mn, k * 2048), idesc_q, k ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)
+            ptx::umma_bf16_ss(tmem_base + ABW_DQ_COL, ptx::desc_advance(ds_desc_k, (k >> 2) * ABW_TILE + (k & 3) * 32),
+                              ptx::desc_advance(k_desc_mn, k * 2048), idesc_q, k ? 1u : 0u);
+        } else {
+          const int ksteps = (kv_len + 15) >> 4;   // dS = 0 beyond kv_len inside the last step
+#pragma unroll 1
+          for (int k = 0; k < ksteps; ++k)
+            ptx::umma_bf16_ss(tmem_base + ABW_DQ_COL, ptx::desc_advance(ds_desc_k, (k >> 2) * ABW_TILE + (k & 3) * 32),
+                              ptx::desc_advance(k_desc_mn, k * 2048), idesc_q, k ? 1u : 0u);
+        }
         ptx::umma_commit(dq_full);
         if (i + 1 < n_q) issue_sdp(i + 1);        // overlaps the dQ drain of tile i
       }
     }
-  } else if (warp < 4) {
-    // ===================== softmax / drain warps =====================
+  } else {
+    // ===================== softmax / drain warps (0 .. ABW_SM_WARPS-1) =====================
     const int q = warp & 3;
+    const int half = warp >> 2;    // which half of the key columns (S / dP phase), of the dQ columns, and dK (0) or dV (1) at the end
     const int r = q * 32 + lane;   // query row inside the tile (S, dP, dQ phases) or key row (final dK / dV drain)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float sl2 = args.scale_log2;
     const float* lse_bh = args.lse2 + (static_cast<long long>(b) * args.heads + h) * N;
     const float* delta_bh = args.delta + (static_cast<long long>(b) * args.heads + h) * N;
-    const uint32_t stg = smem_dq + q * 8192;
+    const uint32_t stg = smem_dq + q * 8192 + half * 4096;
     for (int i = 0; i < n_q; ++i) {
       const int qrow = i * 128 + r;
       const bool qvalid = qrow < N;
@@ -192,7 +218,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       // P / dS of the previous tile have been consumed: the MMA warp committed dq_full(i-1) after those MMAs and
       // this warp waited for it before draining dQ_{i-1}
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 2 * half; c < 2 * half + 2 && c < nch; ++c) {
         uint32_t s[32], dp[32];
         ptx::tmem_ld_32x32b_x32(lane_addr + ABW_S_COL + c * 32, s);
         ptx::tmem_ld_32x32b_x32(lane_addr + ABW_DP_COL + c * 32, dp);
@@ -226,35 +252,29 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       // ---- dQ_i: TMEM -> fp32 boxes -> reduce-add into dQacc[b, i*128 + q*32 .., h*64 ..]
       ptx::mbar_wait(dq_full, i & 1, 46);
       ptx::tc_fence_after();
-      uint32_t t0[32], t1[32];
-      ptx::tmem_ld_32x32b_x32(lane_addr + ABW_DQ_COL, t0);
-      ptx::tmem_ld_32x32b_x32(lane_addr + ABW_DQ_COL + 32, t1);
-      if (lane == 0) ptx::bulk_wait_read0();   // the previous tile's reduce has finished reading the boxes
+      uint32_t t0[32];
+      ptx::tmem_ld_32x32b_x32(lane_addr + ABW_DQ_COL + half * 32, t0);
+      if (lane == 0) ptx::bulk_wait_read0();   // the previous tile's reduce has finished reading the box
       __syncwarp();
       ptx::tmem_ld_wait(t0);
-      ptx::tmem_ld_wait(t1);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(dq_empty);
       const int sw = lane & 7;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        ptx::sts_v4(stg + lane * 128 + ((g ^ sw) << 4), t0[4 * g], t0[4 * g + 1], t0[4 * g + 2], t0[4 * g + 3]);
-        ptx::sts_v4(stg + 4096 + lane * 128 + ((g ^ sw) << 4), t1[4 * g], t1[4 * g + 1], t1[4 * g + 2], t1[4 * g + 3]);
-      }
+      for (int g = 0; g < 8; ++g) ptx::sts_v4(stg + lane * 128 + ((g ^ sw) << 4), t0[4 * g], t0[4 * g + 1], t0[4 * g + 2], t0[4 * g + 3]);
       ptx::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        tma_reduce_add_3d(&tmap_dq, stg, h * 64, i * 128 + q * 32, b);
-        tma_reduce_add_3d(&tmap_dq, stg + 4096, h * 64 + 32, i * 128 + q * 32, b);
+      if (lane == 0 && i * 128 + q * 32 < N) {
+        tma_reduce_add_3d(&tmap_dq, stg, h * 64 + half * 32, i * 128 + q * 32, b);
         ptx::bulk_commit();
       }
     }
     // ---- dK_j, dV_j: complete once dq_full of the last tile fired (the commit covers all earlier MMAs)
     {
       __nv_bfloat16* orow = args.dqkv + static_cast<long long>(row_base + j * 128 + r) * args.ld + h * 64;
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {   // 0: dK -> column block D, 1: dV -> column block 2D
+      {   // warps 0..3: dK -> column block D; warps 4..7: dV -> column block 2D
+        const int which = half;
         __nv_bfloat16* o = orow + (which == 0 ? D : 2 * D);
 #pragma unroll
         for (int c = 0; c < 64; c += 32) {
@@ -278,7 +298,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == ABW_SM_WARPS + 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, ABW_TMEM_COLS);
   }

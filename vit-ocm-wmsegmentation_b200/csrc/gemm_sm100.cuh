@@ -39,7 +39,8 @@ struct GemmArgs {
   int nterms;         // 1 (bf16 mode) or 3 (split mode: hi*hi + hi*lo + lo*hi)
   int lo_k;           // split mode: column where the lo halves of A and B start (= K)
   const float* bias;  // [N] or nullptr
-  int split_out;      // bf16 outputs only: also write lo = bf16(v - hi) at column offset lo_off
+  int split_out;      // bf16 outputs only: 1 = also write lo = bf16(v - hi) at column offset lo_off;
+                      // 2 (EPI_BIAS_GELU_BF16, training) = also write the pre-activation acc + bias at column offset lo_off
   int lo_off;
   // EPI_RESID_LN only: the LayerNorm that consumes the updated residual stream (vit.py:107/111), fused here
   const float* ln_gamma;
@@ -575,6 +576,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bv[j];
+        uint32_t pre[16];   // training: the GELU input, kept for the backward (vit.py:59)
+        if (EPI == EPI_BIAS_GELU_BF16 && args.split_out == 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pre[j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        }
         if (EPI == EPI_BIAS_GELU_BF16) {
           if (args.nterms == 1) {
 #pragma unroll
@@ -620,7 +626,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int j = 0; j < 4; ++j)
             ptx::sts_v4(rowaddr + ((j ^ sw) << 4), ptx::pack_bf16x2(v[8 * j], v[8 * j + 1]), ptx::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                         ptx::pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), ptx::pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-          if (args.split_out) {
+          if (EPI == EPI_BIAS_GELU_BF16 && args.split_out == 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              ptx::sts_v4(rowaddr + Cfg::STG_BOX_BYTES + ((j ^ sw) << 4), pre[4 * j], pre[4 * j + 1], pre[4 * j + 2], pre[4 * j + 3]);
+          } else if (args.split_out) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] -= ptx::bf16_round(v[j]);
 #pragma unroll

@@ -44,46 +44,67 @@ gelu_fwd_kernel(const uint4* __restrict__ pre, uint4* __restrict__ hid, long lon
   }
 }
 
-// dh <- dh * gelu'(pre)   (in place)
-__global__ void __launch_bounds__(256)
-gelu_bwd_kernel(const uint4* __restrict__ pre, uint4* __restrict__ dh, long long n8) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const uint4 v = pre[i], g = dh[i];
-    const uint32_t in[4] = {v.x, v.y, v.z, v.w}, gi[4] = {g.x, g.y, g.z, g.w};
-    uint32_t out[4];
+// dh <- dh * gelu'(pre) (in place) and, fused, the fc1 bias gradient db[c] += sum_rows dh[row][c].
+// blockDim.x = ncols / 8 threads (one 16-byte column group each), rows grid-strided, four rows in flight per thread;
+// pre has a row pitch of pre_ld8 16-byte groups (it shares a buffer with the activations).
+__global__ void __launch_bounds__(1024)
+gelu_bwd_kernel(const uint4* __restrict__ pre, long long pre_ld8, uint4* __restrict__ dh, int M, int ncols8, float* __restrict__ db) {
+  const int c = threadIdx.x;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int row0 = blockIdx.x * 4; row0 < M; row0 += gridDim.x * 4) {
+    uint4 v[4], g[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      out[k] = ptx::pack_bf16x2(bf16lo(gi[k]) * gelu_grad_erf(bf16lo(in[k])), bf16hi(gi[k]) * gelu_grad_erf(bf16hi(in[k])));
-    dh[i] = make_uint4(out[0], out[1], out[2], out[3]);
+    for (int u = 0; u < 4; ++u) {
+      if (row0 + u < M) {
+        v[u] = pre[static_cast<long long>(row0 + u) * pre_ld8 + c];
+        g[u] = dh[static_cast<long long>(row0 + u) * ncols8 + c];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (row0 + u < M) {
+        const uint32_t in[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, gi[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+        uint32_t out[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float d0 = bf16lo(gi[k]) * gelu_grad_erf(bf16lo(in[k])), d1 = bf16hi(gi[k]) * gelu_grad_erf(bf16hi(in[k]));
+          acc[2 * k] += d0;
+          acc[2 * k + 1] += d1;
+          out[k] = ptx::pack_bf16x2(d0, d1);
+        }
+        dh[static_cast<long long>(row0 + u) * ncols8 + c] = make_uint4(out[0], out[1], out[2], out[3]);
+      }
+    }
   }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) atomicAdd(db + 8 * c + k, acc[k]);
 }
 
 // ------------------------------------------------------------------------------------------------ bias gradient
-// out[c] += sum_m G[m][c]; block = (64 column pairs) x (4 row lanes); grid = (ceil(ncols / 128), row splits)
-__global__ void __launch_bounds__(256)
+// out[c] += sum_m G[m][c].  blockDim = (ncols / 8 column groups of 16 bytes, ROWS row lanes); rows grid-strided,
+// four rows in flight per thread; one atomicAdd per column and block.
+__global__ void __launch_bounds__(1024)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ G, long long ld, int M, int ncols, float* __restrict__ out) {
-  __shared__ float red[4][128];
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  const int col = blockIdx.x * 128 + 2 * tx;
-  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
-  const int m0 = blockIdx.y * rows_per;
-  const int m1 = min(M, m0 + rows_per);
-  float s0 = 0.f, s1 = 0.f;
-  if (col < ncols) {
-    for (int m = m0 + ty; m < m1; m += 4) {
-      const uint32_t v = *reinterpret_cast<const uint32_t*>(G + static_cast<long long>(m) * ld + col);
-      s0 += bf16lo(v);
-      s1 += bf16hi(v);
+  const int c = threadIdx.x;                 // column group
+  const int lanes = blockDim.y;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int row0 = (blockIdx.x * lanes + threadIdx.y) * 4; row0 < M; row0 += gridDim.x * lanes * 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      v[u] = row0 + u < M ? *reinterpret_cast<const uint4*>(G + static_cast<long long>(row0 + u) * ld + 8 * c) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t in[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[2 * k] += bf16lo(in[k]);
+        acc[2 * k + 1] += bf16hi(in[k]);
+      }
     }
   }
-  red[ty][2 * tx] = s0;
-  red[ty][2 * tx + 1] = s1;
-  __syncthreads();
-  if (threadIdx.x < 128) {
-    const int c = blockIdx.x * 128 + threadIdx.x;
-    if (c < ncols) atomicAdd(out + c, (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]));
-  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) atomicAdd(out + 8 * c + k, acc[k]);
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
@@ -91,23 +112,26 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ G, long long ld, int M, int
 //   g = dy * gamma;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
 //   dX[row] = (accumulate ? dX[row] : 0) + dx   (the residual branch, vit.py:110-111)   and   dXb = bf16(dX)
 //   dgamma += dy * xhat,  dbeta += dy           (per-lane partials -> shared memory -> one atomicAdd per block and column)
+//   dbias_out += column sums of the new dX      (= the bias gradient of the Linear whose output was added into this
+//                                                residual stream: proj of this block / fc2 of the previous one)
 template <int NV>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, long long ld_dy, const float* __restrict__ gamma,
               float* __restrict__ dX, __nv_bfloat16* __restrict__ dXb, float* __restrict__ dgamma, float* __restrict__ dbeta,
-              int accumulate, int M, int D, float eps) {
+              float* __restrict__ dbias_out, int accumulate, int M, int D, float eps) {
   constexpr int CNT = NV > 0 ? NV : LN_MAX_VEC;
-  extern __shared__ float ln_red[];   // [2][D]
+  extern __shared__ float ln_red[];   // [3][D]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int nvec = D >> 2;
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) ln_red[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) ln_red[i] = 0.f;
   __syncthreads();
-  float4 gm[CNT], accg[CNT], accb[CNT];
+  float4 gm[CNT], accg[CNT], accb[CNT], acco[CNT];
 #pragma unroll
   for (int i = 0; i < CNT; ++i) {
     const int idx = lane + 32 * i;
     accg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     accb[i] = accg[i];
+    acco[i] = accg[i];
     gm[i] = (NV > 0 || idx < nvec) ? __ldg(reinterpret_cast<const float4*>(gamma) + idx) : accg[i];
   }
   const float inv_d = 1.0f / static_cast<float>(D);
@@ -165,6 +189,7 @@ ln_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
         o.w += rstd * (g[i].w - c1 - v[i].w * c2);
         dxr[idx] = o;
         dbr[idx] = make_uint2(ptx::pack_bf16x2(o.x, o.y), ptx::pack_bf16x2(o.z, o.w));
+        acco[i].x += o.x; acco[i].y += o.y; acco[i].z += o.z; acco[i].w += o.w;
       }
     }
   }
@@ -176,12 +201,17 @@ ln_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
       atomicAdd(ln_red + 4 * idx + 2, accg[i].z); atomicAdd(ln_red + 4 * idx + 3, accg[i].w);
       atomicAdd(ln_red + D + 4 * idx, accb[i].x); atomicAdd(ln_red + D + 4 * idx + 1, accb[i].y);
       atomicAdd(ln_red + D + 4 * idx + 2, accb[i].z); atomicAdd(ln_red + D + 4 * idx + 3, accb[i].w);
+      if (dbias_out != nullptr) {
+        atomicAdd(ln_red + 2 * D + 4 * idx, acco[i].x); atomicAdd(ln_red + 2 * D + 4 * idx + 1, acco[i].y);
+        atomicAdd(ln_red + 2 * D + 4 * idx + 2, acco[i].z); atomicAdd(ln_red + 2 * D + 4 * idx + 3, acco[i].w);
+      }
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     atomicAdd(dgamma + i, ln_red[i]);
     atomicAdd(dbeta + i, ln_red[D + i]);
+    if (dbias_out != nullptr) atomicAdd(dbias_out + i, ln_red[2 * D + i]);
   }
 }
 
@@ -204,18 +234,35 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __re
   }
 }
 
-// dqkv[row][0:D] = bf16(acc[row][:]);  acc <- 0   (4 fp32 per thread)
+// dqkv[row][0:D] = bf16(acc[row][:]);  acc <- 0.  One warp per pair of rows (grid-strided); all loads of a pass (up to
+// 2 rows x 4 float4 per lane) are issued before the first store so that a warp keeps 4 KB in flight.
 __global__ void __launch_bounds__(256)
-dq_convert_kernel(float4* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long ld, long long M, int D) {
+dq_convert_kernel(float4* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long ld, int M, int D) {
   const int nvec = D >> 2;
-  const long long total = M * nvec;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = i / nvec;
-    const int c = static_cast<int>(i - row * nvec);
-    const float4 v = acc[i];
-    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    *reinterpret_cast<uint2*>(dqkv + row * ld + 4 * c) = make_uint2(ptx::pack_bf16x2(v.x, v.y), ptx::pack_bf16x2(v.z, v.w));
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row0 = 2 * (blockIdx.x * wpb + (threadIdx.x >> 5)); row0 < M; row0 += 2 * gridDim.x * wpb) {
+    for (int base = 0; base < nvec; base += 128) {
+      float4 v[2][4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = base + lane + 32 * u;
+          if (row0 + r < M && c < nvec) v[r][u] = acc[static_cast<long long>(row0 + r) * nvec + c];
+        }
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = base + lane + 32 * u;
+          if (row0 + r < M && c < nvec) {
+            acc[static_cast<long long>(row0 + r) * nvec + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<uint2*>(dqkv + static_cast<long long>(row0 + r) * ld + 4 * c) =
+                make_uint2(ptx::pack_bf16x2(v[r][u].x, v[r][u].y), ptx::pack_bf16x2(v[r][u].z, v[r][u].w));
+          }
+        }
+    }
   }
 }
 

@@ -346,7 +346,7 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
   // measured (profiles/r01_gemm_pair.txt): pairs win once the launch is long enough to amortise the cluster lockstep
   // (M = 137k: qkv +21 %, fc2 +6 %, fc1 +3 %) and for long K at any size; mode 2 forces pairs wherever legal
   const bool pair_pays = pair_mode == 2 || M >= 65536 || (K >= 1024 && M >= 4096);
-  if (pair_mode != 0 && pair_pays && !split_in && !split_out && M >= 4 * GEMM_BM && (N % 256 == 0 || N % 192 == 0 || N % 128 == 0)) {
+  if (pair_mode != 0 && pair_pays && !split_in && split_out != 1 && M >= 4 * GEMM_BM && (N % 256 == 0 || N % 192 == 0 || N % 128 == 0)) {
     static const int gelu_bn = [] { const char* v = getenv("VITOCM_GELU_BN"); return v ? atoi(v) : 192; }();   // measured: 835 vs 794 TFLOP/s
     int pbn = N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 128);
     if (epi == EPI_BIAS_GELU_BF16 && gelu_bn == 192 && N % 192 == 0) pbn = 192;   // 12 epilogue warps instead of 8
@@ -357,6 +357,7 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
     TRY(make_tmap(&pc, out, of32, ldo, M, ldo, 32, 32, of32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
     GemmArgs pg{};
     pg.M = M; pg.N = N; pg.kblocks = K / GEMM_BK; pg.nterms = 1; pg.lo_k = K; pg.bias = bias; pg.out_f32 = reinterpret_cast<float*>(out);
+    pg.split_out = split_out; pg.lo_off = lo_off;
     { static const int dbgp = [] { const char* v = getenv("VITOCM_GEMM_DEBUG"); return v ? atoi(v) : 0; }(); pg.debug = dbgp; }
     if (pbn == 256) return launch_gemm_pair_bn<256>(epi, pa, pb, pc, pg, e->num_sms, st);
     if (pbn == 192) return launch_gemm_pair_bn<192>(epi, pa, pb, pc, pg, e->num_sms, st);
