@@ -243,6 +243,10 @@ int vitocm_attention_bwd(vitocm_engine* e, const void* qkv, int64_t ld, const vo
                          const float* lse2, float* delta, float* dqacc, void* dqkv, int64_t ldq, int B, int n_tokens,
                          void* stream);
 
+/* Diagnostics: SM-clock stamps of one CTA of the last vitocm_attention_bwd run under VITOCM_ABW_DEBUG=2: host int64
+ * [role: softmax warp 0, MMA thread][query tile < 8][event < 8]. */
+int vitocm_debug_abw_timeline(int64_t* host_out);
+
 /* Optional per-kernel-class device timing: when enabled every launch is bracketed by CUDA events on
  * its own stream; vitocm_profile_read synchronises, sums milliseconds and launch counts per class
  * (vitocm_profile_classes() slots, names from vitocm_profile_class_name) and clears the log. */

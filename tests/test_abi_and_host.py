@@ -124,6 +124,14 @@ def _gloo_worker(rank, world, port, tmp):
         hist = torch.full((3, 256), rank + 1, dtype=torch.int64)
         dist.all_reduce(hist)
         assert int(hist[0, 0]) == sum(range(1, world + 1))
+        # MIM data parallelism: the flat gradient buffer is summed over ranks (DataParallel + loss.sum(), SSS/mim.py:102,174)
+        from functools import partial
+        enc = v.VisionTransformerForSimMIM(patch_size=8, embed_dim=128, depth=1, num_heads=2, mlp_ratio=4, img_size=[32], qkv_bias=True,
+                                           norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+        mim = v.MIM(encoder=enc, encoder_stride=8)
+        mim._gflat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+        mim.all_reduce_grads()
+        assert torch.equal(mim._gflat, torch.arange(10, dtype=torch.float32) * sum(range(1, world + 1)))
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

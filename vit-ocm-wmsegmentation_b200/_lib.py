@@ -78,6 +78,7 @@ SIGNATURES = {
     "vitocm_attention_fwd_lse": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "vitocm_attention_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int64, c_int, c_int, c_void_p]),
+    "vitocm_debug_abw_timeline": (c_int, [c_void_p]),
     "vitocm_launch_count": (c_int64, []),
     "vitocm_profile_enable": (c_int, [c_int]),
     "vitocm_profile_classes": (c_int, []),

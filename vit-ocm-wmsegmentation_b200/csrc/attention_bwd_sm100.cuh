@@ -14,7 +14,7 @@
 //   MMA   dV += P^T dO_i, dK += dS^T Q_i                     (A = P / dS read MN-major: the contraction runs over the
 //                                                             rows q; B = dO_i / Q_i MN-major)  -> TMEM dV | dK
 //   MMA   dQ_i = dS K_j                                      (A = dS K-major, B = K_j MN-major) -> TMEM dQ
-//   warps 0..3: dQ tile -> shared memory -> TMA reduce-add (fp32, done by the L2) into dQacc[b, i*128.., h*64..];
+//   softmax warps: dQ tile -> shared memory -> TMA reduce-add (fp32, done by the L2) into dQacc[b, i*128.., h*64..];
 //               a 3-D tensor map [B][N][D] clips the rows beyond the image.
 // The same shared-memory image of P / dS serves as MN-major A (dV, dK) and as K-major A (dQ): no transposes.
 // dK_j, dV_j leave through registers as bf16 into the dQKV activation; dQacc is converted by dq_convert_kernel.
@@ -37,15 +37,25 @@ struct AttnBwdArgs {
   const float* delta; // [B][H][N]
   __nv_bfloat16* dqkv;  // [B*N][ld]: dK at column D + h*64, dV at 2D + h*64 (dQ comes from dq_convert_kernel)
   long long ld;
+  int debug;          // diagnostics (VITOCM_ABW_DEBUG): 1 = skip the dQ reduce-add
 };
 
 constexpr int ABW_SM_WARPS = 8;    // softmax / drain warps: two per TMEM lane quadrant, each takes half of the key columns
-constexpr int ABW_THREADS = (ABW_SM_WARPS + 2) * 32;   // + warp 8 = TMA producer, warp 9 = MMA issuer
+constexpr int ABW_DRAIN_WARP0 = 8;   // warps 8..11: dQ drain (one per TMEM lane quadrant)
+constexpr int ABW_TMA_WARP = 12, ABW_MMA_WARP = 13;   // warps 14, 15 idle (setmaxnreg works on whole warpgroups)
+constexpr int ABW_THREADS = 512;
+constexpr int ABW_REGS_SOFTMAX = 184, ABW_REGS_OTHER = 72;   // 8 x 32 x 184 + 8 x 32 x 72 = 64 K registers
 constexpr int ABW_TILE = 128 * 64 * 2;          // 16 KB: [128 rows][64 bf16]
 constexpr int ABW_S_COL = 0, ABW_DP_COL = 128, ABW_DV_COL = 256, ABW_DK_COL = 320, ABW_DQ_COL = 384;
 constexpr int ABW_TMEM_COLS = 512;
 // shared memory: K | V | (Q, dO) x 2 | P (2 atoms) | dS (2 atoms) | dQ staging (4 warps x 2 boxes x 4 KB) | barriers
 constexpr int ABW_SMEM_BYTES = 2 * ABW_TILE + 4 * ABW_TILE + 2 * ABW_TILE + 2 * ABW_TILE + 32768 + 1024 + 256;
+
+// diagnostics (VITOCM_ABW_DEBUG=2): SM-clock stamps of CTA (1,0,0) -- [role 0 = softmax warp 0, 1 = MMA thread][query tile < 8][event < 8]
+__device__ long long g_abw_timeline[2 * 8 * 8];
+__device__ __forceinline__ void abw_stamp(bool on, int role, int i, int ev) {
+  if (on && i < 8) g_abw_timeline[(role * 8 + i) * 8 + ev] = clock64();
+}
 
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tmap, uint32_t smem_src, int c0, int c1, int c2) {
   asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -83,7 +93,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   int kv_len = N - j * 128;
   kv_len = kv_len > 128 ? 128 : kv_len;
 
-  if (warp == ABW_SM_WARPS && lane == 0) {
+  if (warp == ABW_TMA_WARP && lane == 0) {
     ptx::prefetch_tmap(&tmap_qkv);
     ptx::prefetch_tmap(&tmap_do);
     ptx::prefetch_tmap(&tmap_dq);
@@ -95,10 +105,10 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     ptx::mbar_init(sdp_full, 1);
     ptx::mbar_init(pds_full, ABW_SM_WARPS);
     ptx::mbar_init(dq_full, 1);
-    ptx::mbar_init(dq_empty, ABW_SM_WARPS);
+    ptx::mbar_init(dq_empty, 4);
     ptx::fence_barrier_init();
   }
-  if (warp == ABW_SM_WARPS + 1) {
+  if (warp == ABW_MMA_WARP) {
     ptx::tmem_alloc(tmem_ptr_smem, ABW_TMEM_COLS);
     ptx::tmem_relinquish();
   }
@@ -108,7 +118,9 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   const uint32_t tmem_base = ptx::lds_u32(tmem_ptr_smem);
 
   const int nch = (kv_len + 31) >> 5;          // 32-key chunks of this key block that hold keys
-  if (warp == ABW_SM_WARPS) {
+  const bool tl = args.debug == 2 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  if (warp >= ABW_SM_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ABW_REGS_OTHER));
+  if (warp == ABW_TMA_WARP) {
     // ===================== TMA producer =====================
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(kv_full, 2 * ABW_TILE);
@@ -122,7 +134,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         ptx::tma_load_2d(smem_qdo + slot * 2 * ABW_TILE + ABW_TILE, &tmap_do, qdo_full + 8 * slot, h * 64, row_base + i * 128);
       }
     }
-  } else if (warp == ABW_SM_WARPS + 1) {
+  } else if (warp == ABW_MMA_WARP) {
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
       const uint32_t idesc_s = ptx::make_idesc(128, nch * 32, false, false);  // S, dP: both operands K-major; only the chunks with keys
@@ -152,8 +164,12 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       issue_sdp(0);
       for (int i = 0; i < n_q; ++i) {
         const int slot = i & 1;
+        abw_stamp(tl, 1, i, 0);
         ptx::mbar_wait(pds_full, i & 1, 43);     // P_i, dS_i in shared memory; S / dP columns read
         ptx::tc_fence_after();
+        abw_stamp(tl, 1, i, 1);
+        // the next tile's logits go first: the softmax warps work on them while the tensor core runs dV / dK / dQ of tile i
+        if (i + 1 < n_q) issue_sdp(i + 1);
         const uint64_t q_desc_mn = ptx::make_smem_desc_sw128(smem_qdo + slot * 2 * ABW_TILE, 1024, 1024);
         const uint64_t do_desc_mn = ptx::desc_advance(q_desc_mn, ABW_TILE);
         const uint32_t acc0 = i > 0 ? 1u : 0u;
@@ -195,81 +211,133 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                               ptx::desc_advance(k_desc_mn, k * 2048), idesc_q, k ? 1u : 0u);
         }
         ptx::umma_commit(dq_full);
-        if (i + 1 < n_q) issue_sdp(i + 1);        // overlaps the dQ drain of tile i
+        abw_stamp(tl, 1, i, 2);
       }
     }
-  } else {
-    // ===================== softmax / drain warps (0 .. ABW_SM_WARPS-1) =====================
+  } else if (warp >= ABW_DRAIN_WARP0 && warp < ABW_DRAIN_WARP0 + 4) {
+    // ===================== dQ drain warps =====================
+    // dQ of tile i: TMEM -> two fp32 boxes -> reduce-add into dQacc[b, i*128 + q*32 .., h*64 ..]; off the softmax warps' path
     const int q = warp & 3;
-    const int half = warp >> 2;    // which half of the key columns (S / dP phase), of the dQ columns, and dK (0) or dV (1) at the end
-    const int r = q * 32 + lane;   // query row inside the tile (S, dP, dQ phases) or key row (final dK / dV drain)
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t stg = smem_dq + q * 8192;
+    for (int i = 0; i < n_q; ++i) {
+      ptx::mbar_wait(dq_full, i & 1, 46);
+      ptx::tc_fence_after();
+      if (lane == 0) ptx::bulk_wait_read0();   // the previous tile's reduces have finished reading the boxes
+      __syncwarp();
+      const int sw = lane & 7;
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {           // one 32-column box at a time (register budget of this warpgroup)
+        uint32_t t0[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + ABW_DQ_COL + hb * 32, t0);
+        ptx::tmem_ld_wait(t0);
+        if (hb == 1) {                           // both halves are in registers / shared memory: dQ columns free
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(dq_empty);
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          ptx::sts_v4(stg + hb * 4096 + lane * 128 + ((g ^ sw) << 4), t0[4 * g], t0[4 * g + 1], t0[4 * g + 2], t0[4 * g + 3]);
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && i * 128 + q * 32 < N && args.debug != 1) {
+        tma_reduce_add_3d(&tmap_dq, stg, h * 64, i * 128 + q * 32, b);
+        tma_reduce_add_3d(&tmap_dq, stg + 4096, h * 64 + 32, i * 128 + q * 32, b);
+        ptx::bulk_commit();
+      }
+    }
+    if (lane == 0) ptx::bulk_wait_all0();
+  } else if (warp < ABW_SM_WARPS) {
+    // ===================== softmax warps (0 .. ABW_SM_WARPS-1) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ABW_REGS_SOFTMAX));
+    const int q = warp & 3;
+    const int half = warp >> 2;    // which half of the key columns (S / dP phase), and dK (0) or dV (1) at the end
+    const int r = q * 32 + lane;   // query row inside the tile (S, dP phases) or key row (final dK / dV drain)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float sl2 = args.scale_log2;
     const float* lse_bh = args.lse2 + (static_cast<long long>(b) * args.heads + h) * N;
     const float* delta_bh = args.delta + (static_cast<long long>(b) * args.heads + h) * N;
-    const uint32_t stg = smem_dq + q * 8192 + half * 4096;
+    const uint64_t sl2_2 = ptx::dup_f32x2(sl2);
+    const uint64_t sc_2 = ptx::dup_f32x2(args.scale);
+    // rows beyond the image: LSE = +inf makes P = 0 and with it dS = 0 (dP is finite: the rows hold other tokens or zeros)
+    float lse_next = r < N ? __ldg(lse_bh + r) : INFINITY;
+    float dlt_next = r < N ? __ldg(delta_bh + r) : 0.f;
     for (int i = 0; i < n_q; ++i) {
-      const int qrow = i * 128 + r;
-      const bool qvalid = qrow < N;
-      const float lse = qvalid ? __ldg(lse_bh + qrow) : INFINITY;     // invalid query rows: P = 0
-      const float dlt = qvalid ? __ldg(delta_bh + qrow) : 0.f;
+      const float lse = lse_next, dlt = dlt_next;
+      {   // next tile's row statistics: issued now, consumed one tile later (global-load latency off the critical path)
+        const int qn = (i + 1) * 128 + r;
+        lse_next = qn < N ? __ldg(lse_bh + qn) : INFINITY;
+        dlt_next = qn < N ? __ldg(delta_bh + qn) : 0.f;
+      }
+      const uint64_t nlse_2 = ptx::dup_f32x2(-lse);
+      const uint64_t ndl_2 = ptx::dup_f32x2(-dlt * args.scale);
+      abw_stamp(tl && warp == 0, 0, i, 0);
       ptx::mbar_wait(sdp_full, i & 1, 45);
       ptx::tc_fence_after();
-      // P / dS of the previous tile have been consumed: the MMA warp committed dq_full(i-1) after those MMAs and
-      // this warp waited for it before draining dQ_{i-1}
-#pragma unroll 1
-      for (int c = 2 * half; c < 2 * half + 2 && c < nch; ++c) {
-        uint32_t s[32], dp[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + ABW_S_COL + c * 32, s);
-        ptx::tmem_ld_32x32b_x32(lane_addr + ABW_DP_COL + c * 32, dp);
-        ptx::tmem_ld_wait(s);
-        ptx::tmem_ld_wait(dp);
-        uint32_t pp[16], dd[16];
+      abw_stamp(tl && warp == 0, 0, i, 1);
+      // ---- P = exp2(S * sl2 - LSE2), dS = P * (dP * scale - Delta * scale) for this warp's (up to) two 32-key chunks, on the
+      //      packed f32x2 pipe; results wait in registers until the previous tile's MMAs have released the P / dS buffers
+      uint32_t pp[2][16], dd[2][16];
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
-          float p0 = ptx::ex2_approx(fmaf(__uint_as_float(s[2 * t]), sl2, -lse));
-          float p1 = ptx::ex2_approx(fmaf(__uint_as_float(s[2 * t + 1]), sl2, -lse));
-          if (c * 32 + 2 * t >= kv_len) p0 = 0.f;
-          if (c * 32 + 2 * t + 1 >= kv_len) p1 = 0.f;
-          const float d0 = p0 * (__uint_as_float(dp[2 * t]) - dlt) * args.scale;
-          const float d1 = p1 * (__uint_as_float(dp[2 * t + 1]) - dlt) * args.scale;
-          pp[t] = ptx::pack_bf16x2(p0, p1);
-          dd[t] = ptx::pack_bf16x2(qvalid ? d0 : 0.f, qvalid ? d1 : 0.f);
-        }
-        // 32 keys = 4 chunks of 16 B in row r of atom c / 2 (SWIZZLE_128B: chunk ^ (r & 7))
-        const uint32_t off = (c >> 1) * ABW_TILE + r * 128;
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * half + cc;
+        if (c < nch) {
+          uint32_t sv[32], dp[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + ABW_S_COL + c * 32, sv);
+          ptx::tmem_ld_32x32b_x32(lane_addr + ABW_DP_COL + c * 32, dp);
+          ptx::tmem_ld_wait(sv);
+          ptx::tmem_ld_wait(dp);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t ch = static_cast<uint32_t>((((c & 1) * 4 + g) ^ (r & 7)) << 4);
-          ptx::sts_v4(smem_p + off + ch, pp[4 * g], pp[4 * g + 1], pp[4 * g + 2], pp[4 * g + 3]);
-          ptx::sts_v4(smem_ds + off + ch, dd[4 * g], dd[4 * g + 1], dd[4 * g + 2], dd[4 * g + 3]);
+          for (int t = 0; t < 16; ++t) {
+            const uint64_t a2 = ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sv[2 * t]), __uint_as_float(sv[2 * t + 1])), sl2_2, nlse_2);
+            float a0, a1;
+            ptx::unpack_f32x2(a2, a0, a1);
+            const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);
+            const uint64_t g2 = ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(dp[2 * t]), __uint_as_float(dp[2 * t + 1])), sc_2, ndl_2);
+            const uint64_t d2 = ptx::mul_f32x2(ptx::pack_f32x2(p0, p1), g2);
+            float d0, d1;
+            ptx::unpack_f32x2(d2, d0, d1);
+            pp[cc][t] = ptx::pack_bf16x2(p0, p1);
+            dd[cc][t] = ptx::pack_bf16x2(d0, d1);
+          }
+          if (c * 32 + 32 > kv_len) {   // ragged key block: keys beyond the image contribute nothing
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const int k0 = c * 32 + 2 * t;
+              const uint32_t keep = (k0 < kv_len ? 0x0000ffffu : 0u) | (k0 + 1 < kv_len ? 0xffff0000u : 0u);
+              pp[cc][t] &= keep;
+              dd[cc][t] &= keep;
+            }
+          }
         }
       }
-      ptx::tc_fence_before();
+      ptx::tc_fence_before();     // S / dP reads are done (ordered before the pds_full arrive below)
+      abw_stamp(tl && warp == 0, 0, i, 2);
+      if (i > 0) ptx::mbar_wait(dq_full, (i - 1) & 1, 47);   // previous tile's dV / dK / dQ MMAs retired: P / dS may be overwritten
+      abw_stamp(tl && warp == 0, 0, i, 3);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * half + cc;
+        if (c < nch) {
+          // 32 keys = 4 chunks of 16 B in row r of atom c / 2 (SWIZZLE_128B: chunk ^ (r & 7))
+          const uint32_t off = (c >> 1) * ABW_TILE + r * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t ch = static_cast<uint32_t>((((c & 1) * 4 + g) ^ (r & 7)) << 4);
+            ptx::sts_v4(smem_p + off + ch, pp[cc][4 * g], pp[cc][4 * g + 1], pp[cc][4 * g + 2], pp[cc][4 * g + 3]);
+            ptx::sts_v4(smem_ds + off + ch, dd[cc][4 * g], dd[cc][4 * g + 1], dd[cc][4 * g + 2], dd[cc][4 * g + 3]);
+          }
+        }
+      }
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(pds_full);
-      // ---- dQ_i: TMEM -> fp32 boxes -> reduce-add into dQacc[b, i*128 + q*32 .., h*64 ..]
-      ptx::mbar_wait(dq_full, i & 1, 46);
-      ptx::tc_fence_after();
-      uint32_t t0[32];
-      ptx::tmem_ld_32x32b_x32(lane_addr + ABW_DQ_COL + half * 32, t0);
-      if (lane == 0) ptx::bulk_wait_read0();   // the previous tile's reduce has finished reading the box
-      __syncwarp();
-      ptx::tmem_ld_wait(t0);
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(dq_empty);
-      const int sw = lane & 7;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) ptx::sts_v4(stg + lane * 128 + ((g ^ sw) << 4), t0[4 * g], t0[4 * g + 1], t0[4 * g + 2], t0[4 * g + 3]);
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0 && i * 128 + q * 32 < N) {
-        tma_reduce_add_3d(&tmap_dq, stg, h * 64 + half * 32, i * 128 + q * 32, b);
-        ptx::bulk_commit();
-      }
+      abw_stamp(tl && warp == 0, 0, i, 4);
     }
+    ptx::mbar_wait(dq_full, (n_q - 1) & 1, 48);
+    ptx::tc_fence_after();
     // ---- dK_j, dV_j: complete once dq_full of the last tile fired (the commit covers all earlier MMAs)
     {
       __nv_bfloat16* orow = args.dqkv + static_cast<long long>(row_base + j * 128 + r) * args.ld + h * 64;
@@ -298,7 +366,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == ABW_SM_WARPS + 1) {
+  if (warp == ABW_MMA_WARP) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, ABW_TMEM_COLS);
   }

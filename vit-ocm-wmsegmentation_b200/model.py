@@ -271,8 +271,9 @@ class MIM(nn.Module):
 
     def forward(self, x, mask):
         """-> (loss, x_rec, mask upsampled to pixels) (model.py:71-77).  With gradients enabled the loss carries the
-        backward of the training step; under ``torch.no_grad()`` this is a plain evaluation."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        backward of the training step (``model.train()``, as SSS/mim.py:154 sets it); in ``eval()`` mode or under
+        ``torch.no_grad()`` this is a plain evaluation."""
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return self._forward_train(x, mask)
         return self._forward_eval(x, mask)
 

@@ -63,6 +63,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self.steps = 0
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=mim._pflat.device)
         self._pending_max_norm = 0.0
+        mim._fused_optimizer = self        # lets clip_grad_norm_(model, ...) find its optimizer
 
     def measure_grad_norm(self, max_norm: float = 0.0) -> torch.Tensor:
         """Global L2 norm of the flat gradient (device tensor); max_norm > 0 arms the clip of the next step()."""
