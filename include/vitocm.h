@@ -90,6 +90,14 @@ int vitocm_set_concurrency(vitocm_engine* e, int lanes);
 int vitocm_forward_cls_attn(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, float* out_rows,
                             void* ws, size_t ws_bytes, int chunk_tiles, void* stream);
 
+/* The same forward for a LIST of query tokens (SSS/analyse_attention.py:183-247: compute_attention(..., query=q) for a
+ * region query) and, optionally, the last block's K features (SSS/analyse_attention.py:139-163, SSS/eval.py:186-202, the
+ * input of the k-means feature clustering): queries = DEVICE int32 [nq] token indices in [0, N) (0 = CLS, 1 + i = patch i);
+ * out_rows [B][heads][nq][N] fp32 = get_last_selfattention(x)[:, :, queries, :]; k_out [B][N][D] fp32 (K projection of the
+ * last block including its bias, heads side by side = qkv[1] of vit.py:81 before the head split) or NULL. */
+int vitocm_forward_query_attn(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const int* queries, int nq,
+                              float* out_rows, float* k_out, void* ws, size_t ws_bytes, int chunk_tiles, void* stream);
+
 /* prepare_tokens (vit.py:198-209): patch embedding + CLS + position add -> X [B][N][D] fp32.
  * mask [B][n] fp32 in {0,1} or NULL: SimMIM mask-token mixing (SSS/model.py:31-33). */
 int vitocm_prepare_tokens(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const float* mask,

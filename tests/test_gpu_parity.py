@@ -204,3 +204,32 @@ def test_larger_tile_448_interpolated_pos_matches_oracle(vits_sd):
     assert rel_err(rows, ref) <= 1e-3, rel_err(rows, ref)
     m16 = build_model(cfg4, sd, "bf16", chunk_tiles=1)
     assert rel_err(m16.cls_attention_rows(x.cuda()).cpu().numpy(), ref) <= 2e-2
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_query_token_rows_and_key_features_match_reference_goldens(tiny_sd, precision):
+    """attention rows of arbitrary query tokens (SSS/analyse_attention.py:183-247,
+    compute_attention(..., query=q)) and the last block's K features (SSS/eval.py:186-202), without N x N, against the
+    reference's own get_intermediate_feat outputs (tests/golden/tiny_vit.npz: attn [B,H,N,N], qkv [3,B,H,N,64])."""
+    g = load_golden("tiny_vit.npz")
+    m = build_model(TINY, tiny_sd, precision, chunk_tiles=2)
+    tol = REL[precision]
+    for name in ("a", "c"):
+        x = torch.from_numpy(g[f"{name}/x"]).cuda()
+        ref_attn, ref_qkv = g[f"{name}/attn"], g[f"{name}/qkv"]
+        N = ref_attn.shape[-1]
+        queries = [0, 1, N // 2, N - 1]
+        rows, keys = m.attention_rows(x, queries, return_keys=True)
+        assert tuple(rows.shape) == (x.shape[0], TINY.num_heads, len(queries), N)
+        assert rel_err(rows.cpu().numpy(), ref_attn[:, :, queries, :]) <= tol
+        assert np.allclose(rows.sum(-1).cpu().numpy(), 1.0, atol=1e-4)
+        kerr = np.abs(keys.cpu().numpy() - ref_qkv[1]).max()
+        assert kerr <= (1e-4 if precision == "fp32" else 3e-2) * max(1.0, np.abs(ref_qkv[1]).max()), kerr
+        # the reference call pattern: attentions[0, :, query, 1:] on the lazy object -> served from query rows, no N x N
+        feat, attns, qkvs = m.get_intermediate_feat(x, n=1)
+        q = N // 2
+        sl = attns[0][0, :, q, 1:].cpu().numpy()
+        assert attns[0]._value is None, "a single query row must not materialise the N x N matrix"
+        assert rel_err(sl, ref_attn[0, :, q, 1:]) <= tol
+    with pytest.raises(IndexError):
+        m.attention_rows(x, [N])

@@ -1,5 +1,5 @@
 // Bandwidth-bound kernels of the MIM training step (SSS/mim.py:153-182: loss.backward(), clip_grad_norm_, AdamW):
-//   gelu_fwd_kernel / gelu_bwd_kernel    vit.py:59 (nn.GELU, exact erf form) and its derivative
+//   gelu_bwd_kernel                      derivative of vit.py:59 (nn.GELU; the forward is the fc1 GEMM epilogue) + fc1 bias gradient
 //   colsum_bf16_kernel                   bias gradients: d b = sum_m dY[m, :]
 //   ln_bwd_kernel                        nn.LayerNorm backward (vit.py:107,111,215) fused with the residual-gradient
 //                                        accumulation of Block.forward (vit.py:110-111) and the bf16 copy the next GEMMs read
@@ -20,38 +20,32 @@ __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v <
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
 // ------------------------------------------------------------------------------------------------ GELU
-__device__ __forceinline__ float gelu_grad_erf(float x) {
-  // d/dx [x Phi(x)] = Phi(x) + x phi(x)
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
-}
-
-// hid = gelu(pre), 8 bf16 per thread; n8 = number of 16-byte groups
-__global__ void __launch_bounds__(256)
-gelu_fwd_kernel(const uint4* __restrict__ pre, uint4* __restrict__ hid, long long n8) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const uint4 v = pre[i];
-    const uint32_t in[4] = {v.x, v.y, v.z, v.w};
-    uint32_t out[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float a = bf16lo(in[k]), b = bf16hi(in[k]);
-      out[k] = ptx::pack_bf16x2(0.5f * a * (1.0f + erff(a * 0.70710678118654752440f)), 0.5f * b * (1.0f + erff(b * 0.70710678118654752440f)));
-    }
-    hid[i] = make_uint4(out[0], out[1], out[2], out[3]);
-  }
+// Derivative of the GELU the forward epilogue evaluates (gemm_sm100.cuh, gelu_sigmoid_x2):  gelu(x) = x * s(x),
+// s = sigmoid(t), t = x (a + b u + c u^2), u = min(x^2, 100)  (fitted to the exact erf form, max |error| 2.5e-5):
+//     gelu'(x) = s + x s (1 - s) t'(x),   t' = a + 3 b u + 5 c u^2   (a + b u + c u^2 where u is clamped)
+// max |error| against the exact erf-form derivative 1.1e-4; one ex2 + one rcp per element, so the kernel stays
+// bandwidth bound (erff + expf made it issue bound: 45 instructions per element).
+__device__ __forceinline__ float gelu_grad(float x) {
+  // (a, b, c) = -(coefficients of gelu_sigmoid_x2) / log2(e)
+  constexpr float A = 1.595015768531f, B = 0.074011292043f, C = -0.000703033580f;
+  const float xx = x * x;
+  const float u = fminf(xx, 100.f);
+  const float poly = fmaf(fmaf(C, u, B), u, A);
+  const float s = ptx::rcp_approx(1.0f + ptx::ex2_approx(-1.4426950408889634f * x * poly));
+  const float dt = xx <= 100.f ? fmaf(fmaf(5.0f * C, u, 3.0f * B), u, A) : poly;
+  return fmaf(x * s * (1.0f - s), dt, s);
 }
 
 // dh <- dh * gelu'(pre) (in place) and, fused, the fc1 bias gradient db[c] += sum_rows dh[row][c].
-// blockDim.x = ncols / 8 threads (one 16-byte column group each), rows grid-strided, four rows in flight per thread;
-// pre has a row pitch of pre_ld8 16-byte groups (it shares a buffer with the activations).
+// blockDim = (ncols / 8 column groups of 16 bytes, row lanes); rows grid-strided, four rows in flight per thread; the lanes'
+// column sums meet in shared memory so that a block issues one atomicAdd per column (global atomics are ~60 ps each: with
+// one per thread they cost more than the pass itself at small batch).  pre has a row pitch of pre_ld8 16-byte groups.
 __global__ void __launch_bounds__(1024)
 gelu_bwd_kernel(const uint4* __restrict__ pre, long long pre_ld8, uint4* __restrict__ dh, int M, int ncols8, float* __restrict__ db) {
-  const int c = threadIdx.x;
+  extern __shared__ float gb_red[];   // [lanes][ncols]
+  const int c = threadIdx.x, ty = threadIdx.y, lanes = blockDim.y;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int row0 = blockIdx.x * 4; row0 < M; row0 += gridDim.x * 4) {
+  for (int row0 = (blockIdx.x * lanes + ty) * 4; row0 < M; row0 += gridDim.x * lanes * 4) {
     uint4 v[4], g[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -67,7 +61,7 @@ gelu_bwd_kernel(const uint4* __restrict__ pre, long long pre_ld8, uint4* __restr
         uint32_t out[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float d0 = bf16lo(gi[k]) * gelu_grad_erf(bf16lo(in[k])), d1 = bf16hi(gi[k]) * gelu_grad_erf(bf16hi(in[k]));
+          const float d0 = bf16lo(gi[k]) * gelu_grad(bf16lo(in[k])), d1 = bf16hi(gi[k]) * gelu_grad(bf16hi(in[k]));
           acc[2 * k] += d0;
           acc[2 * k + 1] += d1;
           out[k] = ptx::pack_bf16x2(d0, d1);
@@ -76,13 +70,23 @@ gelu_bwd_kernel(const uint4* __restrict__ pre, long long pre_ld8, uint4* __restr
       }
     }
   }
+  float* mine = gb_red + (static_cast<long long>(ty) * ncols8 + c) * 8;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) atomicAdd(db + 8 * c + k, acc[k]);
+  for (int k = 0; k < 8; ++k) mine[k] = acc[k];
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = 0.f;
+      for (int l = 0; l < lanes; ++l) t += gb_red[(static_cast<long long>(l) * ncols8 + c) * 8 + k];
+      atomicAdd(db + 8 * c + k, t);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ bias gradient
 // out[c] += sum_m G[m][c].  blockDim = (ncols / 8 column groups of 16 bytes, ROWS row lanes); rows grid-strided,
-// four rows in flight per thread; one atomicAdd per column and block.
+// four rows in flight per thread; the lanes' sums meet in shared memory: one atomicAdd per column and block.
 __global__ void __launch_bounds__(1024)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ G, long long ld, int M, int ncols, float* __restrict__ out) {
   const int c = threadIdx.x;                 // column group
@@ -103,8 +107,20 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ G, long long ld, int M, int
       }
     }
   }
+  extern __shared__ float cs_red[];   // [lanes][ncols]: one atomicAdd per column and block
+  const int groups = blockDim.x;
+  float* mine = cs_red + (static_cast<long long>(threadIdx.y) * groups + c) * 8;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) atomicAdd(out + 8 * c + k, acc[k]);
+  for (int k = 0; k < 8; ++k) mine[k] = acc[k];
+  __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = 0.f;
+      for (int l = 0; l < lanes; ++l) t += cs_red[(static_cast<long long>(l) * groups + c) * 8 + k];
+      atomicAdd(out + 8 * c + k, t);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
@@ -422,6 +438,46 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
     p[i] = pi;
     m[i] = mi;
     v[i] = vi;
+  }
+}
+
+// One launch for every Linear weight of the model (bf16 engines): fp32 master [R][C] -> bf16 [R][C] (forward B operand) and
+// bf16 [C][R] (input-gradient B operand).  blockIdx.x walks 32 x 32 tiles; the table gives each matrix its first tile.
+struct RepackEntry {
+  const float* src;
+  __nv_bfloat16* dst;     // [R][C]
+  __nv_bfloat16* dst_t;   // [C][R] or nullptr
+  int R, C;
+  int tile0;              // index of this matrix's first tile
+  int tiles_c;            // tiles per row of tiles
+};
+__global__ void __launch_bounds__(256)
+repack_weights_kernel(const RepackEntry* __restrict__ table, int n_entries) {
+  __shared__ float tile[32][33];
+  int lo = 0, hi = n_entries - 1;
+  const int t = blockIdx.x;
+  while (lo < hi) {            // last entry whose tile0 <= t
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].tile0 <= t) lo = mid; else hi = mid - 1;
+  }
+  const RepackEntry e = table[lo];
+  const int local = t - e.tile0;
+  const int r0 = (local / e.tiles_c) * 32, c0 = (local % e.tiles_c) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int k = ty; k < 32; k += 8) {
+    const int r = r0 + k, c = c0 + tx;
+    float v = 0.f;
+    if (r < e.R && c < e.C) {
+      v = e.src[static_cast<long long>(r) * e.C + c];
+      e.dst[static_cast<long long>(r) * e.C + c] = __float2bfloat16_rn(v);
+    }
+    tile[k][tx] = v;
+  }
+  if (e.dst_t == nullptr) return;
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int c = c0 + k, r = r0 + tx;
+    if (c < e.C && r < e.R) e.dst_t[static_cast<long long>(c) * e.R + r] = __float2bfloat16_rn(tile[tx][k]);
   }
 }
 

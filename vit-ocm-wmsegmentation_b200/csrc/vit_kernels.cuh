@@ -1,7 +1,7 @@
 // Bandwidth-bound ViT kernels (vectorised, coalesced, fp32 statistics):
 //   cls_rows_kernel      SSS/dino/vision_transformer.py:203-207, CLS row (patch rows: gemm_sm100.cuh A_PATCH)
 //   layernorm_kernel     vit.py:107,111 (norm1/norm2) and :215/:234 (final norm), eps = 1e-6
-//   cls_attn_row_kernel  vit.py:80-84 restricted to the CLS query of the last block
+//   cls_attn_row_kernel  vit.py:80-84 restricted to the CLS query (or a list of query tokens, SSS/analyse_attention.py:183-247) of the last block
 //   attn_probs_kernel    vit.py:83-84 full softmax(QK^T) (API-complete get_last_selfattention)
 //   mim_shuffle_loss_kernel  SSS/model.py:61-66,73-76 (PixelShuffle + masked L1 of MIM.forward)
 #pragma once
@@ -111,8 +111,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 __global__ void __launch_bounds__(256)
 cls_attn_row_kernel(const float* __restrict__ X, const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps,
                     const float* __restrict__ Wq /*[D][D] rows = q outputs*/, const float* __restrict__ bq,
-                    const float* __restrict__ Kmat /*[B*N][D] fp32*/, float* __restrict__ out /*[B][H][N]*/, int N, int D,
-                    int heads, float scale) {
+                    const float* __restrict__ Kmat /*[B*N][D] fp32*/, float* __restrict__ out /*[B][H][nq][N]*/, int N, int D,
+                    int heads, float scale, const int* __restrict__ queries /*[nq] token indices or nullptr = {0}*/, int nq) {
   extern __shared__ float cls_smem[];  // xn[D] | q[64] | logits[N] | red[32]
   float* xn = cls_smem;
   float* qv = xn + D;
@@ -120,7 +120,9 @@ cls_attn_row_kernel(const float* __restrict__ X, const float* __restrict__ ln_w,
   float* red = logits + N;
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const float* xr = X + static_cast<long long>(b) * N * D;  // CLS token row
+  const int qi = blockIdx.z;
+  const int token = queries != nullptr ? queries[qi] : 0;    // 0 = the CLS token (SSS/utils.py:232, query = 0)
+  const float* xr = X + (static_cast<long long>(b) * N + token) * D;
 
   // LayerNorm of the CLS row (block-wide two-pass)
   float s = 0.f;
@@ -182,7 +184,7 @@ cls_attn_row_kernel(const float* __restrict__ X, const float* __restrict__ ln_w,
   float gsum = 0.f;
   for (int w = 0; w < nwarps; ++w) gsum += red[w];
   const float inv = 1.0f / gsum;
-  float* o = out + (static_cast<long long>(b) * heads + h) * N;
+  float* o = out + ((static_cast<long long>(b) * heads + h) * nq + qi) * N;
   for (int j = tid; j < N; j += blockDim.x) o[j] = logits[j] * inv;
 }
 

@@ -156,6 +156,9 @@ struct vitocm_engine {
   DevBuf patch_w;   // bf16 [D][2K]  (hi | lo): the conv filter as a K-major GEMM operand
   DevBuf dec_w;     // MIM decoder 1x1 conv weight, bf16 [C p^2][D * parts] (present iff "decoder.0.weight" was loaded)
   DevBuf dec_w_t;   // bf16 [D][C p^2] (training)
+  DevBuf repack_table;   // RepackEntry[] for the one-launch repack of the Linear weights (bf16 engines)
+  int repack_entries = 0, repack_tiles = 0;
+  std::vector<const void*> repack_key;   // the pointers the table was built for
   std::map<std::string, float*> grads;   // vitocm_bind_grad: where vitocm_mim_backward accumulates dL/d(parameter)
   // chunk-level concurrency: independent chunks of tiles run on `lanes` streams (lane 0 = the caller's stream) so that
   // one chunk's kernel tails and bandwidth-bound kernels overlap the other chunk's tensor-bound kernels
@@ -665,6 +668,16 @@ static int repack_weights(vitocm_engine* e, cudaStream_t st) {
     LAUNCH_CHECK();
     return 0;
   };
+  std::vector<RepackEntry> entries;
+  int total_tiles = 0;
+  auto add_entry = [&](DevBuf& dst, DevBuf& dst_t, const float* src, int R, int C) -> int {
+    TRY(dst.alloc(static_cast<size_t>(R) * C * 2));
+    TRY(dst_t.alloc(static_cast<size_t>(R) * C * 2));
+    RepackEntry en{src, dst.as<__nv_bfloat16>(), dst_t.as<__nv_bfloat16>(), R, C, total_tiles, (C + 31) / 32};
+    total_tiles += ((R + 31) / 32) * en.tiles_c;
+    entries.push_back(en);
+    return 0;
+  };
   TRY(pack(e->patch_w, e->w("patch_embed.proj.weight"), D, K, 1));   // always hi | lo: K is tiny, keep the tokens fp32-grade
   for (int l = 0; l < e->cfg.depth; ++l) {
     const std::string pre = "blocks." + std::to_string(l) + ".";
@@ -680,25 +693,40 @@ static int repack_weights(vitocm_engine* e, cudaStream_t st) {
     L.bqkv = e->w(pre + "attn.qkv.bias"); L.bproj = e->w(pre + "attn.proj.bias");
     L.b1 = e->w(pre + "mlp.fc1.bias"); L.b2 = e->w(pre + "mlp.fc2.bias");
     L.wqkv_f32 = e->w(pre + "attn.qkv.weight");
-    TRY(pack(L.wqkv, e->w(pre + "attn.qkv.weight"), 3 * D, D, S));
-    TRY(pack(L.wproj, e->w(pre + "attn.proj.weight"), D, D, S));
-    TRY(pack(L.w1, e->w(pre + "mlp.fc1.weight"), Hd, D, S));
-    TRY(pack(L.w2, e->w(pre + "mlp.fc2.weight"), D, Hd, S));
-    if (l == e->cfg.depth - 1) TRY(pack(L.wk_split, L.wqkv_f32 + static_cast<long long>(D) * D, D, D, 1));
-    if (!S) {
-      TRY(pack_t(L.wqkv_t, e->w(pre + "attn.qkv.weight"), 3 * D, D));
-      TRY(pack_t(L.wproj_t, e->w(pre + "attn.proj.weight"), D, D));
-      TRY(pack_t(L.w1_t, e->w(pre + "mlp.fc1.weight"), Hd, D));
-      TRY(pack_t(L.w2_t, e->w(pre + "mlp.fc2.weight"), D, Hd));
+    if (S) {
+      TRY(pack(L.wqkv, e->w(pre + "attn.qkv.weight"), 3 * D, D, S));
+      TRY(pack(L.wproj, e->w(pre + "attn.proj.weight"), D, D, S));
+      TRY(pack(L.w1, e->w(pre + "mlp.fc1.weight"), Hd, D, S));
+      TRY(pack(L.w2, e->w(pre + "mlp.fc2.weight"), D, Hd, S));
+    } else {   // bf16 engines: plain + transposed copies of all Linear weights in ONE launch (below)
+      TRY(add_entry(L.wqkv, L.wqkv_t, e->w(pre + "attn.qkv.weight"), 3 * D, D));
+      TRY(add_entry(L.wproj, L.wproj_t, e->w(pre + "attn.proj.weight"), D, D));
+      TRY(add_entry(L.w1, L.w1_t, e->w(pre + "mlp.fc1.weight"), Hd, D));
+      TRY(add_entry(L.w2, L.w2_t, e->w(pre + "mlp.fc2.weight"), D, Hd));
     }
+    if (l == e->cfg.depth - 1) TRY(pack(L.wk_split, L.wqkv_f32 + static_cast<long long>(D) * D, D, D, 1));
   }
   (void)P;
   const long long dec_rows = static_cast<long long>(e->cfg.in_chans) * e->cfg.patch_size * e->cfg.patch_size;
   if (e->numel("decoder.0.weight") > 0) {   // MIM decoder (SSS/model.py:61-64), optional
     TRY(need("decoder.0.weight", dec_rows * D));
     TRY(need("decoder.0.bias", dec_rows));
-    TRY(pack(e->dec_w, e->w("decoder.0.weight"), static_cast<int>(dec_rows), D, S));
-    if (!S) TRY(pack_t(e->dec_w_t, e->w("decoder.0.weight"), static_cast<int>(dec_rows), D));
+    if (S) TRY(pack(e->dec_w, e->w("decoder.0.weight"), static_cast<int>(dec_rows), D, S));
+    else TRY(add_entry(e->dec_w, e->dec_w_t, e->w("decoder.0.weight"), static_cast<int>(dec_rows), D));
+  }
+  if (!entries.empty()) {
+    std::vector<const void*> key;
+    for (const RepackEntry& en : entries) { key.push_back(en.src); key.push_back(en.dst); key.push_back(en.dst_t); }
+    if (key != e->repack_key) {   // (re)upload the table only when a pointer changed; the steady-state refresh is one launch
+      TRY(e->repack_table.alloc(entries.size() * sizeof(RepackEntry)));
+      CUDA_TRY(cudaMemcpyAsync(e->repack_table.p, entries.data(), entries.size() * sizeof(RepackEntry), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaStreamSynchronize(st));   // `entries` is a local
+      e->repack_key = key;
+      e->repack_entries = static_cast<int>(entries.size());
+      e->repack_tiles = total_tiles;
+    }
+    repack_weights_kernel<<<e->repack_tiles, 256, 0, st>>>(e->repack_table.as<RepackEntry>(), e->repack_entries);
+    LAUNCH_CHECK();
   }
   return 0;
 }
@@ -757,8 +785,22 @@ int vitocm_prepare_tokens(vitocm_engine* e, const float* x, int B, int H, int W,
   return run_patch_embed(e, x, B, H, W, pos, mask, X, static_cast<cudaStream_t>(stream));
 }
 
+static int forward_rows(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const int* queries, int nq,
+                        float* out_rows, float* k_out, void* ws, size_t ws_bytes, int chunk_tiles, void* stream);
+
 int vitocm_forward_cls_attn(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, float* out_rows,
                             void* ws, size_t ws_bytes, int chunk_tiles, void* stream) {
+  return forward_rows(e, x, B, H, W, pos, nullptr, 1, out_rows, nullptr, ws, ws_bytes, chunk_tiles, stream);
+}
+
+int vitocm_forward_query_attn(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const int* queries, int nq,
+                              float* out_rows, float* k_out, void* ws, size_t ws_bytes, int chunk_tiles, void* stream) {
+  if (queries == nullptr || nq < 1) return fail(VITOCM_ERR_INVALID, "forward_query_attn needs a device array of nq >= 1 token indices");
+  return forward_rows(e, x, B, H, W, pos, queries, nq, out_rows, k_out, ws, ws_bytes, chunk_tiles, stream);
+}
+
+static int forward_rows(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const int* queries, int nq,
+                        float* out_rows, float* k_out, void* ws, size_t ws_bytes, int chunk_tiles, void* stream) {
   TRY(check_engine(e));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int p = e->cfg.patch_size, D = e->cfg.embed_dim, heads = e->cfg.num_heads, C = e->cfg.in_chans;
@@ -825,10 +867,14 @@ int vitocm_forward_cls_attn(vitocm_engine* e, const float* x, int B, int H, int 
       TRY(run_layernorm(wsp.X, last.ln1w, last.ln1b, wsp.XN, 2LL * D, 1, D, nullptr, 0, M, D, e->cfg.ln_eps, lane_st[k]));
       TRY(run_gemm(e, wsp.XN, 2LL * D, last.wk_split.p, 2LL * D, M, D, D, 1, EPI_BIAS_F32, last.bqkv + D, KF, D, 0, 0, lane_st[k], PC_GEMM_KLAST));
       ProfScope prof(PC_CLSROW, lane_st[k]);
-      dim3 grid(heads, bcs[k]);
+      dim3 grid(heads, bcs[k], nq);
       cls_attn_row_kernel<<<grid, 256, cls_smem, lane_st[k]>>>(wsp.X, last.ln1w, last.ln1b, e->cfg.ln_eps, last.wqkv_f32, last.bqkv, KF,
-                                                               out_rows + static_cast<long long>(b0s[k]) * heads * N, N, D, heads, e->cfg.qk_scale);
+                                                               out_rows + static_cast<long long>(b0s[k]) * heads * nq * N, N, D, heads, e->cfg.qk_scale,
+                                                               queries, nq);
       LAUNCH_CHECK();
+      if (k_out != nullptr)   // last-block K features (SSS/analyse_attention.py:139-163, SSS/eval.py:186-202 cluster these)
+        CUDA_TRY(cudaMemcpyAsync(k_out + static_cast<long long>(b0s[k]) * N * D, KF, static_cast<size_t>(M) * D * sizeof(float), cudaMemcpyDeviceToDevice,
+                                 lane_st[k]));
     }
   }
   for (int k = 1; k < lanes; ++k) {   // join

@@ -117,15 +117,21 @@ class LazyAttention(LazyTensor):
     """``attn`` of a block, [B, heads, N, N].  ``attn[b, :, 0, c]`` (CLS query, any column index)
     is answered from the eagerly computed CLS rows; everything else materialises N x N."""
 
-    def __init__(self, shape, producer, cls_rows: torch.Tensor):
+    def __init__(self, shape, producer, cls_rows: torch.Tensor, row_fn=None):
         super().__init__(shape, producer)
         self.cls_rows = cls_rows                    # [B, heads, N] fp32, device
+        self._row_fn = row_fn                       # q -> [B, heads, N] rows of query token q (computed on demand)
+        self._rows = {0: cls_rows}
 
     def __getitem__(self, idx):
         if self._value is None and isinstance(idx, tuple) and len(idx) >= 3:
             q = idx[2]
-            if isinstance(q, int) and q == 0:
-                return self.cls_rows[(idx[0], idx[1]) + tuple(idx[3:])]
+            if isinstance(q, int):
+                q = q % self._shape[2]
+                if q not in self._rows and self._row_fn is not None:
+                    self._rows[q] = self._row_fn(q)      # region query (SSS/analyse_attention.py:183-247) without N x N
+                if q in self._rows:
+                    return self._rows[q][(idx[0], idx[1]) + tuple(idx[3:])]
         return self.materialize()[idx]
 
 
@@ -339,6 +345,30 @@ class VisionTransformer(nn.Module):
         return out
 
     @torch.no_grad()
+    def attention_rows(self, x: torch.Tensor, queries, return_keys: bool = False):
+        """get_last_selfattention(x)[:, :, queries, :] -> [B, heads, nq, N] fp32 for a list of query tokens (0 = CLS,
+        1 + i = patch i; SSS/analyse_attention.py:183-247 region queries), without forming N x N.  With ``return_keys``
+        also the last block's K features [B, heads, N, 64] (= qkv[1] of get_intermediate_feat; SSS/eval.py:186-202)."""
+        x = self._check_input(x)
+        eng = self._ensure_engine()
+        B, _, H, W = x.shape
+        N = self._tokens(x)
+        q = torch.as_tensor(queries, dtype=torch.int32).reshape(-1)
+        if q.numel() == 0 or int(q.min()) < -N or int(q.max()) >= N:
+            raise IndexError(f"query tokens must lie in [0, {N})")
+        q = (q % N).to(device=x.device).contiguous()
+        pos = self._pos_table(N - 1, H, W)
+        chunk = max(1, min(self.chunk_tiles, B))
+        ws = self._workspace(chunk, N, x.device)
+        out = torch.empty(B, self.num_heads, q.numel(), N, dtype=torch.float32, device=x.device)
+        keys = torch.empty(B, N, self.embed_dim, dtype=torch.float32, device=x.device) if return_keys else None
+        check(_lib.load_library().vitocm_forward_query_attn(eng, ptr(x), B, H, W, ptr(pos), ptr(q), q.numel(), ptr(out), ptr(keys), ptr(ws),
+                                                            ws.numel(), chunk, cur_stream()))
+        if return_keys:
+            return out, keys.reshape(B, N, self.num_heads, self.embed_dim // self.num_heads).permute(0, 2, 1, 3)
+        return out
+
+    @torch.no_grad()
     def prepare_tokens(self, x, mask=None):
         """vit.py:198-209 -> [B, N, D] fp32."""
         x = self._check_input(x)
@@ -447,7 +477,7 @@ class VisionTransformer(nn.Module):
             return cache["v"]
 
         feat = LazyTensor((B, N, D), lambda: full()[0][0])
-        attn = LazyAttention((B, H, N, N), lambda: full()[1][0], rows)
+        attn = LazyAttention((B, H, N, N), lambda: full()[1][0], rows, row_fn=lambda q: self.attention_rows(x, [q])[:, :, 0, :])
         qkv = LazyTensor((3, B, H, N, D // H), lambda: full()[2][0])
         return [feat], [attn], [qkv]
 
