@@ -242,10 +242,11 @@ int vitocm_adamw_step(float* p, float* g, float* m, float* v, const uint8_t* dec
 /* kernel-level: dW[R][C] (fp32) += G[M][R]^T . A[M][C], bf16 row-major activations (the weight gradient of nn.Linear) */
 int vitocm_wgrad(vitocm_engine* e, const void* G, int64_t ldg, const void* A, int64_t lda, int M, int R, int C, float* dW,
                  void* stream);
-/* vitocm_attention that also returns lse2 [B][heads][N] = log2 sum_k exp(scale q.k) */
+/* vitocm_attention that also returns lse2 [B][heads][Npad] = log2 sum_k exp(scale q.k); Npad = n_tokens rounded up to a
+ * multiple of 128, pad rows hold +inf */
 int vitocm_attention_fwd_lse(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo,
                              float* lse2, void* stream);
-/* backward of vitocm_attention: dqkv bf16 [B*N][ldq] (columns [3][H][64]) from dctx; scratch: delta [B][heads][N] fp32,
+/* backward of vitocm_attention: dqkv bf16 [B*N][ldq] (columns [3][H][64]) from dctx; scratch: delta [B][heads][Npad] fp32,
  * dqacc [B*N][D] fp32 (zero on entry, zero again on return) */
 int vitocm_attention_bwd(vitocm_engine* e, const void* qkv, int64_t ld, const void* ctx, const void* dctx, int64_t ldc,
                          const float* lse2, float* delta, float* dqacc, void* dqkv, int64_t ldq, int B, int n_tokens,

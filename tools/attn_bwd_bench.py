@@ -15,9 +15,9 @@ g = torch.Generator(device="cuda").manual_seed(0)
 qkv = torch.randn(B * N, 3 * D, generator=g, device="cuda").to(torch.bfloat16)
 dctx = (torch.randn(B * N, D, generator=g, device="cuda") * 0.5).to(torch.bfloat16)
 ctx = torch.empty(B * N, D, device="cuda", dtype=torch.bfloat16)
-lse = torch.empty(B, H, N, device="cuda")
+lse = torch.empty(B, H, (N + 127) // 128 * 128, device="cuda")
 dqkv = torch.empty(B * N, 3 * D, device="cuda", dtype=torch.bfloat16)
-delta = torch.empty(B, H, N, device="cuda")
+delta = torch.empty(B, H, (N + 127) // 128 * 128, device="cuda")
 dqacc = torch.zeros(B * N, D, device="cuda")
 def fwd():
     check(lib.vitocm_attention_fwd_lse(eng, ptr(qkv), qkv.stride(0), B, N, ptr(ctx), ctx.stride(0), ptr(lse), cur_stream()))
@@ -46,7 +46,7 @@ if os.environ.get("VITOCM_ABW_DEBUG") == "2":
     t0 = tl[0, 0, 0]
     print("softmax warp 0: per query tile [wait S/dP, S/dP ready, P/dS computed, dQ(i-1) drained, P/dS handed over | dq_full(i-1) seen]")
     for i in range(7):
-        print("  i=%d " % i, [int(v - t0) if v else None for v in tl[0, i, :6]])
+        print("  i=%d " % i, [int(v - t0) if v else None for v in tl[0, i, :7]])
     print("MMA thread: [waiting for P/dS, P/dS ready, all MMAs of tile issued]")
     for i in range(7):
         print("  i=%d " % i, [int(v - t0) if v else None for v in tl[1, i, :3]])

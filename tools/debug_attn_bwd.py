@@ -16,11 +16,11 @@ qkv = _rand((B * N, 3 * D), 30).to(torch.bfloat16)
 dctx = _rand((B * N, D), 31, 0.5).to(torch.bfloat16)
 ctx_ref, dqkv_ref, lse_ref = _attention_autograd(qkv, dctx, B, H, N, 0.125)
 ctx = torch.empty(B * N, D, device="cuda", dtype=torch.bfloat16)
-lse = torch.full((B, H, N), float("nan"), device="cuda")
+lse = torch.full((B, H, (N + 127) // 128 * 128), float("nan"), device="cuda")
 check(lib.vitocm_attention_fwd_lse(eng, ptr(qkv), qkv.stride(0), B, N, ptr(ctx), ctx.stride(0), ptr(lse), cur_stream()))
 torch.cuda.synchronize()
 dqkv = torch.full((B * N, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
-delta = torch.empty(B, H, N, device="cuda")
+delta = torch.empty(B, H, (N + 127) // 128 * 128, device="cuda")
 dqacc = torch.zeros(B * N, D, device="cuda")
 check(lib.vitocm_attention_bwd(eng, ptr(qkv), qkv.stride(0), ptr(ctx), ptr(dctx), dctx.stride(0), ptr(lse), ptr(delta), ptr(dqacc),
                                ptr(dqkv), dqkv.stride(0), B, N, cur_stream()))

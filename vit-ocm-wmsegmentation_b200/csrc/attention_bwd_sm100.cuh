@@ -33,8 +33,8 @@ struct AttnBwdArgs {
   int heads;
   float scale;        // qk scale
   float scale_log2;   // scale * log2(e)
-  const float* lse2;  // [B][H][N]
-  const float* delta; // [B][H][N]
+  const float* lse2;  // [B][H][Npad], Npad = N rounded up to 128; +inf in the pad rows
+  const float* delta; // [B][H][Npad]; 0 in the pad rows
   __nv_bfloat16* dqkv;  // [B*N][ld]: dK at column D + h*64, dV at 2D + h*64 (dQ comes from dq_convert_kernel)
   long long ld;
   int debug;          // diagnostics (VITOCM_ABW_DEBUG): 1 = skip the dQ reduce-add
@@ -44,12 +44,13 @@ constexpr int ABW_SM_WARPS = 8;    // softmax / drain warps: two per TMEM lane q
 constexpr int ABW_DRAIN_WARP0 = 8;   // warps 8..11: dQ drain (one per TMEM lane quadrant)
 constexpr int ABW_TMA_WARP = 12, ABW_MMA_WARP = 13;   // warps 14, 15 idle (setmaxnreg works on whole warpgroups)
 constexpr int ABW_THREADS = 512;
-constexpr int ABW_REGS_SOFTMAX = 184, ABW_REGS_OTHER = 72;   // 8 x 32 x 184 + 8 x 32 x 72 = 64 K registers
+constexpr int ABW_REGS_SOFTMAX = 192, ABW_REGS_OTHER = 64;   // 8 x 32 x 192 + 8 x 32 x 64 = 64 K registers
 constexpr int ABW_TILE = 128 * 64 * 2;          // 16 KB: [128 rows][64 bf16]
 constexpr int ABW_S_COL = 0, ABW_DP_COL = 128, ABW_DV_COL = 256, ABW_DK_COL = 320, ABW_DQ_COL = 384;
 constexpr int ABW_TMEM_COLS = 512;
 // shared memory: K | V | (Q, dO) x 2 | P (2 atoms) | dS (2 atoms) | dQ staging (4 warps x 2 boxes x 4 KB) | barriers
-constexpr int ABW_SMEM_BYTES = 2 * ABW_TILE + 4 * ABW_TILE + 2 * ABW_TILE + 2 * ABW_TILE + 32768 + 1024 + 256;
+constexpr int ABW_STAT_BYTES = 2 * 1024;   // [2 slots][LSE2 | Delta][128 rows] fp32
+constexpr int ABW_SMEM_BYTES = 2 * ABW_TILE + 4 * ABW_TILE + 2 * ABW_TILE + 2 * ABW_TILE + 32768 + ABW_STAT_BYTES + 1024 + 256;
 
 // diagnostics (VITOCM_ABW_DEBUG=2): SM-clock stamps of CTA (1,0,0) -- [role 0 = softmax warp 0, 1 = MMA thread][query tile < 8][event < 8]
 __device__ long long g_abw_timeline[2 * 8 * 8];
@@ -74,7 +75,8 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   const uint32_t smem_p = smem_qdo + 4 * ABW_TILE;        // [2 atoms of 64 keys][128 q][128 B]
   const uint32_t smem_ds = smem_p + 2 * ABW_TILE;
   const uint32_t smem_dq = smem_ds + 2 * ABW_TILE;        // fp32 staging
-  const uint32_t bars = smem_dq + 32768;
+  const uint32_t smem_stat = smem_dq + 32768;             // per query tile: LSE2 and Delta rows (bulk-copied by the producer)
+  const uint32_t bars = smem_stat + ABW_STAT_BYTES;
   const uint32_t kv_full = bars;            // K_j, V_j landed
   const uint32_t qdo_full = bars + 8;       // [2]
   const uint32_t qdo_empty = bars + 24;     // [2]
@@ -82,7 +84,8 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   const uint32_t pds_full = bars + 48;      // softmax -> MMA: P, dS in shared memory (4 warps)
   const uint32_t dq_full = bars + 56;       // MMA -> softmax: dQ_i complete (also: P / dS / dV / dK MMAs retired)
   const uint32_t dq_empty = bars + 64;      // softmax -> MMA: dQ columns drained (4 warps)
-  const uint32_t tmem_ptr_smem = bars + 72;
+  const uint32_t sdp_free = bars + 72;      // softmax -> MMA: S, dP columns are in registers (ABW_SM_WARPS arrivals)
+  const uint32_t tmem_ptr_smem = bars + 80;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -103,6 +106,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       ptx::mbar_init(qdo_empty + 8 * s, 1);
     }
     ptx::mbar_init(sdp_full, 1);
+    ptx::mbar_init(sdp_free, ABW_SM_WARPS);
     ptx::mbar_init(pds_full, ABW_SM_WARPS);
     ptx::mbar_init(dq_full, 1);
     ptx::mbar_init(dq_empty, 4);
@@ -129,7 +133,10 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       for (int i = 0; i < n_q; ++i) {
         const int slot = i & 1;
         ptx::mbar_wait(qdo_empty + 8 * slot, ((i >> 1) & 1) ^ 1, 40);
-        ptx::mbar_arrive_expect_tx(qdo_full + 8 * slot, 2 * ABW_TILE);
+        ptx::mbar_arrive_expect_tx(qdo_full + 8 * slot, 2 * ABW_TILE + 1024);
+        const long long stat_off = (static_cast<long long>(b) * args.heads + h) * (n_q * 128) + i * 128;
+        ptx::bulk_load_1d(smem_stat + slot * 1024, args.lse2 + stat_off, 512, qdo_full + 8 * slot);
+        ptx::bulk_load_1d(smem_stat + slot * 1024 + 512, args.delta + stat_off, 512, qdo_full + 8 * slot);
         ptx::tma_load_2d(smem_qdo + slot * 2 * ABW_TILE, &tmap_qkv, qdo_full + 8 * slot, h * 64, row_base + i * 128);
         ptx::tma_load_2d(smem_qdo + slot * 2 * ABW_TILE + ABW_TILE, &tmap_do, qdo_full + 8 * slot, h * 64, row_base + i * 128);
       }
@@ -165,11 +172,16 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       for (int i = 0; i < n_q; ++i) {
         const int slot = i & 1;
         abw_stamp(tl, 1, i, 0);
-        ptx::mbar_wait(pds_full, i & 1, 43);     // P_i, dS_i in shared memory; S / dP columns read
+        // the next tile's logits go first, as soon as the softmax warps hold S_i / dP_i in registers: they are ready long
+        // before those warps finish tile i, and the tensor core runs dV / dK / dQ of tile i under the exponentials of i + 1
+        if (i + 1 < n_q) {
+          ptx::mbar_wait(sdp_free, i & 1, 49);
+          ptx::tc_fence_after();
+          issue_sdp(i + 1);
+        }
+        ptx::mbar_wait(pds_full, i & 1, 43);     // P_i, dS_i in shared memory
         ptx::tc_fence_after();
         abw_stamp(tl, 1, i, 1);
-        // the next tile's logits go first: the softmax warps work on them while the tensor core runs dV / dK / dQ of tile i
-        if (i + 1 < n_q) issue_sdp(i + 1);
         const uint64_t q_desc_mn = ptx::make_smem_desc_sw128(smem_qdo + slot * 2 * ABW_TILE, 1024, 1024);
         const uint64_t do_desc_mn = ptx::desc_advance(q_desc_mn, ABW_TILE);
         const uint32_t acc0 = i > 0 ? 1u : 0u;
@@ -257,20 +269,15 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     const int r = q * 32 + lane;   // query row inside the tile (S, dP phases) or key row (final dK / dV drain)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float sl2 = args.scale_log2;
-    const float* lse_bh = args.lse2 + (static_cast<long long>(b) * args.heads + h) * N;
-    const float* delta_bh = args.delta + (static_cast<long long>(b) * args.heads + h) * N;
     const uint64_t sl2_2 = ptx::dup_f32x2(sl2);
     const uint64_t sc_2 = ptx::dup_f32x2(args.scale);
-    // rows beyond the image: LSE = +inf makes P = 0 and with it dS = 0 (dP is finite: the rows hold other tokens or zeros)
-    float lse_next = r < N ? __ldg(lse_bh + r) : INFINITY;
-    float dlt_next = r < N ? __ldg(delta_bh + r) : 0.f;
     for (int i = 0; i < n_q; ++i) {
-      const float lse = lse_next, dlt = dlt_next;
-      {   // next tile's row statistics: issued now, consumed one tile later (global-load latency off the critical path)
-        const int qn = (i + 1) * 128 + r;
-        lse_next = qn < N ? __ldg(lse_bh + qn) : INFINITY;
-        dlt_next = qn < N ? __ldg(delta_bh + qn) : 0.f;
-      }
+      abw_stamp(tl && warp == 0, 0, i, 6);
+      // row statistics of this query tile from shared memory (rows beyond the image: LSE2 = +inf -> P = 0 -> dS = 0; dP is
+      // finite there: the rows hold other tokens or zeros)
+      ptx::mbar_wait(qdo_full + 8 * (i & 1), (i >> 1) & 1, 50);
+      const float lse = ptx::lds_f32(smem_stat + (i & 1) * 1024 + r * 4);
+      const float dlt = ptx::lds_f32(smem_stat + (i & 1) * 1024 + 512 + r * 4);
       const uint64_t nlse_2 = ptx::dup_f32x2(-lse);
       const uint64_t ndl_2 = ptx::dup_f32x2(-dlt * args.scale);
       abw_stamp(tl && warp == 0, 0, i, 0);
@@ -279,41 +286,53 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       abw_stamp(tl && warp == 0, 0, i, 1);
       // ---- P = exp2(S * sl2 - LSE2), dS = P * (dP * scale - Delta * scale) for this warp's (up to) two 32-key chunks, on the
       //      packed f32x2 pipe; results wait in registers until the previous tile's MMAs have released the P / dS buffers
-      uint32_t pp[2][16], dd[2][16];
+      uint32_t sv[2][32], dp[2][32];   // S / dP, then (in place, first 16 words of each) the packed bf16 P / dS
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c = 2 * half + cc;
         if (c < nch) {
-          uint32_t sv[32], dp[32];
-          ptx::tmem_ld_32x32b_x32(lane_addr + ABW_S_COL + c * 32, sv);
-          ptx::tmem_ld_32x32b_x32(lane_addr + ABW_DP_COL + c * 32, dp);
-          ptx::tmem_ld_wait(sv);
-          ptx::tmem_ld_wait(dp);
+          ptx::tmem_ld_32x32b_x32(lane_addr + ABW_S_COL + c * 32, sv[cc]);
+          ptx::tmem_ld_32x32b_x32(lane_addr + ABW_DP_COL + c * 32, dp[cc]);
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        if (2 * half + cc < nch) {
+          ptx::tmem_ld_wait(sv[cc]);
+          ptx::tmem_ld_wait(dp[cc]);
+        }
+      }
+      ptx::tc_fence_before();     // S / dP are in registers: the MMA warp may overwrite the columns with the next tile's
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(sdp_free);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * half + cc;
+        if (c < nch) {
 #pragma unroll
           for (int t = 0; t < 16; ++t) {
-            const uint64_t a2 = ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sv[2 * t]), __uint_as_float(sv[2 * t + 1])), sl2_2, nlse_2);
+            const uint64_t a2 = ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sv[cc][2 * t]), __uint_as_float(sv[cc][2 * t + 1])), sl2_2, nlse_2);
             float a0, a1;
             ptx::unpack_f32x2(a2, a0, a1);
             const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);
-            const uint64_t g2 = ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(dp[2 * t]), __uint_as_float(dp[2 * t + 1])), sc_2, ndl_2);
+            const uint64_t g2 = ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(dp[cc][2 * t]), __uint_as_float(dp[cc][2 * t + 1])), sc_2, ndl_2);
             const uint64_t d2 = ptx::mul_f32x2(ptx::pack_f32x2(p0, p1), g2);
             float d0, d1;
             ptx::unpack_f32x2(d2, d0, d1);
-            pp[cc][t] = ptx::pack_bf16x2(p0, p1);
-            dd[cc][t] = ptx::pack_bf16x2(d0, d1);
+            sv[cc][t] = ptx::pack_bf16x2(p0, p1);     // words t <= 2t have been consumed
+            dp[cc][t] = ptx::pack_bf16x2(d0, d1);
           }
           if (c * 32 + 32 > kv_len) {   // ragged key block: keys beyond the image contribute nothing
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
               const int k0 = c * 32 + 2 * t;
               const uint32_t keep = (k0 < kv_len ? 0x0000ffffu : 0u) | (k0 + 1 < kv_len ? 0xffff0000u : 0u);
-              pp[cc][t] &= keep;
-              dd[cc][t] &= keep;
+              sv[cc][t] &= keep;
+              dp[cc][t] &= keep;
             }
           }
         }
       }
-      ptx::tc_fence_before();     // S / dP reads are done (ordered before the pds_full arrive below)
       abw_stamp(tl && warp == 0, 0, i, 2);
       if (i > 0) ptx::mbar_wait(dq_full, (i - 1) & 1, 47);   // previous tile's dV / dK / dQ MMAs retired: P / dS may be overwritten
       abw_stamp(tl && warp == 0, 0, i, 3);
@@ -326,8 +345,8 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const uint32_t ch = static_cast<uint32_t>((((c & 1) * 4 + g) ^ (r & 7)) << 4);
-            ptx::sts_v4(smem_p + off + ch, pp[cc][4 * g], pp[cc][4 * g + 1], pp[cc][4 * g + 2], pp[cc][4 * g + 3]);
-            ptx::sts_v4(smem_ds + off + ch, dd[cc][4 * g], dd[cc][4 * g + 1], dd[cc][4 * g + 2], dd[cc][4 * g + 3]);
+            ptx::sts_v4(smem_p + off + ch, sv[cc][4 * g], sv[cc][4 * g + 1], sv[cc][4 * g + 2], sv[cc][4 * g + 3]);
+            ptx::sts_v4(smem_ds + off + ch, dp[cc][4 * g], dp[cc][4 * g + 1], dp[cc][4 * g + 2], dp[cc][4 * g + 3]);
           }
         }
       }

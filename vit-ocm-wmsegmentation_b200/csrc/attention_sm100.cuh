@@ -35,7 +35,8 @@ struct AttnArgs {
   __nv_bfloat16* out;  // ctx [B*N, ldo]
   long long ldo;
   int out_lo_off;    // SPLIT: column offset of the lo half of ctx
-  float* lse2;       // training: [B][H][N] log2-sum-exp of the scaled logits (max * scale_log2 + log2 l), or nullptr
+  float* lse2;       // training: [B][H][Npad] (Npad = N rounded up to 128) log2-sum-exp of the scaled logits
+                     // (max * scale_log2 + log2 l); +inf in the pad rows; or nullptr
   long long* timeline;  // diagnostics (vitocm_attention_timeline) or nullptr: clock64 stamps of CTAs (0,0,0) and (1,0,0)
 };
 
@@ -383,8 +384,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     ptx::tc_fence_after();
     const float inv = 1.0f / l_run;
     const int qrow = qt * ATT_BQ + r;
-    if (args.lse2 != nullptr && qrow < N)
-      args.lse2[(static_cast<long long>(b) * gridDim.y + h) * N + qrow] = m_used * sl2 + log2f(l_run);
+    if (args.lse2 != nullptr)   // pad rows get +inf: the backward turns that into P = 0 without a bounds test
+      args.lse2[(static_cast<long long>(b) * gridDim.y + h) * (gridDim.x * ATT_BQ) + qrow] = qrow < N ? m_used * sl2 + log2f(l_run) : INFINITY;
     __nv_bfloat16* o = args.out + static_cast<long long>(row_base + qrow) * args.ldo + h * ATT_DH;
 #pragma unroll
     for (int c = 0; c < ATT_DH; c += 32) {

@@ -232,10 +232,10 @@ ln_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
 }
 
 // ------------------------------------------------------------------------------------------------ attention backward helpers
-// delta[b][h][q] = sum_d dO[row][h*64 + d] * O[row][h*64 + d]; one warp per token row, two bf16 per lane per head
+// delta[b][h][q] (row pitch npad) = sum_d dO[row][h*64 + d] * O[row][h*64 + d]; one warp per token row, two bf16 per lane per head
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO, long long ld, float* __restrict__ delta,
-                  int B, int N, int heads) {
+                  int B, int N, int heads, int npad) {
   const int lane = threadIdx.x & 31;
   const long long M = static_cast<long long>(B) * N;
   for (long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5); row < M;
@@ -245,7 +245,7 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __re
       const uint32_t o = *reinterpret_cast<const uint32_t*>(O + row * ld + h * 64 + 2 * lane);
       const uint32_t d = *reinterpret_cast<const uint32_t*>(dO + row * ld + h * 64 + 2 * lane);
       const float s = warp_sum(bf16lo(o) * bf16lo(d) + bf16hi(o) * bf16hi(d));
-      if (lane == 0) delta[(static_cast<long long>(b) * heads + h) * N + q] = s;
+      if (lane == 0) delta[(static_cast<long long>(b) * heads + h) * npad + q] = s;
     }
   }
 }
