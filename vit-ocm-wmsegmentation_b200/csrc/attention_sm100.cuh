@@ -3,7 +3,7 @@
 // Replaces SSS/dino/vision_transformer.py:83-87 (q@k^T*scale, softmax, attn@v, transpose/reshape)
 // for the blocks whose attention matrix is not returned.
 //
-// One CTA = one (image b, head h, 128-query tile).  q/k/v are read straight out of the fused
+// One work item = one (image b, head h, 128-query tile); CTAs are persistent and walk the items.  q/k/v are read straight out of the fused
 // QKV activation [B*N, ld] (bf16, columns [3][H][64]) by one 2-D TMA tensor map (box 64 x 128,
 // SWIZZLE_128B).  Warp roles (256 threads): warps 0..3 = softmax (one thread per query row; TMEM lane
 // quadrant = warp % 4), warp 4 = TMA producer, warp 5 = MMA issuer + TMEM allocator, warps 6..7 idle.
@@ -28,6 +28,8 @@
 namespace vitocm {
 
 struct AttnArgs {
+  int n_items;       // work items = query tiles x heads x images (persistent CTAs walk them with stride gridDim.x)
+  int n_qtiles, heads;
   int n_tokens;      // N per image (785 for 224^2 / patch 8)
   int embed_dim;     // D = H * 64
   int lo_col_off;    // SPLIT: column offset of the lo halves inside the qkv activation (= 3D)
@@ -90,16 +92,19 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
   const uint32_t s_empty = bars + 64;       // softmax -> MMA   (4 warps)
   const uint32_t p_full = bars + 72;        // softmax -> MMA   (4 warps)
   const uint32_t o_full = bars + 80;        // MMA -> softmax
-  const uint32_t tmem_ptr_smem = bars + 88;
+  const uint32_t q_empty = bars + 88;       // MMA -> producer: all S MMAs of the work item retired (Q tile reusable)
+  const uint32_t o_empty = bars + 96;       // softmax -> MMA: O of the finished work item has been read (4 warps)
+  const uint32_t tmem_ptr_smem = bars + 104;
 
+  // Persistent CTA: work items (query tile, head, image), query tile fastest so that the CTAs running side by side share
+  // one image-head's K / V through L2.  Barriers, the K/V ring and TMEM live across items (all phase counters run on), so
+  // the next item's Q / K loads and its first S MMA overlap the current item's last exponentials and its epilogue.
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int N = args.n_tokens;
   const int D = args.embed_dim;
   const int n_kv = (N + ATT_BKV - 1) / ATT_BKV;
-  const int row_base = b * N;  // first row of this image in the [B*N, ld] activation
-  const bool tl = args.timeline != nullptr && blockIdx.x < 2 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0;
+  const bool tl0 = args.timeline != nullptr && blockIdx.x < 2 && (threadIdx.x & 31) == 0;
 
   if (warp == 4 && lane == 0) {
     ptx::prefetch_tmap(&tmap_qkv);
@@ -112,6 +117,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     ptx::mbar_init(s_empty, 4);
     ptx::mbar_init(p_full, 4);
     ptx::mbar_init(o_full, 1);
+    ptx::mbar_init(q_empty, 1);
+    ptx::mbar_init(o_empty, 4);
     ptx::fence_barrier_init();
   }
   if (warp == 5) {
@@ -128,12 +135,17 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
    if (warp == 4) {
     // ===================== TMA producer =====================
     if (ptx::elect_one()) {
+      int item = 0;   // K/V ring position, running across work items
+      int w = 0;
+      for (int it = blockIdx.x; it < args.n_items; it += gridDim.x, ++w) {
+      const int qt = it % args.n_qtiles, h = (it / args.n_qtiles) % args.heads, b = it / (args.n_qtiles * args.heads);
+      const int row_base = b * N;  // first row of this image in the [B*N, ld] activation
+      ptx::mbar_wait(q_empty, (w & 1) ^ 1, 16);   // the previous item's S MMAs have retired
       ptx::mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
       for (int part = 0; part < NPART; ++part)
         ptx::tma_load_2d(smem_q + part * ATT_TILE_BYTES, &tmap_qkv, q_full, part * args.lo_col_off + h * ATT_DH,
                          row_base + qt * ATT_BQ);
       // ring order = consumption order of the MMA warp: K0, K1, V0, K2, V1, ..., V_{n-1}
-      int item = 0;
       auto load = [&](int which /*1 = K, 2 = V*/, int j) {
         const int slot = item % ATT_RING;
         const uint32_t parity = ((item / ATT_RING) & 1) ^ 1;
@@ -149,6 +161,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
         if (j + 1 < n_kv) load(1, j + 1);
         load(2, j);
       }
+      }
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
@@ -158,7 +171,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
       const uint32_t s_tmem = tmem_base + ATT_S_COL;
       const uint32_t o_tmem = tmem_base + ATT_O_COL;
       const uint64_t q_desc = ptx::make_smem_desc_sw128(smem_q, 1024, 0);
-      int item = 0;
+      int item = 0;   // K/V ring position, running across work items
+      int g = 0;      // KV blocks processed so far (all work items): phase counter of s_full / s_empty / p_full / o_full
+      int w = 0;
+      for (int it = blockIdx.x; it < args.n_items; it += gridDim.x, ++w) {
+      const bool tl = tl0 && w == 0;
       auto kv_len_mma = [&](int j) {  // keys of block j rounded up to the MMA granularity (16)
         int len = N - j * ATT_BKV;
         len = len > ATT_BKV ? ATT_BKV : len;
@@ -195,6 +212,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
         constexpr uint32_t idesc = ptx::make_idesc(ATT_BQ, ATT_DH, false, /*B = V is MN-major*/ true);
         const int ksteps = kv_len_mma(j) / 16;
         const uint32_t acc0 = j > 0 ? 1u : 0u;
+        if (j == 0 && w > 0) {   // O still holds the previous work item until the softmax warps have read it out
+          ptx::mbar_wait(o_empty, (w - 1) & 1, 17);
+          ptx::tc_fence_after();
+        }
         // terms: (Phi,Vhi) [, (Phi,Vlo), (Plo,Vhi)]
 #pragma unroll
         for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
@@ -215,18 +236,22 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
         att_stamp(args, tl, 1, j, 1);   // PV_j issued
         ++item;
       };
-      ptx::mbar_wait(q_full, 0, 13);
+      ptx::mbar_wait(q_full, w & 1, 13);
+      if (g > 0) ptx::mbar_wait(s_empty, (g - 1) & 1, 14);   // the previous item's last S has been read out of TMEM
       ptx::tc_fence_after();
       issue_s(0);
-      for (int j = 0; j < n_kv; ++j) {
+      if (n_kv == 1) ptx::umma_commit(q_empty);
+      for (int j = 0; j < n_kv; ++j, ++g) {
         if (j + 1 < n_kv) {
-          ptx::mbar_wait(s_empty, j & 1, 14);  // softmax has read S_j out of TMEM
+          ptx::mbar_wait(s_empty, g & 1, 14);  // softmax has read S_j out of TMEM
           ptx::tc_fence_after();
           issue_s(j + 1);
+          if (j + 2 == n_kv) ptx::umma_commit(q_empty);   // last S MMA of the item: Q tile reusable once it retires
         }
-        ptx::mbar_wait(p_full, j & 1, 15);     // P_j in TMEM, O rescaled if needed
+        ptx::mbar_wait(p_full, g & 1, 15);     // P_j in TMEM, O rescaled if needed
         ptx::tc_fence_after();
         issue_pv(j);
+      }
       }
     }
    }
@@ -238,16 +263,22 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float sl2 = args.scale_log2;
     const uint64_t sl2_2 = ptx::dup_f32x2(sl2);
+    int g = 0;                    // KV blocks processed so far (all work items): barrier phase counter
+    int w = 0;
+    for (int it = blockIdx.x; it < args.n_items; it += gridDim.x, ++w) {
+    const int qt = it % args.n_qtiles, h = (it / args.n_qtiles) % args.heads, b = it / (args.n_qtiles * args.heads);
+    const int row_base = b * N;
+    const bool tl = tl0 && w == 0;
     float m_used = -INFINITY;     // the row maximum the exponentials are taken against
     float m_next = -INFINITY;     // a larger maximum seen in the previous block (lazy rescale pending)
     float l_run = 0.f;            // running row sum (same units as O in TMEM)
 
-    for (int j = 0; j < n_kv; ++j) {
+    for (int j = 0; j < n_kv; ++j, ++g) {
       int kv_len = N - j * ATT_BKV;
       kv_len = kv_len > ATT_BKV ? ATT_BKV : kv_len;
       const int nchunks = (((kv_len + 15) & ~15) + 31) >> 5;   // 32-column chunks the MMA produced
       att_stamp(args, tl && warp == 0, 0, j, 0);   // waiting for S_j
-      ptx::mbar_wait(s_full, j & 1, 21);
+      ptx::mbar_wait(s_full, g & 1, 21);
       ptx::tc_fence_after();
       att_stamp(args, tl && warp == 0, 0, j, 1);   // S_j complete
       // ---- S_j -> registers (one pass), then hand the TMEM columns back to the MMA warp
@@ -308,7 +339,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
         }
       };
       if (j > 0) {
-        ptx::mbar_wait(o_full, (j - 1) & 1, 20);   // PV_{j-1} done: the P columns are free, O is complete up to j-1
+        ptx::mbar_wait(o_full, (g - 1) & 1, 20);   // PV_{j-1} done: the P columns are free, O is complete up to j-1
         ptx::tc_fence_after();
         att_stamp(args, tl && warp == 0, 0, j, 4); // PV_{j-1} complete
         if (__any_sync(0xffffffffu, alpha != 1.0f)) rescale_o(alpha);
@@ -380,37 +411,44 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
       att_stamp(args, tl && warp == 0, 0, j, 6);   // P_j handed to the MMA warp
     }
     // ---- epilogue: ctx = O / l
-    ptx::mbar_wait(o_full, (n_kv - 1) & 1, 22);
+    ptx::mbar_wait(o_full, (g - 1) & 1, 22);
     ptx::tc_fence_after();
     const float inv = 1.0f / l_run;
     const int qrow = qt * ATT_BQ + r;
     if (args.lse2 != nullptr)   // pad rows get +inf: the backward turns that into P = 0 without a bounds test
-      args.lse2[(static_cast<long long>(b) * gridDim.y + h) * (gridDim.x * ATT_BQ) + qrow] = qrow < N ? m_used * sl2 + log2f(l_run) : INFINITY;
+      args.lse2[(static_cast<long long>(b) * args.heads + h) * (args.n_qtiles * ATT_BQ) + qrow] = qrow < N ? m_used * sl2 + log2f(l_run) : INFINITY;
     __nv_bfloat16* o = args.out + static_cast<long long>(row_base + qrow) * args.ldo + h * ATT_DH;
+    uint32_t t[ATT_DH / 32][32];
 #pragma unroll
-    for (int c = 0; c < ATT_DH; c += 32) {
-      uint32_t t[32];
-      ptx::tmem_ld_32x32b_x32(lane_addr + ATT_O_COL + c, t);
-      ptx::tmem_ld_wait(t);
-      if (qrow < N) {
+    for (int c = 0; c < ATT_DH / 32; ++c) ptx::tmem_ld_32x32b_x32(lane_addr + ATT_O_COL + c * 32, t[c]);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+    for (int c = 0; c < ATT_DH / 32; ++c) ptx::tmem_ld_wait(t[c]);
+    // O is in registers: the MMA warp may start accumulating the next work item into the same columns
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(o_empty);
+    if (qrow < N) {
+#pragma unroll
+      for (int c = 0; c < ATT_DH / 32; ++c) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
           float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(t[8 * g + i]) * inv;
-          reinterpret_cast<uint4*>(o + c)[g] = make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]),
-                                                          ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(t[c][8 * q4 + i]) * inv;
+          reinterpret_cast<uint4*>(o + c * 32)[q4] = make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]),
+                                                               ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
           if (SPLIT) {
-            float w[8];
+            float lo[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = v[i] - ptx::bf16_round(v[i]);
-            reinterpret_cast<uint4*>(o + args.out_lo_off + c)[g] =
-                make_uint4(ptx::pack_bf16x2(w[0], w[1]), ptx::pack_bf16x2(w[2], w[3]), ptx::pack_bf16x2(w[4], w[5]),
-                           ptx::pack_bf16x2(w[6], w[7]));
+            for (int i = 0; i < 8; ++i) lo[i] = v[i] - ptx::bf16_round(v[i]);
+            reinterpret_cast<uint4*>(o + args.out_lo_off + c * 32)[q4] =
+                make_uint4(ptx::pack_bf16x2(lo[0], lo[1]), ptx::pack_bf16x2(lo[2], lo[3]), ptx::pack_bf16x2(lo[4], lo[5]),
+                           ptx::pack_bf16x2(lo[6], lo[7]));
           }
         }
       }
     }
+    }   // work items
   }
 
   ptx::tc_fence_before();

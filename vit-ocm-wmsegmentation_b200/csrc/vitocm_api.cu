@@ -437,7 +437,14 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
   a.n_tokens = N; a.embed_dim = D; a.lo_col_off = 3 * D;
   a.scale_log2 = e->cfg.qk_scale * 1.44269504088896340736f;
   a.out = reinterpret_cast<__nv_bfloat16*>(ctx); a.ldo = ldo; a.out_lo_off = D; a.timeline = timeline; a.lse2 = lse2;
-  dim3 grid((N + ATT_BQ - 1) / ATT_BQ, H, B);
+  a.n_qtiles = (N + ATT_BQ - 1) / ATT_BQ; a.heads = H;
+  const long long items = static_cast<long long>(a.n_qtiles) * H * B;
+  if (items > 0x7fffffffLL) return fail(VITOCM_ERR_INVALID, "attention: too many work items");
+  a.n_items = static_cast<int>(items);
+  // persistent CTAs: as many as are co-resident (2 per SM in bf16 mode, 1 in split mode)
+  const int resident = e->num_sms * (e->split ? 1 : 2);
+  static const int persist = [] { const char* v = getenv("VITOCM_ATTN_PERSISTENT"); return v ? atoi(v) : 1; }();
+  const dim3 grid(persist && a.n_items > resident ? resident : a.n_items);
   auto launch = [&](auto kern, int smem_bytes, bool& attr) -> int {
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); attr = true; }
     kern<<<grid, ATT_THREADS, smem_bytes, st>>>(tq, a);
