@@ -7,8 +7,10 @@
 //     dP  = dO V^T                                           dK = dS^T Q
 //     dS  = scale * P o (dP - Delta)                         dQ = dS K
 //
-// One CTA = one (image b, head h, 128-key block j); it keeps K_j, V_j in shared memory, accumulates dK_j, dV_j in
-// TMEM and walks over the 128-query tiles i.  Per (i, j):
+// One work item = one (image b, head h, 128-key block j): K_j, V_j stay in shared memory, dK_j, dV_j accumulate in TMEM
+// over the 128-query tiles i.  CTAs are persistent (one per SM) and walk the items: barrier phases, the Q/dO ring, the
+// double-buffered K/V slot and TMEM live across items, so the next item's K/V arrive under the current item's last tiles
+// and its first S / dP MMAs run while dK_j / dV_j are drained.  Per (i, j):
 //   MMA   S  = Q_i K_j^T, dP = dO_i V_j^T                    (K-major operands)            -> TMEM S | dP
 //   warps 0..3 (thread = query row): tcgen05.ld S, dP -> P, dS (bf16) -> shared memory, row-major [q][k]
 //   MMA   dV += P^T dO_i, dK += dS^T Q_i                     (A = P / dS read MN-major: the contraction runs over the
@@ -37,20 +39,22 @@ struct AttnBwdArgs {
   const float* delta; // [B][H][Npad]; 0 in the pad rows
   __nv_bfloat16* dqkv;  // [B*N][ld]: dK at column D + h*64, dV at 2D + h*64 (dQ comes from dq_convert_kernel)
   long long ld;
-  int debug;          // diagnostics (VITOCM_ABW_DEBUG): 1 = skip the dQ reduce-add
+  int n_items;        // work items = key blocks x heads x images; persistent CTAs walk them with stride gridDim.x
+  int debug;          // diagnostics (VITOCM_ABW_DEBUG): 1 = skip the dQ reduce-add, 2 = timeline stamps
 };
 
 constexpr int ABW_SM_WARPS = 8;    // softmax / drain warps: two per TMEM lane quadrant, each takes half of the key columns
 constexpr int ABW_DRAIN_WARP0 = 8;   // warps 8..11: dQ drain (one per TMEM lane quadrant)
 constexpr int ABW_TMA_WARP = 12, ABW_MMA_WARP = 13;   // warps 14, 15 idle (setmaxnreg works on whole warpgroups)
 constexpr int ABW_THREADS = 512;
-constexpr int ABW_REGS_SOFTMAX = 192, ABW_REGS_OTHER = 64;   // 8 x 32 x 192 + 8 x 32 x 64 = 64 K registers
+constexpr int ABW_REGS_SOFTMAX = 200, ABW_REGS_OTHER = 56;   // 8 x 32 x 200 + 8 x 32 x 56 = 64 K registers
 constexpr int ABW_TILE = 128 * 64 * 2;          // 16 KB: [128 rows][64 bf16]
 constexpr int ABW_S_COL = 0, ABW_DP_COL = 128, ABW_DV_COL = 256, ABW_DK_COL = 320, ABW_DQ_COL = 384;
 constexpr int ABW_TMEM_COLS = 512;
-// shared memory: K | V | (Q, dO) x 2 | P (2 atoms) | dS (2 atoms) | dQ staging (4 warps x 2 boxes x 4 KB) | barriers
+// shared memory: (K, V) x 2 | (Q, dO) x 2 | P (2 atoms) | dS (2 atoms) | dQ staging (4 warps x 4 KB) | row statistics | barriers
 constexpr int ABW_STAT_BYTES = 2 * 1024;   // [2 slots][LSE2 | Delta][128 rows] fp32
-constexpr int ABW_SMEM_BYTES = 2 * ABW_TILE + 4 * ABW_TILE + 2 * ABW_TILE + 2 * ABW_TILE + 32768 + ABW_STAT_BYTES + 1024 + 256;
+constexpr int ABW_DQ_STG_BYTES = 4 * 4096;
+constexpr int ABW_SMEM_BYTES = 4 * ABW_TILE + 4 * ABW_TILE + 2 * ABW_TILE + 2 * ABW_TILE + ABW_DQ_STG_BYTES + ABW_STAT_BYTES + 1024 + 256;
 
 // diagnostics (VITOCM_ABW_DEBUG=2): SM-clock stamps of CTA (1,0,0) -- [role 0 = softmax warp 0, 1 = MMA thread][query tile < 8][event < 8]
 __device__ long long g_abw_timeline[2 * 8 * 8];
@@ -69,39 +73,50 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                         const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_k = smem;
-  const uint32_t smem_v = smem_k + ABW_TILE;
-  const uint32_t smem_qdo = smem_v + ABW_TILE;            // [2 slots][Q | dO]
+  const uint32_t smem_kv = smem;                          // [2 slots][K | V]
+  const uint32_t smem_qdo = smem_kv + 4 * ABW_TILE;       // [2 slots][Q | dO]
   const uint32_t smem_p = smem_qdo + 4 * ABW_TILE;        // [2 atoms of 64 keys][128 q][128 B]
   const uint32_t smem_ds = smem_p + 2 * ABW_TILE;
-  const uint32_t smem_dq = smem_ds + 2 * ABW_TILE;        // fp32 staging
-  const uint32_t smem_stat = smem_dq + 32768;             // per query tile: LSE2 and Delta rows (bulk-copied by the producer)
+  const uint32_t smem_dq = smem_ds + 2 * ABW_TILE;        // fp32 staging, one 32 x 32 box per drain warp
+  const uint32_t smem_stat = smem_dq + ABW_DQ_STG_BYTES;  // per query tile: LSE2 and Delta rows (bulk-copied by the producer)
   const uint32_t bars = smem_stat + ABW_STAT_BYTES;
-  const uint32_t kv_full = bars;            // K_j, V_j landed
-  const uint32_t qdo_full = bars + 8;       // [2]
-  const uint32_t qdo_empty = bars + 24;     // [2]
-  const uint32_t sdp_full = bars + 40;      // MMA -> softmax: S, dP complete
-  const uint32_t pds_full = bars + 48;      // softmax -> MMA: P, dS in shared memory (4 warps)
-  const uint32_t dq_full = bars + 56;       // MMA -> softmax: dQ_i complete (also: P / dS / dV / dK MMAs retired)
-  const uint32_t dq_empty = bars + 64;      // softmax -> MMA: dQ columns drained (4 warps)
-  const uint32_t sdp_free = bars + 72;      // softmax -> MMA: S, dP columns are in registers (ABW_SM_WARPS arrivals)
-  const uint32_t tmem_ptr_smem = bars + 80;
+  const uint32_t kv_full = bars;            // [2] K_j, V_j of an item landed
+  const uint32_t kv_empty = bars + 16;      // [2] all MMAs reading that K / V slot retired
+  const uint32_t qdo_full = bars + 32;      // [2]
+  const uint32_t qdo_empty = bars + 48;     // [2]
+  const uint32_t sdp_full = bars + 64;      // MMA -> softmax: S, dP complete
+  const uint32_t pds_full = bars + 72;      // softmax -> MMA: P, dS in shared memory (ABW_SM_WARPS arrivals)
+  const uint32_t dq_full = bars + 80;       // MMA -> softmax / drain: dQ of a tile complete (also: P / dS / dV / dK MMAs retired)
+  const uint32_t dq_empty = bars + 88;      // drain -> MMA: dQ columns drained (4 warps)
+  const uint32_t sdp_free = bars + 96;      // softmax -> MMA: S, dP columns are in registers (ABW_SM_WARPS arrivals)
+  const uint32_t dkv_empty = bars + 104;    // softmax -> MMA: dK / dV of the finished item are in registers (ABW_SM_WARPS arrivals)
+  const uint32_t tmem_ptr_smem = bars + 112;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int N = args.n_tokens, D = args.embed_dim;
-  const int n_q = (N + 127) / 128;
-  const int row_base = b * N;
-  int kv_len = N - j * 128;
-  kv_len = kv_len > 128 ? 128 : kv_len;
+  const int n_q = (N + 127) / 128;           // query tiles per item == key blocks per (image, head)
+  // this CTA's items: blockIdx.x, blockIdx.x + gridDim.x, ...; tiles are numbered t = w * n_q + i across them
+  const int my_items = (args.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int T = my_items * n_q;
+  auto item_of = [&](int w, int& j, int& h, int& b) {
+    const int it = blockIdx.x + w * gridDim.x;
+    j = it % n_q;
+    h = (it / n_q) % args.heads;
+    b = it / (n_q * args.heads);
+  };
+  auto kv_len_of = [&](int j) {
+    const int len = N - j * 128;
+    return len > 128 ? 128 : len;
+  };
 
   if (warp == ABW_TMA_WARP && lane == 0) {
     ptx::prefetch_tmap(&tmap_qkv);
     ptx::prefetch_tmap(&tmap_do);
     ptx::prefetch_tmap(&tmap_dq);
-    ptx::mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(kv_full + 8 * s, 1);
+      ptx::mbar_init(kv_empty + 8 * s, 1);
       ptx::mbar_init(qdo_full + 8 * s, 1);
       ptx::mbar_init(qdo_empty + 8 * s, 1);
     }
@@ -110,6 +125,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     ptx::mbar_init(pds_full, ABW_SM_WARPS);
     ptx::mbar_init(dq_full, 1);
     ptx::mbar_init(dq_empty, 4);
+    ptx::mbar_init(dkv_empty, ABW_SM_WARPS);
     ptx::fence_barrier_init();
   }
   if (warp == ABW_MMA_WARP) {
@@ -121,42 +137,50 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
   ptx::tc_fence_after();
   const uint32_t tmem_base = ptx::lds_u32(tmem_ptr_smem);
 
-  const int nch = (kv_len + 31) >> 5;          // 32-key chunks of this key block that hold keys
-  const bool tl = args.debug == 2 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
   if (warp >= ABW_SM_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ABW_REGS_OTHER));
   if (warp == ABW_TMA_WARP) {
     // ===================== TMA producer =====================
     if (ptx::elect_one()) {
-      ptx::mbar_arrive_expect_tx(kv_full, 2 * ABW_TILE);
-      ptx::tma_load_2d(smem_k, &tmap_qkv, kv_full, D + h * 64, row_base + j * 128);
-      ptx::tma_load_2d(smem_v, &tmap_qkv, kv_full, 2 * D + h * 64, row_base + j * 128);
-      for (int i = 0; i < n_q; ++i) {
-        const int slot = i & 1;
-        ptx::mbar_wait(qdo_empty + 8 * slot, ((i >> 1) & 1) ^ 1, 40);
-        ptx::mbar_arrive_expect_tx(qdo_full + 8 * slot, 2 * ABW_TILE + 1024);
-        const long long stat_off = (static_cast<long long>(b) * args.heads + h) * (n_q * 128) + i * 128;
-        ptx::bulk_load_1d(smem_stat + slot * 1024, args.lse2 + stat_off, 512, qdo_full + 8 * slot);
-        ptx::bulk_load_1d(smem_stat + slot * 1024 + 512, args.delta + stat_off, 512, qdo_full + 8 * slot);
-        ptx::tma_load_2d(smem_qdo + slot * 2 * ABW_TILE, &tmap_qkv, qdo_full + 8 * slot, h * 64, row_base + i * 128);
-        ptx::tma_load_2d(smem_qdo + slot * 2 * ABW_TILE + ABW_TILE, &tmap_do, qdo_full + 8 * slot, h * 64, row_base + i * 128);
+      for (int w = 0; w < my_items; ++w) {
+        int j, h, b;
+        item_of(w, j, h, b);
+        const int row_base = b * N;
+        const int ks = w & 1;
+        ptx::mbar_wait(kv_empty + 8 * ks, ((w >> 1) & 1) ^ 1, 40);
+        ptx::mbar_arrive_expect_tx(kv_full + 8 * ks, 2 * ABW_TILE);
+        ptx::tma_load_2d(smem_kv + ks * 2 * ABW_TILE, &tmap_qkv, kv_full + 8 * ks, D + h * 64, row_base + j * 128);
+        ptx::tma_load_2d(smem_kv + ks * 2 * ABW_TILE + ABW_TILE, &tmap_qkv, kv_full + 8 * ks, 2 * D + h * 64, row_base + j * 128);
+        const long long stat_base = (static_cast<long long>(b) * args.heads + h) * (n_q * 128);
+        for (int i = 0; i < n_q; ++i) {
+          const int t = w * n_q + i, slot = t & 1;
+          ptx::mbar_wait(qdo_empty + 8 * slot, ((t >> 1) & 1) ^ 1, 41);
+          ptx::mbar_arrive_expect_tx(qdo_full + 8 * slot, 2 * ABW_TILE + 1024);
+          ptx::bulk_load_1d(smem_stat + slot * 1024, args.lse2 + stat_base + i * 128, 512, qdo_full + 8 * slot);
+          ptx::bulk_load_1d(smem_stat + slot * 1024 + 512, args.delta + stat_base + i * 128, 512, qdo_full + 8 * slot);
+          ptx::tma_load_2d(smem_qdo + slot * 2 * ABW_TILE, &tmap_qkv, qdo_full + 8 * slot, h * 64, row_base + i * 128);
+          ptx::tma_load_2d(smem_qdo + slot * 2 * ABW_TILE + ABW_TILE, &tmap_do, qdo_full + 8 * slot, h * 64, row_base + i * 128);
+        }
       }
     }
   } else if (warp == ABW_MMA_WARP) {
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
-      const uint32_t idesc_s = ptx::make_idesc(128, nch * 32, false, false);  // S, dP: both operands K-major; only the chunks with keys
       constexpr uint32_t idesc_t = ptx::make_idesc(128, 64, true, true);      // dV, dK: A (P / dS) and B (dO / Q) MN-major
       constexpr uint32_t idesc_q = ptx::make_idesc(128, 64, false, true);     // dQ: A = dS K-major, B = K_j MN-major
-      const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_k, 1024, 0);
-      const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_v, 1024, 0);
-      const uint64_t k_desc_mn = ptx::make_smem_desc_sw128(smem_k, 1024, 1024);
       const uint64_t p_desc_mn = ptx::make_smem_desc_sw128(smem_p, 1024, ABW_TILE);    // 64-key atoms 16 KB apart
       const uint64_t ds_desc_mn = ptx::make_smem_desc_sw128(smem_ds, 1024, ABW_TILE);
       const uint64_t ds_desc_k = ptx::make_smem_desc_sw128(smem_ds, 1024, 0);
-      auto issue_sdp = [&](int i) {
-        const int slot = i & 1;
-        ptx::mbar_wait(qdo_full + 8 * slot, (i >> 1) & 1, 41);
+      // S = Q K^T and dP = dO V^T of tile t (item w = t / n_q); only the 32-key chunks that hold keys
+      auto issue_sdp = [&](int t) {
+        const int w = t / n_q, i = t - w * n_q, slot = t & 1, ks = w & 1;
+        int j, h, b;
+        item_of(w, j, h, b);
+        if (i == 0) ptx::mbar_wait(kv_full + 8 * ks, (w >> 1) & 1, 42);
+        ptx::mbar_wait(qdo_full + 8 * slot, (t >> 1) & 1, 41);
         ptx::tc_fence_after();
+        const uint32_t idesc_s = ptx::make_idesc(128, ((kv_len_of(j) + 31) >> 5) * 32, false, false);
+        const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_kv + ks * 2 * ABW_TILE, 1024, 0);
+        const uint64_t v_desc = ptx::desc_advance(k_desc, ABW_TILE);
         const uint64_t q_desc = ptx::make_smem_desc_sw128(smem_qdo + slot * 2 * ABW_TILE, 1024, 0);
         const uint64_t do_desc = ptx::desc_advance(q_desc, ABW_TILE);
 #pragma unroll
@@ -167,23 +191,31 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           ptx::umma_bf16_ss(tmem_base + ABW_DP_COL, ptx::desc_advance(do_desc, k * 32), ptx::desc_advance(v_desc, k * 32), idesc_s, k ? 1u : 0u);
         ptx::umma_commit(sdp_full);
       };
-      ptx::mbar_wait(kv_full, 0, 42);
-      issue_sdp(0);
-      for (int i = 0; i < n_q; ++i) {
-        const int slot = i & 1;
+      if (T > 0) issue_sdp(0);
+      for (int t = 0; t < T; ++t) {
+        const int w = t / n_q, i = t - w * n_q, slot = t & 1, ks = w & 1;
+        int j, h, b;
+        item_of(w, j, h, b);
+        const int kv_len = kv_len_of(j);
+        const bool tl = args.debug == 2 && blockIdx.x == 1 && w == 0;
         abw_stamp(tl, 1, i, 0);
-        // the next tile's logits go first, as soon as the softmax warps hold S_i / dP_i in registers: they are ready long
-        // before those warps finish tile i, and the tensor core runs dV / dK / dQ of tile i under the exponentials of i + 1
-        if (i + 1 < n_q) {
-          ptx::mbar_wait(sdp_free, i & 1, 49);
+        // the next tile's logits go first, as soon as the softmax warps hold S / dP of this tile in registers: they are ready
+        // long before those warps finish tile t, and the tensor core runs dV / dK / dQ of tile t under the exponentials of t + 1
+        if (t + 1 < T) {
+          ptx::mbar_wait(sdp_free, t & 1, 49);
           ptx::tc_fence_after();
-          issue_sdp(i + 1);
+          issue_sdp(t + 1);
         }
-        ptx::mbar_wait(pds_full, i & 1, 43);     // P_i, dS_i in shared memory
+        ptx::mbar_wait(pds_full, t & 1, 43);     // P, dS of tile t in shared memory
         ptx::tc_fence_after();
         abw_stamp(tl, 1, i, 1);
+        if (i == 0 && w > 0) {                   // dK / dV still hold the previous item until the softmax warps have read them out
+          ptx::mbar_wait(dkv_empty, (w - 1) & 1, 51);
+          ptx::tc_fence_after();
+        }
         const uint64_t q_desc_mn = ptx::make_smem_desc_sw128(smem_qdo + slot * 2 * ABW_TILE, 1024, 1024);
         const uint64_t do_desc_mn = ptx::desc_advance(q_desc_mn, ABW_TILE);
+        const uint64_t k_desc_mn = ptx::make_smem_desc_sw128(smem_kv + ks * 2 * ABW_TILE, 1024, 1024);
         const uint32_t acc0 = i > 0 ? 1u : 0u;
         int q_len = N - i * 128;
         q_len = q_len > 128 ? 128 : q_len;
@@ -206,8 +238,8 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         }
         ptx::umma_commit(qdo_empty + 8 * slot);   // Q_i / dO_i no longer needed
         // dQ_i = dS K_j: 16 keys per MMA (32 B inside a 64-key atom of dS; 2048 B of K_j)
-        if (i > 0) {
-          ptx::mbar_wait(dq_empty, (i - 1) & 1, 44);
+        if (t > 0) {
+          ptx::mbar_wait(dq_empty, (t - 1) & 1, 44);
           ptx::tc_fence_after();
         }
         if (kv_len == 128) {
@@ -223,41 +255,44 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                               ptx::desc_advance(k_desc_mn, k * 2048), idesc_q, k ? 1u : 0u);
         }
         ptx::umma_commit(dq_full);
+        if (i == n_q - 1) ptx::umma_commit(kv_empty + 8 * ks);   // last reader of this K / V slot
         abw_stamp(tl, 1, i, 2);
       }
     }
   } else if (warp >= ABW_DRAIN_WARP0 && warp < ABW_DRAIN_WARP0 + 4) {
     // ===================== dQ drain warps =====================
-    // dQ of tile i: TMEM -> two fp32 boxes -> reduce-add into dQacc[b, i*128 + q*32 .., h*64 ..]; off the softmax warps' path
+    // dQ of tile t: TMEM -> fp32 box -> reduce-add into dQacc[b, i*128 + q*32 .., h*64 ..]; off the softmax warps' path
     const int q = warp & 3;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t stg = smem_dq + q * 8192;
-    for (int i = 0; i < n_q; ++i) {
-      ptx::mbar_wait(dq_full, i & 1, 46);
+    const uint32_t stg = smem_dq + q * 4096;
+    const int sw = lane & 7;
+    for (int t = 0; t < T; ++t) {
+      const int w = t / n_q, i = t - w * n_q;
+      int j, h, b;
+      item_of(w, j, h, b);
+      ptx::mbar_wait(dq_full, t & 1, 46);
       ptx::tc_fence_after();
-      if (lane == 0) ptx::bulk_wait_read0();   // the previous tile's reduces have finished reading the boxes
-      __syncwarp();
-      const int sw = lane & 7;
+      const bool store = i * 128 + q * 32 < N && args.debug != 1;
 #pragma unroll
-      for (int hb = 0; hb < 2; ++hb) {           // one 32-column box at a time (register budget of this warpgroup)
+      for (int hb = 0; hb < 2; ++hb) {           // one 32-column box at a time through one staging box
         uint32_t t0[32];
         ptx::tmem_ld_32x32b_x32(lane_addr + ABW_DQ_COL + hb * 32, t0);
         ptx::tmem_ld_wait(t0);
-        if (hb == 1) {                           // both halves are in registers / shared memory: dQ columns free
+        if (hb == 1) {                           // both halves are out of TMEM: dQ columns free (before any wait on the box)
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(dq_empty);
         }
+        if (lane == 0) ptx::bulk_wait_read0();   // the previous reduce has finished reading the box
+        __syncwarp();
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          ptx::sts_v4(stg + hb * 4096 + lane * 128 + ((g ^ sw) << 4), t0[4 * g], t0[4 * g + 1], t0[4 * g + 2], t0[4 * g + 3]);
-      }
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0 && i * 128 + q * 32 < N && args.debug != 1) {
-        tma_reduce_add_3d(&tmap_dq, stg, h * 64, i * 128 + q * 32, b);
-        tma_reduce_add_3d(&tmap_dq, stg + 4096, h * 64 + 32, i * 128 + q * 32, b);
-        ptx::bulk_commit();
+        for (int g = 0; g < 8; ++g) ptx::sts_v4(stg + lane * 128 + ((g ^ sw) << 4), t0[4 * g], t0[4 * g + 1], t0[4 * g + 2], t0[4 * g + 3]);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && store) {
+          tma_reduce_add_3d(&tmap_dq, stg, h * 64 + hb * 32, i * 128 + q * 32, b);
+          ptx::bulk_commit();
+        }
       }
     }
     if (lane == 0) ptx::bulk_wait_all0();
@@ -265,23 +300,60 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     // ===================== softmax warps (0 .. ABW_SM_WARPS-1) =====================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ABW_REGS_SOFTMAX));
     const int q = warp & 3;
-    const int half = warp >> 2;    // which half of the key columns (S / dP phase), and dK (0) or dV (1) at the end
-    const int r = q * 32 + lane;   // query row inside the tile (S, dP phases) or key row (final dK / dV drain)
+    const int half = warp >> 2;    // which half of the key columns (S / dP phase), and dK (0) or dV (1) at the end of an item
+    const int r = q * 32 + lane;   // query row inside the tile (S, dP phases) or key row (dK / dV drain)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float sl2 = args.scale_log2;
     const uint64_t sl2_2 = ptx::dup_f32x2(sl2);
     const uint64_t sc_2 = ptx::dup_f32x2(args.scale);
-    for (int i = 0; i < n_q; ++i) {
+    // dK_j (warps 0..3) / dV_j (warps 4..7) of item w: TMEM -> registers -> bf16 rows of dQKV.  Called once all MMAs of the item
+    // have retired (dq_full of its last tile); the MMA warp may overwrite the accumulators after the dkv_empty arrive.
+    auto drain_dkv = [&](int w) {
+      int j, h, b;
+      item_of(w, j, h, b);
+      const int kv_len = kv_len_of(j);
+      __nv_bfloat16* o = args.dqkv + static_cast<long long>(b * N + j * 128 + r) * args.ld + h * 64 + (half == 0 ? D : 2 * D);
+      uint32_t t0[32], t1[32];
+      ptx::tmem_ld_32x32b_x32(lane_addr + (half == 0 ? ABW_DK_COL : ABW_DV_COL), t0);        // warp-collective
+      ptx::tmem_ld_32x32b_x32(lane_addr + (half == 0 ? ABW_DK_COL : ABW_DV_COL) + 32, t1);
+      ptx::tmem_ld_wait(t0);
+      ptx::tmem_ld_wait(t1);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(dkv_empty);
+      if (r < kv_len) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          reinterpret_cast<uint4*>(o)[g] =
+              make_uint4(ptx::pack_bf16x2(__uint_as_float(t0[8 * g]), __uint_as_float(t0[8 * g + 1])),
+                         ptx::pack_bf16x2(__uint_as_float(t0[8 * g + 2]), __uint_as_float(t0[8 * g + 3])),
+                         ptx::pack_bf16x2(__uint_as_float(t0[8 * g + 4]), __uint_as_float(t0[8 * g + 5])),
+                         ptx::pack_bf16x2(__uint_as_float(t0[8 * g + 6]), __uint_as_float(t0[8 * g + 7])));
+          reinterpret_cast<uint4*>(o + 32)[g] =
+              make_uint4(ptx::pack_bf16x2(__uint_as_float(t1[8 * g]), __uint_as_float(t1[8 * g + 1])),
+                         ptx::pack_bf16x2(__uint_as_float(t1[8 * g + 2]), __uint_as_float(t1[8 * g + 3])),
+                         ptx::pack_bf16x2(__uint_as_float(t1[8 * g + 4]), __uint_as_float(t1[8 * g + 5])),
+                         ptx::pack_bf16x2(__uint_as_float(t1[8 * g + 6]), __uint_as_float(t1[8 * g + 7])));
+        }
+      }
+    };
+    for (int t = 0; t < T; ++t) {
+      const int w = t / n_q, i = t - w * n_q;
+      int j, h, b;
+      item_of(w, j, h, b);
+      const int kv_len = kv_len_of(j);
+      const int nch = (kv_len + 31) >> 5;          // 32-key chunks of this key block that hold keys
+      const bool tl = args.debug == 2 && blockIdx.x == 1 && w == 0 && lane == 0;
       abw_stamp(tl && warp == 0, 0, i, 6);
       // row statistics of this query tile from shared memory (rows beyond the image: LSE2 = +inf -> P = 0 -> dS = 0; dP is
       // finite there: the rows hold other tokens or zeros)
-      ptx::mbar_wait(qdo_full + 8 * (i & 1), (i >> 1) & 1, 50);
-      const float lse = ptx::lds_f32(smem_stat + (i & 1) * 1024 + r * 4);
-      const float dlt = ptx::lds_f32(smem_stat + (i & 1) * 1024 + 512 + r * 4);
+      ptx::mbar_wait(qdo_full + 8 * (t & 1), (t >> 1) & 1, 50);
+      const float lse = ptx::lds_f32(smem_stat + (t & 1) * 1024 + r * 4);
+      const float dlt = ptx::lds_f32(smem_stat + (t & 1) * 1024 + 512 + r * 4);
       const uint64_t nlse_2 = ptx::dup_f32x2(-lse);
       const uint64_t ndl_2 = ptx::dup_f32x2(-dlt * args.scale);
       abw_stamp(tl && warp == 0, 0, i, 0);
-      ptx::mbar_wait(sdp_full, i & 1, 45);
+      ptx::mbar_wait(sdp_full, t & 1, 45);
       ptx::tc_fence_after();
       abw_stamp(tl && warp == 0, 0, i, 1);
       // ---- P = exp2(S * sl2 - LSE2), dS = P * (dP * scale - Delta * scale) for this warp's (up to) two 32-key chunks, on the
@@ -310,31 +382,37 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         const int c = 2 * half + cc;
         if (c < nch) {
 #pragma unroll
-          for (int t = 0; t < 16; ++t) {
-            const uint64_t a2 = ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sv[cc][2 * t]), __uint_as_float(sv[cc][2 * t + 1])), sl2_2, nlse_2);
+          for (int u = 0; u < 16; ++u) {
+            const uint64_t a2 = ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sv[cc][2 * u]), __uint_as_float(sv[cc][2 * u + 1])), sl2_2, nlse_2);
             float a0, a1;
             ptx::unpack_f32x2(a2, a0, a1);
             const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);
-            const uint64_t g2 = ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(dp[cc][2 * t]), __uint_as_float(dp[cc][2 * t + 1])), sc_2, ndl_2);
+            const uint64_t g2 = ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(dp[cc][2 * u]), __uint_as_float(dp[cc][2 * u + 1])), sc_2, ndl_2);
             const uint64_t d2 = ptx::mul_f32x2(ptx::pack_f32x2(p0, p1), g2);
             float d0, d1;
             ptx::unpack_f32x2(d2, d0, d1);
-            sv[cc][t] = ptx::pack_bf16x2(p0, p1);     // words t <= 2t have been consumed
-            dp[cc][t] = ptx::pack_bf16x2(d0, d1);
+            sv[cc][u] = ptx::pack_bf16x2(p0, p1);     // words u <= 2u have been consumed
+            dp[cc][u] = ptx::pack_bf16x2(d0, d1);
           }
           if (c * 32 + 32 > kv_len) {   // ragged key block: keys beyond the image contribute nothing
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-              const int k0 = c * 32 + 2 * t;
+            for (int u = 0; u < 16; ++u) {
+              const int k0 = c * 32 + 2 * u;
               const uint32_t keep = (k0 < kv_len ? 0x0000ffffu : 0u) | (k0 + 1 < kv_len ? 0xffff0000u : 0u);
-              sv[cc][t] &= keep;
-              dp[cc][t] &= keep;
+              sv[cc][u] &= keep;
+              dp[cc][u] &= keep;
             }
           }
         }
       }
       abw_stamp(tl && warp == 0, 0, i, 2);
-      if (i > 0) ptx::mbar_wait(dq_full, (i - 1) & 1, 47);   // previous tile's dV / dK / dQ MMAs retired: P / dS may be overwritten
+      if (t > 0) {   // previous tile's dV / dK / dQ MMAs retired: P / dS may be overwritten
+        ptx::mbar_wait(dq_full, (t - 1) & 1, 47);
+        if (i == 0) {   // ... and it closed an item: its dK / dV leave now, under the tensor core's work on this item
+          ptx::tc_fence_after();
+          drain_dkv(w - 1);
+        }
+      }
       abw_stamp(tl && warp == 0, 0, i, 3);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
@@ -355,32 +433,11 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       if (lane == 0) ptx::mbar_arrive(pds_full);
       abw_stamp(tl && warp == 0, 0, i, 4);
     }
-    ptx::mbar_wait(dq_full, (n_q - 1) & 1, 48);
-    ptx::tc_fence_after();
-    // ---- dK_j, dV_j: complete once dq_full of the last tile fired (the commit covers all earlier MMAs)
-    {
-      __nv_bfloat16* orow = args.dqkv + static_cast<long long>(row_base + j * 128 + r) * args.ld + h * 64;
-      {   // warps 0..3: dK -> column block D; warps 4..7: dV -> column block 2D
-        const int which = half;
-        __nv_bfloat16* o = orow + (which == 0 ? D : 2 * D);
-#pragma unroll
-        for (int c = 0; c < 64; c += 32) {
-          uint32_t t[32];
-          ptx::tmem_ld_32x32b_x32(lane_addr + (which == 0 ? ABW_DK_COL : ABW_DV_COL) + c, t);   // warp-collective
-          ptx::tmem_ld_wait(t);
-          if (r < kv_len) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              reinterpret_cast<uint4*>(o + c)[g] =
-                  make_uint4(ptx::pack_bf16x2(__uint_as_float(t[8 * g]), __uint_as_float(t[8 * g + 1])),
-                             ptx::pack_bf16x2(__uint_as_float(t[8 * g + 2]), __uint_as_float(t[8 * g + 3])),
-                             ptx::pack_bf16x2(__uint_as_float(t[8 * g + 4]), __uint_as_float(t[8 * g + 5])),
-                             ptx::pack_bf16x2(__uint_as_float(t[8 * g + 6]), __uint_as_float(t[8 * g + 7])));
-          }
-        }
-      }
+    if (T > 0) {
+      ptx::mbar_wait(dq_full, (T - 1) & 1, 48);
+      ptx::tc_fence_after();
+      drain_dkv(my_items - 1);
     }
-    if (lane == 0) ptx::bulk_wait_all0();
   }
 
   ptx::tc_fence_before();
