@@ -148,3 +148,85 @@ def test_vit_small_224_gradients_match_oracle():
           f"global relative L2 error {(num / den) ** 0.5:.3e}")
     assert (num / den) ** 0.5 <= 2e-2
     assert worst[1] <= 6e-2, worst
+
+
+def _make_mim(cfg_init, img, precision="bf16", seed=21):
+    sd = VO.randomize_affine(VO.init_state_dict(cfg_init, seed=seed, mim=True), seed=seed + 1)
+    gd = torch.Generator().manual_seed(seed + 2)
+    D = cfg_init.embed_dim
+    dec_w, dec_b = torch.randn(192, D, 1, 1, generator=gd) * 0.05, torch.randn(192, generator=gd) * 0.05
+    enc = vob.VisionTransformerForSimMIM(patch_size=8, embed_dim=D, depth=cfg_init.depth, num_heads=cfg_init.num_heads, mlp_ratio=4,
+                                         img_size=[img], qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), precision=precision)
+    enc.load_state_dict(sd, strict=True)
+    mim = vob.MIM(encoder=enc, encoder_stride=8)
+    mim.decoder[0].weight.data.copy_(dec_w)
+    mim.decoder[0].bias.data.copy_(dec_b)
+    params = dict(sd)
+    params["decoder.0.weight"], params["decoder.0.bias"] = dec_w, dec_b
+    return mim.cuda().train(), params
+
+
+def _global_rel_err(mim, ref):
+    num = den = 0.0
+    for n, p in mim.named_parameters():
+        r = ref[_key(n)]
+        num += float((p.grad.cpu() - r).double().pow(2).sum())
+        den += float(r.double().pow(2).sum())
+    return (num / den) ** 0.5
+
+
+@pytest.mark.parametrize("D,heads,img,batch", [(768, 12, 64, 3), (128, 2, 16, 1), (384, 6, 96, 5)])
+def test_other_shapes_gradients_match_oracle(D, heads, img, batch):
+    """ViT-B width (wgrad / LayerNorm / GELU instantiations for D = 768, hidden 3072), a 2 x 2-patch image (N = 5: every tile
+    ragged) and a multi-tile ragged sequence (N = 145) -- position table bicubically resized in all three."""
+    cfg_init = VO.ViTConfig(embed_dim=D, depth=2, num_heads=heads, patch_size=8, img_size=224)
+    cfg = VO.ViTConfig(embed_dim=D, depth=2, num_heads=heads, patch_size=8, img_size=img)
+    mim, params = _make_mim(cfg_init, img)
+    x = VO.synthetic_tile(img, seed=31, batch=batch)
+    rs = np.random.RandomState(6)
+    mask = torch.from_numpy(np.stack([VO.mask_generator(rs, img, 16 if img % 16 == 0 else 8, 8, 0.5) for _ in range(batch)]))
+    ref_loss, ref = TO.mim_loss_and_grads(params, cfg, x, mask)
+    loss, _, _ = mim(x.cuda(), mask.cuda())
+    loss.sum().backward()
+    err = _global_rel_err(mim, ref)
+    print(f"D={D} img={img} batch={batch}: loss {loss.item():.5f} vs {ref_loss.item():.5f}, global relative L2 gradient error {err:.3e}")
+    assert abs(loss.item() - ref_loss.item()) <= 2e-2 * abs(ref_loss.item())
+    # with a handful of masked tokens (the 16 x 16 image has 4) a single flipped sign of the L1 gradient is a visible
+    # fraction of every gradient; the bar is looser there
+    assert err <= (3e-2 if batch * (img // 8) ** 2 >= 64 else 6e-2)
+
+
+def test_gradient_accumulation_and_grad_scale():
+    """ACCUMULATION_STEPS > 1 (SSS/mim.py:160-171): (loss / k).backward() twice accumulates into .grad like autograd does."""
+    cfg_init = VO.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=8, img_size=224)
+    mim, _ = _make_mim(cfg_init, 32)
+    xs = [VO.synthetic_tile(32, seed=40 + k, batch=2).cuda() for k in range(2)]
+    rs = np.random.RandomState(7)
+    ms = [torch.from_numpy(np.stack([VO.mask_generator(rs, 32, 16, 8, 0.5) for _ in range(2)])).cuda() for _ in range(2)]
+    singles = []
+    for x, m in zip(xs, ms):
+        mim.zero_grad(set_to_none=True)
+        loss, _, _ = mim(x, m)
+        (loss / 2).sum().backward()
+        singles.append(mim._gflat.clone())
+    mim.zero_grad(set_to_none=True)
+    for x, m in zip(xs, ms):
+        loss, _, _ = mim(x, m)
+        (loss / 2).sum().backward()
+    want = singles[0] + singles[1]
+    assert (mim._gflat - want).abs().max().item() <= 1e-5 * want.abs().max().item() + 1e-7
+    # every parameter's .grad is a view into the flat buffer
+    assert all(p.grad.data_ptr() >= mim._gflat.data_ptr() and p.grad.data_ptr() < mim._gflat.data_ptr() + 4 * mim._gflat.numel()
+               for p in mim.parameters())
+
+
+def test_training_needs_bf16_engine_and_eval_mode_is_plain_forward():
+    cfg_init = VO.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=8, img_size=224)
+    mim, _ = _make_mim(cfg_init, 32, precision="fp32")
+    x = VO.synthetic_tile(32, seed=3, batch=2).cuda()
+    mask = torch.from_numpy(np.stack([VO.mask_generator(np.random.RandomState(1), 32, 16, 8, 0.5) for _ in range(2)])).cuda()
+    with pytest.raises(vob._lib.VitocmError, match="bf16"):
+        mim(x, mask)
+    mim.eval()
+    loss, x_rec, _ = mim(x, mask)            # evaluation works in the fp32-parity mode
+    assert not loss.requires_grad and torch.isfinite(loss)

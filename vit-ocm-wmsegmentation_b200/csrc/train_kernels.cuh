@@ -8,7 +8,7 @@
 //   mim_loss_bwd_kernel                  model.py:73-76 backward through the masked L1 and PixelShuffle
 //   patch_grad_rows_kernel, im2col_bf16_kernel, token_grad_kernel   model.py:29-41 backward (mask-token mix, cls, pos)
 //   sumsq_kernel, adamw_kernel           torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW (optimizer.py:73-75)
-//   transpose_weight_kernel              fp32 [R][C] master -> bf16 [C][R] (the dgrad GEMM's K-major B operand)
+//   repack_weights_kernel                fp32 masters -> bf16 [R][C] and [C][R] (forward / input-gradient B operands), one launch
 // All vectorised and coalesced; statistics and accumulations in fp32 (fp64 for the global gradient norm).
 #pragma once
 #include "ptx.cuh"
@@ -478,23 +478,6 @@ repack_weights_kernel(const RepackEntry* __restrict__ table, int n_entries) {
   for (int k = ty; k < 32; k += 8) {
     const int c = c0 + k, r = r0 + tx;
     if (c < e.C && r < e.R) e.dst_t[static_cast<long long>(c) * e.R + r] = __float2bfloat16_rn(tile[tx][k]);
-  }
-}
-
-// fp32 master [R][C] -> bf16 [C][R]: B operand (K-major) of the input-gradient GEMM  dX = dY . W
-__global__ void __launch_bounds__(256)
-transpose_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int R, int C) {
-  __shared__ float tile[32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int k = ty; k < 32; k += 8) {
-    const int r = r0 + k, c = c0 + tx;
-    tile[k][tx] = (r < R && c < C) ? w[static_cast<long long>(r) * C + c] : 0.f;
-  }
-  __syncthreads();
-  for (int k = ty; k < 32; k += 8) {
-    const int c = c0 + k, r = r0 + tx;
-    if (c < C && r < R) out[static_cast<long long>(c) * R + r] = __float2bfloat16_rn(tile[tx][k]);
   }
 }
 

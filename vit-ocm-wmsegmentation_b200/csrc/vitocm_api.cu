@@ -669,12 +669,6 @@ static int repack_weights(vitocm_engine* e, cudaStream_t st) {
     LAUNCH_CHECK();
     return 0;
   };
-  auto pack_t = [&](DevBuf& dst, const float* src, int R, int C) -> int {   // fp32 [R][C] -> bf16 [C][R]
-    TRY(dst.alloc(static_cast<size_t>(R) * C * 2));
-    transpose_weight_kernel<<<dim3((C + 31) / 32, (R + 31) / 32), 256, 0, st>>>(src, dst.as<__nv_bfloat16>(), R, C);
-    LAUNCH_CHECK();
-    return 0;
-  };
   std::vector<RepackEntry> entries;
   int total_tiles = 0;
   auto add_entry = [&](DevBuf& dst, DevBuf& dst_t, const float* src, int R, int C) -> int {
