@@ -90,6 +90,13 @@ int vitocm_set_concurrency(vitocm_engine* e, int lanes);
 int vitocm_forward_cls_attn(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, float* out_rows,
                             void* ws, size_t ws_bytes, int chunk_tiles, void* stream);
 
+/* Gray fast path of vitocm_forward_cls_attn: x [B][1][H][W] fp32 stands for an image whose in_chans channels are all equal
+ * (every OCM tile of the reference: PIL "RGB" of a gray PNG, SSS/sw_processing.py:225-236).  The patch filter is folded over
+ * the channels at vitocm_finalize_weights, so the patch-embedding GEMM contracts over p*p instead of in_chans*p*p taps and the
+ * tiles are a third of the bytes; same arithmetic up to fp32 summation order. */
+int vitocm_forward_cls_attn_gray(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, float* out_rows,
+                                 void* ws, size_t ws_bytes, int chunk_tiles, void* stream);
+
 /* The same forward for a LIST of query tokens (SSS/analyse_attention.py:183-247: compute_attention(..., query=q) for a
  * region query) and, optionally, the last block's K features (SSS/analyse_attention.py:139-163, SSS/eval.py:186-202, the
  * input of the k-means feature clustering): queries = DEVICE int32 [nq] token indices in [0, N) (0 = CLS, 1 + i = patch i);

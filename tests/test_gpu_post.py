@@ -125,8 +125,10 @@ def test_mosaic_pipeline_vs_oracle(W, S, size):
     crops = PO.sliding_window(mosaic, S, W)
     xs = torch.from_numpy(np.stack(crops)).float().div(255.0).unsqueeze(1).expand(-1, 3, -1, -1).contiguous()
     rows_ref = VO.cls_attention_rows(sd, tiny, xs).numpy()
-    rows_gpu = m.cls_attention_rows(xs.cuda()).cpu().numpy()
+    rows_gpu = m.cls_attention_rows(xs[:, :1].contiguous().cuda()).cpu().numpy()     # gray fast path, as MosaicSegmenter runs it
     assert float((np.abs(rows_gpu - rows_ref) / rows_ref).max()) <= 1e-3
+    rows_rgb = m.cls_attention_rows(xs.cuda()).cpu().numpy()                          # the 3-channel path: same up to summation order
+    assert float((np.abs(rows_gpu - rows_rgb) / rows_rgb).max()) <= 2e-5
     # post stage, exact, from the GPU's rows
     stitched, (th, th2, th3, _, _), gray = PO.mosaic_segment(rows_gpu, mosaic, S, W, 8)
     assert np.array_equal(seg.stitched_map(out["lowres"]).cpu().numpy(), stitched)

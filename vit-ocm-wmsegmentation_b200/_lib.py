@@ -31,6 +31,8 @@ SIGNATURES = {
     "vitocm_set_concurrency": (c_int, [c_void_p, c_int]),
     "vitocm_forward_cls_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                         c_int, c_void_p]),
+    "vitocm_forward_cls_attn_gray": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                             c_int, c_void_p]),
     "vitocm_forward_query_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                           c_size_t, c_int, c_void_p]),
     "vitocm_prepare_tokens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -309,6 +309,17 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, long lo
   }
 }
 
+// Patch filter folded over the input channels: out[d][k] = sum_c w[d][c][k] (k over the p*p taps).  A gray image fed as
+// R = G = B (every OCM tile of the reference) then needs K = p*p instead of C*p*p in the patch-embedding GEMM.
+__global__ void fold_patch_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int D, int C, int pp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D * pp) return;
+  const int d = i / pp, k = i - d * pp;
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += w[(static_cast<long long>(d) * C + c) * pp + k];
+  out[i] = s;
+}
+
 // fp32 [R, C] weight -> bf16 hi (and lo) [R, ldo]  (weight repack at load time)
 __global__ void split_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, long long ldo, int split,
                                     int lo_off, int R, int C) {

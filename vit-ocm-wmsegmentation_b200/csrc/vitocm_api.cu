@@ -154,6 +154,7 @@ struct vitocm_engine {
   std::map<std::string, DevBuf*> master;  // fp32 weights as loaded
   std::vector<LayerW> layers;
   DevBuf patch_w;   // bf16 [D][2K]  (hi | lo): the conv filter as a K-major GEMM operand
+  DevBuf patch_w_gray_f32, patch_w_gray;   // the filter summed over input channels, fp32 [D][p*p] and bf16 [D][2 p*p]: gray fast path
   DevBuf dec_w;     // MIM decoder 1x1 conv weight, bf16 [C p^2][D * parts] (present iff "decoder.0.weight" was loaded)
   DevBuf dec_w_t;   // bf16 [D][C p^2] (training)
   DevBuf repack_table;   // RepackEntry[] for the one-launch repack of the Linear weights (bf16 engines)
@@ -479,8 +480,10 @@ int run_layernorm(const float* X, const float* g, const float* b, void* out_bf16
 
 // prepare_tokens (vit.py:198-209) as an im2col-free tcgen05 GEMM: M = B * n patches, K = C p^2, N = D.
 int run_patch_embed(const vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const float* mask,
-                    float* X, cudaStream_t st) {
-  const int p = e->cfg.patch_size, C = e->cfg.in_chans, D = e->cfg.embed_dim;
+                    float* X, cudaStream_t st, bool gray = false) {
+  // gray: x is [B][1][H][W], standing for an image with equal channels; the channel-folded filter does the same arithmetic
+  const int p = e->cfg.patch_size, C = gray ? 1 : e->cfg.in_chans, D = e->cfg.embed_dim;
+  if (gray && e->patch_w_gray.p == nullptr) return fail(VITOCM_ERR_STATE, "gray fast path needs in_chans > 1");
   if (H % p != 0 || W % p != 0) return fail(VITOCM_ERR_INVALID, "image %dx%d not a multiple of patch %d", H, W, p);
   const int K = C * p * p;
   if (p % 8 != 0 || K % GEMM_BK != 0) return fail(VITOCM_ERR_INVALID, "patch embedding needs patch %% 8 == 0 and C*p*p %% 64 == 0 (patch %d, chans %d)", p, C);
@@ -495,7 +498,7 @@ int run_patch_embed(const vitocm_engine* e, const float* x, int B, int H, int W,
   LAUNCH_CHECK();
   const int bn = (D % 192 == 0) ? 192 : (D % 128 == 0 ? 128 : 64);
   CUtensorMap tb;
-  TRY(make_tmap_bf16(&tb, e->patch_w.p, D, 2LL * K, 2LL * K, bn));
+  TRY(make_tmap_bf16(&tb, gray ? e->patch_w_gray.p : e->patch_w.p, D, 2LL * K, 2LL * K, bn));
   GemmArgs a{};
   a.M = M; a.N = D; a.kblocks = K / GEMM_BK; a.nterms = 3; a.lo_k = K;   // split precision in both modes
   a.bias = e->w("patch_embed.proj.bias");
@@ -679,6 +682,13 @@ static int repack_weights(vitocm_engine* e, cudaStream_t st) {
     entries.push_back(en);
     return 0;
   };
+  if (e->cfg.in_chans > 1) {   // gray fast path (vitocm_forward_cls_attn_gray): filter folded over the channels
+    const int pp = e->cfg.patch_size * e->cfg.patch_size;
+    TRY(e->patch_w_gray_f32.alloc(static_cast<size_t>(D) * pp * 4));
+    fold_patch_weight_kernel<<<(D * pp + 255) / 256, 256, 0, st>>>(e->w("patch_embed.proj.weight"), e->patch_w_gray_f32.as<float>(), D, e->cfg.in_chans, pp);
+    LAUNCH_CHECK();
+    TRY(pack(e->patch_w_gray, e->patch_w_gray_f32.as<float>(), D, pp, 1));
+  }
   TRY(pack(e->patch_w, e->w("patch_embed.proj.weight"), D, K, 1));   // always hi | lo: K is tiny, keep the tokens fp32-grade
   for (int l = 0; l < e->cfg.depth; ++l) {
     const std::string pre = "blocks." + std::to_string(l) + ".";
@@ -787,7 +797,12 @@ int vitocm_prepare_tokens(vitocm_engine* e, const float* x, int B, int H, int W,
 }
 
 static int forward_rows(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const int* queries, int nq,
-                        float* out_rows, float* k_out, void* ws, size_t ws_bytes, int chunk_tiles, void* stream);
+                        float* out_rows, float* k_out, void* ws, size_t ws_bytes, int chunk_tiles, void* stream, bool gray = false);
+
+int vitocm_forward_cls_attn_gray(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, float* out_rows,
+                                 void* ws, size_t ws_bytes, int chunk_tiles, void* stream) {
+  return forward_rows(e, x, B, H, W, pos, nullptr, 1, out_rows, nullptr, ws, ws_bytes, chunk_tiles, stream, true);
+}
 
 int vitocm_forward_cls_attn(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, float* out_rows,
                             void* ws, size_t ws_bytes, int chunk_tiles, void* stream) {
@@ -801,10 +816,10 @@ int vitocm_forward_query_attn(vitocm_engine* e, const float* x, int B, int H, in
 }
 
 static int forward_rows(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const int* queries, int nq,
-                        float* out_rows, float* k_out, void* ws, size_t ws_bytes, int chunk_tiles, void* stream) {
+                        float* out_rows, float* k_out, void* ws, size_t ws_bytes, int chunk_tiles, void* stream, bool gray) {
   TRY(check_engine(e));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int p = e->cfg.patch_size, D = e->cfg.embed_dim, heads = e->cfg.num_heads, C = e->cfg.in_chans;
+  const int p = e->cfg.patch_size, D = e->cfg.embed_dim, heads = e->cfg.num_heads, C = gray ? 1 : e->cfg.in_chans;
   if (B <= 0) return 0;
   if (H % p || W % p) return fail(VITOCM_ERR_INVALID, "image %dx%d not a multiple of patch %d", H, W, p);
   const int N = (H / p) * (W / p) + 1;
@@ -847,7 +862,7 @@ static int forward_rows(vitocm_engine* e, const float* x, int B, int H, int W, c
       ++active;
     }
     for (int k = 0; k < active; ++k)
-      TRY(run_patch_embed(e, x + static_cast<long long>(b0s[k]) * C * H * W, bcs[k], H, W, pos, nullptr, lane_ws[k].X, lane_st[k]));
+      TRY(run_patch_embed(e, x + static_cast<long long>(b0s[k]) * C * H * W, bcs[k], H, W, pos, nullptr, lane_ws[k].X, lane_st[k], gray));
     bool xn_ready[vitocm_engine::MAX_LANES] = {false, false, false, false};
     for (int l = 0; l + 1 < e->cfg.depth; ++l) {
       // the next block's norm1 rides on this block's fc2 epilogue -- except into the last block, whose K projection

@@ -214,7 +214,8 @@ class MosaicSegmenter:
     def lowres_maps(self, mosaic: torch.Tensor, t0: int, t1: int) -> torch.Tensor:
         """Per-tile normalised low-res maps [t1-t0, h, w] for tiles t0..t1-1 of the n x n grid."""
         lib = _lib.load_library()
-        W, S, C = self.window, self.stride, self.model.in_chans
+        W, S = self.window, self.stride
+        C = 1          # the mosaic is gray: one channel per tile and the channel-folded patch filter (gray fast path)
         n = grid_size(mosaic.shape[0], S)
         lh = W // self.patch
         out = torch.empty(max(t1 - t0, 0), lh * lh, dtype=torch.float32, device=mosaic.device)

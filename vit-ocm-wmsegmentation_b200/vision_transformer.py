@@ -315,8 +315,8 @@ class VisionTransformer(nn.Module):
         return table
 
     # ------------------------------------------------------------------ C-ABI calls
-    def _check_input(self, x):
-        if x.dim() != 4 or x.shape[1] != self.in_chans:
+    def _check_input(self, x, allow_gray: bool = False):
+        if x.dim() != 4 or (x.shape[1] != self.in_chans and not (allow_gray and x.shape[1] == 1)):
             raise ValueError(f"expected [B,{self.in_chans},H,W], got {tuple(x.shape)}")
         p = self.patch_embed.patch_size
         if x.shape[2] % p or x.shape[3] % p:
@@ -331,17 +331,20 @@ class VisionTransformer(nn.Module):
 
     @torch.no_grad()
     def cls_attention_rows(self, x: torch.Tensor) -> torch.Tensor:
-        """get_last_selfattention(x)[:, :, 0, :] -> [B, heads, N] fp32, without forming N x N."""
-        x = self._check_input(x)
+        """get_last_selfattention(x)[:, :, 0, :] -> [B, heads, N] fp32, without forming N x N.
+
+        A single-channel ``x`` [B, 1, H, W] on a multi-channel model is the gray fast path: it stands for the image with all
+        channels equal (what the reference feeds for every OCM tile) and runs the channel-folded patch filter."""
+        x = self._check_input(x, allow_gray=True)
         eng = self._ensure_engine()
-        B, _, H, W = x.shape
+        B, Cx, H, W = x.shape
         N = self._tokens(x)
         pos = self._pos_table(N - 1, H, W)
         chunk = max(1, min(self.chunk_tiles, B))
         ws = self._workspace(chunk, N, x.device)
         out = torch.empty(B, self.num_heads, N, dtype=torch.float32, device=x.device)
-        check(_lib.load_library().vitocm_forward_cls_attn(eng, ptr(x), B, H, W, ptr(pos), ptr(out), ptr(ws), ws.numel(),
-                                                          chunk, cur_stream()))
+        fn = _lib.load_library().vitocm_forward_cls_attn_gray if (Cx == 1 and self.in_chans > 1) else _lib.load_library().vitocm_forward_cls_attn
+        check(fn(eng, ptr(x), B, H, W, ptr(pos), ptr(out), ptr(ws), ws.numel(), chunk, cur_stream()))
         return out
 
     @torch.no_grad()
