@@ -215,7 +215,7 @@ def main_mim(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     import vitocm_b200 as vob
-    from oracle import vit_oracle as VO   # synthetic-input recipe only
+    from vitocm_b200 import synthetic as SY   # the GPU arm never touches oracle/
     from functools import partial
     from types import SimpleNamespace as NS
     a = ARCHS["vit_small"]
@@ -230,9 +230,9 @@ def main_mim(args):
     # a few distinct synthetic batches in pinned host memory (rank-dependent seeds), cycled through
     n_host = 4
     rs = np.random.RandomState(1000 + rank)
-    base = VO.synthetic_tile(WINDOW, seed=500 + rank, batch=min(Bg, 8))
+    base = SY.synthetic_tile(WINDOW, seed=500 + rank, batch=min(Bg, 8))
     xs_host = [base[torch.randint(0, base.shape[0], (Bg,), generator=torch.Generator().manual_seed(i))].contiguous().pin_memory() for i in range(n_host)]
-    ms_host = [torch.from_numpy(np.stack([VO.mask_generator(rs, WINDOW, 16, PATCH, 0.5) for _ in range(Bg)])).pin_memory() for _ in range(n_host)]
+    ms_host = [SY.random_masks(rs, Bg, WINDOW, 16, PATCH, 0.5).pin_memory() for _ in range(n_host)]
     xs_dev = [x.to(dev) for x in xs_host]
     ms_dev = [m.to(dev) for m in ms_host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -382,7 +382,7 @@ def main():
         group = dist.group.WORLD
 
     import vitocm_b200 as vob
-    from oracle import vit_oracle as VO   # synthetic-input recipe only (shared with the tests)
+    from vitocm_b200 import synthetic as SY   # the GPU arm never touches oracle/
 
     a = ARCHS[args.arch]
     torch.manual_seed(0)
@@ -391,7 +391,7 @@ def main():
     n, size, extent = mosaic_geometry(world)
     T = n * n
     N = (WINDOW // PATCH) ** 2 + 1
-    mosaic_host = torch.from_numpy(VO.synthetic_mosaic_u8(size, seed=4321)).pin_memory()
+    mosaic_host = torch.from_numpy(SY.synthetic_mosaic_u8(size, seed=4321)).pin_memory()
     mosaic = mosaic_host.to(dev)
     seg = vob.MosaicSegmenter(model, window=WINDOW, stride=STRIDE, tile_batch=args.tile_batch, group=group)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -191,3 +191,14 @@ def test_lr_scheduler_and_param_groups_mirror():
         sched.step_update(t)
         want = TO.cosine_lr(t, 5e-4, 70, 5e-6, 14, 5e-7)
         assert all(abs(gp["lr"] - want) < 1e-12 for gp in opt.param_groups), t
+
+
+def test_package_synthetic_inputs_equal_the_oracle_recipe():
+    """bench.py's GPU arm draws its inputs from vitocm_b200.synthetic (it may not touch oracle/); the recipe must not drift."""
+    from vitocm_b200 import synthetic as SY
+    assert torch.equal(SY.synthetic_tile(64, seed=5, batch=2), VO.synthetic_tile(64, seed=5, batch=2))
+    assert np.array_equal(SY.synthetic_mosaic_u8(160, seed=6), VO.synthetic_mosaic_u8(160, seed=6))
+    a = SY.random_masks(np.random.RandomState(3), 4, 32, 16, 8, 0.5).numpy()
+    rs = np.random.RandomState(3)
+    b = np.stack([VO.mask_generator(rs, 32, 16, 8, 0.5) for _ in range(4)])
+    assert np.array_equal(a, b)

@@ -6,7 +6,7 @@ from types import SimpleNamespace as NS
 import numpy as np
 import torch
 import vitocm_b200 as vob
-from oracle import vit_oracle as VO
+from vitocm_b200 import synthetic as SY
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
@@ -16,10 +16,10 @@ enc = vob.VisionTransformerForSimMIM(patch_size=8, embed_dim=384, depth=12, num_
 mim = vob.MIM(encoder=enc, encoder_stride=8).cuda().train()
 cfg = NS(TRAIN=NS(BASE_LR=5e-4, WEIGHT_DECAY=0.05, CLIP_GRAD=5.0, OPTIMIZER=NS(NAME="adamw", EPS=1e-8, BETAS=(0.9, 0.999))))
 opt = vob.optimizer.build_pretrain_optimizer(cfg, mim, None)
-x = VO.synthetic_tile(224, seed=1, batch=min(B, 8))
+x = SY.synthetic_tile(224, seed=1, batch=min(B, 8))
 x = x[torch.arange(B) % x.shape[0]].contiguous().cuda()
 rs = np.random.RandomState(0)
-m = torch.from_numpy(np.stack([VO.mask_generator(rs, 224, 16, 8, 0.5) for _ in range(B)])).cuda()
+m = SY.random_masks(rs, B, 224, 16, 8, 0.5).cuda()
 for _ in range(steps):
     opt.zero_grad()
     loss, _, _ = mim(x, m)

@@ -16,7 +16,7 @@ All compute is in ``libvitocm.so`` (csrc/, C ABI in include/vitocm.h); build it 
 """
 from . import _lib  # noqa: F401
 from . import vision_transformer as vits  # noqa: F401
-from . import utils, sw_processing, model, optimizer, lr_scheduler  # noqa: F401
+from . import utils, sw_processing, model, optimizer, lr_scheduler, synthetic  # noqa: F401
 from .vision_transformer import VisionTransformer, vit_tiny, vit_small, vit_base, LazyAttention, LazyTensor  # noqa: F401
 from .utils import compute_attention, attention_masks, head_mean_maps  # noqa: F401
 from .sw_processing import MosaicSegmenter, sliding_window, grid_size, shard_range  # noqa: F401
