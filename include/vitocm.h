@@ -246,9 +246,10 @@ int vitocm_grad_sumsq(const float* g, int64_t n, double* out, void* stream);
 int vitocm_adamw_step(float* p, float* g, float* m, float* v, const uint8_t* decay, int64_t n, float lr, float beta1, float beta2,
                       float eps, float weight_decay, int step, float max_norm, float grad_scale, const double* sumsq, void* stream);
 
-/* kernel-level: dW[R][C] (fp32) += G[M][R]^T . A[M][C], bf16 row-major activations (the weight gradient of nn.Linear) */
+/* kernel-level: dW[R][C] (fp32) += G[M][R]^T . A[M][C], bf16 row-major activations (the weight gradient of nn.Linear);
+ * db[R] (fp32, or NULL) += column sums of G (its bias gradient, computed by the same tensor-core pass) */
 int vitocm_wgrad(vitocm_engine* e, const void* G, int64_t ldg, const void* A, int64_t lda, int M, int R, int C, float* dW,
-                 void* stream);
+                 float* db, void* stream);
 /* vitocm_attention that also returns lse2 [B][heads][Npad] = log2 sum_k exp(scale q.k); Npad = n_tokens rounded up to a
  * multiple of 128, pad rows hold +inf */
 int vitocm_attention_fwd_lse(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo,

@@ -37,11 +37,16 @@ def test_wgrad(engine, M, R, C):
     A = _rand((M, C), 2).to(torch.bfloat16)
     dW0 = _rand((R, C), 3)
     dW = dW0.clone()
-    check(lib.vitocm_wgrad(engine, ptr(G), G.stride(0), ptr(A), A.stride(0), M, R, C, ptr(dW), cur_stream()))
+    db0 = _rand((R,), 6)
+    db = db0.clone()
+    check(lib.vitocm_wgrad(engine, ptr(G), G.stride(0), ptr(A), A.stride(0), M, R, C, ptr(dW), ptr(db), cur_stream()))
     torch.cuda.synchronize()
     ref = dW0.double() + G.double().T @ A.double()
     err = (dW.double() - ref).abs().max().item()
     assert err <= 2e-5 * ref.abs().max().item() + 1e-4, (err, ref.abs().max().item())
+    # the bias gradient (column sums of G) from the all-ones MMA of the same pass
+    ref_b = db0.double() + G.double().sum(0)
+    assert (db.double() - ref_b).abs().max().item() <= 2e-5 * ref_b.abs().max().item() + 1e-4
 
 
 def test_wgrad_strided_operands(engine):
@@ -52,7 +57,7 @@ def test_wgrad_strided_operands(engine):
     Aw = _rand((M, 2 * C), 5).to(torch.bfloat16)
     G, A = Gw[:, R:2 * R], Aw[:, C:]
     dW = torch.zeros(R, C, device="cuda")
-    check(lib.vitocm_wgrad(engine, G.data_ptr(), Gw.stride(0), A.data_ptr(), Aw.stride(0), M, R, C, ptr(dW), cur_stream()))
+    check(lib.vitocm_wgrad(engine, G.data_ptr(), Gw.stride(0), A.data_ptr(), Aw.stride(0), M, R, C, ptr(dW), None, cur_stream()))
     torch.cuda.synchronize()
     ref = G.double().T @ A.double()
     assert (dW.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-4

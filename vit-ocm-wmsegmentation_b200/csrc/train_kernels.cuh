@@ -70,6 +70,7 @@ gelu_bwd_kernel(const uint4* __restrict__ pre, long long pre_ld8, uint4* __restr
       }
     }
   }
+  if (db == nullptr) return;    // the bias gradient comes from the weight-gradient GEMM instead (uniform branch)
   float* mine = gb_red + (static_cast<long long>(ty) * ncols8 + c) * 8;
 #pragma unroll
   for (int k = 0; k < 8; ++k) mine[k] = acc[k];

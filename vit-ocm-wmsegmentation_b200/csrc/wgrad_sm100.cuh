@@ -10,6 +10,9 @@
 // warp 1 = MMA issuer (one elected thread) + TMEM allocator, warps 2..5 = epilogue.  The accumulator
 // (128 x NB*BN fp32) lives in TMEM for the whole token range; the epilogue adds it into the fp32 gradient with
 // TMA reduce-add (cp.reduce.async.bulk.tensor .add, performed by the L2), which is also how token splits combine.
+// Bias gradient for free: the column sums of G are G^T . 1, so the CTAs of the first column tile issue one extra N = 16 MMA per
+// k-step against a constant all-ones B tile (8 KB of bf16 1.0: any swizzle of ones is ones) into 16 spare TMEM columns; the
+// epilogue adds column 0 into db with 128 atomics per CTA.  No separate pass over G.
 #pragma once
 #include "ptx.cuh"
 
@@ -21,6 +24,7 @@ struct WgradArgs {
   int tiles_c;    // C tiles of NB*BN columns
   int splits;     // token splits
   int kblocks;    // ceil(M / 64)
+  float* colsum;  // [R] or nullptr: colsum[r] += sum_m G[m][r] -- the bias gradient of the same Linear, from the tensor core
 };
 
 constexpr int WG_BM = 128;      // rows of dW per tile (features of G)
@@ -35,12 +39,14 @@ struct WgradCfg {
   static constexpr int B_BYTES = (WIDTH / 64) * WG_ATOM_BYTES;      // WIDTH features of A
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_BYTES = 4 * 4096;                        // per epilogue warp one 32 x 32 fp32 box
-  static constexpr int FIXED = STG_BYTES + 1024 + 256;
+  static constexpr int ONES_BYTES = WG_ATOM_BYTES;                  // [64 tokens][64 x bf16 1.0]
+  static constexpr int FIXED = STG_BYTES + ONES_BYTES + 1024 + 256;
   static constexpr int STAGES_FIT = (227 * 1024 - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
-  static constexpr int TMEM_COLS = WIDTH <= 32 ? 32 : WIDTH <= 64 ? 64 : WIDTH <= 128 ? 128 : WIDTH <= 256 ? 256 : 512;
-  static_assert(BN % 64 == 0 && BN <= 256 && WIDTH <= 512, "tile width");
+  static constexpr int ACC_COLS = WIDTH + 16;                       // + the bias-gradient accumulator
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
+  static_assert(BN % 64 == 0 && BN <= 256 && ACC_COLS <= 512, "tile width");
   static_assert(STAGES >= 3, "not enough shared memory for a 3-stage pipeline");
 };
 
@@ -53,7 +59,8 @@ wgrad_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_g, const __gr
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_stg = smem_base + STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bars = smem_stg + Cfg::STG_BYTES;
+  const uint32_t smem_ones = smem_stg + Cfg::STG_BYTES;
+  const uint32_t bars = smem_ones + Cfg::ONES_BYTES;
   const uint32_t full_bar = bars;              // [STAGES]
   const uint32_t empty_bar = bars + 64;        // [STAGES]
   const uint32_t acc_bar = bars + 128;         // accumulator complete
@@ -70,6 +77,7 @@ wgrad_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_g, const __gr
   const int kb0 = static_cast<int>(static_cast<long long>(split) * args.kblocks / args.splits);
   const int kb1 = static_cast<int>(static_cast<long long>(split + 1) * args.kblocks / args.splits);
   const int nk = kb1 - kb0;
+  const bool do_colsum = args.colsum != nullptr && tc == 0;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_g);
@@ -85,6 +93,11 @@ wgrad_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_g, const __gr
   if (warp == 1) {
     ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
     ptx::tmem_relinquish();
+  }
+  if (do_colsum && warp >= 2) {   // the all-ones B tile of the bias-gradient MMA
+    for (int i = (warp - 2) * 32 + lane; i < Cfg::ONES_BYTES / 16; i += 128)
+      ptx::sts_v4(smem_ones + i * 16, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    ptx::fence_proxy_async_smem();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -113,6 +126,8 @@ wgrad_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_g, const __gr
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc(WG_BM, BN, /*A MN-major*/ true, /*B MN-major*/ true);
+      constexpr uint32_t idesc_ones = ptx::make_idesc(WG_BM, 16, true, true);
+      const uint64_t ones_desc = ptx::make_smem_desc_sw128(smem_ones, 1024, WG_ATOM_BYTES);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < nk; ++it) {
@@ -129,6 +144,9 @@ wgrad_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_g, const __gr
           for (int nb = 0; nb < NB; ++nb)
             ptx::umma_bf16_ss(tmem_base + nb * BN, ptx::desc_advance(adesc, k * 2048),
                               ptx::desc_advance(bdesc, nb * (BN / 64) * WG_ATOM_BYTES + k * 2048), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          if (do_colsum)
+            ptx::umma_bf16_ss(tmem_base + Cfg::WIDTH, ptx::desc_advance(adesc, k * 2048), ptx::desc_advance(ones_desc, k * 2048), idesc_ones,
+                              (it > 0 || k > 0) ? 1u : 0u);
         }
         ptx::umma_commit(empty_bar + 8 * stage);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -142,6 +160,12 @@ wgrad_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_g, const __gr
     ptx::mbar_wait(acc_bar, 0, 33);
     ptx::tc_fence_after();
     const int row = r0 + q * 32;
+    if (do_colsum) {   // column 0 of the ones-MMA accumulator = sum over this split's tokens of G[:, row + lane]
+      uint32_t cs;
+      ptx::tmem_ld_32x32b_x1(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(Cfg::WIDTH), cs);
+      ptx::tmem_ld_wait1(cs);
+      if (row + lane < args.R) atomicAdd(args.colsum + row + lane, __uint_as_float(cs));
+    }
     if (row < args.R) {
 #pragma unroll 1
       for (int c = 0; c < Cfg::WIDTH; c += 32) {
