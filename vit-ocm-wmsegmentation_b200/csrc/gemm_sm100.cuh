@@ -31,6 +31,7 @@ enum GemmEpilogue : int {
   EPI_BIAS_F32 = 3,        // out_f32 = acc + bias                 (generic / decoder)
   EPI_PATCH_F32 = 4,       // X[b, 1+i, :] = mix(acc + bias, mask_token) + pos[1+i]   (patch embedding)
   EPI_RESID_LN = 5,        // resid_f32 += acc + bias;  xn_bf16 = LayerNorm(resid_f32) * gamma + beta   (proj / fc2 + next LN)
+  EPI_DGELU_BF16 = 6,      // out_bf16 = acc * gelu'(pre)          (training: input gradient of fc2 through the GELU, vit.py:59)
 };
 
 struct GemmArgs {
@@ -60,6 +61,9 @@ struct GemmArgs {
   const float* mask;        // [B][n_patches] in {0,1} or nullptr (SimMIM mask-token mixing, SSS/model.py:31-33)
   const float* mask_token;  // [N]
   float* out_f32;           // X [B][1 + n_patches][N] token stream
+  // EPI_DGELU_BF16 only: the GELU's input saved by the forward fc1 epilogue, bf16 [M][ld_pre]
+  const __nv_bfloat16* pre;
+  long long ld_pre;
 };
 
 constexpr int GEMM_BM = 128;
@@ -67,7 +71,7 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_EPI_WARP0 = 4;
 // epilogue warps: 8 (two column halves per TMEM lane quadrant), or 12 with BN = 192 (three 64-column groups): the
 // GELU epilogue is issue / latency bound, a third warp per scheduler hides its MUFU + FMA chains
-__host__ __device__ constexpr int gemm_epi_warps(int BN, int EPI) { return (EPI == 1 && BN == 192) ? 12 : 8; }
+__host__ __device__ constexpr int gemm_epi_warps(int BN, int EPI) { return ((EPI == 1 || EPI == 6) && BN == 192) ? 12 : 8; }
 // patch embedding: 6 extra warps after the epilogue warps join warps 2-3 as A producers (8 producer warps)
 constexpr int GEMM_PATCH_PRODUCER_WARPS = 8;
 __host__ __device__ constexpr int gemm_threads(int BN, int EPI) {
@@ -95,7 +99,7 @@ constexpr int GEMM_RES_MAX_KBLOCKS = 6;     // B_RES: K <= 384
 // tensor clocks (96 -> 64 B/clk/SM at BN = 256): the plain kernel is L2->SM bandwidth bound.
 template <int BN, int EPI, bool B_RES = false, int CS = 1, bool PAIR = false>
 struct GemmCfg {
-  static constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16);
+  static constexpr bool OUT_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_DGELU_BF16);
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;       // 16 KB
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + (B_RES ? 0 : B_BYTES);
@@ -153,6 +157,35 @@ __device__ __forceinline__ void gelu_sigmoid_x2(float& x0, float& x1) {
   ptx::unpack_f32x2(den, d0, d1);
   const uint64_t r = ptx::mul_f32x2(x2, ptx::pack_f32x2(ptx::rcp_approx(d0), ptx::rcp_approx(d1)));
   ptx::unpack_f32x2(r, x0, x1);
+}
+
+// Derivative of the same function, two values at once on the packed-f32x2 pipe:  gelu(x) = x * s(x),  s = sigmoid(t),
+// t = x (a + b u + c u^2),  u = min(x^2, 100):
+//     gelu'(x) = s + x s (1 - s) t'(x),   t' = a + 3 b u + 5 c u^2
+// (beyond |x| = 10 the clamped u makes t' inexact, but s (1 - s) is 0 there in fp32).  Max |error| against the exact erf-form
+// derivative 1.1e-4.  v <- v * gelu'(x): ~12 packed FMA-pipe instructions + 4 MUFU per pair -- scalar code made the
+// input-gradient epilogue issue bound.
+__device__ __forceinline__ void gelu_grad_mul_x2(float& v0, float& v1, float x0, float x1) {
+  // (a, b, c) = -(coefficients of gelu_sigmoid_x2) / log2(e)
+  constexpr float A = 1.595015768531f, B = 0.074011292043f, C = -0.000703033580f;
+  const uint64_t x2 = ptx::pack_f32x2(x0, x1);
+  const uint64_t sq = ptx::mul_f32x2(x2, x2);
+  float u0, u1;
+  ptx::unpack_f32x2(sq, u0, u1);
+  const uint64_t u = ptx::pack_f32x2(fminf(u0, 100.f), fminf(u1, 100.f));
+  const uint64_t poly = ptx::fma_f32x2(ptx::fma_f32x2(ptx::dup_f32x2(C), u, ptx::dup_f32x2(B)), u, ptx::dup_f32x2(A));
+  const uint64_t arg = ptx::mul_f32x2(ptx::mul_f32x2(x2, poly), ptx::dup_f32x2(-1.4426950408889634f));
+  float a0, a1;
+  ptx::unpack_f32x2(arg, a0, a1);
+  const uint64_t den = ptx::add_f32x2(ptx::pack_f32x2(ptx::ex2_approx(a0), ptx::ex2_approx(a1)), ptx::dup_f32x2(1.0f));
+  float d0, d1;
+  ptx::unpack_f32x2(den, d0, d1);
+  const uint64_t sg = ptx::pack_f32x2(ptx::rcp_approx(d0), ptx::rcp_approx(d1));
+  const uint64_t dt = ptx::fma_f32x2(ptx::fma_f32x2(ptx::dup_f32x2(5.0f * C), u, ptx::dup_f32x2(3.0f * B)), u, ptx::dup_f32x2(A));
+  const uint64_t om = ptx::fma_f32x2(sg, ptx::dup_f32x2(-1.0f), ptx::dup_f32x2(1.0f));
+  const uint64_t g = ptx::fma_f32x2(ptx::mul_f32x2(ptx::mul_f32x2(x2, sg), om), dt, sg);
+  const uint64_t r = ptx::mul_f32x2(ptx::pack_f32x2(v0, v1), g);
+  ptx::unpack_f32x2(r, v0, v1);
 }
 
 template <int BN, int EPI, bool A_PATCH, bool B_RES = false, int CS = 1, bool PAIR = false>
@@ -565,6 +598,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
           for (int j = 0; j < 32; ++j) bv[j] = 0.f;
         }
+        uint4 pq[4];   // EPI_DGELU_BF16: this lane's 32 saved GELU inputs, requested before the TMEM wait
+        if (EPI == EPI_DGELU_BF16) {
+          const int m = row_base + lane;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) pq[g] = make_uint4(0u, 0u, 0u, 0u);
+          if (m < args.M) {
+            const uint4* pp = reinterpret_cast<const uint4*>(args.pre + static_cast<long long>(m) * args.ld_pre + col);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) pq[g] = __ldg(pp + g);
+          }
+        }
         ptx::tmem_ld_wait(r);
         if (args.debug == 1) {
           uint32_t acc = 0;
@@ -576,6 +620,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bv[j];
+        if (EPI == EPI_DGELU_BF16) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t wds[4] = {pq[g].x, pq[g].y, pq[g].z, pq[g].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              gelu_grad_mul_x2(v[8 * g + 2 * k], v[8 * g + 2 * k + 1], __uint_as_float(wds[k] << 16), __uint_as_float(wds[k] & 0xffff0000u));
+          }
+        }
         uint32_t pre[16];   // training: the GELU input, kept for the backward (vit.py:59)
         if (EPI == EPI_BIAS_GELU_BF16 && args.split_out == 2) {
 #pragma unroll

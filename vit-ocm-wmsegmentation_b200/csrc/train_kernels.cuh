@@ -1,6 +1,4 @@
 // Bandwidth-bound kernels of the MIM training step (SSS/mim.py:153-182: loss.backward(), clip_grad_norm_, AdamW):
-//   gelu_bwd_kernel                      derivative of vit.py:59 (nn.GELU; the forward is the fc1 GEMM epilogue) + fc1 bias gradient
-//   colsum_bf16_kernel                   bias gradients: d b = sum_m dY[m, :]
 //   ln_bwd_kernel                        nn.LayerNorm backward (vit.py:107,111,215) fused with the residual-gradient
 //                                        accumulation of Block.forward (vit.py:110-111) and the bf16 copy the next GEMMs read
 //   attn_delta_kernel                    Delta[q] = sum_d dO[q, d] O[q, d] (flash-attention backward preprocess)
@@ -11,6 +9,7 @@
 //   repack_weights_kernel                fp32 masters -> bf16 [R][C] and [C][R] (forward / input-gradient B operands), one launch
 // All vectorised and coalesced; statistics and accumulations in fp32 (fp64 for the global gradient norm).
 #pragma once
+#include "gemm_sm100.cuh"
 #include "ptx.cuh"
 #include "vit_kernels.cuh"
 
@@ -18,111 +17,6 @@ namespace vitocm {
 
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
-
-// ------------------------------------------------------------------------------------------------ GELU
-// Derivative of the GELU the forward epilogue evaluates (gemm_sm100.cuh, gelu_sigmoid_x2):  gelu(x) = x * s(x),
-// s = sigmoid(t), t = x (a + b u + c u^2), u = min(x^2, 100)  (fitted to the exact erf form, max |error| 2.5e-5):
-//     gelu'(x) = s + x s (1 - s) t'(x),   t' = a + 3 b u + 5 c u^2   (a + b u + c u^2 where u is clamped)
-// max |error| against the exact erf-form derivative 1.1e-4; one ex2 + one rcp per element, so the kernel stays
-// bandwidth bound (erff + expf made it issue bound: 45 instructions per element).
-__device__ __forceinline__ float gelu_grad(float x) {
-  // (a, b, c) = -(coefficients of gelu_sigmoid_x2) / log2(e)
-  constexpr float A = 1.595015768531f, B = 0.074011292043f, C = -0.000703033580f;
-  const float xx = x * x;
-  const float u = fminf(xx, 100.f);
-  const float poly = fmaf(fmaf(C, u, B), u, A);
-  const float s = ptx::rcp_approx(1.0f + ptx::ex2_approx(-1.4426950408889634f * x * poly));
-  const float dt = xx <= 100.f ? fmaf(fmaf(5.0f * C, u, 3.0f * B), u, A) : poly;
-  return fmaf(x * s * (1.0f - s), dt, s);
-}
-
-// dh <- dh * gelu'(pre) (in place) and, fused, the fc1 bias gradient db[c] += sum_rows dh[row][c].
-// blockDim = (ncols / 8 column groups of 16 bytes, row lanes); rows grid-strided, four rows in flight per thread; the lanes'
-// column sums meet in shared memory so that a block issues one atomicAdd per column (global atomics are ~60 ps each: with
-// one per thread they cost more than the pass itself at small batch).  pre has a row pitch of pre_ld8 16-byte groups.
-__global__ void __launch_bounds__(1024)
-gelu_bwd_kernel(const uint4* __restrict__ pre, long long pre_ld8, uint4* __restrict__ dh, int M, int ncols8, float* __restrict__ db) {
-  extern __shared__ float gb_red[];   // [lanes][ncols]
-  const int c = threadIdx.x, ty = threadIdx.y, lanes = blockDim.y;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int row0 = (blockIdx.x * lanes + ty) * 4; row0 < M; row0 += gridDim.x * lanes * 4) {
-    uint4 v[4], g[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (row0 + u < M) {
-        v[u] = pre[static_cast<long long>(row0 + u) * pre_ld8 + c];
-        g[u] = dh[static_cast<long long>(row0 + u) * ncols8 + c];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (row0 + u < M) {
-        const uint32_t in[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, gi[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
-        uint32_t out[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float d0 = bf16lo(gi[k]) * gelu_grad(bf16lo(in[k])), d1 = bf16hi(gi[k]) * gelu_grad(bf16hi(in[k]));
-          acc[2 * k] += d0;
-          acc[2 * k + 1] += d1;
-          out[k] = ptx::pack_bf16x2(d0, d1);
-        }
-        dh[static_cast<long long>(row0 + u) * ncols8 + c] = make_uint4(out[0], out[1], out[2], out[3]);
-      }
-    }
-  }
-  if (db == nullptr) return;    // the bias gradient comes from the weight-gradient GEMM instead (uniform branch)
-  float* mine = gb_red + (static_cast<long long>(ty) * ncols8 + c) * 8;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) mine[k] = acc[k];
-  __syncthreads();
-  if (ty == 0) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float t = 0.f;
-      for (int l = 0; l < lanes; ++l) t += gb_red[(static_cast<long long>(l) * ncols8 + c) * 8 + k];
-      atomicAdd(db + 8 * c + k, t);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ bias gradient
-// out[c] += sum_m G[m][c].  blockDim = (ncols / 8 column groups of 16 bytes, ROWS row lanes); rows grid-strided,
-// four rows in flight per thread; the lanes' sums meet in shared memory: one atomicAdd per column and block.
-__global__ void __launch_bounds__(1024)
-colsum_bf16_kernel(const __nv_bfloat16* __restrict__ G, long long ld, int M, int ncols, float* __restrict__ out) {
-  const int c = threadIdx.x;                 // column group
-  const int lanes = blockDim.y;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int row0 = (blockIdx.x * lanes + threadIdx.y) * 4; row0 < M; row0 += gridDim.x * lanes * 4) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      v[u] = row0 + u < M ? *reinterpret_cast<const uint4*>(G + static_cast<long long>(row0 + u) * ld + 8 * c) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t in[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        acc[2 * k] += bf16lo(in[k]);
-        acc[2 * k + 1] += bf16hi(in[k]);
-      }
-    }
-  }
-  extern __shared__ float cs_red[];   // [lanes][ncols]: one atomicAdd per column and block
-  const int groups = blockDim.x;
-  float* mine = cs_red + (static_cast<long long>(threadIdx.y) * groups + c) * 8;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) mine[k] = acc[k];
-  __syncthreads();
-  if (threadIdx.y == 0) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float t = 0.f;
-      for (int l = 0; l < lanes; ++l) t += cs_red[(static_cast<long long>(l) * groups + c) * 8 + k];
-      atomicAdd(out + 8 * c + k, t);
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
 // One warp per row (grid-stride).  y = (x - mean) * rstd * gamma + beta,  dy = dL/dy (bf16):

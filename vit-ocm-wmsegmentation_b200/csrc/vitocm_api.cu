@@ -292,6 +292,7 @@ int launch_gemm_pair_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
     case EPI_BIAS_GELU_BF16: return launch_gemm_pair<BN, EPI_BIAS_GELU_BF16>(ta, tb, tc, a, num_sms, st);
     case EPI_BIAS_RESID_F32: return launch_gemm_pair<BN, EPI_BIAS_RESID_F32>(ta, tb, tc, a, num_sms, st);
     case EPI_BIAS_F32: return launch_gemm_pair<BN, EPI_BIAS_F32>(ta, tb, tc, a, num_sms, st);
+    case EPI_DGELU_BF16: return launch_gemm_pair<BN, EPI_DGELU_BF16>(ta, tb, tc, a, num_sms, st);
   }
   return fail(VITOCM_ERR_INVALID, "unknown GEMM epilogue %d", epi);
 }
@@ -314,6 +315,7 @@ int launch_gemm_bn(int epi, bool res, const CUtensorMap& ta, const CUtensorMap& 
     case EPI_BIAS_GELU_BF16: return launch_gemm_inst<BN, EPI_BIAS_GELU_BF16, false>(ta, tb, tc, a, num_sms, st);
     case EPI_BIAS_RESID_F32: return launch_gemm_inst<BN, EPI_BIAS_RESID_F32, false>(ta, tb, tc, a, num_sms, st);
     case EPI_BIAS_F32: return launch_gemm_inst<BN, EPI_BIAS_F32, false>(ta, tb, tc, a, num_sms, st);
+    case EPI_DGELU_BF16: return launch_gemm_inst<BN, EPI_DGELU_BF16, false>(ta, tb, tc, a, num_sms, st);
   }
   return fail(VITOCM_ERR_INVALID, "unknown GEMM epilogue %d", epi);
 }
@@ -339,7 +341,9 @@ int pick_bn(int M, int N, int num_sms, int max_bn) {
 // A [M][lda] (split: hi at col 0, lo at col K), B [N][ldb] likewise.
 int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
              int split_in, int epi, const float* bias, void* out, long long ldo, int split_out, int lo_off, cudaStream_t st,
-             int pcls = PC_OTHER) {
+             int pcls = PC_OTHER, const void* pre = nullptr, long long ld_pre = 0) {
+  if (epi == EPI_DGELU_BF16 && (pre == nullptr || split_in || ld_pre % 8 != 0 || (reinterpret_cast<uintptr_t>(pre) & 15) != 0))
+    return fail(VITOCM_ERR_INVALID, "GEMM dGELU epilogue needs a 16-byte aligned bf16 pre-activation and single-bf16 operands");
   if (M <= 0) return 0;
   ProfScope prof(pcls, st);
   if (K % GEMM_BK != 0) return fail(VITOCM_ERR_INVALID, "GEMM K=%d must be a multiple of %d", K, GEMM_BK);
@@ -353,7 +357,7 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
   if (pair_mode != 0 && pair_pays && !split_in && split_out != 1 && M >= 4 * GEMM_BM && (N % 256 == 0 || N % 192 == 0 || N % 128 == 0)) {
     static const int gelu_bn = [] { const char* v = getenv("VITOCM_GELU_BN"); return v ? atoi(v) : 192; }();   // measured: 835 vs 794 TFLOP/s
     int pbn = N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 128);
-    if (epi == EPI_BIAS_GELU_BF16 && gelu_bn == 192 && N % 192 == 0) pbn = 192;   // 12 epilogue warps instead of 8
+    if ((epi == EPI_BIAS_GELU_BF16 || epi == EPI_DGELU_BF16) && gelu_bn == 192 && N % 192 == 0) pbn = 192;   // 12 epilogue warps instead of 8
     const bool of32 = (epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_F32);
     CUtensorMap pa, pb, pc;
     TRY(make_tmap_bf16(&pa, A, M, K, lda, GEMM_BM));
@@ -362,6 +366,7 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
     GemmArgs pg{};
     pg.M = M; pg.N = N; pg.kblocks = K / GEMM_BK; pg.nterms = 1; pg.lo_k = K; pg.bias = bias; pg.out_f32 = reinterpret_cast<float*>(out);
     pg.split_out = split_out; pg.lo_off = lo_off;
+    pg.pre = reinterpret_cast<const __nv_bfloat16*>(pre); pg.ld_pre = ld_pre;
     { static const int dbgp = [] { const char* v = getenv("VITOCM_GEMM_DEBUG"); return v ? atoi(v) : 0; }(); pg.debug = dbgp; }
     if (pbn == 256) return launch_gemm_pair_bn<256>(epi, pa, pb, pc, pg, e->num_sms, st);
     if (pbn == 192) return launch_gemm_pair_bn<192>(epi, pa, pb, pc, pg, e->num_sms, st);
@@ -369,7 +374,7 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
   }
   static const bool allow_res = [] { const char* v = getenv("VITOCM_GEMM_RESIDENT"); return v == nullptr || atoi(v) != 0; }();
   // weight panel resident in smem: single-bf16 operands, K <= 384, tile width 192 or 128
-  bool res = allow_res && !split_in && !split_out && K / GEMM_BK <= GEMM_RES_MAX_KBLOCKS && (N % 128 == 0 || N % 192 == 0);
+  bool res = allow_res && !split_in && !split_out && epi != EPI_DGELU_BF16 && K / GEMM_BK <= GEMM_RES_MAX_KBLOCKS && (N % 128 == 0 || N % 192 == 0);
   const int bn = pick_bn(M, N, e->num_sms, res ? 192 : 256);
   if (res && bn < 128) res = false;
   const long long kext = static_cast<long long>(K) * (split_in ? 2 : 1);
@@ -384,6 +389,7 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
   a.bias = bias; a.split_out = split_out; a.lo_off = lo_off;
   static const int dbg = [] { const char* v = getenv("VITOCM_GEMM_DEBUG"); return v ? atoi(v) : 0; }();
   a.debug = dbg; a.out_f32 = reinterpret_cast<float*>(out);
+  a.pre = reinterpret_cast<const __nv_bfloat16*>(pre); a.ld_pre = ld_pre;
   switch (bn) {
     case 256: return launch_gemm_bn<256>(epi, res, ta, tb, tc, a, e->num_sms, st);
     case 192: return launch_gemm_bn<192>(epi, res, ta, tb, tc, a, e->num_sms, st);
