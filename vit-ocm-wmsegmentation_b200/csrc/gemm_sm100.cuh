@@ -108,7 +108,8 @@ struct GemmCfg {
   // path).  B_RES keeps one box per warp (single buffered) to leave room for the panel.
   static constexpr int STG_BOX_BYTES = OUT_BF16 ? 2048 : 4096;
   // LN: per warp two fp32 boxes (the residual rows come in and go out through them) + one bf16 box (normalised rows)
-  static constexpr int STG_WARP_BYTES = EPI == EPI_RESID_LN ? 2 * 4096 + 2048 : (B_RES ? 1 : 2) * STG_BOX_BYTES;
+  // EPI_DGELU_BF16: a third bf16 box per warp receives the saved pre-activation tile by TMA
+  static constexpr int STG_WARP_BYTES = EPI == EPI_RESID_LN ? 2 * 4096 + 2048 : (B_RES ? 1 : (EPI == EPI_DGELU_BF16 ? 3 : 2)) * STG_BOX_BYTES;
   static constexpr int EPI_WARPS = gemm_epi_warps(BN, EPI);
   static constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
   // EPI_RESID_LN: [2 slots][LN_SRC partial sources][128 rows] x (mean, M2)
@@ -215,8 +216,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const uint32_t bfull_bar = bars + 16 * GEMM_MAX_STAGES + 32;      // B_RES: panel loaded
   const uint32_t bempty_bar = bars + 16 * GEMM_MAX_STAGES + 40;     // B_RES: panel no longer read
   const uint32_t stat_bar = bars + 16 * GEMM_MAX_STAGES + 48;       // [2]  LN: partial statistics of a row tile arrived
-  const uint32_t xin_bar = bars + 16 * GEMM_MAX_STAGES + 64;        // [8]  LN: per epilogue warp, residual boxes landed
-  const uint32_t tmem_ptr_smem = bars + 16 * GEMM_MAX_STAGES + 128;
+  const uint32_t xin_bar = bars + 16 * GEMM_MAX_STAGES + 64;        // [12] per epilogue warp: residual boxes (LN) / pre-activation box (dGELU) landed
+  const uint32_t tmem_ptr_smem = bars + 16 * GEMM_MAX_STAGES + 160;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -241,7 +242,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (!A_PATCH) ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
     if (EPI != EPI_PATCH_F32) ptx::prefetch_tmap(&tmap_c);
-    if (LN) ptx::prefetch_tmap(&tmap_d);
+    if (LN || EPI == EPI_DGELU_BF16) ptx::prefetch_tmap(&tmap_d);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -256,7 +257,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     ptx::mbar_init(bempty_bar, 1);
     ptx::mbar_init(stat_bar, 1);        // LN: one expect_tx arrive per row tile; the partials arrive as st.async complete_tx bytes
     ptx::mbar_init(stat_bar + 8, 1);
-    for (int w = 0; w < 8; ++w) ptx::mbar_init(xin_bar + 8 * w, 1);
+    for (int w = 0; w < 12; ++w) ptx::mbar_init(xin_bar + 8 * w, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -435,6 +436,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int as = 0;
     uint32_t aphase = 0;
     int ln_tiles = 0;
+    // EPI_DGELU_BF16: per-warp box for the saved pre-activation tile; the first request goes out before any accumulator is ready
+    const uint32_t pre_box = stg_warp + 2 * Cfg::STG_BOX_BYTES;
+    uint32_t pre_phase = 0;
+    if (EPI == EPI_DGELU_BF16 && lane == 0 && tile_begin < tile_end) {
+      ptx::mbar_arrive_expect_tx(xin_bar + 8 * ew, 2048);
+      ptx::tma_load_2d(pre_box, &tmap_d, xin_bar + 8 * ew, tile_n(tile_begin) * BN + half * COLS_PER_WARP, tile_m(tile_begin) * TILE_M + pair_row + q * 32);
+    }
     for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
       const int m0 = tile_m(tile) * TILE_M + pair_row;
       const int n0 = tile_n(tile) * BN;
@@ -598,18 +606,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
           for (int j = 0; j < 32; ++j) bv[j] = 0.f;
         }
-        uint4 pq[4];   // EPI_DGELU_BF16: this lane's 32 saved GELU inputs, requested before the TMEM wait
+        ptx::tmem_ld_wait(r);
+        uint4 pq[4];   // EPI_DGELU_BF16: this lane's 32 saved GELU inputs out of the TMA-staged box (32 rows x 64 B, SWIZZLE_64B)
         if (EPI == EPI_DGELU_BF16) {
-          const int m = row_base + lane;
+          ptx::mbar_wait(xin_bar + 8 * ew, pre_phase, 9);
+          pre_phase ^= 1u;
+          const uint32_t prow = pre_box + lane * 64;
+          const int psw = (lane >> 1) & 3;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) pq[g] = make_uint4(0u, 0u, 0u, 0u);
-          if (m < args.M) {
-            const uint4* pp = reinterpret_cast<const uint4*>(args.pre + static_cast<long long>(m) * args.ld_pre + col);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) pq[g] = __ldg(pp + g);
+          for (int g = 0; g < 4; ++g) {
+            const float4 f = ptx::lds_v4f(prow + ((g ^ psw) << 4));
+            pq[g] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
+          }
+          // the box is in registers: request the next one (this tile's next chunk, or the next tile's first) so that its
+          // latency hides under this chunk's math and store
+          __syncwarp();
+          int nt = tile, nc = c + 32;
+          if (nc >= COLS_PER_WARP) { nt = tile + tile_step; nc = 0; }
+          if (lane == 0 && nt < tile_end) {
+            ptx::mbar_arrive_expect_tx(xin_bar + 8 * ew, 2048);
+            ptx::tma_load_2d(pre_box, &tmap_d, xin_bar + 8 * ew, tile_n(nt) * BN + half * COLS_PER_WARP + nc, tile_m(nt) * TILE_M + pair_row + q * 32);
           }
         }
-        ptx::tmem_ld_wait(r);
         if (args.debug == 1) {
           uint32_t acc = 0;
 #pragma unroll

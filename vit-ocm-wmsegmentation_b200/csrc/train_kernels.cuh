@@ -49,13 +49,16 @@ ln_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
   for (int row = blockIdx.x * nwarps + warp; row < M; row += gridDim.x * nwarps) {
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * D);
     const uint2* dr = reinterpret_cast<const uint2*>(dy + static_cast<long long>(row) * ld_dy);
-    float4 v[CNT], g[CNT];
+    float4 v[CNT], g[CNT], acc_in[CNT];
+    float4* dxr = reinterpret_cast<float4*>(dX + static_cast<long long>(row) * D);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < CNT; ++i) {
       const int idx = lane + 32 * i;
       if (NV > 0 || idx < nvec) {
         v[i] = xr[idx];
+        // the running residual gradient is requested together with x and dy: one exposed memory latency per row, not two
+        acc_in[i] = accumulate ? dxr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
         const uint2 d2 = dr[idx];
         g[i] = make_float4(bf16lo(d2.x), bf16hi(d2.x), bf16lo(d2.y), bf16hi(d2.y));
         s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -87,13 +90,12 @@ ln_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
     }
     c1 = warp_sum(c1) * inv_d;
     c2 = warp_sum(c2) * inv_d;
-    float4* dxr = reinterpret_cast<float4*>(dX + static_cast<long long>(row) * D);
     uint2* dbr = reinterpret_cast<uint2*>(dXb + static_cast<long long>(row) * D);
 #pragma unroll
     for (int i = 0; i < CNT; ++i) {
       const int idx = lane + 32 * i;
       if (NV > 0 || idx < nvec) {
-        float4 o = accumulate ? dxr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 o = acc_in[i];
         o.x += rstd * (g[i].x - c1 - v[i].x * c2);
         o.y += rstd * (g[i].y - c1 - v[i].y * c2);
         o.z += rstd * (g[i].z - c1 - v[i].z * c2);

@@ -190,7 +190,7 @@ namespace {
 // ---------------------------------------------------------------------------------- GEMM launch
 template <int BN, int EPI, bool A_PATCH>
 int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& a, int num_sms,
-                     cudaStream_t st) {
+                     cudaStream_t st, const CUtensorMap* td = nullptr) {
   using Cfg = GemmCfg<BN, EPI>;
   static bool attr_set = false;
   auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, A_PATCH, false>;
@@ -200,7 +200,7 @@ int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   }
   const int tiles = ((a.M + GEMM_BM - 1) / GEMM_BM) * (a.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, gemm_threads(BN, EPI), Cfg::SMEM_BYTES, st>>>(ta, tb, tc, tc, a);
+  kern<<<grid, gemm_threads(BN, EPI), Cfg::SMEM_BYTES, st>>>(ta, tb, tc, td ? *td : tc, a);
   LAUNCH_CHECK();
   return 0;
 }
@@ -257,7 +257,8 @@ int launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
 
 // cta_group::2 variant: clusters of two CTAs share 256 x BN tiles (see GemmCfg)
 template <int BN, int EPI>
-int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& a, int num_sms, cudaStream_t st) {
+int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& a, int num_sms, cudaStream_t st,
+                     const CUtensorMap* td = nullptr) {
   using Cfg = GemmCfg<BN, EPI, false, 1, true>;
   static int max_pairs = -1;
   auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, false, false, 1, true>;
@@ -279,27 +280,27 @@ int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   }
   const int tiles = ((a.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * (a.N / BN);
   cfg.gridDim = dim3(2 * (tiles < max_pairs ? tiles : max_pairs));
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tc, a));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, td ? *td : tc, a));
   LAUNCH_CHECK();
   return 0;
 }
 
 template <int BN>
 int launch_gemm_pair_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& a, int num_sms,
-                        cudaStream_t st) {
+                        cudaStream_t st, const CUtensorMap* td = nullptr) {
   switch (epi) {
     case EPI_BIAS_BF16: return launch_gemm_pair<BN, EPI_BIAS_BF16>(ta, tb, tc, a, num_sms, st);
     case EPI_BIAS_GELU_BF16: return launch_gemm_pair<BN, EPI_BIAS_GELU_BF16>(ta, tb, tc, a, num_sms, st);
     case EPI_BIAS_RESID_F32: return launch_gemm_pair<BN, EPI_BIAS_RESID_F32>(ta, tb, tc, a, num_sms, st);
     case EPI_BIAS_F32: return launch_gemm_pair<BN, EPI_BIAS_F32>(ta, tb, tc, a, num_sms, st);
-    case EPI_DGELU_BF16: return launch_gemm_pair<BN, EPI_DGELU_BF16>(ta, tb, tc, a, num_sms, st);
+    case EPI_DGELU_BF16: return launch_gemm_pair<BN, EPI_DGELU_BF16>(ta, tb, tc, a, num_sms, st, td);
   }
   return fail(VITOCM_ERR_INVALID, "unknown GEMM epilogue %d", epi);
 }
 
 template <int BN>
 int launch_gemm_bn(int epi, bool res, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& a,
-                   int num_sms, cudaStream_t st) {
+                   int num_sms, cudaStream_t st, const CUtensorMap* td = nullptr) {
   if constexpr (BN == 192 || BN == 128) {
     if (res) {
       switch (epi) {
@@ -315,7 +316,7 @@ int launch_gemm_bn(int epi, bool res, const CUtensorMap& ta, const CUtensorMap& 
     case EPI_BIAS_GELU_BF16: return launch_gemm_inst<BN, EPI_BIAS_GELU_BF16, false>(ta, tb, tc, a, num_sms, st);
     case EPI_BIAS_RESID_F32: return launch_gemm_inst<BN, EPI_BIAS_RESID_F32, false>(ta, tb, tc, a, num_sms, st);
     case EPI_BIAS_F32: return launch_gemm_inst<BN, EPI_BIAS_F32, false>(ta, tb, tc, a, num_sms, st);
-    case EPI_DGELU_BF16: return launch_gemm_inst<BN, EPI_DGELU_BF16, false>(ta, tb, tc, a, num_sms, st);
+    case EPI_DGELU_BF16: return launch_gemm_inst<BN, EPI_DGELU_BF16, false>(ta, tb, tc, a, num_sms, st, td);
   }
   return fail(VITOCM_ERR_INVALID, "unknown GEMM epilogue %d", epi);
 }
@@ -367,10 +368,16 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
     pg.M = M; pg.N = N; pg.kblocks = K / GEMM_BK; pg.nterms = 1; pg.lo_k = K; pg.bias = bias; pg.out_f32 = reinterpret_cast<float*>(out);
     pg.split_out = split_out; pg.lo_off = lo_off;
     pg.pre = reinterpret_cast<const __nv_bfloat16*>(pre); pg.ld_pre = ld_pre;
+    CUtensorMap pd;
+    const CUtensorMap* ppd = nullptr;
+    if (epi == EPI_DGELU_BF16) {   // the saved pre-activation, read by the epilogue as 32 x 32 bf16 boxes
+      TRY(make_tmap(&pd, pre, false, N, M, ld_pre, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+      ppd = &pd;
+    }
     { static const int dbgp = [] { const char* v = getenv("VITOCM_GEMM_DEBUG"); return v ? atoi(v) : 0; }(); pg.debug = dbgp; }
-    if (pbn == 256) return launch_gemm_pair_bn<256>(epi, pa, pb, pc, pg, e->num_sms, st);
-    if (pbn == 192) return launch_gemm_pair_bn<192>(epi, pa, pb, pc, pg, e->num_sms, st);
-    return launch_gemm_pair_bn<128>(epi, pa, pb, pc, pg, e->num_sms, st);
+    if (pbn == 256) return launch_gemm_pair_bn<256>(epi, pa, pb, pc, pg, e->num_sms, st, ppd);
+    if (pbn == 192) return launch_gemm_pair_bn<192>(epi, pa, pb, pc, pg, e->num_sms, st, ppd);
+    return launch_gemm_pair_bn<128>(epi, pa, pb, pc, pg, e->num_sms, st, ppd);
   }
   static const bool allow_res = [] { const char* v = getenv("VITOCM_GEMM_RESIDENT"); return v == nullptr || atoi(v) != 0; }();
   // weight panel resident in smem: single-bf16 operands, K <= 384, tile width 192 or 128
@@ -390,11 +397,17 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
   static const int dbg = [] { const char* v = getenv("VITOCM_GEMM_DEBUG"); return v ? atoi(v) : 0; }();
   a.debug = dbg; a.out_f32 = reinterpret_cast<float*>(out);
   a.pre = reinterpret_cast<const __nv_bfloat16*>(pre); a.ld_pre = ld_pre;
+  CUtensorMap td;
+  const CUtensorMap* ptd = nullptr;
+  if (epi == EPI_DGELU_BF16) {
+    TRY(make_tmap(&td, pre, false, N, M, ld_pre, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+    ptd = &td;
+  }
   switch (bn) {
-    case 256: return launch_gemm_bn<256>(epi, res, ta, tb, tc, a, e->num_sms, st);
-    case 192: return launch_gemm_bn<192>(epi, res, ta, tb, tc, a, e->num_sms, st);
-    case 128: return launch_gemm_bn<128>(epi, res, ta, tb, tc, a, e->num_sms, st);
-    default: return launch_gemm_bn<64>(epi, res, ta, tb, tc, a, e->num_sms, st);
+    case 256: return launch_gemm_bn<256>(epi, res, ta, tb, tc, a, e->num_sms, st, ptd);
+    case 192: return launch_gemm_bn<192>(epi, res, ta, tb, tc, a, e->num_sms, st, ptd);
+    case 128: return launch_gemm_bn<128>(epi, res, ta, tb, tc, a, e->num_sms, st, ptd);
+    default: return launch_gemm_bn<64>(epi, res, ta, tb, tc, a, e->num_sms, st, ptd);
   }
 }
 
