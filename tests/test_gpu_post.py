@@ -139,3 +139,33 @@ def test_mosaic_pipeline_vs_oracle(W, S, size):
     _, (th_o, _, th3_o, _, _), _ = PO.mosaic_segment(rows_ref, mosaic, S, W, 8)
     assert float((out["th"].cpu().numpy() == th_o).mean()) >= 0.999
     assert float((out["th3"].cpu().numpy() == th3_o).mean()) >= 0.999
+
+
+def test_pgt_pseudo_masks_match_the_per_image_reference_loop():
+    """the pseudo-mask generation of SSS/PGT.py:55-91 for a whole batch on the device, against the
+    oracle's per-image restatement (compute_attention -> head mean -> resize pair -> utils.threshold); all heads, and the
+    ``rand`` branch with the reference's numpy draw order."""
+    tiny = VO.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=8, img_size=64)
+    sd = VO.randomize_affine(VO.init_state_dict(tiny, seed=21), seed=22)
+    m = build_model(tiny, sd, "fp32", chunk_tiles=4)
+    x = VO.synthetic_tile(64, seed=91, batch=5)
+    rows = VO.cls_attention_rows(sd, tiny, x).numpy()
+    y = vob.pgt.pseudo_masks(m, x.cuda())
+    assert tuple(y.shape) == (5, 1, 64, 64) and set(np.unique(y.cpu().numpy()).tolist()) <= {0.0, 1.0}
+    for b in range(5):
+        th, _, _, _, _ = PO.eval_tile(rows[b], x[b, 0].numpy(), 8)
+        assert float(((y[b, 0].cpu().numpy() * 255).astype(np.uint8) == th).mean()) >= 0.999
+    # the rand branch draws 1..6 heads (SSS/PGT.py:67-69 assumes the 6 heads of ViT-S): a one-block ViT-S-wide model
+    six = VO.ViTConfig(embed_dim=384, depth=1, num_heads=6, patch_size=8, img_size=64)
+    sd6 = VO.randomize_affine(VO.init_state_dict(six, seed=23), seed=24)
+    m6 = build_model(six, sd6, "fp32", chunk_tiles=4)
+    rows6 = VO.cls_attention_rows(sd6, six, x).numpy()
+    np.random.seed(5)
+    w = vob.pgt.select_heads(5, 6)
+    np.random.seed(5)
+    y2 = vob.pgt.pseudo_masks(m6, x.cuda(), rand=True)
+    assert (w.sum(1) - 1).abs().max().item() < 1e-6
+    for b in range(5):
+        sel = np.nonzero(w[b].numpy())[0]
+        th, _, _, _, _ = PO.eval_tile(rows6[b][sel], x[b, 0].numpy(), 8)
+        assert float(((y2[b, 0].cpu().numpy() * 255).astype(np.uint8) == th).mean()) >= 0.999

@@ -10,13 +10,13 @@ through the ``vitocm_b200`` shim at the repository root:
 
 Modules mirror the reference's file names: ``vision_transformer`` (SSS/dino/vision_transformer.py),
 ``utils`` (SSS/utils.py), ``sw_processing`` (SSS/sw_processing.py), ``model`` (SSS/model.py), ``optimizer``
-(SSS/optimizer.py), ``lr_scheduler`` (SSS/lr_scheduler.py).
+(SSS/optimizer.py), ``lr_scheduler`` (SSS/lr_scheduler.py), ``pgt`` (the mask-generation loop of SSS/PGT.py).
 All compute is in ``libvitocm.so`` (csrc/, C ABI in include/vitocm.h); build it with
 ``python vit-ocm-wmsegmentation_b200/build.py``.  There is no CPU fallback.
 """
 from . import _lib  # noqa: F401
 from . import vision_transformer as vits  # noqa: F401
-from . import utils, sw_processing, model, optimizer, lr_scheduler, synthetic  # noqa: F401
+from . import utils, sw_processing, model, optimizer, lr_scheduler, synthetic, pgt  # noqa: F401
 from .vision_transformer import VisionTransformer, vit_tiny, vit_small, vit_base, LazyAttention, LazyTensor  # noqa: F401
 from .utils import compute_attention, attention_masks, head_mean_maps  # noqa: F401
 from .sw_processing import MosaicSegmenter, sliding_window, grid_size, shard_range  # noqa: F401
