@@ -129,7 +129,9 @@ ln_bwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
 }
 
 // ------------------------------------------------------------------------------------------------ attention backward helpers
-// delta[b][h][q] (row pitch npad) = sum_d dO[row][h*64 + d] * O[row][h*64 + d]; one warp per token row, two bf16 per lane per head
+// delta[b][h][q] (row pitch npad) = sum_d dO[row][h*64 + d] * O[row][h*64 + d]; one warp per token row, two bf16 per lane per
+// head; all heads' loads are issued before the first reduction (HG heads at a time) so that a row costs one memory latency
+template <int HG>
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO, long long ld, float* __restrict__ delta,
                   int B, int N, int heads, int npad) {
@@ -138,11 +140,22 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __re
   for (long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5); row < M;
        row += static_cast<long long>(gridDim.x) * (blockDim.x >> 5)) {
     const int b = static_cast<int>(row / N), q = static_cast<int>(row - static_cast<long long>(b) * N);
-    for (int h = 0; h < heads; ++h) {
-      const uint32_t o = *reinterpret_cast<const uint32_t*>(O + row * ld + h * 64 + 2 * lane);
-      const uint32_t d = *reinterpret_cast<const uint32_t*>(dO + row * ld + h * 64 + 2 * lane);
-      const float s = warp_sum(bf16lo(o) * bf16lo(d) + bf16hi(o) * bf16hi(d));
-      if (lane == 0) delta[(static_cast<long long>(b) * heads + h) * npad + q] = s;
+    for (int h0 = 0; h0 < heads; h0 += HG) {
+      uint32_t o[HG], d[HG];
+#pragma unroll
+      for (int k = 0; k < HG; ++k) {
+        if (h0 + k < heads) {
+          o[k] = *reinterpret_cast<const uint32_t*>(O + row * ld + (h0 + k) * 64 + 2 * lane);
+          d[k] = *reinterpret_cast<const uint32_t*>(dO + row * ld + (h0 + k) * 64 + 2 * lane);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < HG; ++k) {
+        if (h0 + k < heads) {
+          const float s = warp_sum(bf16lo(o[k]) * bf16lo(d[k]) + bf16hi(o[k]) * bf16hi(d[k]));
+          if (lane == 0) delta[(static_cast<long long>(b) * heads + h0 + k) * npad + q] = s;
+        }
+      }
     }
   }
 }
