@@ -320,8 +320,14 @@ def main_mim(args):
     tensor_classes = {k: c for k, c in classes.items() if c["gflop"] > 0}
     dom = max(tensor_classes, key=lambda k: tensor_classes[k]["ms"])
     c = tensor_classes[dom]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        rec = json.load(open(tpath)).get(dom)
+        if rec and "dram_bytes_per_image_per_launch" in rec:   # ncu's DRAM bytes per image and launch x images per launch of this run
+            traffic = rec["dram_bytes_per_image_per_launch"] * Bg
     roofline = {"kernel": dom, "bound": "tensor", "achieved": c["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": c["tflops"] / peak,
-                "traffic": None, "peak_source": peak_src, "launches_per_step": c["launches"], "avg_launch_ms": c["ms"] / c["launches"]}
+                "traffic": traffic, "peak_source": peak_src, "launches_per_step": c["launches"], "avg_launch_ms": c["ms"] / c["launches"]}
     step_tflops = mim_flops_per_image(D, depth, a["num_heads"], N) * Bg / 1e12 / (ms_per_step / 1e3)
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
