@@ -7,7 +7,7 @@ import vitocm_b200 as vob
 from vitocm_b200._lib import check, cur_stream, ptr
 from gpu_util import make_engine
 
-B, H, N = 32, 6, 785
+B, H, N = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (32, 6, 785)
 D = 64 * H
 eng = make_engine(embed_dim=D, heads=H, precision=0)
 qkv = (torch.randn(B * N, 3 * D, device="cuda") * 1.0).to(torch.bfloat16)
@@ -26,3 +26,8 @@ for cta in range(2):
         ev = [int(s[cta, 0, j, k]) - t0 if s[cta, 0, j, k] > 0 else -1 for k in range(7)]
         mma = [int(s[cta, 1, j, k]) - t0 if s[cta, 1, j, k] > 0 else -1 for k in range(2)]
         print(f" j={j} " + " ".join(f"{n}={v}" for n, v in zip(names, ev)) + f" | MMA: S issued={mma[0]} PV issued={mma[1]}")
+
+for cta in range(2):
+    a, b = int(s[cta, 0, 15, 6]), int(s[cta, 0, 15, 7])
+    items = (B * H * ((N + 127) // 128) - cta + 295) // 296
+    print(f"CTA {cta}: lifetime {b - a} clk for {items} work items = {(b - a) / max(items, 1):.0f} clk per item")

@@ -39,6 +39,7 @@ struct AttnArgs {
   int out_lo_off;    // SPLIT: column offset of the lo half of ctx
   float* lse2;       // training: [B][H][Npad] (Npad = N rounded up to 128) log2-sum-exp of the scaled logits
                      // (max * scale_log2 + log2 l); +inf in the pad rows; or nullptr
+  int timeline_item;    // diagnostics: which of a CTA's work items (0, 1, ...) the stamps are taken on
   long long* timeline;  // diagnostics (vitocm_attention_timeline) or nullptr: clock64 stamps of CTAs (0,0,0) and (1,0,0)
 };
 
@@ -129,6 +130,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = ptx::lds_u32(tmem_ptr_smem);
+  if (tl0 && threadIdx.x == 0) args.timeline[((blockIdx.x * 2 + 0) * ATT_TL_BLOCKS + 15) * ATT_TL_EVENTS + 6] = clock64();   // CTA start
 
   if (warp >= 4) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_OTHER));
@@ -175,7 +177,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
       int g = 0;      // KV blocks processed so far (all work items): phase counter of s_full / s_empty / p_full / o_full
       int w = 0;
       for (int it = blockIdx.x; it < args.n_items; it += gridDim.x, ++w) {
-      const bool tl = tl0 && w == 0;
+      const bool tl = tl0 && w == args.timeline_item;
       auto kv_len_mma = [&](int j) {  // keys of block j rounded up to the MMA granularity (16)
         int len = N - j * ATT_BKV;
         len = len > ATT_BKV ? ATT_BKV : len;
@@ -268,7 +270,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     for (int it = blockIdx.x; it < args.n_items; it += gridDim.x, ++w) {
     const int qt = it % args.n_qtiles, h = (it / args.n_qtiles) % args.heads, b = it / (args.n_qtiles * args.heads);
     const int row_base = b * N;
-    const bool tl = tl0 && w == 0;
+    const bool tl = tl0 && w == args.timeline_item;
     float m_used = -INFINITY;     // the row maximum the exponentials are taken against
     float m_next = -INFINITY;     // a larger maximum seen in the previous block (lazy rescale pending)
     float l_run = 0.f;            // running row sum (same units as O in TMEM)
@@ -453,6 +455,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (tl0 && threadIdx.x == 0) args.timeline[((blockIdx.x * 2 + 0) * ATT_TL_BLOCKS + 15) * ATT_TL_EVENTS + 7] = clock64();   // CTA end
   if (warp == 5) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

@@ -457,6 +457,7 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
   a.n_tokens = N; a.embed_dim = D; a.lo_col_off = 3 * D;
   a.scale_log2 = e->cfg.qk_scale * 1.44269504088896340736f;
   a.out = reinterpret_cast<__nv_bfloat16*>(ctx); a.ldo = ldo; a.out_lo_off = D; a.timeline = timeline; a.lse2 = lse2;
+  { static const int tli = [] { const char* v = getenv("VITOCM_ATTN_TL_ITEM"); return v ? atoi(v) : 0; }(); a.timeline_item = tli; }
   a.n_qtiles = (N + ATT_BQ - 1) / ATT_BQ; a.heads = H;
   const long long items = static_cast<long long>(a.n_qtiles) * H * B;
   if (items > 0x7fffffffLL) return fail(VITOCM_ERR_INVALID, "attention: too many work items");
