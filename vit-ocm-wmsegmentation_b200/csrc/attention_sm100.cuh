@@ -46,8 +46,9 @@ struct AttnArgs {
 // timeline layout: [cta 0..1][role 0 = softmax warp 0, 1 = MMA thread][kv block j < 16][event < 8]
 constexpr int ATT_TL_EVENTS = 8;
 constexpr int ATT_TL_BLOCKS = 16;
-__device__ __forceinline__ void att_stamp(const AttnArgs& args, bool on, int role, int j, int ev) {
-  if (on && j < ATT_TL_BLOCKS) args.timeline[((blockIdx.x * 2 + role) * ATT_TL_BLOCKS + j) * ATT_TL_EVENTS + ev] = clock64();
+__device__ __forceinline__ void att_stamp(const AttnArgs& args, bool on, int role, int j, int ev, int pipe = -1) {
+  if (pipe < 0) pipe = blockIdx.x;
+  if (on && j < ATT_TL_BLOCKS) args.timeline[((pipe * 2 + role) * ATT_TL_BLOCKS + j) * ATT_TL_EVENTS + ev] = clock64();
 }
 
 constexpr int ATT_BQ = 128;
