@@ -193,6 +193,17 @@ int vitocm_concat_crops_u8(const uint8_t* crops, int n, int W, int S, int C, con
 int vitocm_crop_u8(const uint8_t* img, int img_h, int img_w, int C, int ny, int nx, int W, int S, uint8_t* crops,
                    void* stream);
 
+/* concat_crops_overlap(crops, stride) (SSS/utils.py:319-347): n x n crops of size W overlapping by 2*stride,
+ * overlaps = floor-halved sum `a // 2 + b // 2` along x then along y; the last strip is appended unblended
+ * (:337-339).  float32 [n*n][W][W] -> out [E][E]; uint8 HWC [n*n][W][W][C] -> out [E][E][C];
+ * E = W + (n-1) * (W - 2*stride).  Needs 0 < 2*stride < W. */
+int vitocm_concat_crops_overlap_f32(const float* crops, int n, int W, int stride, float* out, void* stream);
+int vitocm_concat_crops_overlap_u8(const uint8_t* crops, int n, int W, int stride, int C, uint8_t* out, void* stream);
+/* Plain tiling `concat_crops(crops)` (SSS/utils.py:304-317) of channel c0 of batched crops, as the `--crop 4|16`
+ * evaluation does for the attention maps and the image (SSS/eval.py:160-161):
+ * src [B][cr*cr][C][h][w] fp32 -> dst [B][cr*h][cr*w]. */
+int vitocm_concat_grid_f32(const float* src, int B, int cr, int C, int c0, int h, int w, float* dst, void* stream);
+
 /* ---- kernel-level entry points used by the tests / the bench roofline leg ---- */
 
 /* C = epilogue(A[M][K] . B[N][K]^T): A, B bf16 device (split: [rows][2K] = hi|lo); epilogue enum:

@@ -252,6 +252,67 @@ def blend_profiles(n: int, stride: int, window_size: int) -> np.ndarray:
     return P
 
 
+def concat_crops_overlap(crops: list[np.ndarray], stride: int) -> np.ndarray:
+    """utils.py:319-347.  n x n crops of size W that overlap by V = 2*stride: the running image and the
+    next crop are floor-halved and added in the overlap (`a // 2 + b // 2`, in the crops' dtype), first
+    along x (:324-332), then along y (:334-345) -- where the LAST strip (:337-339) is appended without
+    blending, so its overlap rows keep the running image."""
+    n = int(np.sqrt(len(crops)))
+    V = 2 * stride
+    W = crops[0].shape[0]
+    step = W - V
+
+    def halves(a, b):
+        return a // 2 + b // 2
+
+    strips = []
+    for i in range(n):
+        strip = np.array(crops[i * n])
+        for j in range(1, n):
+            nxt = np.asarray(crops[i * n + j])
+            x0 = j * step                                  # the running strip is x0 + V wide
+            grown = np.empty((strip.shape[0], x0 + W) + strip.shape[2:], dtype=strip.dtype)
+            grown[:, :x0] = strip[:, :x0]
+            grown[:, x0:x0 + V] = halves(strip[:, x0:x0 + V], nxt[:, :V])
+            grown[:, x0 + V:] = nxt[:, V:]
+            strip = grown
+        strips.append(strip)
+    out = strips[0]
+    for i in range(1, n):
+        y0 = i * step
+        grown = np.empty((y0 + W,) + out.shape[1:], dtype=out.dtype)
+        grown[:y0] = out[:y0]
+        grown[y0:y0 + V] = out[y0:y0 + V] if i == n - 1 else halves(out[y0:y0 + V], strips[i][:V])
+        grown[y0 + V:] = strips[i][V:]
+        out = grown
+    return out
+
+
+def sliding_window_utils(image: np.ndarray, window_size: int, stride: int) -> list[np.ndarray]:
+    """utils.py:349-362: the same window walk as sw_processing.sliding_window with (window_size, stride) swapped."""
+    return sliding_window(image, stride, window_size)
+
+
+def eval_cropped(cls_rows_crops: np.ndarray, crops01: np.ndarray, patch_size: int = 8):
+    """eval.py:145-173 (`--crop 4|16`).  cls_rows_crops [cr*cr, H, N]: CLS rows of every crop of ONE image, row-major;
+    crops01 [cr*cr, s, s]: channel 0 of the crops (float in [0,1]).  Per crop: head mean of the nearest-upsampled
+    CLS maps (median_filter size 1 = identity); plain concat (:160-161); resize /p then up to the image size
+    (:169-171); threshold against the PIL "L" image of the tiled crops (:173).
+    Returns (attention [S,S] float32, threshold_utils tuple)."""
+    ncrop, s = crops01.shape[0], crops01.shape[-1]
+    f = s // patch_size
+    maps = []
+    for c in range(ncrop):
+        a, _ = compute_attention_from_rows(cls_rows_crops[c], f, f, patch_size)
+        maps.append(np.mean(a, axis=0))                                      # :156
+    avg = concat_crops_plain(maps)                                           # :160
+    img = concat_crops_plain([np.asarray(c, dtype=np.float32) for c in crops01])   # :161
+    small = resize_linear(avg, (avg.shape[1] // patch_size, avg.shape[0] // patch_size))   # :169
+    att = resize_linear(small, (img.shape[-1], img.shape[-1]))               # :171
+    img_u8 = np.floor(img * np.float32(255.0)).astype(np.uint8)              # ToPILImage + convert("L") on R=G=B
+    return att, threshold_utils(img_u8, att)
+
+
 # --------------------------------------------------------------------------------------
 # drivers
 # --------------------------------------------------------------------------------------

@@ -169,3 +169,50 @@ def test_pgt_pseudo_masks_match_the_per_image_reference_loop():
         sel = np.nonzero(w[b].numpy())[0]
         th, _, _, _, _ = PO.eval_tile(rows6[b][sel], x[b, 0].numpy(), 8)
         assert float(((y2[b, 0].cpu().numpy() * 255).astype(np.uint8) == th).mean()) >= 0.999
+
+
+def test_concat_crops_overlap_and_utils_sliding_window_bit_exact():
+    """SSS/utils.py:319-347 / :349-362 on the device against the reference's golden outputs
+    (float32, uint8 gray, uint8 RGB; overlaps below and above half a window; n = 1)."""
+    g = load_golden("variants.npz")
+    for name, st in {"w16s2n3": 2, "w16s5n4": 5, "w12s3n2": 3, "w10s2n1": 2, "w24s4n5": 4}.items():
+        for kind in ("f32", "u8", "rgb"):
+            tiles = list(g[f"overlap/{name}/{kind}/tiles"])
+            out = vu.concat_crops_overlap(tiles, st)
+            want = g[f"overlap/{name}/{kind}/out"]
+            assert out.dtype == want.dtype and np.array_equal(out, want), (name, kind)
+    crops = vu.sliding_window(g["sw/img"], 24, 10)
+    assert np.array_equal(np.stack(crops), g["sw/crops"])
+    # a larger random case against the oracle (all three dtypes in one geometry the goldens do not hold)
+    rng = np.random.RandomState(5)
+    tiles = [((rng.rand(40, 40) - 0.5) * 1000).astype(np.float32) for _ in range(36)]
+    assert np.array_equal(vu.concat_crops_overlap(tiles, 7), PO.concat_crops_overlap(tiles, 7))
+    tiles = [rng.randint(0, 256, (40, 40, 3)).astype(np.uint8) for _ in range(36)]
+    assert np.array_equal(vu.concat_crops_overlap(tiles, 13), PO.concat_crops_overlap(tiles, 13))
+    with pytest.raises(vob.VitocmError):
+        vu.concat_crops_overlap(tiles, 20)          # 2 * stride must stay below the window
+
+
+@pytest.mark.parametrize("name", ["crop4", "crop16"])
+def test_cropped_evaluation_path_matches_reference_goldens(name):
+    """`--crop 4|16` (SSS/eval.py:145-173, SSS/data.py:85-125) batched on the device against the
+    reference's own run: CLS rows within 1e-3, masks >= 99.9 %; and bit-exact against the oracle fed the GPU's rows."""
+    g = load_golden("variants.npz")
+    tiny = VO.ViTConfig(embed_dim=128, depth=3, num_heads=2, patch_size=8, img_size=32)
+    sd = VO.randomize_affine(VO.init_state_dict(tiny, seed=7), seed=8)
+    m = build_model(tiny, sd, "fp32", chunk_tiles=5)
+    images = torch.from_numpy(g[f"{name}/images"])
+    out = vu.cropped_attention_masks(m, images.cuda(), return_attention=True)
+    B, ncrop = images.shape[:2]
+    rows_gpu = out["cls_rows"].cpu().numpy().reshape(B, ncrop, 2, -1)
+    rows_ref = g[f"{name}/cls_rows"]
+    assert float((np.abs(rows_gpu - rows_ref) / rows_ref).max()) <= 1e-3
+    masks = out["masks"].cpu().numpy()
+    att = out["attention"].cpu().numpy()
+    for b in range(B):
+        o_att, o_th = PO.eval_cropped(rows_gpu[b], images[b, :, 0].numpy(), 8)
+        assert np.array_equal(att[b], o_att)
+        for k in range(3):
+            assert np.array_equal(masks[b, k], o_th[k])
+            assert float((masks[b, k] == g[f"{name}/masks"][b, k]).mean()) >= 0.999
+        assert np.abs(att[b] - g[f"{name}/attention"][b]).max() <= 1e-3 * np.abs(g[f"{name}/attention"][b]).max()

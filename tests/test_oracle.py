@@ -202,3 +202,24 @@ def test_package_synthetic_inputs_equal_the_oracle_recipe():
     rs = np.random.RandomState(3)
     b = np.stack([VO.mask_generator(rs, 32, 16, 8, 0.5) for _ in range(4)])
     assert np.array_equal(a, b)
+
+
+def test_crop_and_overlap_variants_match_reference():
+    """concat_crops_overlap (SSS/utils.py:319-347), utils.sliding_window (:349-362) and the
+    `--crop 4|16` evaluation path (SSS/eval.py:145-173) against outputs of the reference's own functions."""
+    g = load_golden("variants.npz")
+    for name, st in {"w16s2n3": 2, "w16s5n4": 5, "w12s3n2": 3, "w10s2n1": 2, "w24s4n5": 4}.items():
+        for kind in ("f32", "u8", "rgb"):
+            tiles = list(g[f"overlap/{name}/{kind}/tiles"])
+            out = PO.concat_crops_overlap(tiles, st)
+            want = g[f"overlap/{name}/{kind}/out"]
+            assert out.dtype == want.dtype and np.array_equal(out, want), (name, kind)
+    crops = PO.sliding_window_utils(g["sw/img"], 24, 10)
+    assert np.array_equal(np.stack(crops), g["sw/crops"])
+    for name in ("crop4", "crop16"):
+        images, rows = g[f"{name}/images"], g[f"{name}/cls_rows"]
+        for b in range(images.shape[0]):
+            att, th = PO.eval_cropped(rows[b], images[b, :, 0], 8)
+            assert np.abs(att - g[f"{name}/attention"][b]).max() < 1e-6
+            for k in range(3):
+                assert np.array_equal(th[k], g[f"{name}/masks"][b, k])

@@ -355,6 +355,71 @@ __global__ void crop_u8_kernel(const uint8_t* __restrict__ img, int img_h, int i
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Crop variants of the eval / analyse scripts.
+// ---------------------------------------------------------------------------------------
+// concat_crops_overlap(crops, stride) (SSS/utils.py:319-347): n x n crops of size W overlapping by
+// V = 2 * stride; inside an overlap the running image and the next crop are each floor-halved and added
+// (`a // 2 + b // 2`), first along x inside a strip, then along y across strips -- except that the LAST
+// strip is appended without blending: its overlap rows keep the running image (:337-339).
+// Gather form: the value of an output pixel is the fold, in crop order, over the crops that cover it.
+struct OverlapGeom {
+  int n, W, V, step, E;   // step = W - V, E = W + (n-1) * step
+};
+__device__ __forceinline__ float half_floor(float a) { return floorf(__fmul_rn(a, 0.5f)); }
+__device__ __forceinline__ float avg_halves(float a, float b) { return __fadd_rn(half_floor(a), half_floor(b)); }
+__device__ __forceinline__ uint8_t avg_halves(uint8_t a, uint8_t b) { return static_cast<uint8_t>((a >> 1) + (b >> 1)); }
+
+template <typename T>
+__global__ void concat_crops_overlap_kernel(const T* __restrict__ crops /*[n*n][W][W][C]*/, OverlapGeom g, int C,
+                                            T* __restrict__ out /*[E][E][C]*/) {
+  const long long total = static_cast<long long>(g.E) * g.E * C;
+  const long long tsz = static_cast<long long>(g.W) * g.W * C;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C);
+    const long long px = idx / C;
+    const int Y = static_cast<int>(px / g.E), X = static_cast<int>(px % g.E);
+    // crops covering X: j*step <= X < j*step + W
+    int j0 = X < g.W ? 0 : (X - g.W) / g.step + 1;
+    const int j1 = min(X / g.step, g.n - 1);
+    int i0 = Y < g.W ? 0 : (Y - g.W) / g.step + 1;
+    const int i1 = min(Y / g.step, g.n - 1);
+    T v = T(0);
+    for (int i = i0; i <= i1; ++i) {
+      const int ky = Y - i * g.step;
+      T hv = T(0);
+      for (int j = j0; j <= j1; ++j) {
+        const int kx = X - j * g.step;
+        const T tv = crops[(i * g.n + j) * tsz + (static_cast<long long>(ky) * g.W + kx) * C + c];
+        hv = (j > j0 && kx < g.V) ? avg_halves(hv, tv) : tv;
+      }
+      if (i > i0 && ky < g.V) {
+        if (i != g.n - 1) v = avg_halves(v, hv);   // last strip: the running image is kept as it is
+      } else {
+        v = hv;
+      }
+    }
+    out[idx] = v;
+  }
+}
+
+// plain n x n tiling (SSS/utils.py:304-317 `concat_crops`; SSS/eval.py:160-161) of one channel of batched crops:
+// src [B][cr*cr][C][h][w] fp32 -> dst [B][cr*h][cr*w], channel c0.  Pure data movement.
+__global__ void concat_grid_f32_kernel(const float* __restrict__ src, int B, int cr, int C, int c0, int h, int w,
+                                       float* __restrict__ dst) {
+  const int EH = cr * h, EW = cr * w;
+  const long long total = static_cast<long long>(B) * EH * EW;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int X = static_cast<int>(idx % EW);
+    const int Y = static_cast<int>((idx / EW) % EH);
+    const int b = static_cast<int>(idx / (static_cast<long long>(EW) * EH));
+    const int ci = Y / h, cj = X / w;
+    dst[idx] = src[(((static_cast<long long>(b) * cr * cr + ci * cr + cj) * C + c0) * h + (Y - ci * h)) * w + (X - cj * w)];
+  }
+}
+
 // pass 1: global min / max of the stitched map over rows [y_begin, y_end); minmax_ord[0] = min, [1] = max
 // (order-preserving int keys; initialise to INT_MAX / INT_MIN); optionally store the map.
 __global__ void __launch_bounds__(256)

@@ -1149,6 +1149,41 @@ int vitocm_crop_u8(const uint8_t* img, int img_h, int img_w, int C, int ny, int 
   return 0;
 }
 
+static int overlap_geom(int n, int W, int stride, OverlapGeom* g) {
+  const long long V = 2LL * stride;
+  if (n < 1 || stride < 1 || V >= W) return fail(VITOCM_ERR_INVALID, "bad overlap geometry n=%d W=%d stride=%d (needs 0 < 2*stride < W)", n, W, stride);
+  g->n = n; g->W = W; g->V = static_cast<int>(V); g->step = W - g->V; g->E = W + (n - 1) * g->step;
+  return 0;
+}
+
+int vitocm_concat_crops_overlap_f32(const float* crops, int n, int W, int stride, float* out, void* stream) {
+  OverlapGeom g;
+  TRY(overlap_geom(n, W, stride, &g));
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
+  concat_crops_overlap_kernel<float><<<grid_for(static_cast<long long>(g.E) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(crops, g, 1, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int vitocm_concat_crops_overlap_u8(const uint8_t* crops, int n, int W, int stride, int C, uint8_t* out, void* stream) {
+  OverlapGeom g;
+  TRY(overlap_geom(n, W, stride, &g));
+  if (C < 1) return fail(VITOCM_ERR_INVALID, "bad channel count %d", C);
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
+  concat_crops_overlap_kernel<uint8_t><<<grid_for(static_cast<long long>(g.E) * g.E * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(crops, g, C, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int vitocm_concat_grid_f32(const float* src, int B, int cr, int C, int c0, int h, int w, float* dst, void* stream) {
+  if (B < 0 || cr < 1 || C < 1 || c0 < 0 || c0 >= C || h < 1 || w < 1) return fail(VITOCM_ERR_INVALID, "bad crop grid B=%d cr=%d C=%d c0=%d h=%d w=%d", B, cr, C, c0, h, w);
+  if (B == 0) return 0;
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
+  concat_grid_f32_kernel<<<grid_for(static_cast<long long>(B) * cr * h * cr * w, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, B, cr, C, c0, h, w, dst);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------ kernel-level entry points
 int vitocm_gemm(vitocm_engine* e, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int split_in,
                 int epilogue, const float* bias, void* out, int64_t ldo, int split_out, int lo_off, void* stream) {

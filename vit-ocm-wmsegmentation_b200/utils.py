@@ -1,7 +1,8 @@
 """Drop-in for the hot-path half of the reference's ``utils.py`` (eval / PGT flavour):
 ``compute_attention`` (SSS/utils.py:229-235), ``min_max_normalize`` (:55-60), ``threshold``
-(:62-115) and the plain-tiling ``concat_crops`` (:304-317), plus ``attention_masks`` -- the
-batched, device-resident version of the per-image loop body at SSS/eval.py:136-173.
+(:62-115), the plain-tiling ``concat_crops`` (:304-317), ``concat_crops_overlap`` (:319-347) and
+``sliding_window`` (:349-362), plus ``attention_masks`` / ``cropped_attention_masks`` -- the batched,
+device-resident versions of the per-image loop body at SSS/eval.py:136-173 (`--crop 1` and `--crop 4|16`).
 
 All arithmetic runs in libvitocm.so kernels; torch is used for device buffers only.
 """
@@ -109,6 +110,92 @@ def attention_masks(model, x: torch.Tensor, return_attention: bool = False):
     check(_lib.load_library().vitocm_tile_threshold(ptr(low), ptr(xx), B, x.shape[1], S, lh, lw, ptr(masks), ptr(thr),
                                                     ptr(att), None, None, cur_stream()))
     out = dict(masks=masks, thresholds=thr, lowres=low.view(B, lh, lw), cls_rows=rows)
+    if return_attention:
+        out["attention"] = att
+    return out
+
+
+def concat_crops_overlap(crops, stride):
+    """SSS/utils.py:319-347: n x n crops overlapping by 2*stride; overlaps are `a // 2 + b // 2` (floor halves), along x
+    inside each strip and then along y, the last strip being appended unblended.  float crops accumulate in float32,
+    uint8 crops in uint8, as the reference's dtypes do.  Host arrays in and out; the fold runs on the device."""
+    dev = _dev()
+    n = int(np.sqrt(len(crops)))
+    first = np.asarray(crops[0])
+    W = first.shape[0]
+    lib = _lib.load_library()
+    E = W + (n - 1) * (W - 2 * int(stride))
+    if first.dtype == np.uint8:
+        stack = np.ascontiguousarray(np.stack([np.asarray(c) for c in crops[:n * n]]), dtype=np.uint8)
+        squeeze = stack.ndim == 3
+        if squeeze:
+            stack = stack[..., None]
+        C = stack.shape[-1]
+        d = torch.from_numpy(stack).to(dev)
+        out = torch.empty(max(E, 0), max(E, 0), C, dtype=torch.uint8, device=dev)
+        check(lib.vitocm_concat_crops_overlap_u8(ptr(d), n, W, int(stride), C, ptr(out), cur_stream()))
+        res = out.cpu().numpy()
+        return res[..., 0] if squeeze else res
+    stack = np.ascontiguousarray(np.stack([np.asarray(c, dtype=np.float32) for c in crops[:n * n]]))
+    d = torch.from_numpy(stack).to(dev)
+    out = torch.empty(max(E, 0), max(E, 0), dtype=torch.float32, device=dev)
+    check(lib.vitocm_concat_crops_overlap_f32(ptr(d), n, W, int(stride), ptr(out), cur_stream()))
+    return out.cpu().numpy()
+
+
+def sliding_window(image, window_size, stride):
+    """SSS/utils.py:349-362 (note the argument order: the mosaic script's twin takes (image, stride, window_size)).
+    image: PIL image or uint8 array [H, W(, C)] -> list of uint8 crops, row-major, zero padded beyond the image."""
+    dev = _dev()
+    arr = np.ascontiguousarray(np.array(image), dtype=np.uint8)
+    squeeze = arr.ndim == 2
+    if squeeze:
+        arr = arr[:, :, None]
+    H, W, C = arr.shape
+    # `height, width = image.size` unpacks PIL's (width, height): y runs over the width (:351)
+    ny, nx = len(range(0, W - stride * 2, stride)), len(range(0, H - stride * 2, stride))
+    if ny <= 0 or nx <= 0:
+        return []
+    d_img = torch.from_numpy(arr).to(dev)
+    crops = torch.empty(ny * nx, window_size, window_size, C, dtype=torch.uint8, device=dev)
+    check(_lib.load_library().vitocm_crop_u8(ptr(d_img), H, W, C, ny, nx, window_size, stride, ptr(crops), cur_stream()))
+    out = crops.cpu().numpy()
+    if squeeze:
+        out = out[..., 0]
+    return [out[i] for i in range(out.shape[0])]
+
+
+@torch.no_grad()
+def cropped_attention_masks(model, images: torch.Tensor, return_attention: bool = False):
+    """Device-resident, batched SSS/eval.py:145-173 (`--crop 4|16`, data.py:85-125): every image arrives as cr*cr
+    equal crops, images [B, cr*cr, C, s, s]; each crop goes through the ViT on its own, the head-mean CLS maps and
+    channel 0 of the crops are tiled back (plain `concat_crops`, :160-161), the tiled map is upsampled bilinearly
+    over the whole image (:169-171) and thresholded against the tiled image (`utils.threshold`).
+    Returns dict(masks [B, 3, S, S] u8 (ours, otsu, heatmap), thresholds [B, 3], lowres [B, cr*h, cr*w], image
+    [B, 1, S, S] [, attention [B, S, S]]) with S = cr * s."""
+    if images.dim() != 5 or images.shape[-1] != images.shape[-2]:
+        raise ValueError("cropped_attention_masks expects [B, crops, C, s, s]")
+    B, ncrop, C, s, _ = images.shape
+    cr = int(np.sqrt(ncrop))
+    if cr * cr != ncrop:
+        raise ValueError("the number of crops must be a square (4, 16, ...)")
+    lib = _lib.load_library()
+    p = model.patch_embed.patch_size
+    xx = images.detach().to(torch.float32).contiguous()
+    rows = model.cls_attention_rows(xx.view(B * ncrop, C, s, s))
+    low = head_mean_maps(rows, per_tile_minmax255=False)                      # [B*ncrop, h*h]
+    h = s // p
+    S = cr * s
+    low_t = torch.empty(B, cr * h, cr * h, dtype=torch.float32, device=xx.device)
+    check(lib.vitocm_concat_grid_f32(ptr(low), B, cr, 1, 0, h, h, ptr(low_t), cur_stream()))
+    img_t = torch.empty(B, 1, S, S, dtype=torch.float32, device=xx.device)
+    check(lib.vitocm_concat_grid_f32(ptr(xx), B, cr, C, 0, s, s, ptr(img_t), cur_stream()))
+    masks = torch.empty(B, 3, S, S, dtype=torch.uint8, device=xx.device)
+    thr = torch.empty(B, 3, dtype=torch.int32, device=xx.device)
+    att = torch.empty(B, S, S, dtype=torch.float32, device=xx.device) if return_attention else None
+    check(lib.vitocm_tile_threshold(ptr(low_t), ptr(img_t), B, 1, S, cr * h, cr * h, ptr(masks), ptr(thr), ptr(att), None, None,
+                                    cur_stream()))
+    out = dict(masks=masks, thresholds=thr, lowres=low_t, image=img_t, cls_rows=rows)
     if return_attention:
         out["attention"] = att
     return out
