@@ -142,3 +142,30 @@ def test_multi_rank_host_logic_gloo_world2(tmp_path):
     world = 2
     mp.spawn(_gloo_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def test_checkpoint_file_round_trip_on_the_host(tmp_path):
+    """SURVEY.md 8(f) rank 4 (host half; no compute): save_checkpoint writes the reference's dictionary
+    (SSS/utils.py:375-385) and load_pretrained_weights applies eval.py:67-77's key handling."""
+    from functools import partial
+    from types import SimpleNamespace as NS
+    import torch
+    import vitocm_b200 as vob
+
+    torch.manual_seed(3)
+    mk = lambda: vob.VisionTransformer(patch_size=8, embed_dim=64, depth=1, num_heads=1, mlp_ratio=4, img_size=[16], qkv_bias=True,
+                                       norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    a, b = mk(), mk()
+    opt = torch.optim.AdamW(a.parameters(), lr=1e-3)
+    sched = vob.lr_scheduler.CosineLRScheduler(opt, t_initial=10, lr_min=1e-6, warmup_t=0, warmup_lr_init=0.0)
+    path = vob.utils.save_checkpoint(NS(OUTPUT=str(tmp_path)), 7, a, 0.5, opt, sched, None)
+    assert path.endswith("ckpt_epoch_7.pth")
+    msg = vob.utils.load_pretrained_weights(b, path)
+    assert msg.missing_keys == [] and msg.unexpected_keys == []
+    assert all(torch.equal(v, b.state_dict()[k]) for k, v in a.state_dict().items())
+    # DataParallel / multicrop-wrapper prefixes on the top-level keys and a checkpoint_key, as eval.py handles them
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    torch.save({"teacher": {"module.model": ck["model"]}}, tmp_path / "wrapped.pth")
+    c = mk()
+    vob.utils.load_pretrained_weights(c, str(tmp_path / "wrapped.pth"), checkpoint_key="teacher")
+    assert all(torch.equal(v, c.state_dict()[k]) for k, v in a.state_dict().items())

@@ -230,3 +230,75 @@ def test_training_needs_bf16_engine_and_eval_mode_is_plain_forward():
     mim.eval()
     loss, x_rec, _ = mim(x, mask)            # evaluation works in the fp32-parity mode
     assert not loss.requires_grad and torch.isfinite(loss)
+
+
+def test_checkpoint_resume_interchanges_with_stock_torch_adamw(tmp_path):
+    """save_checkpoint (SSS/utils.py:375-385, called on the encoder as SSS/mim.py:123 does) after two fused
+    steps; the optimizer state has torch.optim.AdamW's layout, so (a) the reference's stock optimizer resumes from it and (b) a
+    fresh FusedAdamW resumes from the stock optimizer's state -- both then take the same third step; eval-side loading
+    (SSS/eval.py:67-77) of the saved encoder reproduces the CLS rows."""
+    from types import SimpleNamespace as NS
+    g = load_golden("mim_train_tiny.npz")
+    args = NS(TRAIN=NS(BASE_LR=5e-4, WEIGHT_DECAY=0.05, OPTIMIZER=NS(NAME="adamw", EPS=1e-8, BETAS=(0.9, 0.999))), OUTPUT=str(tmp_path))
+
+    def one_step(mim, opt, it, fused):
+        x, mask = torch.from_numpy(g[f"step{it % 2}/x"]).cuda(), torch.from_numpy(g[f"step{it % 2}/mask"]).cuda()
+        opt.zero_grad()
+        loss, _, _ = mim(x, mask)
+        loss.sum().backward()
+        if fused:
+            vob.optimizer.clip_grad_norm_(mim, 5.0)
+        else:
+            torch.nn.utils.clip_grad_norm_(mim.parameters(), 5.0)
+        opt.step()
+
+    mim, _ = _tiny_mim(g)
+    opt = vob.optimizer.build_pretrain_optimizer(args, mim, None)
+    sched = vob.lr_scheduler.CosineLRScheduler(opt, t_initial=100, lr_min=1e-6, warmup_t=2, warmup_lr_init=1e-6)
+    for it in range(2):
+        one_step(mim, opt, it, True)
+        sched.step_update(it + 1)
+    path = vob.utils.save_checkpoint(args, 3, mim.encoder, 0., opt, sched, None)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"model", "optimizer", "lr_scheduler", "max_accuracy", "epoch", "config"} and ck["epoch"] == 3
+    assert set(ck["model"]) == set(mim.encoder.state_dict()) and all(v.device.type == "cpu" and v.dtype == torch.float32 for v in ck["model"].values())
+    n_params = sum(1 for _ in mim.parameters())
+    assert len(ck["optimizer"]["state"]) == n_params and all(float(s["step"]) == 2.0 for s in ck["optimizer"]["state"].values())
+    mim_sd = {k: v.detach().clone() for k, v in mim.state_dict().items()}
+
+    # (a) stock torch AdamW resumes from the fused optimizer's state
+    mim_a, _ = _tiny_mim(g)
+    mim_a.load_state_dict(mim_sd)
+    groups = vob.optimizer.get_pretrain_param_groups(mim_a, None, mim_a.no_weight_decay(), mim_a.no_weight_decay_keywords())
+    opt_a = torch.optim.AdamW(groups, eps=1e-8, betas=(0.9, 0.999), lr=5e-4, weight_decay=0.05)
+    opt_a.load_state_dict(ck["optimizer"])
+    assert opt_a.param_groups[0]["lr"] == opt.param_groups[0]["lr"]          # the scheduler's rate travels with the groups
+    # (b) a fresh fused optimizer resumes from the stock optimizer's state
+    mim_b, _ = _tiny_mim(g)
+    mim_b.load_state_dict(mim_sd)
+    opt_b = vob.optimizer.build_pretrain_optimizer(args, mim_b, None)
+    opt_b.load_state_dict(opt_a.state_dict())
+    assert opt_b.steps == 2
+    one_step(mim, opt, 2, True)
+    one_step(mim_a, opt_a, 2, False)
+    one_step(mim_b, opt_b, 2, True)
+    for (n, p), (_, pa), (_, pb) in zip(mim.named_parameters(), mim_a.named_parameters(), mim_b.named_parameters()):
+        # three runs of the same third step; not bit-identical (the backward reduces some gradients with atomics)
+        tol = 2e-6 + 1e-5 * p.abs().max().item()
+        assert (p - pb).abs().max().item() <= tol and (p - pa).abs().max().item() <= tol, n
+
+    # eval side: a plain ViT loads the saved encoder (strict=False drops mask_token) and reproduces its CLS rows
+    # (the SimMIM encoder keeps the ViT's default 224 position table whatever img_size it is given, SSS/model.py:11-16)
+    vit = vob.VisionTransformer(patch_size=8, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4, img_size=[224], qkv_bias=True,
+                                norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), precision="bf16").cuda().eval()
+    msg = vob.utils.load_pretrained_weights(vit, path)
+    assert msg.missing_keys == [] and msg.unexpected_keys == ["mask_token"]
+    enc2 = vob.VisionTransformerForSimMIM(patch_size=8, embed_dim=128, depth=2, num_heads=2, mlp_ratio=4, img_size=[32], qkv_bias=True,
+                                          norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), precision="bf16")
+    enc2.load_state_dict(ck["model"], strict=True)
+    x = VO.synthetic_tile(32, seed=5, batch=3).cuda()
+    assert torch.equal(vit.cls_attention_rows(x), enc2.cuda().eval().cls_attention_rows(x))
+    # get_grad_norm (SSS/utils.py:363-373) on the flat buffer and on a parameter list
+    gn = vob.utils.get_grad_norm(opt)
+    assert abs(gn - mim._gflat.double().norm().item()) <= 1e-6 * gn
+    assert abs(vob.utils.get_grad_norm(mim.parameters()) - gn) <= 1e-5 * gn

@@ -55,7 +55,9 @@ class FusedAdamW(torch.optim.Optimizer):
         mim = _unwrap(model)
         mim.flatten_parameters()
         groups = get_pretrain_param_groups(mim, None, skip_list, skip_keywords)
-        super().__init__(groups, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        # the extra keys are torch.optim.AdamW's own defaults: a saved state dict then carries complete groups for the stock optimizer
+        super().__init__(groups, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False, foreach=None,
+                                      capturable=False, differentiable=False, fused=None))
         self.mim = mim
         self.decay = mim.decay_flags(skip_list, skip_keywords)
         self.exp_avg = torch.zeros_like(mim._pflat)
@@ -90,6 +92,51 @@ class FusedAdamW(torch.optim.Optimizer):
         self._pending_max_norm = 0.0
         mim.encoder.refresh_engine()      # asynchronous bf16 repack of the updated masters (vitocm_refresh_weights)
         return None
+
+    # ------------------------------------------------------------------ checkpoint interchange (SSS/utils.py:375-385)
+    def _flat_slices(self):
+        """id(parameter) -> (offset, numel, shape) inside the flat buffers."""
+        return {id(p): (o, p.numel(), tuple(p.shape)) for (_, p), o in zip(self.mim._param_list, self.mim._flat_offsets)}
+
+    def state_dict(self):
+        """The layout ``torch.optim.AdamW.state_dict()`` has for the same two parameter groups (per-parameter ``step`` /
+        ``exp_avg`` / ``exp_avg_sq`` indexed in group order), cut out of the flat moment buffers: a checkpoint written here
+        resumes under the reference's stock optimizer and the other way round."""
+        sd = super().state_dict()
+        state, idx, where = {}, 0, self._flat_slices()
+        for grp in self.param_groups:
+            for p in grp["params"]:
+                if self.steps > 0:
+                    o, n, shape = where[id(p)]
+                    state[idx] = {"step": torch.tensor(float(self.steps)),
+                                  "exp_avg": self.exp_avg[o:o + n].view(shape).clone(),
+                                  "exp_avg_sq": self.exp_avg_sq[o:o + n].view(shape).clone()}
+                idx += 1
+        sd["state"] = state
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        groups = state_dict["param_groups"]
+        if len(groups) != len(self.param_groups) or any(len(a["params"]) != len(b["params"]) for a, b in zip(groups, self.param_groups)):
+            raise ValueError("loaded state dict has different parameter groups")
+        for mine, theirs in zip(self.param_groups, groups):
+            mine.update({k: v for k, v in theirs.items() if k != "params"})
+        where, idx, steps = self._flat_slices(), 0, set()
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for mine, theirs in zip(self.param_groups, groups):
+            for p, key in zip(mine["params"], theirs["params"]):
+                st = state_dict["state"].get(key)
+                if st is not None:
+                    o, n, _ = where[id(p)]
+                    self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                    self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps.add(int(st["step"]))
+                idx += 1
+        if len(steps) > 1:
+            raise ValueError("FusedAdamW keeps one step counter: the loaded per-parameter steps differ")
+        self.steps = steps.pop() if steps else 0
 
     def zero_grad(self, set_to_none: bool = False):
         """One memset of the flat gradient buffer; the ``.grad`` views stay attached."""

@@ -199,3 +199,62 @@ def cropped_attention_masks(model, images: torch.Tensor, return_attention: bool 
     if return_attention:
         out["attention"] = att
     return out
+
+
+# ----------------------------------------------------------------------------- checkpoints
+def get_grad_norm(parameters, norm_type=2):
+    """SSS/utils.py:363-373: total gradient norm over `parameters` (a tensor, an iterable of parameters, or a
+    FusedAdamW / MIM whose gradients live in one flat buffer -- then a single reduction kernel)."""
+    flat = getattr(getattr(parameters, "mim", parameters), "_gflat", None)
+    lib = _lib.load_library()
+    acc = None
+    if flat is not None and float(norm_type) == 2.0:
+        grads = [flat]
+    else:
+        if isinstance(parameters, torch.Tensor):
+            parameters = [parameters]
+        grads = [p.grad.detach() for p in parameters if p.grad is not None]
+    if float(norm_type) != 2.0:
+        raise NotImplementedError("vitocm get_grad_norm: only the 2-norm (the reference's call, SSS/mim.py:178,186) is on the device")
+    total = 0.0
+    for g in grads:
+        g = g.to(torch.float32).contiguous()
+        if g.data_ptr() % 16:
+            g = g.clone()
+        acc = torch.empty(1, dtype=torch.float64, device=g.device)
+        check(lib.vitocm_grad_sumsq(ptr(g), g.numel(), ptr(acc), cur_stream()))
+        total += float(acc.item())
+    return total ** 0.5
+
+
+def save_checkpoint(config, epoch, model, max_accuracy, optimizer, lr_scheduler, logger):
+    """SSS/utils.py:375-385: {'model', 'optimizer', 'lr_scheduler', 'max_accuracy', 'epoch', 'config'} ->
+    config.OUTPUT/ckpt_epoch_{epoch}.pth.  The reference passes the ENCODER (SSS/mim.py:123), so 'model' carries the
+    plain ViT keys that eval.py / sw_processing.py load; tensors are stored as ordinary fp32 CPU tensors (the flat
+    training buffers and the engine's repacked bf16 copies never reach the file)."""
+    save_state = {'model': {k: v.detach().to("cpu", copy=True) for k, v in model.state_dict().items()},
+                  'optimizer': optimizer.state_dict(),
+                  'lr_scheduler': lr_scheduler.state_dict(),
+                  'max_accuracy': max_accuracy,
+                  'epoch': epoch,
+                  'config': config}
+    save_path = os.path.join(config.OUTPUT, f'ckpt_epoch_{epoch}.pth')
+    if logger is not None:
+        logger.info(f"{save_path} saving......")
+    torch.save(save_state, save_path)
+    if logger is not None:
+        logger.info(f"{save_path} saved !!!")
+    return save_path
+
+
+def load_pretrained_weights(model, pretrained_weights, checkpoint_key=None):
+    """The checkpoint branch of SSS/eval.py:67-77 (= sw_processing.py:187-197, analyse_attention.py:61-71): torch.load
+    on the CPU, optional `checkpoint_key`, the `module.` / `backbone.` prefix strips, then
+    ``model.load_state_dict(state_dict["model"], strict=False)``.  Returns the load message.  The engine picks the new
+    values up by itself (parameter versions change -> weights are repacked before the next forward)."""
+    state_dict = torch.load(pretrained_weights, map_location="cpu", weights_only=False)
+    if checkpoint_key is not None and checkpoint_key in state_dict:
+        state_dict = state_dict[checkpoint_key]
+    state_dict = {k.replace("module.", ""): v for k, v in state_dict.items()}
+    state_dict = {k.replace("backbone.", ""): v for k, v in state_dict.items()}
+    return model.load_state_dict(state_dict["model"], strict=False)
