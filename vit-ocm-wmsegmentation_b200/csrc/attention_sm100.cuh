@@ -17,8 +17,13 @@
 // The running maximum is only raised when a row exceeds it by more than 2^8 ("lazy rescale"): softmax
 // is shift invariant, so a stale maximum changes nothing but keeps O in TMEM untouched in the
 // common case; when it is raised the softmax warps rescale their O rows in TMEM.
-// Two CTAs are co-resident per SM (64 KB smem, 256 TMEM columns each: S 128 | O 64 | P 64) so one CTA's MMAs overlap
-// the other's exponentials.  SPLIT = true is the fp32-parity mode: every operand is a bf16
+// Two CTAs are co-resident per SM (65 KB smem, 256 TMEM columns each: S 128 | O 64 | P 64) so one CTA's MMAs overlap
+// the other's exponentials.
+// Ragged query tail ("packed" items): N = 785 leaves 17 query rows per (image, head) beyond the last full tile; a tile of
+// its own would spend a full tile's exponentials on them (1/7 of the kernel).  Instead the tails of `pack` = 4 (<= 32 rows)
+// or 2 (<= 64 rows) consecutive (image, head) pairs share ONE 128-row tile, one 32- or 64-lane slot each: the S and PV MMAs
+// are issued once per slot against that pair's own K / V with a disable-output-lane mask that leaves the other slots'
+// TMEM lanes untouched, and the softmax warps run unchanged (one thread per row, whichever pair the row belongs to).  SPLIT = true is the fp32-parity mode: every operand is a bf16
 // (hi, lo) pair and each product is hi*hi + hi*lo + lo*hi (fp32 accumulate in TMEM).
 #pragma once
 #include <type_traits>
@@ -28,8 +33,14 @@
 namespace vitocm {
 
 struct AttnArgs {
-  int n_items;       // work items = query tiles x heads x images (persistent CTAs walk them with stride gridDim.x)
-  int n_qtiles, heads;
+  int n_items;       // work items (persistent CTAs walk them with stride gridDim.x): groups of `pack` (image, head) pairs,
+                     // each group = pack x n_fullq full query tiles (tile fastest) + one tail item when N % 128 != 0
+  int n_qtiles, heads;   // n_qtiles = ceil(N / 128): rows per (image, head) of lse2 = n_qtiles * 128
+  int n_fullq;       // full 128-row query tiles per pair = N / 128
+  int pack;          // pairs sharing a tail item: 1 (the tail is an ordinary tile, or there is none), 2 or 4
+  int group_items;   // pack * n_fullq + (N % 128 != 0)
+  int n_pairs;       // images x heads
+  int mask_invert;   // diagnostics: invert the disable-output-lane masks
   int n_tokens;      // N per image (785 for 224^2 / patch 8)
   int embed_dim;     // D = H * 64
   int lo_col_off;    // SPLIT: column offset of the lo halves inside the qkv activation (= 3D)
@@ -56,7 +67,10 @@ constexpr int ATT_BKV = 128;
 constexpr int ATT_DH = 64;
 constexpr int ATT_THREADS = 256;   // warpgroup 0 = softmax (warps 0..3), warpgroup 1 = TMA (warp 4) + MMA (warp 5)
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: one [128 x 64] bf16 tile
-constexpr int ATT_RING = 3;
+#ifndef VITOCM_ATT_RING
+#define VITOCM_ATT_RING 3
+#endif
+constexpr int ATT_RING = VITOCM_ATT_RING;     // K / V tiles in flight (measured: 4 / 5 slots are 1-2 % slower, with or without packed tail items)
 constexpr int ATT_S_COL = 0;      // S: 128 columns (fp32)
 constexpr int ATT_O_COL = 128;    // O: 64 columns (fp32)
 constexpr int ATT_P_COL = 192;    // P: 64 columns of packed bf16x2 (128 keys); split mode: lo part in the next 64
@@ -69,17 +83,41 @@ struct AttnCfg {
   static constexpr int NPART = SPLIT ? 2 : 1;                     // hi (+ lo)
   static constexpr int SLOT_BYTES = ATT_TILE_BYTES * NPART;       // one K or V block
   static constexpr int Q_BYTES = ATT_TILE_BYTES * NPART;
-  static constexpr int SMEM_BYTES = Q_BYTES + ATT_RING * SLOT_BYTES + 1024 + 128;
+  static constexpr int SMEM_BYTES = Q_BYTES + ATT_RING * SLOT_BYTES + 1024 + 256;   // + alignment slack + barrier block
   static constexpr int TMEM_COLS = SPLIT ? 512 : 256;
   // setmaxnreg budgets: 2 CTAs/SM x 128 x (208 + 48) = 64 K registers (bf16); one CTA/SM in split mode
   static constexpr int REGS_SOFTMAX = SPLIT ? 240 : 208;
   static constexpr int REGS_OTHER = SPLIT ? 64 : 48;
 };
 
+// work item -> (query tile, first pair, packed?); false = the item does not exist (pair beyond the batch in the last group)
+__device__ __forceinline__ bool att_decode(const AttnArgs& a, int it, int& qt, int& pair0, bool& packed) {
+  const int grp = it / a.group_items, r = it - grp * a.group_items;
+  if (r < a.pack * a.n_fullq) {
+    const int pi = r / a.n_fullq;
+    pair0 = grp * a.pack + pi;
+    qt = r - pi * a.n_fullq;
+    packed = false;
+  } else {
+    pair0 = grp * a.pack;
+    qt = a.n_fullq;
+    packed = a.pack > 1;
+  }
+  return pair0 < a.n_pairs;
+}
+// disable-output-lane mask that leaves only slot s of nslots (2 or 4) equal lane groups writable
+__device__ __forceinline__ void att_slot_mask(int s, int nslots, int invert, uint32_t (&m)[4]) {
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const bool mine = (nslots == 4 ? w : (w >> 1)) == s;
+    m[w] = (mine != (invert != 0)) ? 0u : 0xffffffffu;
+  }
+}
+
 // POLY_MASK: bit i set = pair i of every 16 pairs of a 32-key chunk takes the FMA-pipe exp2 polynomial
 template <bool SPLIT, uint32_t POLY_MASK>
 __global__ void __launch_bounds__(ATT_THREADS, SPLIT ? 1 : 2)
-attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs args) {
+attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_q32, const AttnArgs args) {
   using Cfg = AttnCfg<SPLIT>;
   constexpr int NPART = Cfg::NPART;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -88,15 +126,16 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
   const uint32_t smem_ring = smem_q + Cfg::Q_BYTES;
   const uint32_t bars = smem_ring + ATT_RING * Cfg::SLOT_BYTES;
   const uint32_t q_full = bars;             // [1]
-  const uint32_t kv_full = bars + 8;        // [3]
-  const uint32_t kv_empty = bars + 32;      // [3]
-  const uint32_t s_full = bars + 56;        // MMA -> softmax
-  const uint32_t s_empty = bars + 64;       // softmax -> MMA   (4 warps)
-  const uint32_t p_full = bars + 72;        // softmax -> MMA   (4 warps)
-  const uint32_t o_full = bars + 80;        // MMA -> softmax
-  const uint32_t q_empty = bars + 88;       // MMA -> producer: all S MMAs of the work item retired (Q tile reusable)
-  const uint32_t o_empty = bars + 96;       // softmax -> MMA: O of the finished work item has been read (4 warps)
-  const uint32_t tmem_ptr_smem = bars + 104;
+  const uint32_t kv_full = bars + 8;        // [ATT_RING]
+  const uint32_t kv_empty = kv_full + 8 * ATT_RING;   // [ATT_RING]
+  const uint32_t s_full = kv_empty + 8 * ATT_RING;    // MMA -> softmax
+  const uint32_t s_empty = s_full + 8;      // softmax -> MMA   (4 warps)
+  const uint32_t p_full = s_full + 16;      // softmax -> MMA   (4 warps)
+  const uint32_t o_full = s_full + 24;      // MMA -> softmax
+  const uint32_t q_empty = s_full + 32;     // MMA -> producer: all S MMAs of the work item retired (Q tile reusable)
+  const uint32_t o_empty = s_full + 40;     // softmax -> MMA: O of the finished work item has been read (4 warps)
+  const uint32_t tmem_ptr_smem = s_full + 48;
+  static_assert(8 + 16 * ATT_RING + 56 <= 256, "barrier block overflows its 256 bytes");
 
   // Persistent CTA: work items (query tile, head, image), query tile fastest so that the CTAs running side by side share
   // one image-head's K / V through L2.  Barriers, the K/V ring and TMEM live across items (all phase counters run on), so
@@ -110,6 +149,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
 
   if (warp == 4 && lane == 0) {
     ptx::prefetch_tmap(&tmap_qkv);
+    ptx::prefetch_tmap(&tmap_q32);
     ptx::mbar_init(q_full, 1);
     for (int i = 0; i < ATT_RING; ++i) {
       ptx::mbar_init(kv_full + 8 * i, 1);
@@ -139,31 +179,53 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     // ===================== TMA producer =====================
     if (ptx::elect_one()) {
       int item = 0;   // K/V ring position, running across work items
-      int w = 0;
-      for (int it = blockIdx.x; it < args.n_items; it += gridDim.x, ++w) {
-      const int qt = it % args.n_qtiles, h = (it / args.n_qtiles) % args.heads, b = it / (args.n_qtiles * args.heads);
-      const int row_base = b * N;  // first row of this image in the [B*N, ld] activation
+      int w = 0;      // work items this CTA has processed
+      for (int it = blockIdx.x; it < args.n_items; it += gridDim.x) {
+      int qt, pair0;
+      bool packed;
+      if (!att_decode(args, it, qt, pair0, packed)) continue;
+      const int nslots = packed ? args.pack : 1;
+      // pair of slot s (slots beyond the batch repeat the last pair: their rows are computed and dropped)
+      auto pair_of = [&](int s) { const int pr = pair0 + s; return pr < args.n_pairs ? pr : args.n_pairs - 1; };
       ptx::mbar_wait(q_empty, (w & 1) ^ 1, 16);   // the previous item's S MMAs have retired
       ptx::mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
-      for (int part = 0; part < NPART; ++part)
-        ptx::tma_load_2d(smem_q + part * ATT_TILE_BYTES, &tmap_qkv, q_full, part * args.lo_col_off + h * ATT_DH,
-                         row_base + qt * ATT_BQ);
-      // ring order = consumption order of the MMA warp: K0, K1, V0, K2, V1, ..., V_{n-1}
-      auto load = [&](int which /*1 = K, 2 = V*/, int j) {
-        const int slot = item % ATT_RING;
-        const uint32_t parity = ((item / ATT_RING) & 1) ^ 1;
-        ptx::mbar_wait(kv_empty + 8 * slot, parity, 10);
-        ptx::mbar_arrive_expect_tx(kv_full + 8 * slot, Cfg::SLOT_BYTES);
+      if (!packed) {
+        const int b = pair0 / args.heads, h = pair0 - b * args.heads;
         for (int part = 0; part < NPART; ++part)
-          ptx::tma_load_2d(smem_ring + slot * Cfg::SLOT_BYTES + part * ATT_TILE_BYTES, &tmap_qkv, kv_full + 8 * slot,
-                           part * args.lo_col_off + which * D + h * ATT_DH, row_base + j * ATT_BKV);
-        ++item;
+          ptx::tma_load_2d(smem_q + part * ATT_TILE_BYTES, &tmap_qkv, q_full, part * args.lo_col_off + h * ATT_DH,
+                           b * N + qt * ATT_BQ);
+      } else {
+        // four 32-row boxes; slot s owns tile rows [s * 128 / nslots, (s + 1) * 128 / nslots) = the first rows of its pair's tail
+        const int per = 4 / nslots;
+        for (int part = 0; part < NPART; ++part)
+          for (int u = 0; u < 4; ++u) {
+            const int pr = pair_of(u / per);
+            const int b = pr / args.heads, h = pr - b * args.heads;
+            ptx::tma_load_2d(smem_q + part * ATT_TILE_BYTES + u * 4096, &tmap_q32, q_full, part * args.lo_col_off + h * ATT_DH,
+                             b * N + qt * ATT_BQ + (u % per) * 32);
+          }
+      }
+      // ring order = consumption order of the MMA warp: K0, K1, V0, K2, V1, ..., V_{n-1} (each entry = one tile per slot)
+      auto load = [&](int which /*1 = K, 2 = V*/, int j) {
+        for (int sl = 0; sl < nslots; ++sl) {
+          const int pr = pair_of(sl);
+          const int b = pr / args.heads, h = pr - b * args.heads;
+          const int slot = item % ATT_RING;
+          const uint32_t parity = ((item / ATT_RING) & 1) ^ 1;
+          ptx::mbar_wait(kv_empty + 8 * slot, parity, 10);
+          ptx::mbar_arrive_expect_tx(kv_full + 8 * slot, Cfg::SLOT_BYTES);
+          for (int part = 0; part < NPART; ++part)
+            ptx::tma_load_2d(smem_ring + slot * Cfg::SLOT_BYTES + part * ATT_TILE_BYTES, &tmap_qkv, kv_full + 8 * slot,
+                             part * args.lo_col_off + which * D + h * ATT_DH, b * N + j * ATT_BKV);
+          ++item;
+        }
       };
       load(1, 0);
       for (int j = 0; j < n_kv; ++j) {
         if (j + 1 < n_kv) load(1, j + 1);
         load(2, j);
       }
+      ++w;
       }
     }
   } else if (warp == 5) {
@@ -177,7 +239,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
       int item = 0;   // K/V ring position, running across work items
       int g = 0;      // KV blocks processed so far (all work items): phase counter of s_full / s_empty / p_full / o_full
       int w = 0;
-      for (int it = blockIdx.x; it < args.n_items; it += gridDim.x, ++w) {
+      for (int it = blockIdx.x; it < args.n_items; it += gridDim.x) {
+      int qt_unused, pair0_unused;
+      bool packed;
+      if (!att_decode(args, it, qt_unused, pair0_unused, packed)) continue;
+      const int nslots = packed ? args.pack : 1;
       const bool tl = tl0 && w == args.timeline_item;
       auto kv_len_mma = [&](int j) {  // keys of block j rounded up to the MMA granularity (16)
         int len = N - j * ATT_BKV;
@@ -185,33 +251,40 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
         return (len + 15) & ~15;
       };
       auto issue_s = [&](int j) {
-        const int slot = item % ATT_RING;
-        ptx::mbar_wait(kv_full + 8 * slot, (item / ATT_RING) & 1, 11);
-        ptx::tc_fence_after();
-        const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_ring + slot * Cfg::SLOT_BYTES, 1024, 0);
         const uint32_t idesc = ptx::make_idesc(ATT_BQ, kv_len_mma(j), false, false);
-        // terms: (Qhi,Khi) [, (Qhi,Klo), (Qlo,Khi)]; K-major operands advance 32 B per 16-wide k step
+#pragma unroll 1
+        for (int sl = 0; sl < nslots; ++sl) {   // packed item: one masked MMA group per slot, each against its own pair's K
+          const int slot = item % ATT_RING;
+          ptx::mbar_wait(kv_full + 8 * slot, (item / ATT_RING) & 1, 11);
+          ptx::tc_fence_after();
+          const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_ring + slot * Cfg::SLOT_BYTES, 1024, 0);
+          uint32_t lm[4];
+          att_slot_mask(sl, nslots, args.mask_invert, lm);
+          // terms: (Qhi,Khi) [, (Qhi,Klo), (Qlo,Khi)]; K-major operands advance 32 B per 16-wide k step
 #pragma unroll
-        for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
-          const uint64_t qa = ptx::desc_advance(q_desc, t == 2 ? ATT_TILE_BYTES : 0);
-          const uint64_t ka = ptx::desc_advance(k_desc, t == 1 ? ATT_TILE_BYTES : 0);
+          for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
+            const uint64_t qa = ptx::desc_advance(q_desc, t == 2 ? ATT_TILE_BYTES : 0);
+            const uint64_t ka = ptx::desc_advance(k_desc, t == 1 ? ATT_TILE_BYTES : 0);
+            if (nslots == 1) {
 #pragma unroll
-          for (int k = 0; k < ATT_DH / 16; ++k)
-            ptx::umma_bf16_ss(s_tmem, ptx::desc_advance(qa, k * 32), ptx::desc_advance(ka, k * 32), idesc, (t | k) ? 1u : 0u);
+              for (int k = 0; k < ATT_DH / 16; ++k)
+                ptx::umma_bf16_ss(s_tmem, ptx::desc_advance(qa, k * 32), ptx::desc_advance(ka, k * 32), idesc, (t | k) ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < ATT_DH / 16; ++k)
+                ptx::umma_bf16_ss_masked(s_tmem, ptx::desc_advance(qa, k * 32), ptx::desc_advance(ka, k * 32), idesc, (t | k) ? 1u : 0u, lm);
+            }
+          }
+          ptx::umma_commit(kv_empty + 8 * slot);
+          ++item;
         }
-        ptx::umma_commit(kv_empty + 8 * slot);
         ptx::umma_commit(s_full);
         att_stamp(args, tl, 1, j, 0);   // S_j issued
-        ++item;
       };
       auto issue_pv = [&](int j) {
-        const int slot = item % ATT_RING;
-        ptx::mbar_wait(kv_full + 8 * slot, (item / ATT_RING) & 1, 12);
-        ptx::tc_fence_after();
         // O accumulates across KV blocks in TMEM.
         // A = P in TMEM: 16 keys = 8 packed columns per step
         // B = V: MN-major [keys x 64]; 16 keys = two 8-row groups of 1024 B
-        const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_ring + slot * Cfg::SLOT_BYTES, 1024, 1024);
         constexpr uint32_t idesc = ptx::make_idesc(ATT_BQ, ATT_DH, false, /*B = V is MN-major*/ true);
         const int ksteps = kv_len_mma(j) / 16;
         const uint32_t acc0 = j > 0 ? 1u : 0u;
@@ -219,25 +292,38 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
           ptx::mbar_wait(o_empty, (w - 1) & 1, 17);
           ptx::tc_fence_after();
         }
-        // terms: (Phi,Vhi) [, (Phi,Vlo), (Plo,Vhi)]
-#pragma unroll
-        for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
-          const uint32_t pa = tmem_base + ATT_P_COL + (t == 2 ? 64 : 0);
-          const uint64_t va = ptx::desc_advance(v_desc, t == 1 ? ATT_TILE_BYTES : 0);
-          if (ksteps == ATT_BKV / 16) {
-#pragma unroll
-            for (int k = 0; k < ATT_BKV / 16; ++k)
-              ptx::umma_bf16_ts(o_tmem, pa + k * 8, ptx::desc_advance(va, k * 2048), idesc, (t | k) ? 1u : acc0);
-          } else {
 #pragma unroll 1
-            for (int k = 0; k < ksteps; ++k)
-              ptx::umma_bf16_ts(o_tmem, pa + k * 8, ptx::desc_advance(va, k * 2048), idesc, (t | k) ? 1u : acc0);
+        for (int sl = 0; sl < nslots; ++sl) {   // packed item: slot sl's rows of P against its own pair's V
+          const int slot = item % ATT_RING;
+          ptx::mbar_wait(kv_full + 8 * slot, (item / ATT_RING) & 1, 12);
+          ptx::tc_fence_after();
+          const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_ring + slot * Cfg::SLOT_BYTES, 1024, 1024);
+          uint32_t lm[4];
+          att_slot_mask(sl, nslots, args.mask_invert, lm);
+          // terms: (Phi,Vhi) [, (Phi,Vlo), (Plo,Vhi)]
+#pragma unroll
+          for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
+            const uint32_t pa = tmem_base + ATT_P_COL + (t == 2 ? 64 : 0);
+            const uint64_t va = ptx::desc_advance(v_desc, t == 1 ? ATT_TILE_BYTES : 0);
+            if (nslots > 1) {
+#pragma unroll 1
+              for (int k = 0; k < ksteps; ++k)
+                ptx::umma_bf16_ts_masked(o_tmem, pa + k * 8, ptx::desc_advance(va, k * 2048), idesc, (t | k) ? 1u : acc0, lm);
+            } else if (ksteps == ATT_BKV / 16) {
+#pragma unroll
+              for (int k = 0; k < ATT_BKV / 16; ++k)
+                ptx::umma_bf16_ts(o_tmem, pa + k * 8, ptx::desc_advance(va, k * 2048), idesc, (t | k) ? 1u : acc0);
+            } else {
+#pragma unroll 1
+              for (int k = 0; k < ksteps; ++k)
+                ptx::umma_bf16_ts(o_tmem, pa + k * 8, ptx::desc_advance(va, k * 2048), idesc, (t | k) ? 1u : acc0);
+            }
           }
+          ptx::umma_commit(kv_empty + 8 * slot);
+          ++item;
         }
-        ptx::umma_commit(kv_empty + 8 * slot);
         ptx::umma_commit(o_full);
         att_stamp(args, tl, 1, j, 1);   // PV_j issued
-        ++item;
       };
       ptx::mbar_wait(q_full, w & 1, 13);
       if (g > 0) ptx::mbar_wait(s_empty, (g - 1) & 1, 14);   // the previous item's last S has been read out of TMEM
@@ -255,6 +341,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
         ptx::tc_fence_after();
         issue_pv(j);
       }
+      ++w;
       }
     }
    }
@@ -268,8 +355,20 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     const uint64_t sl2_2 = ptx::dup_f32x2(sl2);
     int g = 0;                    // KV blocks processed so far (all work items): barrier phase counter
     int w = 0;
-    for (int it = blockIdx.x; it < args.n_items; it += gridDim.x, ++w) {
-    const int qt = it % args.n_qtiles, h = (it / args.n_qtiles) % args.heads, b = it / (args.n_qtiles * args.heads);
+    for (int it = blockIdx.x; it < args.n_items; it += gridDim.x) {
+    int qt, pair0;
+    bool packed;
+    if (!att_decode(args, it, qt, pair0, packed)) continue;
+    // this thread's row: tile row r of an ordinary item; in a packed item row (r % slot_rows) of the tail of pair0 + r / slot_rows
+    int my_pair = pair0, row_in_tile = r, slot_rows = ATT_BQ;
+    if (packed) {
+      slot_rows = ATT_BQ / args.pack;
+      const int sl = r / slot_rows;
+      row_in_tile = r - sl * slot_rows;
+      my_pair = pair0 + sl;
+    }
+    const bool pair_ok = my_pair < args.n_pairs;
+    const int b = my_pair / args.heads, h = my_pair - b * args.heads;
     const int row_base = b * N;
     const bool tl = tl0 && w == args.timeline_item;
     float m_used = -INFINITY;     // the row maximum the exponentials are taken against
@@ -417,9 +516,12 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     ptx::mbar_wait(o_full, (g - 1) & 1, 22);
     ptx::tc_fence_after();
     const float inv = 1.0f / l_run;
-    const int qrow = qt * ATT_BQ + r;
-    if (args.lse2 != nullptr)   // pad rows get +inf: the backward turns that into P = 0 without a bounds test
-      args.lse2[(static_cast<long long>(b) * args.heads + h) * (args.n_qtiles * ATT_BQ) + qrow] = qrow < N ? m_used * sl2 + log2f(l_run) : INFINITY;
+    const int qrow = qt * ATT_BQ + row_in_tile;
+    if (args.lse2 != nullptr && pair_ok) {   // pad rows get +inf: the backward turns that into P = 0 without a bounds test
+      float* lrow = args.lse2 + static_cast<long long>(my_pair) * (args.n_qtiles * ATT_BQ);
+      lrow[qrow] = qrow < N ? m_used * sl2 + log2f(l_run) : INFINITY;
+      for (int k = slot_rows; k < ATT_BQ; k += slot_rows) lrow[qrow + k] = INFINITY;   // packed item: the rest of the pad rows
+    }
     __nv_bfloat16* o = args.out + static_cast<long long>(row_base + qrow) * args.ldo + h * ATT_DH;
     uint32_t t[ATT_DH / 32][32];
 #pragma unroll
@@ -430,7 +532,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
     ptx::tc_fence_before();
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(o_empty);
-    if (qrow < N) {
+    if (qrow < N && pair_ok) {
 #pragma unroll
       for (int c = 0; c < ATT_DH / 32; ++c) {
 #pragma unroll
@@ -451,6 +553,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Attn
         }
       }
     }
+    ++w;
     }   // work items
   }
 

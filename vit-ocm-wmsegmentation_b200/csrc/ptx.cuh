@@ -217,6 +217,26 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same two instructions with a disable-output-lane mask: bit i of m[w] set = TMEM lane 32 w + i of D is NOT written
+// (neither overwritten nor accumulated into).  Lets several independent row groups share one 128-lane accumulator.
+__device__ __forceinline__ void umma_bf16_ss_masked(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                    uint32_t accumulate, const uint32_t (&m)[4]) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3])
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_masked(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                                    uint32_t accumulate, const uint32_t (&m)[4]) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3])
+      : "memory");
+}
 // ---- cta_group::2: the tensor cores of a CTA pair (cluster ranks 2i, 2i+1) compute one 256 x N tile; each CTA holds
 // its own 128 rows of A and HALF of the B tile (N/2 rows), the accumulator rows of each CTA live in its own TMEM.
 // Issued by one thread of the even ("leader") CTA; smem descriptors carry the same offsets in both CTAs.

@@ -451,15 +451,25 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
   const int D = e->cfg.embed_dim, H = e->cfg.num_heads;
   const long long M = static_cast<long long>(B) * N;
   ProfScope prof(PC_ATTN, st);
-  CUtensorMap tq;
+  CUtensorMap tq, tq32;
   TRY(make_tmap_bf16(&tq, qkv, M, 3LL * D * e->parts, ld, 128));
+  TRY(make_tmap_bf16(&tq32, qkv, M, 3LL * D * e->parts, ld, 32));   // 32-row boxes: the query slots of packed tail items
   AttnArgs a{};
   a.n_tokens = N; a.embed_dim = D; a.lo_col_off = 3 * D;
   a.scale_log2 = e->cfg.qk_scale * 1.44269504088896340736f;
   a.out = reinterpret_cast<__nv_bfloat16*>(ctx); a.ldo = ldo; a.out_lo_off = D; a.timeline = timeline; a.lse2 = lse2;
   { static const int tli = [] { const char* v = getenv("VITOCM_ATTN_TL_ITEM"); return v ? atoi(v) : 0; }(); a.timeline_item = tli; }
   a.n_qtiles = (N + ATT_BQ - 1) / ATT_BQ; a.heads = H;
-  const long long items = static_cast<long long>(a.n_qtiles) * H * B;
+  // ragged query tail: <= 32 rows -> 4 (image, head) pairs share one tile, <= 64 rows -> 2 (VITOCM_ATTN_PACK=0: never)
+  static const int pack_on = [] { const char* v = getenv("VITOCM_ATTN_PACK"); return v ? atoi(v) : 1; }();
+  static const int mask_inv = [] { const char* v = getenv("VITOCM_ATTN_MASK_INV"); return v ? atoi(v) : 0; }();
+  const int tail = N % ATT_BQ;
+  a.n_fullq = N / ATT_BQ;
+  a.pack = (!pack_on || tail == 0 || tail > 64) ? 1 : (tail > 32 ? 2 : 4);
+  a.group_items = a.pack * a.n_fullq + (tail != 0 ? 1 : 0);
+  a.n_pairs = B * H;
+  a.mask_invert = mask_inv;
+  const long long items = static_cast<long long>((a.n_pairs + a.pack - 1) / a.pack) * a.group_items;
   if (items > 0x7fffffffLL) return fail(VITOCM_ERR_INVALID, "attention: too many work items");
   a.n_items = static_cast<int>(items);
   // persistent CTAs: as many as are co-resident (2 per SM in bf16 mode, 1 in split mode)
@@ -468,7 +478,7 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
   const dim3 grid(persist && a.n_items > resident ? resident : a.n_items);
   auto launch = [&](auto kern, int smem_bytes, bool& attr) -> int {
     if (!attr) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); attr = true; }
-    kern<<<grid, ATT_THREADS, smem_bytes, st>>>(tq, a);
+    kern<<<grid, ATT_THREADS, smem_bytes, st>>>(tq, tq32, a);
     return 0;
   };
   // fraction of the exponentials moved from MUFU to the FMA pipe (bf16 mode): tuning knob, default from measurement
