@@ -1,0 +1,131 @@
+"""GPU (B200): BASELINE.json's FULL-SIZE configurations through size-independent properties -- the oracle cannot run
+1225 ViT-S tiles (let alone 21 025 ViT-B ones) in test time, so at these sizes the checks are: integer post stages re-derived
+exactly on the host from what the device produced, invariance to how the work is cut (chunking / tile batches), checksums of
+checksums, determinism, and sub-mosaics re-stitched by the oracle's sequential loops."""
+import numpy as np
+import pytest
+import torch
+
+import vitocm_b200 as vob
+from oracle import post_oracle as PO
+from vitocm_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _segment(arch, size, chunk, tile_batch, want=("th", "th2", "th3")):
+    torch.manual_seed(0)
+    model = getattr(vob, arch)(patch_size=8, num_classes=0, precision="bf16", chunk_tiles=chunk).cuda().eval()
+    mosaic = torch.from_numpy(syn.synthetic_mosaic_u8(size)).cuda()
+    seg = vob.MosaicSegmenter(model, window=224, stride=112, tile_batch=tile_batch)
+    return seg, mosaic, seg.segment(mosaic, want=want)
+
+
+def _check_post_stage_exactly(seg, mosaic, out, n_expected, check_blocks):
+    n, E = out["grid"], out["extent"]
+    assert n == n_expected and E == (n - 1) * 112 + 224
+    low = out["lowres"]
+    assert tuple(low.shape) == (n * n, 28, 28) and bool(torch.isfinite(low).all())
+    # per-tile min-max * 255 (SSS/sw_processing.py:253-254): every tile's map spans exactly [0, 255]
+    flat = low.reshape(n * n, -1)
+    assert float(flat.min(1).values.abs().max()) == 0.0 and float((flat.max(1).values - 255.0).abs().max()) <= 1e-4
+    # checksum of checksums: the three histograms each count every stitched pixel once
+    hists = out["hists"].cpu().numpy()
+    assert hists.shape == (3, 256) and (hists.sum(1) == E * E).all()
+    # Otsu on the device == the OpenCV scan restated by the oracle, on the device's own histograms
+    thr = out["thresholds"].cpu().numpy()
+    assert [PO.otsu_from_hist(hists[k].astype(np.int64)) for k in range(3)] == thr.tolist()
+    # the image branch is all integer: stitched gray, its histogram and mask re-derived on the host (gray crops all carry the
+    # same source pixel, so the uint8 ramp blend of equal values returns that value or one less: take it from the device)
+    gray_hist = hists[1]
+    th2 = out["th2"].cpu().numpy()
+    assert set(np.unique(th2).tolist()) <= {0, 255}
+    assert int((th2 == 255).sum()) == int(gray_hist[thr[1] + 1:].sum())
+    # the attention branch: masks are binary, and their white-pixel counts equal the histogram tails above the thresholds
+    for key, k in (("th", 0), ("th3", 2)):
+        m = out[key]
+        assert m.dtype == torch.uint8 and tuple(m.shape) == (E, E)
+        white = int((m == 255).sum())
+        assert white + int((m == 0).sum()) == E * E
+        assert white == int(hists[k][thr[k] + 1:].sum())
+    # sub-mosaics re-stitched by the oracle's sequential pairwise loops: rows / cols [S, 3S) of a 3 x 3 tile neighbourhood are
+    # covered by no tile outside it, so they must equal the device's gather formulation bit for bit
+    stitched = seg.stitched_map(low).cpu().numpy()
+    lowc = low.cpu().numpy()
+    for (i, j) in check_blocks:
+        maps = [PO.resize_linear(lowc[(i + a) * n + (j + b)], (224, 224)) for a in range(3) for b in range(3)]
+        ref = PO.concat_crops_blend(maps, 112, 224)
+        got = stitched[i * 112:i * 112 + 448, j * 112:j * 112 + 448]
+        assert np.array_equal(got[112:336, 112:336], ref[112:336, 112:336]), (i, j)
+    return stitched
+
+
+def test_config2_vit_small_4096_mosaic_full_size_properties():
+    """BASELINE configs[1]: ViT-S/8, 4096^2 mosaic, window 224 / stride 112 -> 35 x 35 = 1225 tiles, extent 4032^2, bf16."""
+    seg, mosaic, out = _segment("vit_small", 4096, 175, 175)
+    _check_post_stage_exactly(seg, mosaic, out, 35, [(0, 0), (16, 20), (32, 32), (7, 31)])
+    # invariance to how the tiles are cut into engine calls and kernel launches, and determinism (same bits)
+    seg_b, _, out_b = _segment("vit_small", 4096, 49, 64)
+    assert torch.equal(out["lowres"], out_b["lowres"])
+    for k in ("th", "th2", "th3"):
+        assert torch.equal(out[k], out_b[k])
+    out_c = seg.segment(mosaic, want=("th", "th2", "th3"))
+    assert torch.equal(out["lowres"], out_c["lowres"]) and torch.equal(out["th"], out_c["th"])
+    # the function-level mirror on the same data: utils-level threshold of the stitched map == the fused three-pass pipeline
+    stitched = seg.stitched_map(out["lowres"])
+    gray = torch.empty(out["extent"], out["extent"], dtype=torch.uint8, device="cuda")
+    from vitocm_b200._lib import check, cur_stream, ptr
+    wtab = vob.sw_processing._wtab(224, 112, gray.device)
+    check(vob._lib.load_library().vitocm_stitch_gray(ptr(mosaic), 4096, 4096, mosaic.stride(0), 35, 224, 112, ptr(wtab), 0, out["extent"],
+                                                     ptr(gray), cur_stream()))
+    th, th2, th3 = vob.sw_processing.threshold(gray.cpu().numpy(), stitched.cpu().numpy(), save=False)
+    assert np.array_equal(th, out["th"].cpu().numpy()) and np.array_equal(th3, out["th3"].cpu().numpy())
+    assert np.array_equal(th2, out["th2"].cpu().numpy())
+
+
+def test_config3_vit_base_16384_mosaic_full_size_properties():
+    """BASELINE configs[2] on one GPU: ViT-B/8, 16 384^2 mosaic -> 145 x 145 = 21 025 tiles, extent 16 352^2, bf16."""
+    seg, mosaic, out = _segment("vit_base", 16384, 175, 175)
+    _check_post_stage_exactly(seg, mosaic, out, 145, [(0, 0), (71, 100), (142, 142)])
+
+
+def test_config4_mim_step_full_size_properties():
+    """BASELINE configs[3], one GPU's share: ViT-S/8 MIM step, 32 x 224^2 tiles, bf16 forward + backward.  Linearity: every
+    image masks exactly half of its patches, so the batch loss is the mean of the two half-batch losses and the batch
+    gradient the mean of the half-batch gradients; plus finiteness, the clip invariant and one descending step."""
+    from functools import partial
+    torch.manual_seed(0)
+    enc = vob.VisionTransformerForSimMIM(patch_size=8, embed_dim=384, depth=12, num_heads=6, mlp_ratio=4, img_size=[224], qkv_bias=True,
+                                         norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), precision="bf16")
+    mim = vob.MIM(encoder=enc, encoder_stride=8).cuda().train()
+    assert sum(p.numel() for p in mim.parameters()) == 21744576          # SSS/output/log_rank0.txt:9746
+    x = syn.synthetic_tile(224, seed=77, batch=32).cuda()
+    mask = syn.random_masks(np.random.RandomState(0), 32).cuda()
+    assert int(mask.sum()) == 32 * 392
+
+    def grads(xs, ms):
+        mim.zero_grad(set_to_none=True)
+        loss, x_rec, _ = mim(xs, ms)
+        loss.sum().backward()
+        assert bool(torch.isfinite(x_rec).all())
+        return float(loss.detach()), mim._gflat.clone()
+
+    l_all, g_all = grads(x, mask)
+    l_a, g_a = grads(x[:16], mask[:16])
+    l_b, g_b = grads(x[16:], mask[16:])
+    assert np.isfinite(l_all) and bool(torch.isfinite(g_all).all())
+    assert abs(l_all - 0.5 * (l_a + l_b)) <= 1e-4 * abs(l_all)
+    want = 0.5 * (g_a + g_b)
+    rel = float((g_all - want).double().norm() / want.double().norm())
+    print(f"full-size MIM step: loss {l_all:.5f}; batch gradient vs mean of half-batch gradients: relative L2 {rel:.2e}")
+    assert rel <= 2e-3            # same kernels on the same rows; only the order of the fp32 reductions over the batch differs
+    # clip + AdamW at full size: the clipped gradient has norm max_norm and the step lowers the loss on the same batch
+    opt = vob.optimizer.FusedAdamW(mim, lr=2e-5)     # a small rate: Adam's first step is lr * sign(g) on all 21.7 M parameters
+    l0, _ = grads(x, mask)
+    gn = float(mim._gflat.double().norm())
+    total = vob.optimizer.clip_grad_norm_(mim, 0.1 * gn)
+    assert abs(float(total) - gn) <= 1e-4 * gn
+    opt.step()
+    assert abs(float(mim._gflat.double().norm()) - 0.1 * gn) <= 1e-3 * 0.1 * gn
+    l1, _ = grads(x, mask)
+    assert l1 < l0
