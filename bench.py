@@ -62,24 +62,46 @@ def mosaic_geometry(n_gpus):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    """Clocks / throttle reasons of one GPU while the timed region runs: ONE long-lived `nvidia-smi -lms 200` (the recipe's
+    clocks line) started before the warm-up -- its NVML start-up then falls outside the timed region and nothing is spawned
+    inside it -- read line by line; `open_window()` / `stop()` bracket the timed region and only samples taken inside it count.
+    Only the rank that prints the JSON line samples (enabled=False elsewhere)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.index, self.enabled = index, enabled
+        self.raw, self.samples, self.t_open, self.t_close, self.proc = [], [], None, None, None
+        if enabled:
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                              "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except Exception:
+                self.proc = None
 
     def run(self):
-        while not self.stop_flag.is_set():
+        if self.proc is None:
+            return
+        for line in self.proc.stdout:
+            line = line.strip()
+            if line:
+                self.raw.append((time.perf_counter(), [s.strip() for s in line.split(",")]))
+
+    def open_window(self):
+        self.t_open = time.perf_counter()
+
+    def stop(self):
+        self.t_close = time.perf_counter()
+        if self.proc is not None:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                self.proc.terminate()
+                self.proc.wait(timeout=3)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+        self.join(timeout=3)
+        inside = [v for t, v in self.raw if self.t_open is not None and self.t_open <= t <= self.t_close]
+        self.samples = inside if inside else [v for _, v in self.raw[-2:]]   # a region shorter than one sampling period
 
     def summary(self):
         sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
@@ -251,11 +273,14 @@ def main_mim(args):
         opt.step()
         return loss
 
-    for i in range(args.warmup):
-        train_step(xs_dev[i % n_host], ms_dev[i % n_host])
-    barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, enabled=rank == 0)
     sampler.start()
+    for i in range(args.warmup):          # same cadence as the timed iterations (flush, barrier, step, barrier): the power-cap
+        flush.fill_(1)                    # controller then enters the timed region in its steady state
+        barrier()
+        train_step(xs_dev[i % n_host], ms_dev[i % n_host])
+        barrier()
+    sampler.open_window()
     launches0 = vob._lib.launch_count()
     step_ms = []
     for i in range(args.steps):
@@ -268,8 +293,7 @@ def main_mim(args):
         barrier()
         step_ms.append(e0.elapsed_time(e1))
     launches = vob._lib.launch_count() - launches0
-    sampler.stop_flag.set()
-    sampler.join(timeout=3)
+    sampler.stop()
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
@@ -331,7 +355,7 @@ def main_mim(args):
     step_tflops = mim_flops_per_image(D, depth, a["num_heads"], N) * Bg / 1e12 / (ms_per_step / 1e3)
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "ms_per_step": ms_per_step, "step_ms_rank0": [round(v, 3) for v in step_ms], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"MIM pre-training step (SimMIM masked patches), vit_small/8, 224^2 synthetic tiles, batch {Bg} per GPU = {Bg * world} global, "
                                        "bf16 fwd+bwd, fp32 master weights + fused clip/AdamW, NCCL all-reduce(SUM) of the flat gradient",
                            "batch_per_gpu": Bg, "global_batch": Bg * world, "weights": "random init (seed 0)",
@@ -410,11 +434,14 @@ def main():
     def step_device():
         return seg.segment(mosaic, want=("th", "th3"), gather=True)
 
-    for _ in range(args.warmup):
-        out = step_device()
-    barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, enabled=rank == 0)
     sampler.start()
+    for _ in range(args.warmup):          # same cadence as the timed iterations (flush, barrier, step, barrier): the power-cap
+        flush.fill_(1)                    # controller then enters the timed region in its steady state
+        barrier()
+        out = step_device()
+        barrier()
+    sampler.open_window()
     launches0 = vob._lib.launch_count()
     step_ms = []
     barrier()
@@ -428,8 +455,7 @@ def main():
         barrier()
         step_ms.append(e0.elapsed_time(e1))
     launches = vob._lib.launch_count() - launches0
-    sampler.stop_flag.set()
-    sampler.join(timeout=3)
+    sampler.stop()
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
@@ -496,7 +522,7 @@ def main():
     line = None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "step_ms_rank0": [round(v, 3) for v in step_ms], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": f"{args.arch}/8 sliding-window segmentation, {size}x{size} gray mosaic, window {WINDOW}, stride {STRIDE}, "
                                        f"{T} tiles, extent {extent}^2", "tiles": T, "tiles_per_gpu": my_tiles, "weights": "random init (seed 0)",
