@@ -146,6 +146,10 @@ int vitocm_head_mean(const float* rows, float* lowres, int T, int heads, int n_t
  * img_in [T][S][S] u8 (optional): the PIL "L" image, used instead of deriving it from x. */
 int vitocm_tile_threshold(const float* lowres, const float* x, int T, int C, int S, int lh, int lw, uint8_t* masks,
                           int* thresholds, float* att_out, const float* att_in, const uint8_t* img_in, void* stream);
+/* The same with the two images utils.threshold also writes out (SSS/utils.py:77-81, saved at :107-108): aux [T][2][S][S] u8 =
+ * (result = the 0.6 / 0.4 image / attention blend "weighted_iamge_attention.png", att_u8 = the normalised attention * 255). */
+int vitocm_tile_threshold_aux(const float* lowres, const float* x, int T, int C, int S, int lh, int lw, uint8_t* masks,
+                              int* thresholds, float* att_out, const float* att_in, const uint8_t* img_in, uint8_t* aux, void* stream);
 
 /* sliding_window (SSS/sw_processing.py:151-163) + ToTensor for tiles t0..t0+T-1 of an n x n grid:
  * mosaic u8 gray [mos_h][pitch] -> x [T][C][W][W] fp32. */
@@ -182,6 +186,12 @@ int vitocm_otsu(const uint64_t* hists, int nhist, int* thresholds, void* stream)
 int vitocm_stitch_mask(const float* lowres, int n, int W, int S, int lh, int lw, const double* wtab,
                        const uint8_t* gray, const int* minmax_ord, const int* thr, int y_begin, int y_end, uint8_t* th,
                        uint8_t* th2, uint8_t* th3, const float* map_in, void* stream);
+
+/* The weighted image of the mosaic flavour, result = (img * att / max(att)).astype(u8) (SSS/sw_processing.py:44-46, saved as
+ * "weighted_iamge_attention.png" at :75), and att_u8 (:47-48) for rows [y_begin, y_end): each [(y_end-y_begin)][E] u8 or NULL. */
+int vitocm_stitch_result(const float* lowres, int n, int W, int S, int lh, int lw, const double* wtab, const uint8_t* gray,
+                         const int* minmax_ord, int y_begin, int y_end, uint8_t* result, uint8_t* att_u8, const float* map_in,
+                         void* stream);
 
 /* concat_crops(crops, stride, window_size) (SSS/sw_processing.py:113-149) on full-resolution crops:
  * float32 [n*n][W][W] -> out [E][E]; uint8 HWC [n*n][W][W][C] -> out [E][E][C]. */

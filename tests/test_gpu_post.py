@@ -49,6 +49,21 @@ def test_threshold_flavours_bit_exact():
         assert all(np.array_equal(a, b) for a, b in zip(got, exp[:3]))
 
 
+def test_threshold_saves_the_reference_files_bit_exact(tmp_path):
+    """save=True writes the reference's five PNGs (SSS/utils.py:102-114, SSS/sw_processing.py:68-80); the masks,
+    the weighted image `result` and the normalised attention read back from disk equal the oracle's arrays."""
+    from PIL import Image
+    g = load_golden("threshold.npz")
+    for fn, orc, sub in ((vu.threshold, PO.threshold_utils, "ut"), (sw.threshold, PO.threshold_sw, "sw")):
+        out = tmp_path / sub
+        fn(g["img"], g["att"], output_directory=str(out), save=True, name="case")
+        th, th2, th3, result, att_u8 = orc(g["img"], g["att"])
+        files = {"case/OTSU_th_average.png": th, "OTSU_th_original.png": th2, "weighted_iamge_attention.png": result,
+                 "heatmap_otsu_attention.png": th3, "temp.png": att_u8}
+        for rel, want in files.items():
+            assert np.array_equal(np.array(Image.open(out / rel)), want), (sub, rel)
+
+
 @pytest.mark.parametrize("name,W,S,n", [("w32s16n4", 32, 16, 4), ("w48s16n3", 48, 16, 3), ("w24s8n5", 24, 8, 5), ("w32s16n1", 32, 16, 1)])
 def test_concat_crops_and_sliding_window_bit_exact(name, W, S, n):
     g = load_golden("stitch.npz")

@@ -47,6 +47,10 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p]),
     "vitocm_extract_tiles": (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                      c_void_p]),
+    "vitocm_tile_threshold_aux": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vitocm_stitch_result": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "vitocm_stitch_gray": (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
                                    c_void_p]),
     "vitocm_minmax_init": (c_int, [c_void_p, c_void_p]),

@@ -130,7 +130,8 @@ tile_threshold_kernel(const float* __restrict__ lowres /*[T][lh][lw]*/, const fl
                       int C, int S, int lh, int lw, uint8_t* __restrict__ masks /*[T][3][S][S]*/,
                       int* __restrict__ thresholds /*[T][3]*/, float* __restrict__ att_out /*[T][S][S] or null*/,
                       const float* __restrict__ att_in /*[T][S][S] or null: use instead of upsampling lowres*/,
-                      const uint8_t* __restrict__ img_in /*[T][S][S] or null: use instead of deriving from x*/) {
+                      const uint8_t* __restrict__ img_in /*[T][S][S] or null: use instead of deriving from x*/,
+                      uint8_t* __restrict__ aux /*[T][2][S][S] or null: the blended image `result` and att_u8 (the images utils.threshold saves)*/) {
   __shared__ float red_mn[16], red_mx[16];
   __shared__ unsigned int hist[3][256];
   __shared__ unsigned long long hist64[256];
@@ -193,6 +194,10 @@ tile_threshold_kernel(const float* __restrict__ lowres /*[T][lh][lw]*/, const fl
     m0[i] = res > thr[0] ? 255 : 0;
     m0[plane + i] = img > thr[1] ? 255 : 0;
     m0[2 * plane + i] = au > thr[2] ? 255 : 0;
+    if (aux != nullptr) {
+      aux[static_cast<long long>(t) * 2 * plane + i] = static_cast<uint8_t>(res);
+      aux[static_cast<long long>(t) * 2 * plane + plane + i] = static_cast<uint8_t>(au);
+    }
   }
 }
 
@@ -513,6 +518,28 @@ stitch_mask_kernel(const float* __restrict__ lowres, StitchGeom g, const double*
     if (th != nullptr) th[idx] = res > t0 ? 255 : 0;
     if (th2 != nullptr) th2[idx] = img > t1 ? 255 : 0;
     if (th3 != nullptr) th3[idx] = au > t2 ? 255 : 0;
+  }
+}
+
+// the weighted image `result = (img * att / max(att)).astype(u8)` of the mosaic flavour (SSS/sw_processing.py:44-46, the
+// "weighted_iamge_attention.png" it saves at :75) and att_u8, for rows [y_begin, y_end)
+__global__ void __launch_bounds__(256)
+stitch_result_kernel(const float* __restrict__ lowres, StitchGeom g, const double* __restrict__ wtab, const uint8_t* __restrict__ gray,
+                     const int* __restrict__ minmax_ord, int y_begin, int y_end, uint8_t* __restrict__ result, uint8_t* __restrict__ att_u8,
+                     const float* __restrict__ map_in) {
+  const float mn = ord2f(minmax_ord[0]), mx = ord2f(minmax_ord[1]);
+  const bool flat = (mx == mn);
+  const float range = __fsub_rn(mx, mn);
+  const float att_max = flat ? mx : 1.0f;
+  const long long total = static_cast<long long>(y_end - y_begin) * g.E;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int Y = y_begin + static_cast<int>(idx / g.E), X = static_cast<int>(idx % g.E);
+    const float v = map_in != nullptr ? map_in[static_cast<long long>(Y) * g.E + X] : stitched_value(lowres, g, wtab, Y, X);
+    int res, au;
+    sw_classify(v, mn, range, flat, att_max, gray[static_cast<long long>(Y) * g.E + X], res, au);
+    if (result != nullptr) result[idx] = static_cast<uint8_t>(res);
+    if (att_u8 != nullptr) att_u8[idx] = static_cast<uint8_t>(au);
   }
 }
 

@@ -1036,7 +1036,18 @@ int vitocm_tile_threshold(const float* lowres, const float* x, int T, int C, int
   if (lowres == nullptr && att_in == nullptr) return fail(VITOCM_ERR_INVALID, "tile_threshold needs lowres or att_in");
   if (x == nullptr && img_in == nullptr) return fail(VITOCM_ERR_INVALID, "tile_threshold needs x or img_in");
   ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
-  tile_threshold_kernel<<<T, 512, 0, static_cast<cudaStream_t>(stream)>>>(lowres, x, C, S, lh, lw, masks, thresholds, att_out, att_in, img_in);
+  tile_threshold_kernel<<<T, 512, 0, static_cast<cudaStream_t>(stream)>>>(lowres, x, C, S, lh, lw, masks, thresholds, att_out, att_in, img_in, nullptr);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int vitocm_tile_threshold_aux(const float* lowres, const float* x, int T, int C, int S, int lh, int lw, uint8_t* masks,
+                              int* thresholds, float* att_out, const float* att_in, const uint8_t* img_in, uint8_t* aux, void* stream) {
+  if (T <= 0) return 0;
+  if (lowres == nullptr && att_in == nullptr) return fail(VITOCM_ERR_INVALID, "tile_threshold needs lowres or att_in");
+  if (x == nullptr && img_in == nullptr) return fail(VITOCM_ERR_INVALID, "tile_threshold needs x or img_in");
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
+  tile_threshold_kernel<<<T, 512, 0, static_cast<cudaStream_t>(stream)>>>(lowres, x, C, S, lh, lw, masks, thresholds, att_out, att_in, img_in, aux);
   LAUNCH_CHECK();
   return 0;
 }
@@ -1129,6 +1140,18 @@ int vitocm_stitch_mask(const float* lowres, int n, int W, int S, int lh, int lw,
   ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
   stitch_mask_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       lowres, g, wtab, gray, minmax_ord, thr, y_begin, y_end, th, th2, th3, map_in);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int vitocm_stitch_result(const float* lowres, int n, int W, int S, int lh, int lw, const double* wtab, const uint8_t* gray,
+                         const int* minmax_ord, int y_begin, int y_end, uint8_t* result, uint8_t* att_u8, const float* map_in, void* stream) {
+  TRY(check_geom(n, W, S, y_begin, y_end));
+  if (y_end == y_begin) return 0;
+  const StitchGeom g = make_geom(n, W, S, lh, lw);
+  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
+  stitch_result_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      lowres, g, wtab, gray, minmax_ord, y_begin, y_end, result, att_u8, map_in);
   LAUNCH_CHECK();
   return 0;
 }

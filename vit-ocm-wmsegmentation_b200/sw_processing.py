@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from ._lib import check, cur_stream, ptr
-from .utils import _dev, _save_gray, head_mean_maps
+from .utils import _dev, _save_threshold_images, head_mean_maps
 
 
 def _wtab(window_size: int, stride: int, device) -> torch.Tensor:
@@ -124,15 +124,15 @@ def threshold(img, attention, output_directory="", save=True, name=None):
     # geometry with a single "tile" covering the whole extent: n=1, W=E (S only has to be < W)
     geom = (1, E, E - 1 if E > 1 else 1, 1, 1)
     wtab = torch.zeros(max(E - geom[2], 1), dtype=torch.float64, device=dev)
-    masks, thr, _, _ = _threshold_device(_lib.load_library(), None, geom, wtab, gray, amap, 0, E, want=("th", "th2", "th3"))
+    lib = _lib.load_library()
+    masks, thr, minmax, _ = _threshold_device(lib, None, geom, wtab, gray, amap, 0, E, want=("th", "th2", "th3"))
     th, th2, th3 = (masks[k].cpu().numpy() for k in ("th", "th2", "th3"))
     if save:
-        import os
-        sub = (name + "/") if name is not None else ""
-        os.makedirs(os.path.join(output_directory, sub) or ".", exist_ok=True)
-        _save_gray(os.path.join(output_directory, sub, "OTSU_th_average.png"), th)
-        _save_gray(os.path.join(output_directory, "OTSU_th_original.png"), th2)
-        _save_gray(os.path.join(output_directory, "heatmap_otsu_attention.png"), th3)
+        result = torch.empty(E, E, dtype=torch.uint8, device=dev)
+        att_u8 = torch.empty(E, E, dtype=torch.uint8, device=dev)
+        check(lib.vitocm_stitch_result(None, geom[0], geom[1], geom[2], geom[3], geom[4], ptr(wtab), ptr(gray), ptr(minmax), 0, E,
+                                       ptr(result), ptr(att_u8), ptr(amap), cur_stream()))
+        _save_threshold_images(output_directory, name, th, th2, th3, result.cpu().numpy(), att_u8.cpu().numpy())
     return th, th2, th3
 
 

@@ -57,6 +57,18 @@ def _save_gray(path, arr):
     Image.fromarray(np.asarray(arr, dtype=np.uint8)).save(path)
 
 
+def _save_threshold_images(output_directory, name, th, th2, th3, result, att_u8):
+    """The five files of SSS/utils.py:102-114 (= SSS/sw_processing.py:68-80), same names and places.  `temp.png` is the
+    normalised attention as a gray image (the reference sends the float map through matplotlib's default colour map)."""
+    sub = (name + "/") if name is not None else ""
+    os.makedirs(os.path.join(output_directory, sub) or ".", exist_ok=True)
+    _save_gray(os.path.join(output_directory, sub, "OTSU_th_average.png"), th)
+    _save_gray(os.path.join(output_directory, "OTSU_th_original.png"), th2)
+    _save_gray(os.path.join(output_directory, "weighted_iamge_attention.png"), result)
+    _save_gray(os.path.join(output_directory, "heatmap_otsu_attention.png"), th3)
+    _save_gray(os.path.join(output_directory, "temp.png"), att_u8)
+
+
 def threshold(img, attention, output_directory="", save=True, name=None):
     """SSS/utils.py:62-115.  img: PIL "L" image or uint8 array [S, S]; attention: float array [S, S].
     Returns (th, th2, th3) uint8 {0,255} host arrays: Otsu of the 0.6/0.4 image/attention blend
@@ -71,15 +83,12 @@ def threshold(img, attention, output_directory="", save=True, name=None):
     d_att = torch.from_numpy(att_np).to(dev)
     masks = torch.empty(1, 3, S, S, dtype=torch.uint8, device=dev)
     thr = torch.empty(1, 3, dtype=torch.int32, device=dev)
-    check(_lib.load_library().vitocm_tile_threshold(None, None, 1, 1, S, 1, 1, ptr(masks), ptr(thr), None, ptr(d_att),
-                                                    ptr(d_img), cur_stream()))
+    aux = torch.empty(1, 2, S, S, dtype=torch.uint8, device=dev) if save else None
+    check(_lib.load_library().vitocm_tile_threshold_aux(None, None, 1, 1, S, 1, 1, ptr(masks), ptr(thr), None, ptr(d_att),
+                                                        ptr(d_img), ptr(aux), cur_stream()))
     th, th2, th3 = (m.cpu().numpy() for m in masks[0])
     if save:
-        sub = (name + "/") if name is not None else ""
-        os.makedirs(os.path.join(output_directory, sub) or ".", exist_ok=True)
-        _save_gray(os.path.join(output_directory, sub, "OTSU_th_average.png"), th)
-        _save_gray(os.path.join(output_directory, "OTSU_th_original.png"), th2)
-        _save_gray(os.path.join(output_directory, "heatmap_otsu_attention.png"), th3)
+        _save_threshold_images(output_directory, name, th, th2, th3, aux[0, 0].cpu().numpy(), aux[0, 1].cpu().numpy())
     return th, th2, th3
 
 
