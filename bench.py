@@ -388,6 +388,7 @@ def main():
     ap.add_argument("--chunk-tiles", type=int, default=175)
     ap.add_argument("--tile-batch", type=int, default=175)
     ap.add_argument("--lanes", type=int, default=1, help="chunks in flight on concurrent streams")
+    ap.add_argument("--ingest", default="direct", choices=["direct", "crops"], help="segmentation: tiles read out of the uint8 mosaic by the patch embedding, or fp32 crops cut first")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="segmentation", choices=["segmentation", "mim_train"],
                     help="segmentation = BASELINE.json configs[1] (the headline); mim_train = configs[3] (MIM pre-training step)")
@@ -423,7 +424,7 @@ def main():
     N = (WINDOW // PATCH) ** 2 + 1
     mosaic_host = torch.from_numpy(SY.synthetic_mosaic_u8(size, seed=4321)).pin_memory()
     mosaic = mosaic_host.to(dev)
-    seg = vob.MosaicSegmenter(model, window=WINDOW, stride=STRIDE, tile_batch=args.tile_batch, group=group)
+    seg = vob.MosaicSegmenter(model, window=WINDOW, stride=STRIDE, tile_batch=args.tile_batch, group=group, ingest=args.ingest)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():

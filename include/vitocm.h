@@ -96,6 +96,13 @@ int vitocm_forward_cls_attn(vitocm_engine* e, const float* x, int B, int H, int 
  * tiles are a third of the bytes; same arithmetic up to fp32 summation order. */
 int vitocm_forward_cls_attn_gray(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, float* out_rows,
                                  void* ws, size_t ws_bytes, int chunk_tiles, void* stream);
+/* The same with the tiles cut straight out of a gray uint8 mosaic by the patch-embedding producer -- sliding_window + ToTensor
+ * (SSS/sw_processing.py:151-163, :236) without materialised crops: tile t0 + i (i < T) is the W x W window of the n x n grid at
+ * stride S, origin ((t / n) * S, (t % n) * S), pixel value v / 255, zero beyond the mosaic (PIL's crop).  mosaic [mos_h][pitch]
+ * device memory; out_rows [T][heads][N]. */
+int vitocm_forward_cls_attn_mosaic(vitocm_engine* e, const uint8_t* mosaic, int mos_h, int mos_w, int64_t pitch, int n, int W, int S,
+                                   int t0, int T, const float* pos, float* out_rows, void* ws, size_t ws_bytes, int chunk_tiles,
+                                   void* stream);
 
 /* The same forward for a LIST of query tokens (SSS/analyse_attention.py:183-247: compute_attention(..., query=q) for a
  * region query) and, optionally, the last block's K features (SSS/analyse_attention.py:139-163, SSS/eval.py:186-202, the

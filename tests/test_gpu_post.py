@@ -231,3 +231,33 @@ def test_cropped_evaluation_path_matches_reference_goldens(name):
             assert np.array_equal(masks[b, k], o_th[k])
             assert float((masks[b, k] == g[f"{name}/masks"][b, k]).mean()) >= 0.999
         assert np.abs(att[b] - g[f"{name}/attention"][b]).max() <= 1e-3 * np.abs(g[f"{name}/attention"][b]).max()
+
+
+def test_direct_mosaic_ingest_equals_materialised_crops_bit_for_bit():
+    """the patch-embedding producer cuts its tiles out of the uint8 mosaic (v / 255 by a correctly rounded
+    reciprocal product, zero beyond the mosaic) -- same CLS rows, bit for bit, as fp32 crops cut by vitocm_extract_tiles, on an
+    aligned mosaic, a ragged one (windows hanging over the edge, odd pitch) and a row-strided view; all 256 byte values occur."""
+    tiny = VO.ViTConfig(embed_dim=128, depth=2, num_heads=2, patch_size=8, img_size=32)
+    sd = VO.randomize_affine(VO.init_state_dict(tiny, seed=21), seed=22)
+    m = build_model(tiny, sd, "bf16", chunk_tiles=5)
+    rng = np.random.RandomState(3)
+    lib = vob._lib.load_library()
+    for size, W, S, view in ((112, 32, 16, False), (101, 32, 16, False), (67, 24, 8, False), (96, 32, 16, True)):
+        base = rng.randint(0, 256, (size, size + (13 if view else 0))).astype(np.uint8)
+        base.flat[:256] = np.arange(256, dtype=np.uint8)
+        full = torch.from_numpy(base).cuda()
+        mosaic = full[:, 5:5 + size] if view else full            # a view: column offset 5 breaks the 8-byte alignment, pitch != width
+        n = vob.grid_size(size, S)
+        T = n * n
+        x = torch.empty(T, 1, W, W, device="cuda")
+        check(lib.vitocm_extract_tiles(mosaic.data_ptr(), size, size, mosaic.stride(0), n, W, S, 0, T, 1, ptr(x), cur_stream()))
+        want = m.cls_attention_rows(x)
+        got = m.cls_attention_rows_mosaic(mosaic, n, W, S, 0, T)
+        assert torch.equal(got, want), (size, W, S, view)
+        part = m.cls_attention_rows_mosaic(mosaic, n, W, S, 3, T - 4)         # a sub-range of the windows
+        assert torch.equal(part, want[3:T - 1])
+    seg_a = vob.MosaicSegmenter(m, window=32, stride=16, tile_batch=7, ingest="direct")
+    seg_b = vob.MosaicSegmenter(m, window=32, stride=16, tile_batch=7, ingest="crops")
+    mos = torch.from_numpy(VO.synthetic_mosaic_u8(100, seed=5)).cuda()
+    a, b = seg_a.segment(mos), seg_b.segment(mos)
+    assert torch.equal(a["lowres"], b["lowres"]) and torch.equal(a["th"], b["th"]) and torch.equal(a["th3"], b["th3"])

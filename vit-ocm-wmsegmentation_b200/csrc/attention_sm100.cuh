@@ -40,7 +40,6 @@ struct AttnArgs {
   int pack;          // pairs sharing a tail item: 1 (the tail is an ordinary tile, or there is none), 2 or 4
   int group_items;   // pack * n_fullq + (N % 128 != 0)
   int n_pairs;       // images x heads
-  int mask_invert;   // diagnostics: invert the disable-output-lane masks
   int n_tokens;      // N per image (785 for 224^2 / patch 8)
   int embed_dim;     // D = H * 64
   int lo_col_off;    // SPLIT: column offset of the lo halves inside the qkv activation (= 3D)
@@ -106,12 +105,9 @@ __device__ __forceinline__ bool att_decode(const AttnArgs& a, int it, int& qt, i
   return pair0 < a.n_pairs;
 }
 // disable-output-lane mask that leaves only slot s of nslots (2 or 4) equal lane groups writable
-__device__ __forceinline__ void att_slot_mask(int s, int nslots, int invert, uint32_t (&m)[4]) {
+__device__ __forceinline__ void att_slot_mask(int s, int nslots, uint32_t (&m)[4]) {
 #pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    const bool mine = (nslots == 4 ? w : (w >> 1)) == s;
-    m[w] = (mine != (invert != 0)) ? 0u : 0xffffffffu;
-  }
+  for (int w = 0; w < 4; ++w) m[w] = ((nslots == 4 ? w : (w >> 1)) == s) ? 0u : 0xffffffffu;   // set bit = lane not written
 }
 
 // POLY_MASK: bit i set = pair i of every 16 pairs of a 32-key chunk takes the FMA-pipe exp2 polynomial
@@ -259,7 +255,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           ptx::tc_fence_after();
           const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_ring + slot * Cfg::SLOT_BYTES, 1024, 0);
           uint32_t lm[4];
-          att_slot_mask(sl, nslots, args.mask_invert, lm);
+          att_slot_mask(sl, nslots, lm);
           // terms: (Qhi,Khi) [, (Qhi,Klo), (Qlo,Khi)]; K-major operands advance 32 B per 16-wide k step
 #pragma unroll
           for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
@@ -299,7 +295,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           ptx::tc_fence_after();
           const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_ring + slot * Cfg::SLOT_BYTES, 1024, 1024);
           uint32_t lm[4];
-          att_slot_mask(sl, nslots, args.mask_invert, lm);
+          att_slot_mask(sl, nslots, lm);
           // terms: (Phi,Vhi) [, (Phi,Vlo), (Plo,Vhi)]
 #pragma unroll
           for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {

@@ -60,6 +60,11 @@ struct GemmArgs {
   const float* pos;         // [1 + n_patches][N] position table
   const float* mask;        // [B][n_patches] in {0,1} or nullptr (SimMIM mask-token mixing, SSS/model.py:31-33)
   const float* mask_token;  // [N]
+  // A_PATCH, tile ingest straight from a gray uint8 mosaic (sliding_window + ToTensor, SSS/sw_processing.py:151-163, :236): image b of
+  // this launch is window mos_t0 + b of the n x n grid at stride mos_S, pixel value v / 255, zero beyond the mosaic; img is unused
+  const uint8_t* mos;       // [mos_h][mos_pitch] or nullptr
+  long long mos_pitch;
+  int mos_h, mos_w, mos_n, mos_S, mos_t0;
   float* out_f32;           // X [B][1 + n_patches][N] token stream
   // EPI_DGELU_BF16 only: the GELU's input saved by the forward fc1 epilogue, bf16 [M][ld_pre]
   const __nv_bfloat16* pre;
@@ -128,6 +133,15 @@ struct GemmCfg {
   }
   static constexpr int res_smem_bytes(int kblocks) { return res_stages(kblocks) * A_BYTES + kblocks * B_BYTES + FIXED_BYTES; }
 };
+
+// v / 255 for an 8-bit value, correctly rounded (== __fdiv_rn(v, 255.f), the ToTensor arithmetic) without the division: one
+// residual-correction step on the reciprocal product is exact for all 256 inputs (checked exhaustively, tests/test_gpu_post.py)
+__device__ __forceinline__ float u8_unit(uint32_t b) {
+  constexpr float R = 1.0f / 255.0f;
+  const float v = static_cast<float>(b);
+  const float q = __fmul_rn(v, R);
+  return __fmaf_rn(__fmaf_rn(-q, 255.0f, v), R, q);
+}
 
 __device__ __forceinline__ float gelu_erf(float x) {
   // nn.GELU() default (approximate='none'): x * Phi(x)
@@ -381,7 +395,55 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1, 5);
           const uint32_t a_tile = smem_a + stage * Cfg::A_BYTES;
           // 4 items per thread: all 8 loads are issued before the first conversion so that their latencies overlap
-          {
+          if (args.mos != nullptr) {   // gray uint8 mosaic: 8 pixels = 8 bytes of one mosaic row
+            uint2 raw[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int item = t + 256 * u;
+              const int chunk = item >> 7;
+              const int row = item & 127;
+              const int m = m0 + row;
+              raw[u] = make_uint2(0u, 0u);
+              if (m < args.M) {
+                const int b = m / args.n_patches, i = m - b * args.n_patches;
+                const int py = i / Wp, px = i - py * Wp;
+                const int k = kb * GEMM_BK + chunk * 8;      // one channel: k = yi * p + xi
+                const int yi = k / p, xi = k - yi * p;
+                const int tl = args.mos_t0 + b;
+                const int gy = (tl / args.mos_n) * args.mos_S + py * p + yi;
+                const int gx = (tl % args.mos_n) * args.mos_S + px * p + xi;
+                if (gy < args.mos_h && gx < args.mos_w) {
+                  const uint8_t* src = args.mos + static_cast<long long>(gy) * args.mos_pitch + gx;
+                  if (gx + 8 <= args.mos_w && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+                    raw[u] = __ldg(reinterpret_cast<const uint2*>(src));
+                  } else {
+                    unsigned long long acc = 0ull;
+                    for (int j = 0; j < 8; ++j)
+                      if (gx + j < args.mos_w) acc |= static_cast<unsigned long long>(__ldg(src + j)) << (8 * j);
+                    raw[u] = make_uint2(static_cast<uint32_t>(acc), static_cast<uint32_t>(acc >> 32));
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int item = t + 256 * u;
+              const int chunk = item >> 7;
+              const int row = item & 127;
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[j] = u8_unit((raw[u].x >> (8 * j)) & 0xffu);
+                v[4 + j] = u8_unit((raw[u].y >> (8 * j)) & 0xffu);
+              }
+              if (want_lo) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] -= ptx::bf16_round(v[j]);
+              }
+              ptx::sts_v4(a_tile + row * 128 + ((chunk ^ (row & 7)) << 4), ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]),
+                          ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+            }
+          } else {
             float4 f[4][2];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {

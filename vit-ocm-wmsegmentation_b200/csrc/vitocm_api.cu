@@ -462,13 +462,11 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
   a.n_qtiles = (N + ATT_BQ - 1) / ATT_BQ; a.heads = H;
   // ragged query tail: <= 32 rows -> 4 (image, head) pairs share one tile, <= 64 rows -> 2 (VITOCM_ATTN_PACK=0: never)
   static const int pack_on = [] { const char* v = getenv("VITOCM_ATTN_PACK"); return v ? atoi(v) : 1; }();
-  static const int mask_inv = [] { const char* v = getenv("VITOCM_ATTN_MASK_INV"); return v ? atoi(v) : 0; }();
   const int tail = N % ATT_BQ;
   a.n_fullq = N / ATT_BQ;
   a.pack = (!pack_on || tail == 0 || tail > 64) ? 1 : (tail > 32 ? 2 : 4);
   a.group_items = a.pack * a.n_fullq + (tail != 0 ? 1 : 0);
   a.n_pairs = B * H;
-  a.mask_invert = mask_inv;
   const long long items = static_cast<long long>((a.n_pairs + a.pack - 1) / a.pack) * a.group_items;
   if (items > 0x7fffffffLL) return fail(VITOCM_ERR_INVALID, "attention: too many work items");
   a.n_items = static_cast<int>(items);
@@ -509,16 +507,25 @@ int run_layernorm(const float* X, const float* g, const float* b, void* out_bf16
 }
 
 // prepare_tokens (vit.py:198-209) as an im2col-free tcgen05 GEMM: M = B * n patches, K = C p^2, N = D.
+// tiles cut straight out of a gray uint8 mosaic by the patch-embedding producer (GemmArgs::mos)
+struct MosaicSrc {
+  const uint8_t* p;
+  long long pitch;
+  int h, w, n, S, t0;
+};
+
 int run_patch_embed(const vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const float* mask,
-                    float* X, cudaStream_t st, bool gray = false) {
+                    float* X, cudaStream_t st, bool gray = false, const MosaicSrc* mos = nullptr) {
   // gray: x is [B][1][H][W], standing for an image with equal channels; the channel-folded filter does the same arithmetic
   const int p = e->cfg.patch_size, C = gray ? 1 : e->cfg.in_chans, D = e->cfg.embed_dim;
   if (gray && e->patch_w_gray.p == nullptr) return fail(VITOCM_ERR_STATE, "gray fast path needs in_chans > 1");
   if (H % p != 0 || W % p != 0) return fail(VITOCM_ERR_INVALID, "image %dx%d not a multiple of patch %d", H, W, p);
   const int K = C * p * p;
   if (p % 8 != 0 || K % GEMM_BK != 0) return fail(VITOCM_ERR_INVALID, "patch embedding needs patch %% 8 == 0 and C*p*p %% 64 == 0 (patch %d, chans %d)", p, C);
-  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(pos) & 15) != 0)
+  if ((mos == nullptr && (reinterpret_cast<uintptr_t>(x) & 15) != 0) || (reinterpret_cast<uintptr_t>(pos) & 15) != 0)
     return fail(VITOCM_ERR_INVALID, "patch embedding inputs must be 16-byte aligned");
+  if (mos != nullptr && (!gray || mos->p == nullptr || mos->n < 1 || mos->S < 1))
+    return fail(VITOCM_ERR_INVALID, "mosaic ingest needs the gray path and a valid window grid");
   const float* mask_token = e->w("mask_token");
   if (mask != nullptr && mask_token == nullptr) return fail(VITOCM_ERR_STATE, "mask given but mask_token was never loaded");
   const int n = (H / p) * (W / p);
@@ -533,6 +540,7 @@ int run_patch_embed(const vitocm_engine* e, const float* x, int B, int H, int W,
   a.M = M; a.N = D; a.kblocks = K / GEMM_BK; a.nterms = 3; a.lo_k = K;   // split precision in both modes
   a.bias = e->w("patch_embed.proj.bias");
   a.img = x; a.img_h = H; a.img_w = W; a.patch = p; a.n_patches = n; a.pos = pos; a.mask = mask; a.mask_token = mask_token; a.out_f32 = X;
+  if (mos != nullptr) { a.mos = mos->p; a.mos_pitch = mos->pitch; a.mos_h = mos->h; a.mos_w = mos->w; a.mos_n = mos->n; a.mos_S = mos->S; a.mos_t0 = mos->t0; }
   switch (bn) {
     case 192: return launch_gemm_inst<192, EPI_PATCH_F32, true>(tb, tb, tb, a, e->num_sms, st);
     case 128: return launch_gemm_inst<128, EPI_PATCH_F32, true>(tb, tb, tb, a, e->num_sms, st);
@@ -827,11 +835,20 @@ int vitocm_prepare_tokens(vitocm_engine* e, const float* x, int B, int H, int W,
 }
 
 static int forward_rows(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const int* queries, int nq,
-                        float* out_rows, float* k_out, void* ws, size_t ws_bytes, int chunk_tiles, void* stream, bool gray = false);
+                        float* out_rows, float* k_out, void* ws, size_t ws_bytes, int chunk_tiles, void* stream, bool gray = false,
+                        const MosaicSrc* mos = nullptr);
 
 int vitocm_forward_cls_attn_gray(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, float* out_rows,
                                  void* ws, size_t ws_bytes, int chunk_tiles, void* stream) {
   return forward_rows(e, x, B, H, W, pos, nullptr, 1, out_rows, nullptr, ws, ws_bytes, chunk_tiles, stream, true);
+}
+
+int vitocm_forward_cls_attn_mosaic(vitocm_engine* e, const uint8_t* mosaic, int mos_h, int mos_w, int64_t pitch, int n, int W, int S, int t0,
+                                   int T, const float* pos, float* out_rows, void* ws, size_t ws_bytes, int chunk_tiles, void* stream) {
+  if (mosaic == nullptr || n < 1 || S < 1 || W < 1 || t0 < 0 || T < 0 || t0 + T > n * n)
+    return fail(VITOCM_ERR_INVALID, "forward_cls_attn_mosaic: bad window grid n=%d W=%d S=%d tiles [%d, %d)", n, W, S, t0, t0 + T);
+  const MosaicSrc src{mosaic, static_cast<long long>(pitch), mos_h, mos_w, n, S, t0};
+  return forward_rows(e, nullptr, T, W, W, pos, nullptr, 1, out_rows, nullptr, ws, ws_bytes, chunk_tiles, stream, true, &src);
 }
 
 int vitocm_forward_cls_attn(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, float* out_rows,
@@ -846,7 +863,8 @@ int vitocm_forward_query_attn(vitocm_engine* e, const float* x, int B, int H, in
 }
 
 static int forward_rows(vitocm_engine* e, const float* x, int B, int H, int W, const float* pos, const int* queries, int nq,
-                        float* out_rows, float* k_out, void* ws, size_t ws_bytes, int chunk_tiles, void* stream, bool gray) {
+                        float* out_rows, float* k_out, void* ws, size_t ws_bytes, int chunk_tiles, void* stream, bool gray,
+                        const MosaicSrc* mos) {
   TRY(check_engine(e));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int p = e->cfg.patch_size, D = e->cfg.embed_dim, heads = e->cfg.num_heads, C = gray ? 1 : e->cfg.in_chans;
@@ -892,7 +910,13 @@ static int forward_rows(vitocm_engine* e, const float* x, int B, int H, int W, c
       ++active;
     }
     for (int k = 0; k < active; ++k)
-      TRY(run_patch_embed(e, x + static_cast<long long>(b0s[k]) * C * H * W, bcs[k], H, W, pos, nullptr, lane_ws[k].X, lane_st[k], gray));
+      if (mos != nullptr) {
+        MosaicSrc part = *mos;
+        part.t0 += b0s[k];
+        TRY(run_patch_embed(e, nullptr, bcs[k], H, W, pos, nullptr, lane_ws[k].X, lane_st[k], true, &part));
+      } else {
+        TRY(run_patch_embed(e, x + static_cast<long long>(b0s[k]) * C * H * W, bcs[k], H, W, pos, nullptr, lane_ws[k].X, lane_st[k], gray));
+      }
     bool xn_ready[vitocm_engine::MAX_LANES] = {false, false, false, false};
     for (int l = 0; l + 1 < e->cfg.depth; ++l) {
       // the next block's norm1 rides on this block's fc2 epilogue -- except into the last block, whose K projection

@@ -195,9 +195,14 @@ class MosaicSegmenter:
 
     model: vitocm VisionTransformer (patch 8); window/stride: crop geometry (reference default
     384/128; BASELINE configs use 224/112); tile_batch: tiles per engine call; group: optional
-    torch.distributed process group (NCCL) to shard over -- None = single GPU."""
+    torch.distributed process group (NCCL) to shard over -- None = single GPU; ingest: "direct" = the
+    patch embedding reads its pixels straight out of the uint8 mosaic, "crops" = fp32 crops are cut first
+    (vitocm_extract_tiles); both give the same bits."""
 
-    def __init__(self, model, window=384, stride=128, tile_batch=64, group=None):
+    def __init__(self, model, window=384, stride=128, tile_batch=64, group=None, ingest="direct"):
+        if ingest not in ("direct", "crops"):
+            raise ValueError("ingest must be 'direct' (tiles read out of the mosaic by the patch embedding) or 'crops' (materialised fp32 crops)")
+        self.ingest = ingest
         self.model = model
         self.window, self.stride, self.tile_batch = int(window), int(stride), int(tile_batch)
         self.group = group
@@ -219,13 +224,17 @@ class MosaicSegmenter:
         n = grid_size(mosaic.shape[0], S)
         lh = W // self.patch
         out = torch.empty(max(t1 - t0, 0), lh * lh, dtype=torch.float32, device=mosaic.device)
-        xbuf = torch.empty(self.tile_batch, C, W, W, dtype=torch.float32, device=mosaic.device)
+        direct = self.ingest == "direct" and self.model.in_chans > 1
+        xbuf = None if direct else torch.empty(self.tile_batch, C, W, W, dtype=torch.float32, device=mosaic.device)
         for a in range(t0, t1, self.tile_batch):
             b = min(a + self.tile_batch, t1)
-            x = xbuf[: b - a]
-            check(lib.vitocm_extract_tiles(ptr(mosaic), mosaic.shape[0], mosaic.shape[1], mosaic.stride(0), n, W, S, a,
-                                           b - a, C, ptr(x), cur_stream()))
-            rows = self.model.cls_attention_rows(x)
+            if direct:   # the patch-embedding producer reads the uint8 mosaic itself: no crop is materialised
+                rows = self.model.cls_attention_rows_mosaic(mosaic, n, W, S, a, b - a)
+            else:
+                x = xbuf[: b - a]
+                check(lib.vitocm_extract_tiles(ptr(mosaic), mosaic.shape[0], mosaic.shape[1], mosaic.stride(0), n, W, S, a,
+                                               b - a, C, ptr(x), cur_stream()))
+                rows = self.model.cls_attention_rows(x)
             out[a - t0:b - t0] = head_mean_maps(rows, per_tile_minmax255=True)
         return out.view(-1, lh, lh)
 

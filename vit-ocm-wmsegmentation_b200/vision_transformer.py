@@ -348,6 +348,29 @@ class VisionTransformer(nn.Module):
         return out
 
     @torch.no_grad()
+    def cls_attention_rows_mosaic(self, mosaic: torch.Tensor, grid: int, window: int, stride: int, t0: int, count: int) -> torch.Tensor:
+        """cls_attention_rows of the windows t0 .. t0+count-1 (row-major in the grid x grid sliding-window grid,
+        SSS/sw_processing.py:151-163) of a gray uint8 CUDA mosaic, cut out by the patch-embedding producer itself: no crop
+        is ever materialised.  -> [count, heads, N] fp32."""
+        if mosaic.dtype != torch.uint8 or mosaic.dim() != 2 or not mosaic.is_cuda or mosaic.stride(1) != 1:
+            raise ValueError("mosaic must be a 2-D uint8 CUDA tensor with unit column stride")
+        if self.in_chans < 2:
+            raise NotImplementedError("mosaic ingest runs the channel-folded (gray) patch filter of a multi-channel model")
+        p = self.patch_embed.patch_size
+        if window % p:
+            raise ValueError("window must be a multiple of the patch size")
+        eng = self._ensure_engine()
+        N = (window // p) ** 2 + 1
+        pos = self._pos_table(N - 1, window, window)
+        chunk = max(1, min(self.chunk_tiles, count))
+        ws = self._workspace(chunk, N, mosaic.device)
+        out = torch.empty(count, self.num_heads, N, dtype=torch.float32, device=mosaic.device)
+        check(_lib.load_library().vitocm_forward_cls_attn_mosaic(eng, mosaic.data_ptr(), mosaic.shape[0], mosaic.shape[1], mosaic.stride(0), grid,
+                                                                 window, stride, t0, count, ptr(pos), ptr(out), ptr(ws), ws.numel(), chunk,
+                                                                 cur_stream()))
+        return out
+
+    @torch.no_grad()
     def attention_rows(self, x: torch.Tensor, queries, return_keys: bool = False):
         """get_last_selfattention(x)[:, :, queries, :] -> [B, heads, nq, N] fp32 for a list of query tokens (0 = CLS,
         1 + i = patch i; SSS/analyse_attention.py:183-247 region queries), without forming N x N.  With ``return_keys``
