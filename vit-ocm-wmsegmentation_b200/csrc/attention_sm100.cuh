@@ -202,17 +202,22 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           }
       }
       // ring order = consumption order of the MMA warp: K0, K1, V0, K2, V1, ..., V_{n-1} (each entry = one tile per slot)
+      int kv_col[4], kv_row[4];   // per slot: first column (head) and first row (image) of its pair's K / V, decoded once per item
+      for (int sl = 0; sl < nslots; ++sl) {
+        const int pr = pair_of(sl);
+        const int b = pr / args.heads;
+        kv_col[sl] = (pr - b * args.heads) * ATT_DH;
+        kv_row[sl] = b * N;
+      }
       auto load = [&](int which /*1 = K, 2 = V*/, int j) {
         for (int sl = 0; sl < nslots; ++sl) {
-          const int pr = pair_of(sl);
-          const int b = pr / args.heads, h = pr - b * args.heads;
           const int slot = item % ATT_RING;
           const uint32_t parity = ((item / ATT_RING) & 1) ^ 1;
           ptx::mbar_wait(kv_empty + 8 * slot, parity, 10);
           ptx::mbar_arrive_expect_tx(kv_full + 8 * slot, Cfg::SLOT_BYTES);
           for (int part = 0; part < NPART; ++part)
             ptx::tma_load_2d(smem_ring + slot * Cfg::SLOT_BYTES + part * ATT_TILE_BYTES, &tmap_qkv, kv_full + 8 * slot,
-                             part * args.lo_col_off + which * D + h * ATT_DH, b * N + j * ATT_BKV);
+                             part * args.lo_col_off + which * D + kv_col[sl], kv_row[sl] + j * ATT_BKV);
           ++item;
         }
       };
@@ -248,31 +253,42 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       };
       auto issue_s = [&](int j) {
         const uint32_t idesc = ptx::make_idesc(ATT_BQ, kv_len_mma(j), false, false);
-#pragma unroll 1
-        for (int sl = 0; sl < nslots; ++sl) {   // packed item: one masked MMA group per slot, each against its own pair's K
+        if (nslots == 1) {   // ordinary item: straight-line issue (this is the path every full tile takes)
           const int slot = item % ATT_RING;
           ptx::mbar_wait(kv_full + 8 * slot, (item / ATT_RING) & 1, 11);
           ptx::tc_fence_after();
           const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_ring + slot * Cfg::SLOT_BYTES, 1024, 0);
-          uint32_t lm[4];
-          att_slot_mask(sl, nslots, lm);
           // terms: (Qhi,Khi) [, (Qhi,Klo), (Qlo,Khi)]; K-major operands advance 32 B per 16-wide k step
 #pragma unroll
           for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
             const uint64_t qa = ptx::desc_advance(q_desc, t == 2 ? ATT_TILE_BYTES : 0);
             const uint64_t ka = ptx::desc_advance(k_desc, t == 1 ? ATT_TILE_BYTES : 0);
-            if (nslots == 1) {
 #pragma unroll
-              for (int k = 0; k < ATT_DH / 16; ++k)
-                ptx::umma_bf16_ss(s_tmem, ptx::desc_advance(qa, k * 32), ptx::desc_advance(ka, k * 32), idesc, (t | k) ? 1u : 0u);
-            } else {
+            for (int k = 0; k < ATT_DH / 16; ++k)
+              ptx::umma_bf16_ss(s_tmem, ptx::desc_advance(qa, k * 32), ptx::desc_advance(ka, k * 32), idesc, (t | k) ? 1u : 0u);
+          }
+          ptx::umma_commit(kv_empty + 8 * slot);
+          ++item;
+        } else {
+#pragma unroll 1
+          for (int sl = 0; sl < nslots; ++sl) {   // packed item: one masked MMA group per slot, each against its own pair's K
+            const int slot = item % ATT_RING;
+            ptx::mbar_wait(kv_full + 8 * slot, (item / ATT_RING) & 1, 11);
+            ptx::tc_fence_after();
+            const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_ring + slot * Cfg::SLOT_BYTES, 1024, 0);
+            uint32_t lm[4];
+            att_slot_mask(sl, nslots, lm);
+#pragma unroll
+            for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
+              const uint64_t qa = ptx::desc_advance(q_desc, t == 2 ? ATT_TILE_BYTES : 0);
+              const uint64_t ka = ptx::desc_advance(k_desc, t == 1 ? ATT_TILE_BYTES : 0);
 #pragma unroll
               for (int k = 0; k < ATT_DH / 16; ++k)
                 ptx::umma_bf16_ss_masked(s_tmem, ptx::desc_advance(qa, k * 32), ptx::desc_advance(ka, k * 32), idesc, (t | k) ? 1u : 0u, lm);
             }
+            ptx::umma_commit(kv_empty + 8 * slot);
+            ++item;
           }
-          ptx::umma_commit(kv_empty + 8 * slot);
-          ++item;
         }
         ptx::umma_commit(s_full);
         att_stamp(args, tl, 1, j, 0);   // S_j issued
@@ -288,24 +304,17 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           ptx::mbar_wait(o_empty, (w - 1) & 1, 17);
           ptx::tc_fence_after();
         }
-#pragma unroll 1
-        for (int sl = 0; sl < nslots; ++sl) {   // packed item: slot sl's rows of P against its own pair's V
+        if (nslots == 1) {   // ordinary item: straight-line issue
           const int slot = item % ATT_RING;
           ptx::mbar_wait(kv_full + 8 * slot, (item / ATT_RING) & 1, 12);
           ptx::tc_fence_after();
           const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_ring + slot * Cfg::SLOT_BYTES, 1024, 1024);
-          uint32_t lm[4];
-          att_slot_mask(sl, nslots, lm);
           // terms: (Phi,Vhi) [, (Phi,Vlo), (Plo,Vhi)]
 #pragma unroll
           for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
             const uint32_t pa = tmem_base + ATT_P_COL + (t == 2 ? 64 : 0);
             const uint64_t va = ptx::desc_advance(v_desc, t == 1 ? ATT_TILE_BYTES : 0);
-            if (nslots > 1) {
-#pragma unroll 1
-              for (int k = 0; k < ksteps; ++k)
-                ptx::umma_bf16_ts_masked(o_tmem, pa + k * 8, ptx::desc_advance(va, k * 2048), idesc, (t | k) ? 1u : acc0, lm);
-            } else if (ksteps == ATT_BKV / 16) {
+            if (ksteps == ATT_BKV / 16) {
 #pragma unroll
               for (int k = 0; k < ATT_BKV / 16; ++k)
                 ptx::umma_bf16_ts(o_tmem, pa + k * 8, ptx::desc_advance(va, k * 2048), idesc, (t | k) ? 1u : acc0);
@@ -317,6 +326,26 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           }
           ptx::umma_commit(kv_empty + 8 * slot);
           ++item;
+        } else {
+#pragma unroll 1
+          for (int sl = 0; sl < nslots; ++sl) {   // packed item: slot sl's rows of P against its own pair's V
+            const int slot = item % ATT_RING;
+            ptx::mbar_wait(kv_full + 8 * slot, (item / ATT_RING) & 1, 12);
+            ptx::tc_fence_after();
+            const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_ring + slot * Cfg::SLOT_BYTES, 1024, 1024);
+            uint32_t lm[4];
+            att_slot_mask(sl, nslots, lm);
+#pragma unroll
+            for (int t = 0; t < (SPLIT ? 3 : 1); ++t) {
+              const uint32_t pa = tmem_base + ATT_P_COL + (t == 2 ? 64 : 0);
+              const uint64_t va = ptx::desc_advance(v_desc, t == 1 ? ATT_TILE_BYTES : 0);
+#pragma unroll 1
+              for (int k = 0; k < ksteps; ++k)
+                ptx::umma_bf16_ts_masked(o_tmem, pa + k * 8, ptx::desc_advance(va, k * 2048), idesc, (t | k) ? 1u : acc0, lm);
+            }
+            ptx::umma_commit(kv_empty + 8 * slot);
+            ++item;
+          }
         }
         ptx::umma_commit(o_full);
         att_stamp(args, tl, 1, j, 1);   // PV_j issued
@@ -352,20 +381,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     int g = 0;                    // KV blocks processed so far (all work items): barrier phase counter
     int w = 0;
     for (int it = blockIdx.x; it < args.n_items; it += gridDim.x) {
-    int qt, pair0;
-    bool packed;
-    if (!att_decode(args, it, qt, pair0, packed)) continue;
-    // this thread's row: tile row r of an ordinary item; in a packed item row (r % slot_rows) of the tail of pair0 + r / slot_rows
-    int my_pair = pair0, row_in_tile = r, slot_rows = ATT_BQ;
-    if (packed) {
-      slot_rows = ATT_BQ / args.pack;
-      const int sl = r / slot_rows;
-      row_in_tile = r - sl * slot_rows;
-      my_pair = pair0 + sl;
+    {
+      int qt0, pair00;
+      bool packed0;
+      if (!att_decode(args, it, qt0, pair00, packed0)) continue;   // (decoded again for the epilogue: nothing of it stays live over the KV loop)
     }
-    const bool pair_ok = my_pair < args.n_pairs;
-    const int b = my_pair / args.heads, h = my_pair - b * args.heads;
-    const int row_base = b * N;
     const bool tl = tl0 && w == args.timeline_item;
     float m_used = -INFINITY;     // the row maximum the exponentials are taken against
     float m_next = -INFINITY;     // a larger maximum seen in the previous block (lazy rescale pending)
@@ -512,6 +532,20 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     ptx::mbar_wait(o_full, (g - 1) & 1, 22);
     ptx::tc_fence_after();
     const float inv = 1.0f / l_run;
+    // this thread's row: tile row r of an ordinary item; in a packed item row (r % slot_rows) of the tail of pair0 + r / slot_rows
+    int qt, pair0;
+    bool packed;
+    att_decode(args, it, qt, pair0, packed);
+    int my_pair = pair0, row_in_tile = r, slot_rows = ATT_BQ;
+    if (packed) {
+      slot_rows = ATT_BQ / args.pack;
+      const int sl = r / slot_rows;
+      row_in_tile = r - sl * slot_rows;
+      my_pair = pair0 + sl;
+    }
+    const bool pair_ok = my_pair < args.n_pairs;
+    const int b = my_pair / args.heads, h = my_pair - b * args.heads;
+    const int row_base = b * N;
     const int qrow = qt * ATT_BQ + row_in_tile;
     if (args.lse2 != nullptr && pair_ok) {   // pad rows get +inf: the backward turns that into P = 0 without a bounds test
       float* lrow = args.lse2 + static_cast<long long>(my_pair) * (args.n_qtiles * ATT_BQ);
