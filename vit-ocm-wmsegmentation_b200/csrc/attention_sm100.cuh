@@ -90,7 +90,14 @@ struct AttnCfg {
 };
 
 // work item -> (query tile, first pair, packed?); false = the item does not exist (pair beyond the batch in the last group)
+template <bool PACKED>
 __device__ __forceinline__ bool att_decode(const AttnArgs& a, int it, int& qt, int& pair0, bool& packed) {
+  if (!PACKED) {   // launches without packed items (pack == 1): query tile fastest, then the pair; every item exists
+    pair0 = it / a.n_qtiles;
+    qt = it - pair0 * a.n_qtiles;
+    packed = false;
+    return true;
+  }
   const int grp = it / a.group_items, r = it - grp * a.group_items;
   if (r < a.pack * a.n_fullq) {
     const int pi = r / a.n_fullq;
@@ -111,7 +118,8 @@ __device__ __forceinline__ void att_slot_mask(int s, int nslots, uint32_t (&m)[4
 }
 
 // POLY_MASK: bit i set = pair i of every 16 pairs of a 32-key chunk takes the FMA-pipe exp2 polynomial
-template <bool SPLIT, uint32_t POLY_MASK>
+// PACKED: the launch contains packed tail items (args.pack > 1); false compiles the slot logic out (every item is an ordinary tile)
+template <bool SPLIT, uint32_t POLY_MASK, bool PACKED>
 __global__ void __launch_bounds__(ATT_THREADS, SPLIT ? 1 : 2)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_q32, const AttnArgs args) {
   using Cfg = AttnCfg<SPLIT>;
@@ -179,13 +187,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       for (int it = blockIdx.x; it < args.n_items; it += gridDim.x) {
       int qt, pair0;
       bool packed;
-      if (!att_decode(args, it, qt, pair0, packed)) continue;
-      const int nslots = packed ? args.pack : 1;
+      if (!att_decode<PACKED>(args, it, qt, pair0, packed)) continue;
+      const int nslots = (PACKED && packed) ? args.pack : 1;
       // pair of slot s (slots beyond the batch repeat the last pair: their rows are computed and dropped)
       auto pair_of = [&](int s) { const int pr = pair0 + s; return pr < args.n_pairs ? pr : args.n_pairs - 1; };
       ptx::mbar_wait(q_empty, (w & 1) ^ 1, 16);   // the previous item's S MMAs have retired
       ptx::mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
-      if (!packed) {
+      if (!PACKED || !packed) {
         const int b = pair0 / args.heads, h = pair0 - b * args.heads;
         for (int part = 0; part < NPART; ++part)
           ptx::tma_load_2d(smem_q + part * ATT_TILE_BYTES, &tmap_qkv, q_full, part * args.lo_col_off + h * ATT_DH,
@@ -243,8 +251,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       for (int it = blockIdx.x; it < args.n_items; it += gridDim.x) {
       int qt_unused, pair0_unused;
       bool packed;
-      if (!att_decode(args, it, qt_unused, pair0_unused, packed)) continue;
-      const int nslots = packed ? args.pack : 1;
+      if (!att_decode<PACKED>(args, it, qt_unused, pair0_unused, packed)) continue;
+      const int nslots = (PACKED && packed) ? args.pack : 1;
       const bool tl = tl0 && w == args.timeline_item;
       auto kv_len_mma = [&](int j) {  // keys of block j rounded up to the MMA granularity (16)
         int len = N - j * ATT_BKV;
@@ -384,7 +392,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     {
       int qt0, pair00;
       bool packed0;
-      if (!att_decode(args, it, qt0, pair00, packed0)) continue;   // (decoded again for the epilogue: nothing of it stays live over the KV loop)
+      if (!att_decode<PACKED>(args, it, qt0, pair00, packed0)) continue;   // (decoded again for the epilogue: nothing of it stays live over the KV loop)
     }
     const bool tl = tl0 && w == args.timeline_item;
     float m_used = -INFINITY;     // the row maximum the exponentials are taken against
@@ -535,9 +543,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
     // this thread's row: tile row r of an ordinary item; in a packed item row (r % slot_rows) of the tail of pair0 + r / slot_rows
     int qt, pair0;
     bool packed;
-    att_decode(args, it, qt, pair0, packed);
+    att_decode<PACKED>(args, it, qt, pair0, packed);
     int my_pair = pair0, row_in_tile = r, slot_rows = ATT_BQ;
-    if (packed) {
+    if (PACKED && packed) {
       slot_rows = ATT_BQ / args.pack;
       const int sl = r / slot_rows;
       row_in_tile = r - sl * slot_rows;

@@ -464,7 +464,8 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
   static const int pack_on = [] { const char* v = getenv("VITOCM_ATTN_PACK"); return v ? atoi(v) : 1; }();
   const int tail = N % ATT_BQ;
   a.n_fullq = N / ATT_BQ;
-  a.pack = (!pack_on || tail == 0 || tail > 64) ? 1 : (tail > 32 ? 2 : 4);
+  // (only where the tail tiles are a visible share of the work: beyond 16 full tiles per pair the slot logic costs more than it saves)
+  a.pack = (!pack_on || tail == 0 || tail > 64 || a.n_fullq > 16) ? 1 : (tail > 32 ? 2 : 4);
   a.group_items = a.pack * a.n_fullq + (tail != 0 ? 1 : 0);
   a.n_pairs = B * H;
   const long long items = static_cast<long long>((a.n_pairs + a.pack - 1) / a.pack) * a.group_items;
@@ -481,11 +482,18 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
   };
   // fraction of the exponentials moved from MUFU to the FMA pipe (bf16 mode): tuning knob, default from measurement
   static const int poly = [] { const char* v = getenv("VITOCM_ATTN_POLY"); return v ? atoi(v) : ATT_POLY_DEFAULT; }();
-  static bool attr[4] = {false, false, false, false};
-  if (e->split) TRY(launch(attn_fwd_tcgen05_kernel<true, 0u>, AttnCfg<true>::SMEM_BYTES, attr[3]));
-  else if (poly == 1) TRY(launch(attn_fwd_tcgen05_kernel<false, 0x1248u>, AttnCfg<false>::SMEM_BYTES, attr[1]));   // 4 of 16 pairs
-  else if (poly == 2) TRY(launch(attn_fwd_tcgen05_kernel<false, 0x5529u>, AttnCfg<false>::SMEM_BYTES, attr[2]));   // 7 of 16 pairs
-  else TRY(launch(attn_fwd_tcgen05_kernel<false, 0u>, AttnCfg<false>::SMEM_BYTES, attr[0]));
+  static bool attr[8] = {false, false, false, false, false, false, false, false};
+  if (a.pack > 1) {   // kernels with the packed-item logic
+    if (e->split) TRY(launch(attn_fwd_tcgen05_kernel<true, 0u, true>, AttnCfg<true>::SMEM_BYTES, attr[3]));
+    else if (poly == 1) TRY(launch(attn_fwd_tcgen05_kernel<false, 0x1248u, true>, AttnCfg<false>::SMEM_BYTES, attr[1]));   // 4 of 16 pairs
+    else if (poly == 2) TRY(launch(attn_fwd_tcgen05_kernel<false, 0x5529u, true>, AttnCfg<false>::SMEM_BYTES, attr[2]));   // 7 of 16 pairs
+    else TRY(launch(attn_fwd_tcgen05_kernel<false, 0u, true>, AttnCfg<false>::SMEM_BYTES, attr[0]));
+  } else {
+    if (e->split) TRY(launch(attn_fwd_tcgen05_kernel<true, 0u, false>, AttnCfg<true>::SMEM_BYTES, attr[7]));
+    else if (poly == 1) TRY(launch(attn_fwd_tcgen05_kernel<false, 0x1248u, false>, AttnCfg<false>::SMEM_BYTES, attr[5]));
+    else if (poly == 2) TRY(launch(attn_fwd_tcgen05_kernel<false, 0x5529u, false>, AttnCfg<false>::SMEM_BYTES, attr[6]));
+    else TRY(launch(attn_fwd_tcgen05_kernel<false, 0u, false>, AttnCfg<false>::SMEM_BYTES, attr[4]));
+  }
   LAUNCH_CHECK();
   return 0;
 }
