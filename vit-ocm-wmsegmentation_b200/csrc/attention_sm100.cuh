@@ -23,8 +23,11 @@
 // its own would spend a full tile's exponentials on them (1/7 of the kernel).  Instead the tails of `pack` = 4 (<= 32 rows)
 // or 2 (<= 64 rows) consecutive (image, head) pairs share ONE 128-row tile, one 32- or 64-lane slot each: the S and PV MMAs
 // are issued once per slot against that pair's own K / V with a disable-output-lane mask that leaves the other slots'
-// TMEM lanes untouched, and the softmax warps run unchanged (one thread per row, whichever pair the row belongs to).  SPLIT = true is the fp32-parity mode: every operand is a bf16
-// (hi, lo) pair and each product is hi*hi + hi*lo + lo*hi (fp32 accumulate in TMEM).
+// TMEM lanes untouched, and the softmax warps run unchanged (one thread per row, whichever pair the row belongs to).
+// The slot logic only exists in the PACKED = true instantiations; launches without packed items (no ragged tail, a tail
+// of more than 64 rows, or more than 16 full tiles per pair) run PACKED = false, where every item is an ordinary tile.
+// SPLIT = true is the fp32-parity mode: every operand is a bf16 (hi, lo) pair and each product is
+// hi*hi + hi*lo + lo*hi (fp32 accumulate in TMEM).
 #pragma once
 #include <type_traits>
 
