@@ -283,9 +283,11 @@ def test_checkpoint_resume_interchanges_with_stock_torch_adamw(tmp_path):
     one_step(mim_a, opt_a, 2, False)
     one_step(mim_b, opt_b, 2, True)
     for (n, p), (_, pa), (_, pb) in zip(mim.named_parameters(), mim_a.named_parameters(), mim_b.named_parameters()):
-        # three runs of the same third step; not bit-identical (the backward reduces some gradients with atomics)
-        tol = 2e-6 + 1e-5 * p.abs().max().item()
-        assert (p - pb).abs().max().item() <= tol and (p - pa).abs().max().item() <= tol, n
+        # three runs of the same third step; not bit-identical (the backward reduces some gradients with atomics, and Adam's
+        # normalised update turns a last-bit difference of a near-zero moment into up to 2 * lr on that element), so the bar is on the
+        # tensor as a whole: a lost or mis-indexed moment moves EVERY element by ~lr, i.e. > 1e-2 of the tensor's norm
+        den = p.double().norm().item() + 1e-12
+        assert (p - pb).double().norm().item() <= 2e-3 * den and (p - pa).double().norm().item() <= 2e-3 * den, n
 
     # eval side: a plain ViT loads the saved encoder (strict=False drops mask_token) and reproduces its CLS rows
     # (the SimMIM encoder keeps the ViT's default 224 position table whatever img_size it is given, SSS/model.py:11-16)
