@@ -384,7 +384,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arch", default="vit_small", choices=sorted(ARCHS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", help="bf16 | fp16 | fp32, optionally +mlp2[:blocks] (vision_transformer.parse_precision)")
     ap.add_argument("--chunk-tiles", type=int, default=175)
     ap.add_argument("--tile-batch", type=int, default=175)
     ap.add_argument("--lanes", type=int, default=1, help="chunks in flight on concurrent streams")

@@ -38,7 +38,10 @@ typedef enum vitocm_status {
 
 typedef enum vitocm_precision {
   VITOCM_BF16 = 0, /* bf16 tensor-core operands, fp32 accumulate / residual / LN / softmax statistics */
-  VITOCM_FP32 = 1  /* fp32-parity mode: every operand a bf16 (hi, lo) pair, products hi*hi+hi*lo+lo*hi */
+  VITOCM_FP32 = 1, /* fp32-parity mode: every operand a bf16 (hi, lo) pair, products hi*hi+hi*lo+lo*hi */
+  VITOCM_FP16 = 2  /* IEEE fp16 tensor-core operands (11 significand bits instead of 8, same rate), saturating conversions,
+                    * fp32 accumulate / residual / LN / softmax statistics: the inference default -- the reference is an fp32
+                    * model (vit.py:78-90, no autocast anywhere) and its masks need ~1e-4 relative CLS rows */
 } vitocm_precision;
 
 /* Constructor constants of VisionTransformer (vit.py:137-139) and of the factories
@@ -71,6 +74,12 @@ int vitocm_destroy(vitocm_engine* e);
  * transposed patch filter) and must be called after the last load and before any forward. */
 int vitocm_load_weight(vitocm_engine* e, const char* name, const float* host_data, int64_t numel);
 int vitocm_finalize_weights(vitocm_engine* e);
+
+/* Precision schedule, per transformer block (call before vitocm_workspace_bytes / the forwards; bf16 and fp16 engines):
+ * mode 0 = the engine's precision; mode 1 = this block's fc1 / fc2 (vit.py:57-63) read their activations -- norm2's output and
+ * gelu(fc1) -- as (hi, lo) pairs of the engine's 16-bit format against single-precision weights, two MMAs per product.  These two
+ * roundings carry ~70 % of the CLS-row error variance of a 16-bit forward (profiles/r02_precision_sim.txt). */
+int vitocm_set_layer_mode(vitocm_engine* e, int layer, int mode);
 
 /* Bytes of workspace needed by the forward entry points for chunks of `chunk_tiles` images of
  * n_tokens tokens each. */

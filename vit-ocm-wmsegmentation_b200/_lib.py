@@ -29,6 +29,7 @@ SIGNATURES = {
     "vitocm_finalize_weights": (c_int, [c_void_p]),
     "vitocm_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "vitocm_set_concurrency": (c_int, [c_void_p, c_int]),
+    "vitocm_set_layer_mode": (c_int, [c_void_p, c_int, c_int]),
     "vitocm_forward_cls_attn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                         c_int, c_void_p]),
     "vitocm_forward_cls_attn_gray": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,

@@ -78,6 +78,7 @@ constexpr int ATT_O_COL = 128;    // O: 64 columns (fp32)
 constexpr int ATT_P_COL = 192;    // P: 64 columns of packed bf16x2 (128 keys); split mode: lo part in the next 64
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units: raise the running maximum (rescale O, l) before the next block
 constexpr float ATT_REDO_THRESHOLD = 60.0f;    // log2 units: exp2 of the current block may overflow -> redo it now
+constexpr float ATT_REDO_THRESHOLD_F16 = 14.0f;   // fp16 P: 2^14 < 65504
 constexpr int ATT_POLY_DEFAULT = 0;            // see run_attention (0: all MUFU, 1: 4/16 polynomial, 2: 7/16)
 
 template <bool SPLIT>
@@ -122,7 +123,10 @@ __device__ __forceinline__ void att_slot_mask(int s, int nslots, uint32_t (&m)[4
 
 // POLY_MASK: bit i set = pair i of every 16 pairs of a 32-key chunk takes the FMA-pipe exp2 polynomial
 // PACKED: the launch contains packed tail items (args.pack > 1); false compiles the slot logic out (every item is an ordinary tile)
-template <bool SPLIT, uint32_t POLY_MASK, bool PACKED>
+// F16: q / k / v, P and ctx are IEEE fp16 instead of bf16 (fp16 engines): 11 significand bits at the same tensor-core rate.  P is
+//      exp2 of (logit - running maximum) <= 2^ATT_RESCALE_THRESHOLD, or <= 2^redo threshold inside one block: the redo threshold
+//      drops to 14 so that P stays below fp16's 65504; below 6e-8 P flushes to zero, like everything under 2^-24 of the row sum.
+template <bool SPLIT, uint32_t POLY_MASK, bool PACKED, bool F16 = false>
 __global__ void __launch_bounds__(ATT_THREADS, SPLIT ? 1 : 2)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_q32, const AttnArgs args) {
   using Cfg = AttnCfg<SPLIT>;
@@ -263,7 +267,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         return (len + 15) & ~15;
       };
       auto issue_s = [&](int j) {
-        const uint32_t idesc = ptx::make_idesc(ATT_BQ, kv_len_mma(j), false, false);
+        const uint32_t idesc = ptx::make_idesc(ATT_BQ, kv_len_mma(j), false, false, F16 ? 0u : 1u);
         if (nslots == 1) {   // ordinary item: straight-line issue (this is the path every full tile takes)
           const int slot = item % ATT_RING;
           ptx::mbar_wait(kv_full + 8 * slot, (item / ATT_RING) & 1, 11);
@@ -308,7 +312,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         // O accumulates across KV blocks in TMEM.
         // A = P in TMEM: 16 keys = 8 packed columns per step
         // B = V: MN-major [keys x 64]; 16 keys = two 8-row groups of 1024 B
-        constexpr uint32_t idesc = ptx::make_idesc(ATT_BQ, ATT_DH, false, /*B = V is MN-major*/ true);
+        constexpr uint32_t idesc = ptx::make_idesc(ATT_BQ, ATT_DH, false, /*B = V is MN-major*/ true, F16 ? 0u : 1u);
         const int ksteps = kv_len_mma(j) / 16;
         const uint32_t acc0 = j > 0 ? 1u : 0u;
         if (j == 0 && w > 0) {   // O still holds the previous work item until the softmax warps have read it out
@@ -499,8 +503,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
                 e1 = ptx::ex2_approx(a1);
               }
               sum2[i & 1] = ptx::add_f32x2(sum2[i & 1], ptx::pack_f32x2(e0, e1));
-              ph[i] = ptx::pack_bf16x2(e0, e1);
-              if (SPLIT) pl[i] = ptx::pack_bf16x2(e0 - ptx::bf16_round(e0), e1 - ptx::bf16_round(e1));
+              ph[i] = ptx::pack_h2<F16>(e0, e1);
+              if (SPLIT) pl[i] = ptx::pack_h2<F16>(e0 - ptx::round_h<F16>(e0), e1 - ptx::round_h<F16>(e1));
             }
             ptx::tmem_st_32x32b_x16(lane_addr + ATT_P_COL + c * 16, ph);
             if (SPLIT) ptx::tmem_st_32x32b_x16(lane_addr + ATT_P_COL + 64 + c * 16, pl);
@@ -513,10 +517,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
       run_exps();
       if (j > 0) {
         const float excess = (row_max() - m_used) * sl2;       // independent of the exponentials above: overlaps them
-        if (__any_sync(0xffffffffu, excess > ATT_REDO_THRESHOLD)) {
+        constexpr float REDO = F16 ? ATT_REDO_THRESHOLD_F16 : ATT_REDO_THRESHOLD;
+        if (__any_sync(0xffffffffu, excess > REDO)) {
           // rare: a row jumped so far above the running maximum that exp2 may have overflowed -> raise the maximum
           // now (O is complete up to block j-1 and may be rescaled here) and redo this block's exponentials
-          const float m_new = excess > ATT_REDO_THRESHOLD ? m_used + excess / sl2 : m_used;
+          const float m_new = excess > REDO ? m_used + excess / sl2 : m_used;
           const float a = ptx::ex2_approx((m_used - m_new) * sl2);
           m_used = m_new;
           l_run *= a;
@@ -581,15 +586,15 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(t[c][8 * q4 + i]) * inv;
-          reinterpret_cast<uint4*>(o + c * 32)[q4] = make_uint4(ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]),
-                                                               ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+          reinterpret_cast<uint4*>(o + c * 32)[q4] = make_uint4(ptx::pack_h2<F16>(v[0], v[1]), ptx::pack_h2<F16>(v[2], v[3]),
+                                                               ptx::pack_h2<F16>(v[4], v[5]), ptx::pack_h2<F16>(v[6], v[7]));
           if (SPLIT) {
             float lo[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) lo[i] = v[i] - ptx::bf16_round(v[i]);
+            for (int i = 0; i < 8; ++i) lo[i] = v[i] - ptx::round_h<F16>(v[i]);
             reinterpret_cast<uint4*>(o + args.out_lo_off + c * 32)[q4] =
-                make_uint4(ptx::pack_bf16x2(lo[0], lo[1]), ptx::pack_bf16x2(lo[2], lo[3]), ptx::pack_bf16x2(lo[4], lo[5]),
-                           ptx::pack_bf16x2(lo[6], lo[7]));
+                make_uint4(ptx::pack_h2<F16>(lo[0], lo[1]), ptx::pack_h2<F16>(lo[2], lo[3]), ptx::pack_h2<F16>(lo[4], lo[5]),
+                           ptx::pack_h2<F16>(lo[6], lo[7]));
           }
         }
       }

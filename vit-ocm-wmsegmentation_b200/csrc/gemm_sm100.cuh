@@ -20,6 +20,8 @@
 // (A_PATCH: warps 2, 3 and six more warps after the epilogue warps are the A producers) (lane quadrant = warp % 4,
 // column group = (warp - 4) / 4).
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace vitocm {
@@ -37,8 +39,13 @@ enum GemmEpilogue : int {
 struct GemmArgs {
   int M, N;
   int kblocks;        // K / 64 per term
-  int nterms;         // 1 (bf16 mode) or 3 (split mode: hi*hi + hi*lo + lo*hi)
+  int nterms;         // 1 (single 16-bit operands), 3 (split mode: hi*hi + hi*lo + lo*hi) or 2 (A split only: hi*hi + lo*hi)
   int lo_k;           // split mode: column where the lo halves of A and B start (= K)
+  int a_lo_mask;      // bit t set: term t reads the lo half of A   (3 terms: 0b100, 2 terms: 0b10)
+  int b_lo_mask;      // bit t set: term t reads the lo half of B   (3 terms: 0b010, 2 terms: 0)
+  int gelu_mode;      // EPI_BIAS_GELU_BF16: 0 = three-coefficient sigmoid form (bf16 outputs), 1 = erff (fp32-parity mode),
+                      // 2 = five-coefficient sigmoid form (fp16 outputs)
+  int f16;            // 16-bit operand format of A, B and of bf16-typed outputs: 0 = bf16, 1 = IEEE fp16 (fp16 engines)
   const float* bias;  // [N] or nullptr
   int split_out;      // bf16 outputs only: 1 = also write lo = bf16(v - hi) at column offset lo_off;
                       // 2 (EPI_BIAS_GELU_BF16, training) = also write the pre-activation acc + bias at column offset lo_off
@@ -143,6 +150,24 @@ __device__ __forceinline__ float u8_unit(uint32_t b) {
   return __fmaf_rn(__fmaf_rn(-q, 255.0f, v), R, q);
 }
 
+// 8 consecutive A-tile values of the patch embedding -> one 16-byte shared-memory store: the hi part, or lo = v - hi, in the
+// engine's 16-bit format (the format branch is warp uniform)
+__device__ __forceinline__ void patch_store8(uint32_t addr, float (&v)[8], bool want_lo, bool f16) {
+  if (f16) {
+    if (want_lo) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] -= ptx::f16_round(v[j]);
+    }
+    ptx::sts_v4(addr, ptx::pack_f16x2(v[0], v[1]), ptx::pack_f16x2(v[2], v[3]), ptx::pack_f16x2(v[4], v[5]), ptx::pack_f16x2(v[6], v[7]));
+  } else {
+    if (want_lo) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] -= ptx::bf16_round(v[j]);
+    }
+    ptx::sts_v4(addr, ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+  }
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
   // nn.GELU() default (approximate='none'): x * Phi(x)
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
@@ -164,6 +189,30 @@ __device__ __forceinline__ void gelu_sigmoid_x2(float& x0, float& x1) {
   // coefficients pre-multiplied by -log2(e):  ex2(x * w) = exp(-x (a + b u + c u^2))
   uint64_t w = ptx::fma_f32x2(u, ptx::dup_f32x2(0.0010142630596f), ptx::dup_f32x2(-0.1067757240f));
   w = ptx::fma_f32x2(w, u, ptx::dup_f32x2(-2.3011213394f));
+  const uint64_t arg = ptx::mul_f32x2(x2, w);
+  float a0, a1;
+  ptx::unpack_f32x2(arg, a0, a1);
+  const uint64_t den = ptx::add_f32x2(ptx::pack_f32x2(ptx::ex2_approx(a0), ptx::ex2_approx(a1)), ptx::dup_f32x2(1.0f));
+  float d0, d1;
+  ptx::unpack_f32x2(den, d0, d1);
+  const uint64_t r = ptx::mul_f32x2(x2, ptx::pack_f32x2(ptx::rcp_approx(d0), ptx::rcp_approx(d1)));
+  ptx::unpack_f32x2(r, x0, x1);
+}
+
+// Five-coefficient member of the same family for fp16 engines (their outputs keep 11 significand bits, so the 2.5e-5 of the
+// three-coefficient fit would show): Phi(x) ~= sigmoid(x (c0 + c1 u + c2 u^2 + c3 u^3 + c4 u^4)), u = min(x^2, 30), max |error|
+// of gelu 3.0e-6 over [-8, 8] (fitted like the above; tests/test_gpu_kernels.py checks it against erf): two more FFMA2 per pair.
+__device__ __forceinline__ void gelu_sigmoid5_x2(float& x0, float& x1) {
+  const uint64_t x2 = ptx::pack_f32x2(x0, x1);
+  const uint64_t sq = ptx::mul_f32x2(x2, x2);
+  float u0, u1;
+  ptx::unpack_f32x2(sq, u0, u1);
+  const uint64_t u = ptx::pack_f32x2(fminf(u0, 30.f), fminf(u1, 30.f));
+  // coefficients pre-multiplied by -log2(e)
+  uint64_t w = ptx::fma_f32x2(u, ptx::dup_f32x2(-3.2290010e-06f), ptx::dup_f32x2(8.8238336e-05f));
+  w = ptx::fma_f32x2(w, u, ptx::dup_f32x2(3.6027357e-04f));
+  w = ptx::fma_f32x2(w, u, ptx::dup_f32x2(-0.10522669f));
+  w = ptx::fma_f32x2(w, u, ptx::dup_f32x2(-2.3020453f));
   const uint64_t arg = ptx::mul_f32x2(x2, w);
   float a0, a1;
   ptx::unpack_f32x2(arg, a0, a1);
@@ -313,9 +362,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const int term = A_PATCH ? it % args.nterms : it / args.kblocks;
           const int kb = A_PATCH ? it / args.nterms : it - term * args.kblocks;
           ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1, 1);
-          // split mode terms: (hi,hi) (hi,lo) (lo,hi); lo halves start at column K of each operand
-          const int a_off = (term == 2 ? args.lo_k : 0) + kb * GEMM_BK;
-          const int b_off = (term == 1 ? args.lo_k : 0) + kb * GEMM_BK;
+          // split mode terms: (hi,hi) (hi,lo) (lo,hi), or (hi,hi) (lo,hi) with a single-precision B; lo halves start at column K
+          const int a_off = (((args.a_lo_mask >> term) & 1) ? args.lo_k : 0) + kb * GEMM_BK;
+          const int b_off = (((args.b_lo_mask >> term) & 1) ? args.lo_k : 0) + kb * GEMM_BK;
           if (PAIR) {
             // both CTAs load into their own stage; all bytes complete on the leader's full barrier
             if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * Cfg::STAGE_BYTES);
@@ -335,7 +384,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // One elected thread issues (elect.sync lets ptxas emit the tcgen05 instructions without a per-instruction
     // leader-election loop); descriptors are advanced by compile-time constants in fully unrolled loops.
     if ((!PAIR || cta_rank == 0) && ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc(TILE_M, BN, false, false);
+      const uint32_t idesc = ptx::make_idesc(TILE_M, BN, false, false, args.f16 ? 0u : 1u);
       const uint64_t a_desc0 = ptx::make_smem_desc_sw128(smem_a, 1024, 0);
       const uint64_t b_desc0 = ptx::make_smem_desc_sw128(smem_b, 1024, 0);
       int stage = 0;
@@ -391,7 +440,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int it = 0; it < k_iters; ++it) {
           const int term = it % args.nterms;
           const int kb = it / args.nterms;
-          const bool want_lo = term == 2;
+          const bool want_lo = ((args.a_lo_mask >> term) & 1) != 0;
           ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1, 5);
           const uint32_t a_tile = smem_a + stage * Cfg::A_BYTES;
           // 4 items per thread: all 8 loads are issued before the first conversion so that their latencies overlap
@@ -436,12 +485,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 v[j] = u8_unit((raw[u].x >> (8 * j)) & 0xffu);
                 v[4 + j] = u8_unit((raw[u].y >> (8 * j)) & 0xffu);
               }
-              if (want_lo) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] -= ptx::bf16_round(v[j]);
-              }
-              ptx::sts_v4(a_tile + row * 128 + ((chunk ^ (row & 7)) << 4), ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]),
-                          ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+              patch_store8(a_tile + row * 128 + ((chunk ^ (row & 7)) << 4), v, want_lo, args.f16 != 0);
             }
           } else {
             float4 f[4][2];
@@ -471,12 +515,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               const int chunk = item >> 7;
               const int row = item & 127;
               float v[8] = {f[u][0].x, f[u][0].y, f[u][0].z, f[u][0].w, f[u][1].x, f[u][1].y, f[u][1].z, f[u][1].w};
-              if (want_lo) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] -= ptx::bf16_round(v[j]);
-              }
-              ptx::sts_v4(a_tile + row * 128 + ((chunk ^ (row & 7)) << 4), ptx::pack_bf16x2(v[0], v[1]), ptx::pack_bf16x2(v[2], v[3]),
-                          ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+              patch_store8(a_tile + row * 128 + ((chunk ^ (row & 7)) << 4), v, want_lo, args.f16 != 0);
             }
           }
           ptx::fence_proxy_async_smem();
@@ -611,13 +650,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int g = 0; g < 2; ++g) {
           const int col = col_base + g * 32;
           uint32_t pk[16];
+          auto norm_pack = [&](auto f16_tag) {
+            constexpr bool F16 = decltype(f16_tag)::value;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(args.ln_gamma + col) + j);
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.ln_beta + col) + j);
-            pk[2 * j] = ptx::pack_bf16x2((y[g][4 * j] - mean) * rstd * g4.x + b4.x, (y[g][4 * j + 1] - mean) * rstd * g4.y + b4.y);
-            pk[2 * j + 1] = ptx::pack_bf16x2((y[g][4 * j + 2] - mean) * rstd * g4.z + b4.z, (y[g][4 * j + 3] - mean) * rstd * g4.w + b4.w);
-          }
+            for (int j = 0; j < 8; ++j) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(args.ln_gamma + col) + j);
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.ln_beta + col) + j);
+              pk[2 * j] = ptx::pack_h2<F16>((y[g][4 * j] - mean) * rstd * g4.x + b4.x, (y[g][4 * j + 1] - mean) * rstd * g4.y + b4.y);
+              pk[2 * j + 1] = ptx::pack_h2<F16>((y[g][4 * j + 2] - mean) * rstd * g4.z + b4.z, (y[g][4 * j + 3] - mean) * rstd * g4.w + b4.w);
+            }
+          };
+          if (args.f16) norm_pack(std::true_type{}); else norm_pack(std::false_type{});
           if (g == 1) {   // the bf16 box is still being read by the first chunk's store
             if (lane == 0) ptx::bulk_wait_read0();
             __syncwarp();
@@ -715,9 +758,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int j = 0; j < 16; ++j) pre[j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
         }
         if (EPI == EPI_BIAS_GELU_BF16) {
-          if (args.nterms == 1) {
+          if (args.gelu_mode == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2) gelu_sigmoid_x2(v[j], v[j + 1]);
+          } else if (args.gelu_mode == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) gelu_sigmoid5_x2(v[j], v[j + 1]);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
@@ -755,22 +801,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           // 32 rows x 64 B, SWIZZLE_64B: 16-byte chunk j of row r sits at r*64 + ((j ^ ((r >> 1) & 3)) << 4)
           const uint32_t rowaddr = stg + lane * 64;
           const int sw = (lane >> 1) & 3;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            ptx::sts_v4(rowaddr + ((j ^ sw) << 4), ptx::pack_bf16x2(v[8 * j], v[8 * j + 1]), ptx::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                        ptx::pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), ptx::pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-          if (EPI == EPI_BIAS_GELU_BF16 && args.split_out == 2) {
+          auto put_rows = [&](auto f16_tag) {   // hi (and lo = v - hi) in the engine's 16-bit format; the format branch is warp uniform
+            constexpr bool F16 = decltype(f16_tag)::value;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              ptx::sts_v4(rowaddr + Cfg::STG_BOX_BYTES + ((j ^ sw) << 4), pre[4 * j], pre[4 * j + 1], pre[4 * j + 2], pre[4 * j + 3]);
-          } else if (args.split_out) {
+              ptx::sts_v4(rowaddr + ((j ^ sw) << 4), ptx::pack_h2<F16>(v[8 * j], v[8 * j + 1]), ptx::pack_h2<F16>(v[8 * j + 2], v[8 * j + 3]),
+                          ptx::pack_h2<F16>(v[8 * j + 4], v[8 * j + 5]), ptx::pack_h2<F16>(v[8 * j + 6], v[8 * j + 7]));
+            if (EPI == EPI_BIAS_GELU_BF16 && args.split_out == 2) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] -= ptx::bf16_round(v[j]);
+              for (int j = 0; j < 4; ++j)
+                ptx::sts_v4(rowaddr + Cfg::STG_BOX_BYTES + ((j ^ sw) << 4), pre[4 * j], pre[4 * j + 1], pre[4 * j + 2], pre[4 * j + 3]);
+            } else if (args.split_out) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              ptx::sts_v4(rowaddr + Cfg::STG_BOX_BYTES + ((j ^ sw) << 4), ptx::pack_bf16x2(v[8 * j], v[8 * j + 1]), ptx::pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                          ptx::pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), ptx::pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-          }
+              for (int j = 0; j < 32; ++j) v[j] -= ptx::round_h<F16>(v[j]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                ptx::sts_v4(rowaddr + Cfg::STG_BOX_BYTES + ((j ^ sw) << 4), ptx::pack_h2<F16>(v[8 * j], v[8 * j + 1]), ptx::pack_h2<F16>(v[8 * j + 2], v[8 * j + 3]),
+                            ptx::pack_h2<F16>(v[8 * j + 4], v[8 * j + 5]), ptx::pack_h2<F16>(v[8 * j + 6], v[8 * j + 7]));
+            }
+          };
+          if (args.f16) put_rows(std::true_type{}); else put_rows(std::false_type{});
         } else {
           // 32 rows x 128 B, SWIZZLE_128B: chunk j of row r sits at r*128 + ((j ^ (r & 7)) << 4)
           const uint32_t rowaddr = stg + lane * 128;

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -381,6 +382,36 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// IEEE fp16 operands (fp16 engines: 11 significand bits instead of bf16's 8 at the same tensor-core rate; the narrower
+// exponent range is handled by saturating conversions -- 65504 instead of inf)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t v;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(v) : "f"(hi), "f"(lo));
+  return v;
+}
+__device__ __forceinline__ float f16_round(float x) {
+  unsigned short h;
+  float f;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
+  return f;
+}
+// 16-bit operand format selected at compile time (F16) ...
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) { return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+template <bool F16>
+__device__ __forceinline__ float round_h(float x) { return F16 ? f16_round(x) : bf16_round(x); }
+// ... or by a warp-uniform run-time flag (callers branch once per chunk of values, not per value)
+__device__ __forceinline__ uint32_t pack_h2(bool f16, float lo, float hi) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+__device__ __forceinline__ float round_h(bool f16, float x) { return f16 ? f16_round(x) : bf16_round(x); }
+__device__ __forceinline__ float h16_to_f32(bool f16, unsigned short bits) {
+  if (f16) {
+    float f;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(bits));
+    return f;
+  }
+  return __uint_as_float(static_cast<uint32_t>(bits) << 16);
+}
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -362,7 +362,7 @@ struct RepackEntry {
   int tiles_c;            // tiles per row of tiles
 };
 __global__ void __launch_bounds__(256)
-repack_weights_kernel(const RepackEntry* __restrict__ table, int n_entries) {
+repack_weights_kernel(const RepackEntry* __restrict__ table, int n_entries, int f16 = 0 /*fp16 engines: IEEE half operands*/) {
   __shared__ float tile[32][33];
   int lo = 0, hi = n_entries - 1;
   const int t = blockIdx.x;
@@ -379,7 +379,8 @@ repack_weights_kernel(const RepackEntry* __restrict__ table, int n_entries) {
     float v = 0.f;
     if (r < e.R && c < e.C) {
       v = e.src[static_cast<long long>(r) * e.C + c];
-      e.dst[static_cast<long long>(r) * e.C + c] = __float2bfloat16_rn(v);
+      if (f16) reinterpret_cast<__half*>(e.dst)[static_cast<long long>(r) * e.C + c] = __float2half_rn(ptx::f16_round(v));
+      else e.dst[static_cast<long long>(r) * e.C + c] = __float2bfloat16_rn(v);
     }
     tile[k][tx] = v;
   }
@@ -387,7 +388,10 @@ repack_weights_kernel(const RepackEntry* __restrict__ table, int n_entries) {
   __syncthreads();
   for (int k = ty; k < 32; k += 8) {
     const int c = c0 + k, r = r0 + tx;
-    if (c < e.C && r < e.R) e.dst_t[static_cast<long long>(c) * e.R + r] = __float2bfloat16_rn(tile[tx][k]);
+    if (c < e.C && r < e.R) {
+      if (f16) reinterpret_cast<__half*>(e.dst_t)[static_cast<long long>(c) * e.R + r] = __float2half_rn(ptx::f16_round(tile[tx][k]));
+      else e.dst_t[static_cast<long long>(c) * e.R + r] = __float2bfloat16_rn(tile[tx][k]);
+    }
   }
 }
 

@@ -44,7 +44,8 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ out_bf16, long long ldo, int split, int lo_off,
-                 float* __restrict__ out_f32, long long ldf, int M, int D, float eps, float* __restrict__ x_copy = nullptr) {
+                 float* __restrict__ out_f32, long long ldf, int M, int D, float eps, float* __restrict__ x_copy = nullptr,
+                 int f16 = 0 /*16-bit output format: 0 = bf16, 1 = IEEE fp16*/) {
   constexpr int CNT = NV > 0 ? NV : LN_MAX_VEC;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -88,11 +89,20 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
       y.w = (v[i].w - mean) * rstd * g.w + bb.w;
       if (out_bf16 != nullptr) {
         __nv_bfloat16* o = out_bf16 + static_cast<long long>(row) * ldo + idx * 4;
-        *reinterpret_cast<uint2*>(o) = make_uint2(ptx::pack_bf16x2(y.x, y.y), ptx::pack_bf16x2(y.z, y.w));
-        if (split) {
-          *reinterpret_cast<uint2*>(o + lo_off) =
-              make_uint2(ptx::pack_bf16x2(y.x - ptx::bf16_round(y.x), y.y - ptx::bf16_round(y.y)),
-                         ptx::pack_bf16x2(y.z - ptx::bf16_round(y.z), y.w - ptx::bf16_round(y.w)));
+        if (f16) {
+          *reinterpret_cast<uint2*>(o) = make_uint2(ptx::pack_f16x2(y.x, y.y), ptx::pack_f16x2(y.z, y.w));
+          if (split) {
+            *reinterpret_cast<uint2*>(o + lo_off) =
+                make_uint2(ptx::pack_f16x2(y.x - ptx::f16_round(y.x), y.y - ptx::f16_round(y.y)),
+                           ptx::pack_f16x2(y.z - ptx::f16_round(y.z), y.w - ptx::f16_round(y.w)));
+          }
+        } else {
+          *reinterpret_cast<uint2*>(o) = make_uint2(ptx::pack_bf16x2(y.x, y.y), ptx::pack_bf16x2(y.z, y.w));
+          if (split) {
+            *reinterpret_cast<uint2*>(o + lo_off) =
+                make_uint2(ptx::pack_bf16x2(y.x - ptx::bf16_round(y.x), y.y - ptx::bf16_round(y.y)),
+                           ptx::pack_bf16x2(y.z - ptx::bf16_round(y.z), y.w - ptx::bf16_round(y.w)));
+          }
         }
       }
       if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * ldf)[idx] = y;
@@ -297,14 +307,15 @@ mim_shuffle_loss_kernel(const float* __restrict__ Y, const float* __restrict__ x
 
 // bf16 (hi [+ lo]) activation -> fp32 (qkv / ctx export for the API-complete path)
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, long long ldi, int split, int lo_off,
-                                   float* __restrict__ out, long long ldo, int M, int ncols) {
+                                   float* __restrict__ out, long long ldo, int M, int ncols, int f16 = 0) {
+  const unsigned short* in16 = reinterpret_cast<const unsigned short*>(in);
   const long long total = static_cast<long long>(M) * ncols;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / ncols;
     const int c = static_cast<int>(i - r * ncols);
-    float v = __bfloat162float(in[r * ldi + c]);
-    if (split) v += __bfloat162float(in[r * ldi + lo_off + c]);
+    float v = ptx::h16_to_f32(f16 != 0, in16[r * ldi + c]);
+    if (split) v += ptx::h16_to_f32(f16 != 0, in16[r * ldi + lo_off + c]);
     out[r * ldo + c] = v;
   }
 }
@@ -322,16 +333,23 @@ __global__ void fold_patch_weight_kernel(const float* __restrict__ w, float* __r
 
 // fp32 [R, C] weight -> bf16 hi (and lo) [R, ldo]  (weight repack at load time)
 __global__ void split_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, long long ldo, int split,
-                                    int lo_off, int R, int C) {
+                                    int lo_off, int R, int C, int f16 = 0) {
   const long long total = static_cast<long long>(R) * C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / C;
     const int c = static_cast<int>(i - r * C);
     const float v = w[i];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    out[r * ldo + c] = hi;
-    if (split) out[r * ldo + lo_off + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    if (f16) {
+      __half* oh = reinterpret_cast<__half*>(out);
+      const float hi = ptx::f16_round(v);
+      oh[r * ldo + c] = __float2half_rn(hi);
+      if (split) oh[r * ldo + lo_off + c] = __float2half_rn(ptx::f16_round(v - hi));
+    } else {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      out[r * ldo + c] = hi;
+      if (split) out[r * ldo + lo_off + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
   }
 }
 

@@ -147,8 +147,12 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct vitocm_engine {
   vitocm_config cfg{};
-  int split = 0;
+  int split = 0;         // fp32-parity mode: every operand a (hi, lo) pair, three MMAs per product
   int parts = 1;
+  int f16 = 0;           // fp16 engines: all 16-bit tensor-core operands are IEEE half instead of bf16
+  std::vector<int> layer_mode;   // per block: 0 = the engine's mode; 1 = fc1 / fc2 read their activations as (hi, lo) pairs (two MMAs
+                                 // per product, single-precision weights): vitocm_set_layer_mode
+  bool any_mlp_split() const { for (int m : layer_mode) if (m == 1) return true; return false; }
   int num_sms = 148;
   bool finalized = false;
   std::map<std::string, DevBuf*> master;  // fp32 weights as loaded
@@ -355,17 +359,19 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
   // measured (profiles/r01_gemm_pair.txt): pairs win once the launch is long enough to amortise the cluster lockstep
   // (M = 137k: qkv +21 %, fc2 +6 %, fc1 +3 %) and for long K at any size; mode 2 forces pairs wherever legal
   const bool pair_pays = pair_mode == 2 || M >= 65536 || (K >= 1024 && M >= 4096);
-  if (pair_mode != 0 && pair_pays && !split_in && split_out != 1 && M >= 4 * GEMM_BM && (N % 256 == 0 || N % 192 == 0 || N % 128 == 0)) {
+  if (pair_mode != 0 && pair_pays && split_in != 1 && M >= 4 * GEMM_BM && (N % 256 == 0 || N % 192 == 0 || N % 128 == 0)) {
     static const int gelu_bn = [] { const char* v = getenv("VITOCM_GELU_BN"); return v ? atoi(v) : 192; }();   // measured: 835 vs 794 TFLOP/s
     int pbn = N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 128);
     if ((epi == EPI_BIAS_GELU_BF16 || epi == EPI_DGELU_BF16) && gelu_bn == 192 && N % 192 == 0) pbn = 192;   // 12 epilogue warps instead of 8
     const bool of32 = (epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_F32);
     CUtensorMap pa, pb, pc;
-    TRY(make_tmap_bf16(&pa, A, M, K, lda, GEMM_BM));
+    TRY(make_tmap_bf16(&pa, A, M, split_in == 2 ? 2LL * K : K, lda, GEMM_BM));
     TRY(make_tmap_bf16(&pb, B, N, K, ldb, pbn / 2));
     TRY(make_tmap(&pc, out, of32, ldo, M, ldo, 32, 32, of32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
     GemmArgs pg{};
-    pg.M = M; pg.N = N; pg.kblocks = K / GEMM_BK; pg.nterms = 1; pg.lo_k = K; pg.bias = bias; pg.out_f32 = reinterpret_cast<float*>(out);
+    pg.M = M; pg.N = N; pg.kblocks = K / GEMM_BK; pg.nterms = split_in == 2 ? 2 : 1; pg.lo_k = K; pg.a_lo_mask = split_in == 2 ? 2 : 0; pg.b_lo_mask = 0;
+    pg.f16 = e->f16; pg.gelu_mode = e->f16 ? 2 : 0;
+    pg.bias = bias; pg.out_f32 = reinterpret_cast<float*>(out);
     pg.split_out = split_out; pg.lo_off = lo_off;
     pg.pre = reinterpret_cast<const __nv_bfloat16*>(pre); pg.ld_pre = ld_pre;
     CUtensorMap pd;
@@ -388,10 +394,13 @@ int run_gemm(const vitocm_engine* e, const void* A, long long lda, const void* B
   const bool out_f32 = (epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_F32);
   CUtensorMap ta, tb, tc;
   TRY(make_tmap_bf16(&ta, A, M, kext, lda, GEMM_BM));
-  TRY(make_tmap_bf16(&tb, B, N, kext, ldb, bn));
+  TRY(make_tmap_bf16(&tb, B, N, split_in == 2 ? K : kext, ldb, bn));
   TRY(make_tmap(&tc, out, out_f32, ldo, M, ldo, 32, 32, out_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
   GemmArgs a{};
-  a.M = M; a.N = N; a.kblocks = K / GEMM_BK; a.nterms = split_in ? 3 : 1;
+  // split_in: 0 = single operands (1 MMA per product); 1 = A and B as (hi, lo) pairs, hi*hi + hi*lo + lo*hi; 2 = A as a pair, B single
+  a.M = M; a.N = N; a.kblocks = K / GEMM_BK; a.nterms = split_in == 1 ? 3 : (split_in == 2 ? 2 : 1);
+  a.a_lo_mask = split_in == 1 ? 4 : (split_in == 2 ? 2 : 0); a.b_lo_mask = split_in == 1 ? 2 : 0;
+  a.f16 = e->f16; a.gelu_mode = split_in == 1 ? 1 : (e->f16 ? 2 : 0);
   a.lo_k = K;
   a.bias = bias; a.split_out = split_out; a.lo_off = lo_off;
   static const int dbg = [] { const char* v = getenv("VITOCM_GEMM_DEBUG"); return v ? atoi(v) : 0; }();
@@ -432,7 +441,7 @@ int run_gemm_ln(const vitocm_engine* e, const void* A, long long lda, const void
   TRY(make_tmap(&tc, X, true, N, M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
   TRY(make_tmap(&td, XN, false, ld_xn, M, ld_xn, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   GemmArgs a{};
-  a.M = M; a.N = N; a.kblocks = K / GEMM_BK; a.nterms = 1; a.lo_k = K;
+  a.M = M; a.N = N; a.kblocks = K / GEMM_BK; a.nterms = 1; a.lo_k = K; a.f16 = e->f16;
   a.bias = bias; a.out_f32 = X;
   a.ln_gamma = gamma; a.ln_beta = beta; a.ln_eps = eps;
   a.xn = reinterpret_cast<__nv_bfloat16*>(XN); a.ld_xn = ld_xn;
@@ -480,36 +489,37 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
     kern<<<grid, ATT_THREADS, smem_bytes, st>>>(tq, tq32, a);
     return 0;
   };
-  // fraction of the exponentials moved from MUFU to the FMA pipe (bf16 mode): tuning knob, default from measurement
-  static const int poly = [] { const char* v = getenv("VITOCM_ATTN_POLY"); return v ? atoi(v) : ATT_POLY_DEFAULT; }();
+  // (the FMA-pipe exp2 polynomial variants of round 1 measured 15-19 % slower and are no longer instantiated)
   static bool attr[8] = {false, false, false, false, false, false, false, false};
   if (a.pack > 1) {   // kernels with the packed-item logic
-    if (e->split) TRY(launch(attn_fwd_tcgen05_kernel<true, 0u, true>, AttnCfg<true>::SMEM_BYTES, attr[3]));
-    else if (poly == 1) TRY(launch(attn_fwd_tcgen05_kernel<false, 0x1248u, true>, AttnCfg<false>::SMEM_BYTES, attr[1]));   // 4 of 16 pairs
-    else if (poly == 2) TRY(launch(attn_fwd_tcgen05_kernel<false, 0x5529u, true>, AttnCfg<false>::SMEM_BYTES, attr[2]));   // 7 of 16 pairs
-    else TRY(launch(attn_fwd_tcgen05_kernel<false, 0u, true>, AttnCfg<false>::SMEM_BYTES, attr[0]));
+    if (e->split) {
+      if (e->f16) TRY(launch(attn_fwd_tcgen05_kernel<true, 0u, true, true>, AttnCfg<true>::SMEM_BYTES, attr[1]));
+      else TRY(launch(attn_fwd_tcgen05_kernel<true, 0u, true, false>, AttnCfg<true>::SMEM_BYTES, attr[3]));
+    } else if (e->f16) TRY(launch(attn_fwd_tcgen05_kernel<false, 0u, true, true>, AttnCfg<false>::SMEM_BYTES, attr[2]));
+    else TRY(launch(attn_fwd_tcgen05_kernel<false, 0u, true, false>, AttnCfg<false>::SMEM_BYTES, attr[0]));
   } else {
-    if (e->split) TRY(launch(attn_fwd_tcgen05_kernel<true, 0u, false>, AttnCfg<true>::SMEM_BYTES, attr[7]));
-    else if (poly == 1) TRY(launch(attn_fwd_tcgen05_kernel<false, 0x1248u, false>, AttnCfg<false>::SMEM_BYTES, attr[5]));
-    else if (poly == 2) TRY(launch(attn_fwd_tcgen05_kernel<false, 0x5529u, false>, AttnCfg<false>::SMEM_BYTES, attr[6]));
-    else TRY(launch(attn_fwd_tcgen05_kernel<false, 0u, false>, AttnCfg<false>::SMEM_BYTES, attr[4]));
+    if (e->split) {
+      if (e->f16) TRY(launch(attn_fwd_tcgen05_kernel<true, 0u, false, true>, AttnCfg<true>::SMEM_BYTES, attr[5]));
+      else TRY(launch(attn_fwd_tcgen05_kernel<true, 0u, false, false>, AttnCfg<true>::SMEM_BYTES, attr[7]));
+    } else if (e->f16) TRY(launch(attn_fwd_tcgen05_kernel<false, 0u, false, true>, AttnCfg<false>::SMEM_BYTES, attr[6]));
+    else TRY(launch(attn_fwd_tcgen05_kernel<false, 0u, false, false>, AttnCfg<false>::SMEM_BYTES, attr[4]));
   }
   LAUNCH_CHECK();
   return 0;
 }
 
 int run_layernorm(const float* X, const float* g, const float* b, void* out_bf16, long long ldo, int split, int lo_off,
-                  float* out_f32, long long ldf, int M, int D, float eps, cudaStream_t st, float* x_copy = nullptr) {
+                  float* out_f32, long long ldf, int M, int D, float eps, cudaStream_t st, float* x_copy = nullptr, int f16 = 0) {
   if (M <= 0) return 0;
   if (D % 4 != 0 || D > LN_MAX_VEC * 128) return fail(VITOCM_ERR_INVALID, "LayerNorm D=%d unsupported", D);
   ProfScope prof(PC_LN, st);
   const int rows_per_block = 8;
   const dim3 grid((M + rows_per_block - 1) / rows_per_block), block(rows_per_block * 32);
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  if (D == 384) layernorm_kernel<3><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps, x_copy);
-  else if (D == 768) layernorm_kernel<6><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps, x_copy);
-  else if (D == 128) layernorm_kernel<1><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps, x_copy);
-  else layernorm_kernel<0><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps, x_copy);
+  if (D == 384) layernorm_kernel<3><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps, x_copy, f16);
+  else if (D == 768) layernorm_kernel<6><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps, x_copy, f16);
+  else if (D == 128) layernorm_kernel<1><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps, x_copy, f16);
+  else layernorm_kernel<0><<<grid, block, 0, st>>>(X, g, b, ob, ldo, split, lo_off, out_f32, ldf, M, D, eps, x_copy, f16);
   LAUNCH_CHECK();
   return 0;
 }
@@ -545,7 +555,7 @@ int run_patch_embed(const vitocm_engine* e, const float* x, int B, int H, int W,
   CUtensorMap tb;
   TRY(make_tmap_bf16(&tb, gray ? e->patch_w_gray.p : e->patch_w.p, D, 2LL * K, 2LL * K, bn));
   GemmArgs a{};
-  a.M = M; a.N = D; a.kblocks = K / GEMM_BK; a.nterms = 3; a.lo_k = K;   // split precision in both modes
+  a.M = M; a.N = D; a.kblocks = K / GEMM_BK; a.nterms = 3; a.lo_k = K; a.a_lo_mask = 4; a.b_lo_mask = 2; a.f16 = e->f16;   // split precision in all modes
   a.bias = e->w("patch_embed.proj.bias");
   a.img = x; a.img_h = H; a.img_w = W; a.patch = p; a.n_patches = n; a.pos = pos; a.mask = mask; a.mask_token = mask_token; a.out_f32 = X;
   if (mos != nullptr) { a.mos = mos->p; a.mos_pitch = mos->pitch; a.mos_h = mos->h; a.mos_w = mos->w; a.mos_n = mos->n; a.mos_S = mos->S; a.mos_t0 = mos->t0; }
@@ -576,7 +586,7 @@ Workspace carve(const vitocm_engine* e, void* base, int tiles, int N) {
   w.XN = reinterpret_cast<__nv_bfloat16*>(take(M * 2 * D * 2));
   w.QKV = reinterpret_cast<__nv_bfloat16*>(take(M * 3 * D * P * 2));
   w.CTX = reinterpret_cast<__nv_bfloat16*>(take(M * D * P * 2));
-  size_t hid = M * Hd * P * 2;
+  size_t hid = M * Hd * (e->any_mlp_split() ? 2 : P) * 2;
   if (hid < M * D * 4) hid = M * D * 4;
   w.HID = reinterpret_cast<__nv_bfloat16*>(take(hid));
   w.total = off;
@@ -593,29 +603,35 @@ int block_forward(const vitocm_engine* e, int l, const Workspace& ws, int B, int
   const int D = e->cfg.embed_dim, Hd = e->cfg.mlp_hidden, P = e->parts, S = e->split;
   const int M = B * N;
   if (xn_done != nullptr) *xn_done = false;
-  if (!xn_ready) TRY(run_layernorm(ws.X, L.ln1w, L.ln1b, ws.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
+  if (!xn_ready) TRY(run_layernorm(ws.X, L.ln1w, L.ln1b, ws.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st, nullptr, e->f16));
   TRY(run_gemm(e, ws.XN, 2LL * D, L.wqkv.p, static_cast<long long>(D) * P, M, 3 * D, D, S, EPI_BIAS_BF16, L.bqkv, ws.QKV,
                3LL * D * P, S, 3 * D, st, PC_GEMM_QKV));
   TRY(run_attention(e, ws.QKV, 3LL * D * P, B, N, ws.CTX, static_cast<long long>(D) * P, st));
+  // MLP of an act-split block (vitocm_set_layer_mode 1): norm2's output and the hidden activations are kept as (hi, lo) pairs and
+  // fc1 / fc2 contract both halves against the single-precision weights (two MMAs per product) -- the rounding of these two
+  // activations is where most of the CLS-row error of a 16-bit forward comes from (profiles/r02_precision_sim.txt)
+  const bool mlp2 = !S && l < static_cast<int>(e->layer_mode.size()) && e->layer_mode[l] == 1;
   // proj + residual (+ norm2 fused when possible)
-  int rc = run_gemm_ln(e, ws.CTX, static_cast<long long>(D) * P, L.wproj.p, static_cast<long long>(D) * P, M, D, D, L.bproj, ws.X,
-                       L.ln2w, L.ln2b, e->cfg.ln_eps, ws.XN, 2LL * D, st, PC_GEMM_PROJ);
+  int rc = mlp2 ? 1 : run_gemm_ln(e, ws.CTX, static_cast<long long>(D) * P, L.wproj.p, static_cast<long long>(D) * P, M, D, D, L.bproj, ws.X,
+                                  L.ln2w, L.ln2b, e->cfg.ln_eps, ws.XN, 2LL * D, st, PC_GEMM_PROJ);
   if (rc < 0) return rc;
   if (rc == 1) {
     TRY(run_gemm(e, ws.CTX, static_cast<long long>(D) * P, L.wproj.p, static_cast<long long>(D) * P, M, D, D, S,
                  EPI_BIAS_RESID_F32, L.bproj, ws.X, D, 0, 0, st, PC_GEMM_PROJ));
-    TRY(run_layernorm(ws.X, L.ln2w, L.ln2b, ws.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
+    TRY(run_layernorm(ws.X, L.ln2w, L.ln2b, ws.XN, 2LL * D, S || mlp2, D, nullptr, 0, M, D, e->cfg.ln_eps, st, nullptr, e->f16));
   }
-  TRY(run_gemm(e, ws.XN, 2LL * D, L.w1.p, static_cast<long long>(D) * P, M, Hd, D, S, EPI_BIAS_GELU_BF16, L.b1, ws.HID,
-               static_cast<long long>(Hd) * P, S, Hd, st, PC_GEMM_FC1));
+  const int HP = mlp2 ? 2 : P;        // hidden activations: (hi | lo) in split engines and in act-split blocks
+  const int mlp_in = S ? 1 : (mlp2 ? 2 : 0);
+  TRY(run_gemm(e, ws.XN, 2LL * D, L.w1.p, static_cast<long long>(D) * P, M, Hd, D, mlp_in, EPI_BIAS_GELU_BF16, L.b1, ws.HID,
+               static_cast<long long>(Hd) * HP, S || mlp2, Hd, st, PC_GEMM_FC1));
   // fc2 + residual (+ the next block's norm1 fused when possible)
   rc = 1;
-  if (next_ln_w != nullptr)
+  if (next_ln_w != nullptr && !mlp2)
     rc = run_gemm_ln(e, ws.HID, static_cast<long long>(Hd) * P, L.w2.p, static_cast<long long>(Hd) * P, M, D, Hd, L.b2, ws.X, next_ln_w,
                      next_ln_b, e->cfg.ln_eps, ws.XN, 2LL * D, st, PC_GEMM_FC2);
   if (rc < 0) return rc;
   if (rc == 1) {
-    TRY(run_gemm(e, ws.HID, static_cast<long long>(Hd) * P, L.w2.p, static_cast<long long>(Hd) * P, M, D, Hd, S,
+    TRY(run_gemm(e, ws.HID, static_cast<long long>(Hd) * HP, L.w2.p, static_cast<long long>(Hd) * P, M, D, Hd, mlp_in,
                  EPI_BIAS_RESID_F32, L.b2, ws.X, D, 0, 0, st, PC_GEMM_FC2));
   } else if (xn_done != nullptr) {
     *xn_done = true;
@@ -665,7 +681,7 @@ int vitocm_create(const vitocm_config* cfg, vitocm_engine** out) {
   if (cfg->num_heads <= 0 || cfg->embed_dim != cfg->num_heads * 64)
     return fail(VITOCM_ERR_INVALID, "head_dim must be 64 (embed_dim %d, heads %d)", cfg->embed_dim, cfg->num_heads);
   if (cfg->mlp_hidden % 64 != 0 || cfg->depth < 1) return fail(VITOCM_ERR_INVALID, "bad mlp_hidden/depth");
-  if (cfg->precision != VITOCM_BF16 && cfg->precision != VITOCM_FP32) return fail(VITOCM_ERR_INVALID, "bad precision");
+  if (cfg->precision != VITOCM_BF16 && cfg->precision != VITOCM_FP32 && cfg->precision != VITOCM_FP16) return fail(VITOCM_ERR_INVALID, "bad precision");
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   cudaDeviceProp prop;
@@ -675,8 +691,10 @@ int vitocm_create(const vitocm_config* cfg, vitocm_engine** out) {
   e->cfg = *cfg;
   e->split = cfg->precision == VITOCM_FP32 ? 1 : 0;
   e->parts = e->split ? 2 : 1;
+  e->f16 = cfg->precision == VITOCM_FP16 ? 1 : 0;
   e->num_sms = prop.multiProcessorCount;
   e->layers.resize(cfg->depth);
+  e->layer_mode.assign(cfg->depth, 0);
   *out = e;
   return 0;
 }
@@ -714,7 +732,7 @@ static int repack_weights(vitocm_engine* e, cudaStream_t st) {
   auto pack = [&](DevBuf& dst, const float* src, int R, int C, int split) -> int {
     const int parts = split ? 2 : 1;
     TRY(dst.alloc(static_cast<size_t>(R) * C * parts * 2));
-    split_weight_kernel<<<512, 256, 0, st>>>(src, dst.as<__nv_bfloat16>(), static_cast<long long>(C) * parts, split, C, R, C);
+    split_weight_kernel<<<512, 256, 0, st>>>(src, dst.as<__nv_bfloat16>(), static_cast<long long>(C) * parts, split, C, R, C, e->f16);
     LAUNCH_CHECK();
     return 0;
   };
@@ -782,7 +800,7 @@ static int repack_weights(vitocm_engine* e, cudaStream_t st) {
       e->repack_entries = static_cast<int>(entries.size());
       e->repack_tiles = total_tiles;
     }
-    repack_weights_kernel<<<e->repack_tiles, 256, 0, st>>>(e->repack_table.as<RepackEntry>(), e->repack_entries);
+    repack_weights_kernel<<<e->repack_tiles, 256, 0, st>>>(e->repack_table.as<RepackEntry>(), e->repack_entries, e->f16);
     LAUNCH_CHECK();
   }
   return 0;
@@ -833,6 +851,15 @@ int vitocm_set_concurrency(vitocm_engine* e, int lanes) {
     if (e->ev_join[i] == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
   }
   e->lanes = lanes;
+  return 0;
+}
+
+int vitocm_set_layer_mode(vitocm_engine* e, int layer, int mode) {
+  if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
+  if (layer < 0 || layer >= e->cfg.depth) return fail(VITOCM_ERR_INVALID, "layer %d out of range", layer);
+  if (mode != 0 && mode != 1) return fail(VITOCM_ERR_INVALID, "layer mode must be 0 (engine default) or 1 (MLP activations as hi/lo pairs)");
+  if (mode == 1 && e->split) return fail(VITOCM_ERR_INVALID, "the fp32-parity engine already splits every operand");
+  e->layer_mode[layer] = mode;
   return 0;
 }
 
@@ -942,7 +969,7 @@ static int forward_rows(vitocm_engine* e, const float* x, int B, int H, int W, c
       const Workspace& wsp = lane_ws[k];
       const int M = bcs[k] * N;
       float* KF = reinterpret_cast<float*>(wsp.HID);
-      TRY(run_layernorm(wsp.X, last.ln1w, last.ln1b, wsp.XN, 2LL * D, 1, D, nullptr, 0, M, D, e->cfg.ln_eps, lane_st[k]));
+      TRY(run_layernorm(wsp.X, last.ln1w, last.ln1b, wsp.XN, 2LL * D, 1, D, nullptr, 0, M, D, e->cfg.ln_eps, lane_st[k], nullptr, e->f16));
       TRY(run_gemm(e, wsp.XN, 2LL * D, last.wk_split.p, 2LL * D, M, D, D, 1, EPI_BIAS_F32, last.bqkv + D, KF, D, 0, 0, lane_st[k], PC_GEMM_KLAST));
       ProfScope prof(PC_CLSROW, lane_st[k]);
       dim3 grid(heads, bcs[k], nq);
@@ -986,7 +1013,7 @@ int vitocm_block_attn_probs(vitocm_engine* e, int layer, const float* X, int B, 
   if (ws == nullptr || wsp.total > avail) return fail(VITOCM_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", wsp.total + 1024, ws_bytes);
   const LayerW& L = e->layers[layer];
   const int M = B * N;
-  TRY(run_layernorm(X, L.ln1w, L.ln1b, wsp.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
+  TRY(run_layernorm(X, L.ln1w, L.ln1b, wsp.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st, nullptr, e->f16));
   TRY(run_gemm(e, wsp.XN, 2LL * D, L.wqkv.p, static_cast<long long>(D) * P, M, 3 * D, D, S, EPI_BIAS_F32, L.bqkv, qkv_out, 3LL * D, 0, 0, st));
   const int kchunk = 256;
   int qrows = AP_QROWS;
@@ -1032,7 +1059,7 @@ int vitocm_mim_forward(vitocm_engine* e, const float* x, int B, int H, int W, co
     // VisionTransformerForSimMIM.forward (SSS/model.py:25-53): patch embed + mask-token mix + cls + pos, all blocks, norm
     TRY(run_patch_embed(e, xc, bc, H, W, pos, mc, wsp.X, st));
     for (int l = 0; l < e->cfg.depth; ++l) TRY(block_forward(e, l, wsp, bc, N, st));
-    TRY(run_layernorm(wsp.X, e->w("norm.weight"), e->w("norm.bias"), wsp.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st));
+    TRY(run_layernorm(wsp.X, e->w("norm.weight"), e->w("norm.bias"), wsp.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st, nullptr, e->f16));
     // decoder: 1x1 conv D -> C p^2 == per-token linear (model.py:61-64); CLS rows are computed and ignored
     TRY(run_gemm(e, wsp.XN, 2LL * D, e->dec_w.p, static_cast<long long>(D) * P, M, ldy, D, S, EPI_BIAS_F32, e->w("decoder.0.bias"), Y,
                  ldy, 0, 0, st));
@@ -1279,7 +1306,7 @@ int vitocm_layernorm(vitocm_engine* e, const float* X, const float* gamma, const
                      int split, int lo_off, int M, void* stream) {
   if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
   return run_layernorm(X, gamma, beta, out_bf16, ldo, split, lo_off, nullptr, 0, M, e->cfg.embed_dim, e->cfg.ln_eps,
-                       static_cast<cudaStream_t>(stream));
+                       static_cast<cudaStream_t>(stream), nullptr, e->f16);
 }
 
 }  // extern "C"

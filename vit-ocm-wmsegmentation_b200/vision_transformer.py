@@ -24,7 +24,30 @@ import torch.nn as nn
 from . import _lib
 from ._lib import VitocmConfig, check, cur_stream, ptr
 
-PRECISIONS = {"bf16": 0, "fp32": 1}
+PRECISIONS = {"bf16": 0, "fp32": 1, "fp16": 2}
+
+
+def parse_precision(spec: str, depth: int):
+    """"bf16" | "fp32" | "fp16", optionally followed by "+mlp2" (every block) or "+mlp2:a-b,c" (blocks a..b and c): those blocks'
+    fc1 / fc2 read their activations as (hi, lo) pairs (vitocm_set_layer_mode 1).  -> (engine precision, [mode per block])."""
+    base, _, extra = spec.partition("+")
+    if base not in PRECISIONS:
+        raise ValueError(f"precision must start with one of {sorted(PRECISIONS)} (got {spec!r})")
+    modes = [0] * depth
+    if extra:
+        kind, _, sel = extra.partition(":")
+        if kind != "mlp2" or base == "fp32":
+            raise ValueError(f"unknown precision schedule {spec!r} (bf16|fp16[+mlp2[:blocks]], fp32)")
+        if not sel:
+            modes = [1] * depth
+        else:
+            for part in sel.split(","):
+                a, _, b = part.partition("-")
+                for l in range(int(a), int(b or a) + 1):
+                    if not 0 <= l < depth:
+                        raise ValueError(f"block {l} out of range in {spec!r}")
+                    modes[l] = 1
+    return base, modes
 
 
 def _trunc_normal_(t: torch.Tensor, std: float = 0.02, a: float = -2.0, b: float = 2.0) -> torch.Tensor:
@@ -140,7 +163,7 @@ class VisionTransformer(nn.Module):
     """Vision Transformer whose forward passes run in libvitocm (B200 / sm_100a).
 
     Constructor signature follows the reference (vit.py:137-139); ``precision`` ("bf16" |
-    "fp32"), ``chunk_tiles`` (tiles per kernel launch) and ``lanes`` (chunks in flight on concurrent streams) are additions.  Dropout / stochastic depth must be 0 (the
+    "fp16" | "fp32", see parse_precision), ``chunk_tiles`` (tiles per kernel launch) and ``lanes`` (chunks in flight on concurrent streams) are additions.  Dropout / stochastic depth must be 0 (the
     reference's inference and MIM configurations all use 0)."""
 
     def __init__(self, img_size=[224], patch_size=16, in_chans=3, num_classes=0, embed_dim=768, depth=12,
@@ -151,8 +174,7 @@ class VisionTransformer(nn.Module):
             raise NotImplementedError("vitocm: dropout / drop-path rates must be 0 on this path")
         if embed_dim % num_heads or embed_dim // num_heads != 64:
             raise NotImplementedError("vitocm kernels are specialised for head_dim 64")
-        if precision not in PRECISIONS:
-            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        parse_precision(precision, depth)
         self.num_features = self.embed_dim = embed_dim
         self.num_heads = num_heads
         self.depth = depth
@@ -230,11 +252,15 @@ class VisionTransformer(nn.Module):
         if not torch.cuda.is_available():
             raise _lib.VitocmError("vitocm needs a CUDA device (B200, sm_100a); there is no CPU path")
         if self._engine is None:
+            base, modes = parse_precision(self.precision, self.depth)
             cfg = VitocmConfig(self.embed_dim, self.depth, self.num_heads, int(self.embed_dim * self.mlp_ratio),
                                self.patch_embed.patch_size, self.in_chans, self.ln_eps, float(self.qk_scale),
-                               PRECISIONS[self.precision])
+                               PRECISIONS[base])
             handle = C.c_void_p()
             check(lib.vitocm_create(C.byref(cfg), C.byref(handle)))
+            for l, m in enumerate(modes):
+                if m:
+                    check(lib.vitocm_set_layer_mode(handle, l, m))
             self._engine = handle
             self._bound_ptrs = None
             check(lib.vitocm_set_concurrency(handle, self.lanes))
@@ -270,8 +296,7 @@ class VisionTransformer(nn.Module):
                 pass
 
     def set_precision(self, precision: str):
-        if precision not in PRECISIONS:
-            raise ValueError(precision)
+        parse_precision(precision, self.depth)
         if precision != self.precision:
             self.precision = precision
             if self._engine is not None:
