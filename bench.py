@@ -7,14 +7,22 @@
 One "step" = one pass of the whole hot path over one synthetic gray mosaic: sliding window ->
 ViT-S/8 CLS attention rows per 224x224 tile -> head mean / per-tile min-max / bilinear / ramp-blended
 stitch -> global min-max -> img*att -> Otsu -> masks.  N=1 is BASELINE.json configs[1] (4096x4096,
-window 224, stride 112 -> 35x35 = 1225 tiles, stitched extent 4032^2 = 16.257 MP, bf16).  For N>1 the
+window 224, stride 112 -> 35x35 = 1225 tiles, stitched extent 4032^2 = 16.257 MP).  For N>1 the
 mosaic grows so that tiles per GPU stay ~1225 (weak scaling); tiles shard over ranks, low-res maps are
 all-gathered, {min,max,histograms} all-reduced and the mask bands gathered on rank 0.
 Prints ONE JSON line on rank 0.
+
+Precision: the headline runs fp16 engines (IEEE half tensor-core operands, fp32 accumulate / residual / LN / softmax statistics):
+same tensor-core rate as bf16 and 8x less operand rounding -- the reference is an fp32 model and its masks only agree on >= 99.9 %
+of the pixels when the CLS rows are good to ~1e-4.  The line carries `mask_agreement` (this run's masks
+against the fp32-parity mode on the same mosaic), `precision_modes` (throughput + agreement of bf16 / fp16+mlp2 / fp32 on the
+same box), `cfg3` (BASELINE configs[2]: ViT-B/8, fixed 16384^2 mosaic, strong scaling), `mim_train` (configs[3], batch 32 per
+GPU) and, for N > 1, `multi_gpu_bitwise_equal` (rank 0 re-segments the whole mosaic alone and compares the bits).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import math
 import os
@@ -148,12 +156,26 @@ def cpu_value(tiles_per_s, post_s_per_mp, n_tiles, extent):
     return mp / (n_tiles / tiles_per_s + post_s_per_mp * mp)
 
 
+
+def workload_config(arch, n_gpus, precision="fp16", chunk_tiles=175, lanes=1):
+    """config dict of the segmentation workload at n_gpus ranks -- the SAME keys and strings in the GPU arm and the reference arm."""
+    n, size, extent = mosaic_geometry(n_gpus)
+    T = n * n
+    return {"workload": f"{arch}/8 sliding-window segmentation, {size}x{size} gray mosaic, window {WINDOW}, stride {STRIDE}, "
+                        f"{T} tiles, extent {extent}^2", "tiles": T, "tiles_per_gpu": -(-T // n_gpus), "weights": "random init (seed 0)",
+            "chunk_tiles": chunk_tiles, "lanes": lanes, "precision": precision,
+            "l2": "flushed between timed steps (256 MiB write, untimed); per-step working set >> L2",
+            "parallelism": f"tiles sharded over {n_gpus} rank(s)"}
+
+
 def run_reference_arm(args):
+    """The reference algorithm on the host cores (oracle port).  Host only: the number does not depend on --gpus; for N > 1 it is
+    extrapolated to the N-GPU arm's (larger) mosaic so that both arms state the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n, size, extent = mosaic_geometry(1)
+    n, size, extent = mosaic_geometry(args.gpus)
     vals = []
     t_start = time.perf_counter()
     for i in range(args.warmup + args.steps):
@@ -162,11 +184,12 @@ def run_reference_arm(args):
             vals.append(cpu_value(tps, ppm, n * n, extent))
     v = statistics.mean(vals)
     mp = extent * extent / 1e6
+    cfg = workload_config(args.arch, args.gpus, "f32 (torch CPU)", 1, 1)
+    cfg["parallelism"] = f"host only ({threads} threads), independent of --gpus; stated on the workload of the {args.gpus}-GPU arm"
+    cfg["note"] = "each step times a bounded sample and extrapolates linearly in tiles and pixels"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * mp / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.arch}/8 sliding-window segmentation, {size}x{size} gray mosaic, window {WINDOW}, stride {STRIDE}, "
-                                   f"{n * n} tiles, extent {extent}^2", "note": "each step times a bounded sample and extrapolates linearly in tiles and pixels"},
+            "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": v, "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t_start}
@@ -203,43 +226,86 @@ def mim_cpu_sample(threads, batch=2, steps=1):
     return batch * steps / dt, f"{steps} training step(s) of ViT-S/8 MIM at batch {batch} (224^2): torch-CPU fwd+bwd, clip 5.0, AdamW"
 
 
-def main_mim(args):
+
+class Dist:
+    """One process per GPU (torch.distributed over NCCL when WORLD_SIZE > 1)."""
+
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.group = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.group = dist.group.WORLD
+
+    def barrier(self):
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, v: float) -> float:
+        t = torch.tensor([v], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    def bcast_obj(self, obj):
+        if self.world == 1:
+            return obj
+        box = [obj]
+        torch.distributed.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def close(self):
+        if self.world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+
+
+def peak_tflops():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peaks = json.load(open(peaks_path))
+        return float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))), "measured (sustained cuBLAS bf16, MEASURED_PEAKS.json)"
+    return 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+
+
+def kernel_source_hash(*names):
+    h = hashlib.sha256()
+    for n in names:
+        with open(os.path.join(ROOT, "vit-ocm-wmsegmentation_b200", "csrc", n), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel_class, key, scale):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/roofline_traffic.json) -- only while the kernel's
+    source is the one that was captured (the record carries the source hash); otherwise null rather than a stale number."""
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(tpath):
+        return None
+    rec = json.load(open(tpath)).get(kernel_class)
+    if not rec or key not in rec:
+        return None
+    files = rec.get("source_files")
+    if not files or rec.get("source_sha16") != kernel_source_hash(*files):
+        return None
+    return rec[key] * scale
+
+
+def mim_step(D, args, steps, warmup, with_e2e=True, sampler=None):
     """BASELINE.json configs[3]: MIM (SimMIM-style) pre-training step, ViT-S/8, 224^2 synthetic tiles, bf16 fwd+bwd with fp32
-    master weights / AdamW, batch 32 per GPU (256 on 8), NCCL all-reduce of the flat gradient.  One step = zero_grad,
-    forward, loss.sum().backward(), all-reduce, clip_grad_norm_(5.0), AdamW, bf16 weight repack."""
-    metric = "mim_pretrain_images_per_s"
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        threads = os.cpu_count() or 1
-        vals = []
-        for i in range(args.warmup + args.steps):
-            ips, sample = mim_cpu_sample(threads, batch=2, steps=1)
-            if i >= args.warmup:
-                vals.append(ips)
-        v = statistics.mean(vals)
-        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch_per_gpu * args.gpus / v, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": f"MIM pre-training step, vit_small/8, 224^2, global batch {args.batch_per_gpu * args.gpus}",
-                                     "note": "each step times a bounded batch-2 sample and extrapolates linearly in images"},
-                          "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
-                          "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
-        return
-    if args.warmup < 3:
-        args.warmup = 3
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    master weights / AdamW, batch `batch_per_gpu` per GPU (32 -> 256 on 8), NCCL all-reduce of the flat gradient.  One step =
+    zero_grad, forward, loss.sum().backward(), all-reduce, clip_grad_norm_(5.0), AdamW, bf16 weight repack.  -> dict of results."""
     import vitocm_b200 as vob
     from vitocm_b200 import synthetic as SY   # the GPU arm never touches oracle/
     from functools import partial
     from types import SimpleNamespace as NS
+    world, rank, dev = D.world, D.rank, D.dev
     a = ARCHS["vit_small"]
     torch.manual_seed(0)
     enc = vob.VisionTransformerForSimMIM(patch_size=PATCH, embed_dim=a["embed_dim"], depth=a["depth"], num_heads=a["num_heads"], mlp_ratio=4,
@@ -247,6 +313,8 @@ def main_mim(args):
     mim = vob.MIM(encoder=enc, encoder_stride=PATCH).cuda().train()
     cfg = NS(TRAIN=NS(BASE_LR=5e-4, WEIGHT_DECAY=0.05, CLIP_GRAD=5.0, OPTIMIZER=NS(NAME="adamw", EPS=1e-8, BETAS=(0.9, 0.999))))
     opt = vob.optimizer.build_pretrain_optimizer(cfg, mim, None)
+    if world > 1:
+        mim.overlap_grad_allreduce(True)     # every backward of this loop is final (no gradient accumulation)
     Bg = args.batch_per_gpu
     N = (WINDOW // PATCH) ** 2 + 1
     # a few distinct synthetic batches in pinned host memory (rank-dependent seeds), cycled through
@@ -259,65 +327,58 @@ def main_mim(args):
     ms_dev = [m.to(dev) for m in ms_host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
     def train_step(x, m):
         opt.zero_grad()
         loss, _, _ = mim(x, m)
-        loss.sum().backward()
+        loss.sum().backward()        # (the gradient all-reduce is launched from inside the backward, bucket by bucket)
         mim.all_reduce_grads()
         vob.optimizer.clip_grad_norm_(mim, cfg.TRAIN.CLIP_GRAD)
         opt.step()
         return loss
 
-    sampler = ClockSampler(local, enabled=rank == 0)
-    sampler.start()
-    for i in range(args.warmup):          # same cadence as the timed iterations (flush, barrier, step, barrier): the power-cap
-        flush.fill_(1)                    # controller then enters the timed region in its steady state
-        barrier()
+    for i in range(warmup):          # same cadence as the timed iterations (flush, barrier, step, barrier): the power-cap
+        flush.fill_(1)               # controller then enters the timed region in its steady state
+        D.barrier()
         train_step(xs_dev[i % n_host], ms_dev[i % n_host])
-        barrier()
-    sampler.open_window()
+        D.barrier()
+    if sampler is not None:
+        sampler.open_window()
     launches0 = vob._lib.launch_count()
     step_ms = []
-    for i in range(args.steps):
+    for i in range(steps):
         flush.fill_(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
+        D.barrier()
         e0.record()
         loss = train_step(xs_dev[i % n_host], ms_dev[i % n_host])
         e1.record()
-        barrier()
+        D.barrier()
         step_ms.append(e0.elapsed_time(e1))
     launches = vob._lib.launch_count() - launches0
-    sampler.stop()
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
-    ms_per_step = float(total_ms.item()) / args.steps
-    value = Bg * world / (ms_per_step / 1e3)
-    # ---- end to end: pinned host batch -> device inside the timed region, loss read back every step
-    e2e_ms = []
-    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-    for i in range(2 + args.steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        x = xs_host[i % n_host].to(dev, non_blocking=True)
-        m = ms_host[i % n_host].to(dev, non_blocking=True)
-        loss = train_step(x, m)
-        loss_host.copy_(loss.detach(), non_blocking=True)
-        e1.record()
-        barrier()
-        if i >= 2:
-            e2e_ms.append(e0.elapsed_time(e1))
-    e2e_t = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(e2e_t, op=torch.distributed.ReduceOp.MAX)
-    final_loss = float(loss_host.item())
+    if sampler is not None:
+        sampler.stop()
+    ms_per_step = D.max_over_ranks(sum(step_ms)) / steps
+    res = {"value": Bg * world / (ms_per_step / 1e3), "unit": "images/s", "ms_per_step": ms_per_step, "step_ms_rank0": [round(v, 3) for v in step_ms],
+           "batch_per_gpu": Bg, "global_batch": Bg * world, "gpu_launches": int(launches)}
+    if with_e2e:   # pinned host batch -> device inside the timed region, loss read back every step
+        e2e_ms = []
+        loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+        for i in range(2 + steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            D.barrier()
+            e0.record()
+            x = xs_host[i % n_host].to(dev, non_blocking=True)
+            m = ms_host[i % n_host].to(dev, non_blocking=True)
+            loss = train_step(x, m)
+            loss_host.copy_(loss.detach(), non_blocking=True)
+            e1.record()
+            D.barrier()
+            if i >= 2:
+                e2e_ms.append(e0.elapsed_time(e1))
+        e2e_t = D.max_over_ranks(sum(e2e_ms) / len(e2e_ms))
+        res["e2e"] = {"value": Bg * world / (e2e_t / 1e3), "unit": "images/s",
+                      "h2d_bytes_per_step": int(xs_host[0].numel() * 4 + ms_host[0].numel() * 8) * world, "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_t}
+        res["final_loss"] = float(loss_host.item())
     # ---- per-kernel-class device times
     vob._lib.profile_enable(True)
     train_step(xs_dev[0], ms_dev[0])
@@ -325,58 +386,160 @@ def main_mim(args):
     prof = vob._lib.profile_read()
     vob._lib.profile_enable(False)
     classes = {k: {"ms": v[0], "launches": v[1]} for k, v in prof.items() if v[1] > 0}
-    D, depth = a["embed_dim"], a["depth"]
+    Dm, depth = a["embed_dim"], a["depth"]
     M = Bg * N
-    gemm_fwd = 2.0 * M * D * (3 * D + D + 8 * D) * depth
-    attn_fwd = 4.0 * N * N * D * Bg * depth
-    cls_gflop = {"gemm_wgrad": gemm_fwd + 2.0 * M * D * 192 * 2, "gemm_dgrad": gemm_fwd + 2.0 * M * D * 192, "attention": attn_fwd, "attention_bwd": 2.5 * attn_fwd,
-                 "gemm_qkv": 2.0 * M * D * 3 * D * depth, "gemm_proj": 2.0 * M * D * D * depth, "gemm_fc1_gelu": 2.0 * M * D * 4 * D * depth,
-                 "gemm_fc2": 2.0 * M * D * 4 * D * depth}
+    gemm_fwd = 2.0 * M * Dm * (3 * Dm + Dm + 8 * Dm) * depth
+    attn_fwd = 4.0 * N * N * Dm * Bg * depth
+    cls_gflop = {"gemm_wgrad": gemm_fwd + 2.0 * M * Dm * 192 * 2, "gemm_dgrad": gemm_fwd + 2.0 * M * Dm * 192, "attention": attn_fwd, "attention_bwd": 2.5 * attn_fwd,
+                 "gemm_qkv": 2.0 * M * Dm * 3 * Dm * depth, "gemm_proj": 2.0 * M * Dm * Dm * depth, "gemm_fc1_gelu": 2.0 * M * Dm * 4 * Dm * depth,
+                 "gemm_fc2": 2.0 * M * Dm * 4 * Dm * depth}
     for k, c in classes.items():
         c["gflop"] = cls_gflop.get(k, 0.0) / 1e9
         c["tflops"] = c["gflop"] / c["ms"] if c["ms"] > 0 and c["gflop"] > 0 else None
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peaks = json.load(open(peaks_path))
-        peak, peak_src = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))), "measured (sustained cuBLAS bf16, MEASURED_PEAKS.json)"
-    else:
-        peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+    peak, peak_src = peak_tflops()
     tensor_classes = {k: c for k, c in classes.items() if c["gflop"] > 0}
     dom = max(tensor_classes, key=lambda k: tensor_classes[k]["ms"])
     c = tensor_classes[dom]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        rec = json.load(open(tpath)).get(dom)
-        if rec and "dram_bytes_per_image_per_launch" in rec:   # ncu's DRAM bytes per image and launch x images per launch of this run
-            traffic = rec["dram_bytes_per_image_per_launch"] * Bg
-    roofline = {"kernel": dom, "bound": "tensor", "achieved": c["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": c["tflops"] / peak,
-                "traffic": traffic, "peak_source": peak_src, "launches_per_step": c["launches"], "avg_launch_ms": c["ms"] / c["launches"]}
-    step_tflops = mim_flops_per_image(D, depth, a["num_heads"], N) * Bg / 1e12 / (ms_per_step / 1e3)
-    if rank == 0:
-        line = {"metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "step_ms_rank0": [round(v, 3) for v in step_ms], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"MIM pre-training step (SimMIM masked patches), vit_small/8, 224^2 synthetic tiles, batch {Bg} per GPU = {Bg * world} global, "
-                                       "bf16 fwd+bwd, fp32 master weights + fused clip/AdamW, NCCL all-reduce(SUM) of the flat gradient",
-                           "batch_per_gpu": Bg, "global_batch": Bg * world, "weights": "random init (seed 0)",
+    res["roofline"] = {"kernel": dom, "bound": "tensor", "achieved": c["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": c["tflops"] / peak,
+                       "traffic": ncu_traffic(dom, "dram_bytes_per_image_per_launch", Bg), "peak_source": peak_src,
+                       "launches_per_step": c["launches"], "avg_launch_ms": c["ms"] / c["launches"]}
+    gf = mim_flops_per_image(Dm, depth, a["num_heads"], N)
+    step_tflops = gf * Bg / 1e12 / (ms_per_step / 1e3)
+    res["step_tensor"] = {"tflops_per_gpu": step_tflops, "frac_of_peak": step_tflops / peak, "gflop_per_image": gf / 1e9}
+    res["kernel_classes"] = classes
+    del mim, opt, enc
+    torch.cuda.empty_cache()
+    return res
+
+
+def main_mim(args):
+    metric = "mim_pretrain_images_per_s"
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        threads = os.cpu_count() or 1
+        vals = []
+        for i in range(args.warmup + args.steps):
+            ips, sample = mim_cpu_sample(threads, batch=2, steps=1)
+            if i >= args.warmup:
+                vals.append(ips)
+        v = statistics.mean(vals)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch_per_gpu * args.gpus / v, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"MIM pre-training step, vit_small/8, 224^2, global batch {args.batch_per_gpu * args.gpus}",
+                                     "note": "host only; each step times a bounded batch-2 sample and extrapolates linearly in images"},
+                          "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    D = Dist()
+    sampler = ClockSampler(D.local, enabled=D.rank == 0)
+    sampler.start()
+    r = mim_step(D, args, args.steps, args.warmup, with_e2e=True, sampler=sampler)
+    if D.rank == 0:
+        Bg = args.batch_per_gpu
+        line = {"metric": metric, "value": r["value"], "unit": "images/s", "n_gpus": D.world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": r["ms_per_step"], "step_ms_rank0": r["step_ms_rank0"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"MIM pre-training step (SimMIM masked patches), vit_small/8, 224^2 synthetic tiles, batch {Bg} per GPU = {Bg * D.world} global, "
+                                       "bf16 fwd+bwd, fp32 master weights + fused clip/AdamW, NCCL all-reduce(SUM) of the gradient buckets overlapped with the backward",
+                           "batch_per_gpu": Bg, "global_batch": Bg * D.world, "weights": "random init (seed 0)",
                            "l2": "flushed between timed steps (256 MiB write, untimed); per-step working set >> L2",
-                           "parallelism": f"data parallel over {world} rank(s)", "final_loss": final_loss},
-                "e2e": {"value": Bg * world / (float(e2e_t.item()) / 1e3), "unit": "images/s",
-                        "h2d_bytes_per_step": int(xs_host[0].numel() * 4 + ms_host[0].numel() * 8), "d2h_bytes_per_step": 4, "ms_per_step": float(e2e_t.item())},
-                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
-                "step_tensor": {"tflops_per_gpu": step_tflops, "frac_of_peak": step_tflops / peak, "gflop_per_image": mim_flops_per_image(D, depth, a["num_heads"], N) / 1e9},
-                "kernel_classes": classes}
-        if world == 1 and not args.no_cpu_baseline:
+                           "parallelism": f"data parallel over {D.world} rank(s)", "final_loss": r.get("final_loss")},
+                "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": sampler.summary(), "roofline": r["roofline"],
+                "step_tensor": r["step_tensor"], "kernel_classes": r["kernel_classes"]}
+        if D.world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             ips, sample = mim_cpu_sample(threads)
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+    D.close()
 
 
 # ------------------------------------------------------------------------------------- GPU arm
+def time_segmentation(D, seg, mosaic, steps, warmup, flush, sampler=None, want=("th", "th3")):
+    """`warmup` untimed + `steps` timed passes with the mosaic resident in HBM; CUDA events on the launching stream, barrier +
+    synchronize on both sides of every step, L2 flushed in between.  -> (ms per step = max over ranks, rank-0 step list, last result)."""
+    out = None
+    for _ in range(warmup):
+        flush.fill_(1)
+        D.barrier()
+        out = seg.segment(mosaic, want=want, gather=True)
+        D.barrier()
+    if sampler is not None:
+        sampler.open_window()
+    step_ms = []
+    D.barrier()
+    for _ in range(steps):
+        flush.fill_(1)                                   # evict L2 between timed steps (not timed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.barrier()
+        e0.record()
+        out = seg.segment(mosaic, want=want, gather=True)
+        e1.record()
+        D.barrier()
+        step_ms.append(e0.elapsed_time(e1))
+    if sampler is not None:
+        sampler.stop()
+    return D.max_over_ranks(sum(step_ms)) / max(steps, 1), step_ms, out
+
+
+def time_segmentation_e2e(D, seg, mosaic_host, host_masks, steps, warmup):
+    """The same pass through the public API with HOST buffers: every rank uploads the rows of the pinned host mosaic it needs and
+    copies its band of each mask into the shared pinned host image, all inside the timed region."""
+    ms = []
+    for i in range(warmup + steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.barrier()
+        e0.record()
+        seg.segment(mosaic_host, want=tuple(host_masks), gather=False, host_out=host_masks)
+        e1.record()
+        D.barrier()
+        if i >= warmup:
+            ms.append(e0.elapsed_time(e1))
+    return D.max_over_ranks(sum(ms) / len(ms))
+
+
+def shared_host_masks(D, vob, extent, names=("th", "th3"), tag="m"):
+    """Page-locked host images [extent, extent] that every rank maps (one file per mask under /dev/shm for N > 1)."""
+    if D.world == 1:
+        return {k: torch.empty(extent, extent, dtype=torch.uint8).pin_memory() for k in names}, []
+    paths = D.bcast_obj([f"/dev/shm/vitocm_bench_{os.getpid()}_{tag}_{k}" for k in names] if D.rank == 0 else None)
+    masks = {}
+    if D.rank == 0:
+        for k, pth in zip(names, paths):
+            masks[k] = vob.shared_pinned_u8(pth, (extent, extent), create=True)
+    D.barrier()
+    if D.rank != 0:
+        for k, pth in zip(names, paths):
+            masks[k] = vob.shared_pinned_u8(pth, (extent, extent), create=False)
+    D.barrier()
+    return masks, (paths if D.rank == 0 else [])
+
+
+def release_host_masks(masks, paths):
+    for t in masks.values():
+        try:
+            if not t.is_pinned() or paths:
+                torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
+        except Exception:
+            pass
+    for pth in paths:
+        try:
+            os.unlink(pth)
+        except OSError:
+            pass
+
+
+def masks_sha(out, names=("th", "th3")):
+    h = hashlib.sha256()
+    for k in names:
+        h.update(out[k].cpu().numpy().tobytes())
+    return h.hexdigest()[:16]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -384,12 +547,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arch", default="vit_small", choices=sorted(ARCHS))
-    ap.add_argument("--precision", default="bf16", help="bf16 | fp16 | fp32, optionally +mlp2[:blocks] (vision_transformer.parse_precision)")
+    ap.add_argument("--precision", default="fp16", help="bf16 | fp16 | fp32, optionally +mlp2[:blocks] (vision_transformer.parse_precision)")
     ap.add_argument("--chunk-tiles", type=int, default=175)
     ap.add_argument("--tile-batch", type=int, default=175)
     ap.add_argument("--lanes", type=int, default=1, help="chunks in flight on concurrent streams")
     ap.add_argument("--ingest", default="direct", choices=["direct", "crops"], help="segmentation: tiles read out of the uint8 mosaic by the patch embedding, or fp32 crops cut first")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip mask_agreement / precision_modes / cfg3 / mim_train / multi_gpu_bitwise_equal")
     ap.add_argument("--workload", default="segmentation", choices=["segmentation", "mim_train"],
                     help="segmentation = BASELINE.json configs[1] (the headline); mim_train = configs[3] (MIM pre-training step)")
     ap.add_argument("--batch-per-gpu", type=int, default=32, help="mim_train: images per GPU per step (256 over 8 GPUs)")
@@ -401,93 +565,51 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    group = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-        group = dist.group.WORLD
-
+    D = Dist()
+    world, rank, dev = D.world, D.rank, D.dev
     import vitocm_b200 as vob
     from vitocm_b200 import synthetic as SY   # the GPU arm never touches oracle/
 
+    def make_model(arch, precision):
+        torch.manual_seed(0)               # identical random-init weights in every precision and on every rank
+        return getattr(vob, arch)(patch_size=PATCH, num_classes=0, precision=precision, chunk_tiles=args.chunk_tiles, lanes=args.lanes).cuda().eval()
+
     a = ARCHS[args.arch]
-    torch.manual_seed(0)
-    model = getattr(vob, args.arch)(patch_size=PATCH, num_classes=0, precision=args.precision, chunk_tiles=args.chunk_tiles, lanes=args.lanes)
-    model = model.cuda().eval()
+    model = make_model(args.arch, args.precision)
     n, size, extent = mosaic_geometry(world)
     T = n * n
     N = (WINDOW // PATCH) ** 2 + 1
     mosaic_host = torch.from_numpy(SY.synthetic_mosaic_u8(size, seed=4321)).pin_memory()
     mosaic = mosaic_host.to(dev)
-    seg = vob.MosaicSegmenter(model, window=WINDOW, stride=STRIDE, tile_batch=args.tile_batch, group=group, ingest=args.ingest)
+    seg = vob.MosaicSegmenter(model, window=WINDOW, stride=STRIDE, tile_batch=args.tile_batch, group=D.group, ingest=args.ingest)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
-    def step_device():
-        return seg.segment(mosaic, want=("th", "th3"), gather=True)
-
-    sampler = ClockSampler(local, enabled=rank == 0)
-    sampler.start()
-    for _ in range(args.warmup):          # same cadence as the timed iterations (flush, barrier, step, barrier): the power-cap
-        flush.fill_(1)                    # controller then enters the timed region in its steady state
-        barrier()
-        out = step_device()
-        barrier()
-    sampler.open_window()
-    launches0 = vob._lib.launch_count()
-    step_ms = []
-    barrier()
-    for _ in range(args.steps):
-        flush.fill_(1)                                   # evict L2 between timed steps (not timed)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        out = step_device()
-        e1.record()
-        barrier()
-        step_ms.append(e0.elapsed_time(e1))
-    launches = vob._lib.launch_count() - launches0
-    sampler.stop()
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(total_ms, op=torch.distributed.ReduceOp.MAX)
-    ms_per_step = float(total_ms.item()) / args.steps
     mp = extent * extent / 1e6
+
+    sampler = ClockSampler(D.local, enabled=rank == 0)
+    sampler.start()
+    launches0 = None
+    # warm-up first (same cadence as the timed steps), then count launches over the timed steps only
+    ms_w, _, _ = time_segmentation(D, seg, mosaic, 0, args.warmup, flush)
+    launches0 = vob._lib.launch_count()
+    ms_per_step, step_ms, out = time_segmentation(D, seg, mosaic, args.steps, 0, flush, sampler=sampler)
+    launches = vob._lib.launch_count() - launches0
     value = mp / (ms_per_step / 1e3)
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
-    host_masks = {k: torch.empty(extent, extent, dtype=torch.uint8).pin_memory() for k in ("th", "th3")} if rank == 0 else {}
-    e2e_ms = []
-    for i in range(2 + args.steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        d_mosaic = mosaic_host.to(dev, non_blocking=True)
-        res = seg.segment(d_mosaic, want=("th", "th3"), gather=True)
-        if rank == 0:
-            for k in host_masks:
-                host_masks[k].copy_(res[k], non_blocking=True)
-        e1.record()
-        barrier()
-        if i >= 2:
-            e2e_ms.append(e0.elapsed_time(e1))
-    e2e_t = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device=dev)
+    host_masks, shm_paths = shared_host_masks(D, vob, extent)
+    e2e_ms = time_segmentation_e2e(D, seg, mosaic_host, host_masks, args.steps, 2)
+    e2e_value = mp / (e2e_ms / 1e3)
+    r0, r1 = seg.mosaic_rows_needed(size)
+    h2d = torch.tensor([float((r1 - r0) * size)], dtype=torch.float64, device=dev)
     if world > 1:
-        torch.distributed.all_reduce(e2e_t, op=torch.distributed.ReduceOp.MAX)
-    e2e_value = mp / (float(e2e_t.item()) / 1e3)
+        torch.distributed.all_reduce(h2d)
+    host_ok = None
+    if rank == 0:     # the host images assembled by all ranks equal the masks gathered on the device
+        host_ok = bool(all(torch.equal(host_masks[k], out[k].cpu()) for k in host_masks))
 
     # ---- per-kernel-class device times (CUDA events on the launching stream) for the roofline
     vob._lib.profile_enable(True)
-    step_device()
+    seg.segment(mosaic, want=("th", "th3"), gather=True)
     torch.cuda.synchronize()
     prof = vob._lib.profile_read()
     vob._lib.profile_enable(False)
@@ -497,55 +619,160 @@ def main():
                for k, v in prof.items() if v[1] > 0}
     for k, c in classes.items():
         c["tflops"] = (c["gflop"] / c["ms"]) if c["ms"] > 0 and c["gflop"] > 0 else None
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peaks = json.load(open(peaks_path))
-        peak, peak_src = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))), "measured (sustained cuBLAS bf16, MEASURED_PEAKS.json)"
-    else:
-        peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+    peak, peak_src = peak_tflops()
     tensor_classes = {k: c for k, c in classes.items() if c["gflop"] > 0}
     dom = max(tensor_classes, key=lambda k: tensor_classes[k]["ms"]) if tensor_classes else None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if dom and os.path.exists(tpath):
-        rec = json.load(open(tpath)).get(dom)
-        if rec:   # DRAM bytes per launch = ncu's per-tile figure x tiles per launch of this run
-            tiles_per_launch = my_tiles * (a["depth"] - 1) / max(classes[dom]["launches"], 1)
-            traffic = rec["dram_bytes_per_tile"] * tiles_per_launch
     roofline = None
     if dom:
         c = tensor_classes[dom]
+        tiles_per_launch = my_tiles * (a["depth"] - 1) / max(c["launches"], 1)
         roofline = {"kernel": dom, "bound": "tensor", "achieved": c["tflops"], "peak": peak, "unit": "TFLOP/s",
-                    "frac": c["tflops"] / peak, "traffic": traffic, "peak_source": peak_src,
+                    "frac": c["tflops"] / peak, "traffic": ncu_traffic(dom, "dram_bytes_per_tile", tiles_per_launch), "peak_source": peak_src,
                     "launches_per_step": c["launches"], "avg_launch_ms": c["ms"] / c["launches"]}
+    # the bandwidth-bound post-processing class against the HBM roofline (3 B per stitched pixel + 4 h w B per tile)
+    hbm_roofline = None
+    if "post" in classes:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak = float(json.load(open(peaks_path)).get("hbm_gbs", 6546.6)) if os.path.exists(peaks_path) else 6500.0
+        y0, y1 = vob.shard_range(extent, rank, world)
+        alg_bytes = 3.0 * (y1 - y0) * extent + 4.0 * (WINDOW // PATCH) ** 2 * T + 4.0 * a["num_heads"] * N * my_tiles
+        ach = alg_bytes / 1e9 / (classes["post"]["ms"] / 1e3)
+        hbm_roofline = {"kernel": "post (head_mean + stitch_gray/minmax/hist/mask + otsu)", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": ach / hbm_peak, "algorithmic_bytes": alg_bytes, "ms": classes["post"]["ms"], "launches": classes["post"]["launches"]}
     step_tflops = flops_per_tile(a["embed_dim"], a["depth"], a["num_heads"], N) * my_tiles / 1e12 / (ms_per_step / 1e3)
+    clocks = sampler.summary()
 
-    line = None
+    extras = {}
+    if not args.no_extras:
+        # ---- mask agreement of the headline precision against the fp32-parity mode (same mosaic, same weights, untimed)
+        ref_model = make_model(args.arch, "fp32")
+        ref_seg = vob.MosaicSegmenter(ref_model, window=WINDOW, stride=STRIDE, tile_batch=args.tile_batch, group=D.group, ingest=args.ingest)
+        ref_out = ref_seg.segment(mosaic, want=("th", "th3"), gather=True)
+        tiles_x = torch.cat([SY.synthetic_tile(WINDOW, seed=1234 if i == 0 else 100 + i, batch=1) for i in range(32)]).to(dev)
+
+        def tile_agreement(m):
+            got = vob.attention_masks(m, tiles_x)["masks"]
+            ag = {}
+            for i, k in ((0, "th"), (2, "th3")):
+                v = (got[:, i] == tile_ref[:, i]).float().mean(dim=(1, 2))
+                ag[k] = {"mean": float(v.mean()), "min": float(v.min()), "frac_tiles_ge_0.999": float((v >= 0.999).float().mean()), "config1_tile": float(v[0])}
+            return ag
+
+        tile_ref = vob.attention_masks(ref_model, tiles_x)["masks"]
+        if rank == 0:
+            extras["mask_agreement"] = {
+                "against": "the fp32-parity mode (split-bf16, pinned to the reference at 4e-6 by tests/test_gpu_parity.py) on this GPU, same weights and inputs",
+                "precision": args.precision,
+                "mosaic": {k: float((out[k] == ref_out[k]).float().mean()) for k in ("th", "th3")},
+                "tiles_224": tile_agreement(model), "n_tiles": 32, "bar": 0.999}
+        # ---- other precision schedules on the same box (N = 1 only: short runs, same mosaic)
+        if world == 1:
+            modes = {}
+            for prec in ("bf16", "fp16+mlp2", "fp32"):
+                if prec == args.precision:
+                    continue
+                m2 = ref_model if prec == "fp32" else make_model(args.arch, prec)
+                s2 = ref_seg if prec == "fp32" else vob.MosaicSegmenter(m2, window=WINDOW, stride=STRIDE, tile_batch=args.tile_batch, ingest=args.ingest)
+                ms2, _, o2 = time_segmentation(D, s2, mosaic, 3, 2, flush)
+                modes[prec] = {"value": mp / (ms2 / 1e3), "unit": "MP/s", "ms_per_step": ms2, "steps": 3, "warmup": 2,
+                               "mask_agreement_mosaic": {k: float((o2[k] == ref_out[k]).float().mean()) for k in ("th", "th3")},
+                               "mask_agreement_tiles_224": tile_agreement(m2)}
+                if prec != "fp32":
+                    del m2, s2
+            extras["precision_modes"] = modes
+        del ref_model, ref_seg, ref_out
+        # ---- N > 1: the sharded result is bit-identical to one GPU doing everything
+        if world > 1:
+            same = None
+            if rank == 0:
+                solo = vob.MosaicSegmenter(model, window=WINDOW, stride=STRIDE, tile_batch=args.tile_batch, group=None, ingest=args.ingest)
+                so = solo.segment(mosaic, want=("th", "th3"))
+                same = bool(torch.equal(so["th"], out["th"]) and torch.equal(so["th3"], out["th3"]) and torch.equal(so["thresholds"], out["thresholds"]))
+                del solo, so
+            D.barrier()
+            extras["multi_gpu_bitwise_equal"] = same
+        del out
+        torch.cuda.empty_cache()
+        # ---- BASELINE configs[2]: ViT-B/8, fixed 16384^2 mosaic (21 025 tiles, extent 16 352^2), strong scaling
+        extras["cfg3"] = run_cfg3(D, vob, SY, args, flush)
+        torch.cuda.empty_cache()
+        # ---- BASELINE configs[3]: MIM pre-training step at batch 32 per GPU
+        r = mim_step(D, args, steps=5, warmup=3, with_e2e=True)
+        r.pop("step_ms_rank0", None)
+        r["config"] = "MIM pre-training step (SimMIM), vit_small/8, 224^2, batch 32 per GPU, bf16 fwd+bwd, fp32 master weights, fused clip + AdamW, NCCL all-reduce of gradient buckets overlapped with the backward"
+        extras["mim_train"] = r
+
     if rank == 0:
+        cfgd = workload_config(args.arch, world, args.precision, args.chunk_tiles, args.lanes)
+        cfgd["tiles_per_gpu"] = my_tiles
         line = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "step_ms_rank0": [round(v, 3) for v in step_ms], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": f"{args.arch}/8 sliding-window segmentation, {size}x{size} gray mosaic, window {WINDOW}, stride {STRIDE}, "
-                                       f"{T} tiles, extent {extent}^2", "tiles": T, "tiles_per_gpu": my_tiles, "weights": "random init (seed 0)",
-                           "chunk_tiles": args.chunk_tiles, "lanes": args.lanes, "l2": "flushed between timed steps (256 MiB write, untimed); per-step working set >> L2",
-                           "parallelism": f"tiles sharded over {world} rank(s)"},
+                "dtype": args.precision, "data": "synthetic", "config": cfgd,
                 "tiles_per_s": T / (ms_per_step / 1e3),
-                "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": int(mosaic_host.numel()),
-                        "d2h_bytes_per_step": int(2 * extent * extent), "ms_per_step": float(e2e_t.item())},
+                "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": int(h2d.item()),
+                        "d2h_bytes_per_step": int(2 * extent * extent), "ms_per_step": e2e_ms, "host_masks_match_device": host_ok,
+                        "path": "MosaicSegmenter.segment(host mosaic, host_out=...): per-rank band upload, per-rank band download into one shared pinned image"},
                 "gpu_launches": int(launches),
-                "clocks": sampler.summary(),
+                "clocks": clocks,
                 "roofline": roofline,
+                "roofline_hbm": hbm_roofline,
                 "step_tensor": {"tflops_per_gpu": step_tflops, "frac_of_peak": step_tflops / peak, "gflop_per_tile": flops_per_tile(a["embed_dim"], a["depth"], a["num_heads"], N) / 1e9},
                 "kernel_classes": classes}
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             tps, ppm, sample = cpu_reference_sample(args.arch, threads, n_s=3)
             line["cpu_baseline"] = {"value": cpu_value(tps, ppm, T, extent), "unit": "MP/s", "cores": threads, "kind": "port",
                                     "sample": sample, "tiles_per_s": tps}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+    release_host_masks(host_masks, shm_paths)
+    D.close()
+
+
+def run_cfg3(D, vob, SY, args, flush):
+    """BASELINE.json configs[2]: ViT-B/8 sliding-window segmentation of a fixed 16384^2 mosaic (145^2 = 21 025 tiles, extent 16 352^2 =
+    267.4 MP), tiles sharded over the ranks: STRONG scaling.  The mosaic is the 4096^2 synthetic field repeated 4 x 4.  Few steps
+    (a step is seconds of ViT-B work); `mask_sha256_16` is the same string at every N when the result does not depend on the sharding."""
+    size = 16384
+    n = len(range(0, size - 2 * STRIDE, STRIDE))
+    extent = (n - 1) * STRIDE + WINDOW
+    mp = extent * extent / 1e6
+    torch.manual_seed(0)
+    model = vob.vit_base(patch_size=PATCH, num_classes=0, precision=args.precision, chunk_tiles=args.chunk_tiles).cuda().eval()
+    base = torch.from_numpy(SY.synthetic_mosaic_u8(4096, seed=4321))
+    mosaic_host = base.repeat(4, 4).contiguous().pin_memory()
+    mosaic = mosaic_host.to(D.dev)
+    seg = vob.MosaicSegmenter(model, window=WINDOW, stride=STRIDE, tile_batch=args.tile_batch, group=D.group, ingest=args.ingest)
+    steps = 1 if D.world == 1 else 2
+    ms, _, out = time_segmentation(D, seg, mosaic, steps, 1, flush)
+    sha = masks_sha(out) if D.rank == 0 else None
+    del out
+    host_masks, paths = shared_host_masks(D, vob, extent, tag="c3")
+    e2e_ms = time_segmentation_e2e(D, seg, mosaic_host, host_masks, 1, 1)
+    r0, r1 = seg.mosaic_rows_needed(size)
+    h2d = torch.tensor([float((r1 - r0) * size)], dtype=torch.float64, device=D.dev)
+    if D.world > 1:
+        torch.distributed.all_reduce(h2d)
+    sha_host = None
+    if D.rank == 0:
+        hh = hashlib.sha256()
+        for k in ("th", "th3"):
+            hh.update(host_masks[k].numpy().tobytes())
+        sha_host = hh.hexdigest()[:16]
+    release_host_masks(host_masks, paths)
+    T = n * n
+    N = (WINDOW // PATCH) ** 2 + 1
+    ab = ARCHS["vit_base"]
+    tf = flops_per_tile(ab["embed_dim"], ab["depth"], ab["num_heads"], N) * T / 1e12 / (ms / 1e3) / D.world
+    peak, _ = peak_tflops()
+    res = {"workload": f"vit_base/8 sliding-window segmentation, {size}x{size} gray mosaic (4096^2 synthetic field repeated 4x4), window {WINDOW}, stride {STRIDE}, "
+                       f"{T} tiles, extent {extent}^2, tiles sharded over {D.world} rank(s)", "scaling": "strong", "precision": args.precision,
+           "value": mp / (ms / 1e3), "unit": "MP/s", "ms_per_step": ms, "steps": steps, "warmup": 1, "tiles_per_s": T / (ms / 1e3),
+           "step_tflops_per_gpu": tf, "frac_of_peak": tf / peak,
+           "e2e": {"value": mp / (e2e_ms / 1e3), "unit": "MP/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(2 * extent * extent)},
+           "mask_sha256_16": sha, "mask_sha256_16_host_path": sha_host}
+    del model, seg, mosaic
+    return res
 
 
 if __name__ == "__main__":

@@ -154,6 +154,14 @@ int vitocm_final_norm(vitocm_engine* e, const float* X, float* out, int M, void*
  * (a-min)/(max-min)*255 of SSS/sw_processing.py:253-254. */
 int vitocm_head_mean(const float* rows, float* lowres, int T, int heads, int n_tokens, int mode, void* stream);
 
+/* Cumulative-mass threshold per head (the `--threshold` flag whose help text is at SSS/eval.py:33-34; the arithmetic is upstream
+ * DINO's visualize_attention.py, not under /root/reference: parity unpinned by the reference, oracle = a PyTorch restatement):
+ * per (tile, head) over the N - 1 patch columns of the CLS row: sort ascending, normalise by the sum, cumulative sum, keep the
+ * patches whose cumulative mass exceeds 1 - threshold, back in patch order.  rows [T][heads][N] fp32 -> mask [T][heads][N-1] u8
+ * in {0,1}; up [T][heads][lh*patch][lw*patch] fp32 (optional, NULL to skip) = the nearest x patch upsampling of the mask. */
+int vitocm_attn_cummass(const float* rows, int T, int heads, int n_tokens, float threshold, uint8_t* mask, float* up, int lh, int lw,
+                        int patch, void* stream);
+
 /* SSS/eval.py:169-173 + utils.threshold (SSS/utils.py:62-115) for T images: lowres [T][lh][lw],
  * x [T][C][S][S] fp32 in [0,1]; masks [T][3][S][S] u8 = (th "ours", th2 "otsu", th3 "heatmap_threshold");
  * thresholds [T][3] int32; att_out [T][S][S] fp32 or NULL (the bilinearly upsampled map).
@@ -274,9 +282,21 @@ int vitocm_mim_train_forward(vitocm_engine* e, const float* x, int B, int H, int
 int vitocm_mim_backward(vitocm_engine* e, const float* x, int B, int H, int W, const float* mask, const float* x_rec,
                         const double* loss_sums, const float* grad_scale, float* dpos, void* ws, size_t ws_bytes, void* stream);
 
+/* Gradient buckets for an all-reduce that overlaps the backward (data-parallel training): fills events[0..depth]
+ * with cudaEvent_t handles owned by the engine; every later vitocm_mim_backward records events[l] on its stream once ALL
+ * parameter gradients of transformer block l are complete (blocks finish last to first) and events[depth] once those of the
+ * decoder and the final norm are.  The embedding gradients (cls / mask token, patch filter; pos via dpos) complete when the call's
+ * last kernel does.  vitocm_stream_wait_event(stream, event) = cudaStreamWaitEvent, for callers without a CUDA binding. */
+int vitocm_mim_backward_events(vitocm_engine* e, void** events, int n);
+int vitocm_stream_wait_event(void* stream, void* event);
+
 /* torch.nn.utils.clip_grad_norm_ (mim.py:176), first half: out[0] = sum g^2 over a flat fp32 gradient buffer (fp64). */
 int vitocm_grad_sumsq(const float* g, int64_t n, double* out, void* stream);
-/* Second half fused with torch.optim.AdamW.step (optimizer.py:73-75) over flat fp32 buffers of n elements:
+/* Second half, in place like the reference's call (mim.py:176): g <- g * min(1, max_norm / (sqrt(*sumsq) + 1e-6)), the coefficient
+ * formed on the device from the sum of squares vitocm_grad_sumsq just wrote (no host sync). */
+int vitocm_grad_clip(float* g, int64_t n, float max_norm, const double* sumsq, void* stream);
+/* torch.optim.AdamW.step (the clip may also be folded in: max_norm > 0 with the sumsq of the CURRENT gradient)
+ * Second half fused with torch.optim.AdamW.step (optimizer.py:73-75) over flat fp32 buffers of n elements:
  * g <- g * grad_scale * min(1, max_norm / (sqrt(*sumsq) * grad_scale + 1e-6)) (max_norm <= 0 or sumsq NULL: no clipping),
  * then the decoupled-weight-decay Adam update with bias correction for step number `step` (1-based); decay[i] != 0
  * selects weight decay per element (none for 1-D parameters and biases, optimizer.py:14-33). */

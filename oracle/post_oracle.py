@@ -38,6 +38,28 @@ def compute_attention_from_rows(cls_rows: np.ndarray, w_featmap: int, h_featmap:
     return np.ascontiguousarray(a, dtype=np.float32), nh
 
 
+def cummass_threshold(cls_rows: np.ndarray, threshold: float, w_featmap: int, h_featmap: int, patch_size: int):
+    """The `--threshold` mode named by the flag at SSS/eval.py:33-34.  Its arithmetic is NOT under /root/reference (the reference
+    only keeps the flag): this restates upstream DINO's visualize_attention.py (facebookresearch/dino, the file the reference's
+    eval script was derived from) -- PARITY UNPINNED BY THE REFERENCE.  cls_rows [H, N] of one image ->
+    (th_attn [H, w*p, h*p] float32 in {0, 1}, low-res keep mask [H, n] bool)."""
+    import torch
+    import torch.nn.functional as F
+    a = torch.from_numpy(np.ascontiguousarray(cls_rows[:, 1:], dtype=np.float32))
+    nh = a.shape[0]
+    val, idx = torch.sort(a)                       # ascending
+    val = val / torch.sum(val, dim=1, keepdim=True)
+    cumval = torch.cumsum(val, dim=1)
+    th_attn = cumval > (1 - threshold)
+    idx2 = torch.argsort(idx)
+    for head in range(nh):
+        th_attn[head] = th_attn[head][idx2[head]]
+    low = th_attn.clone().numpy()
+    th_attn = th_attn.reshape(nh, w_featmap, h_featmap).float()
+    up = F.interpolate(th_attn.unsqueeze(0), scale_factor=patch_size, mode="nearest")[0].numpy()
+    return up, low, (cumval.numpy(), idx.numpy())
+
+
 # --------------------------------------------------------------------------------------
 # P3: cv2.resize(..., INTER_LINEAR) on a 2-D float32 image
 # --------------------------------------------------------------------------------------

@@ -261,3 +261,33 @@ def test_direct_mosaic_ingest_equals_materialised_crops_bit_for_bit():
     mos = torch.from_numpy(VO.synthetic_mosaic_u8(100, seed=5)).cuda()
     a, b = seg_a.segment(mos), seg_b.segment(mos)
     assert torch.equal(a["lowres"], b["lowres"]) and torch.equal(a["th"], b["th"]) and torch.equal(a["th3"], b["th3"])
+
+
+@pytest.mark.parametrize("threshold", [0.6, 0.9, 0.1])
+def test_cumulative_mass_threshold_matches_the_upstream_restatement(threshold):
+    """`--threshold` (SSS/eval.py:33-34): keep the patches holding the top `threshold` of each head's attention mass.  Oracle =
+    the PyTorch restatement of upstream DINO's visualize_attention.py (parity unpinned by the reference).  Sorting and the mask
+    scatter are exact; the cumulative sum is a parallel scan here and sequential in torch, so an element whose cumulative mass
+    lies within 1e-5 of 1 - threshold may fall on either side -- those are excluded, everything else must agree exactly."""
+    rng = np.random.RandomState(7)
+    T, H, N = 5, 6, 785
+    logits = rng.randn(T, H, N).astype(np.float32) * 1.5
+    rows = np.exp(logits) / np.exp(logits).sum(-1, keepdims=True)
+    rows[1, 2, 5:9] = rows[1, 2, 5]                      # ties
+    d = torch.from_numpy(rows).cuda()
+    mask, up = vob.utils.cummass_threshold(d, threshold, 28, 28, 8)
+    mask, up = mask.cpu().numpy(), up.cpu().numpy()
+    assert mask.shape == (T, H, N - 1) and up.shape == (T, H, 224, 224)
+    for t in range(T):
+        o_up, o_low, (cumval, idx) = PO.cummass_threshold(rows[t], threshold, 28, 28, 8)
+        near = np.zeros((H, N - 1), dtype=bool)
+        for h in range(H):
+            near[h, idx[h][np.abs(cumval[h] - np.float32(1 - threshold)) <= 1e-5]] = True
+        assert ((mask[t] != 0) == o_low)[~near].all()
+        assert near.sum() <= 4 * H
+        # kept mass is at least `threshold` of the head's total, and dropping the smallest kept patch would go below it
+        for h in range(H):
+            kept = rows[t, h, 1:][mask[t, h] != 0].sum() / rows[t, h, 1:].sum()
+            assert kept >= threshold - 1e-4
+        # nearest x 8 upsampling of the device's own low-res mask
+        assert np.array_equal(up[t], np.repeat(np.repeat(mask[t].reshape(H, 28, 28), 8, 1), 8, 2).astype(np.float32))

@@ -91,7 +91,7 @@ def test_fused_optimizer_path_tracks_oracle():
         opt.zero_grad()
         loss, _, _ = mim(x, mask)
         loss.sum().backward()
-        total = vob.optimizer.clip_grad_norm_(mim.parameters() if False else mim, clip)
+        total = vob.optimizer.clip_grad_norm_(mim.parameters(), clip)      # the reference's call form (SSS/mim.py:176)
         opt.step()
         assert abs(loss.item() - float(g[f"step{it}/loss"])) <= 2e-2 * abs(float(g[f"step{it}/loss"]))
         assert abs(total.item() - float(g[f"step{it}/grad_norm"])) <= 2e-2 * float(g[f"step{it}/grad_norm"])

@@ -105,6 +105,21 @@ def test_vits8_tile_post_chain_matches_reference():
         assert (a == b).mean() >= 0.9999
 
 
+def test_vitb8_oracle_matches_reference_golden():
+    """ViT-B/8 (BASELINE configs[2]): the oracle's functional forward against the reference's own CLS rows and masks."""
+    g = load_golden("vitb8_tile.npz")
+    cfg = VO.ViTConfig(**VO.VIT_BASE)
+    sd = VO.randomize_affine(VO.init_state_dict(cfg, seed=0), seed=1, scale=0.02)
+    check_weight_sums(sd, g)
+    x = VO.synthetic_tile(224, seed=int(g["x_seed"]), batch=1)
+    rows = VO.cls_attention_rows(sd, cfg, x).numpy()
+    assert rows.shape == (1, 12, 785)
+    assert (np.abs(rows - g["cls_rows"]) / np.abs(g["cls_rows"])).max() <= 1e-5
+    th, th2, th3, _, _ = PO.eval_tile(rows[0], x[0, 0].numpy(), 8)
+    for a, b in ((th, g["th"]), (th2, g["th2"]), (th3, g["th3"])):
+        assert (a == b).mean() >= 0.9999
+
+
 def test_mask_generator_and_mim_loss():
     g = load_golden("mim_tiny.npz")
     m = VO.mask_generator(np.random.RandomState(0), 224, 16, 8, 0.5)

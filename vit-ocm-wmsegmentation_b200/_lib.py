@@ -46,6 +46,7 @@ SIGNATURES = {
                                    c_int, c_void_p]),
     "vitocm_final_norm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vitocm_head_mean": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "vitocm_attn_cummass": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vitocm_tile_threshold": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
     "vitocm_extract_tiles": (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
@@ -85,7 +86,10 @@ SIGNATURES = {
                                          c_size_t, c_void_p]),
     "vitocm_mim_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_size_t, c_void_p]),
+    "vitocm_mim_backward_events": (c_int, [c_void_p, c_void_p, c_int]),
+    "vitocm_stream_wait_event": (c_int, [c_void_p, c_void_p]),
     "vitocm_grad_sumsq": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "vitocm_grad_clip": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_void_p]),
     "vitocm_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_float,
                                   c_int, c_float, c_float, c_void_p, c_void_p]),
     "vitocm_wgrad": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

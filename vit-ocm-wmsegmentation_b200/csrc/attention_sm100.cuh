@@ -52,6 +52,12 @@ struct AttnArgs {
   int out_lo_off;    // SPLIT: column offset of the lo half of ctx
   float* lse2;       // training: [B][H][Npad] (Npad = N rounded up to 128) log2-sum-exp of the scaled logits
                      // (max * scale_log2 + log2 l); +inf in the pad rows; or nullptr
+  int track_max;        // 1 = round-1 behaviour: every KV block's row maximum is computed (128 FMNMX per thread and block) to detect a
+                        // row rising above the maximum in use; 0 (default) = only block 0's maximum is computed; later blocks
+                        // are checked through their row SUM of exponentials (one compare + vote): while no sum exceeds
+                        // 2^ATT_SUM_TRIGGER no single exponential can have overflowed the 16-bit P format, and a stale maximum is
+                        // exact otherwise (softmax is shift invariant, O and l accumulate in fp32).  Only a block that trips
+                        // the trigger pays for row_max(), the rescale of O and a second pass of exponentials.
   int timeline_item;    // diagnostics: which of a CTA's work items (0, 1, ...) the stamps are taken on
   long long* timeline;  // diagnostics (vitocm_attention_timeline) or nullptr: clock64 stamps of CTAs (0,0,0) and (1,0,0)
 };
@@ -79,6 +85,10 @@ constexpr int ATT_P_COL = 192;    // P: 64 columns of packed bf16x2 (128 keys); 
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units: raise the running maximum (rescale O, l) before the next block
 constexpr float ATT_REDO_THRESHOLD = 60.0f;    // log2 units: exp2 of the current block may overflow -> redo it now
 constexpr float ATT_REDO_THRESHOLD_F16 = 14.0f;   // fp16 P: 2^14 < 65504
+// track_max == 0: a block whose row sum of exponentials exceeds this is redone against its true maximum.  bf16 P shares fp32's
+// exponent range (trigger far below fp32 overflow of the sum and of O: 2^100 x 12 545 keys << 2^127); fp16 P must stay < 65504.
+constexpr float ATT_SUM_TRIGGER = 1.2676506e30f;      // 2^100
+constexpr float ATT_SUM_TRIGGER_F16 = 16384.0f;       // 2^14
 constexpr int ATT_POLY_DEFAULT = 0;            // see run_attention (0: all MUFU, 1: 4/16 polynomial, 2: 7/16)
 
 template <bool SPLIT>
@@ -515,7 +525,22 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gr
         if (!SPLIT && POLY_MASK != 0 && kv_len == ATT_BKV) exp_chunks(std::true_type{}); else exp_chunks(std::false_type{});
       };
       run_exps();
-      if (j > 0) {
+      if (j > 0 && !args.track_max) {
+        float a0, a1, b0, b1;
+        ptx::unpack_f32x2(sum2[0], a0, a1);
+        ptx::unpack_f32x2(sum2[1], b0, b1);
+        const float bsum = (a0 + a1) + (b0 + b1);
+        // !(bsum <= T) also catches inf / NaN sums
+        if (__any_sync(0xffffffffu, !(bsum <= (F16 ? ATT_SUM_TRIGGER_F16 : ATT_SUM_TRIGGER)))) {
+          const float m_blk = row_max();
+          const float m_new = fmaxf(m_used, m_blk);
+          const float a = ptx::ex2_approx((m_used - m_new) * sl2);
+          m_used = m_new;
+          l_run *= a;
+          rescale_o(a);
+          run_exps();
+        }
+      } else if (j > 0) {
         const float excess = (row_max() - m_used) * sl2;       // independent of the exponentials above: overlaps them
         constexpr float REDO = F16 ? ATT_REDO_THRESHOLD_F16 : ATT_REDO_THRESHOLD;
         if (__any_sync(0xffffffffu, excess > REDO)) {

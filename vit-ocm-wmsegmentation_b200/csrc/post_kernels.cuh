@@ -78,6 +78,87 @@ head_mean_kernel(const float* __restrict__ rows, float* __restrict__ lowres, int
 }
 
 // ---------------------------------------------------------------------------------------
+// Cumulative-mass threshold of upstream DINO's visualize_attention.py, the semantics behind the reference's `--threshold`
+// flag (help text at SSS/eval.py:33-34; the code itself is not under /root/reference: parity unpinned by the reference,
+// oracle = oracle/post_oracle.py cummass_threshold).  Per (tile, head), over the n patch columns of the CLS row:
+//     val, idx = sort(a) ascending;  val /= sum(val);  cum = cumsum(val);  keep = cum > 1 - th;  mask[idx] = keep
+// i.e. the SMALLEST-attention patches holding 1 - th of the mass are dropped.  One block per (tile, head): bitonic sort of
+// (value, index) pairs in shared memory (n padded to a power of two with +inf), row sum and inclusive scan by warp shuffles,
+// scatter through the sorted indices; optionally the nearest x p upsampling (F.interpolate(mode="nearest")) as floats.
+// ---------------------------------------------------------------------------------------
+constexpr int CM_MAX = 4096;   // patches per tile (power of two bound): 224^2 / 8^2 = 784 -> 1024; 448^2 -> 3136 -> 4096
+__global__ void __launch_bounds__(256)
+cummass_kernel(const float* __restrict__ rows /*[T][H][N]*/, int heads, int N, int npow2, float keep_above /*fp32(1 - th)*/,
+               uint8_t* __restrict__ mask /*[T][H][N-1]*/, float* __restrict__ up /*[T][H][lh*p][lw*p] or null*/, int lh, int lw, int p) {
+  extern __shared__ float cm_smem[];           // val[npow2] | idx[npow2] (int) | warp partials[8]
+  float* val = cm_smem;
+  int* idx = reinterpret_cast<int*>(cm_smem + npow2);
+  float* part = cm_smem + 2 * npow2;
+  const int n = N - 1;
+  const long long th_ = blockIdx.x;            // (tile, head) pair
+  const float* a = rows + th_ * N + 1;         // skip the CLS column
+  for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+    val[i] = i < n ? a[i] : INFINITY;
+    idx[i] = i;
+  }
+  __syncthreads();
+  // bitonic sort ascending by (value, index)
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool up_dir = (i & k) == 0;
+          const float vi = val[i], vl = val[l];
+          const int ii = idx[i], il = idx[l];
+          const bool gt = vi > vl || (vi == vl && ii > il);
+          if (gt == up_dir) { val[i] = vl; val[l] = vi; idx[i] = il; idx[l] = ii; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // total mass
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += val[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float total = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) total += part[w];
+  __syncthreads();
+  // inclusive scan of val / total in sorted order: each thread owns a contiguous run of `per` elements
+  const int per = (n + blockDim.x - 1) / blockDim.x;
+  const int b0 = threadIdx.x * per, b1 = min(b0 + per, n);
+  float run = 0.f;
+  for (int i = b0; i < b1; ++i) run += __fdiv_rn(val[i], total);
+  float incl = run;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) part[warp] = incl;
+  __syncthreads();
+  float base = incl - run;
+  for (int w = 0; w < warp; ++w) base += part[w];
+  uint8_t* m = mask + th_ * n;
+  float c = base;
+  for (int i = b0; i < b1; ++i) {
+    c += __fdiv_rn(val[i], total);
+    m[idx[i]] = c > keep_above ? 1 : 0;
+  }
+  if (up == nullptr) return;
+  __syncthreads();                             // the mask row (global, written by this block) is read back below
+  const int S = lw * p;
+  float* u = up + th_ * static_cast<long long>(lh * p) * S;
+  for (int i = threadIdx.x; i < lh * p * S; i += blockDim.x) {
+    const int y = i / S, x = i - y * S;
+    u[i] = static_cast<float>(m[(y / p) * lw + x / p]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Otsu threshold from a 256-bin histogram (OpenCV's scan, fp64, first maximum wins).
 // ---------------------------------------------------------------------------------------
 __device__ inline int otsu_from_hist(const unsigned long long* hist) {
@@ -236,30 +317,48 @@ __global__ void extract_tiles_kernel(const uint8_t* __restrict__ mosaic, int mos
 __device__ __forceinline__ uint8_t blend_u8(uint8_t a, uint8_t b, double w) {
   return static_cast<uint8_t>(static_cast<int>(__dadd_rn(__dmul_rn(static_cast<double>(a), w), __dmul_rn(static_cast<double>(b), __dsub_rn(1.0, w)))));
 }
-__global__ void stitch_gray_kernel(const uint8_t* __restrict__ mosaic, int mos_h, int mos_w, long long pitch, StitchGeom g,
-                                   const double* __restrict__ wtab, int y_begin, int y_end, uint8_t* __restrict__ out /*[E][E]*/) {
-  const long long total = static_cast<long long>(y_end - y_begin) * g.E;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int Y = y_begin + static_cast<int>(idx / g.E), X = static_cast<int>(idx % g.E);
-    // every crop holds the same source pixel (zero beyond the mosaic)
-    const uint8_t src = (Y < mos_h && X < mos_w) ? mosaic[Y * pitch + X] : 0;
-    int j0 = (X - g.W + g.S) / g.S; if (X - g.W + 1 <= 0) j0 = 0; if (j0 < 0) j0 = 0;
-    int j1 = min(X / g.S, g.n - 1);
-    int i0 = (Y - g.W + g.S) / g.S; if (Y - g.W + 1 <= 0) i0 = 0; if (i0 < 0) i0 = 0;
-    int i1 = min(Y / g.S, g.n - 1);
-    // horizontal sequence is identical for every strip (same source value)
-    uint8_t hv = src;
-    for (int j = j0 + 1; j <= j1; ++j) {
-      const int kx = X - j * g.S;
-      hv = (kx < g.step) ? blend_u8(hv, src, wtab[kx]) : src;
+// Row-organised: a thread owns V consecutive pixels of a row; the covering-tile ranges come from one division per thread,
+// the vertical blend sequence (same for the whole row) from the row index.
+template <int V>
+__global__ void __launch_bounds__(256)
+stitch_gray_kernel(const uint8_t* __restrict__ mosaic, int mos_h, int mos_w, long long pitch, StitchGeom g,
+                   const double* __restrict__ wtab, int y_begin, int y_end, uint8_t* __restrict__ out /*[E][E]*/) {
+  const int X0 = (blockIdx.x * 256 + threadIdx.x) * V;
+  if (X0 >= g.E) return;
+  const int dW = g.W / g.S, eW = g.W % g.S;
+  const int q0 = X0 / g.S, r0 = X0 - q0 * g.S;
+  for (int Y = y_begin + blockIdx.y; Y < y_end; Y += gridDim.y) {
+    const int qy = Y / g.S, ry = Y - qy * g.S;
+    int i1 = min(qy, g.n - 1);
+    int i0 = qy + 1 - dW - (ry < eW ? 1 : 0);
+    if (i0 < 0) i0 = 0;
+    uint8_t res[V];
+    int q = q0, r = r0;
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      const int X = X0 + u;
+      // every crop holds the same source pixel (zero beyond the mosaic)
+      const uint8_t src = (Y < mos_h && X < mos_w) ? __ldg(mosaic + Y * pitch + X) : 0;
+      int j1 = min(q, g.n - 1);
+      int j0 = q + 1 - dW - (r < eW ? 1 : 0);
+      if (j0 < 0) j0 = 0;
+      // horizontal sequence is identical for every strip (same source value)
+      uint8_t hv = src;
+      for (int j = j0 + 1; j <= j1; ++j) {
+        const int kx = (q - j) * g.S + r;
+        hv = (kx < g.step) ? blend_u8(hv, src, __ldg(wtab + kx)) : src;
+      }
+      uint8_t v = hv;
+      for (int i = i0 + 1; i <= i1; ++i) {
+        const int ky = Y - i * g.S;
+        v = (ky < g.step) ? blend_u8(v, hv, __ldg(wtab + ky)) : hv;
+      }
+      res[u] = v;
+      if (++r == g.S) { r = 0; ++q; }
     }
-    uint8_t v = hv;
-    for (int i = i0 + 1; i <= i1; ++i) {
-      const int ky = Y - i * g.S;
-      v = (ky < g.step) ? blend_u8(v, hv, wtab[ky]) : hv;
-    }
-    out[static_cast<long long>(Y) * g.E + X] = v;
+    const long long o = static_cast<long long>(Y) * g.E + X0;
+    if (V == 4) *reinterpret_cast<uchar4*>(out + o) = make_uchar4(res[0], res[1 % V], res[2 % V], res[3 % V]);
+    else out[o] = res[0];
   }
 }
 
@@ -425,22 +524,120 @@ __global__ void concat_grid_f32_kernel(const float* __restrict__ src, int B, int
   }
 }
 
-// pass 1: global min / max of the stitched map over rows [y_begin, y_end); minmax_ord[0] = min, [1] = max
-// (order-preserving int keys; initialise to INT_MAX / INT_MIN); optionally store the map.
-__global__ void __launch_bounds__(256)
+// ---------------------------------------------------------------------------------------
+// Row-organised mosaic passes (round 2).  The first versions of these kernels walked a flat pixel index (two 64-bit divisions
+// per pixel), moved one byte per thread and re-evaluated the stitched map -- <= 4 bilinear samples and 3 fp64 blends per pixel --
+// in all three passes: 1.4 ms per 4032^2 mosaic, ~0.6 % of the HBM roofline.  Now a block owns 256*V consecutive pixels of a
+// row (V = 4 when rows are 16-byte aligned), everything that depends on the row only (covering tile rows, vertical bilinear
+// coefficients, vertical blend weights) is computed once per row, the horizontal coefficients come from a per-block table,
+// accesses are float4 / uchar4, and the stitched map is evaluated ONCE (pass 1 stores it as fp32, passes 2 and 3 stream it
+// back, mostly out of the 126 MB L2).  The arithmetic per value is unchanged (bilinear_tab == bilinear_up, blend_f32,
+// sw_classify), so the outputs stay bit-identical to the reference's sequential loops.
+// ---------------------------------------------------------------------------------------
+constexpr int ST_THREADS = 256;
+constexpr int ST_MAX_W = 1024;          // per-block coefficient table: W entries
+
+struct LinTab { int s0, s1; float f; };
+
+__device__ __forceinline__ float bilinear_tab(const float* __restrict__ lo, int lw, int y0, int y1, float fy, int x0, int x1, float fx) {
+  const float a0 = __fsub_rn(1.0f, fx), b0 = __fsub_rn(1.0f, fy);
+  const float r0 = __fadd_rn(__fmul_rn(__ldg(lo + y0 * lw + x0), a0), __fmul_rn(__ldg(lo + y0 * lw + x1), fx));
+  const float r1 = __fadd_rn(__fmul_rn(__ldg(lo + y1 * lw + x0), a0), __fmul_rn(__ldg(lo + y1 * lw + x1), fx));
+  return __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, fy));
+}
+
+// tiles covering coordinate P = q * S + r (q = P / S): [c0, c1]
+__device__ __forceinline__ void cover_range(const StitchGeom& g, int q, int r, int dW, int eW, int& c0, int& c1) {
+  c1 = min(q, g.n - 1);
+  c0 = q + 1 - dW - (r < eW ? 1 : 0);      // = (P - W + S) / S for P >= W - S ... clamped below
+  if (c0 < 0) c0 = 0;
+}
+
+// stitched value at (row context, X): same evaluation order as stitched_value()
+struct RowCtx {
+  int i0, i1;
+  int ky[4], y0[4], y1[4];
+  float fy[4];
+};
+__device__ __forceinline__ void make_row_ctx(const StitchGeom& g, int Y, RowCtx& rc) {
+  const int q = Y / g.S, r = Y - q * g.S;
+  cover_range(g, q, r, g.W / g.S, g.W % g.S, rc.i0, rc.i1);
+  if (rc.i1 - rc.i0 > 3) rc.i1 = rc.i0 + 3;   // (host guarantees W <= 4 S)
+  for (int k = 0; k <= rc.i1 - rc.i0; ++k) {
+    rc.ky[k] = Y - (rc.i0 + k) * g.S;
+    linear_coeff(rc.ky[k], g.scale, g.lh, rc.y0[k], rc.y1[k], rc.fy[k]);
+  }
+}
+__device__ __forceinline__ float stitched_value_row(const float* __restrict__ lowres, const StitchGeom& g, const double* __restrict__ wtab,
+                                                    const LinTab* __restrict__ tab, const RowCtx& rc, int q, int r, int dW, int eW) {
+  int j0, j1;
+  cover_range(g, q, r, dW, eW, j0, j1);
+  const int lsz = g.lh * g.lw;
+  float v = 0.f;
+  for (int k = 0; k <= rc.i1 - rc.i0; ++k) {
+    const int i = rc.i0 + k;
+    float hv = 0.f;
+    for (int j = j0; j <= j1; ++j) {
+      const int kx = (q - j) * g.S + r;
+      const LinTab t = tab[kx];
+      const float tv = bilinear_tab(lowres + static_cast<long long>(i * g.n + j) * lsz, g.lw, rc.y0[k], rc.y1[k], rc.fy[k], t.s0, t.s1, t.f);
+      hv = (j > j0 && kx < g.step) ? blend_f32(hv, tv, __ldg(wtab + kx)) : tv;
+    }
+    v = (k > 0 && rc.ky[k] < g.step) ? blend_f32(v, hv, __ldg(wtab + rc.ky[k])) : hv;
+  }
+  return v;
+}
+
+// launch geometry: grid.x covers a row in groups of 256 * V pixels, grid.y strides over the rows of the band
+template <int V>
+__device__ __forceinline__ int st_x0() { return (blockIdx.x * ST_THREADS + threadIdx.x) * V; }
+
+// pass 1: stitched map of rows [y_begin, y_end) -> map_out (fp32, absolute row index) and its global min / max
+// (order-preserving int keys; initialise to INT_MAX / INT_MIN).  map_in: take the values from there instead (function-level
+// sw_processing.threshold(img, attention)).
+template <int V>
+__global__ void __launch_bounds__(ST_THREADS)
 stitch_minmax_kernel(const float* __restrict__ lowres, StitchGeom g, const double* __restrict__ wtab, int y_begin, int y_end,
                      int* __restrict__ minmax_ord, float* __restrict__ map_out /*[E][E] or null*/,
                      const float* __restrict__ map_in /*[E][E] or null: use instead of stitching lowres*/) {
-  __shared__ float red_mn[8], red_mx[8];
-  const long long total = static_cast<long long>(y_end - y_begin) * g.E;
+  __shared__ LinTab tab[ST_MAX_W];
+  __shared__ float red_mn[ST_THREADS / 32], red_mx[ST_THREADS / 32];
+  if (map_in == nullptr) {
+    for (int k = threadIdx.x; k < g.W; k += ST_THREADS) linear_coeff(k, g.scale, g.lw, tab[k].s0, tab[k].s1, tab[k].f);
+    __syncthreads();
+  }
+  const int X0 = st_x0<V>();
+  const int dW = g.W / g.S, eW = g.W % g.S;
   float mn = INFINITY, mx = -INFINITY;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int Y = y_begin + static_cast<int>(idx / g.E), X = static_cast<int>(idx % g.E);
-    const float v = map_in != nullptr ? map_in[static_cast<long long>(Y) * g.E + X] : stitched_value(lowres, g, wtab, Y, X);
-    if (map_out != nullptr) map_out[static_cast<long long>(Y) * g.E + X] = v;
-    mn = fminf(mn, v);
-    mx = fmaxf(mx, v);
+  if (X0 < g.E) {
+    const int q0 = X0 / g.S, r0 = X0 - q0 * g.S;
+    for (int Y = y_begin + blockIdx.y; Y < y_end; Y += gridDim.y) {
+      float v[V];
+      const long long off = static_cast<long long>(Y) * g.E + X0;
+      if (map_in != nullptr) {
+        if (V == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(map_in + off);
+          v[0] = t.x; v[1 % V] = t.y; v[2 % V] = t.z; v[3 % V] = t.w;
+        } else {
+          v[0] = map_in[off];
+        }
+      } else {
+        RowCtx rc;
+        make_row_ctx(g, Y, rc);
+        int q = q0, r = r0;
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+          v[u] = stitched_value_row(lowres, g, wtab, tab, rc, q, r, dW, eW);
+          if (++r == g.S) { r = 0; ++q; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < V; ++u) { mn = fminf(mn, v[u]); mx = fmaxf(mx, v[u]); }
+      if (map_out != nullptr) {
+        if (V == 4) *reinterpret_cast<float4*>(map_out + off) = make_float4(v[0], v[1 % V], v[2 % V], v[3 % V]);
+        else map_out[off] = v[0];
+      }
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -449,7 +646,7 @@ stitch_minmax_kernel(const float* __restrict__ lowres, StitchGeom g, const doubl
   if ((threadIdx.x & 31) == 0) { red_mn[threadIdx.x >> 5] = mn; red_mx[threadIdx.x >> 5] = mx; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < (blockDim.x >> 5); ++w) { mn = fminf(mn, red_mn[w]); mx = fmaxf(mx, red_mx[w]); }
+    for (int w = 1; w < ST_THREADS / 32; ++w) { mn = fminf(mn, red_mn[w]); mx = fmaxf(mx, red_mx[w]); }
     if (mn <= mx) {
       atomicMin(&minmax_ord[0], f2ord(mn));
       atomicMax(&minmax_ord[1], f2ord(mx));
@@ -464,82 +661,161 @@ __device__ __forceinline__ void sw_classify(float v, float mn, float range, bool
   au = static_cast<int>(static_cast<uint8_t>(static_cast<int>(__fmul_rn(an, 255.0f))));
 }
 
-// pass 2: histograms of result (= img * att), of the stitched gray image and of att_u8 -> hists[3][256]
-__global__ void __launch_bounds__(256)
+// V stitched values + V gray bytes of (Y, X0 ...): the map comes from map_in when given (the fast path: pass 1 stored it),
+// else it is re-evaluated from the low-res maps
+template <int V>
+__device__ __forceinline__ void st_load_px(const float* __restrict__ lowres, const StitchGeom& g, const double* __restrict__ wtab,
+                                           const LinTab* __restrict__ tab, const float* __restrict__ map_in, const uint8_t* __restrict__ gray,
+                                           int Y, int X0, int q0, int r0, float (&v)[V], int (&img)[V]) {
+  const long long off = static_cast<long long>(Y) * g.E + X0;
+  if (map_in != nullptr) {
+    if (V == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(map_in + off);
+      v[0] = t.x; v[1 % V] = t.y; v[2 % V] = t.z; v[3 % V] = t.w;
+    } else {
+      v[0] = map_in[off];
+    }
+  } else {
+    RowCtx rc;
+    make_row_ctx(g, Y, rc);
+    int q = q0, r = r0;
+    const int dW = g.W / g.S, eW = g.W % g.S;
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      v[u] = stitched_value_row(lowres, g, wtab, tab, rc, q, r, dW, eW);
+      if (++r == g.S) { r = 0; ++q; }
+    }
+  }
+  if (V == 4) {
+    const uchar4 b = *reinterpret_cast<const uchar4*>(gray + off);
+    img[0] = b.x; img[1 % V] = b.y; img[2 % V] = b.z; img[3 % V] = b.w;
+  } else {
+    img[0] = gray[off];
+  }
+}
+
+// pass 2: histograms of result (= img * att), of the stitched gray image and of att_u8 -> hists[3][256].
+// One private histogram set per warp (the images are dark: a block-wide table serialises on a few bins).
+template <int V>
+__global__ void __launch_bounds__(ST_THREADS)
 stitch_hist_kernel(const float* __restrict__ lowres, StitchGeom g, const double* __restrict__ wtab,
                    const uint8_t* __restrict__ gray /*[E][E]*/, const int* __restrict__ minmax_ord, int y_begin, int y_end,
                    unsigned long long* __restrict__ hists, const float* __restrict__ map_in) {
-  __shared__ unsigned int h[3][256];
-  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) (&h[0][0])[i] = 0u;
+  __shared__ LinTab tab[ST_MAX_W];
+  __shared__ unsigned int h[ST_THREADS / 32][3][256];
+  for (int i = threadIdx.x; i < (ST_THREADS / 32) * 3 * 256; i += ST_THREADS) (&h[0][0][0])[i] = 0u;
+  if (map_in == nullptr)
+    for (int k = threadIdx.x; k < g.W; k += ST_THREADS) linear_coeff(k, g.scale, g.lw, tab[k].s0, tab[k].s1, tab[k].f);
   __syncthreads();
   const float mn = ord2f(minmax_ord[0]), mx = ord2f(minmax_ord[1]);
   const bool flat = (mx == mn);
   const float range = __fsub_rn(mx, mn);
   const float att_max = flat ? mx : 1.0f;  // np.max(attention) after min_max_normalize
-  const long long total = static_cast<long long>(y_end - y_begin) * g.E;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int Y = y_begin + static_cast<int>(idx / g.E), X = static_cast<int>(idx % g.E);
-    const float v = map_in != nullptr ? map_in[static_cast<long long>(Y) * g.E + X] : stitched_value(lowres, g, wtab, Y, X);
-    const int img = gray[static_cast<long long>(Y) * g.E + X];
-    int res, au;
-    sw_classify(v, mn, range, flat, att_max, img, res, au);
-    atomicAdd(&h[0][res], 1u);
-    atomicAdd(&h[1][img], 1u);
-    atomicAdd(&h[2][au], 1u);
+  const int X0 = st_x0<V>();
+  unsigned int (*hw)[256] = h[threadIdx.x >> 5];
+  if (X0 < g.E) {
+    const int q0 = X0 / g.S, r0 = X0 - q0 * g.S;
+    for (int Y = y_begin + blockIdx.y; Y < y_end; Y += gridDim.y) {
+      float v[V];
+      int img[V];
+      st_load_px<V>(lowres, g, wtab, tab, map_in, gray, Y, X0, q0, r0, v, img);
+#pragma unroll
+      for (int u = 0; u < V; ++u) {
+        int res, au;
+        sw_classify(v[u], mn, range, flat, att_max, img[u], res, au);
+        atomicAdd(&hw[0][res], 1u);
+        atomicAdd(&hw[1][img[u]], 1u);
+        atomicAdd(&hw[2][au], 1u);
+      }
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
-    const unsigned int c = (&h[0][0])[i];
+  for (int i = threadIdx.x; i < 3 * 256; i += ST_THREADS) {
+    unsigned int c = 0;
+#pragma unroll
+    for (int w = 0; w < ST_THREADS / 32; ++w) c += (&h[w][0][0])[i];
     if (c) atomicAdd(&hists[i], static_cast<unsigned long long>(c));
   }
 }
 
 // pass 3: masks th (result > t0), th2 (gray > t1), th3 (att_u8 > t2); rows [y_begin, y_end) written at
 // out + (Y - y_begin) * E so that a rank can hold only its own band.
-__global__ void __launch_bounds__(256)
+template <int V>
+__global__ void __launch_bounds__(ST_THREADS)
 stitch_mask_kernel(const float* __restrict__ lowres, StitchGeom g, const double* __restrict__ wtab,
                    const uint8_t* __restrict__ gray, const int* __restrict__ minmax_ord, const int* __restrict__ thr,
                    int y_begin, int y_end, uint8_t* __restrict__ th, uint8_t* __restrict__ th2, uint8_t* __restrict__ th3,
                    const float* __restrict__ map_in) {
+  __shared__ LinTab tab[ST_MAX_W];
+  if (map_in == nullptr) {
+    for (int k = threadIdx.x; k < g.W; k += ST_THREADS) linear_coeff(k, g.scale, g.lw, tab[k].s0, tab[k].s1, tab[k].f);
+    __syncthreads();
+  }
   const float mn = ord2f(minmax_ord[0]), mx = ord2f(minmax_ord[1]);
   const bool flat = (mx == mn);
   const float range = __fsub_rn(mx, mn);
   const float att_max = flat ? mx : 1.0f;
   const int t0 = thr[0], t1 = thr[1], t2 = thr[2];
-  const long long total = static_cast<long long>(y_end - y_begin) * g.E;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int Y = y_begin + static_cast<int>(idx / g.E), X = static_cast<int>(idx % g.E);
-    const float v = map_in != nullptr ? map_in[static_cast<long long>(Y) * g.E + X] : stitched_value(lowres, g, wtab, Y, X);
-    const int img = gray[static_cast<long long>(Y) * g.E + X];
-    int res, au;
-    sw_classify(v, mn, range, flat, att_max, img, res, au);
-    if (th != nullptr) th[idx] = res > t0 ? 255 : 0;
-    if (th2 != nullptr) th2[idx] = img > t1 ? 255 : 0;
-    if (th3 != nullptr) th3[idx] = au > t2 ? 255 : 0;
+  const int X0 = st_x0<V>();
+  if (X0 >= g.E) return;
+  const int q0 = X0 / g.S, r0 = X0 - q0 * g.S;
+  for (int Y = y_begin + blockIdx.y; Y < y_end; Y += gridDim.y) {
+    float v[V];
+    int img[V];
+    st_load_px<V>(lowres, g, wtab, tab, map_in, gray, Y, X0, q0, r0, v, img);
+    uint8_t m0[V], m1[V], m2[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      int res, au;
+      sw_classify(v[u], mn, range, flat, att_max, img[u], res, au);
+      m0[u] = res > t0 ? 255 : 0;
+      m1[u] = img[u] > t1 ? 255 : 0;
+      m2[u] = au > t2 ? 255 : 0;
+    }
+    const long long o = static_cast<long long>(Y - y_begin) * g.E + X0;
+    if (V == 4) {
+      if (th != nullptr) *reinterpret_cast<uchar4*>(th + o) = make_uchar4(m0[0], m0[1 % V], m0[2 % V], m0[3 % V]);
+      if (th2 != nullptr) *reinterpret_cast<uchar4*>(th2 + o) = make_uchar4(m1[0], m1[1 % V], m1[2 % V], m1[3 % V]);
+      if (th3 != nullptr) *reinterpret_cast<uchar4*>(th3 + o) = make_uchar4(m2[0], m2[1 % V], m2[2 % V], m2[3 % V]);
+    } else {
+      if (th != nullptr) th[o] = m0[0];
+      if (th2 != nullptr) th2[o] = m1[0];
+      if (th3 != nullptr) th3[o] = m2[0];
+    }
   }
 }
 
 // the weighted image `result = (img * att / max(att)).astype(u8)` of the mosaic flavour (SSS/sw_processing.py:44-46, the
 // "weighted_iamge_attention.png" it saves at :75) and att_u8, for rows [y_begin, y_end)
-__global__ void __launch_bounds__(256)
+template <int V>
+__global__ void __launch_bounds__(ST_THREADS)
 stitch_result_kernel(const float* __restrict__ lowres, StitchGeom g, const double* __restrict__ wtab, const uint8_t* __restrict__ gray,
                      const int* __restrict__ minmax_ord, int y_begin, int y_end, uint8_t* __restrict__ result, uint8_t* __restrict__ att_u8,
                      const float* __restrict__ map_in) {
+  __shared__ LinTab tab[ST_MAX_W];
+  if (map_in == nullptr) {
+    for (int k = threadIdx.x; k < g.W; k += ST_THREADS) linear_coeff(k, g.scale, g.lw, tab[k].s0, tab[k].s1, tab[k].f);
+    __syncthreads();
+  }
   const float mn = ord2f(minmax_ord[0]), mx = ord2f(minmax_ord[1]);
   const bool flat = (mx == mn);
   const float range = __fsub_rn(mx, mn);
   const float att_max = flat ? mx : 1.0f;
-  const long long total = static_cast<long long>(y_end - y_begin) * g.E;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int Y = y_begin + static_cast<int>(idx / g.E), X = static_cast<int>(idx % g.E);
-    const float v = map_in != nullptr ? map_in[static_cast<long long>(Y) * g.E + X] : stitched_value(lowres, g, wtab, Y, X);
-    int res, au;
-    sw_classify(v, mn, range, flat, att_max, gray[static_cast<long long>(Y) * g.E + X], res, au);
-    if (result != nullptr) result[idx] = static_cast<uint8_t>(res);
-    if (att_u8 != nullptr) att_u8[idx] = static_cast<uint8_t>(au);
+  const int X0 = st_x0<V>();
+  if (X0 >= g.E) return;
+  const int q0 = X0 / g.S, r0 = X0 - q0 * g.S;
+  for (int Y = y_begin + blockIdx.y; Y < y_end; Y += gridDim.y) {
+    float v[V];
+    int img[V];
+    st_load_px<V>(lowres, g, wtab, tab, map_in, gray, Y, X0, q0, r0, v, img);
+    const long long o = static_cast<long long>(Y - y_begin) * g.E + X0;
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      int res, au;
+      sw_classify(v[u], mn, range, flat, att_max, img[u], res, au);
+      if (result != nullptr) result[o + u] = static_cast<uint8_t>(res);
+      if (att_u8 != nullptr) att_u8[o + u] = static_cast<uint8_t>(au);
+    }
   }
 }
 

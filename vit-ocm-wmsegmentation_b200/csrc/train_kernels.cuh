@@ -314,6 +314,21 @@ sumsq_kernel(const float4* __restrict__ g, long long n4, const float* __restrict
   }
 }
 
+// second half of clip_grad_norm_ applied in place: g <- g * min(1, max_norm / (sqrt(sumsq) + 1e-6)); the coefficient is formed on
+// the device from the sum of squares (no host sync)
+__global__ void __launch_bounds__(256)
+grad_clip_kernel(float4* __restrict__ g, long long n4, float* __restrict__ tail, int ntail, const double* __restrict__ sumsq, float max_norm) {
+  const float c = max_norm / (static_cast<float>(sqrt(*sumsq)) + 1e-6f);
+  if (!(c < 1.0f)) return;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 v = g[i];
+    v.x *= c; v.y *= c; v.z *= c; v.w *= c;
+    g[i] = v;
+  }
+  if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < ntail) tail[threadIdx.x] *= c;
+}
+
 struct AdamWArgs {
   float lr, beta1, beta2, eps, weight_decay;
   float bias_corr1, bias_corr2_sqrt;   // 1 - beta1^t, sqrt(1 - beta2^t)

@@ -171,7 +171,9 @@ struct vitocm_engine {
   int lanes = 1;
   cudaStream_t aux[MAX_LANES - 1] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES - 1] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> bwd_events;   // vitocm_mim_backward_events: [depth] blocks + [1] head, recorded as the gradient buckets complete
   ~vitocm_engine() {
+    for (cudaEvent_t ev : bwd_events) if (ev) cudaEventDestroy(ev);
     for (auto& kv : master) delete kv.second;
     for (int i = 0; i < MAX_LANES - 1; ++i) {
       if (aux[i]) cudaStreamDestroy(aux[i]);
@@ -468,6 +470,7 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
   a.scale_log2 = e->cfg.qk_scale * 1.44269504088896340736f;
   a.out = reinterpret_cast<__nv_bfloat16*>(ctx); a.ldo = ldo; a.out_lo_off = D; a.timeline = timeline; a.lse2 = lse2;
   { static const int tli = [] { const char* v = getenv("VITOCM_ATTN_TL_ITEM"); return v ? atoi(v) : 0; }(); a.timeline_item = tli; }
+  { static const int tm = [] { const char* v = getenv("VITOCM_ATTN_TRACK_MAX"); return v ? atoi(v) : 0; }(); a.track_max = tm; }
   a.n_qtiles = (N + ATT_BQ - 1) / ATT_BQ; a.heads = H;
   // ragged query tail: <= 32 rows -> 4 (image, head) pairs share one tile, <= 64 rows -> 2 (VITOCM_ATTN_PACK=0: never)
   static const int pack_on = [] { const char* v = getenv("VITOCM_ATTN_PACK"); return v ? atoi(v) : 1; }();
@@ -1089,6 +1092,24 @@ int vitocm_head_mean(const float* rows, float* lowres, int T, int heads, int n_t
   return 0;
 }
 
+int vitocm_attn_cummass(const float* rows, int T, int heads, int n_tokens, float threshold, uint8_t* mask, float* up, int lh, int lw,
+                        int patch, void* stream) {
+  if (T <= 0) return 0;
+  if (rows == nullptr || mask == nullptr || heads < 1 || n_tokens < 2) return fail(VITOCM_ERR_INVALID, "attn_cummass: bad argument");
+  if (up != nullptr && (lh * lw != n_tokens - 1 || patch < 1)) return fail(VITOCM_ERR_INVALID, "attn_cummass: lh * lw must equal n_tokens - 1 for the upsampled output");
+  int npow2 = 32;
+  while (npow2 < n_tokens - 1) npow2 <<= 1;
+  if (npow2 > CM_MAX) return fail(VITOCM_ERR_INVALID, "attn_cummass: at most %d patches per tile", CM_MAX);
+  const size_t smem = static_cast<size_t>(2 * npow2 + 8) * sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof(PC_POST, st);
+  // `cumval > (1 - threshold)`: the Python double 1 - th is compared in the tensor's dtype, fp32
+  const float keep_above = static_cast<float>(1.0 - static_cast<double>(threshold));
+  cummass_kernel<<<T * heads, 256, smem, st>>>(rows, heads, n_tokens, npow2, keep_above, mask, up, lh, lw, patch);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 int vitocm_tile_threshold(const float* lowres, const float* x, int T, int C, int S, int lh, int lw, uint8_t* masks,
                           int* thresholds, float* att_out, const float* att_in, const uint8_t* img_in, void* stream) {
   if (T <= 0) return 0;
@@ -1127,6 +1148,38 @@ int vitocm_extract_tiles(const uint8_t* mosaic, int mos_h, int mos_w, int64_t pi
   return 0;
 }
 
+// Row-organised mosaic kernels: grid.x covers one row in groups of 256 * V pixels (V = 4 when every row of every buffer is
+// 16-byte aligned, i.e. E % 4 == 0 and aligned bases, else 1); grid.y strides over the rows of the band, ~8 blocks per SM
+struct StitchLaunch { dim3 grid; int V; };
+static StitchLaunch stitch_launch(int E, int rows, int num_sms, std::initializer_list<const void*> f32_ptrs, std::initializer_list<const void*> u8_ptrs) {
+  bool vec = (E % 4) == 0;
+  for (const void* p : f32_ptrs) if (p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15) != 0) vec = false;
+  for (const void* p : u8_ptrs) if (p != nullptr && (reinterpret_cast<uintptr_t>(p) & 3) != 0) vec = false;
+  StitchLaunch L;
+  L.V = vec ? 4 : 1;
+  const int gx = (E + 256 * L.V - 1) / (256 * L.V);
+  int gy = (num_sms * 8 + gx - 1) / gx;
+  if (gy > rows) gy = rows;
+  if (gy < 1) gy = 1;
+  L.grid = dim3(gx, gy);
+  return L;
+}
+static int device_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// kernels that evaluate the stitched map from the low-res maps keep a W-entry coefficient table in shared memory
+static int check_tab(const void* map_in, int W) {
+  if (map_in == nullptr && W > ST_MAX_W) return fail(VITOCM_ERR_INVALID, "window %d exceeds the stitch kernels' limit of %d pixels", W, ST_MAX_W);
+  return 0;
+}
+
 static StitchGeom make_geom(int n, int W, int S, int lh, int lw) {
   StitchGeom g;
   g.n = n; g.W = W; g.S = S; g.step = W - S; g.E = (n - 1) * S + W; g.lh = lh; g.lw = lw;
@@ -1135,6 +1188,7 @@ static StitchGeom make_geom(int n, int W, int S, int lh, int lw) {
 }
 static int check_geom(int n, int W, int S, int y_begin, int y_end) {
   if (n < 1 || S < 1 || W <= S) return fail(VITOCM_ERR_INVALID, "bad sliding-window geometry n=%d W=%d S=%d", n, W, S);
+  if (W > 4 * S) return fail(VITOCM_ERR_INVALID, "sliding-window geometry W=%d S=%d: at most four windows may overlap (W <= 4 S)", W, S);
   const int E = (n - 1) * S + W;
   if (y_begin < 0 || y_end > E || y_begin > y_end) return fail(VITOCM_ERR_INVALID, "bad row band [%d,%d) for extent %d", y_begin, y_end, E);
   return 0;
@@ -1145,9 +1199,11 @@ int vitocm_stitch_gray(const uint8_t* mosaic, int mos_h, int mos_w, int64_t pitc
   TRY(check_geom(n, W, S, y_begin, y_end));
   if (y_end == y_begin) return 0;
   const StitchGeom g = make_geom(n, W, S, 1, 1);
-  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
-  stitch_gray_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      mosaic, mos_h, mos_w, pitch, g, wtab, y_begin, y_end, out);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof(PC_POST, st);
+  const StitchLaunch L = stitch_launch(g.E, y_end - y_begin, device_sms(), {}, {out});
+  if (L.V == 4) stitch_gray_kernel<4><<<L.grid, 256, 0, st>>>(mosaic, mos_h, mos_w, pitch, g, wtab, y_begin, y_end, out);
+  else stitch_gray_kernel<1><<<L.grid, 256, 0, st>>>(mosaic, mos_h, mos_w, pitch, g, wtab, y_begin, y_end, out);
   LAUNCH_CHECK();
   return 0;
 }
@@ -1161,11 +1217,14 @@ int vitocm_minmax_init(int* minmax_ord, void* stream) {
 int vitocm_stitch_minmax(const float* lowres, int n, int W, int S, int lh, int lw, const double* wtab, int y_begin, int y_end,
                          int* minmax_ord, float* map_out, const float* map_in, void* stream) {
   TRY(check_geom(n, W, S, y_begin, y_end));
+  TRY(check_tab(map_in, W));
   if (y_end == y_begin) return 0;
   const StitchGeom g = make_geom(n, W, S, lh, lw);
-  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
-  stitch_minmax_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      lowres, g, wtab, y_begin, y_end, minmax_ord, map_out, map_in);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof(PC_POST, st);
+  const StitchLaunch L = stitch_launch(g.E, y_end - y_begin, device_sms(), {map_out, map_in}, {});
+  if (L.V == 4) stitch_minmax_kernel<4><<<L.grid, ST_THREADS, 0, st>>>(lowres, g, wtab, y_begin, y_end, minmax_ord, map_out, map_in);
+  else stitch_minmax_kernel<1><<<L.grid, ST_THREADS, 0, st>>>(lowres, g, wtab, y_begin, y_end, minmax_ord, map_out, map_in);
   LAUNCH_CHECK();
   return 0;
 }
@@ -1173,11 +1232,15 @@ int vitocm_stitch_minmax(const float* lowres, int n, int W, int S, int lh, int l
 int vitocm_stitch_hist(const float* lowres, int n, int W, int S, int lh, int lw, const double* wtab, const uint8_t* gray,
                        const int* minmax_ord, int y_begin, int y_end, uint64_t* hists, const float* map_in, void* stream) {
   TRY(check_geom(n, W, S, y_begin, y_end));
+  TRY(check_tab(map_in, W));
   if (y_end == y_begin) return 0;
   const StitchGeom g = make_geom(n, W, S, lh, lw);
-  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
-  stitch_hist_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      lowres, g, wtab, gray, minmax_ord, y_begin, y_end, reinterpret_cast<unsigned long long*>(hists), map_in);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof(PC_POST, st);
+  const StitchLaunch L = stitch_launch(g.E, y_end - y_begin, device_sms(), {map_in}, {gray});
+  unsigned long long* h = reinterpret_cast<unsigned long long*>(hists);
+  if (L.V == 4) stitch_hist_kernel<4><<<L.grid, ST_THREADS, 0, st>>>(lowres, g, wtab, gray, minmax_ord, y_begin, y_end, h, map_in);
+  else stitch_hist_kernel<1><<<L.grid, ST_THREADS, 0, st>>>(lowres, g, wtab, gray, minmax_ord, y_begin, y_end, h, map_in);
   LAUNCH_CHECK();
   return 0;
 }
@@ -1194,11 +1257,14 @@ int vitocm_stitch_mask(const float* lowres, int n, int W, int S, int lh, int lw,
                        const int* minmax_ord, const int* thr, int y_begin, int y_end, uint8_t* th, uint8_t* th2, uint8_t* th3,
                        const float* map_in, void* stream) {
   TRY(check_geom(n, W, S, y_begin, y_end));
+  TRY(check_tab(map_in, W));
   if (y_end == y_begin) return 0;
   const StitchGeom g = make_geom(n, W, S, lh, lw);
-  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
-  stitch_mask_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      lowres, g, wtab, gray, minmax_ord, thr, y_begin, y_end, th, th2, th3, map_in);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof(PC_POST, st);
+  const StitchLaunch L = stitch_launch(g.E, y_end - y_begin, device_sms(), {map_in}, {gray, th, th2, th3});
+  if (L.V == 4) stitch_mask_kernel<4><<<L.grid, ST_THREADS, 0, st>>>(lowres, g, wtab, gray, minmax_ord, thr, y_begin, y_end, th, th2, th3, map_in);
+  else stitch_mask_kernel<1><<<L.grid, ST_THREADS, 0, st>>>(lowres, g, wtab, gray, minmax_ord, thr, y_begin, y_end, th, th2, th3, map_in);
   LAUNCH_CHECK();
   return 0;
 }
@@ -1206,11 +1272,14 @@ int vitocm_stitch_mask(const float* lowres, int n, int W, int S, int lh, int lw,
 int vitocm_stitch_result(const float* lowres, int n, int W, int S, int lh, int lw, const double* wtab, const uint8_t* gray,
                          const int* minmax_ord, int y_begin, int y_end, uint8_t* result, uint8_t* att_u8, const float* map_in, void* stream) {
   TRY(check_geom(n, W, S, y_begin, y_end));
+  TRY(check_tab(map_in, W));
   if (y_end == y_begin) return 0;
   const StitchGeom g = make_geom(n, W, S, lh, lw);
-  ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
-  stitch_result_kernel<<<grid_for(static_cast<long long>(y_end - y_begin) * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      lowres, g, wtab, gray, minmax_ord, y_begin, y_end, result, att_u8, map_in);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof(PC_POST, st);
+  const StitchLaunch L = stitch_launch(g.E, y_end - y_begin, device_sms(), {map_in}, {gray});
+  if (L.V == 4) stitch_result_kernel<4><<<L.grid, ST_THREADS, 0, st>>>(lowres, g, wtab, gray, minmax_ord, y_begin, y_end, result, att_u8, map_in);
+  else stitch_result_kernel<1><<<L.grid, ST_THREADS, 0, st>>>(lowres, g, wtab, gray, minmax_ord, y_begin, y_end, result, att_u8, map_in);
   LAUNCH_CHECK();
   return 0;
 }

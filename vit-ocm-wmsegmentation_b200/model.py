@@ -146,6 +146,7 @@ class _MIMStep(torch.autograd.Function):
         gs = grad_loss.detach().to(torch.float32).reshape(1).contiguous()      # stays on the device: no host sync
         check(_lib.load_library().vitocm_mim_backward(mim.encoder._engine, ptr(xx), B, H, W, ptr(maskf), ptr(x_rec), ptr(sums), ptr(gs),
                                                       ptr(dpos), ptr(mim._train_ws), mim._train_ws.numel(), cur_stream()))
+        mim._launch_bucket_allreduce()
         return (None, None, None, dpos) + (None,) * len(mim._param_list)
 
 
@@ -172,6 +173,11 @@ class MIM(nn.Module):
         self._grad_views = None
         self._grads_bound_to = None
         self._flat_ptrs = None
+        self._overlap_group = None   # overlap_grad_allreduce(): process group (or True = WORLD) for the bucketed all-reduce
+        self._overlap = False
+        self._comm_stream = None
+        self._comm_done = None       # event: the bucket all-reduces of the last backward have finished
+        self._bwd_events = None
 
     # ------------------------------------------------------------------ training plumbing
     def _engine_name(self, pname: str) -> str:
@@ -248,12 +254,76 @@ class MIM(nn.Module):
                     check(lib.vitocm_bind_grad(eng, name.encode(), g.data_ptr()))
             self._grads_bound_to = key
 
-    def all_reduce_grads(self, group=None):
-        """Data parallelism over one process per GPU: sum the flat gradient buffer across ranks (NCCL over NVLink).
-        The reference trains under nn.DataParallel with ``loss.sum().backward()`` (SSS/mim.py:102,174): the gradient is
-        the SUM over replicas of each replica's mean loss, which is exactly all_reduce(SUM) of the per-rank gradients."""
+    def overlap_grad_allreduce(self, enabled: bool = True, group=None):
+        """Data-parallel training: launch the gradient all-reduce from INSIDE the next backward(s), one bucket per transformer
+        block (plus one for decoder + final norm), each as soon as that block's gradients are complete
+        (vitocm_mim_backward_events), on a side stream -- the collectives then run under the rest of the backward instead of
+        after it.  ``all_reduce_grads()`` afterwards only reduces the small embedding bucket (its pos_embed part is accumulated by
+        autograd after the backward kernel sequence) and joins the side stream.  Enable it only for a backward whose gradient is
+        final (the LAST micro-step under gradient accumulation): reducing a partial sum twice would count it R times."""
+        self._overlap = bool(enabled)
+        self._overlap_group = group
+        return self
+
+    def _buckets(self):
+        """[(event index, flat begin, flat end)] in backward order + the embedding range: blocks l own a contiguous range of the
+        flat buffer (named_parameters order), decoder + final norm the tail, cls / pos / mask token / patch filter the head."""
+        names = [n for n, _ in self._param_list]
+        offs = list(self._flat_offsets) + [self._pflat.numel()]
+        depth = self.encoder.depth
+
+        def span(pred):
+            idx = [i for i, n in enumerate(names) if pred(n)]
+            assert idx == list(range(idx[0], idx[-1] + 1)), "parameters of one bucket must be contiguous in the flat buffer"
+            return offs[idx[0]], offs[idx[-1] + 1]
+
+        out = [(depth,) + span(lambda n: n.startswith("norm.") or n.startswith("decoder."))]
+        for l in range(depth - 1, -1, -1):
+            out.append((l,) + span(lambda n, l=l: n.startswith(f"blocks.{l}.")))
+        embed = span(lambda n: not (n.startswith("blocks.") or n.startswith("norm.") or n.startswith("decoder.")))
+        return out, embed
+
+    def _launch_bucket_allreduce(self):
+        """Called by the backward right after vitocm_mim_backward has enqueued its kernels."""
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        self._comm_done = None
+        if not self._overlap or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self._overlap_group) < 2:
+            return
+        lib = _lib.load_library()
+        eng = self.encoder._engine
+        depth = self.encoder.depth
+        if self._bwd_events is None or self._bwd_events[0] != eng.value:
+            import ctypes as C
+            arr = (C.c_void_p * (depth + 1))()
+            check(lib.vitocm_mim_backward_events(eng, arr, depth + 1))
+            self._bwd_events = (eng.value, [arr[i] for i in range(depth + 1)])
+            # the events only exist from now on: this first backward was not instrumented -> flat reduce in all_reduce_grads()
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream()
+        buckets, _ = self._buckets()
+        with torch.cuda.stream(self._comm_stream):
+            for ev_idx, lo, hi in buckets:
+                check(lib.vitocm_stream_wait_event(self._comm_stream.cuda_stream, self._bwd_events[1][ev_idx]))
+                dist.all_reduce(self._gflat[lo:hi], op=dist.ReduceOp.SUM, group=self._overlap_group)
+            self._comm_done = torch.cuda.Event()
+            self._comm_done.record(self._comm_stream)
+
+    def all_reduce_grads(self, group=None):
+        """Data parallelism over one process per GPU: sum the gradients across ranks (NCCL over NVLink).
+        The reference trains under nn.DataParallel with ``loss.sum().backward()`` (SSS/mim.py:102,174): the gradient is
+        the SUM over replicas of each replica's mean loss, which is exactly all_reduce(SUM) of the per-rank gradients.
+        Order: backward -> all_reduce_grads -> clip_grad_norm_ -> optimizer.step.  After a backward that ran with
+        ``overlap_grad_allreduce`` only the embedding bucket is left to reduce; otherwise the whole flat buffer is."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return
+        if self._comm_done is not None:
+            _, (lo, hi) = self._buckets()
+            dist.all_reduce(self._gflat[lo:hi], op=dist.ReduceOp.SUM, group=group)
+            torch.cuda.current_stream().wait_event(self._comm_done)
+            self._comm_done = None
+        else:
             dist.all_reduce(self._gflat, op=dist.ReduceOp.SUM, group=group)
 
     def _forward_train(self, x, mask):

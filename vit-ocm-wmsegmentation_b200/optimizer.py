@@ -8,11 +8,14 @@ buffers of ``model.MIM``: gradient clipping coefficient, decoupled weight decay,
     grad_norm = clip_grad_norm_(model.parameters(), config.TRAIN.CLIP_GRAD)   # this module's, or torch's
     optimizer.step()
 
-``clip_grad_norm_`` here only measures the norm (fp64 sum of squares on the device, no host sync) and leaves the scaling
-to the next ``optimizer.step()``, which folds min(1, max_norm / (norm + 1e-6)) into the update and writes the clipped
-gradient back -- the values ``torch.nn.utils.clip_grad_norm_`` + ``torch.optim.AdamW`` would produce.
+``clip_grad_norm_`` here measures the norm (fp64 sum of squares on the device, no host sync) and scales the flat gradient in
+place by min(1, max_norm / (norm + 1e-6)) -- ``.grad`` holds the clipped values from then on, exactly as after
+``torch.nn.utils.clip_grad_norm_``; ``optimizer.step()`` then is ``torch.optim.AdamW``'s update on whatever ``.grad`` holds.
+In data-parallel training the order is backward -> ``MIM.all_reduce_grads()`` -> ``clip_grad_norm_`` -> ``step``.
 """
 from __future__ import annotations
+
+import weakref
 
 import torch
 
@@ -42,6 +45,9 @@ def get_pretrain_param_groups(model, logger=None, skip_list=(), skip_keywords=()
     return [{'params': has_decay}, {'params': no_decay, 'weight_decay': 0.}]
 
 
+_PARAM_OWNER: dict = {}     # id(parameter) -> weakref to the FusedAdamW that owns its flat buffers
+
+
 def _unwrap(model):
     return model.module if hasattr(model, "module") else model
 
@@ -64,15 +70,23 @@ class FusedAdamW(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros_like(mim._pflat)
         self.steps = 0
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=mim._pflat.device)
-        self._pending_max_norm = 0.0
         mim._fused_optimizer = self        # lets clip_grad_norm_(model, ...) find its optimizer
+        for _, p in mim._param_list:       # ... and clip_grad_norm_(model.parameters(), ...), the reference's call form
+            _PARAM_OWNER[id(p)] = weakref.ref(self)
 
     def measure_grad_norm(self, max_norm: float = 0.0) -> torch.Tensor:
-        """Global L2 norm of the flat gradient (device tensor); max_norm > 0 arms the clip of the next step()."""
+        """Global L2 norm of the flat gradient (device tensor, no host sync); with max_norm > 0 the gradient is clipped IN
+        PLACE right away, like torch.nn.utils.clip_grad_norm_ (SSS/mim.py:165-176 clips ``.grad`` on every micro-step):
+        whatever happens to ``.grad`` between this call and ``step()`` -- another micro-step's backward, an all-reduce --
+        acts on the clipped values, and ``step()`` never sees a stale coefficient.  Order in data-parallel training:
+        backward -> all_reduce_grads -> clip_grad_norm_ -> step (the clip must see the reduced gradient)."""
         g = self.mim._gflat
-        check(_lib.load_library().vitocm_grad_sumsq(ptr(g), g.numel(), ptr(self._sumsq), cur_stream()))
-        self._pending_max_norm = float(max_norm)
-        return self._sumsq.sqrt().to(torch.float32)[0]
+        lib = _lib.load_library()
+        check(lib.vitocm_grad_sumsq(ptr(g), g.numel(), ptr(self._sumsq), cur_stream()))
+        norm = self._sumsq.sqrt().to(torch.float32)[0]
+        if max_norm is not None and float(max_norm) > 0:
+            check(lib.vitocm_grad_clip(ptr(g), g.numel(), float(max_norm), ptr(self._sumsq), cur_stream()))
+        return norm
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
@@ -87,9 +101,7 @@ class FusedAdamW(torch.optim.Optimizer):
         n = mim._pflat.numel()
         check(_lib.load_library().vitocm_adamw_step(ptr(mim._pflat), ptr(mim._gflat), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.decay), n,
                                                     float(g0["lr"]), float(b1), float(b2), float(g0["eps"]), float(g0["weight_decay"]),
-                                                    self.steps, float(self._pending_max_norm), float(grad_scale),
-                                                    ptr(self._sumsq) if self._pending_max_norm > 0 else None, cur_stream()))
-        self._pending_max_norm = 0.0
+                                                    self.steps, 0.0, float(grad_scale), None, cur_stream()))
         mim.encoder.refresh_engine()      # asynchronous bf16 repack of the updated masters (vitocm_refresh_weights)
         return None
 
@@ -148,17 +160,21 @@ class FusedAdamW(torch.optim.Optimizer):
 
 
 def clip_grad_norm_(parameters, max_norm, optimizer: FusedAdamW | None = None):
-    """``torch.nn.utils.clip_grad_norm_`` for the fused path: returns the total norm (device tensor, no sync) and arms
-    the clip coefficient of the next ``optimizer.step()``.  ``parameters`` may be the model, its ``.parameters()`` or a
-    FusedAdamW; the optimizer is found through the model it was built for."""
+    """``torch.nn.utils.clip_grad_norm_`` for the fused path: clips the flat gradient in place and returns the total norm
+    (device tensor, no sync).  ``parameters`` may be the model, ``model.parameters()`` (any iterable of its parameters -- the
+    reference's call form, SSS/mim.py:176), a single parameter, or a FusedAdamW; the optimizer is found through the model /
+    the parameters it was built for.  All parameters of the model are clipped together (the reference always passes all)."""
     opt = optimizer
     if opt is None and isinstance(parameters, FusedAdamW):
         opt = parameters
+    if opt is None and hasattr(parameters, "parameters"):
+        opt = getattr(_unwrap(parameters), "_fused_optimizer", None)
     if opt is None:
-        mim = _unwrap(parameters) if hasattr(parameters, "parameters") else None
-        opt = getattr(mim, "_fused_optimizer", None) if mim is not None else None
+        first = parameters if isinstance(parameters, torch.Tensor) else next(iter(parameters), None)
+        ref = _PARAM_OWNER.get(id(first)) if first is not None else None
+        opt = ref() if ref is not None else None
     if opt is None:
-        raise _lib.VitocmError("clip_grad_norm_: pass the FusedAdamW optimizer (or the model it was built for)")
+        raise _lib.VitocmError("clip_grad_norm_: pass the FusedAdamW optimizer, the model it was built for, or that model's parameters")
     return opt.measure_grad_norm(max_norm)
 
 

@@ -82,29 +82,39 @@ def concat_crops(crops, stride, window_size):
     return out.cpu().numpy()
 
 
-def _threshold_device(lib, lowres, geom, wtab, gray, map_in, y0, y1, group=None, want=("th", "th3")):
-    """Three passes over output rows [y0, y1): min/max -> histograms -> Otsu -> masks."""
+def _threshold_device(lib, lowres, geom, wtab, gray, map_in, y0, y1, group=None, want=("th", "th3"), gray_base=None):
+    """Three passes over output rows [y0, y1): stitched map + min/max -> histograms -> Otsu -> masks.  The stitched map is
+    evaluated once (pass 1 keeps it as an fp32 band, passes 2 and 3 read it back).  gray: full [E, E] uint8 tensor, or None with
+    gray_base = address such that row Y of the stitched image starts at gray_base + Y * E (a band buffer shifted by y0 rows)."""
     n, W, S, lh, lw = geom
     E = (n - 1) * S + W
-    dev = gray.device
+    dev = lowres.device if lowres is not None else map_in.device
     st = cur_stream()
+    gray_p = ptr(gray) if gray is not None else gray_base
+    rows = y1 - y0
     minmax = torch.empty(2, dtype=torch.int32, device=dev)
     check(lib.vitocm_minmax_init(ptr(minmax), st))
-    check(lib.vitocm_stitch_minmax(ptr(lowres), n, W, S, lh, lw, ptr(wtab), y0, y1, ptr(minmax), None, ptr(map_in), st))
+    band_map = None
+    if map_in is None:
+        # absolute-row addressing into a band-sized buffer: base = data_ptr - y0 * E * 4 (never dereferenced outside [y0, y1))
+        band_map = torch.empty(max(rows, 1), E, dtype=torch.float32, device=dev)
+        map_p = band_map.data_ptr() - y0 * E * 4
+        check(lib.vitocm_stitch_minmax(ptr(lowres), n, W, S, lh, lw, ptr(wtab), y0, y1, ptr(minmax), map_p, None, st))
+    else:
+        map_p = ptr(map_in)
+        check(lib.vitocm_stitch_minmax(None, n, W, S, lh, lw, ptr(wtab), y0, y1, ptr(minmax), None, map_p, st))
     if group is not None:
         allreduce_minmax(minmax, group)
     hists = torch.zeros(3, 256, dtype=torch.int64, device=dev)
-    check(lib.vitocm_stitch_hist(ptr(lowres), n, W, S, lh, lw, ptr(wtab), ptr(gray), ptr(minmax), y0, y1, ptr(hists),
-                                 ptr(map_in), st))
+    check(lib.vitocm_stitch_hist(ptr(lowres), n, W, S, lh, lw, ptr(wtab), gray_p, ptr(minmax), y0, y1, ptr(hists), map_p, st))
     if group is not None:
         import torch.distributed as dist
         dist.all_reduce(hists, op=dist.ReduceOp.SUM, group=group)
     thr = torch.empty(3, dtype=torch.int32, device=dev)
     check(lib.vitocm_otsu(ptr(hists), 3, ptr(thr), st))
-    rows = y1 - y0
     masks = {k: torch.empty(rows, E, dtype=torch.uint8, device=dev) for k in want}
-    check(lib.vitocm_stitch_mask(ptr(lowres), n, W, S, lh, lw, ptr(wtab), ptr(gray), ptr(minmax), ptr(thr), y0, y1,
-                                 ptr(masks.get("th")), ptr(masks.get("th2")), ptr(masks.get("th3")), ptr(map_in), st))
+    check(lib.vitocm_stitch_mask(ptr(lowres), n, W, S, lh, lw, ptr(wtab), gray_p, ptr(minmax), ptr(thr), y0, y1,
+                                 ptr(masks.get("th")), ptr(masks.get("th2")), ptr(masks.get("th3")), map_p, st))
     return masks, thr, minmax, hists
 
 
@@ -144,17 +154,37 @@ def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+_COLL_CACHE: dict = {}
+
+
+def _cached(key, shape, dtype, device, zero=False):
+    """Buffers of the collectives are allocated once per (role, shape, dtype, device) and reused by every later call."""
+    k = (key, tuple(shape), dtype, str(device))
+    t = _COLL_CACHE.get(k)
+    if t is None:
+        t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=device)
+        _COLL_CACHE[k] = t
+    return t
+
+
 def allgather_shards(local: torch.Tensor, total: int, rank: int, world: int, group=None) -> torch.Tensor:
     """Every rank holds items shard_range(total, rank, world) along dim 0; returns all `total`
-    items on every rank (one padded all_gather; works for NCCL on CUDA and gloo on CPU tensors)."""
+    items on every rank (one padded all_gather into a preallocated buffer; NCCL on CUDA, gloo on CPU tensors)."""
     if world == 1:
         return local.contiguous()
     import torch.distributed as dist
     per = (total + world - 1) // world
-    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    tail = tuple(local.shape[1:])
+    pad = _cached("ag_in", (per,) + tail, local.dtype, local.device, zero=True)
     pad[: local.shape[0]] = local
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad, group=group)
+    full = _cached("ag_out", (world * per,) + tail, local.dtype, local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(full, pad, group=group)
+    else:                                            # gloo: list form
+        dist.all_gather(list(full.view((world, per) + tail).unbind(0)), pad, group=group)
+    if total == world * per:
+        return full
+    parts = full.view((world, per) + tail)
     out = []
     for r in range(world):
         a, b = shard_range(total, r, world)
@@ -164,18 +194,25 @@ def allgather_shards(local: torch.Tensor, total: int, rank: int, world: int, gro
 
 def gather_bands(band: torch.Tensor, total_rows: int, rank: int, world: int, group=None, dst: int = 0):
     """Row bands shard_range(total_rows, r, world) -> the full [total_rows, ...] tensor on group rank
-    `dst` (None elsewhere): the final mask gather."""
+    `dst` (None elsewhere): the final mask gather.  Receive buffers are preallocated views of one tensor."""
     if world == 1:
         return band
     import torch.distributed as dist
     per = (total_rows + world - 1) // world
-    pad = torch.zeros((per,) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
-    pad[: band.shape[0]] = band
-    buf = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    tail = tuple(band.shape[1:])
+    if band.shape[0] == per:
+        pad = band.contiguous()
+    else:
+        pad = _cached("gb_in", (per,) + tail, band.dtype, band.device, zero=True)
+        pad[: band.shape[0]] = band
+    full = _cached(("gb_out", id(group)), (world * per,) + tail, band.dtype, band.device) if rank == dst else None
+    buf = list(full.view((world, per) + tail).unbind(0)) if rank == dst else None
     gdst = dist.get_global_rank(group, dst) if group is not None else dst
     dist.gather(pad, buf, dst=gdst, group=group)
     if rank != dst:
         return None
+    if total_rows == world * per:
+        return full
     out = []
     for r in range(world):
         a, b = shard_range(total_rows, r, world)
@@ -188,6 +225,23 @@ def allreduce_minmax(minmax_ord: torch.Tensor, group=None) -> None:
     import torch.distributed as dist
     dist.all_reduce(minmax_ord[0:1], op=dist.ReduceOp.MIN, group=group)
     dist.all_reduce(minmax_ord[1:2], op=dist.ReduceOp.MAX, group=group)
+
+
+def shared_pinned_u8(path: str, shape, create: bool) -> torch.Tensor:
+    """uint8 HOST tensor backed by a shared file mapping (put `path` under /dev/shm) and page-locked with cudaHostRegister, so
+    that several single-GPU processes can each copy their band of a mask device -> host into ONE image, in parallel over their
+    own PCIe links.  The creator passes create=True before the others open it; unlink the file when done."""
+    numel = 1
+    for d in shape:
+        numel *= int(d)
+    if create:
+        with open(path, "wb") as f:
+            f.truncate(numel)
+    t = torch.from_file(path, shared=True, size=numel, dtype=torch.uint8)
+    rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), numel, 0)
+    if int(rc) != 0:
+        raise _lib.VitocmError(f"cudaHostRegister failed with {rc}")
+    return t.view(*shape)
 
 
 class MosaicSegmenter:
@@ -216,57 +270,97 @@ class MosaicSegmenter:
             raise ValueError("window must be a multiple of the patch size")
 
     @torch.no_grad()
-    def lowres_maps(self, mosaic: torch.Tensor, t0: int, t1: int) -> torch.Tensor:
-        """Per-tile normalised low-res maps [t1-t0, h, w] for tiles t0..t1-1 of the n x n grid."""
+    def lowres_maps(self, mosaic, t0: int, t1: int) -> torch.Tensor:
+        """Per-tile normalised low-res maps [t1-t0, h, w] for tiles t0..t1-1 of the n x n grid.  mosaic: uint8 CUDA tensor, or a
+        tuple (device address of row 0, height, width, pitch, device) for a band buffer addressed by absolute rows."""
         lib = _lib.load_library()
         W, S = self.window, self.stride
         C = 1          # the mosaic is gray: one channel per tile and the channel-folded patch filter (gray fast path)
-        n = grid_size(mosaic.shape[0], S)
+        if isinstance(mosaic, tuple):
+            mos_ptr, mos_h, mos_w, pitch, dev = mosaic
+        else:
+            mos_ptr, mos_h, mos_w, pitch, dev = mosaic.data_ptr(), mosaic.shape[0], mosaic.shape[1], mosaic.stride(0), mosaic.device
+        n = grid_size(mos_h, S)
         lh = W // self.patch
-        out = torch.empty(max(t1 - t0, 0), lh * lh, dtype=torch.float32, device=mosaic.device)
+        out = torch.empty(max(t1 - t0, 0), lh * lh, dtype=torch.float32, device=dev)
         direct = self.ingest == "direct" and self.model.in_chans > 1
-        xbuf = None if direct else torch.empty(self.tile_batch, C, W, W, dtype=torch.float32, device=mosaic.device)
+        xbuf = None if direct else torch.empty(self.tile_batch, C, W, W, dtype=torch.float32, device=dev)
         for a in range(t0, t1, self.tile_batch):
             b = min(a + self.tile_batch, t1)
             if direct:   # the patch-embedding producer reads the uint8 mosaic itself: no crop is materialised
-                rows = self.model.cls_attention_rows_mosaic(mosaic, n, W, S, a, b - a)
+                rows = self.model.cls_attention_rows_mosaic((mos_ptr, mos_h, mos_w, pitch, dev), n, W, S, a, b - a)
             else:
                 x = xbuf[: b - a]
-                check(lib.vitocm_extract_tiles(ptr(mosaic), mosaic.shape[0], mosaic.shape[1], mosaic.stride(0), n, W, S, a,
-                                               b - a, C, ptr(x), cur_stream()))
+                check(lib.vitocm_extract_tiles(mos_ptr, mos_h, mos_w, pitch, n, W, S, a, b - a, C, ptr(x), cur_stream()))
                 rows = self.model.cls_attention_rows(x)
             out[a - t0:b - t0] = head_mean_maps(rows, per_tile_minmax255=True)
         return out.view(-1, lh, lh)
 
+    def mosaic_rows_needed(self, size: int) -> tuple[int, int]:
+        """Rows [r0, r1) of a size x size mosaic that this rank reads: the windows of its tile shard and its band of output rows."""
+        W, S = self.window, self.stride
+        n = grid_size(size, S)
+        T = n * n
+        E = (n - 1) * S + W
+        t0, t1 = shard_range(T, self.rank, self.world)
+        y0, y1 = shard_range(E, self.rank, self.world)
+        r0, r1 = y0, y1
+        if t1 > t0:
+            r0 = min(r0, (t0 // n) * S)
+            r1 = max(r1, ((t1 - 1) // n) * S + W)
+        return max(r0, 0), min(r1, size)
+
     @torch.no_grad()
-    def segment(self, mosaic: torch.Tensor, want=("th", "th3"), gather: bool = True):
-        """mosaic: uint8 gray [E0, E0] CUDA tensor.  Returns dict with the masks of this rank's row
-        band (and, on rank 0 with gather=True, the full [E, E] masks), thresholds, min/max, lowres."""
-        if mosaic.dtype != torch.uint8 or mosaic.dim() != 2 or not mosaic.is_cuda or mosaic.shape[0] != mosaic.shape[1]:
-            raise ValueError("mosaic must be a square uint8 gray CUDA tensor")
+    def segment(self, mosaic: torch.Tensor, want=("th", "th3"), gather: bool = True, host_out: dict | None = None):
+        """mosaic: uint8 gray [E0, E0], a CUDA tensor or a HOST tensor (pinned for an asynchronous copy).  A host mosaic is
+        uploaded band-wise: every rank copies only the rows its own windows and output rows touch (mosaic_rows_needed), so R
+        ranks move ~1/R of the image each over their own PCIe link instead of R whole copies.  host_out: optional dict
+        name -> uint8 HOST tensor [E, E] (pinned; for several ranks a shared mapping, see shared_pinned_u8): every rank copies its
+        band of each mask straight into rows [y0, y1) of it -- the final "gather" then happens in host memory, in parallel, and
+        the NCCL gather to rank 0 is skipped unless gather=True.
+        Returns dict with the masks of this rank's row band (and, on rank 0 with gather=True, the full [E, E] masks), thresholds,
+        min/max, lowres."""
+        if mosaic.dtype != torch.uint8 or mosaic.dim() != 2 or mosaic.shape[0] != mosaic.shape[1]:
+            raise ValueError("mosaic must be a square uint8 gray tensor")
         lib = _lib.load_library()
         W, S = self.window, self.stride
-        n = grid_size(mosaic.shape[0], S)
+        size = mosaic.shape[0]
+        n = grid_size(size, S)
         if n < 1:
             raise ValueError("mosaic smaller than one window")
         T = n * n
         lh = W // self.patch
         E = (n - 1) * S + W
-        dev = mosaic.device
+        dev = _dev() if not mosaic.is_cuda else mosaic.device
+        if mosaic.is_cuda:
+            mos_ptr, pitch = mosaic.data_ptr(), mosaic.stride(0)
+            mos_keep = mosaic
+        else:
+            if mosaic.stride(1) != 1:
+                raise ValueError("host mosaic must have unit column stride")
+            r0, r1 = self.mosaic_rows_needed(size)
+            mos_keep = _cached("mosaic_band", (max(r1 - r0, 1), size), torch.uint8, dev)
+            mos_keep[: r1 - r0].copy_(mosaic[r0:r1], non_blocking=True)
+            pitch = size
+            mos_ptr = mos_keep.data_ptr() - r0 * pitch      # absolute-row addressing: rows outside [r0, r1) are never read
         wtab = _wtab(W, S, dev)
         # 1. ViT on this rank's tiles
         t0, t1 = shard_range(T, self.rank, self.world)
-        mine = self.lowres_maps(mosaic, t0, t1)
+        mine = self.lowres_maps((mos_ptr, size, size, pitch, dev), t0, t1)
         lowres = allgather_shards(mine, T, self.rank, self.world, self.group)
         # 2. this rank's band of output rows
         y0, y1 = shard_range(E, self.rank, self.world)
-        gray = torch.empty(E, E, dtype=torch.uint8, device=dev)
-        check(lib.vitocm_stitch_gray(ptr(mosaic), mosaic.shape[0], mosaic.shape[1], mosaic.stride(0), n, W, S, ptr(wtab),
-                                     y0, y1, ptr(gray), cur_stream()))
-        masks, thr, minmax, hists = _threshold_device(lib, lowres, (n, W, S, lh, lh), wtab, gray, None, y0, y1,
-                                                      group=self.group if self.world > 1 else None, want=want)
+        gray_band = torch.empty(max(y1 - y0, 1), E, dtype=torch.uint8, device=dev)     # this rank's rows only
+        gray_base = gray_band.data_ptr() - y0 * E                                       # absolute-row addressing (see _threshold_device)
+        check(lib.vitocm_stitch_gray(mos_ptr, size, size, pitch, n, W, S, ptr(wtab), y0, y1, gray_base, cur_stream()))
+        masks, thr, minmax, hists = _threshold_device(lib, lowres, (n, W, S, lh, lh), wtab, None, None, y0, y1,
+                                                      group=self.group if self.world > 1 else None, want=want, gray_base=gray_base)
         out = dict(band=(y0, y1), thresholds=thr, minmax_ord=minmax, hists=hists, lowres=lowres, extent=E, grid=n)
         out.update({k + "_band": v for k, v in masks.items()})
+        if host_out is not None:
+            for k, v in masks.items():
+                if k in host_out and y1 > y0:
+                    host_out[k][y0:y1].copy_(v, non_blocking=True)
         # 3. final mask gather on rank 0
         if self.world > 1 and gather:
             for k, v in masks.items():

@@ -33,6 +33,26 @@ def head_mean_maps(cls_rows: torch.Tensor, per_tile_minmax255: bool = False) -> 
     return out
 
 
+def cummass_threshold(cls_rows: torch.Tensor, threshold: float, w_featmap: int | None = None, h_featmap: int | None = None,
+                      patch_size: int | None = None):
+    """The `--threshold` mode (flag at SSS/eval.py:33-34; semantics of upstream DINO's visualize_attention.py: "we keep only a
+    certain percentage of the mass"): per tile and head, the patches are sorted by CLS attention, normalised to unit mass, and
+    those whose ascending cumulative mass exceeds 1 - threshold are kept.  cls_rows [T, heads, N] (e.g. model.cls_attention_rows(x))
+    -> mask [T, heads, N - 1] uint8 in {0, 1}; with (w_featmap, h_featmap, patch_size) also the nearest-upsampled float masks
+    [T, heads, w*p, h*p] that visualize_attention.py displays.  Everything on the device (one block per (tile, head): bitonic
+    sort + shuffle scan).  Not under /root/reference: parity unpinned by the reference (oracle/post_oracle.py cummass_threshold)."""
+    cls_rows = cls_rows.contiguous()
+    T, H, N = cls_rows.shape
+    mask = torch.empty(T, H, N - 1, dtype=torch.uint8, device=cls_rows.device)
+    up = None
+    lh = lw = p = 0
+    if patch_size is not None:
+        lh, lw, p = int(w_featmap), int(h_featmap), int(patch_size)
+        up = torch.empty(T, H, lh * p, lw * p, dtype=torch.float32, device=cls_rows.device)
+    check(_lib.load_library().vitocm_attn_cummass(ptr(cls_rows), T, H, N, float(threshold), ptr(mask), ptr(up), lh, lw, p, cur_stream()))
+    return (mask, up) if up is not None else mask
+
+
 def compute_attention(attentions, query, w_featmap, h_featmap, patch_size):
     """SSS/utils.py:229-235: attention of `query` for batch element 0, per head, nearest-upsampled
     by the patch size, as a host numpy array [nh, w*p, h*p]; returns (array, nh)."""

@@ -377,8 +377,12 @@ class VisionTransformer(nn.Module):
         """cls_attention_rows of the windows t0 .. t0+count-1 (row-major in the grid x grid sliding-window grid,
         SSS/sw_processing.py:151-163) of a gray uint8 CUDA mosaic, cut out by the patch-embedding producer itself: no crop
         is ever materialised.  -> [count, heads, N] fp32."""
-        if mosaic.dtype != torch.uint8 or mosaic.dim() != 2 or not mosaic.is_cuda or mosaic.stride(1) != 1:
-            raise ValueError("mosaic must be a 2-D uint8 CUDA tensor with unit column stride")
+        if isinstance(mosaic, tuple):      # (device address of row 0, height, width, pitch, device): a band buffer addressed by absolute rows
+            mos_ptr, mos_h, mos_w, pitch, dev = mosaic
+        else:
+            if mosaic.dtype != torch.uint8 or mosaic.dim() != 2 or not mosaic.is_cuda or mosaic.stride(1) != 1:
+                raise ValueError("mosaic must be a 2-D uint8 CUDA tensor with unit column stride")
+            mos_ptr, mos_h, mos_w, pitch, dev = mosaic.data_ptr(), mosaic.shape[0], mosaic.shape[1], mosaic.stride(0), mosaic.device
         if self.in_chans < 2:
             raise NotImplementedError("mosaic ingest runs the channel-folded (gray) patch filter of a multi-channel model")
         p = self.patch_embed.patch_size
@@ -388,9 +392,9 @@ class VisionTransformer(nn.Module):
         N = (window // p) ** 2 + 1
         pos = self._pos_table(N - 1, window, window)
         chunk = max(1, min(self.chunk_tiles, count))
-        ws = self._workspace(chunk, N, mosaic.device)
-        out = torch.empty(count, self.num_heads, N, dtype=torch.float32, device=mosaic.device)
-        check(_lib.load_library().vitocm_forward_cls_attn_mosaic(eng, mosaic.data_ptr(), mosaic.shape[0], mosaic.shape[1], mosaic.stride(0), grid,
+        ws = self._workspace(chunk, N, dev)
+        out = torch.empty(count, self.num_heads, N, dtype=torch.float32, device=dev)
+        check(_lib.load_library().vitocm_forward_cls_attn_mosaic(eng, mos_ptr, mos_h, mos_w, pitch, grid,
                                                                  window, stride, t0, count, ptr(pos), ptr(out), ptr(ws), ws.numel(), chunk,
                                                                  cur_stream()))
         return out
