@@ -250,6 +250,15 @@ int vitocm_gemm(vitocm_engine* e, const void* A, int64_t lda, const void* B, int
  * bf16 engines only; N / 128 must be 1, 2, 3, 4 or 6 (one thread-block cluster spans a row). */
 int vitocm_gemm_ln(vitocm_engine* e, const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, const float* bias,
                    float* X, const float* gamma, const float* beta, void* XN, int64_t ld_xn, void* stream);
+/* X[M][D] += gelu(XN . W1^T + bias1) . W2^T + bias2 in ONE kernel (Mlp.forward + the residual add, SSS/dino/vision_transformer.py:57-63,
+ * :111): XN 16-bit [M][ld_xn], W1 [hidden][ldw1], W2 [D][ldw2] (K-major, the engine's 16-bit format), X fp32 [M][D].  The hidden
+ * activations stay in shared / tensor memory.  D = 128 or 384, hidden a multiple of 128, engines with single 16-bit operands. */
+int vitocm_mlp_fused(vitocm_engine* e, const void* XN, int64_t ld_xn, const void* W1, int64_t ldw1, const void* W2, int64_t ldw2, int M,
+                     int D, int hidden, const float* bias1, const float* bias2, float* X, void* stream);
+/* Diagnostics: vitocm_mlp_fused that also records SM-clock stamps of the leader CTA of pair 0 on its second work item
+ * (VITOCM_MLP_TL_ITEM): stamps int64 [2 role: epilogue warp 0, MMA thread][16 chunks][8 events]. */
+int vitocm_mlp_fused_timeline(vitocm_engine* e, const void* XN, int64_t ld_xn, const void* W1, int64_t ldw1, const void* W2, int64_t ldw2,
+                              int M, int D, int hidden, const float* bias1, const float* bias2, float* X, int64_t* stamps, void* stream);
 /* ctx = MHSA(qkv) for B images of n_tokens tokens: qkv bf16 [B*N][ld], ctx bf16 [B*N][ldo]. */
 int vitocm_attention(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo,
                      void* stream);

@@ -221,3 +221,62 @@ def test_launch_counter_counts():
     out = torch.empty(128, 64, device="cuda", dtype=torch.bfloat16)
     gemm(eng, A, A[:64].contiguous(), 128, 64, 64, 0, 0, None, out, 64)
     assert vob._lib.launch_count() == before + 1
+
+
+def _mlp_reference(A, W1, b1, W2, b2, resid, dt):
+    """fp32 statement of Mlp.forward + residual with the hidden activations rounded to the engine's 16-bit format (the fused
+    kernel keeps them in shared memory in that format)."""
+    hid = torch.nn.functional.gelu(A.float() @ W1.float().T + b1).to(dt).float()
+    return resid + hid @ W2.float().T + b2
+
+
+@pytest.mark.parametrize("M,D,Hd", [(785, 384, 1536), (256, 384, 1536), (130, 128, 512), (1, 128, 128), (5000, 384, 1536), (40000, 384, 1536),
+                                    (257, 128, 256)])
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_mlp_fused(M, D, Hd, precision):
+    """fc1 + GELU + fc2 + residual in one kernel (CTA pairs, hidden chunks through TMEM and shared memory): ragged row tiles, one
+    and many items per pair, both instantiated widths."""
+    lib = vob._lib.load_library()
+    eng = make_engine(precision=2 if precision == "fp16" else 0)
+    dt = torch.float16 if precision == "fp16" else torch.bfloat16
+    # strided rows like the workspace's XN [M][2D]; the unused half is NaN
+    A2 = torch.cat([_rand((M, D), 60).to(dt), torch.full((M, D), float("nan"), device="cuda", dtype=dt)], dim=1).contiguous()
+    A = A2[:, :D]
+    W1 = _rand((Hd, D), 61, 0.06).to(dt)
+    W2 = _rand((D, Hd), 62, 0.03).to(dt)
+    b1, b2 = _rand((Hd,), 63, 0.2), _rand((D,), 64, 0.1)
+    resid = _rand((M, D), 65)
+    x = resid.clone()
+    check(lib.vitocm_mlp_fused(eng, ptr(A2), A2.stride(0), ptr(W1), W1.stride(0), ptr(W2), W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(x),
+                               cur_stream()))
+    torch.cuda.synchronize()
+    ref = _mlp_reference(A, W1, b1, W2, b2, resid, dt)
+    tol = 3e-3 if precision == "fp16" else 1.5e-2     # the GELU approximation and the fp32 summation order differ from torch's
+    err = (x - ref).abs().max().item()
+    assert err <= tol * (ref - resid).abs().max().item() + 1e-4, err
+    # twice on the same residual stream = two blocks' worth of accumulation (reduce-add, not overwrite)
+    check(lib.vitocm_mlp_fused(eng, ptr(A2), A2.stride(0), ptr(W1), W1.stride(0), ptr(W2), W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(x),
+                               cur_stream()))
+    torch.cuda.synchronize()
+    ref2 = ref + (ref - resid)
+    assert (x - ref2).abs().max().item() <= 2 * tol * (ref - resid).abs().max().item() + 2e-4
+
+
+def test_mlp_fused_matches_separate_gemms(engine):
+    """The fused kernel against the two-GEMM path it replaces (same operands, same GELU form): only the summation order differs."""
+    lib = vob._lib.load_library()
+    M, D, Hd = 3000, 384, 1536
+    A = _rand((M, D), 70).to(torch.bfloat16)
+    W1 = _rand((Hd, D), 71, 0.06).to(torch.bfloat16)
+    W2 = _rand((D, Hd), 72, 0.03).to(torch.bfloat16)
+    b1, b2 = _rand((Hd,), 73, 0.2), _rand((D,), 74, 0.1)
+    resid = _rand((M, D), 75)
+    x = resid.clone()
+    check(lib.vitocm_mlp_fused(engine, ptr(A), A.stride(0), ptr(W1), W1.stride(0), ptr(W2), W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(x),
+                               cur_stream()))
+    hid = torch.empty(M, Hd, device="cuda", dtype=torch.bfloat16)
+    gemm(engine, A, W1, M, Hd, D, 0, 1, b1, hid, Hd)
+    y = resid.clone()
+    gemm(engine, hid, W2, M, D, Hd, 0, 2, b2, y, D)
+    torch.cuda.synchronize()
+    assert (x - y).abs().max().item() <= 2e-4 * (y - resid).abs().max().item() + 1e-5

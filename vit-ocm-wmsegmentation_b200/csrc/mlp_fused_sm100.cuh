@@ -1,0 +1,397 @@
+// Fused transformer MLP for sm_100a (embed dim D <= 384, inference engines with single 16-bit operands):
+//     X[M, D] += gelu(XN[M, D] . W1[Hd, D]^T + b1) . W2[D, Hd]^T + b2
+// Replaces Mlp.forward (SSS/dino/vision_transformer.py:57-63: fc1 -> GELU -> fc2, dropout p = 0) together with the residual
+// add of Block.forward (:111).  The hidden activations [M, Hd] never leave the SM: the separate fc1 / fc2 GEMMs wrote and
+// re-read them through HBM (6 KB per token row and block at ViT-S -- a quarter of the whole forward's HBM traffic), and
+// the fc1 kernel was bound by its GELU epilogue, not by the tensor core.  Here the GELU of hidden chunk c runs on the
+// epilogue warps while the tensor core works on fc1 of chunk c + 1 and fc2 of chunk c - 1.
+//
+// One work item = a 256-row tile owned by a CTA pair (cta_group::2: each CTA holds its own 128 rows of every A operand
+// and half of every B operand, so weights cross the L2 -> SM link once per 256 rows).  Per CTA:
+//   A     = XN tile [128 x D] bf16, resident for the whole item (KB1 = D / 64 SWIZZLE_128B k-blocks, TMA)
+//   for each chunk c of 128 hidden columns:
+//     fc1:  Hacc[128 x 128] (TMEM)  = A . W1[c]^T                         KB1 x 4 MMAs  (M 256, N 128, K 16)
+//     GELU: Hacc -> registers -> + b1 -> gelu -> 16-bit -> smem H[128 x 128] (two SWIZZLE_128B k-blocks: fc2's A operand)
+//     fc2:  OUT[128 x D] (TMEM)   += H . W2[:, c]^T                       2 x D/128 x 4 MMAs
+//   OUT + b2 -> TMA reduce-add into the fp32 residual stream (performed by the L2)
+// Weights stream through a ring of 8 KB slots ([64 rows x 64 k] per CTA = its half of a [128 x 64] B tile), in the order the
+// MMA thread consumes them: fc1(0), fc1(1), fc2(0), fc1(2), fc2(1), ...  TMEM: OUT in columns [0, D), Hacc in [384, 512).
+// Warp roles: 0 = weight TMA, 1 = MMA issuer (leader CTA), 2 = TMEM allocator, 3 = A-tile TMA, 4.. = EW epilogue warps
+// (lane quadrant = warp % 4, column group = (warp - 4) / 4).
+#pragma once
+#include "gemm_sm100.cuh"
+
+namespace vitocm {
+
+struct MlpArgs {
+  int M;               // token rows
+  int hidden;          // Hd (multiple of 128)
+  int f16;             // 16-bit operand format: 0 = bf16, 1 = IEEE fp16
+  int gelu_mode;       // 0 = three-coefficient sigmoid form (bf16 engines), 2 = five-coefficient sigmoid form (fp16 engines)
+  const float* bias1;  // [Hd]
+  const float* bias2;  // [D]
+  // diagnostics (vitocm_mlp_fused_timeline) or nullptr: clock64 stamps of the leader CTA of pair 0, work item `timeline_item`,
+  // [role: 0 = epilogue warp 0, 1 = MMA thread][chunk < MLP_TL_CHUNKS][event < MLP_TL_EVENTS]
+  long long* timeline;
+  int timeline_item;
+};
+constexpr int MLP_TL_CHUNKS = 16;
+constexpr int MLP_TL_EVENTS = 8;
+__device__ __forceinline__ void mlp_stamp(const MlpArgs& args, bool on, int role, int c, int ev) {
+  if (on && c < MLP_TL_CHUNKS) args.timeline[(role * MLP_TL_CHUNKS + c) * MLP_TL_EVENTS + ev] = clock64();
+}
+
+constexpr int MLP_HC = 128;                 // hidden columns per chunk
+constexpr int MLP_SLOT_BYTES = 64 * 64 * 2; // one CTA's half of a [128 x 64] weight tile
+constexpr int MLP_KB_BYTES = 128 * 64 * 2;  // one [128 x 64] k-block of an A operand
+constexpr int MLP_H_COL = 384;              // TMEM column of the hidden-chunk accumulator
+constexpr int MLP_MAX_SLOTS = 8;
+
+template <int KB1, int EW>
+struct MlpCfg {
+  static constexpr int D = KB1 * 64;
+  static constexpr int NP2 = D / 128;                   // 128-column output parts (one fc2 MMA group each)
+  static_assert(D % 128 == 0 && D <= 384, "fused MLP: D must be 128, 256 or 384");
+  static_assert(EW == 8 || EW == 16, "fused MLP: 8 or 16 epilogue warps");
+  static constexpr int THREADS = (4 + EW) * 32;
+  static constexpr int A_BYTES = KB1 * MLP_KB_BYTES;
+  static constexpr int H_BYTES = 2 * MLP_KB_BYTES;      // also 8 output staging boxes (32 x 32 fp32) between items
+  static constexpr int STG_BYTES = 8 * 4096;            // 8 dedicated output staging boxes
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int FIXED = A_BYTES + H_BYTES + STG_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
+  static constexpr int SLOTS_FIT = (GEMM_SMEM_LIMIT - FIXED) / MLP_SLOT_BYTES;
+  static constexpr int SLOTS = SLOTS_FIT > MLP_MAX_SLOTS ? MLP_MAX_SLOTS : SLOTS_FIT;
+  static_assert(SLOTS >= 4, "fused MLP: weight ring too shallow");
+  static constexpr int SMEM_BYTES = FIXED + SLOTS * MLP_SLOT_BYTES;
+  // setmaxnreg budgets, EW = 16 only (640 threads x 96 registers at launch): 128 x 48 + 512 x 104 <= 640 x 96
+  static constexpr int REGS_CTRL = 48;
+  static constexpr int REGS_EPI = 104;
+};
+
+template <int KB1, int EW>
+__global__ void __launch_bounds__(MlpCfg<KB1, EW>::THREADS, 1)
+mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
+                         const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_x, const MlpArgs args) {
+  using Cfg = MlpCfg<KB1, EW>;
+  constexpr int D = Cfg::D, NP2 = Cfg::NP2, SLOTS = Cfg::SLOTS;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_h = smem_a + Cfg::A_BYTES;
+  const uint32_t smem_w = smem_h + Cfg::H_BYTES;
+  const uint32_t smem_stg = smem_w + SLOTS * MLP_SLOT_BYTES;
+  const uint32_t bars = smem_stg + Cfg::STG_BYTES;
+  const uint32_t w_full = bars;                       // [SLOTS] TMA -> MMA (leader's copy counts both CTAs' bytes)
+  const uint32_t w_empty = bars + 8 * MLP_MAX_SLOTS;  // [SLOTS] MMA -> TMA (both CTAs)
+  const uint32_t a_full = bars + 16 * MLP_MAX_SLOTS;  // A tile landed (leader's copy)
+  const uint32_t a_empty = a_full + 8;                // last fc1 of the item retired (both CTAs)
+  const uint32_t h_full = a_full + 16;                // fc1 chunk complete in TMEM (both CTAs)
+  const uint32_t h_tmem_empty = a_full + 24;          // epilogue warps of both CTAs read the chunk out of TMEM (leader's copy)
+  const uint32_t h_smem_full = a_full + 32;           // epilogue warps of both CTAs wrote gelu(chunk) to smem (leader's copy)
+  const uint32_t h_smem_empty = a_full + 40;          // fc2 of the chunk retired (both CTAs)
+  const uint32_t out_full = a_full + 48;              // last fc2 of the item retired (both CTAs)
+  const uint32_t out_empty = a_full + 56;             // epilogue warps of both CTAs read OUT out of TMEM (leader's copy)
+  const uint32_t tmem_ptr_smem = a_full + 64;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(ptx::cluster_ctarank());
+  const int pair = static_cast<int>(blockIdx.x) >> 1;
+  const int npairs = static_cast<int>(gridDim.x) >> 1;
+  const int tiles_m = (args.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int NC = args.hidden / MLP_HC;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_w1);
+    ptx::prefetch_tmap(&tmap_w2);
+    ptx::prefetch_tmap(&tmap_x);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < SLOTS; ++s) {
+      ptx::mbar_init(w_full + 8 * s, 1);
+      ptx::mbar_init(w_empty + 8 * s, 1);
+    }
+    ptx::mbar_init(a_full, 1);
+    ptx::mbar_init(a_empty, 1);
+    ptx::mbar_init(h_full, 1);
+    ptx::mbar_init(h_tmem_empty, 2 * EW);
+    ptx::mbar_init(h_smem_full, 2 * EW);
+    ptx::mbar_init(h_smem_empty, 1);
+    ptx::mbar_init(out_full, 1);
+    ptx::mbar_init(out_empty, 2 * EW);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_2cta(tmem_ptr_smem, 512);
+    ptx::tmem_relinquish_2cta();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them remotely
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ptx::lds_u32(tmem_ptr_smem);
+
+  if (warp < 4) {
+    if (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_CTRL));
+    if (warp == 0) {
+      // ===================== weight TMA producer (both CTAs: each stages its half of every B tile) =====================
+      if (lane == 0) {
+        int slot = 0;
+        uint32_t phase = 0;
+        auto put = [&](const CUtensorMap* tm, int c0, int c1) {
+          ptx::mbar_wait(w_empty + 8 * slot, phase ^ 1, 31);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(w_full + 8 * slot, 2 * MLP_SLOT_BYTES);
+          ptx::tma_load_2d_2cta(smem_w + slot * MLP_SLOT_BYTES, tm, w_full + 8 * slot, c0, c1);
+          if (++slot == SLOTS) { slot = 0; phase ^= 1; }
+        };
+        auto load_fc1 = [&](int c) {
+          for (int kb = 0; kb < KB1; ++kb) put(&tmap_w1, kb * GEMM_BK, c * MLP_HC + rank * 64);
+        };
+        auto load_fc2 = [&](int c) {
+          for (int kb2 = 0; kb2 < 2; ++kb2)
+            for (int np = 0; np < NP2; ++np) put(&tmap_w2, c * MLP_HC + kb2 * GEMM_BK, np * 128 + rank * 64);
+        };
+        for (int tile = pair; tile < tiles_m; tile += npairs) {
+          load_fc1(0);
+          for (int c = 0; c < NC; ++c) {
+            if (c + 1 < NC) load_fc1(c + 1);
+            load_fc2(c);
+          }
+        }
+      }
+    } else if (warp == 3) {
+      // ===================== A-tile TMA producer =====================
+      if (lane == 0) {
+        int t = 0;
+        for (int tile = pair; tile < tiles_m; tile += npairs, ++t) {
+          ptx::mbar_wait(a_empty, (t & 1) ^ 1, 32);   // the previous item's fc1 MMAs no longer read the tile
+          if (rank == 0) ptx::mbar_arrive_expect_tx(a_full, 2 * Cfg::A_BYTES);
+          for (int kb = 0; kb < KB1; ++kb)
+            ptx::tma_load_2d_2cta(smem_a + kb * MLP_KB_BYTES, &tmap_a, a_full, kb * GEMM_BK, tile * 2 * GEMM_BM + rank * GEMM_BM);
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer (leader CTA) =====================
+      if (rank == 0 && ptx::elect_one()) {
+        const uint32_t idesc = ptx::make_idesc(2 * GEMM_BM, 128, false, false, args.f16 ? 0u : 1u);
+        const uint64_t a_desc0 = ptx::make_smem_desc_sw128(smem_a, 1024, 0);
+        const uint64_t h_desc0 = ptx::make_smem_desc_sw128(smem_h, 1024, 0);
+        const uint64_t w_desc0 = ptx::make_smem_desc_sw128(smem_w, 1024, 0);
+        const uint32_t h_tmem = tmem_base + MLP_H_COL;
+        int slot = 0;
+        uint32_t phase = 0;
+        int g1 = 0, g2 = 0;   // fc1 / fc2 chunks issued so far (all items): phase counters
+        int t = 0;
+        bool tl = false;
+        auto issue_fc1 = [&](int c) {
+          if (g1 > 0) {   // the previous chunk has been read out of the TMEM accumulator
+            ptx::mbar_wait(h_tmem_empty, (g1 - 1) & 1, 33);
+            ptx::tc_fence_after();
+          }
+          mlp_stamp(args, tl, 1, c, 0);   // accumulator free: fc1(c) may be issued
+#pragma unroll 1
+          for (int kb = 0; kb < KB1; ++kb) {
+            ptx::mbar_wait(w_full + 8 * slot, phase, 34);
+            ptx::tc_fence_after();
+            const uint64_t adesc = ptx::desc_advance(a_desc0, kb * MLP_KB_BYTES);
+            const uint64_t bdesc = ptx::desc_advance(w_desc0, slot * MLP_SLOT_BYTES);
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              ptx::umma_bf16_ss_2cta(h_tmem, ptx::desc_advance(adesc, k * 32), ptx::desc_advance(bdesc, k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            ptx::umma_commit_2cta(w_empty + 8 * slot);
+            if (++slot == SLOTS) { slot = 0; phase ^= 1; }
+          }
+          ptx::umma_commit_2cta(h_full);
+          mlp_stamp(args, tl, 1, c, 1);   // fc1(c) issued
+          ++g1;
+        };
+        auto issue_fc2 = [&](int c) {
+          mlp_stamp(args, tl, 1, c, 2);   // waiting for gelu(chunk c)
+          ptx::mbar_wait_cluster(h_smem_full, g2 & 1, 35);   // gelu(chunk) sits in both CTAs' shared memory
+          ptx::tc_fence_after();
+          mlp_stamp(args, tl, 1, c, 3);   // gelu(chunk c) ready
+          if (c == 0 && t > 0) {   // OUT still holds the previous item until both CTAs' epilogue warps have read it
+            ptx::mbar_wait(out_empty, (t - 1) & 1, 36);
+            ptx::tc_fence_after();
+          }
+#pragma unroll 1
+          for (int kb2 = 0; kb2 < 2; ++kb2) {
+            const uint64_t adesc = ptx::desc_advance(h_desc0, kb2 * MLP_KB_BYTES);
+#pragma unroll 1
+            for (int np = 0; np < NP2; ++np) {
+              ptx::mbar_wait(w_full + 8 * slot, phase, 37);
+              ptx::tc_fence_after();
+              const uint64_t bdesc = ptx::desc_advance(w_desc0, slot * MLP_SLOT_BYTES);
+#pragma unroll
+              for (int k = 0; k < GEMM_BK / 16; ++k)
+                ptx::umma_bf16_ss_2cta(tmem_base + np * 128, ptx::desc_advance(adesc, k * 32), ptx::desc_advance(bdesc, k * 32), idesc,
+                                       (c > 0 || kb2 > 0 || k > 0) ? 1u : 0u);
+              ptx::umma_commit_2cta(w_empty + 8 * slot);
+              if (++slot == SLOTS) { slot = 0; phase ^= 1; }
+            }
+          }
+          ptx::umma_commit_2cta(h_smem_empty);
+          mlp_stamp(args, tl, 1, c, 4);   // fc2(c) issued
+          ++g2;
+        };
+        for (int tile = pair; tile < tiles_m; tile += npairs, ++t) {
+          tl = args.timeline != nullptr && blockIdx.x == 0 && t == args.timeline_item;
+          ptx::mbar_wait(a_full, t & 1, 38);
+          ptx::tc_fence_after();
+          issue_fc1(0);
+          if (NC == 1) ptx::umma_commit_2cta(a_empty);
+          for (int c = 0; c < NC; ++c) {
+            if (c + 1 < NC) {
+              issue_fc1(c + 1);
+              if (c + 2 == NC) ptx::umma_commit_2cta(a_empty);   // last fc1 of the item: the A tile may be replaced once it retires
+            }
+            issue_fc2(c);
+          }
+          ptx::umma_commit_2cta(out_full);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    if (EW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_EPI));
+    const int ew = warp - 4;
+    const int q = warp & 3;          // TMEM lane quadrant
+    const int cg = ew >> 2;          // column group
+    constexpr int CPW = MLP_HC / (EW / 4);   // hidden columns per warp and chunk (32 or 64)
+    constexpr int NSUB = CPW / 32;
+    constexpr int OCW = D / (EW / 4);        // output columns per warp
+    constexpr int NOS = OCW / 32;
+    static_assert(OCW % 32 == 0, "fused MLP: output columns per epilogue warp must be a multiple of 32");
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int row = q * 32 + lane;   // row of the CTA's 128
+    // output staging boxes: warp ew < 8 owns a dedicated box, warp ew >= 8 a box inside the H buffer (idle between items);
+    // with 8 warps each warp alternates between its two
+    const uint32_t box0 = ew < 8 ? smem_stg + ew * 4096 : smem_h + (ew - 8) * 4096;
+    const uint32_t box1 = EW == 8 ? smem_h + ew * 4096 : box0;
+    int ge = 0;   // chunks processed (all items)
+    int t = 0;
+    for (int tile = pair; tile < tiles_m; tile += npairs, ++t) {
+      const bool tl = args.timeline != nullptr && blockIdx.x == 0 && t == args.timeline_item && ew == 0 && lane == 0;
+      for (int c = 0; c < NC; ++c, ++ge) {
+        mlp_stamp(args, tl, 0, c, 0);   // waiting for fc1(c)
+        ptx::mbar_wait(h_full, ge & 1, 40);
+        ptx::tc_fence_after();
+        mlp_stamp(args, tl, 0, c, 1);   // fc1(c) complete
+        uint32_t r[NSUB][32];
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s) ptx::tmem_ld_32x32b_x32(lane_taddr + MLP_H_COL + cg * CPW + s * 32, r[s]);
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s) ptx::tmem_ld_wait(r[s]);
+        // the chunk is in registers: the accumulator goes back to the MMA thread (fc1 of the next chunk)
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_leader(h_tmem_empty);
+        mlp_stamp(args, tl, 0, c, 2);   // chunk in registers
+        uint32_t pk[NSUB][16];
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s) {
+          const float* bp = args.bias1 + c * MLP_HC + cg * CPW + s * 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + j);   // same address in every lane
+            v[4 * j] = __uint_as_float(r[s][4 * j]) + b4.x;
+            v[4 * j + 1] = __uint_as_float(r[s][4 * j + 1]) + b4.y;
+            v[4 * j + 2] = __uint_as_float(r[s][4 * j + 2]) + b4.z;
+            v[4 * j + 3] = __uint_as_float(r[s][4 * j + 3]) + b4.w;
+          }
+          if (args.gelu_mode == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) gelu_sigmoid_x2(v[j], v[j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) gelu_sigmoid5_x2(v[j], v[j + 1]);
+          }
+          if (args.f16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[s][j] = ptx::pack_f16x2(v[2 * j], v[2 * j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[s][j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          }
+        }
+        // the H buffer is free once fc2 of the previous chunk has retired
+        mlp_stamp(args, tl, 0, c, 3);   // gelu done
+        if (ge > 0) ptx::mbar_wait(h_smem_empty, (ge - 1) & 1, 41);
+        mlp_stamp(args, tl, 0, c, 4);   // fc2(c - 1) retired: H buffer free
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s) {
+          const int hc = cg * CPW + s * 32;            // first hidden column of this sub-chunk inside the chunk
+          const uint32_t tile_addr = smem_h + (hc >> 6) * MLP_KB_BYTES + row * 128;
+          const int j0 = (hc & 63) >> 3;               // first 16-byte chunk of the row
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            ptx::sts_v4(tile_addr + (((j0 + j) ^ (row & 7)) << 4), pk[s][4 * j], pk[s][4 * j + 1], pk[s][4 * j + 2], pk[s][4 * j + 3]);
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_remote(ptx::mapa(h_smem_full, 0));
+        mlp_stamp(args, tl, 0, c, 5);   // gelu(chunk) handed to the MMA thread
+      }
+      // ---- item epilogue: OUT + b2 -> fp32 boxes -> TMA reduce-add into the residual stream
+      mlp_stamp(args, tl, 0, MLP_TL_CHUNKS - 1, 0);   // waiting for the item's last fc2
+      ptx::mbar_wait(out_full, t & 1, 42);
+      ptx::tc_fence_after();
+      mlp_stamp(args, tl, 0, MLP_TL_CHUNKS - 1, 1);   // OUT complete
+      const int row_g = tile * 2 * GEMM_BM + rank * GEMM_BM + q * 32;
+#pragma unroll 1
+      for (int s = 0; s < NOS; ++s) {
+        const int col = cg * OCW + s * 32;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(lane_taddr + col, r);
+        float bv[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias2 + col) + j);
+          bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
+        }
+        ptx::tmem_ld_wait(r);
+        if (s == NOS - 1) {   // this warp's part of OUT is in registers
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_leader(out_empty);
+        }
+        const uint32_t box = (s & 1) ? box1 : box0;
+        if (lane == 0) {
+          if (EW == 8) ptx::bulk_wait_read1(); else ptx::bulk_wait_read0();
+        }
+        __syncwarp();
+        const uint32_t rowaddr = box + lane * 128;
+        const int sw = lane & 7;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          ptx::sts_v4(rowaddr + ((j ^ sw) << 4), __float_as_uint(__uint_as_float(r[4 * j]) + bv[4 * j]),
+                      __float_as_uint(__uint_as_float(r[4 * j + 1]) + bv[4 * j + 1]), __float_as_uint(__uint_as_float(r[4 * j + 2]) + bv[4 * j + 2]),
+                      __float_as_uint(__uint_as_float(r[4 * j + 3]) + bv[4 * j + 3]));
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_reduce_add_2d(&tmap_x, box, col, row_g);
+          ptx::bulk_commit();
+        }
+      }
+      // every staging box inside the H buffer has been read before any warp writes the next item's first chunk there
+      if (lane == 0) ptx::bulk_wait_read0();
+      __syncwarp();
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+      mlp_stamp(args, tl, 0, MLP_TL_CHUNKS - 1, 2);   // item epilogue done
+    }
+    if (lane == 0) ptx::bulk_wait_all0();   // global writes complete before the CTA exits
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();   // no CTA leaves while the peer could still address its shared memory / TMEM
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+}  // namespace vitocm

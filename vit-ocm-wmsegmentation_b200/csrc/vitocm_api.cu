@@ -17,6 +17,7 @@
 #include "attention_bwd_sm100.cuh"
 #include "attention_sm100.cuh"
 #include "gemm_sm100.cuh"
+#include "mlp_fused_sm100.cuh"
 #include "post_kernels.cuh"
 #include "train_kernels.cuh"
 #include "vit_kernels.cuh"
@@ -55,10 +56,10 @@ int fail(int code, const char* fmt, ...) {
 
 // ---- optional per-kernel-class device timing (CUDA events on the launching stream) ----
 enum ProfClass { PC_PATCH = 0, PC_LN, PC_GEMM_QKV, PC_ATTN, PC_GEMM_PROJ, PC_GEMM_FC1, PC_GEMM_FC2, PC_GEMM_KLAST, PC_CLSROW,
-                 PC_POST, PC_OTHER, PC_WGRAD, PC_DGRAD, PC_ATTN_BWD, PC_TRAIN_ELEM, PC_OPTIM, PC_COUNT };
+                 PC_POST, PC_OTHER, PC_WGRAD, PC_DGRAD, PC_ATTN_BWD, PC_TRAIN_ELEM, PC_OPTIM, PC_MLP, PC_COUNT };
 const char* const kProfNames[PC_COUNT] = {"patch_embed", "layernorm", "gemm_qkv", "attention", "gemm_proj", "gemm_fc1_gelu",
                                           "gemm_fc2", "gemm_k_last", "cls_attn_row", "post", "other", "gemm_wgrad", "gemm_dgrad",
-                                          "attention_bwd", "train_elementwise", "optimizer"};
+                                          "attention_bwd", "train_elementwise", "optimizer", "mlp_fused"};
 struct ProfRec { int cls; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
@@ -456,6 +457,60 @@ int run_gemm_ln(const vitocm_engine* e, const void* A, long long lda, const void
   }
 }
 
+// ---------------------------------------------------------------------------------- fused MLP launch
+// X[M][D] += gelu(XN . W1^T + b1) . W2^T + b2 in one kernel (mlp_fused_sm100.cuh).  Returns 1 when the shape / engine has no
+// fused instantiation (the caller then runs fc1 and fc2 as separate GEMMs).
+template <int KB1, int EW>
+int launch_mlp_fused(const CUtensorMap& ta, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx, const MlpArgs& a,
+                     int num_sms, cudaStream_t st) {
+  using Cfg = MlpCfg<KB1, EW>;
+  static int max_pairs = -1;
+  auto kern = mlp_fused_tcgen05_kernel<KB1, EW>;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (max_pairs < 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    cfg.gridDim = dim3(2 * (num_sms / 2));
+    int n = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    if (n < 1) return fail(VITOCM_ERR_CUDA, "no CTA pair of the fused MLP kernel fits on this device");
+    max_pairs = n < num_sms / 2 ? n : num_sms / 2;
+  }
+  const int tiles = (a.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  cfg.gridDim = dim3(2 * (tiles < max_pairs ? tiles : max_pairs));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tw1, tw2, tx, a));
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int run_mlp_fused(const vitocm_engine* e, const void* XN, long long ld_xn, const void* W1, long long ldw1, const void* W2, long long ldw2,
+                  int M, int D, int Hd, const float* b1, const float* b2, float* X, cudaStream_t st, bool force = false,
+                  long long* timeline = nullptr) {
+  // VITOCM_FUSE_MLP: 0 = never, 1 = 16 epilogue warps (default), 8 = 8 epilogue warps
+  static const int mode = [] { const char* v = getenv("VITOCM_FUSE_MLP"); return v == nullptr ? 1 : atoi(v); }();
+  if (mode == 0 && !force) return 1;
+  if (e->split || M <= 0 || (D != 128 && D != 384) || Hd % MLP_HC != 0 || b1 == nullptr || b2 == nullptr) return 1;
+  if ((reinterpret_cast<uintptr_t>(b1) & 15) != 0 || (reinterpret_cast<uintptr_t>(b2) & 15) != 0) return 1;
+  ProfScope prof(PC_MLP, st);
+  CUtensorMap ta, tw1, tw2, tx;
+  TRY(make_tmap_bf16(&ta, XN, M, D, ld_xn, GEMM_BM));
+  TRY(make_tmap_bf16(&tw1, W1, Hd, D, ldw1, 64));
+  TRY(make_tmap_bf16(&tw2, W2, D, Hd, ldw2, 64));
+  TRY(make_tmap(&tx, X, true, D, M, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  MlpArgs a{};
+  a.M = M; a.hidden = Hd; a.f16 = e->f16; a.gelu_mode = e->f16 ? 2 : 0; a.bias1 = b1; a.bias2 = b2;
+  a.timeline = timeline;
+  { static const int tli = [] { const char* v = getenv("VITOCM_MLP_TL_ITEM"); return v ? atoi(v) : 1; }(); a.timeline_item = tli; }
+  if (D == 384) return mode == 8 ? launch_mlp_fused<6, 8>(ta, tw1, tw2, tx, a, e->num_sms, st) : launch_mlp_fused<6, 16>(ta, tw1, tw2, tx, a, e->num_sms, st);
+  return mode == 8 ? launch_mlp_fused<2, 8>(ta, tw1, tw2, tx, a, e->num_sms, st) : launch_mlp_fused<2, 16>(ta, tw1, tw2, tx, a, e->num_sms, st);
+}
+
 // ---------------------------------------------------------------------------------- attention launch
 int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, int N, void* ctx, long long ldo, cudaStream_t st,
                   long long* timeline = nullptr, float* lse2 = nullptr) {
@@ -625,6 +680,13 @@ int block_forward(const vitocm_engine* e, int l, const Workspace& ws, int B, int
   }
   const int HP = mlp2 ? 2 : P;        // hidden activations: (hi | lo) in split engines and in act-split blocks
   const int mlp_in = S ? 1 : (mlp2 ? 2 : 0);
+  // fc1 + GELU + fc2 + residual in one kernel where an instantiation exists (single 16-bit operands, D = 128 / 384): the hidden
+  // activations never reach HBM
+  if (!S && !mlp2) {
+    rc = run_mlp_fused(e, ws.XN, 2LL * D, L.w1.p, D, L.w2.p, Hd, M, D, Hd, L.b1, L.b2, ws.X, st);
+    if (rc < 0) return rc;
+    if (rc == 0) return 0;
+  }
   TRY(run_gemm(e, ws.XN, 2LL * D, L.w1.p, static_cast<long long>(D) * P, M, Hd, D, mlp_in, EPI_BIAS_GELU_BF16, L.b1, ws.HID,
                static_cast<long long>(Hd) * HP, S || mlp2, Hd, st, PC_GEMM_FC1));
   // fc2 + residual (+ the next block's norm1 fused when possible)
@@ -1360,6 +1422,21 @@ int vitocm_gemm_ln(vitocm_engine* e, const void* A, int64_t lda, const void* B, 
   return rc;
 }
 
+int vitocm_mlp_fused(vitocm_engine* e, const void* XN, int64_t ld_xn, const void* W1, int64_t ldw1, const void* W2, int64_t ldw2, int M, int D,
+                     int hidden, const float* bias1, const float* bias2, float* X, void* stream) {
+  if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
+  const int rc = run_mlp_fused(e, XN, ld_xn, W1, ldw1, W2, ldw2, M, D, hidden, bias1, bias2, X, reinterpret_cast<cudaStream_t>(stream), true);
+  if (rc == 1) return fail(VITOCM_ERR_INVALID, "fused MLP: no instantiation for D=%d hidden=%d in this engine mode", D, hidden);
+  return rc;
+}
+int vitocm_mlp_fused_timeline(vitocm_engine* e, const void* XN, int64_t ld_xn, const void* W1, int64_t ldw1, const void* W2, int64_t ldw2,
+                              int M, int D, int hidden, const float* bias1, const float* bias2, float* X, int64_t* stamps, void* stream) {
+  if (e == nullptr || stamps == nullptr) return fail(VITOCM_ERR_INVALID, "null engine / stamps");
+  const int rc = run_mlp_fused(e, XN, ld_xn, W1, ldw1, W2, ldw2, M, D, hidden, bias1, bias2, X, reinterpret_cast<cudaStream_t>(stream), true,
+                               reinterpret_cast<long long*>(stamps));
+  if (rc == 1) return fail(VITOCM_ERR_INVALID, "fused MLP: no instantiation for D=%d hidden=%d in this engine mode", D, hidden);
+  return rc;
+}
 int vitocm_attention(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo, void* stream) {
   if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
   return run_attention(e, qkv, ld, B, n_tokens, ctx, ldo, static_cast<cudaStream_t>(stream));
