@@ -256,7 +256,7 @@ int vitocm_gemm_ln(vitocm_engine* e, const void* A, int64_t lda, const void* B, 
 int vitocm_mlp_fused(vitocm_engine* e, const void* XN, int64_t ld_xn, const void* W1, int64_t ldw1, const void* W2, int64_t ldw2, int M,
                      int D, int hidden, const float* bias1, const float* bias2, float* X, void* stream);
 /* Diagnostics: vitocm_mlp_fused that also records SM-clock stamps of the leader CTA of pair 0 on its second work item
- * (VITOCM_MLP_TL_ITEM): stamps int64 [2 role: epilogue warp 0, MMA thread][16 chunks][8 events]. */
+ * (VITOCM_MLP_TL_ITEM): stamps int64 [64] (layout: MlpArgs::timeline in csrc/mlp_fused_sm100.cuh). */
 int vitocm_mlp_fused_timeline(vitocm_engine* e, const void* XN, int64_t ld_xn, const void* W1, int64_t ldw1, const void* W2, int64_t ldw2,
                               int M, int D, int hidden, const float* bias1, const float* bias2, float* X, int64_t* stamps, void* stream);
 /* ctx = MHSA(qkv) for B images of n_tokens tokens: qkv bf16 [B*N][ld], ctx bf16 [B*N][ldo]. */

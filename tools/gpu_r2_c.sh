@@ -4,17 +4,14 @@ mkdir -p gpurun_out
 L=gpurun_out/r2c.log
 : > $L
 timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q --no-header -x -k "mlp_fused" 2>&1 | grep -E "passed|failed|FAILED|Error|error|vitocm:|assert" | head -30 >> $L
-echo "=== mlp timeline" >> $L
-VITOCM_FUSE_MLP=1 timeout 120 python tools/mlp_timeline.py 2>&1 | tail -16 >> $L
-VITOCM_FUSE_MLP=8 timeout 120 python tools/mlp_timeline.py 2>&1 | tail -16 >> $L
 echo "=== mlp bench" >> $L
-for ew in 1 8; do for pr in 0 2; do
+for ew in 2 4; do for pr in 0 2; do
   VITOCM_FUSE_MLP=$ew PRECISION=$pr timeout 120 python tools/mlp_bench.py 2>&1 | tail -2 >> $L
 done; done
 echo "=== suite" >> $L
 timeout 900 python -m pytest tests -m gpu -q --no-header 2>&1 | grep -E "passed|failed|FAILED|Error|error|vitocm:|agreement|rel err" | head -40 >> $L
 echo "=== bench" >> $L
-for fm in 1 8 0; do
+for fm in 2 4 0; do
 VITOCM_FUSE_MLP=$fm timeout 600 python bench.py --no-extras --no-cpu-baseline > gpurun_out/r2c_bench_$fm.json 2> gpurun_out/r2c_bench_$fm.err
 tail -3 gpurun_out/r2c_bench_$fm.err >> $L
 python - $fm >> $L <<'PY'

@@ -1,5 +1,5 @@
 """Fused MLP kernel against the fc1 + fc2 GEMM pair it replaces, at the bench chunk (M = 175 x 785 rows of ViT-S): device time per
-launch.  Env: ROWS, PRECISION (0 bf16 / 2 fp16), VITOCM_FUSE_MLP (1 = 16 epilogue warps, 8 = 8)."""
+launch.  Env: ROWS, PRECISION (0 bf16 / 2 fp16), VITOCM_FUSE_MLP (cluster size 4 or 2), VITOCM_MLP_STAGGER."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -33,4 +33,4 @@ for name, fn in (("fused", fused), ("fc1+fc2", separate)):
     for _ in range(30): fn()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 30
-    print(f"mlp {name} prec={PREC} epi_warps={os.environ.get('VITOCM_FUSE_MLP','1')} M={M}: {ms*1e3:.1f} us/launch, {4*M*D*Hd/ms/1e9:.0f} TFLOP/s")
+    print(f"mlp {name} prec={PREC} cluster={os.environ.get('VITOCM_FUSE_MLP','4')} stagger={os.environ.get('VITOCM_MLP_STAGGER','40000')} M={M}: {ms*1e3:.1f} us/launch, {4*M*D*Hd/ms/1e9:.0f} TFLOP/s")

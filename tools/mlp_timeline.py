@@ -1,5 +1,5 @@
-"""Per-chunk timeline of the fused MLP kernel (SM clocks) for the leader CTA of pair 0 on its second work item, at full-chip load.
-Env: ROWS, PRECISION, VITOCM_FUSE_MLP (1 / 8 epilogue-warp variant), VITOCM_MLP_TL_ITEM."""
+"""Per-chunk timeline of the fused MLP kernel (SM clocks) for the leader CTA of cluster 0 on its second work item, at full-chip load.
+Env: ROWS, PRECISION, VITOCM_FUSE_MLP (cluster size 4 / 2), VITOCM_MLP_TL_ITEM, VITOCM_MLP_DEBUG."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -19,17 +19,16 @@ W1 = (torch.randn(Hd, D, device="cuda") * 0.05).to(dt)
 W2 = (torch.randn(D, Hd, device="cuda") * 0.03).to(dt)
 b1, b2 = torch.randn(Hd, device="cuda") * 0.1, torch.randn(D, device="cuda") * 0.1
 X = torch.zeros(M, D, device="cuda")
-stamps = torch.zeros(2, 16, 8, dtype=torch.int64, device="cuda")
+stamps = torch.zeros(64, dtype=torch.int64, device="cuda")
 for _ in range(3):
     check(lib.vitocm_mlp_fused_timeline(eng, ptr(A), A.stride(0), ptr(W1), W1.stride(0), ptr(W2), W2.stride(0), M, D, Hd, ptr(b1), ptr(b2),
                                         ptr(X), ptr(stamps), cur_stream()))
 torch.cuda.synchronize()
-s = stamps.cpu()
-t0 = int(s[s > 0].min())
-rel = lambda v: int(v) - t0 if v > 0 else -1
-print("epilogue warp 0:  wait fc1 | fc1 done | in regs | gelu done | H free | handed      ||  MMA thread: acc free | fc1 issued | wait gelu | gelu ready | fc2 issued")
+s = [int(v) for v in stamps.cpu()]
+t0 = s[60]
+rel = lambda v: (v - t0) & 0xffffffff
+print(f"fused MLP timeline (cluster {os.environ.get('VITOCM_FUSE_MLP', '4')}, debug {os.environ.get('VITOCM_MLP_DEBUG', '0')}); clocks since the item's A tile landed")
+print("        epilogue warp 0: fc1(c) complete | gelu arithmetic done | gelu(c) handed over   ||   MMA thread: fc1(c) issued | gelu(c) available")
 for c in range(Hd // 128):
-    e = [rel(s[0, c, k]) for k in range(6)]
-    m = [rel(s[1, c, k]) for k in range(5)]
-    print(f" c={c:2d}  " + " ".join(f"{v:7d}" for v in e) + "   ||  " + " ".join(f"{v:7d}" for v in m))
-print("item epilogue: wait OUT", rel(s[0, 15, 0]), "OUT complete", rel(s[0, 15, 1]), "done", rel(s[0, 15, 2]))
+    print(f" c={c:2d}   {rel(s[3*c]):8d} {rel(s[3*c+1]):8d} {rel(s[3*c+2]):8d}   ||   {rel(s[36+2*c]):8d} {rel(s[36+2*c+1]):8d}")
+print(f"OUT complete {rel(s[61])}, item epilogue done {rel(s[62])}")

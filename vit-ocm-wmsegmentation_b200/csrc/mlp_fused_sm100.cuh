@@ -12,12 +12,15 @@
 //   for each chunk c of 128 hidden columns:
 //     fc1:  Hacc[128 x 128] (TMEM)  = A . W1[c]^T                         KB1 x 4 MMAs  (M 256, N 128, K 16)
 //     GELU: Hacc -> registers -> + b1 -> gelu -> 16-bit -> smem H[128 x 128] (two SWIZZLE_128B k-blocks: fc2's A operand)
-//     fc2:  OUT[128 x D] (TMEM)   += H . W2[:, c]^T                       2 x D/128 x 4 MMAs
+//     fc2:  OUT[128 x D] (TMEM)   += H . W2[:, c]^T                       2 x NP2 x 4 MMAs  (M 256, N D/NP2 = 192 at D = 384)
 //   OUT + b2 -> TMA reduce-add into the fp32 residual stream (performed by the L2)
-// Weights stream through a ring of 8 KB slots ([64 rows x 64 k] per CTA = its half of a [128 x 64] B tile), in the order the
-// MMA thread consumes them: fc1(0), fc1(1), fc2(0), fc1(2), fc2(1), ...  TMEM: OUT in columns [0, D), Hacc in [384, 512).
+// Weights stream through a ring of four 24 KB slots, in the order the MMA thread consumes them: fc1(0), fc1(1), fc2(0), fc1(2),
+// fc2(1), ...  A slot holds three fc1 k-blocks ([64 rows x 64 k] per CTA = its half of a [128 x 64] B tile) or the D/NP2-wide output
+// parts of one fc2 k-block: ONE barrier wait and ONE commit per 8-12 MMAs.  (With one 8 KB tile per slot the issuing thread spent
+// ~290 clk per slot on the wait / commit round trip against 256 clk of tensor work: the kernel was MMA-issue bound, and neither a
+// deeper ring nor multicast weights changed its speed -- profiles/r02_mlp_fused.txt.)  TMEM: OUT in columns [0, D), Hacc in [384, 512).
 // Warp roles: 0 = weight TMA, 1 = MMA issuer (leader CTA), 2 = TMEM allocator, 3 = A-tile TMA, 4.. = EW epilogue warps
-// (lane quadrant = warp % 4, column group = (warp - 4) / 4).
+// (lane quadrant = warp % 4, column group = (warp - 4) / 4); the first 8 of them also drain OUT through boxes inside the H buffer.
 #pragma once
 #include "gemm_sm100.cuh"
 
@@ -30,57 +33,70 @@ struct MlpArgs {
   int gelu_mode;       // 0 = three-coefficient sigmoid form (bf16 engines), 2 = five-coefficient sigmoid form (fp16 engines)
   const float* bias1;  // [Hd]
   const float* bias2;  // [D]
-  // diagnostics (vitocm_mlp_fused_timeline) or nullptr: clock64 stamps of the leader CTA of pair 0, work item `timeline_item`,
-  // [role: 0 = epilogue warp 0, 1 = MMA thread][chunk < MLP_TL_CHUNKS][event < MLP_TL_EVENTS]
+  // diagnostics (vitocm_mlp_fused_timeline) or nullptr: 64 SM-clock stamps (low 32 bits) of the leader CTA of cluster 0 on its work
+  // item `timeline_item`, collected in shared memory (global stores would sit in front of the cluster-scope barrier arrives) and
+  // written out when the kernel ends: [3 c + e], c < 12: epilogue warp 0, e = 0 fc1(c) complete, 1 gelu arithmetic done, 2 gelu(c)
+  // handed over; [36 + 2 c + e]: MMA thread, e = 0 fc1(c) issued, 1 gelu(c) available; [60] item start, [61] OUT complete,
+  // [62] item epilogue done
   long long* timeline;
   int timeline_item;
+  // Start stagger: every cluster does the same work in the same time, so without it all of them write their 128 x D output
+  // tiles in the same instant (a burst the L2 absorbs at ~1/3 of the kernel's average rate) and fetch the same weights in the
+  // same instant.  Clusters with index >= stagger_from -- those that have one work item fewer than the busiest, so the delay
+  // costs nothing -- start up to stagger_clk SM clocks late, evenly spread.  stagger_from >= the cluster count disables it.
+  int stagger_from;
+  int stagger_clk;
+  int debug;           // diagnostics (VITOCM_MLP_DEBUG): bit 0 = the MMA thread issues no MMAs (barrier traffic only), bit 1 = the
+                       // epilogue skips the GELU arithmetic, bit 2 = the epilogue skips the shared-memory stores of gelu(chunk)
 };
-constexpr int MLP_TL_CHUNKS = 16;
-constexpr int MLP_TL_EVENTS = 8;
-__device__ __forceinline__ void mlp_stamp(const MlpArgs& args, bool on, int role, int c, int ev) {
-  if (on && c < MLP_TL_CHUNKS) args.timeline[(role * MLP_TL_CHUNKS + c) * MLP_TL_EVENTS + ev] = clock64();
+__device__ __forceinline__ void mlp_stamp(bool on, uint32_t smem_tl, int idx) {
+  if (on) asm volatile("{\n\t.reg .b32 t;\n\tmov.u32 t, %%clock;\n\tst.shared.b32 [%0], t;\n\t}" ::"r"(smem_tl + 4u * idx) : "memory");
 }
 
 constexpr int MLP_HC = 128;                 // hidden columns per chunk
-constexpr int MLP_SLOT_BYTES = 64 * 64 * 2; // one CTA's half of a [128 x 64] weight tile
+constexpr int MLP_SLOT_BYTES = 3 * 64 * 64 * 2;   // one ring slot: up to three [64 rows x 64 k] weight tiles (24 KB), one mbarrier round trip
 constexpr int MLP_KB_BYTES = 128 * 64 * 2;  // one [128 x 64] k-block of an A operand
 constexpr int MLP_H_COL = 384;              // TMEM column of the hidden-chunk accumulator
-constexpr int MLP_MAX_SLOTS = 8;
+constexpr int MLP_MAX_SLOTS = 4;
 
-template <int KB1, int EW>
+constexpr int MLP_EW = 16;                  // epilogue warps
+template <int KB1, int CL>
 struct MlpCfg {
+  static constexpr int EW = MLP_EW;
+  static_assert(CL == 2 || CL == 4, "fused MLP: clusters of one or two CTA pairs");
   static constexpr int D = KB1 * 64;
-  static constexpr int NP2 = D / 128;                   // 128-column output parts (one fc2 MMA group each)
+  static constexpr int NP2 = (D + 255) / 256;           // output parts, one fc2 MMA each per k step: N = BN2 = D / NP2 (192 at D = 384)
+  static constexpr int BN2 = D / NP2;
+  static constexpr int T1 = KB1 % 3 == 0 ? 3 : (KB1 % 2 == 0 ? 2 : 1);   // fc1 k-blocks per ring slot
+  static constexpr int W2_TILE_BYTES = (BN2 / 2) * 128;  // one CTA's half of a [BN2 x 64] fc2 weight tile
+  static_assert(NP2 * W2_TILE_BYTES <= MLP_SLOT_BYTES && T1 * 8192 <= MLP_SLOT_BYTES, "fused MLP: ring slot too small");
   static_assert(D % 128 == 0 && D <= 384, "fused MLP: D must be 128, 256 or 384");
-  static_assert(EW == 8 || EW == 16, "fused MLP: 8 or 16 epilogue warps");
   static constexpr int THREADS = (4 + EW) * 32;
   static constexpr int A_BYTES = KB1 * MLP_KB_BYTES;
-  static constexpr int H_BYTES = 2 * MLP_KB_BYTES;      // also 8 output staging boxes (32 x 32 fp32) between items
-  static constexpr int STG_BYTES = 8 * 4096;            // 8 dedicated output staging boxes
+  static constexpr int H_BYTES = 2 * MLP_KB_BYTES;      // between items: the 8 output staging boxes (32 x 32 fp32)
   static constexpr int BAR_BYTES = 512;
-  static constexpr int FIXED = A_BYTES + H_BYTES + STG_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
+  static constexpr int FIXED = A_BYTES + H_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
   static constexpr int SLOTS_FIT = (GEMM_SMEM_LIMIT - FIXED) / MLP_SLOT_BYTES;
   static constexpr int SLOTS = SLOTS_FIT > MLP_MAX_SLOTS ? MLP_MAX_SLOTS : SLOTS_FIT;
-  static_assert(SLOTS >= 4, "fused MLP: weight ring too shallow");
+  static_assert(SLOTS >= 3, "fused MLP: weight ring too shallow");
   static constexpr int SMEM_BYTES = FIXED + SLOTS * MLP_SLOT_BYTES;
   // setmaxnreg budgets, EW = 16 only (640 threads x 96 registers at launch): 128 x 48 + 512 x 104 <= 640 x 96
   static constexpr int REGS_CTRL = 48;
   static constexpr int REGS_EPI = 104;
 };
 
-template <int KB1, int EW>
-__global__ void __launch_bounds__(MlpCfg<KB1, EW>::THREADS, 1)
+template <int KB1, int CL>
+__global__ void __launch_bounds__(MlpCfg<KB1, CL>::THREADS, 1)
 mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w1,
                          const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_x, const MlpArgs args) {
-  using Cfg = MlpCfg<KB1, EW>;
-  constexpr int D = Cfg::D, NP2 = Cfg::NP2, SLOTS = Cfg::SLOTS;
+  using Cfg = MlpCfg<KB1, CL>;
+  constexpr int D = Cfg::D, NP2 = Cfg::NP2, BN2 = Cfg::BN2, T1 = Cfg::T1, SLOTS = Cfg::SLOTS, EW = Cfg::EW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_h = smem_a + Cfg::A_BYTES;
   const uint32_t smem_w = smem_h + Cfg::H_BYTES;
-  const uint32_t smem_stg = smem_w + SLOTS * MLP_SLOT_BYTES;
-  const uint32_t bars = smem_stg + Cfg::STG_BYTES;
+  const uint32_t bars = smem_w + SLOTS * MLP_SLOT_BYTES;
   const uint32_t w_full = bars;                       // [SLOTS] TMA -> MMA (leader's copy counts both CTAs' bytes)
   const uint32_t w_empty = bars + 8 * MLP_MAX_SLOTS;  // [SLOTS] MMA -> TMA (both CTAs)
   const uint32_t a_full = bars + 16 * MLP_MAX_SLOTS;  // A tile landed (leader's copy)
@@ -92,13 +108,22 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const uint32_t out_full = a_full + 48;              // last fc2 of the item retired (both CTAs)
   const uint32_t out_empty = a_full + 56;             // epilogue warps of both CTAs read OUT out of TMEM (leader's copy)
   const uint32_t tmem_ptr_smem = a_full + 64;
+  const uint32_t smem_tl = bars + 256;                // [64] diagnostics stamps
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int rank = static_cast<int>(ptx::cluster_ctarank());
-  const int pair = static_cast<int>(blockIdx.x) >> 1;
-  const int npairs = static_cast<int>(gridDim.x) >> 1;
+  const int crank = static_cast<int>(ptx::cluster_ctarank());
+  const int rank = crank & 1;            // rank inside the CTA pair (0 = leader: issues the MMAs)
+  const int pairid = crank >> 1;         // pair inside the cluster (CL == 4: two pairs share every weight slot by multicast)
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pairid));
+  const uint16_t all_mask = CL == 4 ? 0xF : 0x3;
+  // work items: 256-row tiles; cluster k walks tile groups k, k + gridDim / CL, ... (CL / 2 consecutive tiles per group, one per pair:
+  // the pairs of a cluster run in lockstep on the shared weight ring, so a pair whose tile lies beyond M still goes through the
+  // motions -- its A rows are zero-filled and its stores clipped by the tensor maps)
   const int tiles_m = (args.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int groups = (tiles_m + CL / 2 - 1) / (CL / 2);
+  const int group0 = static_cast<int>(blockIdx.x) / CL;
+  const int gstep = static_cast<int>(gridDim.x) / CL;
   const int NC = args.hidden / MLP_HC;
 
   if (warp == 0 && lane == 0) {
@@ -110,7 +135,7 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < SLOTS; ++s) {
       ptx::mbar_init(w_full + 8 * s, 1);
-      ptx::mbar_init(w_empty + 8 * s, 1);
+      ptx::mbar_init(w_empty + 8 * s, CL / 2);   // one commit per pair sharing the slot
     }
     ptx::mbar_init(a_full, 1);
     ptx::mbar_init(a_empty, 1);
@@ -119,7 +144,7 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     ptx::mbar_init(h_smem_full, 2 * EW);
     ptx::mbar_init(h_smem_empty, 1);
     ptx::mbar_init(out_full, 1);
-    ptx::mbar_init(out_empty, 2 * EW);
+    ptx::mbar_init(out_empty, 2 * 8);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -133,26 +158,49 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const uint32_t tmem_base = ptx::lds_u32(tmem_ptr_smem);
 
   if (warp < 4) {
-    if (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_CTRL));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_CTRL));
     if (warp == 0) {
       // ===================== weight TMA producer (both CTAs: each stages its half of every B tile) =====================
       if (lane == 0) {
+        // start stagger (see MlpArgs::stagger_clk): everything downstream waits for the first weights
+        if (group0 >= args.stagger_from) {
+          const long long wait_clk = static_cast<long long>(args.stagger_clk) * (group0 - args.stagger_from + 1) / (gstep - args.stagger_from + 1);
+          const long long t0 = clock64();
+          while (clock64() - t0 < wait_clk) {}
+        }
         int slot = 0;
         uint32_t phase = 0;
-        auto put = [&](const CUtensorMap* tm, int c0, int c1) {
-          ptx::mbar_wait(w_empty + 8 * slot, phase ^ 1, 31);
-          if (rank == 0) ptx::mbar_arrive_expect_tx(w_full + 8 * slot, 2 * MLP_SLOT_BYTES);
-          ptx::tma_load_2d_2cta(smem_w + slot * MLP_SLOT_BYTES, tm, w_full + 8 * slot, c0, c1);
+        int n = 0;   // loads so far: the pairs of a 4-CTA cluster take turns issuing the multicast load of a slot
+        // one ring slot = `ntiles` boxes: acquire it, arm the leader's barrier with both CTAs' bytes, then the boxes (CL == 4: only the
+        // pair whose turn it is issues them, multicast to the CTA of the same rank in the other pair)
+        auto acquire = [&](int bytes) {
+          ptx::mbar_wait(w_empty + 8 * slot, phase ^ 1, 31);   // every pair sharing the slot has consumed it
+          if (rank == 0) ptx::mbar_arrive_expect_tx(w_full + 8 * slot, 2 * bytes);
+          return CL == 2 || (n & 1) == pairid;
+        };
+        auto box = [&](const CUtensorMap* tm, int off, int c0, int c1) {
+          if (CL == 2) ptx::tma_load_2d_2cta(smem_w + slot * MLP_SLOT_BYTES + off, tm, w_full + 8 * slot, c0, c1);
+          else ptx::tma_load_2d_2cta_mc(smem_w + slot * MLP_SLOT_BYTES + off, tm, w_full + 8 * slot, c0, c1, static_cast<uint16_t>(5u << rank));
+        };
+        auto release = [&]() {
+          ++n;
           if (++slot == SLOTS) { slot = 0; phase ^= 1; }
         };
         auto load_fc1 = [&](int c) {
-          for (int kb = 0; kb < KB1; ++kb) put(&tmap_w1, kb * GEMM_BK, c * MLP_HC + rank * 64);
+          for (int kb = 0; kb < KB1; kb += T1) {
+            if (acquire(T1 * 8192))
+              for (int kk = 0; kk < T1; ++kk) box(&tmap_w1, kk * 8192, (kb + kk) * GEMM_BK, c * MLP_HC + rank * 64);
+            release();
+          }
         };
         auto load_fc2 = [&](int c) {
-          for (int kb2 = 0; kb2 < 2; ++kb2)
-            for (int np = 0; np < NP2; ++np) put(&tmap_w2, c * MLP_HC + kb2 * GEMM_BK, np * 128 + rank * 64);
+          for (int kb2 = 0; kb2 < 2; ++kb2) {
+            if (acquire(NP2 * Cfg::W2_TILE_BYTES))
+              for (int np = 0; np < NP2; ++np) box(&tmap_w2, np * Cfg::W2_TILE_BYTES, c * MLP_HC + kb2 * GEMM_BK, np * BN2 + rank * (BN2 / 2));
+            release();
+          }
         };
-        for (int tile = pair; tile < tiles_m; tile += npairs) {
+        for (int grp = group0; grp < groups; grp += gstep) {
           load_fc1(0);
           for (int c = 0; c < NC; ++c) {
             if (c + 1 < NC) load_fc1(c + 1);
@@ -164,7 +212,8 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       // ===================== A-tile TMA producer =====================
       if (lane == 0) {
         int t = 0;
-        for (int tile = pair; tile < tiles_m; tile += npairs, ++t) {
+        for (int grp = group0; grp < groups; grp += gstep, ++t) {
+          const int tile = grp * (CL / 2) + pairid;
           ptx::mbar_wait(a_empty, (t & 1) ^ 1, 32);   // the previous item's fc1 MMAs no longer read the tile
           if (rank == 0) ptx::mbar_arrive_expect_tx(a_full, 2 * Cfg::A_BYTES);
           for (int kb = 0; kb < KB1; ++kb)
@@ -174,7 +223,8 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     } else if (warp == 1) {
       // ===================== MMA issuer (leader CTA) =====================
       if (rank == 0 && ptx::elect_one()) {
-        const uint32_t idesc = ptx::make_idesc(2 * GEMM_BM, 128, false, false, args.f16 ? 0u : 1u);
+        const uint32_t idesc = ptx::make_idesc(2 * GEMM_BM, MLP_HC, false, false, args.f16 ? 0u : 1u);    // fc1: N = one hidden chunk
+        const uint32_t idesc2 = ptx::make_idesc(2 * GEMM_BM, BN2, false, false, args.f16 ? 0u : 1u);      // fc2: N = one output part
         const uint64_t a_desc0 = ptx::make_smem_desc_sw128(smem_a, 1024, 0);
         const uint64_t h_desc0 = ptx::make_smem_desc_sw128(smem_h, 1024, 0);
         const uint64_t w_desc0 = ptx::make_smem_desc_sw128(smem_w, 1024, 0);
@@ -189,28 +239,31 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             ptx::mbar_wait(h_tmem_empty, (g1 - 1) & 1, 33);
             ptx::tc_fence_after();
           }
-          mlp_stamp(args, tl, 1, c, 0);   // accumulator free: fc1(c) may be issued
 #pragma unroll 1
-          for (int kb = 0; kb < KB1; ++kb) {
+          for (int kb = 0; kb < KB1; kb += T1) {
             ptx::mbar_wait(w_full + 8 * slot, phase, 34);
             ptx::tc_fence_after();
             const uint64_t adesc = ptx::desc_advance(a_desc0, kb * MLP_KB_BYTES);
             const uint64_t bdesc = ptx::desc_advance(w_desc0, slot * MLP_SLOT_BYTES);
+            if (!(args.debug & 1)) {
 #pragma unroll
-            for (int k = 0; k < GEMM_BK / 16; ++k)
-              ptx::umma_bf16_ss_2cta(h_tmem, ptx::desc_advance(adesc, k * 32), ptx::desc_advance(bdesc, k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            ptx::umma_commit_2cta(w_empty + 8 * slot);
+              for (int kk = 0; kk < T1; ++kk)
+#pragma unroll
+                for (int k = 0; k < GEMM_BK / 16; ++k)
+                  ptx::umma_bf16_ss_2cta(h_tmem, ptx::desc_advance(adesc, kk * MLP_KB_BYTES + k * 32), ptx::desc_advance(bdesc, kk * 8192 + k * 32), idesc,
+                                         (kb > 0 || kk > 0 || k > 0) ? 1u : 0u);
+            }
+            ptx::umma_commit_2cta_mask(w_empty + 8 * slot, all_mask);
             if (++slot == SLOTS) { slot = 0; phase ^= 1; }
           }
-          ptx::umma_commit_2cta(h_full);
-          mlp_stamp(args, tl, 1, c, 1);   // fc1(c) issued
+          ptx::umma_commit_2cta_mask(h_full, pair_mask);
+          if (c < 12) mlp_stamp(tl, smem_tl, 36 + 2 * c);
           ++g1;
         };
         auto issue_fc2 = [&](int c) {
-          mlp_stamp(args, tl, 1, c, 2);   // waiting for gelu(chunk c)
           ptx::mbar_wait_cluster(h_smem_full, g2 & 1, 35);   // gelu(chunk) sits in both CTAs' shared memory
           ptx::tc_fence_after();
-          mlp_stamp(args, tl, 1, c, 3);   // gelu(chunk c) ready
+          if (c < 12) mlp_stamp(tl, smem_tl, 36 + 2 * c + 1);
           if (c == 0 && t > 0) {   // OUT still holds the previous item until both CTAs' epilogue warps have read it
             ptx::mbar_wait(out_empty, (t - 1) & 1, 36);
             ptx::tc_fence_after();
@@ -218,66 +271,64 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll 1
           for (int kb2 = 0; kb2 < 2; ++kb2) {
             const uint64_t adesc = ptx::desc_advance(h_desc0, kb2 * MLP_KB_BYTES);
-#pragma unroll 1
-            for (int np = 0; np < NP2; ++np) {
-              ptx::mbar_wait(w_full + 8 * slot, phase, 37);
-              ptx::tc_fence_after();
-              const uint64_t bdesc = ptx::desc_advance(w_desc0, slot * MLP_SLOT_BYTES);
+            ptx::mbar_wait(w_full + 8 * slot, phase, 37);
+            ptx::tc_fence_after();
+            const uint64_t bdesc = ptx::desc_advance(w_desc0, slot * MLP_SLOT_BYTES);
+            if (!(args.debug & 1)) {
 #pragma unroll
-              for (int k = 0; k < GEMM_BK / 16; ++k)
-                ptx::umma_bf16_ss_2cta(tmem_base + np * 128, ptx::desc_advance(adesc, k * 32), ptx::desc_advance(bdesc, k * 32), idesc,
-                                       (c > 0 || kb2 > 0 || k > 0) ? 1u : 0u);
-              ptx::umma_commit_2cta(w_empty + 8 * slot);
-              if (++slot == SLOTS) { slot = 0; phase ^= 1; }
+              for (int np = 0; np < NP2; ++np)
+#pragma unroll
+                for (int k = 0; k < GEMM_BK / 16; ++k)
+                  ptx::umma_bf16_ss_2cta(tmem_base + np * BN2, ptx::desc_advance(adesc, k * 32), ptx::desc_advance(bdesc, np * Cfg::W2_TILE_BYTES + k * 32),
+                                         idesc2, (c > 0 || kb2 > 0 || k > 0) ? 1u : 0u);
             }
+            ptx::umma_commit_2cta_mask(w_empty + 8 * slot, all_mask);
+            if (++slot == SLOTS) { slot = 0; phase ^= 1; }
           }
-          ptx::umma_commit_2cta(h_smem_empty);
-          mlp_stamp(args, tl, 1, c, 4);   // fc2(c) issued
+          ptx::umma_commit_2cta_mask(h_smem_empty, pair_mask);
           ++g2;
         };
-        for (int tile = pair; tile < tiles_m; tile += npairs, ++t) {
+        for (int grp = group0; grp < groups; grp += gstep, ++t) {
           tl = args.timeline != nullptr && blockIdx.x == 0 && t == args.timeline_item;
           ptx::mbar_wait(a_full, t & 1, 38);
           ptx::tc_fence_after();
+          mlp_stamp(tl, smem_tl, 60);
           issue_fc1(0);
-          if (NC == 1) ptx::umma_commit_2cta(a_empty);
+          if (NC == 1) ptx::umma_commit_2cta_mask(a_empty, pair_mask);
           for (int c = 0; c < NC; ++c) {
             if (c + 1 < NC) {
               issue_fc1(c + 1);
-              if (c + 2 == NC) ptx::umma_commit_2cta(a_empty);   // last fc1 of the item: the A tile may be replaced once it retires
+              if (c + 2 == NC) ptx::umma_commit_2cta_mask(a_empty, pair_mask);   // last fc1 of the item: the A tile may be replaced once it retires
             }
             issue_fc2(c);
           }
-          ptx::umma_commit_2cta(out_full);
+          ptx::umma_commit_2cta_mask(out_full, pair_mask);
         }
       }
     }
   } else {
     // ===================== epilogue warps =====================
-    if (EW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_EPI));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_EPI));
     const int ew = warp - 4;
     const int q = warp & 3;          // TMEM lane quadrant
     const int cg = ew >> 2;          // column group
     constexpr int CPW = MLP_HC / (EW / 4);   // hidden columns per warp and chunk (32 or 64)
     constexpr int NSUB = CPW / 32;
-    constexpr int OCW = D / (EW / 4);        // output columns per warp
+    constexpr int OCW = D / 2;               // output columns per draining warp (the first 8 epilogue warps drain OUT)
     constexpr int NOS = OCW / 32;
-    static_assert(OCW % 32 == 0, "fused MLP: output columns per epilogue warp must be a multiple of 32");
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int row = q * 32 + lane;   // row of the CTA's 128
-    // output staging boxes: warp ew < 8 owns a dedicated box, warp ew >= 8 a box inside the H buffer (idle between items);
-    // with 8 warps each warp alternates between its two
-    const uint32_t box0 = ew < 8 ? smem_stg + ew * 4096 : smem_h + (ew - 8) * 4096;
-    const uint32_t box1 = EW == 8 ? smem_h + ew * 4096 : box0;
+    // output staging: between items the H buffer holds one 32 x 32 fp32 box for each of the first 8 epilogue warps
+    const uint32_t box = smem_h + (ew & 7) * 4096;
     int ge = 0;   // chunks processed (all items)
     int t = 0;
-    for (int tile = pair; tile < tiles_m; tile += npairs, ++t) {
+    for (int grp = group0; grp < groups; grp += gstep, ++t) {
+      const int tile = grp * (CL / 2) + pairid;
       const bool tl = args.timeline != nullptr && blockIdx.x == 0 && t == args.timeline_item && ew == 0 && lane == 0;
       for (int c = 0; c < NC; ++c, ++ge) {
-        mlp_stamp(args, tl, 0, c, 0);   // waiting for fc1(c)
         ptx::mbar_wait(h_full, ge & 1, 40);
         ptx::tc_fence_after();
-        mlp_stamp(args, tl, 0, c, 1);   // fc1(c) complete
+        if (c < 12) mlp_stamp(tl, smem_tl, 3 * c);
         uint32_t r[NSUB][32];
 #pragma unroll
         for (int s = 0; s < NSUB; ++s) ptx::tmem_ld_32x32b_x32(lane_taddr + MLP_H_COL + cg * CPW + s * 32, r[s]);
@@ -287,7 +338,6 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_leader(h_tmem_empty);
-        mlp_stamp(args, tl, 0, c, 2);   // chunk in registers
         uint32_t pk[NSUB][16];
 #pragma unroll
         for (int s = 0; s < NSUB; ++s) {
@@ -301,7 +351,8 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             v[4 * j + 2] = __uint_as_float(r[s][4 * j + 2]) + b4.z;
             v[4 * j + 3] = __uint_as_float(r[s][4 * j + 3]) + b4.w;
           }
-          if (args.gelu_mode == 0) {
+          if (args.debug & 2) {
+          } else if (args.gelu_mode == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2) gelu_sigmoid_x2(v[j], v[j + 1]);
           } else {
@@ -316,10 +367,16 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             for (int j = 0; j < 16; ++j) pk[s][j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
           }
         }
+        if (args.timeline != nullptr) {   // diagnostics: pin the arithmetic above the stamp
+#pragma unroll
+          for (int s = 0; s < NSUB; ++s)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) asm volatile("" : "+r"(pk[s][j]));
+        }
+        if (c < 12) mlp_stamp(tl, smem_tl, 3 * c + 1);
         // the H buffer is free once fc2 of the previous chunk has retired
-        mlp_stamp(args, tl, 0, c, 3);   // gelu done
         if (ge > 0) ptx::mbar_wait(h_smem_empty, (ge - 1) & 1, 41);
-        mlp_stamp(args, tl, 0, c, 4);   // fc2(c - 1) retired: H buffer free
+        if (!(args.debug & 4))
 #pragma unroll
         for (int s = 0; s < NSUB; ++s) {
           const int hc = cg * CPW + s * 32;            // first hidden column of this sub-chunk inside the chunk
@@ -331,62 +388,61 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_remote(ptx::mapa(h_smem_full, 0));
-        mlp_stamp(args, tl, 0, c, 5);   // gelu(chunk) handed to the MMA thread
+        if (lane == 0) ptx::mbar_arrive_remote(ptx::mapa(h_smem_full, crank & ~1));
+        if (c < 12) mlp_stamp(tl, smem_tl, 3 * c + 2);
       }
       // ---- item epilogue: OUT + b2 -> fp32 boxes -> TMA reduce-add into the residual stream
-      mlp_stamp(args, tl, 0, MLP_TL_CHUNKS - 1, 0);   // waiting for the item's last fc2
       ptx::mbar_wait(out_full, t & 1, 42);
       ptx::tc_fence_after();
-      mlp_stamp(args, tl, 0, MLP_TL_CHUNKS - 1, 1);   // OUT complete
+      mlp_stamp(tl, smem_tl, 61);
       const int row_g = tile * 2 * GEMM_BM + rank * GEMM_BM + q * 32;
+      if (ew < 8) {
 #pragma unroll 1
-      for (int s = 0; s < NOS; ++s) {
-        const int col = cg * OCW + s * 32;
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(lane_taddr + col, r);
-        float bv[32];
+        for (int s = 0; s < NOS; ++s) {
+          const int col = (ew >> 2) * OCW + s * 32;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(lane_taddr + col, r);
+          float bv[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias2 + col) + j);
-          bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
-        }
-        ptx::tmem_ld_wait(r);
-        if (s == NOS - 1) {   // this warp's part of OUT is in registers
-          ptx::tc_fence_before();
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias2 + col) + j);
+            bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
+          }
+          ptx::tmem_ld_wait(r);
+          if (s == NOS - 1) {   // this warp's part of OUT is in registers
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_leader(out_empty);
+          }
+          if (lane == 0) ptx::bulk_wait_read0();   // the previous reduce-add has read the box
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_leader(out_empty);
-        }
-        const uint32_t box = (s & 1) ? box1 : box0;
-        if (lane == 0) {
-          if (EW == 8) ptx::bulk_wait_read1(); else ptx::bulk_wait_read0();
-        }
-        __syncwarp();
-        const uint32_t rowaddr = box + lane * 128;
-        const int sw = lane & 7;
+          const uint32_t rowaddr = box + lane * 128;
+          const int sw = lane & 7;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          ptx::sts_v4(rowaddr + ((j ^ sw) << 4), __float_as_uint(__uint_as_float(r[4 * j]) + bv[4 * j]),
-                      __float_as_uint(__uint_as_float(r[4 * j + 1]) + bv[4 * j + 1]), __float_as_uint(__uint_as_float(r[4 * j + 2]) + bv[4 * j + 2]),
-                      __float_as_uint(__uint_as_float(r[4 * j + 3]) + bv[4 * j + 3]));
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          ptx::tma_reduce_add_2d(&tmap_x, box, col, row_g);
-          ptx::bulk_commit();
+          for (int j = 0; j < 8; ++j)
+            ptx::sts_v4(rowaddr + ((j ^ sw) << 4), __float_as_uint(__uint_as_float(r[4 * j]) + bv[4 * j]),
+                        __float_as_uint(__uint_as_float(r[4 * j + 1]) + bv[4 * j + 1]), __float_as_uint(__uint_as_float(r[4 * j + 2]) + bv[4 * j + 2]),
+                        __float_as_uint(__uint_as_float(r[4 * j + 3]) + bv[4 * j + 3]));
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_reduce_add_2d(&tmap_x, box, col, row_g);
+            ptx::bulk_commit();
+          }
         }
       }
       // every staging box inside the H buffer has been read before any warp writes the next item's first chunk there
       if (lane == 0) ptx::bulk_wait_read0();
       __syncwarp();
       asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
-      mlp_stamp(args, tl, 0, MLP_TL_CHUNKS - 1, 2);   // item epilogue done
+      mlp_stamp(tl, smem_tl, 62);
     }
     if (lane == 0) ptx::bulk_wait_all0();   // global writes complete before the CTA exits
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (args.timeline != nullptr && blockIdx.x == 0 && threadIdx.x < 64) args.timeline[threadIdx.x] = ptx::lds_u32(smem_tl + 4 * threadIdx.x);
   ptx::cluster_sync_all();   // no CTA leaves while the peer could still address its shared memory / TMEM
   if (warp == 2) {
     ptx::tc_fence_after();

@@ -255,12 +255,27 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
 }
+// the same arrive delivered to the CTAs of `cta_mask` (bit i = cluster rank i): a pair inside a larger cluster notifies only itself
+// (3 << 2 * pair), a resource shared by every pair of the cluster (a multicast operand slot) notifies them all
+__device__ __forceinline__ void umma_commit_2cta_mask(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address -> same offset in the even CTA of the pair
 // TMA load into this CTA's smem whose transaction bytes complete on the LEADER CTA's mbarrier
 __device__ __forceinline__ void tma_load_2d_2cta(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+// The same load multicast to every CTA of `cta_mask`: the box lands at this shared-memory offset in each destination CTA and its
+// bytes complete on the barrier at this offset in the LEADER of each destination's pair (operand tiles shared by the CTA pairs of
+// a 4-CTA cluster cross the L2 -> SM link once)
+__device__ __forceinline__ void tma_load_2d_2cta_mc(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "h"(cta_mask)
       : "memory");
 }
 // arrive on the leader CTA's barrier at this offset (from either CTA of the pair)

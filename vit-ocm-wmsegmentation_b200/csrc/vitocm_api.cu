@@ -460,30 +460,37 @@ int run_gemm_ln(const vitocm_engine* e, const void* A, long long lda, const void
 // ---------------------------------------------------------------------------------- fused MLP launch
 // X[M][D] += gelu(XN . W1^T + b1) . W2^T + b2 in one kernel (mlp_fused_sm100.cuh).  Returns 1 when the shape / engine has no
 // fused instantiation (the caller then runs fc1 and fc2 as separate GEMMs).
-template <int KB1, int EW>
-int launch_mlp_fused(const CUtensorMap& ta, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx, const MlpArgs& a,
+template <int KB1, int CL>
+int launch_mlp_fused(const CUtensorMap& ta, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx, MlpArgs a,
                      int num_sms, cudaStream_t st) {
-  using Cfg = MlpCfg<KB1, EW>;
-  static int max_pairs = -1;
-  auto kern = mlp_fused_tcgen05_kernel<KB1, EW>;
+  using Cfg = MlpCfg<KB1, CL>;
+  static int max_clusters = -1;
+  auto kern = mlp_fused_tcgen05_kernel<KB1, CL>;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (max_pairs < 0) {
+  if (max_clusters < 0) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    cfg.gridDim = dim3(2 * (num_sms / 2));
+    if (CL > 2) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cfg.gridDim = dim3(CL * (num_sms / CL));
     int n = 0;
     CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-    if (n < 1) return fail(VITOCM_ERR_CUDA, "no CTA pair of the fused MLP kernel fits on this device");
-    max_pairs = n < num_sms / 2 ? n : num_sms / 2;
+    if (n < 1) return fail(VITOCM_ERR_CUDA, "no %d-CTA cluster of the fused MLP kernel fits on this device", CL);
+    max_clusters = n < num_sms / CL ? n : num_sms / CL;
   }
   const int tiles = (a.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
-  cfg.gridDim = dim3(2 * (tiles < max_pairs ? tiles : max_pairs));
+  const int groups = (tiles + CL / 2 - 1) / (CL / 2);
+  const int nclusters = groups < max_clusters ? groups : max_clusters;
+  // clusters [groups % nclusters, nclusters) have one work item fewer than the others: they start late, spread over one item's time
+  static const int stagger = [] { const char* v = getenv("VITOCM_MLP_STAGGER"); return v ? atoi(v) : 40000; }();
+  a.stagger_from = (stagger > 0 && groups > nclusters && groups % nclusters != 0) ? groups % nclusters : nclusters;
+  a.stagger_clk = stagger;
+  cfg.gridDim = dim3(CL * nclusters);
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tw1, tw2, tx, a));
   LAUNCH_CHECK();
   return 0;
@@ -492,8 +499,11 @@ int launch_mlp_fused(const CUtensorMap& ta, const CUtensorMap& tw1, const CUtens
 int run_mlp_fused(const vitocm_engine* e, const void* XN, long long ld_xn, const void* W1, long long ldw1, const void* W2, long long ldw2,
                   int M, int D, int Hd, const float* b1, const float* b2, float* X, cudaStream_t st, bool force = false,
                   long long* timeline = nullptr) {
-  // VITOCM_FUSE_MLP: 0 = never, 1 = 16 epilogue warps (default), 8 = 8 epilogue warps
-  static const int mode = [] { const char* v = getenv("VITOCM_FUSE_MLP"); return v == nullptr ? 1 : atoi(v); }();
+  // VITOCM_FUSE_MLP: 0 = never (fc1 and fc2 as separate GEMMs), otherwise the cluster size: 2 (default: one CTA pair per cluster) or
+  // 4 (two pairs share every weight tile through TMA multicast: half the L2 -> SM weight traffic, but measured 5 % SLOWER -- the
+  // kernel is bound by the GELU arithmetic and by shared-memory reads of its N = 128 MMAs, not by the weight stream, and four
+  // CTAs in lockstep lose more than the traffic saves; profiles/r02_mlp_fused.txt)
+  static const int mode = [] { const char* v = getenv("VITOCM_FUSE_MLP"); return v == nullptr ? 2 : atoi(v); }();
   if (mode == 0 && !force) return 1;
   if (e->split || M <= 0 || (D != 128 && D != 384) || Hd % MLP_HC != 0 || b1 == nullptr || b2 == nullptr) return 1;
   if ((reinterpret_cast<uintptr_t>(b1) & 15) != 0 || (reinterpret_cast<uintptr_t>(b2) & 15) != 0) return 1;
@@ -501,14 +511,16 @@ int run_mlp_fused(const vitocm_engine* e, const void* XN, long long ld_xn, const
   CUtensorMap ta, tw1, tw2, tx;
   TRY(make_tmap_bf16(&ta, XN, M, D, ld_xn, GEMM_BM));
   TRY(make_tmap_bf16(&tw1, W1, Hd, D, ldw1, 64));
-  TRY(make_tmap_bf16(&tw2, W2, D, Hd, ldw2, 64));
+  TRY(make_tmap_bf16(&tw2, W2, D, Hd, ldw2, D == 384 ? 96 : 64));   // one CTA's half of a [BN2 x 64] tile: BN2 = 192 at D = 384
   TRY(make_tmap(&tx, X, true, D, M, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
   MlpArgs a{};
   a.M = M; a.hidden = Hd; a.f16 = e->f16; a.gelu_mode = e->f16 ? 2 : 0; a.bias1 = b1; a.bias2 = b2;
   a.timeline = timeline;
+  { static const int dbg = [] { const char* v = getenv("VITOCM_MLP_DEBUG"); return v ? atoi(v) : 0; }(); a.debug = dbg; }
   { static const int tli = [] { const char* v = getenv("VITOCM_MLP_TL_ITEM"); return v ? atoi(v) : 1; }(); a.timeline_item = tli; }
-  if (D == 384) return mode == 8 ? launch_mlp_fused<6, 8>(ta, tw1, tw2, tx, a, e->num_sms, st) : launch_mlp_fused<6, 16>(ta, tw1, tw2, tx, a, e->num_sms, st);
-  return mode == 8 ? launch_mlp_fused<2, 8>(ta, tw1, tw2, tx, a, e->num_sms, st) : launch_mlp_fused<2, 16>(ta, tw1, tw2, tx, a, e->num_sms, st);
+  const bool pair_only = mode != 4;
+  if (D == 384) return pair_only ? launch_mlp_fused<6, 2>(ta, tw1, tw2, tx, a, e->num_sms, st) : launch_mlp_fused<6, 4>(ta, tw1, tw2, tx, a, e->num_sms, st);
+  return pair_only ? launch_mlp_fused<2, 2>(ta, tw1, tw2, tx, a, e->num_sms, st) : launch_mlp_fused<2, 4>(ta, tw1, tw2, tx, a, e->num_sms, st);
 }
 
 // ---------------------------------------------------------------------------------- attention launch
