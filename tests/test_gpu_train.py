@@ -304,3 +304,17 @@ def test_checkpoint_resume_interchanges_with_stock_torch_adamw(tmp_path):
     gn = vob.utils.get_grad_norm(opt)
     assert abs(gn - mim._gflat.double().norm().item()) <= 1e-6 * gn
     assert abs(vob.utils.get_grad_norm(mim.parameters()) - gn) <= 1e-5 * gn
+
+
+def test_backward_after_a_second_forward_fails_loudly():
+    """All saved activations live in one workspace shared by every forward of the model: the backward of a forward that a later
+    training-mode forward has overwritten must raise, not return wrong gradients."""
+    g = load_golden("mim_train_tiny.npz")
+    mim, _ = _tiny_mim(g)
+    x, mask = torch.from_numpy(g["step0/x"]).cuda(), torch.from_numpy(g["step0/mask"]).cuda()
+    loss_a, _, _ = mim(x, mask)
+    loss_b, _, _ = mim(x, mask)
+    with pytest.raises(Exception, match="overwritten"):
+        loss_a.sum().backward()
+    loss_b.sum().backward()          # the latest forward is intact
+    assert all(p.grad is not None for p in mim.parameters())

@@ -143,6 +143,11 @@ struct LayerW {
 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// bytes of a caller workspace [ws, ws + ws_bytes) left after aligning its start up to `base` (0 when the slack alone exceeds it)
+size_t ws_avail(const void* ws, const void* base, size_t ws_bytes) {
+  const size_t slack = reinterpret_cast<uintptr_t>(base) - reinterpret_cast<uintptr_t>(ws);
+  return ws_bytes > slack ? ws_bytes - slack : 0;
+}
 
 }  // namespace
 
@@ -986,7 +991,7 @@ static int forward_rows(vitocm_engine* e, const float* x, int B, int H, int W, c
   if (chunk_tiles <= 0) return fail(VITOCM_ERR_INVALID, "chunk_tiles must be positive");
   if (chunk_tiles > B) chunk_tiles = B;
   uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
-  const size_t avail = ws_bytes - (reinterpret_cast<uintptr_t>(base) - reinterpret_cast<uintptr_t>(ws));
+  const size_t avail = ws_avail(ws, base, ws_bytes);
   const size_t lane_bytes = carve(e, base, chunk_tiles, N).total;
   if (ws == nullptr || lane_bytes > avail) return fail(VITOCM_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", lane_bytes + 1024, ws_bytes);
   // as many concurrent lanes as configured, as the workspace holds, and as there are chunks
@@ -1070,7 +1075,7 @@ int vitocm_block_forward(vitocm_engine* e, int layer, float* X, int B, int n_tok
   TRY(check_engine(e));
   if (layer < 0 || layer >= e->cfg.depth) return fail(VITOCM_ERR_INVALID, "layer %d out of range", layer);
   void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
-  const size_t avail = ws_bytes - (reinterpret_cast<uintptr_t>(base) - reinterpret_cast<uintptr_t>(ws));
+  const size_t avail = ws_avail(ws, base, ws_bytes);
   Workspace wsp = carve(e, base, B, n_tokens);
   if (ws == nullptr || wsp.total > avail) return fail(VITOCM_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", wsp.total + 1024, ws_bytes);
   wsp.X = X;  // operate in place on the caller's token stream
@@ -1085,7 +1090,7 @@ int vitocm_block_attn_probs(vitocm_engine* e, int layer, const float* X, int B, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int D = e->cfg.embed_dim, P = e->parts, S = e->split, heads = e->cfg.num_heads, N = n_tokens;
   void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
-  const size_t avail = ws_bytes - (reinterpret_cast<uintptr_t>(base) - reinterpret_cast<uintptr_t>(ws));
+  const size_t avail = ws_avail(ws, base, ws_bytes);
   const Workspace wsp = carve(e, base, B, N);
   if (ws == nullptr || wsp.total > avail) return fail(VITOCM_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", wsp.total + 1024, ws_bytes);
   const LayerW& L = e->layers[layer];
@@ -1123,11 +1128,14 @@ int vitocm_mim_forward(vitocm_engine* e, const float* x, int B, int H, int W, co
   if (chunk_tiles <= 0) return fail(VITOCM_ERR_INVALID, "chunk_tiles must be positive");
   if (chunk_tiles > B) chunk_tiles = B;
   void* base = reinterpret_cast<void*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
-  const size_t avail = ws_bytes - (reinterpret_cast<uintptr_t>(base) - reinterpret_cast<uintptr_t>(ws));
+  const size_t avail = ws_avail(ws, base, ws_bytes);
   const Workspace wsp = carve(e, base, chunk_tiles, N);
   if (ws == nullptr || wsp.total > avail) return fail(VITOCM_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", wsp.total + 1024, ws_bytes);
   CUDA_TRY(cudaMemsetAsync(loss_sums, 0, 2 * sizeof(double), st));
-  float* Y = reinterpret_cast<float*>(wsp.QKV);   // [M][C p^2] fp32 fits in the QKV slab (3D*parts bf16 per row)
+  // decoder output Y [M][C p^2] fp32 lives where QKV / CTX / HID are (all idle after the last block); it must end inside the carve-up
+  float* Y = reinterpret_cast<float*>(wsp.QKV);
+  if (static_cast<size_t>(chunk_tiles) * N * ldy * sizeof(float) > wsp.total - (reinterpret_cast<uintptr_t>(wsp.QKV) - reinterpret_cast<uintptr_t>(base)))
+    return fail(VITOCM_ERR_WORKSPACE, "decoder output of width %d does not fit behind the token stream of this workspace", ldy);
   for (int b0 = 0; b0 < B; b0 += chunk_tiles) {
     const int bc = (B - b0 < chunk_tiles) ? (B - b0) : chunk_tiles;
     const int M = bc * N;

@@ -130,6 +130,10 @@ class _MIMStep(torch.autograd.Function):
         check(lib.vitocm_mim_train_forward(eng, ptr(xx), B, H, W, ptr(posc), ptr(maskf), ptr(x_rec), ptr(sums), ptr(mim._train_ws),
                                            mim._train_ws.numel(), cur_stream()))
         ctx.mim = mim
+        # the saved activations live in the ONE shared workspace: stamp it, so that a backward whose forward has since been
+        # overwritten by another training-mode forward fails loudly instead of producing wrong gradients
+        mim._train_ws_gen = getattr(mim, "_train_ws_gen", 0) + 1
+        ctx.ws_gen = mim._train_ws_gen
         ctx.save_for_backward(xx, maskf, x_rec, sums)
         ctx.pos_shape = tuple(pos.shape)
         ctx.mark_non_differentiable(x_rec)
@@ -139,6 +143,9 @@ class _MIMStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss, _grad_xrec):
         mim = ctx.mim
+        if ctx.ws_gen != getattr(mim, "_train_ws_gen", 0):
+            raise _lib.VitocmError("MIM backward: the activations of this forward were overwritten by a later training-mode forward "
+                                   "(call backward() before the next forward, or run evaluation under model.eval())")
         xx, maskf, x_rec, sums = ctx.saved_tensors
         B, C, H, W = xx.shape
         mim._prepare_grads()
