@@ -157,7 +157,7 @@ def cpu_value(tiles_per_s, post_s_per_mp, n_tiles, extent):
 
 
 
-def workload_config(arch, n_gpus, precision="fp16", chunk_tiles=175, lanes=1):
+def workload_config(arch, n_gpus, precision="fp16", chunk_tiles=2048, lanes=1):
     """config dict of the segmentation workload at n_gpus ranks -- the SAME keys and strings in the GPU arm and the reference arm."""
     n, size, extent = mosaic_geometry(n_gpus)
     T = n * n
@@ -548,8 +548,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arch", default="vit_small", choices=sorted(ARCHS))
     ap.add_argument("--precision", default="fp16", help="bf16 | fp16 | fp32, optionally +mlp2[:blocks] (vision_transformer.parse_precision)")
-    ap.add_argument("--chunk-tiles", type=int, default=175)
-    ap.add_argument("--tile-batch", type=int, default=175)
+    ap.add_argument("--chunk-tiles", type=int, default=2048, help="most tiles per kernel launch (a rank's whole shard at the default)")
+    ap.add_argument("--tile-batch", type=int, default=2048, help="most tiles per engine call")
     ap.add_argument("--lanes", type=int, default=1, help="chunks in flight on concurrent streams")
     ap.add_argument("--ingest", default="direct", choices=["direct", "crops"], help="segmentation: tiles read out of the uint8 mosaic by the patch embedding, or fp32 crops cut first")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -248,12 +248,12 @@ class MosaicSegmenter:
     """Sliding-window white-matter segmentation of a gray mosaic (SSS/sw_processing.py:223-262).
 
     model: vitocm VisionTransformer (patch 8); window/stride: crop geometry (reference default
-    384/128; BASELINE configs use 224/112); tile_batch: tiles per engine call; group: optional
+    384/128; BASELINE configs use 224/112); tile_batch: most tiles per engine call (the shard is cut into equal calls); group: optional
     torch.distributed process group (NCCL) to shard over -- None = single GPU; ingest: "direct" = the
     patch embedding reads its pixels straight out of the uint8 mosaic, "crops" = fp32 crops are cut first
     (vitocm_extract_tiles); both give the same bits."""
 
-    def __init__(self, model, window=384, stride=128, tile_batch=64, group=None, ingest="direct"):
+    def __init__(self, model, window=384, stride=128, tile_batch=512, group=None, ingest="direct"):
         if ingest not in ("direct", "crops"):
             raise ValueError("ingest must be 'direct' (tiles read out of the mosaic by the patch embedding) or 'crops' (materialised fp32 crops)")
         self.ingest = ingest
@@ -285,8 +285,11 @@ class MosaicSegmenter:
         out = torch.empty(max(t1 - t0, 0), lh * lh, dtype=torch.float32, device=dev)
         direct = self.ingest == "direct" and self.model.in_chans > 1
         xbuf = None if direct else torch.empty(self.tile_batch, C, W, W, dtype=torch.float32, device=dev)
-        for a in range(t0, t1, self.tile_batch):
-            b = min(a + self.tile_batch, t1)
+        # engine calls of (nearly) equal size, none larger than tile_batch: every kernel is a persistent grid over equal work
+        # items, so a short last call would run its partial wave at the cost of a full one
+        calls = max(1, -(-(t1 - t0) // self.tile_batch))
+        bounds = [t0 + (t1 - t0) * i // calls for i in range(calls + 1)]
+        for a, b in zip(bounds[:-1], bounds[1:]):
             if direct:   # the patch-embedding producer reads the uint8 mosaic itself: no crop is materialised
                 rows = self.model.cls_attention_rows_mosaic((mos_ptr, mos_h, mos_w, pitch, dev), n, W, S, a, b - a)
             else:

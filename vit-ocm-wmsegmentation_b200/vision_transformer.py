@@ -168,7 +168,7 @@ class VisionTransformer(nn.Module):
 
     def __init__(self, img_size=[224], patch_size=16, in_chans=3, num_classes=0, embed_dim=768, depth=12,
                  num_heads=12, mlp_ratio=4., qkv_bias=False, qk_scale=None, drop_rate=0., attn_drop_rate=0.,
-                 drop_path_rate=0., norm_layer=nn.LayerNorm, precision="bf16", chunk_tiles=64, lanes=1, **kwargs):
+                 drop_path_rate=0., norm_layer=nn.LayerNorm, precision="bf16", chunk_tiles=512, lanes=1, **kwargs):
         super().__init__()
         if drop_rate or attn_drop_rate or drop_path_rate:
             raise NotImplementedError("vitocm: dropout / drop-path rates must be 0 on this path")
