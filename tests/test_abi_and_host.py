@@ -118,6 +118,16 @@ def _gloo_worker(rank, world, port, tmp):
             assert torch.equal(got, mask)
         else:
             assert got is None
+        # two results of the same shape gathered back to back stay distinct (one receive buffer per tag) -- bands that divide
+        # evenly come back as the receive buffer itself
+        E2 = 36
+        m1 = (torch.rand(E2, 9, generator=g) > 0.5).to(torch.uint8)
+        m2 = 1 - m1
+        z0, z1 = v.shard_range(E2, rank, world)
+        g1 = sw.gather_bands(m1[z0:z1].clone(), E2, rank, world, dst=0, tag="th")
+        g2 = sw.gather_bands(m2[z0:z1].clone(), E2, rank, world, dst=0, tag="th3")
+        if rank == 0:
+            assert torch.equal(g1, m1) and torch.equal(g2, m2)
         mm = torch.tensor([100 + rank, 7 - rank], dtype=torch.int32)
         sw.allreduce_minmax(mm)
         assert mm.tolist() == [100, 7]

@@ -167,9 +167,10 @@ def _cached(key, shape, dtype, device, zero=False):
     return t
 
 
-def allgather_shards(local: torch.Tensor, total: int, rank: int, world: int, group=None) -> torch.Tensor:
+def allgather_shards(local: torch.Tensor, total: int, rank: int, world: int, group=None, tag=None) -> torch.Tensor:
     """Every rank holds items shard_range(total, rank, world) along dim 0; returns all `total`
-    items on every rank (one padded all_gather into a preallocated buffer; NCCL on CUDA, gloo on CPU tensors)."""
+    items on every rank (one padded all_gather into a preallocated buffer; NCCL on CUDA, gloo on CPU tensors).
+    The result may BE that buffer (one per `tag`, shape and dtype): it is overwritten by the next call with the same tag."""
     if world == 1:
         return local.contiguous()
     import torch.distributed as dist
@@ -177,7 +178,7 @@ def allgather_shards(local: torch.Tensor, total: int, rank: int, world: int, gro
     tail = tuple(local.shape[1:])
     pad = _cached("ag_in", (per,) + tail, local.dtype, local.device, zero=True)
     pad[: local.shape[0]] = local
-    full = _cached("ag_out", (world * per,) + tail, local.dtype, local.device)
+    full = _cached(("ag_out", tag), (world * per,) + tail, local.dtype, local.device)
     if local.is_cuda:
         dist.all_gather_into_tensor(full, pad, group=group)
     else:                                            # gloo: list form
@@ -192,9 +193,11 @@ def allgather_shards(local: torch.Tensor, total: int, rank: int, world: int, gro
     return torch.cat(out).contiguous()
 
 
-def gather_bands(band: torch.Tensor, total_rows: int, rank: int, world: int, group=None, dst: int = 0):
+def gather_bands(band: torch.Tensor, total_rows: int, rank: int, world: int, group=None, dst: int = 0, tag=None):
     """Row bands shard_range(total_rows, r, world) -> the full [total_rows, ...] tensor on group rank
-    `dst` (None elsewhere): the final mask gather.  Receive buffers are preallocated views of one tensor."""
+    `dst` (None elsewhere): the final mask gather.  Receive buffers are preallocated views of one tensor per `tag`:
+    the returned tensor IS that buffer when the bands divide evenly, so results that must stay alive side by side
+    (the masks of one segment() call) need distinct tags; a later call with the same tag overwrites it."""
     if world == 1:
         return band
     import torch.distributed as dist
@@ -205,7 +208,7 @@ def gather_bands(band: torch.Tensor, total_rows: int, rank: int, world: int, gro
     else:
         pad = _cached("gb_in", (per,) + tail, band.dtype, band.device, zero=True)
         pad[: band.shape[0]] = band
-    full = _cached(("gb_out", id(group)), (world * per,) + tail, band.dtype, band.device) if rank == dst else None
+    full = _cached(("gb_out", id(group), tag), (world * per,) + tail, band.dtype, band.device) if rank == dst else None
     buf = list(full.view((world, per) + tail).unbind(0)) if rank == dst else None
     gdst = dist.get_global_rank(group, dst) if group is not None else dst
     dist.gather(pad, buf, dst=gdst, group=group)
@@ -350,7 +353,7 @@ class MosaicSegmenter:
         # 1. ViT on this rank's tiles
         t0, t1 = shard_range(T, self.rank, self.world)
         mine = self.lowres_maps((mos_ptr, size, size, pitch, dev), t0, t1)
-        lowres = allgather_shards(mine, T, self.rank, self.world, self.group)
+        lowres = allgather_shards(mine, T, self.rank, self.world, self.group, tag=id(self))
         # 2. this rank's band of output rows
         y0, y1 = shard_range(E, self.rank, self.world)
         gray_band = torch.empty(max(y1 - y0, 1), E, dtype=torch.uint8, device=dev)     # this rank's rows only
@@ -367,7 +370,9 @@ class MosaicSegmenter:
         # 3. final mask gather on rank 0
         if self.world > 1 and gather:
             for k, v in masks.items():
-                full = gather_bands(v, E, self.rank, self.world, self.group, dst=0)
+                # receive buffers belong to this segmenter and this mask: the returned full masks stay valid until THIS
+                # segmenter's next segment() call
+                full = gather_bands(v, E, self.rank, self.world, self.group, dst=0, tag=(id(self), k))
                 if full is not None:
                     out[k] = full
         elif self.world == 1:
