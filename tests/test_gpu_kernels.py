@@ -231,7 +231,7 @@ def _mlp_reference(A, W1, b1, W2, b2, resid, dt):
 
 
 @pytest.mark.parametrize("M,D,Hd", [(785, 384, 1536), (256, 384, 1536), (130, 128, 512), (1, 128, 128), (5000, 384, 1536), (40000, 384, 1536),
-                                    (257, 128, 256)])
+                                    (257, 128, 256), (40000, 128, 384), (60000, 128, 128)])   # odd chunk counts: the epilogue groups swap per item
 @pytest.mark.parametrize("precision", ["bf16", "fp16"])
 def test_mlp_fused(M, D, Hd, precision):
     """fc1 + GELU + fc2 + residual in one kernel (CTA pairs, hidden chunks through TMEM and shared memory): ragged row tiles, one

@@ -1,0 +1,32 @@
+#!/bin/bash
+# round 2, call H: fused MLP with two epilogue groups (fc1 two chunks ahead) and the double-buffered output drain
+mkdir -p gpurun_out
+L=gpurun_out/r2h.log
+: > $L
+timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q --no-header -x -k "mlp_fused" 2>&1 | grep -E "passed|failed|FAILED|Error|error|vitocm:|assert" | head -30 >> $L
+echo "=== mlp bench" >> $L
+for pr in 0 2; do
+  VITOCM_FUSE_MLP=2 PRECISION=$pr timeout 120 python tools/mlp_bench.py 2>&1 | tail -2 >> $L
+done
+echo "=== timeline" >> $L
+for dbg in 0 1 2; do
+  VITOCM_FUSE_MLP=2 PRECISION=2 VITOCM_MLP_DEBUG=$dbg timeout 120 python tools/mlp_timeline.py 2>&1 | tail -16 >> $L
+done
+if [ "$1" != "quick" ]; then
+echo "=== suite" >> $L
+timeout 900 python -m pytest tests -m gpu -q --no-header 2>&1 | grep -E "passed|failed|FAILED|Error|error|vitocm:" | head -40 >> $L
+echo "=== bench" >> $L
+timeout 600 python bench.py --no-extras --no-cpu-baseline > gpurun_out/r2h_bench.json 2> gpurun_out/r2h_bench.err
+tail -3 gpurun_out/r2h_bench.err >> $L
+python - >> $L <<'PY'
+import json
+try:
+    d = json.loads(open("gpurun_out/r2h_bench.json").read().strip().splitlines()[-1])
+    kc = {k: round(v["ms"], 2) for k, v in d["kernel_classes"].items()}
+    print("bench", d["dtype"], round(d["value"], 1), d["unit"], round(d["ms_per_step"], 2), "ms e2e", round(d["e2e"]["value"], 1), kc, d["clocks"])
+except Exception as e:
+    print("bench ERR", repr(e))
+PY
+fi
+echo "=== done" >> $L
+cat $L

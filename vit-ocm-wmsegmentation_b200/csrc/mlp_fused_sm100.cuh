@@ -14,13 +14,22 @@
 //     GELU: Hacc -> registers -> + b1 -> gelu -> 16-bit -> smem H[128 x 128] (two SWIZZLE_128B k-blocks: fc2's A operand)
 //     fc2:  OUT[128 x D] (TMEM)   += H . W2[:, c]^T                       2 x NP2 x 4 MMAs  (M 256, N D/NP2 = 192 at D = 384)
 //   OUT + b2 -> TMA reduce-add into the fp32 residual stream (performed by the L2)
-// Weights stream through a ring of four 24 KB slots, in the order the MMA thread consumes them: fc1(0), fc1(1), fc2(0), fc1(2),
-// fc2(1), ...  A slot holds three fc1 k-blocks ([64 rows x 64 k] per CTA = its half of a [128 x 64] B tile) or the D/NP2-wide output
-// parts of one fc2 k-block: ONE barrier wait and ONE commit per 8-12 MMAs.  (With one 8 KB tile per slot the issuing thread spent
-// ~290 clk per slot on the wait / commit round trip against 256 clk of tensor work: the kernel was MMA-issue bound, and neither a
-// deeper ring nor multicast weights changed its speed -- profiles/r02_mlp_fused.txt.)  TMEM: OUT in columns [0, D), Hacc in [384, 512).
-// Warp roles: 0 = weight TMA, 1 = MMA issuer (leader CTA), 2 = TMEM allocator, 3 = A-tile TMA, 4.. = EW epilogue warps
-// (lane quadrant = warp % 4, column group = (warp - 4) / 4); the first 8 of them also drain OUT through boxes inside the H buffer.
+// Weights stream through a ring of four 16 KB slots, in the order the MMA thread consumes them: fc1(0), fc1(1), fc1(2), fc2(0),
+// fc1(3), fc2(1), ...  A slot holds two fc1 k-blocks ([64 rows x 64 k] per CTA = its half of a [128 x 64] B tile) or one D/NP2-wide
+// output part of one fc2 k-block: ONE barrier wait and ONE commit per 4-8 MMAs.  (With one 8 KB tile per slot the issuing thread
+// spent ~290 clk per slot on the wait / commit round trip against 256 clk of tensor work: the kernel was MMA-issue bound --
+// profiles/r02_mlp_fused.txt.)  TMEM: OUT in columns [0, D), Hacc in [384, 512).
+// Warp roles: 0 = weight TMA, 1 = MMA issuer (leader CTA), 2 = TMEM allocator, 3 = A-tile TMA, 4.. = 16 epilogue warps in TWO
+// GROUPS of 8 (lane quadrant = warp % 4, column half = ((warp - 4) / 4) % 2, group = (warp - 4) / 8).  The groups take the hidden
+// chunks in turn (group = chunk parity); each has its OWN gelu buffer H[g] in shared memory and its own set of barriers, and fc1
+// runs TWO chunks ahead of fc2.  History (profiles/r02_mlp_fused.txt): with all 16 warps on the same chunk and one H buffer the
+// kernel ran at ~4 700 clk per chunk against 3 072 clk of tensor work, with OR without the MMAs and with OR without the GELU
+// arithmetic -- a latency chain (TMEM read, arithmetic, wait for fc2 of the previous chunk to release H, stores, proxy fence,
+// cluster-scope hand-over, fc2, commit), not a throughput limit.  Two groups on one H buffer still serialised on it (stores of
+// chunk n + 1 only after fc2(n) retired, fc2(n + 1) only after the stores: ~4 300 clk).  With a buffer per group the stores of chunk
+// n + 1 overlap fc2(n), and the other group's arithmetic fills the pipes while one group is in the latency-bound part of its chunk.
+// The group that handled an item's LAST chunk drains OUT (double-buffered 32 x 16 fp32 boxes inside its own H buffer) while the
+// other group already works on the next item's first chunk.
 #pragma once
 #include "gemm_sm100.cuh"
 
@@ -54,12 +63,13 @@ __device__ __forceinline__ void mlp_stamp(bool on, uint32_t smem_tl, int idx) {
 }
 
 constexpr int MLP_HC = 128;                 // hidden columns per chunk
-constexpr int MLP_SLOT_BYTES = 3 * 64 * 64 * 2;   // one ring slot: up to three [64 rows x 64 k] weight tiles (24 KB), one mbarrier round trip
+constexpr int MLP_SLOT_BYTES = 2 * 64 * 64 * 2;   // one ring slot: two [64 rows x 64 k] fc1 weight tiles or one fc2 output part (16 KB), one mbarrier round trip
 constexpr int MLP_KB_BYTES = 128 * 64 * 2;  // one [128 x 64] k-block of an A operand
 constexpr int MLP_H_COL = 384;              // TMEM column of the hidden-chunk accumulator
 constexpr int MLP_MAX_SLOTS = 4;
 
-constexpr int MLP_EW = 16;                  // epilogue warps
+constexpr int MLP_EW = 16;                  // epilogue warps: two groups of 8 (4 lane quadrants x 2 column halves of a chunk)
+constexpr int MLP_GW = MLP_EW / 2;          // warps per group
 template <int KB1, int CL>
 struct MlpCfg {
   static constexpr int EW = MLP_EW;
@@ -67,22 +77,25 @@ struct MlpCfg {
   static constexpr int D = KB1 * 64;
   static constexpr int NP2 = (D + 255) / 256;           // output parts, one fc2 MMA each per k step: N = BN2 = D / NP2 (192 at D = 384)
   static constexpr int BN2 = D / NP2;
-  static constexpr int T1 = KB1 % 3 == 0 ? 3 : (KB1 % 2 == 0 ? 2 : 1);   // fc1 k-blocks per ring slot
-  static constexpr int W2_TILE_BYTES = (BN2 / 2) * 128;  // one CTA's half of a [BN2 x 64] fc2 weight tile
-  static_assert(NP2 * W2_TILE_BYTES <= MLP_SLOT_BYTES && T1 * 8192 <= MLP_SLOT_BYTES, "fused MLP: ring slot too small");
+  static constexpr int T1 = KB1 % 2 == 0 ? 2 : 1;       // fc1 k-blocks per ring slot
+  static constexpr int W2_TILE_BYTES = (BN2 / 2) * 128;  // one CTA's half of a [BN2 x 64] fc2 weight tile: one per ring slot
+  static_assert(W2_TILE_BYTES <= MLP_SLOT_BYTES && T1 * 8192 <= MLP_SLOT_BYTES, "fused MLP: ring slot too small");
   static_assert(D % 128 == 0 && D <= 384, "fused MLP: D must be 128, 256 or 384");
   static constexpr int THREADS = (4 + EW) * 32;
   static constexpr int A_BYTES = KB1 * MLP_KB_BYTES;
-  static constexpr int H_BYTES = 2 * MLP_KB_BYTES;      // between items: the 8 output staging boxes (32 x 32 fp32)
+  static constexpr int H_BYTES = 2 * MLP_KB_BYTES;      // one group's gelu buffer [128 x 128]; between items: its 8 x 2 output staging boxes (32 rows x 16 fp32 columns, SWIZZLE_64B)
   static constexpr int BAR_BYTES = 512;
-  static constexpr int FIXED = A_BYTES + H_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
+  static constexpr int FIXED = A_BYTES + 2 * H_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
   static constexpr int SLOTS_FIT = (GEMM_SMEM_LIMIT - FIXED) / MLP_SLOT_BYTES;
   static constexpr int SLOTS = SLOTS_FIT > MLP_MAX_SLOTS ? MLP_MAX_SLOTS : SLOTS_FIT;
   static_assert(SLOTS >= 3, "fused MLP: weight ring too shallow");
   static constexpr int SMEM_BYTES = FIXED + SLOTS * MLP_SLOT_BYTES;
-  // setmaxnreg budgets, EW = 16 only (640 threads x 96 registers at launch): 128 x 48 + 512 x 104 <= 640 x 96
+  // setmaxnreg budgets, EW = 16 only: the pool is what the CTA was launched with (640 threads x 96 registers), so
+  // 128 x REGS_CTRL + 512 x REGS_EPI <= 640 x 96 -- a larger sum leaves setmaxnreg.inc waiting for ever.  An epilogue thread holds 64
+  // accumulator values of its row per chunk.
   static constexpr int REGS_CTRL = 48;
   static constexpr int REGS_EPI = 104;
+  static_assert(4 * REGS_CTRL + EW * REGS_EPI <= (4 + EW) * 96, "fused MLP: setmaxnreg budgets exceed the launch allocation");
 };
 
 template <int KB1, int CL>
@@ -95,19 +108,20 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_h = smem_a + Cfg::A_BYTES;
-  const uint32_t smem_w = smem_h + Cfg::H_BYTES;
+  const uint32_t smem_w = smem_h + 2 * Cfg::H_BYTES;   // smem_h: H[0] | H[1]
   const uint32_t bars = smem_w + SLOTS * MLP_SLOT_BYTES;
   const uint32_t w_full = bars;                       // [SLOTS] TMA -> MMA (leader's copy counts both CTAs' bytes)
   const uint32_t w_empty = bars + 8 * MLP_MAX_SLOTS;  // [SLOTS] MMA -> TMA (both CTAs)
   const uint32_t a_full = bars + 16 * MLP_MAX_SLOTS;  // A tile landed (leader's copy)
   const uint32_t a_empty = a_full + 8;                // last fc1 of the item retired (both CTAs)
-  const uint32_t h_full = a_full + 16;                // fc1 chunk complete in TMEM (both CTAs)
-  const uint32_t h_tmem_empty = a_full + 24;          // epilogue warps of both CTAs read the chunk out of TMEM (leader's copy)
-  const uint32_t h_smem_full = a_full + 32;           // epilogue warps of both CTAs wrote gelu(chunk) to smem (leader's copy)
-  const uint32_t h_smem_empty = a_full + 40;          // fc2 of the chunk retired (both CTAs)
-  const uint32_t out_full = a_full + 48;              // last fc2 of the item retired (both CTAs)
-  const uint32_t out_empty = a_full + 56;             // epilogue warps of both CTAs read OUT out of TMEM (leader's copy)
-  const uint32_t tmem_ptr_smem = a_full + 64;
+  // per epilogue group g (= chunk parity): every barrier below completes once per chunk of that group
+  const uint32_t h_full = a_full + 16;                // [2] fc1 chunk complete in TMEM (both CTAs)
+  const uint32_t h_tmem_empty = a_full + 32;          // [2] the group's warps of both CTAs read the chunk out of TMEM (leader's copy)
+  const uint32_t h_smem_full = a_full + 48;           // [2] the group's warps of both CTAs wrote gelu(chunk) to smem (leader's copy)
+  const uint32_t h_smem_empty = a_full + 64;          // [2] fc2 of the chunk retired (both CTAs)
+  const uint32_t out_full = a_full + 80;              // [2] last fc2 of an item drained by group g retired (both CTAs)
+  const uint32_t out_empty = a_full + 96;             // [2] group g's warps of both CTAs read OUT out of TMEM (leader's copy)
+  const uint32_t tmem_ptr_smem = a_full + 112;
   const uint32_t smem_tl = bars + 256;                // [64] diagnostics stamps
 
   const int warp = threadIdx.x >> 5;
@@ -139,12 +153,16 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     ptx::mbar_init(a_full, 1);
     ptx::mbar_init(a_empty, 1);
-    ptx::mbar_init(h_full, 1);
-    ptx::mbar_init(h_tmem_empty, 2 * EW);
-    ptx::mbar_init(h_smem_full, 2 * EW);
-    ptx::mbar_init(h_smem_empty, 1);
-    ptx::mbar_init(out_full, 1);
-    ptx::mbar_init(out_empty, 2 * 8);
+    for (int g = 0; g < 2; ++g) {
+      ptx::mbar_init(h_full + 8 * g, 1);
+      ptx::mbar_init(h_tmem_empty + 8 * g, 2 * MLP_GW);
+      ptx::mbar_init(h_smem_full + 8 * g, 2 * MLP_GW);
+      ptx::mbar_init(h_smem_empty + 8 * g, 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      ptx::mbar_init(out_full + 8 * g, 1);
+      ptx::mbar_init(out_empty + 8 * g, 2 * MLP_GW);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -194,16 +212,18 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
         };
         auto load_fc2 = [&](int c) {
-          for (int kb2 = 0; kb2 < 2; ++kb2) {
-            if (acquire(NP2 * Cfg::W2_TILE_BYTES))
-              for (int np = 0; np < NP2; ++np) box(&tmap_w2, np * Cfg::W2_TILE_BYTES, c * MLP_HC + kb2 * GEMM_BK, np * BN2 + rank * (BN2 / 2));
-            release();
-          }
+          for (int kb2 = 0; kb2 < 2; ++kb2)
+            for (int np = 0; np < NP2; ++np) {
+              if (acquire(Cfg::W2_TILE_BYTES)) box(&tmap_w2, 0, c * MLP_HC + kb2 * GEMM_BK, np * BN2 + rank * (BN2 / 2));
+              release();
+            }
         };
+        // the order the MMA thread consumes them in: fc1 runs two chunks ahead of fc2
         for (int grp = group0; grp < groups; grp += gstep) {
           load_fc1(0);
+          if (NC > 1) load_fc1(1);
           for (int c = 0; c < NC; ++c) {
-            if (c + 1 < NC) load_fc1(c + 1);
+            if (c + 2 < NC) load_fc1(c + 2);
             load_fc2(c);
           }
         }
@@ -235,8 +255,8 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         int t = 0;
         bool tl = false;
         auto issue_fc1 = [&](int c) {
-          if (g1 > 0) {   // the previous chunk has been read out of the TMEM accumulator
-            ptx::mbar_wait(h_tmem_empty, (g1 - 1) & 1, 33);
+          if (g1 > 0) {   // the previous chunk has been read out of the TMEM accumulator (by the group of its parity)
+            ptx::mbar_wait(h_tmem_empty + 8 * ((g1 - 1) & 1), ((g1 - 1) >> 1) & 1, 33);
             ptx::tc_fence_after();
           }
 #pragma unroll 1
@@ -256,36 +276,41 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             ptx::umma_commit_2cta_mask(w_empty + 8 * slot, all_mask);
             if (++slot == SLOTS) { slot = 0; phase ^= 1; }
           }
-          ptx::umma_commit_2cta_mask(h_full, pair_mask);
+          ptx::umma_commit_2cta_mask(h_full + 8 * (g1 & 1), pair_mask);
           if (c < 12) mlp_stamp(tl, smem_tl, 36 + 2 * c);
+          if (c + 1 == NC) ptx::umma_commit_2cta_mask(a_empty, pair_mask);   // last fc1 of the item: the A tile may be replaced once it retires
           ++g1;
         };
+        int drains[2] = {0, 0};   // items drained so far by each epilogue group
+        int pend_g = 0, pend_par = 0;   // the previous item's drain: group and parity of its out_empty completion
         auto issue_fc2 = [&](int c) {
-          ptx::mbar_wait_cluster(h_smem_full, g2 & 1, 35);   // gelu(chunk) sits in both CTAs' shared memory
+          ptx::mbar_wait_cluster(h_smem_full + 8 * (g2 & 1), (g2 >> 1) & 1, 35);   // gelu(chunk) sits in both CTAs' shared memory
           ptx::tc_fence_after();
           if (c < 12) mlp_stamp(tl, smem_tl, 36 + 2 * c + 1);
-          if (c == 0 && t > 0) {   // OUT still holds the previous item until both CTAs' epilogue warps have read it
-            ptx::mbar_wait(out_empty, (t - 1) & 1, 36);
+          if (c == 0 && t > 0) {   // OUT still holds the previous item until both CTAs' draining warps have read it
+            ptx::mbar_wait(out_empty + 8 * pend_g, pend_par, 36);
             ptx::tc_fence_after();
           }
+          const uint64_t hdesc = ptx::desc_advance(h_desc0, (g2 & 1) * Cfg::H_BYTES);   // this chunk's group's buffer
 #pragma unroll 1
           for (int kb2 = 0; kb2 < 2; ++kb2) {
-            const uint64_t adesc = ptx::desc_advance(h_desc0, kb2 * MLP_KB_BYTES);
-            ptx::mbar_wait(w_full + 8 * slot, phase, 37);
-            ptx::tc_fence_after();
-            const uint64_t bdesc = ptx::desc_advance(w_desc0, slot * MLP_SLOT_BYTES);
-            if (!(args.debug & 1)) {
-#pragma unroll
-              for (int np = 0; np < NP2; ++np)
+            const uint64_t adesc = ptx::desc_advance(hdesc, kb2 * MLP_KB_BYTES);
+#pragma unroll 1
+            for (int np = 0; np < NP2; ++np) {
+              ptx::mbar_wait(w_full + 8 * slot, phase, 37);
+              ptx::tc_fence_after();
+              const uint64_t bdesc = ptx::desc_advance(w_desc0, slot * MLP_SLOT_BYTES);
+              if (!(args.debug & 1)) {
 #pragma unroll
                 for (int k = 0; k < GEMM_BK / 16; ++k)
-                  ptx::umma_bf16_ss_2cta(tmem_base + np * BN2, ptx::desc_advance(adesc, k * 32), ptx::desc_advance(bdesc, np * Cfg::W2_TILE_BYTES + k * 32),
-                                         idesc2, (c > 0 || kb2 > 0 || k > 0) ? 1u : 0u);
+                  ptx::umma_bf16_ss_2cta(tmem_base + np * BN2, ptx::desc_advance(adesc, k * 32), ptx::desc_advance(bdesc, k * 32), idesc2,
+                                         (c > 0 || kb2 > 0 || k > 0) ? 1u : 0u);
+              }
+              ptx::umma_commit_2cta_mask(w_empty + 8 * slot, all_mask);
+              if (++slot == SLOTS) { slot = 0; phase ^= 1; }
             }
-            ptx::umma_commit_2cta_mask(w_empty + 8 * slot, all_mask);
-            if (++slot == SLOTS) { slot = 0; phase ^= 1; }
           }
-          ptx::umma_commit_2cta_mask(h_smem_empty, pair_mask);
+          ptx::umma_commit_2cta_mask(h_smem_empty + 8 * (g2 & 1), pair_mask);
           ++g2;
         };
         for (int grp = group0; grp < groups; grp += gstep, ++t) {
@@ -294,15 +319,16 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           ptx::tc_fence_after();
           mlp_stamp(tl, smem_tl, 60);
           issue_fc1(0);
-          if (NC == 1) ptx::umma_commit_2cta_mask(a_empty, pair_mask);
+          if (NC > 1) issue_fc1(1);
           for (int c = 0; c < NC; ++c) {
-            if (c + 1 < NC) {
-              issue_fc1(c + 1);
-              if (c + 2 == NC) ptx::umma_commit_2cta_mask(a_empty, pair_mask);   // last fc1 of the item: the A tile may be replaced once it retires
-            }
+            if (c + 2 < NC) issue_fc1(c + 2);   // two chunks ahead: one per epilogue group in flight
             issue_fc2(c);
           }
-          ptx::umma_commit_2cta_mask(out_full, pair_mask);
+          // the group that handled the item's last chunk drains it
+          pend_g = (g2 - 1) & 1;
+          pend_par = drains[pend_g] & 1;
+          ++drains[pend_g];
+          ptx::umma_commit_2cta_mask(out_full + 8 * pend_g, pair_mask);
         }
       }
     }
@@ -311,37 +337,43 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_EPI));
     const int ew = warp - 4;
     const int q = warp & 3;          // TMEM lane quadrant
-    const int cg = ew >> 2;          // column group
-    constexpr int CPW = MLP_HC / (EW / 4);   // hidden columns per warp and chunk (32 or 64)
+    const int ch = (ew >> 2) & 1;    // column half of a chunk (GELU) / of OUT (drain)
+    const int grp = ew >> 3;         // epilogue group: takes the chunks whose global index has this parity
+    constexpr int CPW = MLP_HC / 2;          // hidden columns per warp and chunk
     constexpr int NSUB = CPW / 32;
-    constexpr int OCW = D / 2;               // output columns per draining warp (the first 8 epilogue warps drain OUT)
-    constexpr int NOS = OCW / 32;
+    constexpr int OCW = D / 2;               // output columns per draining warp
+    constexpr int NOS = OCW / 16;            // 16-column steps of the drain
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int row = q * 32 + lane;   // row of the CTA's 128
-    // output staging: between items the H buffer holds one 32 x 32 fp32 box for each of the first 8 epilogue warps
-    const uint32_t box = smem_h + (ew & 7) * 4096;
-    int ge = 0;   // chunks processed (all items)
+    const uint32_t my_h = smem_h + grp * Cfg::H_BYTES;   // this group's gelu buffer
+    // output staging: between items that buffer holds two 32 x 16 fp32 boxes (SWIZZLE_64B) for each warp of the group
+    const uint32_t box = my_h + (ew & 7) * 4096;
+    int my_drains = 0;
+    const uint32_t my_h_full = h_full + 8 * grp, my_tmem_empty = h_tmem_empty + 8 * grp;
+    const uint32_t my_smem_full = ptx::mapa(h_smem_full + 8 * grp, crank & ~1);
+    int n0 = 0;   // global index of the item's first chunk (all items of this CTA)
     int t = 0;
-    for (int grp = group0; grp < groups; grp += gstep, ++t) {
-      const int tile = grp * (CL / 2) + pairid;
-      const bool tl = args.timeline != nullptr && blockIdx.x == 0 && t == args.timeline_item && ew == 0 && lane == 0;
-      for (int c = 0; c < NC; ++c, ++ge) {
-        ptx::mbar_wait(h_full, ge & 1, 40);
+    for (int item = group0; item < groups; item += gstep, ++t, n0 += NC) {
+      const int tile = item * (CL / 2) + pairid;
+      const bool tl = args.timeline != nullptr && blockIdx.x == 0 && t == args.timeline_item && (ew & 7) == 0 && lane == 0;
+      for (int c = (n0 + grp) & 1; c < NC; c += 2) {
+        const int n = n0 + c;          // (n & 1) == grp
+        ptx::mbar_wait(my_h_full, (n >> 1) & 1, 40);
         ptx::tc_fence_after();
         if (c < 12) mlp_stamp(tl, smem_tl, 3 * c);
         uint32_t r[NSUB][32];
 #pragma unroll
-        for (int s = 0; s < NSUB; ++s) ptx::tmem_ld_32x32b_x32(lane_taddr + MLP_H_COL + cg * CPW + s * 32, r[s]);
+        for (int s = 0; s < NSUB; ++s) ptx::tmem_ld_32x32b_x32(lane_taddr + MLP_H_COL + ch * CPW + s * 32, r[s]);
 #pragma unroll
         for (int s = 0; s < NSUB; ++s) ptx::tmem_ld_wait(r[s]);
         // the chunk is in registers: the accumulator goes back to the MMA thread (fc1 of the next chunk)
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_leader(h_tmem_empty);
+        if (lane == 0) ptx::mbar_arrive_leader(my_tmem_empty);
         uint32_t pk[NSUB][16];
 #pragma unroll
         for (int s = 0; s < NSUB; ++s) {
-          const float* bp = args.bias1 + c * MLP_HC + cg * CPW + s * 32;
+          const float* bp = args.bias1 + c * MLP_HC + ch * CPW + s * 32;
           float v[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -374,68 +406,70 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             for (int j = 0; j < 16; ++j) asm volatile("" : "+r"(pk[s][j]));
         }
         if (c < 12) mlp_stamp(tl, smem_tl, 3 * c + 1);
-        // the H buffer is free once fc2 of the previous chunk has retired
-        if (ge > 0) ptx::mbar_wait(h_smem_empty, (ge - 1) & 1, 41);
-        if (!(args.debug & 4))
+        // this group's H buffer is free once fc2 of its previous chunk has retired
+        if (n > 1) ptx::mbar_wait(h_smem_empty + 8 * grp, ((n >> 1) - 1) & 1, 41);
+        if (!(args.debug & 4)) {
+          // this thread's 64 columns are one full 128-byte row of k-block `ch` of the H tile
+          const uint32_t tile_addr = my_h + ch * MLP_KB_BYTES + row * 128;
 #pragma unroll
-        for (int s = 0; s < NSUB; ++s) {
-          const int hc = cg * CPW + s * 32;            // first hidden column of this sub-chunk inside the chunk
-          const uint32_t tile_addr = smem_h + (hc >> 6) * MLP_KB_BYTES + row * 128;
-          const int j0 = (hc & 63) >> 3;               // first 16-byte chunk of the row
+          for (int s = 0; s < NSUB; ++s)
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            ptx::sts_v4(tile_addr + (((j0 + j) ^ (row & 7)) << 4), pk[s][4 * j], pk[s][4 * j + 1], pk[s][4 * j + 2], pk[s][4 * j + 3]);
+            for (int j = 0; j < 4; ++j)
+              ptx::sts_v4(tile_addr + (((s * 4 + j) ^ (row & 7)) << 4), pk[s][4 * j], pk[s][4 * j + 1], pk[s][4 * j + 2], pk[s][4 * j + 3]);
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_remote(ptx::mapa(h_smem_full, crank & ~1));
+        if (lane == 0) ptx::mbar_arrive_remote(my_smem_full);
         if (c < 12) mlp_stamp(tl, smem_tl, 3 * c + 2);
       }
-      // ---- item epilogue: OUT + b2 -> fp32 boxes -> TMA reduce-add into the residual stream
-      ptx::mbar_wait(out_full, t & 1, 42);
-      ptx::tc_fence_after();
-      mlp_stamp(tl, smem_tl, 61);
-      const int row_g = tile * 2 * GEMM_BM + rank * GEMM_BM + q * 32;
-      if (ew < 8) {
+      // ---- item epilogue: OUT + b2 -> fp32 boxes -> TMA reduce-add into the residual stream, by the group that handled the item's
+      // LAST chunk (its H buffer is free once that chunk's fc2 -- the item's last MMA -- has retired); the other group goes straight
+      // on to the next item's first chunk
+      if (grp == ((n0 + NC - 1) & 1)) {
+        ptx::mbar_wait(out_full + 8 * grp, my_drains & 1, 42);
+        ++my_drains;
+        ptx::tc_fence_after();
+        mlp_stamp(tl, smem_tl, 61);
+        const int row_g = tile * 2 * GEMM_BM + rank * GEMM_BM + q * 32;
+        const int sw = (lane >> 1) & 3;
 #pragma unroll 1
         for (int s = 0; s < NOS; ++s) {
-          const int col = (ew >> 2) * OCW + s * 32;
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(lane_taddr + col, r);
-          float bv[32];
+          const int col = ch * OCW + s * 16;
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(lane_taddr + col, r);
+          float bv[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias2 + col) + j);
             bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
           }
-          ptx::tmem_ld_wait(r);
+          ptx::tmem_ld_wait16(r);
           if (s == NOS - 1) {   // this warp's part of OUT is in registers
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_leader(out_empty);
+            if (lane == 0) ptx::mbar_arrive_leader(out_empty + 8 * grp);
           }
-          if (lane == 0) ptx::bulk_wait_read0();   // the previous reduce-add has read the box
+          if (lane == 0) ptx::bulk_wait_read1();   // the reduce-add issued two steps ago has read this box
           __syncwarp();
-          const uint32_t rowaddr = box + lane * 128;
-          const int sw = lane & 7;
+          const uint32_t rowaddr = box + (s & 1) * 2048 + lane * 64;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < 4; ++j)
             ptx::sts_v4(rowaddr + ((j ^ sw) << 4), __float_as_uint(__uint_as_float(r[4 * j]) + bv[4 * j]),
                         __float_as_uint(__uint_as_float(r[4 * j + 1]) + bv[4 * j + 1]), __float_as_uint(__uint_as_float(r[4 * j + 2]) + bv[4 * j + 2]),
                         __float_as_uint(__uint_as_float(r[4 * j + 3]) + bv[4 * j + 3]));
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            ptx::tma_reduce_add_2d(&tmap_x, box, col, row_g);
+            ptx::tma_reduce_add_2d(&tmap_x, box + (s & 1) * 2048, col, row_g);
             ptx::bulk_commit();
           }
         }
+        // every staging box inside the H buffer has been read before any warp of this group writes its next chunk there
+        if (lane == 0) ptx::bulk_wait_read0();
+        __syncwarp();
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(MLP_GW * 32) : "memory");
+        mlp_stamp(tl, smem_tl, 62);
       }
-      // every staging box inside the H buffer has been read before any warp writes the next item's first chunk there
-      if (lane == 0) ptx::bulk_wait_read0();
-      __syncwarp();
-      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
-      mlp_stamp(tl, smem_tl, 62);
     }
     if (lane == 0) ptx::bulk_wait_all0();   // global writes complete before the CTA exits
   }
