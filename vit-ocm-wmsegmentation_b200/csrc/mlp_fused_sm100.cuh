@@ -14,8 +14,8 @@
 //     GELU: Hacc -> registers -> + b1 -> gelu -> 16-bit -> smem H[128 x 128] (two SWIZZLE_128B k-blocks: fc2's A operand)
 //     fc2:  OUT[128 x D] (TMEM)   += H . W2[:, c]^T                       2 x NP2 x 4 MMAs  (M 256, N D/NP2 = 192 at D = 384)
 //   OUT + b2 -> TMA reduce-add into the fp32 residual stream (performed by the L2)
-// Weights stream through a ring of four 16 KB slots, in the order the MMA thread consumes them: fc1(0), fc1(1), fc1(2), fc2(0),
-// fc1(3), fc2(1), ...  A slot holds two fc1 k-blocks ([64 rows x 64 k] per CTA = its half of a [128 x 64] B tile) or one D/NP2-wide
+// Weights stream through a ring of four 16 KB slots, in the order the MMA thread consumes them: fc1(0), fc1(1), fc2(0), fc1(2),
+// fc1(3), fc2(1), fc1(4), fc2(2), ...  A slot holds two fc1 k-blocks ([64 rows x 64 k] per CTA = its half of a [128 x 64] B tile) or one D/NP2-wide
 // output part of one fc2 k-block: ONE barrier wait and ONE commit per 4-8 MMAs.  (With one 8 KB tile per slot the issuing thread
 // spent ~290 clk per slot on the wait / commit round trip against 256 clk of tensor work: the kernel was MMA-issue bound --
 // profiles/r02_mlp_fused.txt.)  TMEM: OUT in columns [0, D), Hacc in [384, 512).
@@ -28,7 +28,7 @@
 // cluster-scope hand-over, fc2, commit), not a throughput limit.  Two groups on one H buffer still serialised on it (stores of
 // chunk n + 1 only after fc2(n) retired, fc2(n + 1) only after the stores: ~4 300 clk).  With a buffer per group the stores of chunk
 // n + 1 overlap fc2(n), and the other group's arithmetic fills the pipes while one group is in the latency-bound part of its chunk.
-// The group that handled an item's LAST chunk drains OUT (double-buffered 32 x 16 fp32 boxes inside its own H buffer) while the
+// The group that handled an item's LAST chunk drains OUT (32 x 32 fp32 boxes inside its own H buffer) while the
 // other group already works on the next item's first chunk.
 #pragma once
 #include "gemm_sm100.cuh"
@@ -83,7 +83,7 @@ struct MlpCfg {
   static_assert(D % 128 == 0 && D <= 384, "fused MLP: D must be 128, 256 or 384");
   static constexpr int THREADS = (4 + EW) * 32;
   static constexpr int A_BYTES = KB1 * MLP_KB_BYTES;
-  static constexpr int H_BYTES = 2 * MLP_KB_BYTES;      // one group's gelu buffer [128 x 128]; between items: its 8 x 2 output staging boxes (32 rows x 16 fp32 columns, SWIZZLE_64B)
+  static constexpr int H_BYTES = 2 * MLP_KB_BYTES;      // one group's gelu buffer [128 x 128]; between items: its 8 output staging boxes (32 x 32 fp32, SWIZZLE_128B)
   static constexpr int BAR_BYTES = 512;
   static constexpr int FIXED = A_BYTES + 2 * H_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
   static constexpr int SLOTS_FIT = (GEMM_SMEM_LIMIT - FIXED) / MLP_SLOT_BYTES;
@@ -222,7 +222,9 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int grp = group0; grp < groups; grp += gstep) {
           load_fc1(0);
           if (NC > 1) load_fc1(1);
-          for (int c = 0; c < NC; ++c) {
+          load_fc2(0);
+          if (NC > 2) load_fc1(2);
+          for (int c = 1; c < NC; ++c) {
             if (c + 2 < NC) load_fc1(c + 2);
             load_fc2(c);
           }
@@ -318,10 +320,14 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           ptx::mbar_wait(a_full, t & 1, 38);
           ptx::tc_fence_after();
           mlp_stamp(tl, smem_tl, 60);
+          // fc1 two chunks ahead of fc2 (one chunk per epilogue group in flight), except at the start of an item: fc1(2) needs the
+          // group that is still draining the previous item (it reads chunk 1 afterwards), fc2(0) only that drain's TMEM reads
           issue_fc1(0);
           if (NC > 1) issue_fc1(1);
-          for (int c = 0; c < NC; ++c) {
-            if (c + 2 < NC) issue_fc1(c + 2);   // two chunks ahead: one per epilogue group in flight
+          issue_fc2(0);
+          if (NC > 2) issue_fc1(2);
+          for (int c = 1; c < NC; ++c) {
+            if (c + 2 < NC) issue_fc1(c + 2);
             issue_fc2(c);
           }
           // the group that handled the item's last chunk drains it
@@ -342,11 +348,11 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     constexpr int CPW = MLP_HC / 2;          // hidden columns per warp and chunk
     constexpr int NSUB = CPW / 32;
     constexpr int OCW = D / 2;               // output columns per draining warp
-    constexpr int NOS = OCW / 16;            // 16-column steps of the drain
+    constexpr int NOS = OCW / 32;            // 32-column steps of the drain
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int row = q * 32 + lane;   // row of the CTA's 128
     const uint32_t my_h = smem_h + grp * Cfg::H_BYTES;   // this group's gelu buffer
-    // output staging: between items that buffer holds two 32 x 16 fp32 boxes (SWIZZLE_64B) for each warp of the group
+    // output staging: between items that buffer holds one 32 x 32 fp32 box (SWIZZLE_128B) for each warp of the group
     const uint32_t box = my_h + (ew & 7) * 4096;
     int my_drains = 0;
     const uint32_t my_h_full = h_full + 8 * grp, my_tmem_empty = h_tmem_empty + 8 * grp;
@@ -431,36 +437,38 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         ptx::tc_fence_after();
         mlp_stamp(tl, smem_tl, 61);
         const int row_g = tile * 2 * GEMM_BM + rank * GEMM_BM + q * 32;
-        const int sw = (lane >> 1) & 3;
+        // 32-column boxes (128-byte rows): the TMA unit's reduce-add runs at a fixed rate per box ROW (~4-5 clk), so 64-byte rows
+        // (double-buffered 32 x 16 boxes) made the drain slower, not faster (11.4 k against 8.5 k clk per item)
+        const int sw = lane & 7;
 #pragma unroll 1
         for (int s = 0; s < NOS; ++s) {
-          const int col = ch * OCW + s * 16;
-          uint32_t r[16];
-          ptx::tmem_ld_32x32b_x16(lane_taddr + col, r);
-          float bv[16];
+          const int col = ch * OCW + s * 32;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(lane_taddr + col, r);
+          float bv[32];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 8; ++j) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias2 + col) + j);
             bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
           }
-          ptx::tmem_ld_wait16(r);
+          ptx::tmem_ld_wait(r);
           if (s == NOS - 1) {   // this warp's part of OUT is in registers
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_leader(out_empty + 8 * grp);
           }
-          if (lane == 0) ptx::bulk_wait_read1();   // the reduce-add issued two steps ago has read this box
+          if (lane == 0) ptx::bulk_wait_read0();   // the previous reduce-add has read the box
           __syncwarp();
-          const uint32_t rowaddr = box + (s & 1) * 2048 + lane * 64;
+          const uint32_t rowaddr = box + lane * 128;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < 8; ++j)
             ptx::sts_v4(rowaddr + ((j ^ sw) << 4), __float_as_uint(__uint_as_float(r[4 * j]) + bv[4 * j]),
                         __float_as_uint(__uint_as_float(r[4 * j + 1]) + bv[4 * j + 1]), __float_as_uint(__uint_as_float(r[4 * j + 2]) + bv[4 * j + 2]),
                         __float_as_uint(__uint_as_float(r[4 * j + 3]) + bv[4 * j + 3]));
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            ptx::tma_reduce_add_2d(&tmap_x, box + (s & 1) * 2048, col, row_g);
+            ptx::tma_reduce_add_2d(&tmap_x, box, col, row_g);
             ptx::bulk_commit();
           }
         }

@@ -517,7 +517,7 @@ int run_mlp_fused(const vitocm_engine* e, const void* XN, long long ld_xn, const
   TRY(make_tmap_bf16(&ta, XN, M, D, ld_xn, GEMM_BM));
   TRY(make_tmap_bf16(&tw1, W1, Hd, D, ldw1, 64));
   TRY(make_tmap_bf16(&tw2, W2, D, Hd, ldw2, D == 384 ? 96 : 64));   // one CTA's half of a [BN2 x 64] tile: BN2 = 192 at D = 384
-  TRY(make_tmap(&tx, X, true, D, M, D, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B));   // output staging boxes: 32 rows x 16 fp32 columns
+  TRY(make_tmap(&tx, X, true, D, M, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));   // output staging boxes: 32 rows x 32 fp32 columns
   MlpArgs a{};
   a.M = M; a.hidden = Hd; a.f16 = e->f16; a.gelu_mode = e->f16 ? 2 : 0; a.bias1 = b1; a.bias2 = b2;
   a.timeline = timeline;
