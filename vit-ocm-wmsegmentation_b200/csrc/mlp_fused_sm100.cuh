@@ -56,7 +56,8 @@ struct MlpArgs {
   int stagger_from;
   int stagger_clk;
   int debug;           // diagnostics (VITOCM_MLP_DEBUG): bit 0 = the MMA thread issues no MMAs (barrier traffic only), bit 1 = the
-                       // epilogue skips the GELU arithmetic, bit 2 = the epilogue skips the shared-memory stores of gelu(chunk)
+                       // epilogue skips the GELU arithmetic, bit 2 = the epilogue skips the shared-memory stores of gelu(chunk), bit 3 = the
+                       // output drain issues no TMA reduce-adds (TMEM reads, shared-memory stores and fences only)
 };
 __device__ __forceinline__ void mlp_stamp(bool on, uint32_t smem_tl, int idx) {
   if (on) asm volatile("{\n\t.reg .b32 t;\n\tmov.u32 t, %%clock;\n\tst.shared.b32 [%0], t;\n\t}" ::"r"(smem_tl + 4u * idx) : "memory");
@@ -467,7 +468,7 @@ mlp_fused_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         __float_as_uint(__uint_as_float(r[4 * j + 3]) + bv[4 * j + 3]));
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(args.debug & 8)) {
             ptx::tma_reduce_add_2d(&tmap_x, box, col, row_g);
             ptx::bulk_commit();
           }
