@@ -73,6 +73,8 @@ struct GemmArgs {
   long long mos_pitch;
   int mos_h, mos_w, mos_n, mos_S, mos_t0;
   float* out_f32;           // X [B][1 + n_patches][N] token stream
+  int patch_tma;            // EPI_PATCH_F32: tmap_c = X as 2-D [B (1 + n_patches)][N] and tmap_d = pos [1 + n_patches][N] (fp32, 32 x 32 boxes,
+                            // SWIZZLE_128B) are valid: position rows arrive and token rows leave through per-warp staging boxes
   // EPI_DGELU_BF16 only: the GELU's input saved by the forward fc1 epilogue, bf16 [M][ld_pre]
   const __nv_bfloat16* pre;
   long long ld_pre;
@@ -537,6 +539,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int as = 0;
     uint32_t aphase = 0;
     int ln_tiles = 0;
+    uint32_t patch_phase = 0;   // EPI_PATCH_F32: phase of this warp's position-box barrier
     // EPI_DGELU_BF16: per-warp box for the saved pre-activation tile; the first request goes out before any accumulator is ready
     const uint32_t pre_box = stg_warp + 2 * Cfg::STG_BOX_BYTES;
     uint32_t pre_phase = 0;
@@ -698,6 +701,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       for (int c = 0; c < COLS_PER_WARP; c += 32) {
         const int col = col_base + c;
         if (args.debug >= 2) continue;
+        // EPI_PATCH_F32, staged path: the 32 patch rows of this warp lie inside one image (and inside M), so their position rows
+        // and their token rows are 32 consecutive rows of pos / X: one TMA box in, one out.  (Each lane writing its own 128 bytes
+        // cost 32 partial sectors per store instruction: the kernel ran 6 x above its HBM floor.)  Warps that straddle an image
+        // boundary -- one in ~49 -- keep the per-lane path.
+        bool patch_fast = false;
+        int patch_i0 = 0, patch_b0 = 0;
+        if (EPI == EPI_PATCH_F32) {
+          patch_b0 = row_base / args.n_patches;
+          patch_i0 = row_base - patch_b0 * args.n_patches;
+          patch_fast = args.patch_tma != 0 && row_base + 32 <= args.M && patch_i0 + 32 <= args.n_patches;
+          if (patch_fast && lane == 0) {   // the box was last read (synchronously) by this warp's previous chunk
+            ptx::mbar_arrive_expect_tx(xin_bar + 8 * ew, 4096);
+            ptx::tma_load_2d(stg_warp, &tmap_d, xin_bar + 8 * ew, col, 1 + patch_i0);
+          }
+        }
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN + half * COLS_PER_WARP + c), r);
         float bv[32];
@@ -773,6 +791,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           // token row of patch m = b*n + i is b*(n+1) + 1 + i: the row remap (and the +1 jump at image
           // boundaries inside a chunk) rules out a box store; each lane writes its own 128 contiguous bytes
           const int m = row_base + lane;
+          if (patch_fast) {
+            if (args.mask != nullptr) {
+              const float mk = __ldg(args.mask + m);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = v[j] * (1.f - mk) + __ldg(args.mask_token + col + j) * mk;
+            }
+            const uint32_t posbox = stg_warp + lane * 128, outbox = stg_warp + 4096 + lane * 128;
+            const int sw = lane & 7;
+            ptx::mbar_wait(xin_bar + 8 * ew, patch_phase, 10);
+            patch_phase ^= 1u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 p4 = ptx::lds_v4f(posbox + ((j ^ sw) << 4));
+              v[4 * j] += p4.x; v[4 * j + 1] += p4.y; v[4 * j + 2] += p4.z; v[4 * j + 3] += p4.w;
+            }
+            if (lane == 0) ptx::bulk_wait_read0();   // the previous token box has been read by its store
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              ptx::sts_v4(outbox + ((j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                          __float_as_uint(v[4 * j + 3]));
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&tmap_c, stg_warp + 4096, col, patch_b0 * (args.n_patches + 1) + 1 + patch_i0);
+              ptx::bulk_commit();
+            }
+            continue;
+          }
           if (m < args.M) {
             const int b = m / args.n_patches, i = m - b * args.n_patches;
             if (args.mask != nullptr) {

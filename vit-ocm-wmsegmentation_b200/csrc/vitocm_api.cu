@@ -634,10 +634,18 @@ int run_patch_embed(const vitocm_engine* e, const float* x, int B, int H, int W,
   a.bias = e->w("patch_embed.proj.bias");
   a.img = x; a.img_h = H; a.img_w = W; a.patch = p; a.n_patches = n; a.pos = pos; a.mask = mask; a.mask_token = mask_token; a.out_f32 = X;
   if (mos != nullptr) { a.mos = mos->p; a.mos_pitch = mos->pitch; a.mos_h = mos->h; a.mos_w = mos->w; a.mos_n = mos->n; a.mos_S = mos->S; a.mos_t0 = mos->t0; }
+  // position rows in / token rows out through TMA boxes (VITOCM_PATCH_TMA=0: every lane reads and writes its own 128 bytes)
+  static const int patch_tma = [] { const char* v = getenv("VITOCM_PATCH_TMA"); return v == nullptr ? 1 : atoi(v); }();
+  CUtensorMap tx = tb, tp = tb;
+  if (patch_tma && D % 32 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    TRY(make_tmap(&tx, X, true, D, static_cast<long long>(B) * (n + 1), D, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+    TRY(make_tmap(&tp, pos, true, D, n + 1, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+    a.patch_tma = 1;
+  }
   switch (bn) {
-    case 192: return launch_gemm_inst<192, EPI_PATCH_F32, true>(tb, tb, tb, a, e->num_sms, st);
-    case 128: return launch_gemm_inst<128, EPI_PATCH_F32, true>(tb, tb, tb, a, e->num_sms, st);
-    default: return launch_gemm_inst<64, EPI_PATCH_F32, true>(tb, tb, tb, a, e->num_sms, st);
+    case 192: return launch_gemm_inst<192, EPI_PATCH_F32, true>(tb, tb, tx, a, e->num_sms, st, &tp);
+    case 128: return launch_gemm_inst<128, EPI_PATCH_F32, true>(tb, tb, tx, a, e->num_sms, st, &tp);
+    default: return launch_gemm_inst<64, EPI_PATCH_F32, true>(tb, tb, tx, a, e->num_sms, st, &tp);
   }
 }
 
