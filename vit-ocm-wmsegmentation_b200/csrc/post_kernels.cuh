@@ -190,6 +190,79 @@ __global__ void otsu_kernel(const unsigned long long* __restrict__ hists, int nh
   if (i < nhist) thresholds[i] = otsu_from_hist(hists + static_cast<long long>(i) * 256);
 }
 
+// The same scan, one block of 256 threads per histogram (the mosaic path's three global histograms sit between two full-image
+// passes: one thread walking 256 bins with two fp64 divisions each took 72 us).  Bit-identical to otsu_from_hist:
+//   * total and the weighted sum add integers < 2^53: exact in any order -> tree reductions;
+//   * p_i and i * p_i are independent per bin -> one thread each;
+//   * the recurrence (mu1, q1) is OpenCV's and stays sequential in one thread, but carries ONE division per bin;
+//   * mu2 / sigma of every bin in parallel, then "first bin with the greatest sigma > 0" as an (value, index) reduction.
+__device__ __forceinline__ double otsu_block_sum(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+__global__ void __launch_bounds__(256) otsu_block_kernel(const unsigned long long* __restrict__ hists, int* __restrict__ thresholds) {
+  __shared__ double p[256], ip[256], q1s[256], mu1s[256], red[8];
+  __shared__ int valid[256];
+  __shared__ double best_s[8];
+  __shared__ int best_i[8];
+  const int i = threadIdx.x;
+  const double h = static_cast<double>(hists[static_cast<long long>(blockIdx.x) * 256 + i]);
+  const double total = otsu_block_sum(h, red);
+  const double wsum = otsu_block_sum(static_cast<double>(i) * h, red);
+  if (total <= 0.0) {
+    if (i == 0) thresholds[blockIdx.x] = 0;
+    return;
+  }
+  const double scale = 1.0 / total;
+  const double mu = __dmul_rn(wsum, scale);
+  const double p_i = __dmul_rn(h, scale);
+  p[i] = p_i;
+  ip[i] = __dmul_rn(static_cast<double>(i), p_i);
+  __syncthreads();
+  if (i == 0) {
+    const double eps = 1.1920928955078125e-07;
+    double mu1 = 0.0, q1 = 0.0;
+    for (int k = 0; k < 256; ++k) {
+      mu1 = __dmul_rn(mu1, q1);
+      q1 = __dadd_rn(q1, p[k]);
+      const double q2 = __dsub_rn(1.0, q1);
+      if (fmin(q1, q2) < eps || fmax(q1, q2) > 1.0 - eps) { valid[k] = 0; continue; }
+      mu1 = __ddiv_rn(__dadd_rn(mu1, ip[k]), q1);
+      q1s[k] = q1;
+      mu1s[k] = mu1;
+      valid[k] = 1;
+    }
+  }
+  __syncthreads();
+  double sigma = -1.0;
+  if (valid[i]) {
+    const double q1 = q1s[i], mu1 = mu1s[i];
+    const double q2 = __dsub_rn(1.0, q1);
+    const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
+    const double dm = __dsub_rn(mu1, mu2);
+    sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), dm), dm);
+    if (!(sigma > 0.0)) sigma = -1.0;   // the scan only accepts sigma > max_sigma >= 0 (NaN never wins)
+  }
+  int idx = i;
+  for (int o = 16; o > 0; o >>= 1) {
+    const double s2 = __shfl_xor_sync(0xffffffffu, sigma, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (s2 > sigma || (s2 == sigma && i2 < idx)) { sigma = s2; idx = i2; }
+  }
+  if ((i & 31) == 0) { best_s[i >> 5] = sigma; best_i[i >> 5] = idx; }
+  __syncthreads();
+  if (i == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (best_s[w] > sigma || (best_s[w] == sigma && best_i[w] < idx)) { sigma = best_s[w]; idx = best_i[w]; }
+    thresholds[blockIdx.x] = sigma > 0.0 ? idx : 0;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Per-image threshold (eval / PGT flavour).  One block per tile, three passes over the tile:
 //   1. att = bilinear_up(lowres) ; block min / max
@@ -355,6 +428,108 @@ stitch_gray_kernel(const uint8_t* __restrict__ mosaic, int mos_h, int mos_w, lon
       }
       res[u] = v;
       if (++r == g.S) { r = 0; ++q; }
+    }
+    const long long o = static_cast<long long>(Y) * g.E + X0;
+    if (V == 4) *reinterpret_cast<uchar4*>(out + o) = make_uchar4(res[0], res[1 % V], res[2 % V], res[3 % V]);
+    else out[o] = res[0];
+  }
+}
+
+// tiles covering coordinate P = q * S + r (q = P / S): [c0, c1]
+__device__ __forceinline__ void cover_range(const StitchGeom& g, int q, int r, int dW, int eW, int& c0, int& c1) {
+  c1 = min(q, g.n - 1);
+  c0 = q + 1 - dW - (r < eW ? 1 : 0);      // = (P - W + S) / S for P >= W - S ... clamped below
+  if (c0 < 0) c0 = 0;
+}
+
+// Column-strip form of stitch_gray_kernel (same structure as stitch_strip_kernel below): a thread owns V adjacent columns over a
+// band of SC_ROWS consecutive rows; its horizontal blend weights are computed once, the vertical ones once per row by one thread.
+// Same blend sequence per pixel (bit-identical); the row-organised kernel re-derived both per pixel (~100 instructions).
+constexpr int SG_THREADS = 256;
+constexpr int SG_ROWS = 32;
+__device__ __forceinline__ uint8_t blend_u8_pre(uint8_t a, uint8_t b, double w, double omw) {   // blend_u8 with 1 - w precomputed
+  return static_cast<uint8_t>(static_cast<int>(__dadd_rn(__dmul_rn(static_cast<double>(a), w), __dmul_rn(static_cast<double>(b), omw))));
+}
+template <int V, int MC>
+__global__ void __launch_bounds__(SG_THREADS)
+stitch_gray_strip_kernel(const uint8_t* __restrict__ mosaic, int mos_h, int mos_w, long long pitch, StitchGeom g,
+                         const double* __restrict__ wtab, int y_begin, int y_end, uint8_t* __restrict__ out /*[E][E]*/) {
+  constexpr int NS = MC - 1;   // blend steps per direction
+  __shared__ int s_n[SG_ROWS];
+  __shared__ int s_bl[SG_ROWS][NS];
+  __shared__ double s_w[SG_ROWS][NS], s_omw[SG_ROWS][NS];
+  const int yb = y_begin + blockIdx.y * SG_ROWS;
+  const int nrows = min(SG_ROWS, y_end - yb);
+  const int dW = g.W / g.S, eW = g.W % g.S;
+  if (static_cast<int>(threadIdx.x) < nrows) {
+    const int Y = yb + threadIdx.x;
+    const int qy = Y / g.S, ry = Y - qy * g.S;
+    int i0, i1;
+    cover_range(g, qy, ry, dW, eW, i0, i1);
+    int nb = i1 - i0;
+    if (nb > NS) nb = NS;
+    s_n[threadIdx.x] = nb;
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2) {
+      if (s2 < nb) {
+        const int ky = Y - (i0 + 1 + s2) * g.S;
+        const int bl = ky < g.step ? 1 : 0;
+        const double w = bl ? wtab[ky] : 0.0;
+        s_bl[threadIdx.x][s2] = bl;
+        s_w[threadIdx.x][s2] = w;
+        s_omw[threadIdx.x][s2] = __dsub_rn(1.0, w);
+      }
+    }
+  }
+  __syncthreads();
+  const int X0 = (blockIdx.x * SG_THREADS + threadIdx.x) * V;
+  if (X0 >= g.E) return;
+  int nbx[V], blx[V][NS];
+  double wx[V][NS], omwx[V][NS];
+  {
+    int q = X0 / g.S, r = X0 - q * g.S;
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      int j0, j1;
+      cover_range(g, q, r, dW, eW, j0, j1);
+      nbx[u] = min(j1 - j0, NS);
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) {
+        blx[u][s2] = 0; wx[u][s2] = 0.0; omwx[u][s2] = 1.0;
+        if (s2 < nbx[u]) {
+          const int kx = (q - (j0 + 1 + s2)) * g.S + r;
+          blx[u][s2] = kx < g.step ? 1 : 0;
+          wx[u][s2] = blx[u][s2] ? wtab[kx] : 0.0;
+          omwx[u][s2] = __dsub_rn(1.0, wx[u][s2]);
+        }
+      }
+      if (++r == g.S) { r = 0; ++q; }
+    }
+  }
+  const bool vec_in = V == 4 && X0 + 4 <= mos_w && ((reinterpret_cast<uintptr_t>(mosaic) | static_cast<uintptr_t>(pitch)) & 3) == 0;
+  for (int t = 0; t < nrows; ++t) {
+    const int Y = yb + t;
+    uint8_t src[V];
+    if (Y < mos_h && vec_in) {
+      const uchar4 b = *reinterpret_cast<const uchar4*>(mosaic + Y * pitch + X0);
+      src[0] = b.x; src[1 % V] = b.y; src[2 % V] = b.z; src[3 % V] = b.w;
+    } else {
+#pragma unroll
+      for (int u = 0; u < V; ++u) src[u] = (Y < mos_h && X0 + u < mos_w) ? __ldg(mosaic + Y * pitch + X0 + u) : 0;   // zero beyond the mosaic
+    }
+    const int nb = s_n[t];
+    uint8_t res[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      uint8_t hv = src[u];   // every crop holds the same source pixel: the horizontal sequence is identical for every strip
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2)
+        if (s2 < nbx[u]) hv = blx[u][s2] ? blend_u8_pre(hv, src[u], wx[u][s2], omwx[u][s2]) : src[u];
+      uint8_t v = hv;
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2)
+        if (s2 < nb) v = s_bl[t][s2] ? blend_u8_pre(v, hv, s_w[t][s2], s_omw[t][s2]) : hv;
+      res[u] = v;
     }
     const long long o = static_cast<long long>(Y) * g.E + X0;
     if (V == 4) *reinterpret_cast<uchar4*>(out + o) = make_uchar4(res[0], res[1 % V], res[2 % V], res[3 % V]);
@@ -546,13 +721,6 @@ __device__ __forceinline__ float bilinear_tab(const float* __restrict__ lo, int 
   return __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, fy));
 }
 
-// tiles covering coordinate P = q * S + r (q = P / S): [c0, c1]
-__device__ __forceinline__ void cover_range(const StitchGeom& g, int q, int r, int dW, int eW, int& c0, int& c1) {
-  c1 = min(q, g.n - 1);
-  c0 = q + 1 - dW - (r < eW ? 1 : 0);      // = (P - W + S) / S for P >= W - S ... clamped below
-  if (c0 < 0) c0 = 0;
-}
-
 // stitched value at (row context, X): same evaluation order as stitched_value()
 struct RowCtx {
   int i0, i1;
@@ -647,6 +815,147 @@ stitch_minmax_kernel(const float* __restrict__ lowres, StitchGeom g, const doubl
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < ST_THREADS / 32; ++w) { mn = fminf(mn, red_mn[w]); mx = fmaxf(mx, red_mx[w]); }
+    if (mn <= mx) {
+      atomicMin(&minmax_ord[0], f2ord(mn));
+      atomicMax(&minmax_ord[1], f2ord(mx));
+    }
+  }
+}
+
+// pass 1, column-strip form (the default when the map is stitched from the low-res maps): a thread owns ONE column X over a band
+// of SC_ROWS consecutive rows.  Everything that depends on X only (covering tile columns, horizontal bilinear coefficients,
+// horizontal blend weights) is computed once per thread; everything that depends on the row only once per row by one thread
+// (shared memory); and the horizontal lerps r0 / r1 of bilinear_tab -- which depend on (tile, y0, y1, X) -- stay in registers
+// while consecutive rows sample the same pair of low-res rows (8 rows at scale 1/8): per pixel and covering tile that leaves two
+// multiplies and an add, plus the fp64 blends.  Same operations in the same order as stitched_value_row (every product and sum
+// rounded separately), so the map is bit-identical; the row-organised kernel above needed ~350 instructions per pixel
+// (264 us per 4032^2 map), most of them re-deriving these invariants.
+constexpr int SC_THREADS = 256;
+constexpr int SC_ROWS = 32;
+template <int MC>
+struct StripRow {
+  int ni;                      // covering tile rows
+  int base0[MC], base1[MC];    // element offsets of low-res rows y0 / y1 of tile row i0 + k (tile column 0)
+  float fy[MC], b0[MC];
+  int blend[MC];               // k > 0 && ky < step
+  double w[MC], omw[MC];
+};
+__device__ __forceinline__ float blend_f32_pre(float a, float b, double w, double omw) {   // blend_f32 with 1 - w precomputed
+  return static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(a), w), __dmul_rn(static_cast<double>(b), omw)));
+}
+template <int MC>
+__global__ void __launch_bounds__(SC_THREADS)
+stitch_strip_kernel(const float* __restrict__ lowres, StitchGeom g, const double* __restrict__ wtab, int y_begin, int y_end,
+                    int* __restrict__ minmax_ord, float* __restrict__ map_out /*[E][E] or null*/) {
+  __shared__ StripRow<MC> rows[SC_ROWS];
+  __shared__ float red_mn[SC_THREADS / 32], red_mx[SC_THREADS / 32];
+  const int yb = y_begin + blockIdx.y * SC_ROWS;
+  const int nrows = min(SC_ROWS, y_end - yb);
+  const int dW = g.W / g.S, eW = g.W % g.S;
+  const int lsz = g.lh * g.lw;
+  if (static_cast<int>(threadIdx.x) < nrows) {
+    const int Y = yb + threadIdx.x;
+    StripRow<MC>& R = rows[threadIdx.x];
+    const int q = Y / g.S, r = Y - q * g.S;
+    int i0, i1;
+    cover_range(g, q, r, dW, eW, i0, i1);
+    if (i1 - i0 > MC - 1) i1 = i0 + MC - 1;
+    R.ni = i1 - i0 + 1;
+#pragma unroll
+    for (int k = 0; k < MC; ++k) {
+      if (k < R.ni) {
+        const int i = i0 + k, ky = Y - i * g.S;
+        int y0, y1;
+        float fy;
+        linear_coeff(ky, g.scale, g.lh, y0, y1, fy);
+        R.base0[k] = i * g.n * lsz + y0 * g.lw;
+        R.base1[k] = i * g.n * lsz + y1 * g.lw;
+        R.fy[k] = fy;
+        R.b0[k] = __fsub_rn(1.0f, fy);
+        R.blend[k] = (k > 0 && ky < g.step) ? 1 : 0;
+        const double w = R.blend[k] ? wtab[ky] : 0.0;
+        R.w[k] = w;
+        R.omw[k] = __dsub_rn(1.0, w);
+      }
+    }
+  }
+  __syncthreads();
+  const int X = blockIdx.x * SC_THREADS + threadIdx.x;
+  const bool live = X < g.E;
+  int nj = 0;
+  int o0[MC], o1[MC], bl[MC];
+  float fx[MC], a0[MC];
+  double wx[MC], omwx[MC];
+  if (live) {
+    const int q = X / g.S, r = X - q * g.S;
+    int j0, j1;
+    cover_range(g, q, r, dW, eW, j0, j1);
+    if (j1 - j0 > MC - 1) j1 = j0 + MC - 1;
+    nj = j1 - j0 + 1;
+#pragma unroll
+    for (int jj = 0; jj < MC; ++jj) {
+      if (jj < nj) {
+        const int j = j0 + jj, kx = (q - j) * g.S + r;
+        int s0, s1;
+        linear_coeff(kx, g.scale, g.lw, s0, s1, fx[jj]);
+        a0[jj] = __fsub_rn(1.0f, fx[jj]);
+        o0[jj] = j * lsz + s0;
+        o1[jj] = j * lsz + s1;
+        bl[jj] = (jj > 0 && kx < g.step) ? 1 : 0;
+        wx[jj] = bl[jj] ? wtab[kx] : 0.0;
+        omwx[jj] = __dsub_rn(1.0, wx[jj]);
+      }
+    }
+  }
+  float r0c[MC][MC], r1c[MC][MC];
+  int cb0[MC], cb1[MC];
+#pragma unroll
+  for (int k = 0; k < MC; ++k) { cb0[k] = -1; cb1[k] = -1; }
+  float mn = INFINITY, mx = -INFINITY;
+  for (int t = 0; t < nrows; ++t) {
+    const StripRow<MC>& R = rows[t];
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < MC; ++k) {
+      if (k < R.ni) {
+        if (R.base0[k] != cb0[k] || R.base1[k] != cb1[k]) {   // (block-uniform) this slot samples other low-res rows than on the previous row
+          cb0[k] = R.base0[k];
+          cb1[k] = R.base1[k];
+          const float* p0 = lowres + cb0[k];
+          const float* p1 = lowres + cb1[k];
+#pragma unroll
+          for (int jj = 0; jj < MC; ++jj) {
+            if (jj < nj) {
+              r0c[k][jj] = __fadd_rn(__fmul_rn(__ldg(p0 + o0[jj]), a0[jj]), __fmul_rn(__ldg(p0 + o1[jj]), fx[jj]));
+              r1c[k][jj] = __fadd_rn(__fmul_rn(__ldg(p1 + o0[jj]), a0[jj]), __fmul_rn(__ldg(p1 + o1[jj]), fx[jj]));
+            }
+          }
+        }
+        float hv = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < MC; ++jj) {
+          if (jj < nj) {
+            const float tv = __fadd_rn(__fmul_rn(r0c[k][jj], R.b0[k]), __fmul_rn(r1c[k][jj], R.fy[k]));
+            hv = bl[jj] ? blend_f32_pre(hv, tv, wx[jj], omwx[jj]) : tv;
+          }
+        }
+        v = R.blend[k] ? blend_f32_pre(v, hv, R.w[k], R.omw[k]) : hv;
+      }
+    }
+    if (live) {
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
+      if (map_out != nullptr) map_out[static_cast<long long>(yb + t) * g.E + X] = v;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { red_mn[threadIdx.x >> 5] = mn; red_mx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < SC_THREADS / 32; ++w) { mn = fminf(mn, red_mn[w]); mx = fmaxf(mx, red_mx[w]); }
     if (mn <= mx) {
       atomicMin(&minmax_ord[0], f2ord(mn));
       atomicMax(&minmax_ord[1], f2ord(mx));

@@ -1292,6 +1292,16 @@ int vitocm_stitch_gray(const uint8_t* mosaic, int mos_h, int mos_w, int64_t pitc
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope prof(PC_POST, st);
   const StitchLaunch L = stitch_launch(g.E, y_end - y_begin, device_sms(), {}, {out});
+  static const int strip = [] { const char* v = getenv("VITOCM_STITCH_STRIP"); return v == nullptr ? 1 : atoi(v); }();
+  if (strip) {   // column-strip kernels (VITOCM_STITCH_STRIP=0: the row-organised ones)
+    const dim3 grid((g.E + SG_THREADS * L.V - 1) / (SG_THREADS * L.V), (y_end - y_begin + SG_ROWS - 1) / SG_ROWS);
+    if (L.V == 4 && W <= 2 * S) stitch_gray_strip_kernel<4, 2><<<grid, SG_THREADS, 0, st>>>(mosaic, mos_h, mos_w, pitch, g, wtab, y_begin, y_end, out);
+    else if (L.V == 4) stitch_gray_strip_kernel<4, 4><<<grid, SG_THREADS, 0, st>>>(mosaic, mos_h, mos_w, pitch, g, wtab, y_begin, y_end, out);
+    else if (W <= 2 * S) stitch_gray_strip_kernel<1, 2><<<grid, SG_THREADS, 0, st>>>(mosaic, mos_h, mos_w, pitch, g, wtab, y_begin, y_end, out);
+    else stitch_gray_strip_kernel<1, 4><<<grid, SG_THREADS, 0, st>>>(mosaic, mos_h, mos_w, pitch, g, wtab, y_begin, y_end, out);
+    LAUNCH_CHECK();
+    return 0;
+  }
   if (L.V == 4) stitch_gray_kernel<4><<<L.grid, 256, 0, st>>>(mosaic, mos_h, mos_w, pitch, g, wtab, y_begin, y_end, out);
   else stitch_gray_kernel<1><<<L.grid, 256, 0, st>>>(mosaic, mos_h, mos_w, pitch, g, wtab, y_begin, y_end, out);
   LAUNCH_CHECK();
@@ -1312,6 +1322,15 @@ int vitocm_stitch_minmax(const float* lowres, int n, int W, int S, int lh, int l
   const StitchGeom g = make_geom(n, W, S, lh, lw);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope prof(PC_POST, st);
+  // stitched from the low-res maps: column-strip kernel (VITOCM_STITCH_STRIP=0: the row-organised one)
+  static const int strip = [] { const char* v = getenv("VITOCM_STITCH_STRIP"); return v == nullptr ? 1 : atoi(v); }();
+  if (map_in == nullptr && strip) {
+    const dim3 grid((g.E + SC_THREADS - 1) / SC_THREADS, (y_end - y_begin + SC_ROWS - 1) / SC_ROWS);
+    if (W <= 2 * S) stitch_strip_kernel<2><<<grid, SC_THREADS, 0, st>>>(lowres, g, wtab, y_begin, y_end, minmax_ord, map_out);
+    else stitch_strip_kernel<4><<<grid, SC_THREADS, 0, st>>>(lowres, g, wtab, y_begin, y_end, minmax_ord, map_out);
+    LAUNCH_CHECK();
+    return 0;
+  }
   const StitchLaunch L = stitch_launch(g.E, y_end - y_begin, device_sms(), {map_out, map_in}, {});
   if (L.V == 4) stitch_minmax_kernel<4><<<L.grid, ST_THREADS, 0, st>>>(lowres, g, wtab, y_begin, y_end, minmax_ord, map_out, map_in);
   else stitch_minmax_kernel<1><<<L.grid, ST_THREADS, 0, st>>>(lowres, g, wtab, y_begin, y_end, minmax_ord, map_out, map_in);
@@ -1338,7 +1357,7 @@ int vitocm_stitch_hist(const float* lowres, int n, int W, int S, int lh, int lw,
 int vitocm_otsu(const uint64_t* hists, int nhist, int* thresholds, void* stream) {
   if (nhist <= 0) return 0;
   ProfScope prof(PC_POST, static_cast<cudaStream_t>(stream));
-  otsu_kernel<<<(nhist + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const unsigned long long*>(hists), nhist, thresholds);
+  otsu_block_kernel<<<nhist, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const unsigned long long*>(hists), thresholds);
   LAUNCH_CHECK();
   return 0;
 }
