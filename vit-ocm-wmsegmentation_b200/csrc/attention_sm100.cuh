@@ -58,6 +58,8 @@ struct AttnArgs {
                         // 2^ATT_SUM_TRIGGER no single exponential can have overflowed the 16-bit P format, and a stale maximum is
                         // exact otherwise (softmax is shift invariant, O and l accumulate in fp32).  Only a block that trips
                         // the trigger pays for row_max(), the rescale of O and a second pass of exponentials.
+  int tails_only;       // 1 = the launch covers only the ragged query tail of every pair (item i = the tail item of group i); the full
+                        // tiles are computed by attn_fwd_quad_kernel (attention_quad_sm100.cuh)
   int timeline_item;    // diagnostics: which of a CTA's work items (0, 1, ...) the stamps are taken on
   long long* timeline;  // diagnostics (vitocm_attention_timeline) or nullptr: clock64 stamps of CTAs (0,0,0) and (1,0,0)
 };
@@ -106,6 +108,12 @@ struct AttnCfg {
 // work item -> (query tile, first pair, packed?); false = the item does not exist (pair beyond the batch in the last group)
 template <bool PACKED>
 __device__ __forceinline__ bool att_decode(const AttnArgs& a, int it, int& qt, int& pair0, bool& packed) {
+  if (a.tails_only) {   // item = the tail of group `it` (one pair, or `pack` pairs sharing a tile)
+    pair0 = it * a.pack;
+    qt = a.n_fullq;
+    packed = PACKED && a.pack > 1;
+    return pair0 < a.n_pairs;
+  }
   if (!PACKED) {   // launches without packed items (pack == 1): query tile fastest, then the pair; every item exists
     pair0 = it / a.n_qtiles;
     qt = it - pair0 * a.n_qtiles;

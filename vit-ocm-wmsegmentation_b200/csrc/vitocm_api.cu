@@ -17,6 +17,7 @@
 #include "attention_bwd_sm100.cuh"
 #include "attention_sm100.cuh"
 #include "gemm_sm100.cuh"
+#include "attention_quad_sm100.cuh"
 #include "mlp_fused_sm100.cuh"
 #include "post_kernels.cuh"
 #include "train_kernels.cuh"
@@ -555,6 +556,31 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
   const long long items = static_cast<long long>((a.n_pairs + a.pack - 1) / a.pack) * a.group_items;
   if (items > 0x7fffffffLL) return fail(VITOCM_ERR_INVALID, "attention: too many work items");
   a.n_items = static_cast<int>(items);
+  // 16-bit engines, inference: the full query tiles go through the four-pipeline kernel (attention_quad_sm100.cuh), the ragged
+  // tails through the packed items of the kernel below (VITOCM_ATTN_QUAD=0: everything through the kernel below)
+  static const int quad = [] { const char* v = getenv("VITOCM_ATTN_QUAD"); return v ? atoi(v) : 1; }();
+  if (quad && !e->split && lse2 == nullptr && timeline == nullptr && a.n_fullq >= 1) {
+    const long long full_items = static_cast<long long>(a.n_pairs) * a.n_fullq;
+    if (full_items > 0x7fffffffLL) return fail(VITOCM_ERR_INVALID, "attention: too many work items");
+    AttnArgs aq = a;
+    aq.n_items = static_cast<int>(full_items);
+    CUtensorMap tkv;
+    TRY(make_tmap_bf16(&tkv, qkv, M, 3LL * D * e->parts, ld, AQ_BKV));
+    const int ctas = (aq.n_items + AQ_PIPES - 1) / AQ_PIPES;
+    const dim3 qgrid(ctas < e->num_sms ? ctas : e->num_sms);
+    static bool qattr[2] = {false, false};
+    if (e->f16) {
+      if (!qattr[1]) { CUDA_TRY(cudaFuncSetAttribute(attn_fwd_quad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AQ_SMEM_BYTES)); qattr[1] = true; }
+      attn_fwd_quad_kernel<true><<<qgrid, AQ_THREADS, AQ_SMEM_BYTES, st>>>(tq, tkv, aq);
+    } else {
+      if (!qattr[0]) { CUDA_TRY(cudaFuncSetAttribute(attn_fwd_quad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AQ_SMEM_BYTES)); qattr[0] = true; }
+      attn_fwd_quad_kernel<false><<<qgrid, AQ_THREADS, AQ_SMEM_BYTES, st>>>(tq, tkv, aq);
+    }
+    LAUNCH_CHECK();
+    if (tail == 0) return 0;
+    a.tails_only = 1;
+    a.n_items = (a.n_pairs + a.pack - 1) / a.pack;
+  }
   // persistent CTAs: as many as are co-resident (2 per SM in bf16 mode, 1 in split mode)
   const int resident = e->num_sms * (e->split ? 1 : 2);
   static const int persist = [] { const char* v = getenv("VITOCM_ATTN_PERSISTENT"); return v ? atoi(v) : 1; }();
