@@ -37,7 +37,7 @@ static_assert(AQ_SMEM_BYTES <= 227 * 1024, "quad attention: shared memory");
 constexpr int AQ_S_COL = 0;     // S: 64 fp32 columns; P (packed pairs, 32 columns) over its first half
 constexpr int AQ_O_COL = 64;    // O: 64 fp32 columns
 
-template <bool F16>
+template <bool F16, bool TL = false>   // TL: clock stamps of tools/attn_quad_timeline.py (a separate instantiation: the stamps cost registers)
 __global__ void __launch_bounds__(AQ_THREADS, 1)
 attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/, const __grid_constant__ CUtensorMap tmap_kv /*box 64 x 64*/,
                      const AttnArgs args) {
@@ -141,30 +141,34 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
       };
       if (first < args.n_items) load_q(first);
       fill();
+      // S_j = Q K_j^T into the columns that held P_{j-1}: it is issued right BEHIND PV_{j-1} (the tensor pipe executes in order, so
+      // PV_{j-1} has read P before S_j lands on it), never behind a wait for PV_{j-1} to retire -- ring refills come after the issue
+      auto issue_s = [&](int j) {
+        const int slot = used % AQ_RING;
+        ptx::mbar_wait(kv_full + 8 * slot, (used / AQ_RING) & 1, 52);
+        ptx::tc_fence_after();
+        const uint32_t idesc = ptx::make_idesc(ATT_BQ, kv_len_mma(j), false, false, F16 ? 0u : 1u);
+        const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_ring + slot * AQ_TILE_BYTES, 1024, 0);
+#pragma unroll
+        for (int k = 0; k < ATT_DH / 16; ++k)
+          ptx::umma_bf16_ss(s_tmem, ptx::desc_advance(q_desc, k * 32), ptx::desc_advance(k_desc, k * 32), idesc, k ? 1u : 0u);
+        ptx::umma_commit(kv_empty + 8 * slot);
+        ptx::umma_commit(s_full);
+        ++used;
+      };
       int g = 0;   // KV blocks so far (all items): phase of s_full / p_full
       int w = 0;   // items so far: phase of q_full / o_full / o_empty
       for (int it = first; it < args.n_items; it += stride, ++w) {
+        const bool tl = TL && args.timeline != nullptr && blockIdx.x == 0 && p < 2 && w == args.timeline_item;
         ptx::mbar_wait(q_full, w & 1, 51);
+        issue_s(0);
+        if constexpr (TL) att_stamp(args, tl, 1, 0, 0, p);   // S_0 issued
         for (int j = 0; j < n_kv; ++j, ++g) {
-          // ---- S_j = Q K_j^T (over the columns that held P_{j-1}: PV_{j-1} was issued before and the tensor pipe runs in order)
-          {
-            const int slot = used % AQ_RING;
-            ptx::mbar_wait(kv_full + 8 * slot, (used / AQ_RING) & 1, 52);
-            ptx::tc_fence_after();
-            const uint32_t idesc = ptx::make_idesc(ATT_BQ, kv_len_mma(j), false, false, F16 ? 0u : 1u);
-            const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_ring + slot * AQ_TILE_BYTES, 1024, 0);
-#pragma unroll
-            for (int k = 0; k < ATT_DH / 16; ++k)
-              ptx::umma_bf16_ss(s_tmem, ptx::desc_advance(q_desc, k * 32), ptx::desc_advance(k_desc, k * 32), idesc, k ? 1u : 0u);
-            ptx::umma_commit(kv_empty + 8 * slot);
-            ptx::umma_commit(s_full);
-            ++used;
-          }
           fill();
           // ---- O += P_j V_j
           ptx::mbar_wait(p_full, g & 1, 53);
           ptx::tc_fence_after();
-          if (j == n_kv - 1 && it + stride < args.n_items) load_q(it + stride);   // P_last exists => every S of the item was produced: Q is free
+          if constexpr (TL) att_stamp(args, tl, 1, j, 1, p);   // P_j seen
           if (j == 0 && w > 0) {   // O still holds the previous item until its rows have been read out
             ptx::mbar_wait(o_empty, (w - 1) & 1, 54);
             ptx::tc_fence_after();
@@ -190,9 +194,16 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
             if (j == n_kv - 1) ptx::umma_commit(o_full);
             ++used;
           }
-          fill();
+          if constexpr (TL) att_stamp(args, tl, 1, j, 2, p);   // PV_j issued
+          if (j + 1 < n_kv) {
+            issue_s(j + 1);
+            if constexpr (TL) att_stamp(args, tl, 1, j + 1, 0, p);   // S_{j+1} issued
+          } else if (it + stride < args.n_items) {
+            load_q(it + stride);   // P_last exists => every S of the item was produced: Q is free
+          }
         }
       }
+      // (every tile requested by fill() has been consumed: requests stop with the last item's last V)
     }
   } else {
     // ===================== softmax / output: warps 4p .. 4p+3 =====================
@@ -204,14 +215,17 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
     const uint64_t sl2_2 = ptx::dup_f32x2(sl2);
     int g = 0, w = 0;
     for (int it = first; it < args.n_items; it += stride, ++w) {
+      const bool tl = TL && args.timeline != nullptr && blockIdx.x == 0 && p < 2 && q == 0 && lane == 0 && w == args.timeline_item;
       float m_used = -INFINITY;   // the row maximum the exponentials are taken against
       float l_run = 0.f;          // running row sum (same units as O in TMEM)
       for (int j = 0; j < n_kv; ++j, ++g) {
         int kv_len = N - j * AQ_BKV;
         kv_len = kv_len > AQ_BKV ? AQ_BKV : kv_len;
         const int nchunks = (((kv_len + 15) & ~15) + 31) >> 5;   // 32-column chunks the MMA produced
+        if constexpr (TL) att_stamp(args, tl, 0, j, 0, p);     // waiting for S_j
         ptx::mbar_wait(s_full, g & 1, 60);   // S_j complete; PV_{j-1} retired too: O is complete up to block j-1, the P columns are free
         ptx::tc_fence_after();
+        if constexpr (TL) att_stamp(args, tl, 0, j, 1, p);     // S_j complete
         // One 32-key chunk at a time (32 logits live, not 64: the kernel runs at 104 registers per softmax thread).  The chunk's P goes
         // into columns S_COL + 16 c ... of the lane: over logits this thread has already consumed (chunk 1's logits sit in columns
         // 32 .. 63, untouched by P).  Reference maximum = the maximum of chunk 0 of block 0; EVERY other chunk is checked through its
@@ -225,6 +239,7 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
             uint32_t s[32];
             ptx::tmem_ld_32x32b_x32(lane_addr + AQ_S_COL + c * 32, s);
             ptx::tmem_ld_wait(s);
+            if constexpr (TL) att_stamp(args, tl, 0, j, 2 + 2 * c, p);   // chunk c in registers
             if (kv_len < AQ_BKV) {   // ragged last block: columns beyond the sequence -> -inf (exp2(-inf) = 0)
 #pragma unroll
               for (int i = 0; i < 32; ++i)
@@ -295,6 +310,8 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
               run_exps();
             }
             bsum += csum;
+            if constexpr (TL) { if (tl) asm volatile("" ::"f"(csum)); }
+            if constexpr (TL) att_stamp(args, tl, 0, j, 3 + 2 * c, p);   // chunk c: exponentials issued
           }
         }
         l_run += bsum;
@@ -302,6 +319,7 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
         ptx::tc_fence_before();    // ... and ordered before the MMA that reads / accumulates on them
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(p_full);
+        if constexpr (TL) att_stamp(args, tl, 0, j, 6, p);   // P_j handed to the control thread
       }
       // ---- epilogue: ctx = O / l
       ptx::mbar_wait(o_full, w & 1, 61);

@@ -559,7 +559,7 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
   // 16-bit engines, inference: the full query tiles go through the four-pipeline kernel (attention_quad_sm100.cuh), the ragged
   // tails through the packed items of the kernel below (VITOCM_ATTN_QUAD=0: everything through the kernel below)
   static const int quad = [] { const char* v = getenv("VITOCM_ATTN_QUAD"); return v ? atoi(v) : 1; }();
-  if (quad && !e->split && lse2 == nullptr && timeline == nullptr && a.n_fullq >= 1) {
+  if (quad && !e->split && lse2 == nullptr && a.n_fullq >= 1) {
     const long long full_items = static_cast<long long>(a.n_pairs) * a.n_fullq;
     if (full_items > 0x7fffffffLL) return fail(VITOCM_ERR_INVALID, "attention: too many work items");
     AttnArgs aq = a;
@@ -568,17 +568,20 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
     TRY(make_tmap_bf16(&tkv, qkv, M, 3LL * D * e->parts, ld, AQ_BKV));
     const int ctas = (aq.n_items + AQ_PIPES - 1) / AQ_PIPES;
     const dim3 qgrid(ctas < e->num_sms ? ctas : e->num_sms);
-    static bool qattr[2] = {false, false};
-    if (e->f16) {
-      if (!qattr[1]) { CUDA_TRY(cudaFuncSetAttribute(attn_fwd_quad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AQ_SMEM_BYTES)); qattr[1] = true; }
-      attn_fwd_quad_kernel<true><<<qgrid, AQ_THREADS, AQ_SMEM_BYTES, st>>>(tq, tkv, aq);
-    } else {
-      if (!qattr[0]) { CUDA_TRY(cudaFuncSetAttribute(attn_fwd_quad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AQ_SMEM_BYTES)); qattr[0] = true; }
-      attn_fwd_quad_kernel<false><<<qgrid, AQ_THREADS, AQ_SMEM_BYTES, st>>>(tq, tkv, aq);
-    }
+    auto qlaunch = [&](auto kern, bool& attr) -> int {
+      if (!attr) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AQ_SMEM_BYTES)); attr = true; }
+      kern<<<qgrid, AQ_THREADS, AQ_SMEM_BYTES, st>>>(tq, tkv, aq);
+      return 0;
+    };
+    static bool qattr[4] = {false, false, false, false};
+    int qrc;
+    if (timeline != nullptr) qrc = e->f16 ? qlaunch(attn_fwd_quad_kernel<true, true>, qattr[3]) : qlaunch(attn_fwd_quad_kernel<false, true>, qattr[2]);
+    else qrc = e->f16 ? qlaunch(attn_fwd_quad_kernel<true, false>, qattr[1]) : qlaunch(attn_fwd_quad_kernel<false, false>, qattr[0]);
+    if (qrc) return qrc;
     LAUNCH_CHECK();
     if (tail == 0) return 0;
     a.tails_only = 1;
+    a.timeline = nullptr;   // (the stamps of a timeline call come from the four-pipeline kernel)
     a.n_items = (a.n_pairs + a.pack - 1) / a.pack;
   }
   // persistent CTAs: as many as are co-resident (2 per SM in bf16 mode, 1 in split mode)
