@@ -262,6 +262,93 @@ def test_mlp_fused(M, D, Hd, precision):
     assert (x - ref2).abs().max().item() <= 2 * tol * (ref - resid).abs().max().item() + 2e-4
 
 
+def _tail_reference(ctx, Wp, bp, g2, be2, W1, b1, W2, b2, gn, ben, resid, dt, eps=1e-6):
+    """fp32 statement of the second half of Block.forward with the two activations the kernel keeps in 16 bits (norm2's output and
+    the hidden chunk) rounded to the engine's format."""
+    x = resid + ctx.float() @ Wp.float().T + bp
+    xn2 = torch.nn.functional.layer_norm(x, (x.shape[1],), g2, be2, eps).to(dt).float()
+    hid = torch.nn.functional.gelu(xn2 @ W1.float().T + b1).to(dt).float()
+    x = x + hid @ W2.float().T + b2
+    xn = torch.nn.functional.layer_norm(x, (x.shape[1],), gn, ben, eps)
+    return x, xn
+
+
+@pytest.mark.parametrize("M,D,Hd", [(785, 384, 1536), (256, 384, 1536), (130, 128, 512), (1, 128, 128), (5000, 384, 1536), (80000, 384, 1536),
+                                    (257, 128, 256), (40000, 128, 384), (60000, 128, 128)])   # odd chunk counts: the epilogue groups swap per item
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("with_next_ln", [True, False])
+def test_block_tail(M, D, Hd, precision, with_next_ln):
+    """proj + residual + norm2 + fc1 + GELU + fc2 + residual + next LayerNorm in one kernel: ragged row tiles, one and many items
+    per CTA pair, both instantiated widths, with and without the trailing LayerNorm."""
+    if not with_next_ln and M > 5000:
+        pytest.skip("covered by the with_next_ln case")
+    lib = vob._lib.load_library()
+    eng = make_engine(precision=2 if precision == "fp16" else 0)
+    dt = torch.float16 if precision == "fp16" else torch.bfloat16
+    ctx = _rand((M, D), 80).to(dt)
+    Wp = _rand((D, D), 81, 0.05).to(dt)
+    W1 = _rand((Hd, D), 82, 0.06).to(dt)
+    W2 = _rand((D, Hd), 83, 0.03).to(dt)
+    bp, b1, b2 = _rand((D,), 84, 0.1), _rand((Hd,), 85, 0.2), _rand((D,), 86, 0.1)
+    g2, be2 = _rand((D,), 87) * 0.1 + 1, _rand((D,), 88) * 0.1
+    gn, ben = _rand((D,), 89) * 0.1 + 1, _rand((D,), 90) * 0.1
+    resid = _rand((M, D), 91) * 2 + 0.5
+    x = resid.clone()
+    # the workspace's XN [M][2D]: only the first D columns are written
+    xn = torch.full((M, 2 * D), float("nan"), device="cuda", dtype=dt)
+    check(lib.vitocm_block_tail(eng, ptr(ctx), ctx.stride(0), ptr(Wp), Wp.stride(0), ptr(bp), ptr(g2), ptr(be2), ptr(W1), W1.stride(0), ptr(W2),
+                                W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(x), ptr(gn) if with_next_ln else None,
+                                ptr(ben) if with_next_ln else None, ptr(xn), xn.stride(0), None, cur_stream()))
+    torch.cuda.synchronize()
+    ref_x, ref_xn = _tail_reference(ctx, Wp, bp, g2, be2, W1, b1, W2, b2, gn, ben, resid, dt)
+    tol = 3e-3 if precision == "fp16" else 1.5e-2
+    scale = (ref_x - resid).abs().max().item()
+    err = (x - ref_x).abs().max().item()
+    assert err <= tol * scale + 1e-4, (err, scale)
+    if with_next_ln:
+        assert torch.isnan(xn[:, D:].float()).all()
+        got = xn[:, :D].float()
+        assert torch.isfinite(got).all()
+        # 16-bit rounding of the output + the error of x divided by the row's standard deviation
+        tol_n = (2e-3 if precision == "fp16" else 1.2e-2) * ref_xn.abs().max().item() + 2 * tol * scale / ref_x.std(dim=1).min().item()
+        assert (got - ref_xn).abs().max().item() <= tol_n
+    else:
+        assert torch.isnan(xn.float()).all()
+
+
+def test_block_tail_matches_separate_kernels(engine):
+    """The one-kernel block tail against the kernels it replaces (proj + LayerNorm GEMM, fused MLP, LayerNorm) on the same operands."""
+    lib = vob._lib.load_library()
+    M, D, Hd = 3000, 384, 1536
+    dt = torch.bfloat16
+    ctx = _rand((M, D), 100).to(dt)
+    Wp = _rand((D, D), 101, 0.05).to(dt)
+    W1 = _rand((Hd, D), 102, 0.06).to(dt)
+    W2 = _rand((D, Hd), 103, 0.03).to(dt)
+    bp, b1, b2 = _rand((D,), 104, 0.1), _rand((Hd,), 105, 0.2), _rand((D,), 106, 0.1)
+    g2, be2 = _rand((D,), 107) * 0.1 + 1, _rand((D,), 108) * 0.1
+    gn, ben = _rand((D,), 109) * 0.1 + 1, _rand((D,), 110) * 0.1
+    resid = _rand((M, D), 111)
+    x = resid.clone()
+    xn = torch.zeros((M, 2 * D), device="cuda", dtype=dt)
+    check(lib.vitocm_block_tail(engine, ptr(ctx), ctx.stride(0), ptr(Wp), Wp.stride(0), ptr(bp), ptr(g2), ptr(be2), ptr(W1), W1.stride(0), ptr(W2),
+                                W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(x), ptr(gn), ptr(ben), ptr(xn), xn.stride(0), None, cur_stream()))
+    y = resid.clone()
+    yn = torch.zeros((M, 2 * D), device="cuda", dtype=dt)
+    check(lib.vitocm_gemm_ln(engine, ptr(ctx), ctx.stride(0), ptr(Wp), Wp.stride(0), M, D, D, ptr(bp), ptr(y), ptr(g2), ptr(be2), ptr(yn),
+                             yn.stride(0), cur_stream()))
+    check(lib.vitocm_mlp_fused(engine, ptr(yn), yn.stride(0), ptr(W1), W1.stride(0), ptr(W2), W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(y),
+                               cur_stream()))
+    torch.cuda.synchronize()
+    scale = (y - resid).abs().max().item()
+    # norm2's rows are rounded to bf16 in both paths, from statistics summed in a different order: a few of them land on the
+    # neighbouring bf16 value
+    assert (x - y).abs().max().item() <= 4e-3 * scale
+    assert (x - y).abs().mean().item() <= 1e-4 * scale
+    ref_n = torch.nn.functional.layer_norm(y, (D,), gn, ben, 1e-6)
+    assert (xn[:, :D].float() - ref_n).abs().max().item() <= 1.5e-2 * ref_n.abs().max().item()
+
+
 def test_mlp_fused_matches_separate_gemms(engine):
     """The fused kernel against the two-GEMM path it replaces (same operands, same GELU form): only the summation order differs."""
     lib = vob._lib.load_library()

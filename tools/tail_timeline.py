@@ -1,0 +1,59 @@
+"""SM-clock timeline of one work item of the block-tail kernel (vitocm_block_tail with stamps; layout: TailArgs::timeline in
+csrc/block_tail_sm100.cuh) + its launch time.  Usage: python tools/tail_timeline.py [tiles] [precision]"""
+import os
+import sys
+import ctypes as C
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import vitocm_b200 as vob  # noqa: E402
+from gpu_util import make_engine, ptr, check, cur_stream  # noqa: E402
+
+tiles = int(sys.argv[1]) if len(sys.argv) > 1 else 175
+precision = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+M, D, Hd = tiles * 785, 384, 1536
+dt = torch.float16 if precision == 2 else torch.bfloat16
+lib = vob._lib.load_library()
+eng = make_engine(embed_dim=D, heads=6, hidden=Hd, precision=precision)
+g = torch.Generator(device="cuda").manual_seed(0)
+rnd = lambda *s, sc=1.0: torch.randn(*s, device="cuda", generator=g) * sc
+ctx = rnd(M, D).to(dt)
+Wp, W1, W2 = rnd(D, D, sc=0.05).to(dt), rnd(Hd, D, sc=0.06).to(dt), rnd(D, Hd, sc=0.03).to(dt)
+bp, b1, b2 = rnd(D, sc=0.1), rnd(Hd, sc=0.2), rnd(D, sc=0.1)
+g2, be2, gn, ben = rnd(D, sc=0.1) + 1, rnd(D, sc=0.1), rnd(D, sc=0.1) + 1, rnd(D, sc=0.1)
+x = rnd(M, D)
+xn = torch.zeros(M, 2 * D, device="cuda", dtype=dt)
+stamps = torch.zeros(64, device="cuda", dtype=torch.int64)
+
+
+def run(st):
+    check(lib.vitocm_block_tail(eng, ptr(ctx), ctx.stride(0), ptr(Wp), Wp.stride(0), ptr(bp), ptr(g2), ptr(be2), ptr(W1), W1.stride(0), ptr(W2),
+                                W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(x), ptr(gn), ptr(ben), ptr(xn), xn.stride(0), st, cur_stream()))
+
+
+for _ in range(3):
+    run(None)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+n = 10
+e0.record()
+for _ in range(n):
+    run(None)
+e1.record()
+torch.cuda.synchronize()
+us = e0.elapsed_time(e1) * 1e3 / n
+flop = 2.0 * M * D * (D + 2 * Hd)
+print(f"block tail: tiles={tiles} M={M} precision={precision}: {us:.1f} us/launch, {flop / us / 1e6:.1f} TFLOP/s")
+run(ptr(stamps))
+torch.cuda.synchronize()
+s = stamps.cpu().tolist()
+t0 = s[60]
+rel = lambda i: (s[i] - t0) & 0xFFFFFFFF if s[i] else -1
+print("MMA thread : CTX landed=0  proj issued=%d  ep1 seen=%d" % (rel(56), rel(59)))
+print("epilogue w0: proj complete=%d  ep1 pass1=%d  ep1 handed=%d" % (rel(57), rel(58), rel(55)))
+print("epilogue w0: ep1 steps=%d %d %d  combined=%d" % (rel(15), rel(16), rel(17), rel(18)))
+for c in range(0, 5, 2):
+    print(" chunk %2d: fc1 complete=%d gelu done=%d handed=%d | mma: fc1 issued=%d gelu seen=%d" % (c, rel(3 * c), rel(3 * c + 1), rel(3 * c + 2), rel(36 + 2 * c), rel(36 + 2 * c + 1)))
+print("epilogue w0: OUT complete=%d  ep2 stats=%d  steps stored=%d %d %d  stores read=%d  ep2 done=%d" % (rel(61), rel(54), rel(20), rel(21), rel(22), rel(24), rel(62)))

@@ -1,6 +1,8 @@
 // Forward attention, "quad" form: FOUR independent softmax pipelines per SM (one 640-thread CTA per SM), 64-key blocks.
 // Replaces SSS/dino/vision_transformer.py:83-87 like attention_sm100.cuh, for the FULL 128-row query tiles of 16-bit engines
-// (the ragged query tail keeps the packed items of attn_fwd_tcgen05_kernel, launched with AttnArgs::tails_only).
+// AND, as its first items, for the ragged query tails: the tails of `pack` = 2 (image, head) pairs share one 128-row tile, one masked
+// MMA group per pair (the packed items of attention_sm100.cuh, here on 64-key blocks; two pairs, not four: a block's K and V tiles of
+// two pairs stream through the five-slot ring without a stall, those of four do not -- measured 4 x slower per item).
 //
 // Why: the exponentials bound this kernel (MUFU: 16 ex2 / clk / SM), and ONE warp per scheduler can only issue a MUFU every
 // ~14 clk against the unit's 8 (profiles/r01_attention_phased_exps.txt).  The two co-resident CTAs of attn_fwd_tcgen05_kernel
@@ -31,16 +33,47 @@ constexpr int AQ_PIPE_SMEM = AQ_Q_BYTES + AQ_RING * AQ_TILE_BYTES;
 constexpr int AQ_PIPE_BARS = 128;
 constexpr int AQ_SMEM_BYTES = AQ_PIPES * (AQ_PIPE_SMEM + AQ_PIPE_BARS) + 64 + 1024 /*alignment slack*/;
 constexpr int AQ_REGS_SOFTMAX = 104;
-constexpr int AQ_REGS_CTRL = 48;
+constexpr int AQ_REGS_CTRL = 64;
 static_assert(16 * AQ_REGS_SOFTMAX + 4 * AQ_REGS_CTRL <= 20 * 96, "quad attention: setmaxnreg budgets exceed the launch allocation");
 static_assert(AQ_SMEM_BYTES <= 227 * 1024, "quad attention: shared memory");
 constexpr int AQ_S_COL = 0;     // S: 64 fp32 columns; P (packed pairs, 32 columns) over its first half
 constexpr int AQ_O_COL = 64;    // O: 64 fp32 columns
 
+// work item -> (first pair, query tile, pairs sharing the tile).  Without tail items (group_items == 0): query tile fastest, then the
+// pair.  With them: groups of `pack` consecutive pairs = pack x n_fullq full tiles followed by the ONE tile their ragged tails
+// share, so that the tail runs while its pairs' K / V are hot in L2 (tails first or last re-read every K / V from HBM: 1.5 GB per
+// launch at the bench's size).  Pairs beyond the batch (last group) are clamped by the callers: computed, not stored.
+__device__ __forceinline__ void aq_decode(const AttnArgs& a, int it, int& pair0, int& qt, int& nslots) {
+  if (a.group_items == 0) {
+    pair0 = it / a.n_fullq;
+    qt = it - pair0 * a.n_fullq;
+    nslots = 1;
+    return;
+  }
+  const int g = it / a.group_items, r = it - g * a.group_items;
+  if (r < a.pack * a.n_fullq) {
+    const int pi = r / a.n_fullq;
+    pair0 = g * a.pack + pi;
+    qt = r - pi * a.n_fullq;
+    nslots = 1;
+  } else {
+    pair0 = g * a.pack;
+    qt = a.n_fullq;
+    nslots = a.pack;
+  }
+}
+// disable-output-lane mask of slot SL of NS equal lane groups as compile-time constants (run-time masks cost the issuing thread four
+// R2UR round trips per MMA: ~150 clk per masked MMA against ~40 -- profiles/r02 timeline of a tail item)
+template <int NS, int SL>
+__device__ __forceinline__ void aq_slot_mask(uint32_t (&m)[4]) {
+#pragma unroll
+  for (int w = 0; w < 4; ++w) m[w] = ((NS == 4 ? w : (NS == 2 ? (w >> 1) : 0)) == SL) ? 0u : 0xffffffffu;
+}
+
 template <bool F16, bool TL = false>   // TL: clock stamps of tools/attn_quad_timeline.py (a separate instantiation: the stamps cost registers)
 __global__ void __launch_bounds__(AQ_THREADS, 1)
 attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/, const __grid_constant__ CUtensorMap tmap_kv /*box 64 x 64*/,
-                     const AttnArgs args) {
+                     const __grid_constant__ CUtensorMap tmap_q32 /*box 64 x 32: the query slots of packed tail items*/, const AttnArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars0 = smem + AQ_PIPES * AQ_PIPE_SMEM;
@@ -66,6 +99,7 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
   if (warp == 4 * AQ_PIPES && lane == 0) {
     ptx::prefetch_tmap(&tmap_q);
     ptx::prefetch_tmap(&tmap_kv);
+    ptx::prefetch_tmap(&tmap_q32);
     for (int pp = 0; pp < AQ_PIPES; ++pp) {
       const uint32_t b = bars0 + pp * AQ_PIPE_BARS;
       ptx::mbar_init(b, 1);
@@ -89,8 +123,8 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
   ptx::tc_fence_after();
   const uint32_t tmem_base = ptx::lds_u32(tmem_ptr_smem) + static_cast<uint32_t>(p * 128);
 
-  // work items of this pipeline: full query tiles (query tile fastest, then the (image, head) pair); the four pipelines of a CTA
-  // take consecutive items, so they read one pair's K / V through L2 at about the same time
+  // work items of this pipeline (aq_decode); the four pipelines of a CTA take consecutive items, so they read one pair's K / V through
+  // L2 at about the same time
   const int first = static_cast<int>(blockIdx.x) * AQ_PIPES + p;
   const int stride = static_cast<int>(gridDim.x) * AQ_PIPES;
 
@@ -105,25 +139,40 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
         len = len > AQ_BKV ? AQ_BKV : len;
         return (len + 15) & ~15;
       };
+      // pair of slot s (slots beyond the batch repeat the last pair: their rows are computed and dropped)
+      auto clamp_pair = [&](int pr) { return pr < args.n_pairs ? pr : args.n_pairs - 1; };
       auto load_q = [&](int it) {
-        const int pair = it / args.n_fullq, qt = it - pair * args.n_fullq;
-        const int b = pair / args.heads, h = pair - b * args.heads;
+        int pair0, qt, ns;
+        aq_decode(args, it, pair0, qt, ns);
         ptx::mbar_arrive_expect_tx(q_full, AQ_Q_BYTES);
-        ptx::tma_load_2d(smem_q, &tmap_q, q_full, h * ATT_DH, b * N + qt * ATT_BQ);
+        if (ns == 1) {
+          const int pair = clamp_pair(pair0);
+          const int b = pair / args.heads, h = pair - b * args.heads;
+          ptx::tma_load_2d(smem_q, &tmap_q, q_full, h * ATT_DH, b * N + qt * ATT_BQ);
+        } else {   // four 32-row boxes; slot s owns tile rows [s * 128 / pack, (s + 1) * 128 / pack) = the first rows of its pair's tail
+          const int per = 4 / ns;
+          for (int u = 0; u < 4; ++u) {
+            const int pr = clamp_pair(pair0 + u / per);
+            const int b = pr / args.heads, h = pr - b * args.heads;
+            ptx::tma_load_2d(smem_q + u * 4096, &tmap_q32, q_full, h * ATT_DH, b * N + qt * ATT_BQ + (u % per) * 32);
+          }
+        }
       };
-      // K / V stream in consumption order (K0, V0, K1, V1, ...), running across the items of this pipeline
+      // K / V stream in consumption order (per block: K of every slot, then V of every slot), running across the items of this pipeline
       int loaded = 0, used = 0;          // tiles requested / handed to an MMA
-      int l_it = first, l_j = 0, l_which = 1;   // next tile to request: item, block, 1 = K / 2 = V
+      int l_it = first, l_j = 0, l_which = 1, l_sl = 0, l_ns = 1;   // next tile to request: item, block, 1 = K / 2 = V, slot; slots of the item
       int l_col = 0, l_row = 0;
-      auto set_load_item = [&]() {
+      auto set_load_coords = [&]() {
         if (l_it < args.n_items) {
-          const int pair = l_it / args.n_fullq;
-          const int b = pair / args.heads;
-          l_col = (pair - b * args.heads) * ATT_DH;
+          int pair0, qt;
+          aq_decode(args, l_it, pair0, qt, l_ns);
+          const int pr = clamp_pair(pair0 + l_sl);
+          const int b = pr / args.heads;
+          l_col = (pr - b * args.heads) * ATT_DH;
           l_row = b * N;
         }
       };
-      set_load_item();
+      set_load_coords();
       auto fill = [&]() {
         while (loaded - used < AQ_RING && l_it < args.n_items) {
           const int slot = loaded % AQ_RING;
@@ -131,37 +180,65 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
           ptx::mbar_arrive_expect_tx(kv_full + 8 * slot, AQ_TILE_BYTES);
           ptx::tma_load_2d(smem_ring + slot * AQ_TILE_BYTES, &tmap_kv, kv_full + 8 * slot, l_which * D + l_col, l_row + l_j * AQ_BKV);
           ++loaded;
-          if (l_which == 1) {
-            l_which = 2;
-          } else {
-            l_which = 1;
-            if (++l_j == n_kv) { l_j = 0; l_it += stride; set_load_item(); }
+          bool recode = l_ns > 1;
+          if (++l_sl == l_ns) {
+            l_sl = 0;
+            if (l_which == 1) {
+              l_which = 2;
+            } else {
+              l_which = 1;
+              if (++l_j == n_kv) { l_j = 0; l_it += stride; recode = true; }
+            }
           }
+          if (recode) set_load_coords();
         }
       };
       if (first < args.n_items) load_q(first);
       fill();
       // S_j = Q K_j^T into the columns that held P_{j-1}: it is issued right BEHIND PV_{j-1} (the tensor pipe executes in order, so
       // PV_{j-1} has read P before S_j lands on it), never behind a wait for PV_{j-1} to retire -- ring refills come after the issue
-      auto issue_s = [&](int j) {
-        const int slot = used % AQ_RING;
-        ptx::mbar_wait(kv_full + 8 * slot, (used / AQ_RING) & 1, 52);
-        ptx::tc_fence_after();
+      auto issue_s = [&](int j, int nslots) {
         const uint32_t idesc = ptx::make_idesc(ATT_BQ, kv_len_mma(j), false, false, F16 ? 0u : 1u);
-        const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_ring + slot * AQ_TILE_BYTES, 1024, 0);
+        if (nslots == 1) {
+          const int slot = used % AQ_RING;
+          ptx::mbar_wait(kv_full + 8 * slot, (used / AQ_RING) & 1, 52);
+          ptx::tc_fence_after();
+          const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_ring + slot * AQ_TILE_BYTES, 1024, 0);
 #pragma unroll
-        for (int k = 0; k < ATT_DH / 16; ++k)
-          ptx::umma_bf16_ss(s_tmem, ptx::desc_advance(q_desc, k * 32), ptx::desc_advance(k_desc, k * 32), idesc, k ? 1u : 0u);
-        ptx::umma_commit(kv_empty + 8 * slot);
+          for (int k = 0; k < ATT_DH / 16; ++k)
+            ptx::umma_bf16_ss(s_tmem, ptx::desc_advance(q_desc, k * 32), ptx::desc_advance(k_desc, k * 32), idesc, k ? 1u : 0u);
+          ptx::umma_commit(kv_empty + 8 * slot);
+          ++used;
+        } else {   // packed item: one masked MMA group per slot, each against its own pair's K
+          auto slot_s = [&](auto ns_tag, auto sl_tag) {
+            if (loaded <= used) fill();   // (pack = 4: a block's eight tiles do not fit the ring, requests continue between the groups)
+            const int slot = used % AQ_RING;
+            ptx::mbar_wait(kv_full + 8 * slot, (used / AQ_RING) & 1, 56);
+            ptx::tc_fence_after();
+            const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_ring + slot * AQ_TILE_BYTES, 1024, 0);
+            uint32_t lm[4];
+            aq_slot_mask<decltype(ns_tag)::value, decltype(sl_tag)::value>(lm);
+#pragma unroll
+            for (int k = 0; k < ATT_DH / 16; ++k)
+              ptx::umma_bf16_ss_masked(s_tmem, ptx::desc_advance(q_desc, k * 32), ptx::desc_advance(k_desc, k * 32), idesc, k ? 1u : 0u, lm);
+            ptx::umma_commit(kv_empty + 8 * slot);
+            ++used;
+          };
+          using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>;
+          using I2 = std::integral_constant<int, 2>; using I3 = std::integral_constant<int, 3>; using I4 = std::integral_constant<int, 4>;
+          if (nslots == 2) { slot_s(I2{}, I0{}); slot_s(I2{}, I1{}); }
+          else { slot_s(I4{}, I0{}); slot_s(I4{}, I1{}); slot_s(I4{}, I2{}); slot_s(I4{}, I3{}); }
+        }
         ptx::umma_commit(s_full);
-        ++used;
       };
       int g = 0;   // KV blocks so far (all items): phase of s_full / p_full
       int w = 0;   // items so far: phase of q_full / o_full / o_empty
       for (int it = first; it < args.n_items; it += stride, ++w) {
         const bool tl = TL && args.timeline != nullptr && blockIdx.x == 0 && p < 2 && w == args.timeline_item;
+        int nslots, pair0_unused, qt_unused;
+        aq_decode(args, it, pair0_unused, qt_unused, nslots);
         ptx::mbar_wait(q_full, w & 1, 51);
-        issue_s(0);
+        issue_s(0, nslots);
         if constexpr (TL) att_stamp(args, tl, 1, 0, 0, p);   // S_0 issued
         for (int j = 0; j < n_kv; ++j, ++g) {
           fill();
@@ -174,29 +251,56 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
             ptx::tc_fence_after();
           }
           {
-            const int slot = used % AQ_RING;
-            ptx::mbar_wait(kv_full + 8 * slot, (used / AQ_RING) & 1, 55);
-            ptx::tc_fence_after();
             constexpr uint32_t idesc = ptx::make_idesc(ATT_BQ, ATT_DH, false, /*B = V is MN-major*/ true, F16 ? 0u : 1u);
-            const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_ring + slot * AQ_TILE_BYTES, 1024, 1024);
             const int ksteps = kv_len_mma(j) / 16;
             const uint32_t acc0 = j > 0 ? 1u : 0u;
-            if (ksteps == AQ_BKV / 16) {
+            if (nslots == 1) {
+              const int slot = used % AQ_RING;
+              ptx::mbar_wait(kv_full + 8 * slot, (used / AQ_RING) & 1, 55);
+              ptx::tc_fence_after();
+              const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_ring + slot * AQ_TILE_BYTES, 1024, 1024);
+              if (ksteps == AQ_BKV / 16) {
 #pragma unroll
-              for (int k = 0; k < AQ_BKV / 16; ++k)
-                ptx::umma_bf16_ts(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc, k ? 1u : acc0);
-            } else {
+                for (int k = 0; k < AQ_BKV / 16; ++k)
+                  ptx::umma_bf16_ts(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc, k ? 1u : acc0);
+              } else {
 #pragma unroll 1
-              for (int k = 0; k < ksteps; ++k)
-                ptx::umma_bf16_ts(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc, k ? 1u : acc0);
+                for (int k = 0; k < ksteps; ++k)
+                  ptx::umma_bf16_ts(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc, k ? 1u : acc0);
+              }
+              ptx::umma_commit(kv_empty + 8 * slot);
+              ++used;
+            } else {   // packed item: every slot's P rows against its own pair's V
+              auto slot_pv = [&](auto ns_tag, auto sl_tag) {
+                if (loaded <= used) fill();
+                const int slot = used % AQ_RING;
+                ptx::mbar_wait(kv_full + 8 * slot, (used / AQ_RING) & 1, 57);
+                ptx::tc_fence_after();
+                const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_ring + slot * AQ_TILE_BYTES, 1024, 1024);
+                uint32_t lm[4];
+                aq_slot_mask<decltype(ns_tag)::value, decltype(sl_tag)::value>(lm);
+                if (ksteps == AQ_BKV / 16) {
+#pragma unroll
+                  for (int k = 0; k < AQ_BKV / 16; ++k)
+                    ptx::umma_bf16_ts_masked(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc, k ? 1u : acc0, lm);
+                } else {
+#pragma unroll 1
+                  for (int k = 0; k < ksteps; ++k)
+                    ptx::umma_bf16_ts_masked(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc, k ? 1u : acc0, lm);
+                }
+                ptx::umma_commit(kv_empty + 8 * slot);
+                ++used;
+              };
+              using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>;
+              using I2 = std::integral_constant<int, 2>; using I3 = std::integral_constant<int, 3>; using I4 = std::integral_constant<int, 4>;
+              if (nslots == 2) { slot_pv(I2{}, I0{}); slot_pv(I2{}, I1{}); }
+              else { slot_pv(I4{}, I0{}); slot_pv(I4{}, I1{}); slot_pv(I4{}, I2{}); slot_pv(I4{}, I3{}); }
             }
-            ptx::umma_commit(kv_empty + 8 * slot);
             if (j == n_kv - 1) ptx::umma_commit(o_full);
-            ++used;
           }
           if constexpr (TL) att_stamp(args, tl, 1, j, 2, p);   // PV_j issued
           if (j + 1 < n_kv) {
-            issue_s(j + 1);
+            issue_s(j + 1, nslots);
             if constexpr (TL) att_stamp(args, tl, 1, j + 1, 0, p);   // S_{j+1} issued
           } else if (it + stride < args.n_items) {
             load_q(it + stride);   // P_last exists => every S of the item was produced: Q is free
@@ -333,9 +437,19 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(o_empty);   // the next item's first PV may overwrite O
-      const int pair = it / args.n_fullq, qt = it - pair * args.n_fullq;
+      int pair, qrow;
+      {
+        int pair0, qt, ns;
+        aq_decode(args, it, pair0, qt, ns);
+        const int slot_rows = ATT_BQ / ns, sl = r / slot_rows;   // packed tail item: slot = lane group, one pair each
+        pair = pair0 + sl;
+        qrow = qt * ATT_BQ + (r - sl * slot_rows);
+      }
+      const bool row_ok = pair < args.n_pairs && qrow < N;
+      if (!row_ok) pair = 0;
       const int b = pair / args.heads, h = pair - b * args.heads;
-      __nv_bfloat16* o = args.out + static_cast<long long>(b * N + qt * ATT_BQ + r) * args.ldo + h * ATT_DH;
+      __nv_bfloat16* o = args.out + static_cast<long long>(b * N + qrow) * args.ldo + h * ATT_DH;
+      if (row_ok)
 #pragma unroll
       for (int c = 0; c < ATT_DH / 32; ++c) {
 #pragma unroll

@@ -19,6 +19,7 @@
 #include "gemm_sm100.cuh"
 #include "attention_quad_sm100.cuh"
 #include "mlp_fused_sm100.cuh"
+#include "block_tail_sm100.cuh"
 #include "post_kernels.cuh"
 #include "train_kernels.cuh"
 #include "vit_kernels.cuh"
@@ -57,10 +58,10 @@ int fail(int code, const char* fmt, ...) {
 
 // ---- optional per-kernel-class device timing (CUDA events on the launching stream) ----
 enum ProfClass { PC_PATCH = 0, PC_LN, PC_GEMM_QKV, PC_ATTN, PC_GEMM_PROJ, PC_GEMM_FC1, PC_GEMM_FC2, PC_GEMM_KLAST, PC_CLSROW,
-                 PC_POST, PC_OTHER, PC_WGRAD, PC_DGRAD, PC_ATTN_BWD, PC_TRAIN_ELEM, PC_OPTIM, PC_MLP, PC_COUNT };
+                 PC_POST, PC_OTHER, PC_WGRAD, PC_DGRAD, PC_ATTN_BWD, PC_TRAIN_ELEM, PC_OPTIM, PC_MLP, PC_TAIL, PC_COUNT };
 const char* const kProfNames[PC_COUNT] = {"patch_embed", "layernorm", "gemm_qkv", "attention", "gemm_proj", "gemm_fc1_gelu",
                                           "gemm_fc2", "gemm_k_last", "cls_attn_row", "post", "other", "gemm_wgrad", "gemm_dgrad",
-                                          "attention_bwd", "train_elementwise", "optimizer", "mlp_fused"};
+                                          "attention_bwd", "train_elementwise", "optimizer", "mlp_fused", "block_tail"};
 struct ProfRec { int cls; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
@@ -529,6 +530,73 @@ int run_mlp_fused(const vitocm_engine* e, const void* XN, long long ld_xn, const
   return pair_only ? launch_mlp_fused<2, 2>(ta, tw1, tw2, tx, a, e->num_sms, st) : launch_mlp_fused<2, 4>(ta, tw1, tw2, tx, a, e->num_sms, st);
 }
 
+// ---------------------------------------------------------------------------------- block tail launch
+// proj + residual + norm2 + fc1 + GELU + fc2 + residual (+ the next LayerNorm) in one kernel (block_tail_sm100.cuh).  Returns 1 when
+// the shape / engine has no instantiation (the caller then runs the separate kernels).
+template <int KB1, bool F16>
+int launch_block_tail(const CUtensorMap& ta, const CUtensorMap& twp, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx,
+                      const CUtensorMap& txn, const TailArgs& a, int num_sms, cudaStream_t st) {
+  using Cfg = TailCfg<KB1>;
+  static int max_clusters = -1;
+  auto kern = block_tail_tcgen05_kernel<KB1, F16>;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (max_clusters < 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    cfg.gridDim = dim3(2 * (num_sms / 2));
+    int n = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    if (n < 1) return fail(VITOCM_ERR_CUDA, "no CTA pair of the block-tail kernel fits on this device");
+    max_clusters = n < num_sms / 2 ? n : num_sms / 2;
+  }
+  const int tiles = (a.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  cfg.gridDim = dim3(2 * (tiles < max_clusters ? tiles : max_clusters));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, twp, tw1, tw2, tx, txn, a));
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int run_block_tail(const vitocm_engine* e, const void* CTX, long long ld_ctx, const void* Wp, long long ldwp, const float* bp,
+                   const float* ln2w, const float* ln2b, const void* W1, long long ldw1, const void* W2, long long ldw2, int M, int D, int Hd,
+                   const float* b1, const float* b2, float* X, const float* lnn_w, const float* lnn_b, float eps, void* XN, long long ld_xn,
+                   cudaStream_t st, bool force = false, long long* timeline = nullptr) {
+  // VITOCM_FUSE_TAIL: 0 = never (proj + LayerNorm GEMM, fused MLP and LayerNorm as separate kernels), 1 = default
+  static const int mode = [] { const char* v = getenv("VITOCM_FUSE_TAIL"); return v == nullptr ? 1 : atoi(v); }();
+  if (mode == 0 && !force) return 1;
+  if (e->split || M <= 0 || (D != 128 && D != 384) || Hd % MLP_HC != 0) return 1;
+  const float* vecs[7] = {bp, ln2w, ln2b, b1, b2, lnn_w, lnn_b};
+  for (int i = 0; i < 7; ++i) {
+    if (i < 5 && vecs[i] == nullptr) return 1;
+    if ((reinterpret_cast<uintptr_t>(vecs[i]) & 15) != 0) return 1;
+  }
+  if ((lnn_w == nullptr) != (lnn_b == nullptr) || (lnn_w != nullptr && XN == nullptr)) return 1;
+  ProfScope prof(PC_TAIL, st);
+  CUtensorMap ta, twp, tw1, tw2, tx, txn;
+  const int w2_rows = D == 384 ? 96 : 64;   // one CTA's half of a [BN2 x 64] tile: BN2 = 192 at D = 384
+  TRY(make_tmap_bf16(&ta, CTX, M, D, ld_ctx, GEMM_BM));
+  TRY(make_tmap_bf16(&twp, Wp, D, D, ldwp, w2_rows));
+  TRY(make_tmap_bf16(&tw1, W1, Hd, D, ldw1, 64));
+  TRY(make_tmap_bf16(&tw2, W2, D, Hd, ldw2, w2_rows));
+  TRY(make_tmap(&tx, X, true, D, M, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  if (lnn_w != nullptr) TRY(make_tmap(&txn, XN, false, ld_xn, M, ld_xn, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+  else txn = tx;
+  TailArgs a{};
+  a.M = M; a.hidden = Hd;
+  a.bias_p = bp; a.ln2_w = ln2w; a.ln2_b = ln2b; a.bias1 = b1; a.bias2 = b2; a.lnn_w = lnn_w; a.lnn_b = lnn_b; a.ln_eps = eps;
+  a.timeline = timeline;
+  { static const int dbg = [] { const char* v = getenv("VITOCM_TAIL_DEBUG"); return v ? atoi(v) : 0; }(); a.debug = dbg; }
+  { static const int stg = [] { const char* v = getenv("VITOCM_TAIL_STAGGER"); return v ? atoi(v) : 0; }(); a.stagger_clk = stg; }
+  { static const int tli = [] { const char* v = getenv("VITOCM_MLP_TL_ITEM"); return v ? atoi(v) : 1; }(); a.timeline_item = tli; }
+  if (D == 384) return e->f16 ? launch_block_tail<6, true>(ta, twp, tw1, tw2, tx, txn, a, e->num_sms, st) : launch_block_tail<6, false>(ta, twp, tw1, tw2, tx, txn, a, e->num_sms, st);
+  return e->f16 ? launch_block_tail<2, true>(ta, twp, tw1, tw2, tx, txn, a, e->num_sms, st) : launch_block_tail<2, false>(ta, twp, tw1, tw2, tx, txn, a, e->num_sms, st);
+}
+
 // ---------------------------------------------------------------------------------- attention launch
 int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, int N, void* ctx, long long ldo, cudaStream_t st,
                   long long* timeline = nullptr, float* lse2 = nullptr) {
@@ -563,14 +631,28 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
     const long long full_items = static_cast<long long>(a.n_pairs) * a.n_fullq;
     if (full_items > 0x7fffffffLL) return fail(VITOCM_ERR_INVALID, "attention: too many work items");
     AttnArgs aq = a;
-    aq.n_items = static_cast<int>(full_items);
+    aq.n_full_items = static_cast<int>(full_items);
+    // the ragged query tails ride along as the kernel's last items when they pack (a.pack > 1: `pack` pairs per tile); otherwise
+    // (VITOCM_ATTN_QUAD_TAILS=0, a tail of more than 64 rows, more than 16 full tiles per pair) they go through the kernel below
+    static const int quad_tails = [] { const char* v = getenv("VITOCM_ATTN_QUAD_TAILS"); return v ? atoi(v) : 1; }();
+    const bool tails_here = quad_tails && a.pack > 1;
+    static const int quad_pack = [] { const char* v = getenv("VITOCM_ATTN_QUAD_PACK"); return v ? atoi(v) : 2; }();   // 2 or 4
+    aq.group_items = 0;
+    aq.n_items = aq.n_full_items;
+    if (tails_here) {   // groups of `pack` pairs: their full tiles, then the one tile their tails share (aq_decode)
+      aq.pack = (quad_pack == 4 && a.pack == 4) ? 4 : 2;
+      aq.group_items = aq.pack * a.n_fullq + 1;
+      const long long gi = static_cast<long long>((a.n_pairs + aq.pack - 1) / aq.pack) * aq.group_items;
+      if (gi > 0x7fffffffLL) return fail(VITOCM_ERR_INVALID, "attention: too many work items");
+      aq.n_items = static_cast<int>(gi);
+    }
     CUtensorMap tkv;
     TRY(make_tmap_bf16(&tkv, qkv, M, 3LL * D * e->parts, ld, AQ_BKV));
     const int ctas = (aq.n_items + AQ_PIPES - 1) / AQ_PIPES;
     const dim3 qgrid(ctas < e->num_sms ? ctas : e->num_sms);
     auto qlaunch = [&](auto kern, bool& attr) -> int {
       if (!attr) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AQ_SMEM_BYTES)); attr = true; }
-      kern<<<qgrid, AQ_THREADS, AQ_SMEM_BYTES, st>>>(tq, tkv, aq);
+      kern<<<qgrid, AQ_THREADS, AQ_SMEM_BYTES, st>>>(tq, tkv, tq32, aq);
       return 0;
     };
     static bool qattr[4] = {false, false, false, false};
@@ -579,7 +661,7 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
     else qrc = e->f16 ? qlaunch(attn_fwd_quad_kernel<true, false>, qattr[1]) : qlaunch(attn_fwd_quad_kernel<false, false>, qattr[0]);
     if (qrc) return qrc;
     LAUNCH_CHECK();
-    if (tail == 0) return 0;
+    if (tail == 0 || tails_here) return 0;
     a.tails_only = 1;
     a.timeline = nullptr;   // (the stamps of a timeline call come from the four-pipeline kernel)
     a.n_items = (a.n_pairs + a.pack - 1) / a.pack;
@@ -723,6 +805,17 @@ int block_forward(const vitocm_engine* e, int l, const Workspace& ws, int B, int
   // fc1 / fc2 contract both halves against the single-precision weights (two MMAs per product) -- the rounding of these two
   // activations is where most of the CLS-row error of a 16-bit forward comes from (profiles/r02_precision_sim.txt)
   const bool mlp2 = !S && l < static_cast<int>(e->layer_mode.size()) && e->layer_mode[l] == 1;
+  // proj + residual + norm2 + MLP + residual (+ the next block's norm1) in ONE kernel where an instantiation exists (single 16-bit
+  // operands, D = 128 / 384): a row of the residual stream is read once and written once, norm2's output never reaches HBM
+  if (!S && !mlp2) {
+    const int rct = run_block_tail(e, ws.CTX, static_cast<long long>(D) * P, L.wproj.p, static_cast<long long>(D) * P, L.bproj, L.ln2w, L.ln2b,
+                                   L.w1.p, D, L.w2.p, Hd, M, D, Hd, L.b1, L.b2, ws.X, next_ln_w, next_ln_b, e->cfg.ln_eps, ws.XN, 2LL * D, st);
+    if (rct < 0) return rct;
+    if (rct == 0) {
+      if (xn_done != nullptr && next_ln_w != nullptr) *xn_done = true;
+      return 0;
+    }
+  }
   // proj + residual (+ norm2 fused when possible)
   int rc = mlp2 ? 1 : run_gemm_ln(e, ws.CTX, static_cast<long long>(D) * P, L.wproj.p, static_cast<long long>(D) * P, M, D, D, L.bproj, ws.X,
                                   L.ln2w, L.ln2b, e->cfg.ln_eps, ws.XN, 2LL * D, st, PC_GEMM_PROJ);
@@ -1511,6 +1604,17 @@ int vitocm_mlp_fused_timeline(vitocm_engine* e, const void* XN, int64_t ld_xn, c
   const int rc = run_mlp_fused(e, XN, ld_xn, W1, ldw1, W2, ldw2, M, D, hidden, bias1, bias2, X, reinterpret_cast<cudaStream_t>(stream), true,
                                reinterpret_cast<long long*>(stamps));
   if (rc == 1) return fail(VITOCM_ERR_INVALID, "fused MLP: no instantiation for D=%d hidden=%d in this engine mode", D, hidden);
+  return rc;
+}
+int vitocm_block_tail(vitocm_engine* e, const void* CTX, int64_t ld_ctx, const void* Wp, int64_t ldwp, const float* bias_p, const float* ln2_w,
+                      const float* ln2_b, const void* W1, int64_t ldw1, const void* W2, int64_t ldw2, int M, int D, int hidden, const float* bias1,
+                      const float* bias2, float* X, const float* next_ln_w, const float* next_ln_b, void* XN, int64_t ld_xn, int64_t* stamps,
+                      void* stream) {
+  if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
+  const int rc = run_block_tail(e, CTX, ld_ctx, Wp, ldwp, bias_p, ln2_w, ln2_b, W1, ldw1, W2, ldw2, M, D, hidden, bias1, bias2, X, next_ln_w,
+                                next_ln_b, e->cfg.ln_eps, XN, ld_xn, reinterpret_cast<cudaStream_t>(stream), true,
+                                reinterpret_cast<long long*>(stamps));
+  if (rc == 1) return fail(VITOCM_ERR_INVALID, "block tail: no instantiation for D = %d, hidden = %d on this engine", D, hidden);
   return rc;
 }
 int vitocm_attention(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo, void* stream) {
