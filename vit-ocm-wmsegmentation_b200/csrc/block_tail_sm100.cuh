@@ -30,6 +30,9 @@ namespace vitocm {
 struct TailArgs {
   int M;               // token rows
   int hidden;          // Hd (multiple of 128)
+  int gelu5;           // 1 = five-coefficient sigmoid form of GELU (fp16 engines), 0 = three coefficients (bf16): a RUN-TIME switch on purpose --
+                       // the branch keeps the two halves of a chunk in separate basic blocks; as straight-line code ptxas interleaves them
+                       // and the chunk loop runs 25 % slower (530 vs 428 us per 175-tile launch)
   const float* bias_p; // [D] proj bias
   const float* ln2_w;  // [D] norm2
   const float* ln2_b;
@@ -533,7 +536,7 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
             v[4 * j + 2] = __uint_as_float(r[s][4 * j + 2]) + b4.z;
             v[4 * j + 3] = __uint_as_float(r[s][4 * j + 3]) + b4.w;
           }
-          if (F16) {   // five-coefficient sigmoid form for fp16 engines, three coefficients for bf16 (MlpArgs::gelu_mode)
+          if (args.gelu5) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2) gelu_sigmoid5_x2(v[j], v[j + 1]);
           } else {

@@ -587,7 +587,7 @@ int run_block_tail(const vitocm_engine* e, const void* CTX, long long ld_ctx, co
   if (lnn_w != nullptr) TRY(make_tmap(&txn, XN, false, ld_xn, M, ld_xn, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   else txn = tx;
   TailArgs a{};
-  a.M = M; a.hidden = Hd;
+  a.M = M; a.hidden = Hd; a.gelu5 = e->f16 ? 1 : 0;
   a.bias_p = bp; a.ln2_w = ln2w; a.ln2_b = ln2b; a.bias1 = b1; a.bias2 = b2; a.lnn_w = lnn_w; a.lnn_b = lnn_b; a.ln_eps = eps;
   a.timeline = timeline;
   { static const int dbg = [] { const char* v = getenv("VITOCM_TAIL_DEBUG"); return v ? atoi(v) : 0; }(); a.debug = dbg; }
