@@ -58,7 +58,7 @@ def class_flops(cls, D, N, tiles, depth):
     M = tiles * N
     L = depth - 1
     return {"gemm_qkv": 2 * M * D * 3 * D * L, "gemm_proj": 2 * M * D * D * L, "gemm_fc1_gelu": 2 * M * D * 4 * D * L,
-            "gemm_fc2": 2 * M * 4 * D * D * L, "mlp_fused": 4 * M * 4 * D * D * L, "attention": 4 * tiles * N * N * D * L, "gemm_k_last": 2 * M * D * D,
+            "gemm_fc2": 2 * M * 4 * D * D * L, "mlp_fused": 4 * M * 4 * D * D * L, "block_tail": (2 * M * D * D + 4 * M * 4 * D * D) * L, "attention": 4 * tiles * N * N * D * L, "gemm_k_last": 2 * M * D * D,
             "patch_embed": 2 * tiles * (N - 1) * 192 * D}.get(cls, 0)
 
 
