@@ -242,7 +242,54 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
         if constexpr (TL) att_stamp(args, tl, 1, 0, 0, p);   // S_0 issued
         for (int j = 0; j < n_kv; ++j, ++g) {
           fill();
-          // ---- O += P_j V_j
+          constexpr uint32_t idesc_pv = ptx::make_idesc(ATT_BQ, ATT_DH, false, /*B = V is MN-major*/ true, F16 ? 0u : 1u);
+          const int ksteps = kv_len_mma(j) / 16;
+          const uint32_t acc0 = j > 0 ? 1u : 0u;
+          if (nslots == 1 && args.ctrl_hoist) {
+            // Everything PV_j and S_{j+1} need is prepared BEFORE the wait for P_j: the control warp shares its scheduler with four
+            // softmax warps, so every instruction between "P_j seen" and the last MMA costs ~5 clk of the pipeline's serial chain
+            // (descriptor arithmetic + operand-landed checks behind the wait: 850 clk from P_j to S_{j+1} issued, of ~3 250 per block)
+            const bool more = j + 1 < n_kv;
+            const int slot_v = used % AQ_RING, slot_k = (used + 1) % AQ_RING;
+            ptx::mbar_wait(kv_full + 8 * slot_v, (used / AQ_RING) & 1, 55);
+            if (more) ptx::mbar_wait(kv_full + 8 * slot_k, ((used + 1) / AQ_RING) & 1, 52);
+            const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_ring + slot_v * AQ_TILE_BYTES, 1024, 1024);
+            const uint64_t k_desc = ptx::make_smem_desc_sw128(smem_ring + slot_k * AQ_TILE_BYTES, 1024, 0);
+            const uint32_t idesc_s = ptx::make_idesc(ATT_BQ, kv_len_mma(more ? j + 1 : j), false, false, F16 ? 0u : 1u);
+            const uint32_t bar_v = kv_empty + 8 * slot_v, bar_k = kv_empty + 8 * slot_k;
+            if (j == 0 && w > 0) ptx::mbar_wait(o_empty, (w - 1) & 1, 54);   // O still holds the previous item until its rows have been read out
+            // ---- O += P_j V_j
+            ptx::mbar_wait(p_full, g & 1, 53);
+            ptx::tc_fence_after();
+            if constexpr (TL) att_stamp(args, tl, 1, j, 1, p);   // P_j seen
+            if (ksteps == AQ_BKV / 16) {
+#pragma unroll
+              for (int k = 0; k < AQ_BKV / 16; ++k)
+                ptx::umma_bf16_ts(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc_pv, k ? 1u : acc0);
+            } else {
+#pragma unroll 1
+              for (int k = 0; k < ksteps; ++k)
+                ptx::umma_bf16_ts(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc_pv, k ? 1u : acc0);
+            }
+            ptx::umma_commit(bar_v);
+            if constexpr (TL) att_stamp(args, tl, 1, j, 2, p);   // PV_j issued
+            if (more) {
+              // ---- S_{j+1} = Q K_{j+1}^T right behind it
+#pragma unroll
+              for (int k = 0; k < ATT_DH / 16; ++k)
+                ptx::umma_bf16_ss(s_tmem, ptx::desc_advance(q_desc, k * 32), ptx::desc_advance(k_desc, k * 32), idesc_s, k ? 1u : 0u);
+              ptx::umma_commit(bar_k);
+              ptx::umma_commit(s_full);
+              used += 2;
+              if constexpr (TL) att_stamp(args, tl, 1, j + 1, 0, p);   // S_{j+1} issued
+            } else {
+              ptx::umma_commit(o_full);
+              ++used;
+              if (it + stride < args.n_items) load_q(it + stride);   // P_last exists => every S of the item was produced: Q is free
+            }
+            continue;
+          }
+          // ---- packed tail item: every slot's P rows against its own pair's V, then the next S per slot
           ptx::mbar_wait(p_full, g & 1, 53);
           ptx::tc_fence_after();
           if constexpr (TL) att_stamp(args, tl, 1, j, 1, p);   // P_j seen
@@ -250,52 +297,42 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
             ptx::mbar_wait(o_empty, (w - 1) & 1, 54);
             ptx::tc_fence_after();
           }
-          {
-            constexpr uint32_t idesc = ptx::make_idesc(ATT_BQ, ATT_DH, false, /*B = V is MN-major*/ true, F16 ? 0u : 1u);
-            const int ksteps = kv_len_mma(j) / 16;
-            const uint32_t acc0 = j > 0 ? 1u : 0u;
-            if (nslots == 1) {
+          if (nslots == 1) {
+            const int slot = used % AQ_RING;
+            ptx::mbar_wait(kv_full + 8 * slot, (used / AQ_RING) & 1, 55);
+            ptx::tc_fence_after();
+            const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_ring + slot * AQ_TILE_BYTES, 1024, 1024);
+#pragma unroll 1
+            for (int k = 0; k < ksteps; ++k)
+              ptx::umma_bf16_ts(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc_pv, k ? 1u : acc0);
+            ptx::umma_commit(kv_empty + 8 * slot);
+            ++used;
+            if (j == n_kv - 1) ptx::umma_commit(o_full);
+          } else {
+            auto slot_pv = [&](auto ns_tag, auto sl_tag) {
+              if (loaded <= used) fill();
               const int slot = used % AQ_RING;
-              ptx::mbar_wait(kv_full + 8 * slot, (used / AQ_RING) & 1, 55);
+              ptx::mbar_wait(kv_full + 8 * slot, (used / AQ_RING) & 1, 57);
               ptx::tc_fence_after();
               const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_ring + slot * AQ_TILE_BYTES, 1024, 1024);
+              uint32_t lm[4];
+              aq_slot_mask<decltype(ns_tag)::value, decltype(sl_tag)::value>(lm);
               if (ksteps == AQ_BKV / 16) {
 #pragma unroll
                 for (int k = 0; k < AQ_BKV / 16; ++k)
-                  ptx::umma_bf16_ts(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc, k ? 1u : acc0);
+                  ptx::umma_bf16_ts_masked(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc_pv, k ? 1u : acc0, lm);
               } else {
 #pragma unroll 1
                 for (int k = 0; k < ksteps; ++k)
-                  ptx::umma_bf16_ts(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc, k ? 1u : acc0);
+                  ptx::umma_bf16_ts_masked(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc_pv, k ? 1u : acc0, lm);
               }
               ptx::umma_commit(kv_empty + 8 * slot);
               ++used;
-            } else {   // packed item: every slot's P rows against its own pair's V
-              auto slot_pv = [&](auto ns_tag, auto sl_tag) {
-                if (loaded <= used) fill();
-                const int slot = used % AQ_RING;
-                ptx::mbar_wait(kv_full + 8 * slot, (used / AQ_RING) & 1, 57);
-                ptx::tc_fence_after();
-                const uint64_t v_desc = ptx::make_smem_desc_sw128(smem_ring + slot * AQ_TILE_BYTES, 1024, 1024);
-                uint32_t lm[4];
-                aq_slot_mask<decltype(ns_tag)::value, decltype(sl_tag)::value>(lm);
-                if (ksteps == AQ_BKV / 16) {
-#pragma unroll
-                  for (int k = 0; k < AQ_BKV / 16; ++k)
-                    ptx::umma_bf16_ts_masked(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc, k ? 1u : acc0, lm);
-                } else {
-#pragma unroll 1
-                  for (int k = 0; k < ksteps; ++k)
-                    ptx::umma_bf16_ts_masked(o_tmem, s_tmem + k * 8, ptx::desc_advance(v_desc, k * 2048), idesc, k ? 1u : acc0, lm);
-                }
-                ptx::umma_commit(kv_empty + 8 * slot);
-                ++used;
-              };
-              using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>;
-              using I2 = std::integral_constant<int, 2>; using I3 = std::integral_constant<int, 3>; using I4 = std::integral_constant<int, 4>;
-              if (nslots == 2) { slot_pv(I2{}, I0{}); slot_pv(I2{}, I1{}); }
-              else { slot_pv(I4{}, I0{}); slot_pv(I4{}, I1{}); slot_pv(I4{}, I2{}); slot_pv(I4{}, I3{}); }
-            }
+            };
+            using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>;
+            using I2 = std::integral_constant<int, 2>; using I3 = std::integral_constant<int, 3>; using I4 = std::integral_constant<int, 4>;
+            if (nslots == 2) { slot_pv(I2{}, I0{}); slot_pv(I2{}, I1{}); }
+            else { slot_pv(I4{}, I0{}); slot_pv(I4{}, I1{}); slot_pv(I4{}, I2{}); slot_pv(I4{}, I3{}); }
             if (j == n_kv - 1) ptx::umma_commit(o_full);
           }
           if constexpr (TL) att_stamp(args, tl, 1, j, 2, p);   // PV_j issued

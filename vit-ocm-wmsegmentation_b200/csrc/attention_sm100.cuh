@@ -59,6 +59,7 @@ struct AttnArgs {
                         // exact otherwise (softmax is shift invariant, O and l accumulate in fp32).  Only a block that trips
                         // the trigger pays for row_max(), the rescale of O and a second pass of exponentials.
   int n_full_items;     // attn_fwd_quad_kernel: items [0, n_full_items) are full query tiles, items beyond it the packed tails of `pack` pairs each
+  int ctrl_hoist;       // attn_fwd_quad_kernel: 1 = PV_j / S_{j+1} operands prepared before the wait for P_j (VITOCM_ATTN_HOIST, A/B knob)
   int tails_only;       // 1 = the launch covers only the ragged query tail of every pair (item i = the tail item of group i); the full
                         // tiles are computed by attn_fwd_quad_kernel (attention_quad_sm100.cuh)
   int timeline_item;    // diagnostics: which of a CTA's work items (0, 1, ...) the stamps are taken on

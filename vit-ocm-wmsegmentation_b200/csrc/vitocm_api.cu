@@ -638,6 +638,7 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
     const bool tails_here = quad_tails && a.pack > 1;
     static const int quad_pack = [] { const char* v = getenv("VITOCM_ATTN_QUAD_PACK"); return v ? atoi(v) : 2; }();   // 2 or 4
     aq.group_items = 0;
+    { static const int hoist = [] { const char* v = getenv("VITOCM_ATTN_HOIST"); return v ? atoi(v) : 1; }(); aq.ctrl_hoist = hoist; }
     aq.n_items = aq.n_full_items;
     if (tails_here) {   // groups of `pack` pairs: their full tiles, then the one tile their tails share (aq_decode)
       aq.pack = (quad_pack == 4 && a.pack == 4) ? 4 : 2;
@@ -899,6 +900,15 @@ int vitocm_create(const vitocm_config* cfg, vitocm_engine** out) {
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
   if (prop.major != 10) return fail(VITOCM_ERR_CUDA, "libvitocm is built for sm_100a only (device is sm_%d%d)", prop.major, prop.minor);
+  // One device per process (one process per GPU is the deployment model): the launch helpers cache per-function opt-ins
+  // (cudaFuncSetAttribute, cluster occupancy) in process-wide statics, and those are per device.  A second device in the same
+  // process is refused here instead of failing at its first launch.
+  {
+    static std::atomic<int> first_dev{-1};
+    int expect = -1;
+    if (!first_dev.compare_exchange_strong(expect, dev) && expect != dev)
+      return fail(VITOCM_ERR_STATE, "libvitocm: engines of one process must live on one device (first engine on device %d, this one on %d)", expect, dev);
+  }
   vitocm_engine* e = new vitocm_engine();
   e->cfg = *cfg;
   e->split = cfg->precision == VITOCM_FP32 ? 1 : 0;
