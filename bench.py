@@ -617,6 +617,16 @@ def main():
     my_tiles = t1 - t0
     classes = {k: {"ms": v[0], "launches": v[1], "gflop": class_flops(k, a["embed_dim"], N, my_tiles, a["depth"]) / 1e9}
                for k, v in prof.items() if v[1] > 0}
+    if "block_tail" in classes:
+        # the block-tail kernel also computes the NEXT block's QKV projection: every QKV projection of the step that is not a launch of
+        # the QKV GEMM class ran inside it (one engine call per chunk: launches per layer = launches of the block-tail class / (depth - 1))
+        L = a["depth"] - 1
+        per_layer = 2.0 * my_tiles * N * a["embed_dim"] * 3 * a["embed_dim"] / 1e9
+        calls = max(classes["block_tail"]["launches"] // L, 1)
+        qkv_launched = classes.get("gemm_qkv", {"launches": 0})["launches"] / calls      # layers whose QKV projection was a GEMM launch
+        if "gemm_qkv" in classes:
+            classes["gemm_qkv"]["gflop"] = per_layer * qkv_launched
+        classes["block_tail"]["gflop"] += per_layer * (L - qkv_launched)
     for k, c in classes.items():
         c["tflops"] = (c["gflop"] / c["ms"]) if c["ms"] > 0 and c["gflop"] > 0 else None
     peak, peak_src = peak_tflops()

@@ -259,16 +259,17 @@ int vitocm_mlp_fused(vitocm_engine* e, const void* XN, int64_t ld_xn, const void
  * (VITOCM_MLP_TL_ITEM): stamps int64 [64] (layout: MlpArgs::timeline in csrc/mlp_fused_sm100.cuh). */
 int vitocm_mlp_fused_timeline(vitocm_engine* e, const void* XN, int64_t ld_xn, const void* W1, int64_t ldw1, const void* W2, int64_t ldw2,
                               int M, int D, int hidden, const float* bias1, const float* bias2, float* X, int64_t* stamps, void* stream);
-/* The second half of Block.forward in ONE kernel (SSS/dino/vision_transformer.py:88, :110-111, :57-63 and the norm1 of the next
- * block, :107):  X += CTX . Wp^T + bias_p;  X += gelu(LayerNorm(X; ln2) . W1^T + bias1) . W2^T + bias2;  and, when next_ln_w is not
- * NULL, XN = LayerNorm(X; next_ln) in the engine's 16-bit format.  CTX 16-bit [M][ld_ctx], Wp [D][ldwp], W1 [hidden][ldw1],
- * W2 [D][ldw2] (K-major), X fp32 [M][D] in place, XN 16-bit [M][ld_xn].  D = 128 or 384, hidden a multiple of 128, engines with
- * single 16-bit operands.  stamps: NULL, or int64 [64] SM-clock stamps (diagnostics; layout: TailArgs::timeline in
- * csrc/block_tail_sm100.cuh). */
+/* The second half of Block.forward in ONE kernel (SSS/dino/vision_transformer.py:88, :110-111, :57-63, and of the NEXT block :107 and
+ * the qkv Linear of :80):  X += CTX . Wp^T + bias_p;  X += gelu(LayerNorm(X; ln2) . W1^T + bias1) . W2^T + bias2;  when next_ln_w is
+ * not NULL, XN = LayerNorm(X; next_ln) in the engine's 16-bit format;  when Wqkv is not NULL as well, QKV = XN . Wqkv^T + bias_qkv is
+ * written INSTEAD of XN (the normalised rows stay in shared memory).  CTX 16-bit [M][ld_ctx], Wp [D][ldwp], W1 [hidden][ldw1],
+ * W2 [D][ldw2], Wqkv [3D][ldwqkv] (K-major), X fp32 [M][D] in place, XN 16-bit [M][ld_xn], QKV 16-bit [M][ld_qkv].  D = 128 or 384,
+ * hidden a multiple of 128, engines with single 16-bit operands.  stamps: NULL, or int64 [64] SM-clock stamps (diagnostics; layout:
+ * TailArgs::timeline in csrc/block_tail_sm100.cuh). */
 int vitocm_block_tail(vitocm_engine* e, const void* CTX, int64_t ld_ctx, const void* Wp, int64_t ldwp, const float* bias_p, const float* ln2_w,
                       const float* ln2_b, const void* W1, int64_t ldw1, const void* W2, int64_t ldw2, int M, int D, int hidden, const float* bias1,
-                      const float* bias2, float* X, const float* next_ln_w, const float* next_ln_b, void* XN, int64_t ld_xn, int64_t* stamps,
-                      void* stream);
+                      const float* bias2, float* X, const float* next_ln_w, const float* next_ln_b, void* XN, int64_t ld_xn, const void* Wqkv,
+                      int64_t ldwqkv, const float* bias_qkv, void* QKV, int64_t ld_qkv, int64_t* stamps, void* stream);
 /* ctx = MHSA(qkv) for B images of n_tokens tokens: qkv bf16 [B*N][ld], ctx bf16 [B*N][ldo]. */
 int vitocm_attention(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo,
                      void* stream);

@@ -298,7 +298,7 @@ def test_block_tail(M, D, Hd, precision, with_next_ln):
     xn = torch.full((M, 2 * D), float("nan"), device="cuda", dtype=dt)
     check(lib.vitocm_block_tail(eng, ptr(ctx), ctx.stride(0), ptr(Wp), Wp.stride(0), ptr(bp), ptr(g2), ptr(be2), ptr(W1), W1.stride(0), ptr(W2),
                                 W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(x), ptr(gn) if with_next_ln else None,
-                                ptr(ben) if with_next_ln else None, ptr(xn), xn.stride(0), None, cur_stream()))
+                                ptr(ben) if with_next_ln else None, ptr(xn), xn.stride(0), None, 0, None, None, 0, None, cur_stream()))
     torch.cuda.synchronize()
     ref_x, ref_xn = _tail_reference(ctx, Wp, bp, g2, be2, W1, b1, W2, b2, gn, ben, resid, dt)
     tol = 3e-3 if precision == "fp16" else 1.5e-2
@@ -314,6 +314,47 @@ def test_block_tail(M, D, Hd, precision, with_next_ln):
         assert (got - ref_xn).abs().max().item() <= tol_n
     else:
         assert torch.isnan(xn.float()).all()
+
+
+@pytest.mark.parametrize("M,D,Hd", [(785, 384, 1536), (130, 128, 512), (1, 128, 128), (5000, 384, 1536), (80000, 384, 1536), (257, 128, 256),
+                                    (60000, 128, 128)])
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_block_tail_with_next_qkv(M, D, Hd, precision):
+    """The block tail that also computes the NEXT block's QKV projection (the normalised rows never leave shared memory): X as before,
+    QKV against the fp32 statement on the 16-bit rounded normalised rows; XN must stay untouched."""
+    lib = vob._lib.load_library()
+    eng = make_engine(precision=2 if precision == "fp16" else 0)
+    dt = torch.float16 if precision == "fp16" else torch.bfloat16
+    ctx = _rand((M, D), 120).to(dt)
+    Wp = _rand((D, D), 121, 0.05).to(dt)
+    W1 = _rand((Hd, D), 122, 0.06).to(dt)
+    W2 = _rand((D, Hd), 123, 0.03).to(dt)
+    Wq = _rand((3 * D, D), 124, 0.05).to(dt)
+    bp, b1, b2, bq = _rand((D,), 125, 0.1), _rand((Hd,), 126, 0.2), _rand((D,), 127, 0.1), _rand((3 * D,), 128, 0.1)
+    g2, be2 = _rand((D,), 129) * 0.1 + 1, _rand((D,), 130) * 0.1
+    gn, ben = _rand((D,), 131) * 0.1 + 1, _rand((D,), 132) * 0.1
+    resid = _rand((M, D), 133) * 2 + 0.5
+    x = resid.clone()
+    xn = torch.full((M, 2 * D), float("nan"), device="cuda", dtype=dt)
+    qkv = torch.full((M, 3 * D), float("nan"), device="cuda", dtype=dt)
+    check(lib.vitocm_block_tail(eng, ptr(ctx), ctx.stride(0), ptr(Wp), Wp.stride(0), ptr(bp), ptr(g2), ptr(be2), ptr(W1), W1.stride(0), ptr(W2),
+                                W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(x), ptr(gn), ptr(ben), ptr(xn), xn.stride(0), ptr(Wq), Wq.stride(0),
+                                ptr(bq), ptr(qkv), qkv.stride(0), None, cur_stream()))
+    torch.cuda.synchronize()
+    ref_x, ref_xn = _tail_reference(ctx, Wp, bp, g2, be2, W1, b1, W2, b2, gn, ben, resid, dt)
+    tol = 3e-3 if precision == "fp16" else 1.5e-2
+    scale = (ref_x - resid).abs().max().item()
+    assert (x - ref_x).abs().max().item() <= tol * scale + 1e-4
+    assert torch.isnan(xn.float()).all()
+    got = qkv.float()
+    assert torch.isfinite(got).all()
+    # from the kernel's own X (so that the error of X does not count twice): LayerNorm -> 16 bits -> Linear -> 16 bits
+    xn_k = torch.nn.functional.layer_norm(x, (D,), gn, ben, 1e-6).to(dt).float()
+    ref_q = xn_k @ Wq.float().T + bq
+    err = (got - ref_q).abs().max().item()
+    # one 16-bit ulp of the output + normalised rows that landed on the neighbouring 16-bit value (each worth |w| 2^-8 / 2^-11)
+    assert err <= (6e-3 if precision == "fp16" else 4e-2) * ref_q.abs().max().item(), (err, ref_q.abs().max().item())
+    assert (got - ref_q).abs().mean().item() <= (4e-4 if precision == "fp16" else 3e-3) * ref_q.abs().max().item()
 
 
 def test_block_tail_matches_separate_kernels(engine):
@@ -332,7 +373,7 @@ def test_block_tail_matches_separate_kernels(engine):
     x = resid.clone()
     xn = torch.zeros((M, 2 * D), device="cuda", dtype=dt)
     check(lib.vitocm_block_tail(engine, ptr(ctx), ctx.stride(0), ptr(Wp), Wp.stride(0), ptr(bp), ptr(g2), ptr(be2), ptr(W1), W1.stride(0), ptr(W2),
-                                W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(x), ptr(gn), ptr(ben), ptr(xn), xn.stride(0), None, cur_stream()))
+                                W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(x), ptr(gn), ptr(ben), ptr(xn), xn.stride(0), None, 0, None, None, 0, None, cur_stream()))
     y = resid.clone()
     yn = torch.zeros((M, 2 * D), device="cuda", dtype=dt)
     check(lib.vitocm_gemm_ln(engine, ptr(ctx), ctx.stride(0), ptr(Wp), Wp.stride(0), M, D, D, ptr(bp), ptr(y), ptr(g2), ptr(be2), ptr(yn),

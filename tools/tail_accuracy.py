@@ -31,7 +31,7 @@ for precision, dt in ((2, torch.float16), (0, torch.bfloat16)):
         xa = resid.clone()
         xn = torch.zeros(M, 2 * D, device="cuda", dtype=dt)
         check(lib.vitocm_block_tail(eng, ptr(ctx), ctx.stride(0), ptr(Wp), Wp.stride(0), ptr(bp), ptr(g2), ptr(be2), ptr(W1), W1.stride(0), ptr(W2),
-                                    W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(xa), ptr(gn), ptr(ben), ptr(xn), xn.stride(0), None, cur_stream()))
+                                    W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(xa), ptr(gn), ptr(ben), ptr(xn), xn.stride(0), None, 0, None, None, 0, None, cur_stream()))
         xb = resid.clone()
         yn = torch.zeros(M, 2 * D, device="cuda", dtype=dt)
         check(lib.vitocm_gemm_ln(eng, ptr(ctx), ctx.stride(0), ptr(Wp), Wp.stride(0), M, D, D, ptr(bp), ptr(xb), ptr(g2), ptr(be2), ptr(yn),

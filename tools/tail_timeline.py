@@ -25,12 +25,16 @@ bp, b1, b2 = rnd(D, sc=0.1), rnd(Hd, sc=0.2), rnd(D, sc=0.1)
 g2, be2, gn, ben = rnd(D, sc=0.1) + 1, rnd(D, sc=0.1), rnd(D, sc=0.1) + 1, rnd(D, sc=0.1)
 x = rnd(M, D)
 xn = torch.zeros(M, 2 * D, device="cuda", dtype=dt)
+with_qkv = int(sys.argv[3]) if len(sys.argv) > 3 else 1   # 1: the kernel also computes the next block's QKV projection
+Wq, bq = rnd(3 * D, D, sc=0.05).to(dt), rnd(3 * D, sc=0.1)
+qkv = torch.zeros(M, 3 * D, device="cuda", dtype=dt)
+wq_p, bq_p, qkv_p = (ptr(Wq), ptr(bq), ptr(qkv)) if with_qkv else (None, None, None)
 stamps = torch.zeros(64, device="cuda", dtype=torch.int64)
 
 
 def run(st):
     check(lib.vitocm_block_tail(eng, ptr(ctx), ctx.stride(0), ptr(Wp), Wp.stride(0), ptr(bp), ptr(g2), ptr(be2), ptr(W1), W1.stride(0), ptr(W2),
-                                W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(x), ptr(gn), ptr(ben), ptr(xn), xn.stride(0), st, cur_stream()))
+                                W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(x), ptr(gn), ptr(ben), ptr(xn), xn.stride(0), wq_p, Wq.stride(0), bq_p, qkv_p, qkv.stride(0), st, cur_stream()))
 
 
 for _ in range(3):
@@ -44,8 +48,8 @@ for _ in range(n):
 e1.record()
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / n
-flop = 2.0 * M * D * (D + 2 * Hd)
-print(f"block tail: tiles={tiles} M={M} precision={precision}: {us:.1f} us/launch, {flop / us / 1e6:.1f} TFLOP/s")
+flop = 2.0 * M * D * (D + 2 * Hd + (3 * D if with_qkv else 0))
+print(f"block tail: tiles={tiles} M={M} precision={precision} with_qkv={with_qkv}: {us:.1f} us/launch, {flop / us / 1e6:.1f} TFLOP/s")
 run(ptr(stamps))
 torch.cuda.synchronize()
 s = stamps.cpu().tolist()
@@ -57,3 +61,6 @@ print("epilogue w0: ep1 steps=%d %d %d  combined=%d" % (rel(15), rel(16), rel(17
 for c in range(0, 5, 2):
     print(" chunk %2d: fc1 complete=%d gelu done=%d handed=%d | mma: fc1 issued=%d gelu seen=%d" % (c, rel(3 * c), rel(3 * c + 1), rel(3 * c + 2), rel(36 + 2 * c), rel(36 + 2 * c + 1)))
 print("epilogue w0: OUT complete=%d  ep2 stats=%d  steps stored=%d %d %d  stores read=%d  ep2 done=%d" % (rel(61), rel(54), rel(20), rel(21), rel(22), rel(24), rel(62)))
+if with_qkv:
+    print("QKV chunks, epilogue w0 (its group's first two): " + " | ".join("complete=%d packed=%d staging free=%d stored=%d" % tuple(rel(25 + 4 * k + e) for e in range(4)) for k in range(2)))
+    print("QKV chunks, MMA thread issued: " + " ".join(str(rel(46 + c)) for c in range(8)))

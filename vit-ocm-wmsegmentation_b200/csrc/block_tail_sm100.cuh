@@ -19,6 +19,10 @@
 //   chunks:  fc1 -> GELU -> fc2 exactly as in the fused MLP kernel, except that EVERY fc2 MMA accumulates: OUT already holds the
 //            residual rows, so the tensor core performs the residual add in fp32 and X never enters shared memory again
 //   ep 2:    x = OUT + b2 -> statistics -> fp32 boxes -> TMA store of X;  (x - mean) rstd gamma + beta -> 16-bit boxes -> TMA store
+//   qkv:     (optional, TailArgs::n_qkv_chunks > 0) the NEXT block's QKV projection: ep 2 then leaves the normalised rows in smem_a
+//            instead of HBM, and QKV[128 x 3D] = XN . Wqkv^T + b runs as 3D / 128 more chunks through the hidden-chunk accumulator
+//            (fc1-shaped MMAs; epilogue: bias, 16-bit, the warp's own 4 KB region of the GELU buffer, one TMA store per warp) --
+//            the stand-alone QKV GEMM, its launch and the XN round trip through HBM (1.5 KB per row) disappear
 // The item boundary is serial (ep 2 of item t, proj and ep 1 of item t + 1 all need the OUT columns: 384 + 128 of 512 TMEM
 // columns are in use), so all 16 epilogue warps work on it; between the boundaries the two groups of 8 take the hidden chunks in
 // turn as before.  Weights stream through the same ring: proj's [D / NP2 x 64] tiles have the shape of fc2's.
@@ -40,12 +44,15 @@ struct TailArgs {
   const float* bias2;  // [D]
   const float* lnn_w;  // [D] the LayerNorm that reads X next, or nullptr (then no XN is written)
   const float* lnn_b;
+  const float* bias_qkv;   // [n_qkv_chunks * 128] bias of the next block's QKV projection (n_qkv_chunks > 0)
+  int n_qkv_chunks;        // 0: XN = LayerNorm(X; lnn) goes to HBM (tmap_xn); 3 D / 128: it stays in shared memory and QKV = XN . Wqkv^T + bias_qkv
+                           // is written instead (tmap_wqkv, tmap_qkv); needs lnn_w
   float ln_eps;
   // diagnostics (vitocm_block_tail_timeline) or nullptr: 64 SM-clock stamps (low 32 bits) of the leader CTA of pair 0 on its work item
   // `timeline_item`: [3 c + e], c < 5: epilogue warp 0 (group 0) on chunk c as MlpArgs; [36 + 2 c + e], c < 5: MMA thread as MlpArgs;
   // MMA thread: [60] item start (CTX landed), [56] OUT free, proj issued, [59] ep 1 done (mid_ready seen);
   // epilogue warp 0: [57] proj complete, [58] ep 1 pass 1 done, [55] ep 1 handed over, [61] OUT complete, [54] ep 2 statistics known,
-  // [62] ep 2 done; [15 + s] ep 1 pass 1 step s done, [18] ep 1 statistics combined, [20 + s] ep 2 pass 2 step s stored, [24] ep 2 stores read
+  // [62] ep 2 done; [25 + 4 k + e]: the group's k-th QKV chunk (k < 2): accumulator complete, packed, staging free, stored; [46 + c]: MMA thread, QKV chunk c issued; [15 + s] ep 1 pass 1 step s done, [18] ep 1 statistics combined, [20 + s] ep 2 pass 2 step s stored, [24] ep 2 stores read
   long long* timeline;
   int timeline_item;
   int debug;           // bit 0: no MMAs (barrier traffic only), bit 1: ep 1 neither loads nor awaits the fp32 rows, bit 2: ep 2 issues no TMA stores
@@ -112,7 +119,9 @@ __global__ void __launch_bounds__(TailCfg<KB1>::THREADS, 1)
 block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, const __grid_constant__ CUtensorMap tmap_wp,
                           const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
                           const __grid_constant__ CUtensorMap tmap_x /*fp32 rows: 32 x 32 boxes, loads and stores*/,
-                          const __grid_constant__ CUtensorMap tmap_xn /*16-bit normalised rows out: 32 x 32 boxes*/, const TailArgs args) {
+                          const __grid_constant__ CUtensorMap tmap_xn /*16-bit normalised rows out: 32 x 32 boxes*/,
+                          const __grid_constant__ CUtensorMap tmap_wqkv /*next block's QKV weight [3D][D]: 64 x 64 boxes*/,
+                          const __grid_constant__ CUtensorMap tmap_qkv /*16-bit QKV rows out: 64 x 32 boxes*/, const TailArgs args) {
   using Cfg = TailCfg<KB1>;
   constexpr int D = Cfg::D, NP2 = Cfg::NP2, BN2 = Cfg::BN2, T1 = Cfg::T1, SLOTS = Cfg::SLOTS, EW = Cfg::EW, CW = Cfg::CW, NS = Cfg::NS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -134,6 +143,7 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
   const uint32_t proj_full = a_full + 96;             // proj complete in TMEM (both CTAs)
   const uint32_t mid_ready = a_full + 104;            // ep 1 done in both CTAs: residual rows in TMEM, norm2 rows in smem_a (leader's copy)
   const uint32_t tmem_ptr_smem = a_full + 112;
+  const uint32_t xn_ready = a_full + 128;             // ep 2 done in both CTAs with the next norm's rows in smem_a (QKV chunks; leader's copy)
   const uint32_t stage_free = a_full + 120;           // this CTA's epilogue warps no longer use smem_a as staging space (ep 2 stores have been read)
   const uint32_t xbox_bar = bars + 256;               // [EW][2] fp32 row boxes landed (per warp: box in H, box in smem_a)
   const uint32_t smem_tl = bars + 512;                // [64] diagnostics stamps
@@ -147,6 +157,7 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
   const int tile0 = static_cast<int>(blockIdx.x) / 2;
   const int tstep = static_cast<int>(gridDim.x) / 2;
   const int NC = args.hidden / MLP_HC;
+  const int NQ = args.n_qkv_chunks;   // QKV chunks behind the MLP chunks of every item (0: none)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
@@ -155,6 +166,8 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
     ptx::prefetch_tmap(&tmap_w2);
     ptx::prefetch_tmap(&tmap_x);
     ptx::prefetch_tmap(&tmap_xn);
+    ptx::prefetch_tmap(&tmap_wqkv);
+    ptx::prefetch_tmap(&tmap_qkv);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < SLOTS; ++s) {
@@ -174,6 +187,7 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
     ptx::mbar_init(proj_full, 1);
     ptx::mbar_init(mid_ready, 2 * EW);
     ptx::mbar_init(stage_free, EW);
+    ptx::mbar_init(xn_ready, 2 * EW);
     for (int i = 0; i < 2 * EW; ++i) ptx::mbar_init(xbox_bar + 8 * i, 1);
     ptx::fence_barrier_init();
   }
@@ -243,6 +257,12 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
             if (c + 2 < NC) load_fc1(c + 2);
             load_fc2(c);
           }
+          for (int c = 0; c < NQ; ++c)   // the next block's QKV weight: fc1-shaped chunks of 128 output columns
+            for (int kb = 0; kb < KB1; kb += T1) {
+              acquire(T1 * 8192);
+              for (int kk = 0; kk < T1; ++kk) box(&tmap_wqkv, kk * 8192, (kb + kk) * GEMM_BK, c * MLP_HC + rank * 64);
+              release();
+            }
         }
       }
     } else if (warp == 3) {
@@ -251,14 +271,14 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
         int t = 0;
         for (int tile = tile0; tile < tiles_m; tile += tstep, ++t) {
           ptx::mbar_wait(a_empty, (t & 1) ^ 1, 32);   // the previous item's fc1 MMAs no longer read smem_a
-          if (t > 0) {
-            // smem_a is the previous item's output staging space until its stores have been read (ep 2): meanwhile the tile goes to L2
-            for (int kb = 0; kb < KB1; ++kb) ptx::tma_prefetch_2d(&tmap_a, kb * GEMM_BK, tile * 2 * GEMM_BM + rank * GEMM_BM);
-            ptx::mbar_wait(stage_free, (t - 1) & 1, 29);
-          }
+          // (NQ == 0: smem_a is also the previous item's output staging space until its stores have been read, ep 2; with QKV chunks
+          // a_empty already lies behind ep 2)
+          if (t > 0 && NQ == 0) ptx::mbar_wait(stage_free, (t - 1) & 1, 29);
           if (rank == 0) ptx::mbar_arrive_expect_tx(a_full, 2 * Cfg::A_BYTES);
           for (int kb = 0; kb < KB1; ++kb)
             ptx::tma_load_2d_2cta(smem_a + kb * MLP_KB_BYTES, &tmap_a, a_full, kb * GEMM_BK, tile * 2 * GEMM_BM + rank * GEMM_BM);
+          if (tile + tstep < tiles_m)   // the next item's tile on its way to L2: its load is issued late (behind this item's last use of smem_a)
+            for (int kb = 0; kb < KB1; ++kb) ptx::tma_prefetch_2d(&tmap_a, kb * GEMM_BK, (tile + tstep) * 2 * GEMM_BM + rank * GEMM_BM);
         }
       }
     } else if (warp == 1) {
@@ -269,10 +289,11 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
         const uint64_t a_desc0 = ptx::make_smem_desc_sw128(smem_a, 1024, 0);
         const uint64_t h_desc0 = ptx::make_smem_desc_sw128(smem_h, 1024, 0);
         const uint64_t w_desc0 = ptx::make_smem_desc_sw128(smem_w, 1024, 0);
-        const uint32_t h_tmem = tmem_base + MLP_H_COL;
         int slot = 0;
         uint32_t phase = 0;
-        int g1 = 0, g2 = 0;   // fc1 / fc2 chunks issued so far (all items): phase counters
+        int g1 = 0;           // fc1-shaped chunks (hidden chunks AND QKV chunks) issued so far, all items: phase counter of h_full / h_tmem_empty,
+                              // chunk g1 belongs to epilogue group g1 & 1
+        int f2[2] = {0, 0};   // fc2 chunks consumed from each group's gelu buffer so far: phases of h_smem_full / h_smem_empty
         int t = 0;
         bool tl = false;
         auto issue_proj = [&]() {
@@ -296,9 +317,15 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
           }
           ptx::umma_commit_2cta_mask(proj_full, pair_mask);
         };
-        auto issue_fc1 = [&](int c) {
-          if (g1 > 0) {   // the previous chunk has been read out of the TMEM accumulator (by the group of its parity)
-            ptx::mbar_wait(h_tmem_empty + 8 * ((g1 - 1) & 1), ((g1 - 1) >> 1) & 1, 33);
+        // one fc1-shaped chunk (128 output columns, K = D): hidden chunk c of W1 into the hidden-chunk accumulator (acc_col = MLP_H_COL,
+        // behind = 1: the chunk before it used the same columns), or a QKV chunk -- those alternate between the hidden-chunk accumulator
+        // and the first 128 OUT columns (free between ep 2 and the next item's proj), so the tensor core never waits for the epilogue
+        // of the chunk it has just finished (behind = 2: the columns' previous user is the chunk before last; 0: nobody to wait for)
+        auto issue_chunk = [&](int c, bool last_use_of_a, uint32_t acc_col = MLP_H_COL, int behind = 1) {
+          const uint32_t h_tmem = tmem_base + acc_col;
+          if (behind > 0 && g1 >= behind) {   // the accumulator's previous user has been read out of TMEM (by the group of its parity)
+            const int u = g1 - behind;
+            ptx::mbar_wait(h_tmem_empty + 8 * (u & 1), (u >> 1) & 1, 33);
             ptx::tc_fence_after();
           }
 #pragma unroll 1
@@ -320,14 +347,18 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
           }
           ptx::umma_commit_2cta_mask(h_full + 8 * (g1 & 1), pair_mask);
           if (c < 5) mlp_stamp(tl, smem_tl, 36 + 2 * c);
-          if (c + 1 == NC) ptx::umma_commit_2cta_mask(a_empty, pair_mask);   // last fc1 of the item: smem_a may take the next CTX tile once it retires
+          if (c >= 100 && c < 108) mlp_stamp(tl, smem_tl, 46 + (c - 100));   // QKV chunk c - 100 issued
+          if (last_use_of_a) ptx::umma_commit_2cta_mask(a_empty, pair_mask);   // smem_a may take the next CTX tile once this chunk retires
           ++g1;
         };
+        int gbase = 0;   // g1 of the item's first hidden chunk
+        auto issue_fc1 = [&](int c) { issue_chunk(c, NQ == 0 && c + 1 == NC); };
         auto issue_fc2 = [&](int c) {
-          ptx::mbar_wait_cluster(h_smem_full + 8 * (g2 & 1), (g2 >> 1) & 1, 35);   // gelu(chunk) sits in both CTAs' shared memory
+          const int g = (gbase + c) & 1;   // the epilogue group (and gelu buffer) of hidden chunk c
+          ptx::mbar_wait_cluster(h_smem_full + 8 * g, f2[g] & 1, 35);   // gelu(chunk) sits in both CTAs' shared memory
           ptx::tc_fence_after();
           if (c < 5) mlp_stamp(tl, smem_tl, 36 + 2 * c + 1);
-          const uint64_t hdesc = ptx::desc_advance(h_desc0, (g2 & 1) * Cfg::H_BYTES);   // this chunk's group's buffer
+          const uint64_t hdesc = ptx::desc_advance(h_desc0, g * Cfg::H_BYTES);
 #pragma unroll 1
           for (int kb2 = 0; kb2 < 2; ++kb2) {
             const uint64_t adesc = ptx::desc_advance(hdesc, kb2 * MLP_KB_BYTES);
@@ -345,8 +376,8 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
               if (++slot == SLOTS) { slot = 0; phase ^= 1; }
             }
           }
-          ptx::umma_commit_2cta_mask(h_smem_empty + 8 * (g2 & 1), pair_mask);
-          ++g2;
+          ptx::umma_commit_2cta_mask(h_smem_empty + 8 * g, pair_mask);
+          ++f2[g];
         };
         for (int tile = tile0; tile < tiles_m; tile += tstep, ++t) {
           tl = args.timeline != nullptr && blockIdx.x == 0 && t == args.timeline_item;
@@ -362,6 +393,7 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
           ptx::mbar_wait_cluster(mid_ready, t & 1, 39);   // residual rows in TMEM, norm2 rows in both CTAs' smem_a
           ptx::tc_fence_after();
           mlp_stamp(tl, smem_tl, 59);
+          gbase = g1;
           issue_fc1(0);
           if (NC > 1) issue_fc1(1);
           issue_fc2(0);
@@ -371,6 +403,14 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
             issue_fc2(c);
           }
           ptx::umma_commit_2cta_mask(out_full, pair_mask);
+          if (NQ > 0) {   // the next block's QKV projection on the rows ep 2 leaves in smem_a
+            ptx::mbar_wait_cluster(xn_ready, t & 1, 28);
+            ptx::tc_fence_after();
+            for (int c = 0; c < NQ; ++c) issue_chunk(c + 100, c + 1 == NQ, (c & 1) ? 0u : static_cast<uint32_t>(MLP_H_COL), c == 0 ? 1 : (c == 1 ? 0 : 2));
+            // both accumulators have been read out before the next item's proj (OUT columns) and first hidden chunk are issued
+            for (int u = g1 - 1; u >= 0 && u >= g1 - 2; --u) ptx::mbar_wait(h_tmem_empty + 8 * (u & 1), (u >> 1) & 1, 27);
+            ptx::tc_fence_after();
+          }
         }
       }
     }
@@ -398,7 +438,8 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
     const uint32_t my_smem_full = ptx::mapa(h_smem_full + 8 * grp, 0);
     const uint32_t mid_ready_leader = ptx::mapa(mid_ready, 0);
     int cnt_h = 0, cnt_a = 0;   // boxes consumed so far: phases of xb_h / xb_a
-    int n0 = 0;                 // global index of the item's first chunk (all items of this CTA)
+    int n0 = 0;                 // global index of the item's first fc1-shaped chunk (hidden + QKV chunks of all items of this CTA)
+    int k2 = 0;                 // hidden chunks this group has handed to fc2 so far: phase of its h_smem_empty
     int t = 0;
     auto load_xbox = [&](uint32_t dst, uint32_t bar, int col, int row_g) {   // lane 0
       ptx::mbar_arrive_expect_tx(bar, 4096);
@@ -425,7 +466,7 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
       rstd = rsqrtf(m2 * (1.0f / static_cast<float>(D)) + args.ln_eps);
     };
     if (tile0 < tiles_m && lane == 0 && !(args.debug & 2)) load_xbox(box_h, xb_h, col0, tile0 * 2 * GEMM_BM + rank * GEMM_BM + q * 32);
-    for (int tile = tile0; tile < tiles_m; tile += tstep, ++t, n0 += NC) {
+    for (int tile = tile0; tile < tiles_m; tile += tstep, ++t, n0 += NC + NQ) {
       const bool tl = args.timeline != nullptr && blockIdx.x == 0 && t == args.timeline_item && ew == 0 && lane == 0;
       const int row_g = tile * 2 * GEMM_BM + rank * GEMM_BM + q * 32;   // first row of this warp's boxes
       // ------------------------------------------------------------------ ep 1: residual add + norm2
@@ -548,7 +589,12 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
         }
         if (c < 5) mlp_stamp(tl, smem_tl, 3 * c + 1);
         // this group's H buffer is free once fc2 of its previous chunk has retired
-        if (n > 1) ptx::mbar_wait(h_smem_empty + 8 * grp, ((n >> 1) - 1) & 1, 41);
+        if (k2 > 0) ptx::mbar_wait(h_smem_empty + 8 * grp, (k2 - 1) & 1, 41);
+        ++k2;
+        if (NQ > 0) {   // ... and once the TMA store of this warp's last QKV chunk has read its region
+          if (lane == 0) ptx::bulk_wait_read0();
+          __syncwarp();
+        }
         const uint32_t tile_addr = my_h + ch * MLP_KB_BYTES + row * 128;
 #pragma unroll
         for (int s = 0; s < NSUB; ++s)
@@ -614,9 +660,10 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) y[j] += __uint_as_float(r[j]);
-        const uint32_t xbox = (s & 1) ? box_a : box_h;
-        if (s >= 2) {   // the store of step s - 2 has read this box
-          if (lane == 0) { if (want_xn) ptx::bulk_wait_read2(); else ptx::bulk_wait_read1(); }
+        const bool to_smem = NQ > 0;   // the normalised rows feed the QKV chunks from smem_a: no staging space there, fp32 boxes through box_h only
+        const uint32_t xbox = (!to_smem && (s & 1)) ? box_a : box_h;
+        if (to_smem ? s >= 1 : s >= 2) {   // the store that used this box last has read it
+          if (lane == 0) { if (to_smem) ptx::bulk_wait_read0(); else if (want_xn) ptx::bulk_wait_read2(); else ptx::bulk_wait_read1(); }
           __syncwarp();
         }
         const uint32_t rowaddr = xbox + lane * 128;
@@ -641,29 +688,92 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
             const float v2 = (y[4 * j + 2] - mean) * rstd * g4.z + b4.z, v3 = (y[4 * j + 3] - mean) * rstd * g4.w + b4.w;
             pk[2 * j] = ptx::pack_h2<F16>(v0, v1); pk[2 * j + 1] = ptx::pack_h2<F16>(v2, v3);
           }
-          if (s >= 1) {   // the previous 16-bit store has read xn_box (only this step's fp32 store may still be pending)
-            if (lane == 0) ptx::bulk_wait_read1();
-            __syncwarp();
-          }
+          if (to_smem) {   // half of a 128-byte row of k-block col / 64 of the A tile (SWIZZLE_128B), as the norm2 rows in ep 1
+            const uint32_t arow = smem_a + (col >> 6) * MLP_KB_BYTES + row * 128;
+            const int c16 = (col & 63) >> 3;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)   // 32 x 32 16-bit box, SWIZZLE_64B
-            ptx::sts_v4(xn_box + lane * 64 + ((j ^ sw2) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0 && !(args.debug & 4)) {
-            ptx::tma_store_2d(&tmap_xn, xn_box, col, row_g);
-            ptx::bulk_commit();
+            for (int j = 0; j < 4; ++j)
+              ptx::sts_v4(arow + (((c16 + j) ^ (row & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          } else {
+            if (s >= 1) {   // the previous 16-bit store has read xn_box (only this step's fp32 store may still be pending)
+              if (lane == 0) ptx::bulk_wait_read1();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)   // 32 x 32 16-bit box, SWIZZLE_64B
+              ptx::sts_v4(xn_box + lane * 64 + ((j ^ sw2) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !(args.debug & 4)) {
+              ptx::tma_store_2d(&tmap_xn, xn_box, col, row_g);
+              ptx::bulk_commit();
+            }
           }
         }
       }
-      // every staging box has been read: smem_a goes to the CTX-tile producer, box_h receives the next item's first fp32 rows
-      if (lane == 0) {
-        ptx::bulk_wait_read0();
-        mlp_stamp(tl, smem_tl, 24);
-        ptx::mbar_arrive(stage_free);
-        if (tile + tstep < tiles_m && !(args.debug & 2)) load_xbox(box_h, xb_h, col0, (tile + tstep) * 2 * GEMM_BM + rank * GEMM_BM + q * 32);
+      if (NQ > 0) {
+        // ------------------------------------------------------------------ the next block's QKV chunks
+        ptx::fence_proxy_async_smem();   // the normalised rows in smem_a, for the tensor core
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_remote(ptx::mapa(xn_ready, 0));
+        const int nq0 = n0 + NC;
+        for (int c = (nq0 + grp) & 1; c < NQ; c += 2) {
+          const int n = nq0 + c;          // (n & 1) == grp
+          ptx::mbar_wait(my_h_full, (n >> 1) & 1, 46);
+          ptx::tc_fence_after();
+          const int ts = c >> 1;   // diagnostics: this group's first two QKV chunks
+          if (ts < 2) mlp_stamp(tl, smem_tl, 25 + 4 * ts);
+          uint32_t r[NSUB][32];
+          ptx::tmem_ld_32x32b_x64_wait(lane_taddr + ((c & 1) ? 0 : MLP_H_COL) + ch * CPW, r[0], r[1]);   // (QKV chunks alternate between two accumulators)
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_leader(my_tmem_empty);
+          uint32_t pk[NSUB][16];
+#pragma unroll
+          for (int s = 0; s < NSUB; ++s) {
+            const float* bp = args.bias_qkv + c * MLP_HC + ch * CPW + s * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + j);
+              pk[s][2 * j] = ptx::pack_h2<F16>(__uint_as_float(r[s][4 * j]) + b4.x, __uint_as_float(r[s][4 * j + 1]) + b4.y);
+              pk[s][2 * j + 1] = ptx::pack_h2<F16>(__uint_as_float(r[s][4 * j + 2]) + b4.z, __uint_as_float(r[s][4 * j + 3]) + b4.w);
+            }
+          }
+          // staging = this warp's own 4 KB region of its group's gelu buffer (32 rows x 64 columns, SWIZZLE_128B = box_h): free once
+          // the warp's previous store has read it (the fp32 boxes of ep 2, the QKV chunk before this one)
+          if (ts < 2) mlp_stamp(tl, smem_tl, 26 + 4 * ts);
+          if (lane == 0) ptx::bulk_wait_read0();
+          __syncwarp();
+          if (ts < 2) mlp_stamp(tl, smem_tl, 27 + 4 * ts);
+#pragma unroll
+          for (int s = 0; s < NSUB; ++s)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              ptx::sts_v4(box_h + lane * 128 + (((s * 4 + j) ^ sw) << 4), pk[s][4 * j], pk[s][4 * j + 1], pk[s][4 * j + 2], pk[s][4 * j + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(args.debug & 4)) {
+            ptx::tma_store_2d(&tmap_qkv, box_h, c * MLP_HC + ch * CPW, row_g);
+            ptx::bulk_commit();
+          }
+          if (ts < 2) mlp_stamp(tl, smem_tl, 28 + 4 * ts);
+        }
+        if (lane == 0) {   // box_h goes on to receive the next item's first fp32 rows
+          ptx::bulk_wait_read0();
+          mlp_stamp(tl, smem_tl, 24);
+          if (tile + tstep < tiles_m && !(args.debug & 2)) load_xbox(box_h, xb_h, col0, (tile + tstep) * 2 * GEMM_BM + rank * GEMM_BM + q * 32);
+        }
+        __syncwarp();
+      } else {
+        // every staging box has been read: smem_a goes to the CTX-tile producer, box_h receives the next item's first fp32 rows
+        if (lane == 0) {
+          ptx::bulk_wait_read0();
+          mlp_stamp(tl, smem_tl, 24);
+          ptx::mbar_arrive(stage_free);
+          if (tile + tstep < tiles_m && !(args.debug & 2)) load_xbox(box_h, xb_h, col0, (tile + tstep) * 2 * GEMM_BM + rank * GEMM_BM + q * 32);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       mlp_stamp(tl, smem_tl, 62);
     }
     if (lane == 0) ptx::bulk_wait_all0();   // global writes complete before the CTA exits

@@ -535,7 +535,7 @@ int run_mlp_fused(const vitocm_engine* e, const void* XN, long long ld_xn, const
 // the shape / engine has no instantiation (the caller then runs the separate kernels).
 template <int KB1, bool F16>
 int launch_block_tail(const CUtensorMap& ta, const CUtensorMap& twp, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx,
-                      const CUtensorMap& txn, const TailArgs& a, int num_sms, cudaStream_t st) {
+                      const CUtensorMap& txn, const CUtensorMap& twqkv, const CUtensorMap& tqkv, const TailArgs& a, int num_sms, cudaStream_t st) {
   using Cfg = TailCfg<KB1>;
   static int max_clusters = -1;
   auto kern = block_tail_tcgen05_kernel<KB1, F16>;
@@ -557,44 +557,57 @@ int launch_block_tail(const CUtensorMap& ta, const CUtensorMap& twp, const CUten
   }
   const int tiles = (a.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
   cfg.gridDim = dim3(2 * (tiles < max_clusters ? tiles : max_clusters));
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, twp, tw1, tw2, tx, txn, a));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, twp, tw1, tw2, tx, txn, twqkv, tqkv, a));
   LAUNCH_CHECK();
   return 0;
 }
 
+// Wqkv != nullptr (needs lnn_w): the kernel also computes the NEXT block's QKV = LayerNorm(X; lnn) . Wqkv^T + bqkv into QKV [M][ld_qkv]
+// and XN is not written.
 int run_block_tail(const vitocm_engine* e, const void* CTX, long long ld_ctx, const void* Wp, long long ldwp, const float* bp,
                    const float* ln2w, const float* ln2b, const void* W1, long long ldw1, const void* W2, long long ldw2, int M, int D, int Hd,
                    const float* b1, const float* b2, float* X, const float* lnn_w, const float* lnn_b, float eps, void* XN, long long ld_xn,
+                   const void* Wqkv, long long ldwqkv, const float* bqkv, void* QKV, long long ld_qkv,
                    cudaStream_t st, bool force = false, long long* timeline = nullptr) {
   // VITOCM_FUSE_TAIL: 0 = never (proj + LayerNorm GEMM, fused MLP and LayerNorm as separate kernels), 1 = default
   static const int mode = [] { const char* v = getenv("VITOCM_FUSE_TAIL"); return v == nullptr ? 1 : atoi(v); }();
   if (mode == 0 && !force) return 1;
   if (e->split || M <= 0 || (D != 128 && D != 384) || Hd % MLP_HC != 0) return 1;
-  const float* vecs[7] = {bp, ln2w, ln2b, b1, b2, lnn_w, lnn_b};
-  for (int i = 0; i < 7; ++i) {
+  const float* vecs[8] = {bp, ln2w, ln2b, b1, b2, lnn_w, lnn_b, bqkv};
+  for (int i = 0; i < 8; ++i) {
     if (i < 5 && vecs[i] == nullptr) return 1;
     if ((reinterpret_cast<uintptr_t>(vecs[i]) & 15) != 0) return 1;
   }
-  if ((lnn_w == nullptr) != (lnn_b == nullptr) || (lnn_w != nullptr && XN == nullptr)) return 1;
+  if ((lnn_w == nullptr) != (lnn_b == nullptr)) return 1;
+  const bool with_qkv = Wqkv != nullptr;
+  if (with_qkv && (lnn_w == nullptr || bqkv == nullptr || QKV == nullptr)) return 1;
+  if (!with_qkv && lnn_w != nullptr && XN == nullptr) return 1;
   ProfScope prof(PC_TAIL, st);
-  CUtensorMap ta, twp, tw1, tw2, tx, txn;
+  CUtensorMap ta, twp, tw1, tw2, tx, txn, twqkv, tqkv;
   const int w2_rows = D == 384 ? 96 : 64;   // one CTA's half of a [BN2 x 64] tile: BN2 = 192 at D = 384
   TRY(make_tmap_bf16(&ta, CTX, M, D, ld_ctx, GEMM_BM));
   TRY(make_tmap_bf16(&twp, Wp, D, D, ldwp, w2_rows));
   TRY(make_tmap_bf16(&tw1, W1, Hd, D, ldw1, 64));
   TRY(make_tmap_bf16(&tw2, W2, D, Hd, ldw2, w2_rows));
   TRY(make_tmap(&tx, X, true, D, M, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B));
-  if (lnn_w != nullptr) TRY(make_tmap(&txn, XN, false, ld_xn, M, ld_xn, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+  if (lnn_w != nullptr && !with_qkv) TRY(make_tmap(&txn, XN, false, ld_xn, M, ld_xn, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   else txn = tx;
+  if (with_qkv) {
+    TRY(make_tmap_bf16(&twqkv, Wqkv, 3LL * D, D, ldwqkv, 64));
+    TRY(make_tmap_bf16(&tqkv, QKV, M, 3LL * D, ld_qkv, 32));   // one warp's 32 rows x 64 columns per store
+  } else {
+    twqkv = tw1; tqkv = ta;
+  }
   TailArgs a{};
   a.M = M; a.hidden = Hd; a.gelu5 = e->f16 ? 1 : 0;
   a.bias_p = bp; a.ln2_w = ln2w; a.ln2_b = ln2b; a.bias1 = b1; a.bias2 = b2; a.lnn_w = lnn_w; a.lnn_b = lnn_b; a.ln_eps = eps;
+  a.bias_qkv = bqkv; a.n_qkv_chunks = with_qkv ? 3 * D / MLP_HC : 0;
   a.timeline = timeline;
   { static const int dbg = [] { const char* v = getenv("VITOCM_TAIL_DEBUG"); return v ? atoi(v) : 0; }(); a.debug = dbg; }
   { static const int stg = [] { const char* v = getenv("VITOCM_TAIL_STAGGER"); return v ? atoi(v) : 0; }(); a.stagger_clk = stg; }
   { static const int tli = [] { const char* v = getenv("VITOCM_MLP_TL_ITEM"); return v ? atoi(v) : 1; }(); a.timeline_item = tli; }
-  if (D == 384) return e->f16 ? launch_block_tail<6, true>(ta, twp, tw1, tw2, tx, txn, a, e->num_sms, st) : launch_block_tail<6, false>(ta, twp, tw1, tw2, tx, txn, a, e->num_sms, st);
-  return e->f16 ? launch_block_tail<2, true>(ta, twp, tw1, tw2, tx, txn, a, e->num_sms, st) : launch_block_tail<2, false>(ta, twp, tw1, tw2, tx, txn, a, e->num_sms, st);
+  if (D == 384) return e->f16 ? launch_block_tail<6, true>(ta, twp, tw1, tw2, tx, txn, twqkv, tqkv, a, e->num_sms, st) : launch_block_tail<6, false>(ta, twp, tw1, tw2, tx, txn, twqkv, tqkv, a, e->num_sms, st);
+  return e->f16 ? launch_block_tail<2, true>(ta, twp, tw1, tw2, tx, txn, twqkv, tqkv, a, e->num_sms, st) : launch_block_tail<2, false>(ta, twp, tw1, tw2, tx, txn, twqkv, tqkv, a, e->num_sms, st);
 }
 
 // ---------------------------------------------------------------------------------- attention launch
@@ -792,15 +805,21 @@ Workspace carve(const vitocm_engine* e, void* base, int tiles, int N) {
 // xn_ready: ws.XN already holds norm1(X) of this block (produced by the previous block's fused fc2 epilogue).
 // next_ln (or null): LayerNorm parameters of the NEXT consumer of X; when the fused epilogue is available, fc2 also
 // leaves that norm's output in ws.XN and *xn_done is set.
+// qkv_ready: ws.QKV already holds this block's QKV projection (produced by the previous block's tail kernel); next_qkv (or null): the
+// NEXT block, whose QKV projection this block's tail kernel computes when it can (*qkv_done).
 int block_forward(const vitocm_engine* e, int l, const Workspace& ws, int B, int N, cudaStream_t st, bool xn_ready = false,
-                  const float* next_ln_w = nullptr, const float* next_ln_b = nullptr, bool* xn_done = nullptr) {
+                  const float* next_ln_w = nullptr, const float* next_ln_b = nullptr, bool* xn_done = nullptr, bool qkv_ready = false,
+                  const LayerW* next_qkv = nullptr, bool* qkv_done = nullptr) {
   const LayerW& L = e->layers[l];
   const int D = e->cfg.embed_dim, Hd = e->cfg.mlp_hidden, P = e->parts, S = e->split;
   const int M = B * N;
   if (xn_done != nullptr) *xn_done = false;
-  if (!xn_ready) TRY(run_layernorm(ws.X, L.ln1w, L.ln1b, ws.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st, nullptr, e->f16));
-  TRY(run_gemm(e, ws.XN, 2LL * D, L.wqkv.p, static_cast<long long>(D) * P, M, 3 * D, D, S, EPI_BIAS_BF16, L.bqkv, ws.QKV,
-               3LL * D * P, S, 3 * D, st, PC_GEMM_QKV));
+  if (qkv_done != nullptr) *qkv_done = false;
+  if (!qkv_ready) {
+    if (!xn_ready) TRY(run_layernorm(ws.X, L.ln1w, L.ln1b, ws.XN, 2LL * D, S, D, nullptr, 0, M, D, e->cfg.ln_eps, st, nullptr, e->f16));
+    TRY(run_gemm(e, ws.XN, 2LL * D, L.wqkv.p, static_cast<long long>(D) * P, M, 3 * D, D, S, EPI_BIAS_BF16, L.bqkv, ws.QKV,
+                 3LL * D * P, S, 3 * D, st, PC_GEMM_QKV));
+  }
   TRY(run_attention(e, ws.QKV, 3LL * D * P, B, N, ws.CTX, static_cast<long long>(D) * P, st));
   // MLP of an act-split block (vitocm_set_layer_mode 1): norm2's output and the hidden activations are kept as (hi, lo) pairs and
   // fc1 / fc2 contract both halves against the single-precision weights (two MMAs per product) -- the rounding of these two
@@ -809,11 +828,17 @@ int block_forward(const vitocm_engine* e, int l, const Workspace& ws, int B, int
   // proj + residual + norm2 + MLP + residual (+ the next block's norm1) in ONE kernel where an instantiation exists (single 16-bit
   // operands, D = 128 / 384): a row of the residual stream is read once and written once, norm2's output never reaches HBM
   if (!S && !mlp2) {
+    // ... and the next block's QKV projection rides along (VITOCM_FUSE_QKV=0: the next norm1's rows go to HBM and its QKV GEMM runs)
+    static const int fuse_qkv = [] { const char* v = getenv("VITOCM_FUSE_QKV"); return v ? atoi(v) : 1; }();
+    const bool with_qkv = fuse_qkv && next_qkv != nullptr && next_ln_w != nullptr && qkv_done != nullptr;
     const int rct = run_block_tail(e, ws.CTX, static_cast<long long>(D) * P, L.wproj.p, static_cast<long long>(D) * P, L.bproj, L.ln2w, L.ln2b,
-                                   L.w1.p, D, L.w2.p, Hd, M, D, Hd, L.b1, L.b2, ws.X, next_ln_w, next_ln_b, e->cfg.ln_eps, ws.XN, 2LL * D, st);
+                                   L.w1.p, D, L.w2.p, Hd, M, D, Hd, L.b1, L.b2, ws.X, next_ln_w, next_ln_b, e->cfg.ln_eps, ws.XN, 2LL * D,
+                                   with_qkv ? next_qkv->wqkv.p : nullptr, static_cast<long long>(D) * P, with_qkv ? next_qkv->bqkv : nullptr,
+                                   ws.QKV, 3LL * D * P, st);
     if (rct < 0) return rct;
     if (rct == 0) {
-      if (xn_done != nullptr && next_ln_w != nullptr) *xn_done = true;
+      if (with_qkv) *qkv_done = true;
+      else if (xn_done != nullptr && next_ln_w != nullptr) *xn_done = true;
       return 0;
     }
   }
@@ -1175,15 +1200,17 @@ static int forward_rows(vitocm_engine* e, const float* x, int B, int H, int W, c
         TRY(run_patch_embed(e, x + static_cast<long long>(b0s[k]) * C * H * W, bcs[k], H, W, pos, nullptr, lane_ws[k].X, lane_st[k], gray));
       }
     bool xn_ready[vitocm_engine::MAX_LANES] = {false, false, false, false};
+    bool qkv_ready[vitocm_engine::MAX_LANES] = {false, false, false, false};
     for (int l = 0; l + 1 < e->cfg.depth; ++l) {
       // the next block's norm1 rides on this block's fc2 epilogue -- except into the last block, whose K projection
       // wants the split-precision (hi | lo) normalised rows
       const bool chain = l + 2 < e->cfg.depth;
       for (int k = 0; k < active; ++k) {
-        bool done = false;
+        bool done = false, qdone = false;
         TRY(block_forward(e, l, lane_ws[k], bcs[k], N, lane_st[k], xn_ready[k], chain ? e->layers[l + 1].ln1w : nullptr,
-                          chain ? e->layers[l + 1].ln1b : nullptr, &done));
+                          chain ? e->layers[l + 1].ln1b : nullptr, &done, qkv_ready[k], chain ? &e->layers[l + 1] : nullptr, &qdone));
         xn_ready[k] = done;
+        qkv_ready[k] = qdone;
       }
     }
     for (int k = 0; k < active; ++k) {
@@ -1618,13 +1645,13 @@ int vitocm_mlp_fused_timeline(vitocm_engine* e, const void* XN, int64_t ld_xn, c
 }
 int vitocm_block_tail(vitocm_engine* e, const void* CTX, int64_t ld_ctx, const void* Wp, int64_t ldwp, const float* bias_p, const float* ln2_w,
                       const float* ln2_b, const void* W1, int64_t ldw1, const void* W2, int64_t ldw2, int M, int D, int hidden, const float* bias1,
-                      const float* bias2, float* X, const float* next_ln_w, const float* next_ln_b, void* XN, int64_t ld_xn, int64_t* stamps,
-                      void* stream) {
+                      const float* bias2, float* X, const float* next_ln_w, const float* next_ln_b, void* XN, int64_t ld_xn, const void* Wqkv,
+                      int64_t ldwqkv, const float* bias_qkv, void* QKV, int64_t ld_qkv, int64_t* stamps, void* stream) {
   if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
   const int rc = run_block_tail(e, CTX, ld_ctx, Wp, ldwp, bias_p, ln2_w, ln2_b, W1, ldw1, W2, ldw2, M, D, hidden, bias1, bias2, X, next_ln_w,
-                                next_ln_b, e->cfg.ln_eps, XN, ld_xn, reinterpret_cast<cudaStream_t>(stream), true,
+                                next_ln_b, e->cfg.ln_eps, XN, ld_xn, Wqkv, ldwqkv, bias_qkv, QKV, ld_qkv, reinterpret_cast<cudaStream_t>(stream), true,
                                 reinterpret_cast<long long*>(stamps));
-  if (rc == 1) return fail(VITOCM_ERR_INVALID, "block tail: no instantiation for D = %d, hidden = %d on this engine", D, hidden);
+  if (rc == 1) return fail(VITOCM_ERR_INVALID, "block tail: no instantiation for D = %d, hidden = %d on this engine (or inconsistent optional arguments)", D, hidden);
   return rc;
 }
 int vitocm_attention(vitocm_engine* e, const void* qkv, int64_t ld, int B, int n_tokens, void* ctx, int64_t ldo, void* stream) {
