@@ -55,7 +55,8 @@ struct TailArgs {
   // [62] ep 2 done; [25 + 4 k + e]: the group's k-th QKV chunk (k < 2): accumulator complete, packed, staging free, stored; [46 + c]: MMA thread, QKV chunk c issued; [15 + s] ep 1 pass 1 step s done, [18] ep 1 statistics combined, [20 + s] ep 2 pass 2 step s stored, [24] ep 2 stores read
   long long* timeline;
   int timeline_item;
-  int debug;           // bit 0: no MMAs (barrier traffic only), bit 1: ep 1 neither loads nor awaits the fp32 rows, bit 2: ep 2 issues no TMA stores
+  int debug;           // bit 0: no MMAs (barrier traffic only), bit 1: ep 1 neither loads nor awaits the fp32 rows, bit 2: ep 2 issues no TMA stores,
+                       // bit 3: the weight ring runs without its TMA loads (results are garbage; timing only)
   // Start stagger: every CTA pair does the same work in the same time, so without it all of them reach the item boundary -- 290 KB
   // of rows in, 290 KB out per CTA -- in the same instant, a burst the L2 serves at a fraction of the kernel's average rate.
   // Pair k starts k / pairs x stagger_clk SM clocks late.
@@ -213,12 +214,13 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
       if (lane == 0) {
         int slot = 0;
         uint32_t phase = 0;
+        const bool no_loads = (args.debug & 8) != 0;   // diagnostics: the ring runs without the weight loads (is the chunk loop bound by them?)
         auto acquire = [&](int bytes) {
           ptx::mbar_wait(w_empty + 8 * slot, phase ^ 1, 31);
-          if (rank == 0) ptx::mbar_arrive_expect_tx(w_full + 8 * slot, 2 * bytes);
+          if (rank == 0) { if (no_loads) ptx::mbar_arrive(w_full + 8 * slot); else ptx::mbar_arrive_expect_tx(w_full + 8 * slot, 2 * bytes); }
         };
         auto box = [&](const CUtensorMap* tm, int off, int c0, int c1) {
-          ptx::tma_load_2d_2cta(smem_w + slot * MLP_SLOT_BYTES + off, tm, w_full + 8 * slot, c0, c1);
+          if (!no_loads) ptx::tma_load_2d_2cta(smem_w + slot * MLP_SLOT_BYTES + off, tm, w_full + 8 * slot, c0, c1);
         };
         auto release = [&]() {
           if (++slot == SLOTS) { slot = 0; phase ^= 1; }
