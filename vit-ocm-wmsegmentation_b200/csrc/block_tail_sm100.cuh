@@ -279,8 +279,13 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
           if (rank == 0) ptx::mbar_arrive_expect_tx(a_full, 2 * Cfg::A_BYTES);
           for (int kb = 0; kb < KB1; ++kb)
             ptx::tma_load_2d_2cta(smem_a + kb * MLP_KB_BYTES, &tmap_a, a_full, kb * GEMM_BK, tile * 2 * GEMM_BM + rank * GEMM_BM);
-          if (tile + tstep < tiles_m)   // the next item's tile on its way to L2: its load is issued late (behind this item's last use of smem_a)
+          if (tile + tstep < tiles_m) {
+            // the next item's tile on its way to L2 (its load is issued late: behind this item's last use of smem_a) -- but not before
+            // this item's hidden chunks are done: a whole item ahead, the kernel's own output stream (~100 MB through a 126 MB L2)
+            // evicts the prefetched lines again and they are read from HBM twice (ncu: +200 MB of DRAM reads per 175-tile launch)
+            ptx::mbar_wait(out_full, t & 1, 26);
             for (int kb = 0; kb < KB1; ++kb) ptx::tma_prefetch_2d(&tmap_a, kb * GEMM_BK, (tile + tstep) * 2 * GEMM_BM + rank * GEMM_BM);
+          }
         }
       }
     } else if (warp == 1) {
@@ -548,11 +553,6 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_remote(mid_ready_leader);
       mlp_stamp(tl, smem_tl, 55);
-      if (lane == 0 && tile + tstep < tiles_m) {   // the next item's fp32 rows on their way to L2 (HBM latency off ep 1's critical path)
-        const int next_row = (tile + tstep) * 2 * GEMM_BM + rank * GEMM_BM + q * 32;
-#pragma unroll
-        for (int s = 0; s < NS; ++s) ptx::tma_prefetch_2d(&tmap_x, col0 + s * 32, next_row);
-      }
       // ------------------------------------------------------------------ hidden chunks (mlp_fused_sm100.cuh)
       for (int c = (n0 + grp) & 1; c < NC; c += 2) {
         const int n = n0 + c;          // (n & 1) == grp
@@ -712,6 +712,11 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
             }
           }
         }
+      }
+      if (lane == 0 && tile + tstep < tiles_m) {   // the next item's fp32 rows on their way to L2 (no earlier: see the CTX-tile producer)
+        const int next_row = (tile + tstep) * 2 * GEMM_BM + rank * GEMM_BM + q * 32;
+#pragma unroll
+        for (int s = 1; s < NS; ++s) ptx::tma_prefetch_2d(&tmap_x, col0 + s * 32, next_row);
       }
       if (NQ > 0) {
         // ------------------------------------------------------------------ the next block's QKV chunks
