@@ -543,8 +543,8 @@ def masks_sha(out, names=("th", "th3")):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=6)   # the power cap needs ~5 steps to settle after an idle phase: a step inside the transition reads 128 ms against 70
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arch", default="vit_small", choices=sorted(ARCHS))
     ap.add_argument("--precision", default="fp16", help="bf16 | fp16 | fp32, optionally +mlp2[:blocks] (vision_transformer.parse_precision)")

@@ -64,3 +64,9 @@ print("epilogue w0: OUT complete=%d  ep2 stats=%d  steps stored=%d %d %d  stores
 if with_qkv:
     print("QKV chunks, epilogue w0 (its group's first two): " + " | ".join("complete=%d packed=%d staging free=%d stored=%d" % tuple(rel(25 + 4 * k + e) for e in range(4)) for k in range(2)))
     print("QKV chunks, MMA thread issued: " + " ".join(str(rel(46 + c)) for c in range(8)))
+if int(os.environ.get("VITOCM_TAIL_DEBUG", "0")) & 16:
+    names = ["accumulator complete", "in registers", "gelu done", "gelu buffer free", "stored+fenced", "handed"]
+    print("chunk 4 (group 0, warp 0): " + " ".join("%s=%d" % (n, rel(25 + i)) for i, n in enumerate(names)))
+    print("chunk 5 (group 1, warp 8): " + " ".join("%s=%d" % (n, rel(46 + i)) for i, n in enumerate(names)))
+    print("MMA thread: gelu(4) seen=%d fc2(4) issued=%d | fc1(6): accumulator free=%d issued=%d | gelu(5) seen=%d fc2(5) issued=%d | fc1(7): accumulator free=%d issued=%d"
+          % (rel(45), rel(33), rel(31), rel(32), rel(34), rel(53), rel(35), rel(52)))

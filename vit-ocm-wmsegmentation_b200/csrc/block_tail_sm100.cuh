@@ -56,7 +56,9 @@ struct TailArgs {
   long long* timeline;
   int timeline_item;
   int debug;           // bit 0: no MMAs (barrier traffic only), bit 1: ep 1 neither loads nor awaits the fp32 rows, bit 2: ep 2 issues no TMA stores,
-                       // bit 3: the weight ring runs without its TMA loads (results are garbage; timing only)
+                       // bit 3: the weight ring runs without its TMA loads (results are garbage; timing only), bit 4: fine stamps of hidden
+                       // chunks 4 / 5 instead of the QKV-phase stamps (tools/tail_timeline.py), bit 5: .release.cluster arrives on the
+                       // shared-memory hand-overs (as before; A/B)
   // Start stagger: every CTA pair does the same work in the same time, so without it all of them reach the item boundary -- 290 KB
   // of rows in, 290 KB out per CTA -- in the same instant, a burst the L2 serves at a fraction of the kernel's average rate.
   // Pair k starts k / pairs x stagger_clk SM clocks late.
@@ -290,6 +292,12 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
       }
     } else if (warp == 1) {
       // ===================== MMA issuer (leader CTA) =====================
+      // (ONE issuing thread, inside the elected branch, on purpose.  It spends ~3 000 of a chunk's ~3 700 clk issuing -- it shares its
+      // scheduler with four epilogue warps and every ring slot costs ~60 instructions, a third of them R2UR moves.  Measured and dropped:
+      // a second issuer for the fc2 chunks on the same weight ring runs more than one ring wrap ahead of the fills of the slots it
+      // skips, so its parity waits succeed on the wrong phase -- a hang (two issuers need two rings); the whole warp running the loop
+      // with only the tcgen05 instructions under elect.sync keeps slot / phase in vector registers all the same: no fewer
+      // instructions, 3 730 against 3 640 us per 1 225-tile launch.  profiles/r02_gpu_call_ai_aj_tail_chunks.log)
       if (rank == 0 && ptx::elect_one()) {
         const uint32_t idesc = ptx::make_idesc(2 * GEMM_BM, MLP_HC, false, false, F16 ? 0u : 1u);    // fc1: N = one hidden chunk
         const uint32_t idesc2 = ptx::make_idesc(2 * GEMM_BM, BN2, false, false, F16 ? 0u : 1u);      // proj, fc2: N = one output part
@@ -330,11 +338,13 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
         // of the chunk it has just finished (behind = 2: the columns' previous user is the chunk before last; 0: nobody to wait for)
         auto issue_chunk = [&](int c, bool last_use_of_a, uint32_t acc_col = MLP_H_COL, int behind = 1) {
           const uint32_t h_tmem = tmem_base + acc_col;
+          const bool fine = tl && (args.debug & 16) && (c == 6 || c == 7);   // diagnostics: fc1(6) -> slots 31 / 32, fc1(7) -> 35 / 52
           if (behind > 0 && g1 >= behind) {   // the accumulator's previous user has been read out of TMEM (by the group of its parity)
             const int u = g1 - behind;
             ptx::mbar_wait(h_tmem_empty + 8 * (u & 1), (u >> 1) & 1, 33);
             ptx::tc_fence_after();
           }
+          mlp_stamp(fine, smem_tl, c == 6 ? 31 : 35);   // accumulator free
 #pragma unroll 1
           for (int kb = 0; kb < KB1; kb += T1) {
             ptx::mbar_wait(w_full + 8 * slot, phase, 34);
@@ -353,8 +363,9 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
             if (++slot == SLOTS) { slot = 0; phase ^= 1; }
           }
           ptx::umma_commit_2cta_mask(h_full + 8 * (g1 & 1), pair_mask);
+          mlp_stamp(fine, smem_tl, c == 6 ? 32 : 52);   // issued
           if (c < 5) mlp_stamp(tl, smem_tl, 36 + 2 * c);
-          if (c >= 100 && c < 108) mlp_stamp(tl, smem_tl, 46 + (c - 100));   // QKV chunk c - 100 issued
+          if (c >= 100 && c < 108) mlp_stamp(tl && !(args.debug & 16), smem_tl, 46 + (c - 100));   // QKV chunk c - 100 issued
           if (last_use_of_a) ptx::umma_commit_2cta_mask(a_empty, pair_mask);   // smem_a may take the next CTX tile once this chunk retires
           ++g1;
         };
@@ -365,6 +376,7 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
           ptx::mbar_wait_cluster(h_smem_full + 8 * g, f2[g] & 1, 35);   // gelu(chunk) sits in both CTAs' shared memory
           ptx::tc_fence_after();
           if (c < 5) mlp_stamp(tl, smem_tl, 36 + 2 * c + 1);
+          if ((args.debug & 16) && c == 5) mlp_stamp(tl, smem_tl, 34);   // diagnostics: gelu(5) seen
           const uint64_t hdesc = ptx::desc_advance(h_desc0, g * Cfg::H_BYTES);
 #pragma unroll 1
           for (int kb2 = 0; kb2 < 2; ++kb2) {
@@ -384,6 +396,7 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
             }
           }
           ptx::umma_commit_2cta_mask(h_smem_empty + 8 * g, pair_mask);
+          if (args.debug & 16) { if (c == 4) mlp_stamp(tl, smem_tl, 33); if (c == 5) mlp_stamp(tl, smem_tl, 53); }   // diagnostics: fc2(4) / fc2(5) issued
           ++f2[g];
         };
         for (int tile = tile0; tile < tiles_m; tile += tstep, ++t) {
@@ -444,6 +457,7 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
     const uint32_t my_h_full = h_full + 8 * grp, my_tmem_empty = h_tmem_empty + 8 * grp;
     const uint32_t my_smem_full = ptx::mapa(h_smem_full + 8 * grp, 0);
     const uint32_t mid_ready_leader = ptx::mapa(mid_ready, 0);
+    const bool strong_arrive = (args.debug & 32) != 0;   // diagnostics / A-B: hand-overs with .release.cluster arrives (ptx::mbar_arrive_remote)
     int cnt_h = 0, cnt_a = 0;   // boxes consumed so far: phases of xb_h / xb_a
     int n0 = 0;                 // global index of the item's first fc1-shaped chunk (hidden + QKV chunks of all items of this CTA)
     int k2 = 0;                 // hidden chunks this group has handed to fc2 so far: phase of its h_smem_empty
@@ -551,17 +565,24 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_remote(mid_ready_leader);
+      if (lane == 0) { if (strong_arrive) ptx::mbar_arrive_remote(mid_ready_leader); else ptx::mbar_arrive_remote_cta(mid_ready_leader); }
       mlp_stamp(tl, smem_tl, 55);
       // ------------------------------------------------------------------ hidden chunks (mlp_fused_sm100.cuh)
       for (int c = (n0 + grp) & 1; c < NC; c += 2) {
         const int n = n0 + c;          // (n & 1) == grp
+        // diagnostics (debug bit 4): one steady-state chunk of each group in detail -- chunk 4 by warp 0 (slots 25..30), chunk 5 by
+        // warp 8 (slots 46..51): accumulator complete, in registers, GELU done, gelu buffer free, stored + fenced, handed over
+        const bool fine = (args.debug & 16) && args.timeline != nullptr && blockIdx.x == 0 && t == args.timeline_item && lane == 0 &&
+                          ((ew == 0 && c == 4) || (ew == 8 && c == 5));
+        const int fs = ew == 0 ? 25 : 46;
         ptx::mbar_wait(my_h_full, (n >> 1) & 1, 40);
         ptx::tc_fence_after();
+        mlp_stamp(fine, smem_tl, fs);
         if (c < 5) mlp_stamp(tl, smem_tl, 3 * c);
         uint32_t r[NSUB][32];
         static_assert(NSUB == 2, "block tail: a warp reads its 64 columns of a hidden chunk in one load");
         ptx::tmem_ld_32x32b_x64_wait(lane_taddr + MLP_H_COL + ch * CPW, r[0], r[1]);
+        mlp_stamp(fine, smem_tl, fs + 1);
         // the chunk is in registers: the accumulator goes back to the MMA thread (fc1 of the next chunk)
         ptx::tc_fence_before();
         __syncwarp();
@@ -590,9 +611,11 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
           for (int j = 0; j < 16; ++j) pk[s][j] = ptx::pack_h2<F16>(v[2 * j], v[2 * j + 1]);
         }
         if (c < 5) mlp_stamp(tl, smem_tl, 3 * c + 1);
+        mlp_stamp(fine, smem_tl, fs + 2);
         // this group's H buffer is free once fc2 of its previous chunk has retired
         if (k2 > 0) ptx::mbar_wait(h_smem_empty + 8 * grp, (k2 - 1) & 1, 41);
         ++k2;
+        mlp_stamp(fine, smem_tl, fs + 3);
         if (NQ > 0) {   // ... and once the TMA store of this warp's last QKV chunk has read its region
           if (lane == 0) ptx::bulk_wait_read0();
           __syncwarp();
@@ -605,7 +628,9 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
             ptx::sts_v4(tile_addr + (((s * 4 + j) ^ (row & 7)) << 4), pk[s][4 * j], pk[s][4 * j + 1], pk[s][4 * j + 2], pk[s][4 * j + 3]);
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_remote(my_smem_full);
+        mlp_stamp(fine, smem_tl, fs + 4);
+        if (lane == 0) { if (strong_arrive) ptx::mbar_arrive_remote(my_smem_full); else ptx::mbar_arrive_remote_cta(my_smem_full); }
+        mlp_stamp(fine, smem_tl, fs + 5);
         if (c < 5) mlp_stamp(tl, smem_tl, 3 * c + 2);
       }
       // ------------------------------------------------------------------ ep 2: X out (+ the next LayerNorm)
@@ -722,14 +747,14 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
         // ------------------------------------------------------------------ the next block's QKV chunks
         ptx::fence_proxy_async_smem();   // the normalised rows in smem_a, for the tensor core
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_remote(ptx::mapa(xn_ready, 0));
+        if (lane == 0) { if (strong_arrive) ptx::mbar_arrive_remote(ptx::mapa(xn_ready, 0)); else ptx::mbar_arrive_remote_cta(ptx::mapa(xn_ready, 0)); }
         const int nq0 = n0 + NC;
         for (int c = (nq0 + grp) & 1; c < NQ; c += 2) {
           const int n = nq0 + c;          // (n & 1) == grp
           ptx::mbar_wait(my_h_full, (n >> 1) & 1, 46);
           ptx::tc_fence_after();
           const int ts = c >> 1;   // diagnostics: this group's first two QKV chunks
-          if (ts < 2) mlp_stamp(tl, smem_tl, 25 + 4 * ts);
+          if (ts < 2) mlp_stamp(tl && !(args.debug & 16), smem_tl, 25 + 4 * ts);
           uint32_t r[NSUB][32];
           ptx::tmem_ld_32x32b_x64_wait(lane_taddr + ((c & 1) ? 0 : MLP_H_COL) + ch * CPW, r[0], r[1]);   // (QKV chunks alternate between two accumulators)
           ptx::tc_fence_before();
@@ -748,10 +773,10 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
           }
           // staging = this warp's own 4 KB region of its group's gelu buffer (32 rows x 64 columns, SWIZZLE_128B = box_h): free once
           // the warp's previous store has read it (the fp32 boxes of ep 2, the QKV chunk before this one)
-          if (ts < 2) mlp_stamp(tl, smem_tl, 26 + 4 * ts);
+          if (ts < 2) mlp_stamp(tl && !(args.debug & 16), smem_tl, 26 + 4 * ts);
           if (lane == 0) ptx::bulk_wait_read0();
           __syncwarp();
-          if (ts < 2) mlp_stamp(tl, smem_tl, 27 + 4 * ts);
+          if (ts < 2) mlp_stamp(tl && !(args.debug & 16), smem_tl, 27 + 4 * ts);
 #pragma unroll
           for (int s = 0; s < NSUB; ++s)
 #pragma unroll
@@ -763,7 +788,7 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
             ptx::tma_store_2d(&tmap_qkv, box_h, c * MLP_HC + ch * CPW, row_g);
             ptx::bulk_commit();
           }
-          if (ts < 2) mlp_stamp(tl, smem_tl, 28 + 4 * ts);
+          if (ts < 2) mlp_stamp(tl && !(args.debug & 16), smem_tl, 28 + 4 * ts);
         }
         if (lane == 0) {   // box_h goes on to receive the next item's first fp32 rows
           ptx::bulk_wait_read0();

@@ -90,6 +90,13 @@ __device__ __forceinline__ void st_async_v2(uint32_t cluster_addr, float a, floa
                ::"r"(cluster_addr), "f"(a), "f"(b), "r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+// The same arrive with the default (.release.cta) semantics: for hand-overs whose data is read by the ASYNC proxy of the writer's own SM
+// (a cta_group::2 MMA reading this CTA's shared memory) -- the writer has executed fence.proxy.async.shared::cta, which only returns
+// once its stores are performed, and the consumer issues the MMA after observing the barrier.  .release.cluster compiles to
+// MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the arrive: ~1 700 clk per hand-over (block-tail timeline, profiles/r02_*).
+__device__ __forceinline__ void mbar_arrive_remote_cta(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
