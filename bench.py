@@ -70,18 +70,35 @@ def mosaic_geometry(n_gpus):
 
 
 class ClockSampler(threading.Thread):
-    """Clocks / throttle reasons of one GPU while the timed region runs: ONE long-lived `nvidia-smi -lms 200` (the recipe's
-    clocks line) started before the warm-up -- its NVML start-up then falls outside the timed region and nothing is spawned
-    inside it -- read line by line; `open_window()` / `stop()` bracket the timed region and only samples taken inside it count.
-    Only the rank that prints the JSON line samples (enabled=False elsewhere)."""
+    """Clocks / throttle reasons of one GPU while the timed region runs (the recipe's clocks line).  Sampled IN PROCESS through NVML
+    (nvidia_ml_py: SM clock, max SM clock, clocks-event reasons every 150 ms) -- a long-lived `nvidia-smi -lms 200` next to the bench
+    cost single timed steps 50-450 ms now and then (profiles/r02_gpu_call_al_final.log, r02_gpu_call_am_bench_spread.log: its
+    queries include power.draw and run through a second process); `nvidia-smi` remains the fall-back when NVML cannot be loaded.
+    `open_window()` / `stop()` bracket the timed region and only samples taken inside it count.  Only the rank that prints the JSON
+    line samples (enabled=False elsewhere)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index, enabled=True):
         super().__init__(daemon=True)
         self.index, self.enabled = index, enabled
         self.raw, self.samples, self.t_open, self.t_close, self.proc = [], [], None, None, None
-        if enabled:
+        self.nvml, self.handle, self.halt = None, None, threading.Event()
+        if not enabled:
+            return
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:   # the CUDA device's own NVML handle (CUDA_VISIBLE_DEVICES may renumber)
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
             try:
                 self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                               "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -89,6 +106,19 @@ class ClockSampler(threading.Thread):
                 self.proc = None
 
     def run(self):
+        if self.nvml is not None:
+            nv = self.nvml
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.halt.is_set():
+                try:
+                    sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                    bits = int(reasons_fn(self.handle))
+                    self.raw.append((time.perf_counter(), [str(sm), str(self.max_sm), ""] +
+                                     ["Active" if bits & mask else "Not Active" for _, mask in self.BITS]))
+                except Exception:
+                    pass
+                self.halt.wait(0.15)
+            return
         if self.proc is None:
             return
         for line in self.proc.stdout:
@@ -101,6 +131,7 @@ class ClockSampler(threading.Thread):
 
     def stop(self):
         self.t_close = time.perf_counter()
+        self.halt.set()
         if self.proc is not None:
             try:
                 self.proc.terminate()
@@ -117,7 +148,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for s in self.samples if len(s) >= 7 for i in range(4) if s[3 + i].lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------- CPU arm
@@ -459,15 +490,39 @@ def main_mim(args):
 
 
 # ------------------------------------------------------------------------------------- GPU arm
-def time_segmentation(D, seg, mosaic, steps, warmup, flush, sampler=None, want=("th", "th3")):
+def time_segmentation(D, seg, mosaic, steps, warmup, flush, sampler=None, want=("th", "th3"), after_warmup=None):
     """`warmup` untimed + `steps` timed passes with the mosaic resident in HBM; CUDA events on the launching stream, barrier +
     synchronize on both sides of every step, L2 flushed in between.  -> (ms per step = max over ranks, rank-0 step list, last result)."""
+    import gc
+    gc.collect()                                         # (before the warm-up: an idle gap between warm-up and timed steps lets the GPU
+    gc_was = gc.isenabled()                              #  boost and then be clamped: one timed step of 150-500 ms in one run of five)
+    gc.disable()                                         # no collector pause between the launches of a step
     out = None
-    for _ in range(warmup):
+    prev = None
+    extra = 0
+    i = 0
+    # warm-up: the requested steps, then (still untimed, at most 12 more) until two consecutive steps agree within 3 % on every rank --
+    # after an idle phase the first steps run at ~1.93 GHz, then the power cap bites, and ONE step inside that transition reads 128 ms
+    # against 70 (profiles/r02_gpu_call_al_final.log); the timed region must not start inside it
+    while warmup > 0 and (i < warmup or extra < 12):
         flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         D.barrier()
+        e0.record()
         out = seg.segment(mosaic, want=want, gather=True)
+        e1.record()
         D.barrier()
+        cur = D.max_over_ranks(e0.elapsed_time(e1))
+        i += 1
+        settled = prev is not None and abs(cur - prev) <= 0.03 * prev
+        prev = cur
+        if i >= warmup:
+            if settled:
+                break
+            extra += 1
+    time_segmentation.extra_warmup = max(i - warmup, 0)
+    if after_warmup is not None:
+        after_warmup()
     if sampler is not None:
         sampler.open_window()
     step_ms = []
@@ -481,6 +536,8 @@ def time_segmentation(D, seg, mosaic, steps, warmup, flush, sampler=None, want=(
         e1.record()
         D.barrier()
         step_ms.append(e0.elapsed_time(e1))
+    if gc_was:
+        gc.enable()
     if sampler is not None:
         sampler.stop()
     return D.max_over_ranks(sum(step_ms)) / max(steps, 1), step_ms, out
@@ -589,10 +646,13 @@ def main():
     sampler.start()
     launches0 = None
     # warm-up first (same cadence as the timed steps), then count launches over the timed steps only
-    ms_w, _, _ = time_segmentation(D, seg, mosaic, 0, args.warmup, flush)
-    launches0 = vob._lib.launch_count()
-    ms_per_step, step_ms, out = time_segmentation(D, seg, mosaic, args.steps, 0, flush, sampler=sampler)
-    launches = vob._lib.launch_count() - launches0
+    # ONE call: the timed steps follow the warm-up without a gap (an idle gap of tens of ms lets the GPU boost, overshoot the power cap
+    # and be clamped for a step: profiles/r02_gpu_call_am_an_bench_spread.log)
+    mark = {}
+    ms_per_step, step_ms, out = time_segmentation(D, seg, mosaic, args.steps, args.warmup, flush, sampler=sampler,
+                                                  after_warmup=lambda: mark.__setitem__("l0", vob._lib.launch_count()))
+    extra_warmup = getattr(time_segmentation, "extra_warmup", 0)
+    launches = vob._lib.launch_count() - mark["l0"]
     value = mp / (ms_per_step / 1e3)
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
@@ -716,6 +776,7 @@ def main():
         cfgd = workload_config(args.arch, world, args.precision, args.chunk_tiles, args.lanes)
         cfgd["tiles_per_gpu"] = my_tiles
         line = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "extra_warmup_steps": int(extra_warmup),   # untimed steps beyond `warmup` until two consecutive steps agreed within 3 %
                 "ms_per_step": ms_per_step, "step_ms_rank0": [round(v, 3) for v in step_ms], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic", "config": cfgd,
                 "tiles_per_s": T / (ms_per_step / 1e3),
