@@ -204,12 +204,13 @@ __device__ __forceinline__ void gelu_sigmoid_x2(float& x0, float& x1) {
 // Five-coefficient member of the same family for fp16 engines (their outputs keep 11 significand bits, so the 2.5e-5 of the
 // three-coefficient fit would show): Phi(x) ~= sigmoid(x (c0 + c1 u + c2 u^2 + c3 u^3 + c4 u^4)), u = min(x^2, 30), max |error|
 // of gelu 3.0e-6 over [-8, 8] (fitted like the above; tests/test_gpu_kernels.py checks it against erf): two more FFMA2 per pair.
+// No clamp of u in the code: the quartic keeps falling beyond u = 30 (w' < 0 there, the u^4 coefficient is negative), so the sigmoid only
+// saturates harder -- gelu -> x or -> 0 as it should, through +-inf without a NaN (ex2(+inf) = inf, rcp(inf) = 0, x finite); the same
+// 3.04e-6 maximum error with and without the clamp over [-12, 12], +-1e5 included.  Two FMNMX per pair fewer in an epilogue that is
+// issue bound (the three-coefficient form above DOES need its clamp: its quadratic turns upwards at u = 53).
 __device__ __forceinline__ void gelu_sigmoid5_x2(float& x0, float& x1) {
   const uint64_t x2 = ptx::pack_f32x2(x0, x1);
-  const uint64_t sq = ptx::mul_f32x2(x2, x2);
-  float u0, u1;
-  ptx::unpack_f32x2(sq, u0, u1);
-  const uint64_t u = ptx::pack_f32x2(fminf(u0, 30.f), fminf(u1, 30.f));
+  const uint64_t u = ptx::mul_f32x2(x2, x2);
   // coefficients pre-multiplied by -log2(e)
   uint64_t w = ptx::fma_f32x2(u, ptx::dup_f32x2(-3.2290010e-06f), ptx::dup_f32x2(8.8238336e-05f));
   w = ptx::fma_f32x2(w, u, ptx::dup_f32x2(3.6027357e-04f));
