@@ -221,3 +221,29 @@ def test_vits8_precision_ladder():
     print("\nCLS-row rms relative error:", rms)
     assert rms["bf16"] > 4 * rms["fp16"] > 4 * rms["fp32"]
     assert rms["fp16+mlp2"] < 0.8 * rms["fp16"]
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_block_tail_folded_layernorm_affine_equals_unfolded(precision, monkeypatch):
+    """vitocm_finalize_weights folds norm2 into W1 / b1 and the next norm1 into Wqkv / bqkv for the block-tail kernel
+    (VITOCM_TAIL_FOLD, read at vitocm_create).  With strongly non-trivial gamma / beta both forms stay inside the precision's
+    CLS-row bar against the CPU oracle and agree with each other far inside it."""
+    tol = 2e-2 if precision == "bf16" else 1e-3
+    for cfg, x in ((TINY, torch.from_numpy(load_golden("tiny_vit.npz")["a/x"])),
+                   (VO.ViTConfig(**VO.VIT_SMALL), VO.synthetic_tile(224, seed=321, batch=1))):
+        sd = VO.randomize_affine(VO.init_state_dict(cfg, seed=3), seed=4, scale=0.3 if cfg is TINY else 0.02)
+        ref = VO.cls_attention_rows(sd, cfg, x).numpy()
+        ref_feat = VO.forward_feats(sd, cfg, x).numpy()   # O(1) dynamic range: a dropped beta or gamma shows here at once
+        atol = 6e-2 if precision == "bf16" else 6e-3
+        rows, feats = {}, {}
+        for fold in ("1", "0"):
+            monkeypatch.setenv("VITOCM_TAIL_FOLD", fold)
+            m = build_model(cfg, sd, precision, chunk_tiles=2)
+            rows[fold] = m.cls_attention_rows(x.cuda()).cpu().numpy()             # chained blocks: fold2 and foldn (QKV rides along)
+            feats[fold] = m.forward_feats(x.cuda()).cpu().numpy()                 # block by block: fold2 only
+            assert rel_err(rows[fold], ref) <= tol, (fold, rel_err(rows[fold], ref))
+            assert np.abs(feats[fold] - ref_feat).max() <= atol, (fold, np.abs(feats[fold] - ref_feat).max())
+        assert not np.array_equal(rows["1"], rows["0"])   # the knob really switches the path
+        assert rel_err(rows["1"], rows["0"]) <= tol / 2, rel_err(rows["1"], rows["0"])
+        print(f"\n{precision} D={cfg.embed_dim}: rows vs oracle folded {rel_err(rows['1'], ref):.2e} / plain {rel_err(rows['0'], ref):.2e}; "
+              f"feat folded {np.abs(feats['1'] - ref_feat).max():.2e} / plain {np.abs(feats['0'] - ref_feat).max():.2e}")

@@ -48,6 +48,11 @@ struct TailArgs {
   int n_qkv_chunks;        // 0: XN = LayerNorm(X; lnn) goes to HBM (tmap_xn); 3 D / 128: it stays in shared memory and QKV = XN . Wqkv^T + bias_qkv
                            // is written instead (tmap_wqkv, tmap_qkv); needs lnn_w
   float ln_eps;
+  // LayerNorm affine parameters folded into the weights that read the normalised rows (W' = W diag(gamma), b' = b + W beta, prepared by
+  // vitocm_finalize_weights): the epilogue then only forms (x - mean) rstd = fma(x, rstd, -mean rstd) -- one instruction per element
+  // instead of three and no gamma / beta loads in phases that are instruction-issue bound.
+  int fold2;           // norm2 is folded into W1 / bias1 (ln2_w / ln2_b are not read)
+  int foldn;           // the next norm1 is folded into Wqkv / bias_qkv (n_qkv_chunks > 0 only; lnn_w is only tested against nullptr)
   // diagnostics (vitocm_block_tail_timeline) or nullptr: 64 SM-clock stamps (low 32 bits) of the leader CTA of pair 0 on its work item
   // `timeline_item`: [3 c + e], c < 5: epilogue warp 0 (group 0) on chunk c as MlpArgs; [36 + 2 c + e], c < 5: MMA thread as MlpArgs;
   // MMA thread: [60] item start (CTX landed), [56] OUT free, proj issued, [59] ep 1 done (mid_ready seen);
@@ -538,6 +543,7 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
       {
         float mean, rstd;
         combine4(mean, rstd);
+        const float nmr = -mean * rstd;   // (x - mean) rstd = fma(x, rstd, nmr)
         mlp_stamp(tl, smem_tl, 18);
 #pragma unroll 1
         for (int s = 0; s < NS; ++s) {
@@ -546,13 +552,19 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
           ptx::tmem_ld_32x32b_x32(lane_taddr + col, r);
           ptx::tmem_ld_wait(r);
           uint32_t pk[16];
+          if (args.fold2) {   // gamma / beta live in W1 / bias1
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(args.ln2_w + col) + j);
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.ln2_b + col) + j);
-            const float v0 = (__uint_as_float(r[4 * j]) - mean) * rstd * g4.x + b4.x, v1 = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
-            const float v2 = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g4.z + b4.z, v3 = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g4.w + b4.w;
-            pk[2 * j] = ptx::pack_h2<F16>(v0, v1); pk[2 * j + 1] = ptx::pack_h2<F16>(v2, v3);
+            for (int j = 0; j < 16; ++j)
+              pk[j] = ptx::pack_h2<F16>(fmaf(__uint_as_float(r[2 * j]), rstd, nmr), fmaf(__uint_as_float(r[2 * j + 1]), rstd, nmr));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(args.ln2_w + col) + j);
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.ln2_b + col) + j);
+              const float v0 = fmaf(fmaf(__uint_as_float(r[4 * j]), rstd, nmr), g4.x, b4.x), v1 = fmaf(fmaf(__uint_as_float(r[4 * j + 1]), rstd, nmr), g4.y, b4.y);
+              const float v2 = fmaf(fmaf(__uint_as_float(r[4 * j + 2]), rstd, nmr), g4.z, b4.z), v3 = fmaf(fmaf(__uint_as_float(r[4 * j + 3]), rstd, nmr), g4.w, b4.w);
+              pk[2 * j] = ptx::pack_h2<F16>(v0, v1); pk[2 * j + 1] = ptx::pack_h2<F16>(v2, v3);
+            }
           }
           // 32 columns = half of a 128-byte row of k-block col / 64 of the A tile (SWIZZLE_128B)
           const uint32_t rowaddr = smem_a + (col >> 6) * MLP_KB_BYTES + row * 128;
@@ -665,6 +677,7 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
         asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");   // every partial has been read: the boxes may be overwritten
       }
       mlp_stamp(tl, smem_tl, 54);
+      const float nmr2 = -mean * rstd;
       const int sw2 = (lane >> 1) & 3;
       // staging: fp32 boxes alternate between box_h and box_a, 16-bit boxes go through xn_box; one bulk group per store, in the order
       // X0, XN0, X1, XN1, X2, XN2 (X0, X1, X2 without the trailing LayerNorm)
@@ -707,13 +720,18 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
         mlp_stamp(tl, smem_tl, 20 + s);
         if (want_xn) {
           uint32_t pk[16];
+          if (args.foldn) {   // gamma / beta live in Wqkv / bias_qkv
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(args.lnn_w + col) + j);
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.lnn_b + col) + j);
-            const float v0 = (y[4 * j] - mean) * rstd * g4.x + b4.x, v1 = (y[4 * j + 1] - mean) * rstd * g4.y + b4.y;
-            const float v2 = (y[4 * j + 2] - mean) * rstd * g4.z + b4.z, v3 = (y[4 * j + 3] - mean) * rstd * g4.w + b4.w;
-            pk[2 * j] = ptx::pack_h2<F16>(v0, v1); pk[2 * j + 1] = ptx::pack_h2<F16>(v2, v3);
+            for (int j = 0; j < 16; ++j) pk[j] = ptx::pack_h2<F16>(fmaf(y[2 * j], rstd, nmr2), fmaf(y[2 * j + 1], rstd, nmr2));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(args.lnn_w + col) + j);
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.lnn_b + col) + j);
+              const float v0 = fmaf(fmaf(y[4 * j], rstd, nmr2), g4.x, b4.x), v1 = fmaf(fmaf(y[4 * j + 1], rstd, nmr2), g4.y, b4.y);
+              const float v2 = fmaf(fmaf(y[4 * j + 2], rstd, nmr2), g4.z, b4.z), v3 = fmaf(fmaf(y[4 * j + 3], rstd, nmr2), g4.w, b4.w);
+              pk[2 * j] = ptx::pack_h2<F16>(v0, v1); pk[2 * j + 1] = ptx::pack_h2<F16>(v2, v3);
+            }
           }
           if (to_smem) {   // half of a 128-byte row of k-block col / 64 of the A tile (SWIZZLE_128B), as the norm2 rows in ep 1
             const uint32_t arow = smem_a + (col >> 6) * MLP_KB_BYTES + row * 128;

@@ -353,4 +353,27 @@ __global__ void split_weight_kernel(const float* __restrict__ w, __nv_bfloat16* 
   }
 }
 
+// LayerNorm affine parameters folded into the Linear that reads the normalised rows (block_tail_sm100.cuh, TailArgs::fold2 / foldn):
+//   W'[n][k] = W[n][k] gamma[k]  (16-bit, K-major, the engine's operand format),   b'[n] = b[n] + sum_k W[n][k] beta[k]  (fp32)
+// so that  (xhat gamma + beta) . W^T + b  ==  xhat . W'^T + b'  with xhat = (x - mean) rstd.  One warp per output row.
+__global__ void fold_ln_weight_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, float* __restrict__ bias_out,
+                                      int R, int C, int f16) {
+  const int row = static_cast<int>((blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* wr = w + static_cast<long long>(row) * C;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float v = wr[c];
+    acc = fmaf(v, beta[c], acc);
+    const float s = v * gamma[c];
+    if (f16) reinterpret_cast<__half*>(out)[static_cast<long long>(row) * C + c] = __float2half_rn(s);
+    else out[static_cast<long long>(row) * C + c] = __float2bfloat16_rn(s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) bias_out[row] = bias[row] + acc;
+}
+
 }  // namespace vitocm

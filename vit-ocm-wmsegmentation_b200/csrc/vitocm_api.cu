@@ -138,6 +138,9 @@ struct DevBuf {
 struct LayerW {
   DevBuf wqkv, wproj, w1, w2;      // bf16 [rows][K * parts]  (hi | lo)
   DevBuf wk_split;                 // last layer: K rows of qkv, always split [D][2D]
+  // single 16-bit inference engines (vitocm_finalize_weights): W1 diag(norm2.weight), b1 + W1 norm2.bias and Wqkv diag(norm1.weight),
+  // bqkv + Wqkv norm1.bias -- the block-tail kernel then skips the LayerNorm affine step (fold_ln_weight_kernel)
+  DevBuf w1_fold, b1_fold, wqkv_fold, bqkv_fold;
   DevBuf wqkv_t, wproj_t, w1_t, w2_t;   // bf16 [K][rows]: transposed copies, the B operand of the input-gradient GEMMs (bf16 engines)
   const float *bqkv = nullptr, *bproj = nullptr, *b1 = nullptr, *b2 = nullptr;
   const float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
@@ -163,6 +166,8 @@ struct vitocm_engine {
   bool any_mlp_split() const { for (int m : layer_mode) if (m == 1) return true; return false; }
   int num_sms = 148;
   bool finalized = false;
+  bool fold_valid = false;   // LayerW::*_fold match the master weights (set by vitocm_finalize_weights, cleared by every other weight change)
+  int tail_fold = 1;         // VITOCM_TAIL_FOLD (read at vitocm_create): 0 = the block tail applies gamma / beta itself
   std::map<std::string, DevBuf*> master;  // fp32 weights as loaded
   std::vector<LayerW> layers;
   DevBuf patch_w;   // bf16 [D][2K]  (hi | lo): the conv filter as a K-major GEMM operand
@@ -568,7 +573,8 @@ int run_block_tail(const vitocm_engine* e, const void* CTX, long long ld_ctx, co
                    const float* ln2w, const float* ln2b, const void* W1, long long ldw1, const void* W2, long long ldw2, int M, int D, int Hd,
                    const float* b1, const float* b2, float* X, const float* lnn_w, const float* lnn_b, float eps, void* XN, long long ld_xn,
                    const void* Wqkv, long long ldwqkv, const float* bqkv, void* QKV, long long ld_qkv,
-                   cudaStream_t st, bool force = false, long long* timeline = nullptr) {
+                   cudaStream_t st, bool force = false, long long* timeline = nullptr, bool fold2 = false, bool foldn = false) {
+  // fold2: W1 / b1 carry norm2's gamma / beta; foldn: Wqkv / bqkv carry the next norm1's (LayerW::*_fold; with Wqkv only)
   // VITOCM_FUSE_TAIL: 0 = never (proj + LayerNorm GEMM, fused MLP and LayerNorm as separate kernels), 1 = default
   static const int mode = [] { const char* v = getenv("VITOCM_FUSE_TAIL"); return v == nullptr ? 1 : atoi(v); }();
   if (mode == 0 && !force) return 1;
@@ -602,6 +608,7 @@ int run_block_tail(const vitocm_engine* e, const void* CTX, long long ld_ctx, co
   a.M = M; a.hidden = Hd; a.gelu5 = e->f16 ? 1 : 0;
   a.bias_p = bp; a.ln2_w = ln2w; a.ln2_b = ln2b; a.bias1 = b1; a.bias2 = b2; a.lnn_w = lnn_w; a.lnn_b = lnn_b; a.ln_eps = eps;
   a.bias_qkv = bqkv; a.n_qkv_chunks = with_qkv ? 3 * D / MLP_HC : 0;
+  a.fold2 = fold2 ? 1 : 0; a.foldn = (foldn && with_qkv) ? 1 : 0;
   a.timeline = timeline;
   { static const int dbg = [] { const char* v = getenv("VITOCM_TAIL_DEBUG"); return v ? atoi(v) : 0; }(); a.debug = dbg; }
   { static const int stg = [] { const char* v = getenv("VITOCM_TAIL_STAGGER"); return v ? atoi(v) : 0; }(); a.stagger_clk = stg; }
@@ -831,10 +838,14 @@ int block_forward(const vitocm_engine* e, int l, const Workspace& ws, int B, int
     // ... and the next block's QKV projection rides along (VITOCM_FUSE_QKV=0: the next norm1's rows go to HBM and its QKV GEMM runs)
     static const int fuse_qkv = [] { const char* v = getenv("VITOCM_FUSE_QKV"); return v ? atoi(v) : 1; }();
     const bool with_qkv = fuse_qkv && next_qkv != nullptr && next_ln_w != nullptr && qkv_done != nullptr;
+    // LayerNorm affine parameters folded into W1 / Wqkv where vitocm_finalize_weights has prepared them (VITOCM_TAIL_FOLD=0: never)
+    const bool fold = e->fold_valid;
     const int rct = run_block_tail(e, ws.CTX, static_cast<long long>(D) * P, L.wproj.p, static_cast<long long>(D) * P, L.bproj, L.ln2w, L.ln2b,
-                                   L.w1.p, D, L.w2.p, Hd, M, D, Hd, L.b1, L.b2, ws.X, next_ln_w, next_ln_b, e->cfg.ln_eps, ws.XN, 2LL * D,
-                                   with_qkv ? next_qkv->wqkv.p : nullptr, static_cast<long long>(D) * P, with_qkv ? next_qkv->bqkv : nullptr,
-                                   ws.QKV, 3LL * D * P, st);
+                                   fold ? L.w1_fold.p : L.w1.p, D, L.w2.p, Hd, M, D, Hd, fold ? L.b1_fold.as<float>() : L.b1, L.b2, ws.X,
+                                   next_ln_w, next_ln_b, e->cfg.ln_eps, ws.XN, 2LL * D,
+                                   with_qkv ? (fold ? next_qkv->wqkv_fold.p : next_qkv->wqkv.p) : nullptr, static_cast<long long>(D) * P,
+                                   with_qkv ? (fold ? next_qkv->bqkv_fold.as<float>() : next_qkv->bqkv) : nullptr, ws.QKV, 3LL * D * P, st, false,
+                                   nullptr, fold, fold);
     if (rct < 0) return rct;
     if (rct == 0) {
       if (with_qkv) *qkv_done = true;
@@ -940,6 +951,7 @@ int vitocm_create(const vitocm_config* cfg, vitocm_engine** out) {
   e->parts = e->split ? 2 : 1;
   e->f16 = cfg->precision == VITOCM_FP16 ? 1 : 0;
   e->num_sms = prop.multiProcessorCount;
+  { const char* v = getenv("VITOCM_TAIL_FOLD"); e->tail_fold = v == nullptr ? 1 : atoi(v); }
   e->layers.resize(cfg->depth);
   e->layer_mode.assign(cfg->depth, 0);
   *out = e;
@@ -961,6 +973,7 @@ int vitocm_load_weight(vitocm_engine* e, const char* name, const float* host_dat
   auto it = e->master.find(name);
   if (it != e->master.end()) { delete it->second; it->second = b; } else { e->master[name] = b; }
   e->finalized = false;
+  e->fold_valid = false;
   return 0;
 }
 
@@ -1053,9 +1066,34 @@ static int repack_weights(vitocm_engine* e, cudaStream_t st) {
   return 0;
 }
 
+// LayerNorm affine parameters folded into the weights behind them, for the block-tail kernel of single 16-bit engines (LayerW::*_fold).
+// Only vitocm_finalize_weights prepares them: a training engine refreshes its repacked weights every step and runs its forward through
+// the separate kernels anyway.
+static int fold_layernorm_weights(vitocm_engine* e, cudaStream_t st) {
+  const int D = e->cfg.embed_dim, Hd = e->cfg.mlp_hidden;
+  e->fold_valid = false;
+  if (e->split || !e->tail_fold || (D != 128 && D != 384)) return 0;
+  auto fold = [&](DevBuf& w_out, DevBuf& b_out, const float* w, const float* b, const float* g, const float* be, int R) -> int {
+    TRY(w_out.alloc(static_cast<size_t>(R) * D * 2));
+    TRY(b_out.alloc(static_cast<size_t>(R) * 4));
+    fold_ln_weight_kernel<<<(R + 7) / 8, 256, 0, st>>>(w, b, g, be, w_out.as<__nv_bfloat16>(), b_out.as<float>(), R, D, e->f16);
+    LAUNCH_CHECK();
+    return 0;
+  };
+  for (int l = 0; l < e->cfg.depth; ++l) {
+    const std::string pre = "blocks." + std::to_string(l) + ".";
+    LayerW& L = e->layers[l];
+    TRY(fold(L.w1_fold, L.b1_fold, e->w(pre + "mlp.fc1.weight"), L.b1, L.ln2w, L.ln2b, Hd));
+    TRY(fold(L.wqkv_fold, L.bqkv_fold, L.wqkv_f32, L.bqkv, L.ln1w, L.ln1b, 3 * D));
+  }
+  e->fold_valid = true;
+  return 0;
+}
+
 int vitocm_finalize_weights(vitocm_engine* e) {
   if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
   TRY(repack_weights(e, nullptr));
+  TRY(fold_layernorm_weights(e, nullptr));
   CUDA_TRY(cudaDeviceSynchronize());
   e->finalized = true;
   return 0;
@@ -1063,6 +1101,7 @@ int vitocm_finalize_weights(vitocm_engine* e) {
 
 int vitocm_refresh_weights(vitocm_engine* e, void* stream) {
   TRY(check_engine(e));
+  e->fold_valid = false;   // the masters have changed: the block tail applies gamma / beta itself until the next vitocm_finalize_weights
   return repack_weights(e, static_cast<cudaStream_t>(stream));
 }
 
@@ -1073,6 +1112,7 @@ int vitocm_bind_weight(vitocm_engine* e, const char* name, float* dev_data, int6
   DevBuf* b = it != e->master.end() ? it->second : (e->master[name] = new DevBuf());
   b->bind(dev_data, static_cast<size_t>(numel) * 4);
   e->finalized = false;
+  e->fold_valid = false;
   return 0;
 }
 
