@@ -8,7 +8,8 @@ import os
 import torch
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libvitocm.so")
+# VITOCM_LIB: another build of the same library (A/B timing of two builds on one box); the default is the in-tree one
+LIB_PATH = os.environ.get("VITOCM_LIB") or os.path.join(PKG_DIR, "libvitocm.so")
 
 c_void_p, c_int, c_int64, c_size_t, c_float, c_char_p = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_char_p
 

@@ -651,6 +651,9 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
       mlp_stamp(tl, smem_tl, 61);
       const bool want_xn = args.lnn_w != nullptr;
       float mean = 0.f, rstd = 0.f;
+      // (Measured and dropped: the statistics pass writing OUT + b2 back into the OUT columns so that the second pass needs no bias
+      // loads / adds -- 1.25 instructions per element fewer on paper, but ptxas answers the extra tcgen05.st and the branch around the
+      // bias loads with 480 instead of 196 bytes of spills: 3 975 against 3 475 us per 1 225-tile launch.  profiles/r02_gpu_call_as_ep2_writeback.log)
       if (want_xn) {
         float mean_w = 0.f, m2_w = 0.f;
 #pragma unroll 1

@@ -1688,9 +1688,12 @@ int vitocm_block_tail(vitocm_engine* e, const void* CTX, int64_t ld_ctx, const v
                       const float* bias2, float* X, const float* next_ln_w, const float* next_ln_b, void* XN, int64_t ld_xn, const void* Wqkv,
                       int64_t ldwqkv, const float* bias_qkv, void* QKV, int64_t ld_qkv, int64_t* stamps, void* stream) {
   if (e == nullptr) return fail(VITOCM_ERR_INVALID, "null engine");
+  // diagnostics (tools/tail_timeline.py): VITOCM_TAIL_ASSUME_FOLDED=1 runs the kernel as the engine's forward does after
+  // vitocm_finalize_weights -- the caller's W1 / bias1 / Wqkv / bias_qkv are taken to carry the LayerNorm affine parameters already
+  static const bool folded = [] { const char* v = getenv("VITOCM_TAIL_ASSUME_FOLDED"); return v != nullptr && atoi(v) != 0; }();
   const int rc = run_block_tail(e, CTX, ld_ctx, Wp, ldwp, bias_p, ln2_w, ln2_b, W1, ldw1, W2, ldw2, M, D, hidden, bias1, bias2, X, next_ln_w,
                                 next_ln_b, e->cfg.ln_eps, XN, ld_xn, Wqkv, ldwqkv, bias_qkv, QKV, ld_qkv, reinterpret_cast<cudaStream_t>(stream), true,
-                                reinterpret_cast<long long*>(stamps));
+                                reinterpret_cast<long long*>(stamps), folded, folded);
   if (rc == 1) return fail(VITOCM_ERR_INVALID, "block tail: no instantiation for D = %d, hidden = %d on this engine (or inconsistent optional arguments)", D, hidden);
   return rc;
 }
