@@ -71,7 +71,11 @@ int vitocm_destroy(vitocm_engine* e);
  * blocks.{i}.{norm1,norm2}.{weight,bias}, blocks.{i}.attn.{qkv,proj}.{weight,bias},
  * blocks.{i}.mlp.{fc1,fc2}.{weight,bias}, norm.{weight,bias}); host_data is fp32, `numel`
  * elements.  vitocm_finalize_weights repacks them into the kernels' layouts (bf16 hi/lo,
- * transposed patch filter) and must be called after the last load and before any forward. */
+ * transposed patch filter) and must be called after the last load and before any forward.  For single 16-bit engines at
+ * embed_dim 128 / 384 it also folds the LayerNorm affine parameters into the Linear behind them (fc1 <- norm2, qkv <- norm1:
+ * W' = W diag(gamma), b' = b + W beta, from the fp32 masters) for the block-tail kernel; vitocm_refresh_weights drops those copies
+ * (the forward then applies gamma / beta itself) until the next vitocm_finalize_weights.  VITOCM_TAIL_FOLD=0 (read at
+ * vitocm_create) disables the folding. */
 int vitocm_load_weight(vitocm_engine* e, const char* name, const float* host_data, int64_t numel);
 int vitocm_finalize_weights(vitocm_engine* e);
 
