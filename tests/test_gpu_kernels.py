@@ -357,6 +357,49 @@ def test_block_tail_with_next_qkv(M, D, Hd, precision):
     assert (got - ref_q).abs().mean().item() <= (4e-4 if precision == "fp16" else 3e-3) * ref_q.abs().max().item()
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_block_tail_statistics_with_large_means(precision):
+    """LayerNorm statistics of the block tail (exact (mean, M2) per 32 values, Chan's combination across steps and warps) on rows
+    whose mean is far from zero: offsets of 0 / 8 / 40 / 300 standard deviations, groups of 32 nearly equal large values and an
+    exactly constant group -- the trailing LayerNorm must match torch's on the kernel's own X.  (Guards any cheaper form of the
+    statistics: a one-sweep sum y^2 - n mean^2 without a fall-back fails here.)"""
+    lib = vob._lib.load_library()
+    eng = make_engine(precision=2 if precision == "fp16" else 0)
+    dt = torch.float16 if precision == "fp16" else torch.bfloat16
+    M, D, Hd = 1100, 384, 1536
+    ctx = _rand((M, D), 140).to(dt)
+    Wp = _rand((D, D), 141, 0.02).to(dt)
+    W1 = _rand((Hd, D), 142, 0.06).to(dt)
+    W2 = _rand((D, Hd), 143, 0.01).to(dt)
+    bp, b1, b2 = _rand((D,), 144, 0.1), _rand((Hd,), 145, 0.2), _rand((D,), 146, 0.1)
+    g2, be2 = _rand((D,), 147) * 0.1 + 1, _rand((D,), 148) * 0.1
+    gn, ben = _rand((D,), 149) * 0.1 + 1, _rand((D,), 150) * 0.1
+    resid = _rand((M, D), 151) * 0.5
+    offs = torch.tensor([0.0, 4.0, 20.0, 150.0, -150.0], device="cuda")
+    resid += offs[torch.arange(M, device="cuda") % 5][:, None]
+    resid[7::11, 32:64] = 500.0 + 0.01 * _rand((len(range(7, M, 11)), 32), 152)    # one group far from the row's other values
+    resid[3::13, 96:128] = -250.0                                                   # ... and an exactly constant one
+    x = resid.clone()
+    xn = torch.full((M, 2 * D), float("nan"), device="cuda", dtype=dt)
+    check(lib.vitocm_block_tail(eng, ptr(ctx), ctx.stride(0), ptr(Wp), Wp.stride(0), ptr(bp), ptr(g2), ptr(be2), ptr(W1), W1.stride(0), ptr(W2),
+                                W2.stride(0), M, D, Hd, ptr(b1), ptr(b2), ptr(x), ptr(gn), ptr(ben), ptr(xn), xn.stride(0), None, 0, None, None, 0,
+                                None, cur_stream()))
+    torch.cuda.synchronize()
+    ref_x, _ = _tail_reference(ctx, Wp, bp, g2, be2, W1, b1, W2, b2, gn, ben, resid, dt)
+    # X: norm2's statistics feed the MLP, so an error there shows as an error of the MLP's contribution
+    scale = (ref_x - resid).abs().max().item()
+    assert (x - ref_x).abs().max().item() <= (3e-3 if precision == "fp16" else 1.5e-2) * scale + 2e-4 * resid.abs().max().item()
+    got = xn[:, :D].float()
+    assert torch.isfinite(got).all()
+    ref_n = torch.nn.functional.layer_norm(x.double(), (D,), gn.double(), ben.double(), 1e-6).float()
+    err = (got - ref_n).abs()
+    assert err.max().item() <= (2e-3 if precision == "fp16" else 1.2e-2) * ref_n.abs().max().item(), err.max().item()
+    # per kind of row, so that a loss of accuracy confined to the offset rows cannot hide behind the others
+    for k in range(5):
+        rows = slice(k, M, 5)
+        assert (err[rows].max() <= (2e-3 if precision == "fp16" else 1.2e-2) * ref_n[rows].abs().max()).item(), k
+
+
 def test_block_tail_matches_separate_kernels(engine):
     """The one-kernel block tail against the kernels it replaces (proj + LayerNorm GEMM, fused MLP, LayerNorm) on the same operands."""
     lib = vob._lib.load_library()

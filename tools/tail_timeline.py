@@ -62,6 +62,7 @@ for c in range(0, 5, 2):
     print(" chunk %2d: fc1 complete=%d gelu done=%d handed=%d | mma: fc1 issued=%d gelu seen=%d" % (c, rel(3 * c), rel(3 * c + 1), rel(3 * c + 2), rel(36 + 2 * c), rel(36 + 2 * c + 1)))
 print("epilogue w0: OUT complete=%d  ep2 stats=%d  steps stored=%d %d %d  stores read=%d  ep2 done=%d" % (rel(61), rel(54), rel(20), rel(21), rel(22), rel(24), rel(62)))
 if with_qkv:
+    print("next norm1 rows: epilogue w0 handed over=%d  MMA thread saw xn_ready=%d" % (rel(19), rel(63)))
     print("QKV chunks, epilogue w0 (its group's first two): " + " | ".join("complete=%d packed=%d staging free=%d stored=%d" % tuple(rel(25 + 4 * k + e) for e in range(4)) for k in range(2)))
     print("QKV chunks, MMA thread issued: " + " ".join(str(rel(46 + c)) for c in range(8)))
 if int(os.environ.get("VITOCM_TAIL_DEBUG", "0")) & 16:

@@ -57,7 +57,7 @@ struct TailArgs {
   // `timeline_item`: [3 c + e], c < 5: epilogue warp 0 (group 0) on chunk c as MlpArgs; [36 + 2 c + e], c < 5: MMA thread as MlpArgs;
   // MMA thread: [60] item start (CTX landed), [56] OUT free, proj issued, [59] ep 1 done (mid_ready seen);
   // epilogue warp 0: [57] proj complete, [58] ep 1 pass 1 done, [55] ep 1 handed over, [61] OUT complete, [54] ep 2 statistics known,
-  // [62] ep 2 done; [25 + 4 k + e]: the group's k-th QKV chunk (k < 2): accumulator complete, packed, staging free, stored; [46 + c]: MMA thread, QKV chunk c issued; [15 + s] ep 1 pass 1 step s done, [18] ep 1 statistics combined, [20 + s] ep 2 pass 2 step s stored, [24] ep 2 stores read
+  // [62] ep 2 done; [25 + 4 k + e]: the group's k-th QKV chunk (k < 2): accumulator complete, packed, staging free, stored; [46 + c]: MMA thread, QKV chunk c issued; [15 + s] ep 1 pass 1 step s done, [18] ep 1 statistics combined, [19] epilogue warp 0 has handed its rows of the next norm1 over, [63] MMA thread: xn_ready seen, [20 + s] ep 2 pass 2 step s stored, [24] ep 2 stores read
   long long* timeline;
   int timeline_item;
   int debug;           // bit 0: no MMAs (barrier traffic only), bit 1: ep 1 neither loads nor awaits the fp32 rows, bit 2: ep 2 issues no TMA stores,
@@ -98,7 +98,10 @@ struct TailCfg {
   static_assert(4 * REGS_CTRL + EW * REGS_EPI <= (4 + EW) * 96, "block tail: setmaxnreg budgets exceed the launch allocation");
 };
 
-// exact (mean, M2) of 32 values
+// exact (mean, M2) of 32 values.  (Measured and dropped: sum y and sum y^2 in one sweep, M2 = sum y^2 - 32 mean^2 with a fall-back to
+// this two-pass form when the subtraction cancels -- two instructions per element instead of three, all tests green, and no change
+// of the launch time at all (3 467 / 3 454 / 3 485 against 3 440 / 3 482 / 3 476 us per 1 225-tile launch): the statistics passes wait
+// for their TMEM loads, not for issue slots.  profiles/r02_gpu_call_au_fast_stats.log)
 __device__ __forceinline__ void tail_stats32(const float (&y)[32], float& mean, float& m2) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -431,6 +434,7 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
           if (NQ > 0) {   // the next block's QKV projection on the rows ep 2 leaves in smem_a
             ptx::mbar_wait_cluster(xn_ready, t & 1, 28);
             ptx::tc_fence_after();
+            mlp_stamp(tl, smem_tl, 63);   // the next norm1's rows seen in both CTAs' smem_a
             for (int c = 0; c < NQ; ++c) issue_chunk(c + 100, c + 1 == NQ, (c & 1) ? 0u : static_cast<uint32_t>(MLP_H_COL), c == 0 ? 1 : (c == 1 ? 0 : 2));
             // both accumulators have been read out before the next item's proj (OUT columns) and first hidden chunk are issued
             for (int u = g1 - 1; u >= 0 && u >= g1 - 2; --u) ptx::mbar_wait(h_tmem_empty + 8 * (u & 1), (u >> 1) & 1, 27);
@@ -769,6 +773,7 @@ block_tail_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a /*CTX*/, co
         ptx::fence_proxy_async_smem();   // the normalised rows in smem_a, for the tensor core
         __syncwarp();
         if (lane == 0) { if (strong_arrive) ptx::mbar_arrive_remote(ptx::mapa(xn_ready, 0)); else ptx::mbar_arrive_remote_cta(ptx::mapa(xn_ready, 0)); }
+        mlp_stamp(tl, smem_tl, 19);   // this warp's share of the next norm1's rows handed over
         const int nq0 = n0 + NC;
         for (int c = (nq0 + grp) & 1; c < NQ; c += 2) {
           const int n = nq0 + c;          // (n & 1) == grp
