@@ -118,6 +118,11 @@ attn_fwd_quad_kernel(const __grid_constant__ CUtensorMap tmap_q /*box 64 x 128*/
     ptx::tmem_alloc(tmem_ptr_smem, 512);
     ptx::tmem_relinquish();
   }
+  if (warp == 4 * AQ_PIPES + 2 && lane == 0 && args.stagger_clk > 0) {   // start stagger (AttnArgs::stagger_clk)
+    const long long wait_clk = static_cast<long long>(args.stagger_clk) * blockIdx.x / gridDim.x;
+    const long long t0 = clock64();
+    while (clock64() - t0 < wait_clk) {}
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();

@@ -64,6 +64,8 @@ struct AttnArgs {
                         // tiles are computed by attn_fwd_quad_kernel (attention_quad_sm100.cuh)
   int timeline_item;    // diagnostics: which of a CTA's work items (0, 1, ...) the stamps are taken on
   long long* timeline;  // diagnostics (vitocm_attention_timeline) or nullptr: clock64 stamps of CTAs (0,0,0) and (1,0,0)
+  int stagger_clk;      // attn_fwd_quad_kernel: CTA k starts k / gridDim.x x stagger_clk SM clocks late (VITOCM_ATTN_STAGGER) -- every CTA
+                        // does the same work in the same time, so without it all of them load K / V and drain O in the same instants
 };
 
 // timeline layout: [cta 0..1][role 0 = softmax warp 0, 1 = MMA thread][kv block j < 16][event < 8]

@@ -611,7 +611,20 @@ int run_block_tail(const vitocm_engine* e, const void* CTX, long long ld_ctx, co
   a.fold2 = fold2 ? 1 : 0; a.foldn = (foldn && with_qkv) ? 1 : 0;
   a.timeline = timeline;
   { static const int dbg = [] { const char* v = getenv("VITOCM_TAIL_DEBUG"); return v ? atoi(v) : 0; }(); a.debug = dbg; }
-  { static const int stg = [] { const char* v = getenv("VITOCM_TAIL_STAGGER"); return v ? atoi(v) : 0; }(); a.stagger_clk = stg; }
+  {
+    // Start stagger of the CTA pairs (TailArgs::stagger_clk): about one item's duration spread over the pairs, so that they sit at
+    // evenly distributed phases of an item instead of all reaching the item boundary together -- 3 494 -> 3 290 us per 1 225-tile
+    // launch, 538 -> 498 us per 175 tiles (profiles/r02_gpu_call_ba_tail_stagger.log).  The last pair starts one item late, so short
+    // launches (fewer than four items per pair) run without it.  VITOCM_TAIL_STAGGER=<clocks> overrides (0: none).
+    static const int stg = [] { const char* v = getenv("VITOCM_TAIL_STAGGER"); return v ? atoi(v) : -1; }();
+    if (stg >= 0) {
+      a.stagger_clk = stg;
+    } else {
+      const long long items = (static_cast<long long>(M) + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+      const double work = static_cast<double>(D) * (D + 2.0 * Hd + (with_qkv ? 3.0 * D : 0.0));   // per row, relative to ViT-S with QKV: ~105 k clk per item
+      a.stagger_clk = items >= 4LL * (e->num_sms / 2) ? static_cast<int>(105000.0 * work / (384.0 * (384.0 + 3072.0 + 1152.0))) : 0;
+    }
+  }
   { static const int tli = [] { const char* v = getenv("VITOCM_MLP_TL_ITEM"); return v ? atoi(v) : 1; }(); a.timeline_item = tli; }
   if (D == 384) return e->f16 ? launch_block_tail<6, true>(ta, twp, tw1, tw2, tx, txn, twqkv, tqkv, a, e->num_sms, st) : launch_block_tail<6, false>(ta, twp, tw1, tw2, tx, txn, twqkv, tqkv, a, e->num_sms, st);
   return e->f16 ? launch_block_tail<2, true>(ta, twp, tw1, tw2, tx, txn, twqkv, tqkv, a, e->num_sms, st) : launch_block_tail<2, false>(ta, twp, tw1, tw2, tx, txn, twqkv, tqkv, a, e->num_sms, st);
@@ -659,6 +672,7 @@ int run_attention(const vitocm_engine* e, const void* qkv, long long ld, int B, 
     static const int quad_pack = [] { const char* v = getenv("VITOCM_ATTN_QUAD_PACK"); return v ? atoi(v) : 2; }();   // 2 or 4
     aq.group_items = 0;
     { static const int hoist = [] { const char* v = getenv("VITOCM_ATTN_HOIST"); return v ? atoi(v) : 1; }(); aq.ctrl_hoist = hoist; }
+    { static const int stg = [] { const char* v = getenv("VITOCM_ATTN_STAGGER"); return v ? atoi(v) : 0; }(); aq.stagger_clk = stg; }
     aq.n_items = aq.n_full_items;
     if (tails_here) {   // groups of `pack` pairs: their full tiles, then the one tile their tails share (aq_decode)
       aq.pack = (quad_pack == 4 && a.pack == 4) ? 4 : 2;
