@@ -614,15 +614,20 @@ int run_block_tail(const vitocm_engine* e, const void* CTX, long long ld_ctx, co
   {
     // Start stagger of the CTA pairs (TailArgs::stagger_clk): about one item's duration spread over the pairs, so that they sit at
     // evenly distributed phases of an item instead of all reaching the item boundary together -- 3 494 -> 3 290 us per 1 225-tile
-    // launch, 538 -> 498 us per 175 tiles (profiles/r02_gpu_call_ba_tail_stagger.log).  The last pair starts one item late, so short
-    // launches (fewer than four items per pair) run without it.  VITOCM_TAIL_STAGGER=<clocks> overrides (0: none).
+    // launch, 538 -> 498 us per 175 tiles (profiles/r02_gpu_call_ba_tail_stagger.log).  What it costs: pair k starts k / pairs of an
+    // item late; with items = n pairs + r the first r pairs carry n + 1 items, so the launch ends (r - 1) / pairs of an item later
+    // (a whole item when r = 0).  The stagger is used while that stays below 4 % of the launch (the gain is 6 - 10 %); shorter
+    // launches run without it.  VITOCM_TAIL_STAGGER=<clocks> overrides (0: none).
     static const int stg = [] { const char* v = getenv("VITOCM_TAIL_STAGGER"); return v ? atoi(v) : -1; }();
     if (stg >= 0) {
       a.stagger_clk = stg;
     } else {
       const long long items = (static_cast<long long>(M) + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+      const long long pairs = e->num_sms / 2;
+      const long long r = items % pairs, rounds = (items + pairs - 1) / pairs;
+      const double late = (r > 0 ? static_cast<double>(r - 1) : static_cast<double>(pairs - 1)) / static_cast<double>(pairs);   // in items
       const double work = static_cast<double>(D) * (D + 2.0 * Hd + (with_qkv ? 3.0 * D : 0.0));   // per row, relative to ViT-S with QKV: ~105 k clk per item
-      a.stagger_clk = items >= 4LL * (e->num_sms / 2) ? static_cast<int>(105000.0 * work / (384.0 * (384.0 + 3072.0 + 1152.0))) : 0;
+      a.stagger_clk = (items > pairs && late <= 0.04 * static_cast<double>(rounds)) ? static_cast<int>(105000.0 * work / (384.0 * (384.0 + 3072.0 + 1152.0))) : 0;
     }
   }
   { static const int tli = [] { const char* v = getenv("VITOCM_MLP_TL_ITEM"); return v ? atoi(v) : 1; }(); a.timeline_item = tli; }
