@@ -38,6 +38,22 @@ def test_no_compute_without_gpu_fails_loudly():
         vob.utils.threshold(np.zeros((8, 8), np.uint8), np.zeros((8, 8), np.float32), save=False)
 
 
+def test_library_path_override_fails_loudly_when_absent(tmp_path):
+    """VITOCM_LIB names another build of libvitocm.so (A/B timing of two builds on one box).  A path that does not exist must raise,
+    never fall back to the in-tree library or to a CPU path; the in-tree path given explicitly loads and exports the same symbols."""
+    import subprocess
+    import sys
+    code = ("import vitocm_b200 as v\n"
+            "try:\n    v._lib.load_library(); print('LOADED', v._lib.LIB_PATH)\n"
+            "except v._lib.VitocmError as e:\n    print('RAISED', e)\n")
+    env = dict(os.environ, VITOCM_LIB=str(tmp_path / "no_such_libvitocm.so"))
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300).stdout
+    assert out.startswith("RAISED") and "no_such_libvitocm.so" in out, out
+    env["VITOCM_LIB"] = vob._lib.LIB_PATH
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300).stdout
+    assert out.startswith("LOADED"), out
+
+
 def test_state_dict_keys_and_param_counts_match_reference():
     m = vob.vit_small(patch_size=8, num_classes=0)
     sd_ref = VO.init_state_dict(VO.ViTConfig(**VO.VIT_SMALL))
